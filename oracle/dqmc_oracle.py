@@ -1,0 +1,839 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU oracle, never imported by the product path.
+
+NumPy restatement of the reference's DQMC sweep hot path (crstnbr/detqmc).  Every routine cites
+the reference file:line it follows.  Only tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline leg may import this module, and only as the checker.
+
+Parity status: PINNED.  tests/test_oracle_vs_reference.py checks this restatement against the
+reference itself compiled into oracle/_ref/libdetqmc_ref.so (RNG stream, field construction,
+checkerboard multiplies, G and singular values after setup, per-slice acceptance, fields and step
+sizes after sweeps, global-shift decisions, Hubbard path), and against the committed fixtures in
+tests/golden/ that were generated from that library (tools/make_golden.py).  The replica-exchange
+ladder walk (detqmcpt.h:1014-1080) cannot be run from the reference here (no MPI): that one
+function is a restatement with parity UNPINNED beyond the exchange probability itself
+(detsdwopdim.cpp:5251-5264), which is pinned.
+
+Layouts follow Armadillo (column-major):
+  phi[k, dim, site]   == arma::Cube(N, OPDIM, m+1) memory   (detsdwopdim.h:455-461)
+  G[row, col]         row/col = site + N*bandspin, bandspin XUP=0,YDOWN=1,XDOWN=2,YUP=3
+"""
+
+import numpy as np
+import scipy.linalg as sla
+
+from dsfmt_oracle import RngOracle
+
+XBAND, YBAND = 0, 1
+BAND_OF_BANDSPIN = (XBAND, YBAND, XBAND, YBAND)   # XUP, YDOWN, XDOWN, YUP  (detsdwopdim.h:265-273)
+UP, DOWN = +1, -1                                   # SweepDirection (detmodel.h:480)
+
+
+def udv_decompose(mat):
+    """udv.h:68-90: M = U diag(d) V_t^dagger via LAPACK gesvd ('std')."""
+    U, d, Vh = sla.svd(mat, lapack_driver="gesvd")
+    return U, d, Vh.conj().T
+
+
+class UdV:
+    __slots__ = ("U", "d", "V_t")
+
+    def __init__(self, U, d, V_t):
+        self.U, self.d, self.V_t = U, d, V_t
+
+    @staticmethod
+    def eye(sz, dtype):
+        return UdV(np.eye(sz, dtype=dtype), np.ones(sz), np.eye(sz, dtype=dtype))
+
+    @staticmethod
+    def of(mat):
+        return UdV(*udv_decompose(mat))
+
+    def copy(self):
+        return UdV(self.U.copy(), self.d.copy(), self.V_t.copy())
+
+
+def green_from_udv(l, r):
+    """detmodel.h:768-818.  G = [1 + (U_r d_r V_r^+)(U_l d_l V_l^+)]^-1; returns (G, sv of G^-1)."""
+    VU = r.V_t.conj().T @ l.U
+    UtVt = r.U.conj().T @ l.V_t
+    Ut, sv, Vt = udv_decompose(UtVt + (r.d[:, None] * VU) * l.d[None, :])
+    Vp = l.V_t @ Vt
+    Up = r.U @ Ut
+    return (Vp * (1.0 / sv)[None, :]) @ Up.conj().T, sv
+
+
+def green_from_eye_and_udv(r):
+    """detmodel.h:822-860."""
+    Ut, sv, Vt = udv_decompose(r.U.conj().T @ r.V_t + np.diag(r.d))
+    Vp = r.V_t @ Vt
+    Up = r.U @ Ut
+    return (Vp * (1.0 / sv)[None, :]) @ Up.conj().T, sv
+
+
+class RunningAverage:
+    """RunningAverage.h:20-80."""
+
+    def __init__(self, sample_size):
+        self.sample_size = sample_size
+        self.samples_added = 0
+        self.values = []
+        self.avg = 0.0
+
+    def add(self, v):
+        if self.samples_added < self.sample_size:
+            self.values.append(v)
+            self.avg += v / self.sample_size
+        else:
+            self.avg -= self.values.pop(0) / self.sample_size
+            self.values.append(v)
+            self.avg += v / self.sample_size
+        self.samples_added += 1
+
+
+class SweepSkeleton:
+    """Restatement of DetModelGC's stabilised sweep (detmodel.h:678-713, 953-1163, 1261-1440).
+
+    Sub-classes provide left/right B-multiplies (and inverses) with the skeleton signature
+    (gc, A, k2, k1), update_in_slice(k) and optionally global_move()."""
+
+    def init_skeleton(self, sz, m, s, n_gc, dtype):
+        self.sz, self.m, self.s = sz, m, s
+        self.n = int(np.ceil(m / s))
+        self.n_gc = n_gc
+        self.dtype = dtype
+        self.green = [np.zeros((sz, sz), dtype=dtype) for _ in range(n_gc)]
+        self.green_inv_sv = [np.zeros(sz) for _ in range(n_gc)]
+        self.storage = [[None] * (self.n + 1) for _ in range(n_gc)]
+        self.current_timeslice = 0
+        self.last_sweep_dir = UP
+        self.wrap_vs_advance = []      # (dir, slice, max|G_wrapped - G_advanced|) log
+
+    # detmodel.h:678-713
+    def setup_udv_storage_and_calculate_green(self):
+        n, s, m = self.n, self.s, self.m
+        eye = np.eye(self.sz, dtype=self.dtype)
+        for gc in range(self.n_gc):
+            st = [None] * (n + 1)
+            st[0] = UdV.eye(self.sz, self.dtype)
+            st[1] = UdV.of(self.left_multiply_bmat(gc, eye, s, 0))
+            for l in range(1, n):
+                k_l = s * l
+                k_lp1 = s * (l + 1) if l < n - 1 else m
+                BU = self.left_multiply_bmat(gc, st[l].U, k_lp1, k_l)
+                nu = UdV.of(BU * st[l].d[None, :])
+                nu.V_t = st[l].V_t @ nu.V_t
+                st[l + 1] = nu
+            self.storage[gc] = st
+        for gc in range(self.n_gc):
+            self.green[gc], self.green_inv_sv[gc] = green_from_eye_and_udv(self.storage[gc][n])
+        self.current_timeslice = m
+        self.last_sweep_dir = UP
+
+    # detmodel.h:605-674 (used by consistency checks only)
+    def green_for_timeslice(self, timeslice, gc=0):
+        n, s, m = self.n, self.s, self.m
+        if timeslice == m:
+            raise ValueError("use setup_udv_storage_and_calculate_green for timeslice == m")
+        eye = np.eye(self.sz, dtype=self.dtype)
+        lk = timeslice // s
+        k_lkp1 = s * (lk + 1) if lk < n - 1 else m
+        cur = UdV.of(self.left_multiply_bmat(gc, eye, k_lkp1, timeslice))
+        for l in range(lk + 1, n):
+            k_l = s * l
+            k_lp1 = s * (l + 1) if l < n - 1 else m
+            nu = UdV.of(self.left_multiply_bmat(gc, cur.U, k_lp1, k_l) * cur.d[None, :])
+            nu.V_t = cur.V_t @ nu.V_t
+            cur = nu
+        target = lk - 1 if lk * s == timeslice else lk
+        for l in range(0, target + 1):
+            k_l = s * l
+            k_lp1 = s * (l + 1) if l < lk else timeslice
+            nu = UdV.of(self.left_multiply_bmat(gc, cur.U, k_lp1, k_l) * cur.d[None, :])
+            nu.V_t = cur.V_t @ nu.V_t
+            cur = nu
+        return green_from_eye_and_udv(cur)
+
+    # detmodel.h:953-1017
+    def advance_down_green(self, l, gc):
+        n, s, m = self.n, self.s, self.m
+        st = self.storage[gc]
+        k_l = s * l if l < n else m
+        k_lm1 = s * (l - 1)
+        if l < n:
+            L = UdV.of(st[l].d[:, None] * self.right_multiply_bmat(gc, st[l].V_t.conj().T, k_l, k_lm1))
+            L.U = st[l].U @ L.U
+        else:
+            L = UdV.of(self.right_multiply_bmat(gc, np.eye(self.sz, dtype=self.dtype), k_l, k_lm1))
+        g_wrapped = self.green[gc]
+        if l - 1 > 0:
+            self.green[gc], self.green_inv_sv[gc] = green_from_udv(L, st[l - 1])
+        else:
+            self.green[gc], self.green_inv_sv[gc] = green_from_eye_and_udv(L)
+        self.wrap_vs_advance.append((DOWN, k_lm1, float(np.abs(g_wrapped - self.green[gc]).max())))
+        st[l - 1] = L
+        self.current_timeslice = s * (l - 1)
+
+    # detmodel.h:1106-1163
+    def advance_up_green(self, l, gc):
+        n, s, m = self.n, self.s, self.m
+        st = self.storage[gc]
+        k_l = s * l
+        k_lp1 = s * (l + 1) if l < n - 1 else m
+        assert self.current_timeslice == k_lp1
+        g_wrapped = self.green[gc]
+        T = UdV.of(self.left_multiply_bmat(gc, st[l].U, k_lp1, k_l) * st[l].d[None, :])
+        T.V_t = st[l].V_t @ T.V_t
+        if k_lp1 != m:
+            self.green[gc], self.green_inv_sv[gc] = green_from_udv(st[l + 1], T)
+        else:
+            self.green[gc], self.green_inv_sv[gc] = green_from_eye_and_udv(T)
+        st[l + 1] = T
+        self.wrap_vs_advance.append((UP, k_lp1, float(np.abs(g_wrapped - self.green[gc]).max())))
+        self.current_timeslice = k_lp1
+
+    # detmodel.h:1064-1095
+    def wrap_down_green(self, k, gc):
+        assert self.current_timeslice == k
+        self.green[gc] = self.left_multiply_bmat_inv(
+            gc, self.right_multiply_bmat(gc, self.green[gc], k, k - 1), k, k - 1)
+        self.current_timeslice = k - 1
+
+    # detmodel.h:1234-1259
+    def wrap_up_green(self, k, gc):
+        assert self.current_timeslice == k
+        self.green[gc] = self.left_multiply_bmat(
+            gc, self.right_multiply_bmat_inv(gc, self.green[gc], k + 1, k), k + 1, k)
+        self.current_timeslice = k + 1
+
+    # detmodel.h:1328-1399
+    def sweep_down(self, update):
+        n, s, m = self.n, self.s, self.m
+        for k in range(m, (n - 1) * s, -1):
+            update(k)
+            for gc in range(self.n_gc):
+                self.wrap_down_green(k, gc) if gc == self.n_gc - 1 else self._wrap_down_keep(k, gc)
+        for l in range(n - 1, 0, -1):
+            for gc in range(self.n_gc):
+                self.advance_down_green(l + 1, gc)
+            for k in range(l * s, (l - 1) * s, -1):
+                update(k)
+                for gc in range(self.n_gc):
+                    self.wrap_down_green(k, gc) if gc == self.n_gc - 1 else self._wrap_down_keep(k, gc)
+        for gc in range(self.n_gc):
+            self.advance_down_green(1, gc)
+
+    def _wrap_down_keep(self, k, gc):
+        # multi-component models wrap every gc at the same slice: do not advance the slice
+        # counter until the last component has been wrapped
+        self.wrap_down_green(k, gc)
+        self.current_timeslice = k
+
+    def _wrap_up_keep(self, k, gc):
+        self.wrap_up_green(k, gc)
+        self.current_timeslice = k
+
+    # detmodel.h:1261-1325
+    def sweep_up(self, update):
+        n, s, m = self.n, self.s, self.m
+        for gc in range(self.n_gc):
+            self.storage[gc][0] = UdV.eye(self.sz, self.dtype)
+        for l in range(0, n - 1):
+            for k in range(l * s + 1, (l + 1) * s + 1):
+                for gc in range(self.n_gc):
+                    self.wrap_up_green(k - 1, gc) if gc == self.n_gc - 1 else self._wrap_up_keep(k - 1, gc)
+                update(k)
+            for gc in range(self.n_gc):
+                self.advance_up_green(l, gc)
+        for k in range((n - 1) * s + 1, m + 1):
+            for gc in range(self.n_gc):
+                self.wrap_up_green(k - 1, gc) if gc == self.n_gc - 1 else self._wrap_up_keep(k - 1, gc)
+            update(k)
+        for gc in range(self.n_gc):
+            self.advance_up_green(n - 1, gc)
+
+    # detmodel.h:1401-1478
+    def sweep_skeleton(self, update):
+        if self.last_sweep_dir == UP:
+            self.global_move()
+            self.sweep_down(update)
+            self.last_sweep_dir = DOWN
+        else:
+            self.sweep_up(update)
+            self.last_sweep_dir = UP
+
+    def global_move(self):
+        pass
+
+
+class SdwParams:
+    """Subset of ModelParamsDetSDW (detsdwparams.h:30-120) that the hot path reads; defaults follow
+    maindetqmcsdwopdim.cpp:93-135 where the reference has any."""
+
+    def __init__(self, **kw):
+        self.opdim = 2
+        self.L = 4
+        self.m = 20
+        self.s = 10
+        self.dtau = 0.1
+        self.r = -1.0
+        self.c = 3.0
+        self.u = 1.0
+        self.lam = 1.0
+        self.txhor, self.txver, self.tyhor, self.tyver = -1.0, -0.5, 0.5, 1.0
+        self.cdwU = 0.0
+        self.mu = -0.5
+        self.accRatio = 0.5
+        self.weakZflux = True
+        self.bc = 0                 # 0 pbc, 1 apbc-x, 2 apbc-y, 3 apbc-xy
+        self.updateMethod = 2       # delayed
+        self.delaySteps = 16
+        self.globalShift = True
+        self.globalUpdateInterval = 10
+        self.repeatUpdateInSlice = 1
+        self.seed = 1020304050
+        self.rngIndex = 1
+        for k, v in kw.items():
+            if not hasattr(self, k):
+                raise KeyError(k)
+            setattr(self, k, v)
+        # updateTemperatureParameters, detmodelparams.h:68-122
+        while self.m <= self.s:
+            self.s -= 1
+        self.N = self.L * self.L
+        self.beta = self.m * self.dtau
+
+
+class SdwOracle(SweepSkeleton):
+    """DetSDW<CB_ASSAAD_BERG, OPDIM> restated (cdwU == 0 only, box proposals, delayed updates)."""
+
+    def __init__(self, pars, rng=None, phi=None):
+        p = self.p = pars
+        assert p.cdwU == 0.0, "oracle restates the cdwU == 0 path only"
+        self.rng = rng if rng is not None else RngOracle(p.seed, p.rngIndex)
+        self.N, self.L = p.N, p.L
+        self.msf = 4 if p.opdim == 3 else 2                 # MatrixSizeFactor, detsdwopdim.h
+        self.init_skeleton(self.msf * p.N, p.m, p.s, 1, np.complex128)
+        self.phi = np.zeros((p.m + 1, p.opdim, p.N))
+        self.cosh_term = np.zeros((p.m + 1, p.N))
+        self.sinh_term = np.zeros((p.m + 1, p.N))
+        self.phi_delta = 0.5                                 # AdjustmentData::InitialPhiDelta
+        self.ra_box = RunningAverage(100)
+        self.last_acc_ratio = 0.0
+        self.performed_sweeps = 0
+        self.accepted_global_shifts = 0
+        self.attempted_global_shifts = 0
+        self.decisions = None                                # optional per-proposal log
+        self._setup_lattice()
+        if phi is None:
+            self._setup_random_field()
+        else:
+            self.phi[...] = phi
+            self.update_cosh_sinh_terms()
+        self._setup_checkerboard()
+        self.setup_udv_storage_and_calculate_green()
+
+    # ------------------------------------------------------------------ lattice, neighbortable.h
+    def _setup_lattice(self):
+        L, N = self.L, self.N
+        site = np.arange(N)
+        x, y = site % L, site // L
+        self.neigh = np.stack([y * L + (x + 1) % L, y * L + (x - 1) % L,
+                               ((y + 1) % L) * L + x, ((y - 1) % L) * L + x])   # +x,-x,+y,-y
+
+    # ------------------------------------------------------------------ detsdwopdim.cpp:1098-1113
+    def _setup_random_field(self):
+        p = self.p
+        for k in range(1, p.m + 1):
+            for site in range(p.N):
+                for dim in range(p.opdim):
+                    self.phi[k, dim, site] = self.rng.rand_range(-1.0, 1.0)
+                self.rng.rand01()                      # cdwl draw, consumed even when cdwU == 0
+        self.update_cosh_sinh_terms()
+
+    # detsdwopdim.cpp:1131-1136
+    def cosh_sinh_term(self, phivec):
+        nrm = np.sqrt(np.sum(np.asarray(phivec) ** 2, axis=0))
+        a = self.p.lam * self.p.dtau * nrm
+        return np.cosh(a), np.sinh(a) / nrm
+
+    def update_cosh_sinh_terms(self):
+        for k in range(1, self.p.m + 1):
+            self.cosh_term[k], self.sinh_term[k] = self.cosh_sinh_term(self.phi[k])
+
+    # ------------------------------------------------------------------ checkerboard
+    def _plaquette_matrix(self, band, i1, i2, prefactor):
+        """4x4 exp(prefactor * h_plaquette) for sites (i, j=i+x, k=i+y, l=k+x);
+        detsdwopdim.cpp:1597-1684 (flux) and 1786-1826 (no flux: cosh/sinh closed form)."""
+        p, L = self.p, self.L
+        hh = (p.txhor, p.tyhor)[band]
+        hv = (p.txver, p.tyver)[band]
+        if p.bc in (1, 3) and i1 == L - 1:
+            hh = -hh
+        if p.bc in (2, 3) and i2 == L - 1:
+            hv = -hv
+        if not p.weakZflux:
+            # prefactor = sign*dtau(/2): ch = cosh(-dtau t), sh = sign * sinh(-dtau t) = sinh(-prefactor t)
+            chh, shh = np.cosh(prefactor * hh), np.sinh(-prefactor * hh)
+            chv, shv = np.cosh(prefactor * hv), np.sinh(-prefactor * hv)
+            return np.array([[chh * chv, chv * shh, chh * shv, shh * shv],
+                             [chv * shh, chh * chv, shh * shv, chh * shv],
+                             [chh * shv, shh * shv, chh * chv, chv * shh],
+                             [shh * shv, chh * shv, chv * shh, chh * chv]], dtype=np.complex128)
+        zmag = 1.0 / p.N                              # zmag[XUP] = zmag[YDOWN] = +1/N (cpp:218-222)
+        j1 = (i1 + 1) % L
+        k2 = (i2 + 1) % L
+        ph_ij = np.exp(-2j * np.pi * zmag * i2)
+        ph_kl = np.exp(-2j * np.pi * zmag * k2)
+        ph_ik = ph_jl = 1.0
+        if i2 == L - 1:
+            ph_ik = np.exp(2j * np.pi * zmag * L * i1)
+            ph_jl = np.exp(2j * np.pi * zmag * L * j1)
+        h = np.zeros((4, 4), dtype=np.complex128)
+        h[0, 1] = ph_ij * hh
+        h[0, 2] = ph_ik * hv
+        h[1, 3] = ph_jl * hv
+        h[2, 3] = ph_kl * hh
+        h = -(h + h.conj().T)
+        w, v = np.linalg.eigh(h)
+        return (v * np.exp(prefactor * w)[None, :]) @ v.conj().T
+
+    def _subgroup_matrix(self, band, subgroup, prefactor):
+        """Dense N x N product of the disjoint plaquette exponentials of one subgroup."""
+        L, N = self.L, self.N
+        E = np.zeros((N, N), dtype=np.complex128)
+        for i1 in range(subgroup, L, 2):
+            for i2 in range(subgroup, L, 2):
+                i = i2 * L + i1
+                j = self.neigh[0, i]
+                k = self.neigh[2, i]
+                l = self.neigh[0, k]
+                idx = np.array([i, j, k, l])
+                E[np.ix_(idx, idx)] = self._plaquette_matrix(band, i1, i2, prefactor)
+        return E
+
+    def _setup_checkerboard(self):
+        """cb[band][sign] = E1(half) E0(full) E1(half) approximating exp(sign*dtau*K_band) without the
+        chemical potential (detsdwopdim.cpp:1836-1869, 1945-1979)."""
+        dtau = self.p.dtau
+        self.cb = {}
+        for band in (XBAND, YBAND):
+            for sign in (-1, +1):
+                E1h = self._subgroup_matrix(band, 1, sign * 0.5 * dtau)
+                E0 = self._subgroup_matrix(band, 0, sign * dtau)
+                self.cb[(band, sign)] = E1h @ E0 @ E1h
+
+    # ------------------------------------------------------------------ potential exponential
+    def ev_matrices(self, sign, phi_k, cosh_k, sinh_k):
+        """Per-site MSF x MSF blocks of exp(sign*dtau*V) (evMatrix, detsdwopdim.cpp:3188-3229,
+        cdwU == 0).  Returns array [msf, msf, nsites]."""
+        msf = self.msf
+        phi_k = np.asarray(phi_k, dtype=float).reshape(self.p.opdim, -1)
+        ns = phi_k.shape[1]
+        c = np.broadcast_to(np.asarray(cosh_k, dtype=float), (ns,))
+        x = np.broadcast_to(np.asarray(sinh_k, dtype=float), (ns,))
+        ev = np.zeros((msf, msf, ns), dtype=np.complex128)
+        p0 = phi_k[0]
+        p1 = phi_k[1] if self.p.opdim > 1 else np.zeros(ns)
+        ev[0, 0] = c
+        ev[1, 1] = c
+        ev[0, 1] = sign * x * (p0 - 1j * p1)
+        ev[1, 0] = sign * x * (p0 + 1j * p1)
+        if self.p.opdim == 3:
+            p2 = phi_k[2]
+            ev[2, 2] = c
+            ev[3, 3] = c
+            ev[0, 3] = sign * p2 * x
+            ev[3, 0] = sign * p2 * x
+            ev[2, 1] = -sign * p2 * x
+            ev[1, 2] = -sign * p2 * x
+            ev[2, 3] = sign * x * (p0 + 1j * p1)
+            ev[3, 2] = sign * x * (p0 - 1j * p1)
+        return ev
+
+    def _apply_v_left(self, ev, A):
+        N, msf = self.N, self.msf
+        out = np.zeros_like(A)
+        for r in range(msf):
+            for c in range(msf):
+                out[r * N:(r + 1) * N, :] += ev[r, c][:, None] * A[c * N:(c + 1) * N, :]
+        return out
+
+    def _apply_v_right(self, A, ev):
+        N, msf = self.N, self.msf
+        out = np.zeros_like(A)
+        for r in range(msf):
+            for c in range(msf):
+                out[:, c * N:(c + 1) * N] += A[:, r * N:(r + 1) * N] * ev[r, c][None, :]
+        return out
+
+    def _apply_k_left(self, sign, A):
+        N = self.N
+        mu = self.p.mu
+        out = np.empty_like(A)
+        for bs in range(self.msf):
+            f = np.exp(-sign * self.p.dtau * mu)       # sign=-1 (B): e^{+dtau mu}; sign=+1: e^{-dtau mu}
+            out[bs * N:(bs + 1) * N, :] = f * (self.cb[(BAND_OF_BANDSPIN[bs], sign)] @ A[bs * N:(bs + 1) * N, :])
+        return out
+
+    def _apply_k_right(self, A, sign):
+        N = self.N
+        mu = self.p.mu
+        out = np.empty_like(A)
+        for bs in range(self.msf):
+            f = np.exp(-sign * self.p.dtau * mu)
+            out[:, bs * N:(bs + 1) * N] = f * (A[:, bs * N:(bs + 1) * N] @ self.cb[(BAND_OF_BANDSPIN[bs], sign)])
+        return out
+
+    # B_k = e^{-dtau V_k} e^{-dtau K};  detsdwopdim.cpp:1994-2070, 2093-2167, 2188-2303, 2326-2402
+    def left_multiply_bk(self, A, k):
+        ev = self.ev_matrices(-1, self.phi[k], self.cosh_term[k], self.sinh_term[k])
+        return self._apply_v_left(ev, self._apply_k_left(-1, A))
+
+    def left_multiply_bk_inv(self, A, k):
+        ev = self.ev_matrices(+1, self.phi[k], self.cosh_term[k], self.sinh_term[k])
+        return self._apply_k_left(+1, self._apply_v_left(ev, A))
+
+    def right_multiply_bk(self, A, k):
+        ev = self.ev_matrices(-1, self.phi[k], self.cosh_term[k], self.sinh_term[k])
+        return self._apply_k_right(self._apply_v_right(A, ev), -1)
+
+    def right_multiply_bk_inv(self, A, k):
+        ev = self.ev_matrices(+1, self.phi[k], self.cosh_term[k], self.sinh_term[k])
+        return self._apply_v_right(self._apply_k_right(A, +1), ev)
+
+    # chains, detsdwopdim.cpp:2074-2090, 2170-2186, 2305-2324, 2404-2420
+    def left_multiply_bmat(self, gc, A, k2, k1):
+        for k in range(k1 + 1, k2 + 1):
+            A = self.left_multiply_bk(A, k)
+        return A
+
+    def left_multiply_bmat_inv(self, gc, A, k2, k1):
+        for k in range(k2, k1, -1):
+            A = self.left_multiply_bk_inv(A, k)
+        return A
+
+    def right_multiply_bmat(self, gc, A, k2, k1):
+        for k in range(k2, k1, -1):
+            A = self.right_multiply_bk(A, k)
+        return A
+
+    def right_multiply_bmat_inv(self, gc, A, k2, k1):
+        for k in range(k1 + 1, k2 + 1):
+            A = self.right_multiply_bk_inv(A, k)
+        return A
+
+    # ------------------------------------------------------------------ bosonic action
+    # detsdwopdim.cpp:4185-4239
+    def delta_s_phi(self, site, k, newphi):
+        p = self.p
+        old = self.phi[k, :, site]
+        diff = newphi - old
+        old_sq = old @ old
+        new_sq = newphi @ newphi
+        sq_diff = new_sq - old_sq
+        pow4_diff = new_sq * new_sq - old_sq * old_sq
+        k_earlier = k - 1 if k > 1 else p.m
+        k_later = k + 1 if k < p.m else 1
+        time_neigh = self.phi[k_later, :, site] + self.phi[k_earlier, :, site]
+        space_neigh = np.zeros(p.opdim)
+        for d in range(4):
+            space_neigh = space_neigh + self.phi[k, :, self.neigh[d, site]]
+        z = 4
+        d1 = (1.0 / (p.c * p.c * p.dtau)) * (sq_diff - time_neigh @ diff)
+        d2 = 0.5 * p.dtau * (z * sq_diff - 2.0 * (space_neigh @ diff))
+        d3 = p.dtau * (0.5 * p.r * sq_diff + 0.25 * p.u * pow4_diff)
+        return d1 + d2 + d3
+
+    # detsdwopdim.cpp:4242-4299
+    def phi_action(self):
+        p = self.p
+        ph = self.phi[1:]                                       # [m, dim, N]
+        earlier = np.roll(ph, 1, axis=0)
+        td = (ph - earlier) / p.dtau
+        action = (p.dtau / (2.0 * p.c * p.c)) * np.sum(td * td)
+        xd = ph - ph[:, :, self.neigh[0]]
+        yd = ph - ph[:, :, self.neigh[2]]
+        action += 0.5 * p.dtau * (np.sum(xd * xd) + np.sum(yd * yd))
+        sq = np.sum(ph * ph, axis=1)
+        action += 0.5 * p.dtau * p.r * np.sum(sq)
+        action += 0.25 * p.dtau * p.u * np.sum(sq * sq)
+        return float(action)
+
+    # detsdwopdim.cpp:5204-5216
+    def exchange_action(self):
+        return 0.5 * self.p.dtau * float(np.sum(self.phi[1:] ** 2))
+
+    # ------------------------------------------------------------------ local updates
+    # get_delta_forsite, detsdwopdim.cpp:3177-3289
+    def delta_forsite(self, newphi, k, site):
+        ev_old = self.ev_matrices(+1, self.phi[k, :, site], self.cosh_term[k, site],
+                                  self.sinh_term[k, site])[:, :, 0]
+        c_new, s_new = self.cosh_sinh_term(newphi)
+        emv_new = self.ev_matrices(-1, newphi, c_new, s_new)[:, :, 0]
+        return emv_new @ ev_old - np.eye(self.msf)
+
+    # updateInSlice_delayed with proposeNewPhiBox; detsdwopdim.cpp:3021-3175, 3920-3931
+    def update_in_slice(self, k):
+        p, N, msf = self.p, self.N, self.msf
+        g = self.green[0]
+        rows_of = lambda site: site + N * np.arange(msf)
+        accepted = 0
+        site = 0
+        while site < N:
+            delay_now = min(p.delaySteps, N - site)
+            X = np.zeros((msf * N, msf * delay_now), dtype=np.complex128)
+            Y = np.zeros((msf * delay_now, msf * N), dtype=np.complex128)
+            j = 0
+            while j < delay_now and site < N:
+                newphi = self.phi[k, :, site].copy()
+                for dim in range(p.opdim):
+                    newphi[dim] += self.rng.rand_range(-self.phi_delta, +self.phi_delta)
+                prob_sphi = np.exp(-self.delta_s_phi(site, k, newphi))
+                delta = self.delta_forsite(newphi, k, site)
+                idx = rows_of(site)
+                Rj = g[idx, :] + X[idx, :msf * j] @ Y[:msf * j, :]
+                Sj = Rj[:, idx]
+                Mj = np.eye(msf) - Sj @ delta + delta
+                det = np.linalg.det(Mj)
+                prob_fermion = det.real if p.opdim == 3 else abs(det) ** 2
+                prob = prob_sphi * prob_fermion
+                u = None
+                if prob > 1.0:
+                    accept = True
+                else:
+                    u = self.rng.rand01()
+                    accept = u < prob
+                if self.decisions is not None:
+                    self.decisions.append((k, site, float(prob), u, bool(accept)))
+                if accept:
+                    accepted += 1
+                    self.phi[k, :, site] = newphi
+                    self.cosh_term[k, site], self.sinh_term[k, site] = self.cosh_sinh_term(newphi)
+                    Cj = g[:, idx] + X[:, :msf * j] @ Y[:msf * j, idx]
+                    Rj = Rj.copy()
+                    Rj[np.arange(msf), idx] -= 1.0
+                    X[:, msf * j:msf * (j + 1)] = Cj @ delta
+                    Y[msf * j:msf * (j + 1), :] = np.linalg.inv(Mj) @ Rj
+                    j += 1
+                site += 1
+            if j > 0:
+                g += X[:, :msf * j] @ Y[:msf * j, :]
+        self.last_acc_ratio = accepted / float(N)
+        return self.last_acc_ratio
+
+    # updateInSliceThermalization, detsdwopdim.cpp:3293-3375 (box proposals only)
+    def update_in_slice_thermalization(self, k):
+        self.update_in_slice(k)
+        self.ra_box.add(self.last_acc_ratio)
+        if self.ra_box.samples_added % 100 == 0:
+            if self.ra_box.avg < self.p.accRatio:
+                self.phi_delta *= 0.95
+            elif self.ra_box.avg > self.p.accRatio:
+                self.phi_delta *= 1.05
+
+    # ------------------------------------------------------------------ global shift move
+    # globalMove, attemptGlobalShiftMove; detsdwopdim.cpp:3460-3485, 3564-3645, 3755-3763
+    def global_move(self):
+        p = self.p
+        if self.performed_sweeps % p.globalUpdateInterval == 0 and p.globalShift:
+            self.attempt_global_shift_move()
+
+    def attempt_global_shift_move(self):
+        p = self.p
+        old_action = self.phi_action()
+        assert self.current_timeslice == p.m
+        backup = (self.phi.copy(), self.cosh_term.copy(), self.sinh_term.copy(), self.green[0],
+                  self.green_inv_sv[0], self.storage[0])
+        old_sv = self.green_inv_sv[0]
+        for dim in range(p.opdim):
+            r = self.rng.rand_range(-self.phi_delta, +self.phi_delta)
+            self.phi[:, dim, :] += r                       # all slices, including the unused k = 0
+        self.update_cosh_sinh_terms()
+        self.setup_udv_storage_and_calculate_green()
+        new_action = self.phi_action()
+        prob_scalar = np.exp(-(new_action - old_action))
+        log_prob = float(np.sum(np.log(self.green_inv_sv[0]) - np.log(old_sv)))
+        prob_fermion = np.exp(log_prob)
+        if p.opdim < 3:
+            prob_fermion = prob_fermion ** 2
+        prob = prob_scalar * prob_fermion
+        self.last_global_shift = dict(prob=float(prob), log_det_ratio=log_prob,
+                                      dS=float(new_action - old_action))
+        self.attempted_global_shifts += 1
+        if prob >= 1.0 or self.rng.rand01() < prob:
+            self.accepted_global_shifts += 1
+            self.last_global_shift["accepted"] = True
+        else:
+            (self.phi, self.cosh_term, self.sinh_term, self.green[0], self.green_inv_sv[0],
+             self.storage[0]) = backup
+            self.last_global_shift["accepted"] = False
+
+    # ------------------------------------------------------------------ sweeps, cpp:4422-4502
+    def sweep(self):
+        self.sweep_skeleton(self.update_in_slice)
+        self.performed_sweeps += 1
+
+    def sweep_thermalization(self):
+        self.sweep_skeleton(self.update_in_slice_thermalization)
+        self.performed_sweeps += 1
+
+
+# ---------------------------------------------------------------------------------------------
+class HubbardParams:
+    def __init__(self, **kw):
+        self.L = 4
+        self.m = 40
+        self.s = 10
+        self.dtau = 0.1
+        self.t = 1.0
+        self.U = 4.0
+        self.mu = 0.0
+        self.checkerboard = False
+        self.seed = 1020304050
+        self.rngIndex = 1
+        for k, v in kw.items():
+            if not hasattr(self, k):
+                raise KeyError(k)
+            setattr(self, k, v)
+        while self.m <= self.s:
+            self.s -= 1
+        self.N = self.L * self.L
+
+
+class HubbardOracle(SweepSkeleton):
+    """DetHubbard restated (dethubbard.cpp:46-171, 741-765, 823-933; dethubbard.h:281-337)."""
+
+    def __init__(self, pars, rng=None, aux=None):
+        p = self.p = pars
+        self.rng = rng if rng is not None else RngOracle(p.seed, p.rngIndex)
+        self.N, self.L = p.N, p.L
+        self.init_skeleton(p.N, p.m, p.s, 2, np.float64)
+        self.alpha = np.arccosh(np.exp(p.dtau * p.U * 0.5))
+        self.aux = np.zeros((p.m + 1, p.N), dtype=np.int32)
+        if aux is None:
+            for k in range(1, p.m + 1):
+                for site in range(p.N):
+                    self.aux[k, site] = +1 if self.rng.rand01() <= 0.5 else -1
+        else:
+            self.aux[...] = aux
+        self._setup_proptmat()
+        self.setup_udv_storage_and_calculate_green()
+
+    def _setup_proptmat(self):
+        p, L, N = self.p, self.L, self.N
+        site = np.arange(N)
+        x, y = site % L, site // L
+        neigh = np.stack([y * L + (x + 1) % L, y * L + (x - 1) % L,
+                          ((y + 1) % L) * L + x, ((y - 1) % L) * L + x])
+        if not p.checkerboard:
+            tmat = -p.mu * np.eye(N)
+            for s_ in range(N):
+                for d in range(4):
+                    tmat[neigh[d, s_], s_] -= p.t
+            w, v = np.linalg.eigh(tmat)
+            self.proptmat = (v * np.exp(-p.dtau * w)[None, :]) @ v.T       # detmodel.cpp:21-29
+        else:
+            # dethubbard.cpp:768-821
+            kxa = np.zeros((N, N)); kxb = np.zeros((N, N)); kya = np.zeros((N, N)); kyb = np.zeros((N, N))
+            for yy in range(L):
+                for xx in range(0, L, 2):
+                    a = yy * L + xx
+                    na = neigh[0, a]
+                    kxa[a, na] = kxa[na, a] = 1.0
+                    nb = neigh[0, na]
+                    kxb[na, nb] = kxb[nb, na] = 1.0
+            for xx in range(L):
+                for yy in range(0, L, 2):
+                    a = yy * L + xx
+                    na = neigh[2, a]
+                    kya[a, na] = kya[na, a] = 1.0
+                    nb = neigh[2, na]
+                    kyb[na, nb] = kyb[nb, na] = 1.0
+            ch, sh = np.cosh(p.dtau * p.t), np.sinh(p.dtau * p.t)
+            self.proptmat = (ch ** 4 * np.eye(N) + ch ** 3 * sh * (kxa + kxb + kya + kyb)
+                             + ch ** 2 * sh ** 2 * (kxa @ kxb + kxa @ kya + kxb @ kya + kxa @ kyb
+                                                   + kxb @ kyb + kya @ kyb)
+                             + ch * sh ** 3 * (kxa @ kxb @ kya + kxa @ kxb @ kyb + kxa @ kya @ kyb
+                                               + kxb @ kya @ kyb)
+                             + sh ** 4 * kxa @ kxb @ kya @ kyb)
+
+    # dethubbard.cpp:823-851
+    def compute_bmat(self, gc, k2, k1):
+        sign = +1.0 if gc == 0 else -1.0
+        if k2 == k1:
+            return np.eye(self.N)
+        single = lambda k: np.exp(sign * self.alpha * self.aux[k].astype(float))[:, None] * self.proptmat
+        B = single(k2)
+        for k in range(k2 - 1, k1, -1):
+            B = B @ single(k)
+        return B
+
+    def left_multiply_bmat(self, gc, A, k2, k1):
+        return self.compute_bmat(gc, k2, k1) @ A
+
+    def right_multiply_bmat(self, gc, A, k2, k1):
+        return A @ self.compute_bmat(gc, k2, k1)
+
+    def left_multiply_bmat_inv(self, gc, A, k2, k1):
+        return np.linalg.inv(self.compute_bmat(gc, k2, k1)) @ A
+
+    def right_multiply_bmat_inv(self, gc, A, k2, k1):
+        return A @ np.linalg.inv(self.compute_bmat(gc, k2, k1))
+
+    # dethubbard.cpp:141-171, 892-933
+    def update_in_slice(self, k):
+        N = self.N
+        gup, gdn = self.green
+        for _ in range(N):
+            site = self.rng.rand_int(0, N - 1)
+            a = float(self.aux[k, site])
+            e_up = np.exp(-2.0 * self.alpha * a)
+            e_dn = np.exp(+2.0 * self.alpha * a)
+            ratio = (1.0 + (e_up - 1.0) * (1.0 - gup[site, site])) * \
+                    (1.0 + (e_dn - 1.0) * (1.0 - gdn[site, site]))
+            if ratio > 1.0 or self.rng.rand01() < ratio:
+                for g, delta in ((gup, e_up - 1.0), (gdn, e_dn - 1.0)):
+                    one_minus = np.eye(N) - g
+                    factor = delta / (1.0 + delta * one_minus[site, site])
+                    g -= np.outer(g[:, site], factor * one_minus[site, :])
+                self.aux[k, site] *= -1
+
+    def sweep(self):
+        self.sweep_skeleton(self.update_in_slice)
+
+    sweep_thermalization = sweep
+
+
+# ---------------------------------------------------------------------------------------------
+def exchange_probability(par1, action1, par2, action2):
+    """detsdwopdim.cpp:5251-5264."""
+    delta = (par1 - par2) * (action2 - action1)
+    return 1.0 if delta <= 0.0 else float(np.exp(-delta))
+
+
+def replica_exchange_walk(control_values, current_par_process, current_process_par, actions, rand01):
+    """Serial ladder walk of DetQMCPT::replicaExchangeStep (detqmcpt.h:1031-1079), rank-0 part only.
+
+    control_values[cpi]        -- the ladder (parspt.controlParameterValues)
+    current_par_process[cpi]   -- which replica ("process") currently holds parameter index cpi
+    current_process_par[pi]    -- which parameter index replica pi currently holds
+    actions[pi]                -- get_exchange_action_contribution() of replica pi
+    rand01                     -- callable drawing from replica 0's RNG stream
+    Returns (new par_process, new process_par, list of (cpi1, prob, accepted)); the caller swaps the
+    control data (step sizes / statistics) of the two replicas on every accepted entry."""
+    par_process = list(current_par_process)
+    process_par = list(current_process_par)
+    log = []
+    P = len(control_values)
+    for cpi1 in range(P - 1):
+        cpi2 = cpi1 + 1
+        p1, p2 = par_process[cpi1], par_process[cpi2]
+        prob = exchange_probability(control_values[cpi1], actions[p1], control_values[cpi2], actions[p2])
+        accepted = prob >= 1 or rand01() <= prob
+        if accepted:
+            process_par[p1] = cpi2
+            process_par[p2] = cpi1
+            par_process[cpi1] = p2
+            par_process[cpi2] = p1
+        log.append((cpi1, prob, bool(accepted)))
+    return par_process, process_par, log

@@ -1,0 +1,145 @@
+"""CPU tests: the NumPy oracle (oracle/dqmc_oracle.py) against the golden vectors that
+tools/make_golden.py produced from the unmodified reference.  This is what pins the oracle."""
+import numpy as np
+import pytest
+
+from dqmc_oracle import (SdwOracle, HubbardOracle, exchange_probability, replica_exchange_walk)
+from dsfmt_oracle import RngOracle
+from helpers import load_golden, sdw_params_of, hubbard_params_of, maxabs
+
+SDW_CASES = ["sdw_o2_flux_L4", "sdw_o2_noflux_apbcxy_L4", "sdw_o3_L4", "sdw_o1_apbcx_L4",
+             "sdw_o2_flux_L4_delay3_s7", "sdw_o2_flux_L6"]
+
+
+def test_rng_streams():
+    g = load_golden("rng_streams")
+    for key in g.files:
+        seed, idx = key[1:].split("_i")
+        r = RngOracle(int(seed), int(idx))
+        mine = np.array([r.rand01() for _ in range(len(g[key]))])
+        assert np.array_equal(mine, g[key]), key      # bit-exact: integer recursion
+
+
+def test_rng_seed_scramble_kat():
+    # seed 1020304050, idx 1 -> 37767 (rngwrapper.cpp:43)
+    assert RngOracle(1020304050, 1).my_seed == 37767
+
+
+@pytest.mark.parametrize("name", SDW_CASES)
+def test_sdw_setup_and_bmult(name):
+    g = load_golden(name)
+    o = SdwOracle(sdw_params_of(g))
+    assert maxabs(o.phi, g["phi0"]) == 0.0
+    assert maxabs(o.cosh_term[1:], g["cosh0"][1:]) < 1e-14
+    assert maxabs(o.sinh_term[1:], g["sinh0"][1:]) < 1e-14
+    assert maxabs(o.green[0], g["green0"]) < 1e-12
+    assert abs(np.log(o.green_inv_sv[0]).sum() - np.log(g["sv0"]).sum()) < 1e-10
+    A = g["A"]
+    k2, k1 = [int(v) for v in g["chain"]]
+    fns = [o.left_multiply_bmat, o.right_multiply_bmat, o.left_multiply_bmat_inv, o.right_multiply_bmat_inv]
+    for op, f in enumerate(fns):
+        ref1 = g["bmult_op%d_single" % op]
+        refc = g["bmult_op%d_chain" % op]
+        assert maxabs(f(0, A, 3, 2), ref1) < 1e-12 * np.abs(ref1).max()
+        assert maxabs(f(0, A, k2, k1), refc) < 1e-12 * np.abs(refc).max()
+    assert abs(o.phi_action() - float(g["phiAction0"])) < 1e-10
+    assert abs(o.exchange_action() - float(g["exchangeAction0"])) < 1e-11
+    gs, _ = o.green_for_timeslice(3)
+    assert maxabs(gs, g["green_slice_3"]) < 1e-11
+
+
+@pytest.mark.parametrize("name", SDW_CASES)
+def test_sdw_sweeps(name):
+    g = load_golden(name)
+    o = SdwOracle(sdw_params_of(g))
+    n = int(g["n_sweeps"])
+    for sw in range(n):
+        o.sweep_thermalization()
+        assert o.last_acc_ratio == g["lastAccRatio"][sw], (name, sw)
+        assert o.accepted_global_shifts == g["acceptedGlobalShifts"][sw]
+        assert abs(o.phi_delta - g["phiDelta"][sw]) < 1e-14
+        key = "phi_after_%d" % (sw + 1)
+        if key in g.files:
+            assert maxabs(o.phi[1:], g[key][1:]) < 1e-12
+            assert maxabs(o.green[0], g["green_after_%d" % (sw + 1)]) < 1e-10
+    assert maxabs(o.phi[1:], g["phi_final"][1:]) < 1e-12
+    nxt = np.array([o.rng.rand01() for _ in range(8)])
+    assert np.array_equal(nxt, g["rng_next"])          # identical RNG consumption
+
+
+def test_sdw_trajectory_100_sweeps():
+    """North-star requirement: identical accept/reject trajectory over the first 100 sweeps."""
+    g = load_golden("sdw_o2_flux_L4_traj100")
+    o = SdwOracle(sdw_params_of(g))
+    for sw in range(100):
+        o.sweep_thermalization()
+        assert o.last_acc_ratio == g["lastAccRatio"][sw], sw
+        assert o.accepted_global_shifts == g["acceptedGlobalShifts"][sw], sw
+    assert abs(o.phi_delta - g["phiDelta"][-1]) < 1e-13
+    assert maxabs(o.phi[1:], g["phi_final"][1:]) < 1e-11
+    assert maxabs(o.green[0], g["green_final"]) < 1e-10
+    nxt = np.array([o.rng.rand01() for _ in range(8)])
+    assert np.array_equal(nxt, g["rng_next"])
+
+
+def test_green_from_udv_kat():
+    from dqmc_oracle import UdV, green_from_udv
+    g = load_golden("sdw_o2_flux_L4")
+    l = UdV(g["udv2_U"], g["udv2_d"], g["udv2_V"])
+    r = UdV(g["udv1_U"], g["udv1_d"], g["udv1_V"])
+    G, sv = green_from_udv(l, r)
+    assert maxabs(G, g["green_from_udv_l2_r1"]) < 1e-11
+    assert abs(np.log(sv).sum() - np.log(g["sv_from_udv_l2_r1"]).sum()) < 1e-9
+
+
+@pytest.mark.parametrize("name", ["hubbard_L4_U4_b4", "hubbard_L4_cb"])
+def test_hubbard(name):
+    g = load_golden(name)
+    p = hubbard_params_of(g)
+    o = HubbardOracle(p)
+    assert np.array_equal(o.aux[1:], g["aux0"])
+    assert maxabs(o.proptmat, g["proptmat"]) < 1e-13
+    for gc in (0, 1):
+        assert maxabs(o.green[gc], g["green0_%d" % gc]) < 1e-10
+        assert maxabs(o.compute_bmat(gc, 9, 4), g["bmat_%d_9_4" % gc]) < 1e-12
+    n = int(g["n_sweeps"])
+    for sw in range(n):
+        o.sweep()
+        key = "aux_after_%d" % (sw + 1)
+        if key in g.files:
+            assert np.array_equal(o.aux[1:], g[key])
+            for gc in (0, 1):
+                assert maxabs(o.green[gc], g["green_after_%d_%d" % (sw + 1, gc)]) < 1e-9
+    nxt = np.array([o.rng.rand01() for _ in range(8)])
+    assert np.array_equal(nxt, g["rng_next"])
+    if p.mu == 0.0 and not p.checkerboard:
+        # half filling: <n> = 1 for every auxiliary-field configuration
+        occ = 2.0 - (np.trace(o.green[0]) + np.trace(o.green[1])) / p.N
+        assert abs(occ - 1.0) < 1e-10
+
+
+def test_exchange_probability_golden():
+    rows = load_golden("exchange_probability")["rows"]
+    for p1, a1, p2, a2, ref in rows:
+        assert abs(exchange_probability(p1, a1, p2, a2) - ref) <= 1e-15 * max(1.0, ref)
+
+
+def test_replica_exchange_walk_properties():
+    """Parity of the ladder walk is unpinned (no MPI here); check its invariants instead."""
+    gen = np.random.default_rng(3)
+    P = 8
+    ladder = np.linspace(-1.9, 0.4, P)
+    par_proc = list(range(P))
+    proc_par = list(range(P))
+    rng = RngOracle(1, 1)
+    for _ in range(50):
+        actions = gen.uniform(10, 20, P)
+        par_proc, proc_par, log = replica_exchange_walk(ladder, par_proc, proc_par, actions, rng.rand01)
+        assert sorted(par_proc) == list(range(P)) and sorted(proc_par) == list(range(P))
+        for cpi in range(P):
+            assert proc_par[par_proc[cpi]] == cpi
+        assert len(log) == P - 1
+    # equal actions -> delta = 0 -> always accepted, no RNG draw
+    draws0 = rng.draws
+    replica_exchange_walk(ladder, par_proc, proc_par, np.ones(P), rng.rand01)
+    assert rng.draws == draws0

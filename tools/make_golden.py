@@ -1,0 +1,131 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz from the UNMODIFIED reference compiled into oracle/_ref
+(oracle/Makefile).  Run in the CPU container where /root/reference exists:
+
+    make -C oracle && python tools/make_golden.py
+
+The fixtures are small known-answer vectors for every row of SURVEY.md section 8(a) that the
+reference can produce deterministically from a seed: RNG stream, initial fields, checkerboard
+B-multiplies, G / singular values after setup, G from two UdVs, fields / step sizes / acceptance
+after thermalisation sweeps (incl. a 100-sweep trajectory), exchange probability, and the
+DetHubbard path.  TEST INFRASTRUCTURE ONLY.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import ref_bindings as rb                                   # noqa: E402
+from dqmc_oracle import SdwParams, HubbardParams            # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+os.makedirs(OUT, exist_ok=True)
+
+
+def pars_json(p):
+    return json.dumps({k: v for k, v in vars(p).items()})
+
+
+def rng_fixture():
+    data = {}
+    for seed, idx in ((1020304050, 1), (1020304050, 2), (5, 7), (4242, 64)):
+        data["s%d_i%d" % (seed, idx)] = rb.RefRng(seed, idx).draw(2000)
+    np.savez_compressed(os.path.join(OUT, "rng_streams.npz"), **data)
+
+
+def sdw_fixture(name, sweeps, kw, chain=(7, 4)):
+    p = SdwParams(**kw)
+    r = rb.RefSdw(p)
+    d = {"params": pars_json(p)}
+    d["phi0"] = r.phi()
+    d["green0"] = r.green()
+    d["sv0"] = r.sv()
+    c, s = r.tables()
+    d["cosh0"], d["sinh0"] = c, s
+    gen = np.random.default_rng(12345)
+    A = gen.standard_normal((r.D, r.D)) + 1j * gen.standard_normal((r.D, r.D))
+    d["A"] = A
+    for op in range(4):
+        d["bmult_op%d_single" % op] = r.bmult(op, A, 3, 2)
+        d["bmult_op%d_chain" % op] = r.bmult(op, A, chain[0], chain[1])
+    d["chain"] = np.array(chain)
+    # G = [1 + M_r M_l]^-1 from two stored UdVs (numerical known-answer for greenFromUdV)
+    for l in (1, 2):
+        U, dd, V = r.udv(l)
+        d["udv%d_U" % l], d["udv%d_d" % l], d["udv%d_V" % l] = U, dd, V
+    g12, sv12 = r.green_from_storage(2, 1)
+    d["green_from_udv_l2_r1"], d["sv_from_udv_l2_r1"] = g12, sv12
+    d["green_slice_3"] = r.green_for_timeslice(3)
+    d["green_slice_%d" % p.s] = r.green_for_timeslice(p.s)
+    sc = r.scalars()
+    d["phiAction0"], d["exchangeAction0"] = sc["phiAction"], sc["exchangeAction"]
+    acc, gsa, pdel = [], [], []
+    for sw in range(sweeps):
+        r.sweep(therm=True)
+        sc = r.scalars()
+        acc.append(sc["lastAccRatio"])
+        gsa.append(sc["acceptedGlobalShifts"])
+        pdel.append(sc["phiDelta"])
+        if sw + 1 in (1, 2, 6):
+            d["phi_after_%d" % (sw + 1)] = r.phi()
+            d["green_after_%d" % (sw + 1)] = r.green()
+    d["phi_final"], d["green_final"] = r.phi(), r.green()
+    d["lastAccRatio"] = np.array(acc)
+    d["acceptedGlobalShifts"] = np.array(gsa)
+    d["phiDelta"] = np.array(pdel)
+    d["n_sweeps"] = sweeps
+    sc = r.scalars()
+    d["phiAction_final"], d["exchangeAction_final"] = sc["phiAction"], sc["exchangeAction"]
+    d["rng_next"] = r.rng_draw(8)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
+    print(name, "done; acc", acc[-1], "global shifts", gsa[-1], "phiDelta", pdel[-1])
+
+
+def hubbard_fixture(name, sweeps, kw):
+    p = HubbardParams(**kw)
+    r = rb.RefHubbard(p)
+    d = {"params": pars_json(p)}
+    d["aux0"] = r.aux()[1:]
+    d["proptmat"] = r.proptmat()
+    for gc in (0, 1):
+        d["green0_%d" % gc] = r.green(gc)
+        d["sv0_%d" % gc] = r.sv(gc)
+        d["bmat_%d_9_4" % gc] = r.bmat(gc, 9, 4)
+    for sw in range(sweeps):
+        r.sweep(False)
+        if sw + 1 in (1, 2, sweeps):
+            d["aux_after_%d" % (sw + 1)] = r.aux()[1:]
+            for gc in (0, 1):
+                d["green_after_%d_%d" % (sw + 1, gc)] = r.green(gc)
+    d["n_sweeps"] = sweeps
+    d["rng_next"] = r.rng_draw(8)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
+    print(name, "done")
+
+
+def exchange_fixture():
+    gen = np.random.default_rng(7)
+    rows = []
+    for _ in range(64):
+        p1, p2 = gen.uniform(-2, 1, 2)
+        a1, a2 = gen.uniform(0, 50, 2)
+        rows.append((p1, a1, p2, a2, rb.exchange_probability(p1, a1, p2, a2)))
+    np.savez_compressed(os.path.join(OUT, "exchange_probability.npz"), rows=np.array(rows))
+
+
+if __name__ == "__main__":
+    assert rb.available(), "build oracle/_ref first: make -C oracle"
+    rng_fixture()
+    exchange_fixture()
+    sdw_fixture("sdw_o2_flux_L4", 6, dict())
+    sdw_fixture("sdw_o2_noflux_apbcxy_L4", 6, dict(weakZflux=False, bc=3))
+    sdw_fixture("sdw_o3_L4", 6, dict(opdim=3, weakZflux=False))
+    sdw_fixture("sdw_o1_apbcx_L4", 6, dict(opdim=1, weakZflux=False, bc=1))
+    sdw_fixture("sdw_o2_flux_L4_delay3_s7", 4, dict(delaySteps=3, s=7, m=24, rngIndex=3, globalUpdateInterval=2))
+    sdw_fixture("sdw_o2_flux_L4_traj100", 100, dict(rngIndex=2))
+    sdw_fixture("sdw_o2_flux_L6", 2, dict(L=6, m=30, rngIndex=5), chain=(20, 10))
+    hubbard_fixture("hubbard_L4_U4_b4", 6, dict())                      # BASELINE config C1
+    hubbard_fixture("hubbard_L4_cb", 4, dict(checkerboard=True, U=6.0, mu=0.3, m=24, s=5))

@@ -1,0 +1,1092 @@
+// The batch context and the C ABI (include/dqmc_gpu.h): device-resident state of R replicas, the
+// stabilised sweep skeleton of DetModelGC (detmodel.h:678-713, 953-1163, 1261-1440) sequenced as
+// batched kernel launches on one CUDA stream, UDT storage management, the global shift move and
+// the replica-exchange helpers.  There is NO CPU fallback: every numerical step is a kernel launch
+// and dqmc_create fails when no CUDA device is usable.
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "dqmc_internal.h"
+
+using namespace dqmc;
+
+namespace {
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__);                        \
+            return DQMC_ERR_CUDA;                                                                  \
+        }                                                                                          \
+    } while (0)
+
+#define CKL(call)                                                                                  \
+    do {                                                                                           \
+        ctx->launches += 1;                                                                        \
+        CK(call);                                                                                  \
+    } while (0)
+
+#define RET(call)                                                                                  \
+    do {                                                                                           \
+        int r__ = (call);                                                                          \
+        if (r__ != DQMC_OK) return r__;                                                            \
+    } while (0)
+
+template <class T>
+cudaError_t dmalloc(T** p, size_t n) {
+    return cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T));
+}
+
+inline size_t DD(const dqmc_ctx* c) { return size_t(c->D) * c->D; }
+inline size_t phi_stride(const dqmc_ctx* c) { return size_t(c->m + 1) * c->opdim * c->N; }
+inline size_t tab_stride(const dqmc_ctx* c) { return size_t(c->m + 1) * c->N; }
+inline cplx* stQ(dqmc_ctx* c, int l) { return c->stQ + size_t(l) * DD(c); }
+inline cplx* stT(dqmc_ctx* c, int l) { return c->stT + size_t(l) * DD(c); }
+inline double* stD(dqmc_ctx* c, int l) { return c->stD + size_t(l) * c->D; }
+inline long long st_stride(const dqmc_ctx* c) { return (long long)(c->n + 1) * (long long)DD(c); }
+inline long long std_stride(const dqmc_ctx* c) { return (long long)(c->n + 1) * c->D; }
+
+// A "view" of one UDT for a batch: base pointers + strides (stride 0 = shared identity)
+struct UdtView {
+    const cplx* Q; long long sQ;
+    const double* d; long long sd;
+    const cplx* T; long long sT;
+};
+
+struct OpSpec { int rows, k_then_v, sign_idx, transposed, ascending; };
+const OpSpec kOps[5] = {
+    {0, 1, 0, 0, 1},   // LEFT       B A
+    {1, 0, 0, 1, 0},   // RIGHT      A B
+    {0, 0, 1, 0, 0},   // LEFT_INV   B^-1 A
+    {1, 1, 1, 1, 1},   // RIGHT_INV  A B^-1
+    {0, 0, 0, 0, 0},   // LEFT_ADJ   B^+ A
+};
+
+// ---- batched building blocks; `off` selects the first replica, `batch` how many ---------------
+
+int sdw_bmult(dqmc_ctx* ctx, int op, cplx* A, long long strideA, int k2, int k1, const double* colscale,
+              long long strideScale, int off, int batch) {
+    if (k2 <= k1) return DQMC_OK;
+    const OpSpec& o = kOps[op];
+    CbLaunch a;
+    a.A = A;
+    a.strideA = strideA;
+    a.phi = ctx->phi + size_t(off) * phi_stride(ctx);
+    a.coshT = ctx->coshT + size_t(off) * tab_stride(ctx);
+    a.sinhT = ctx->sinhT + size_t(off) * tab_stride(ctx);
+    a.stridePhi = (long long)phi_stride(ctx);
+    a.strideTab = (long long)tab_stride(ctx);
+    a.cbtab = ctx->cbtab;
+    a.kcount = k2 - k1;
+    if (o.ascending) { a.kfirst = k1 + 1; a.kstep = +1; }
+    else { a.kfirst = k2; a.kstep = -1; }
+    a.rows = o.rows;
+    a.k_then_v = o.k_then_v;
+    a.sign_idx = o.sign_idx;
+    a.transposed = o.transposed;
+    a.colscale = colscale;
+    a.strideScale = strideScale;
+    a.batch = batch;
+    CKL(cb_launch(ctx->geom, a, ctx->stream));
+    return DQMC_OK;
+}
+
+int gemm(dqmc_ctx* ctx, int ta, int tb, const cplx* A, long long sA, const cplx* B, long long sB, cplx* C,
+         long long sC, const double* rows, long long sRow, const double* cols, long long sCol,
+         const double* ks, long long sK, double beta, int batch) {
+    GemmArgs g;
+    g.M = g.N = g.K = ctx->D;
+    g.transa = ta; g.transb = tb;
+    g.A = A; g.lda = ctx->D; g.strideA = sA;
+    g.B = B; g.ldb = ctx->D; g.strideB = sB;
+    g.C = C; g.ldc = ctx->D; g.strideC = sC;
+    g.rowscale = rows; g.strideRow = sRow;
+    g.colscale = cols; g.strideCol = sCol;
+    g.kscale = ks; g.strideK = sK;
+    g.beta = beta;
+    g.batch = batch;
+    CKL(gemm_launch(g, ctx->stream));
+    return DQMC_OK;
+}
+
+// M (in `work`, destroyed) -> Q, d, T' with M = Q diag(d) T'
+int udt_decompose(dqmc_ctx* ctx, cplx* work, long long sW, cplx* Qout, long long sQ, double* dout, long long sd,
+                  cplx* Tout, long long sT, int off, int batch) {
+    const int D = ctx->D;
+    cplx* tau = ctx->tau + size_t(off) * D;
+    int* perm = ctx->perm + size_t(off) * D;
+    double* cn = ctx->colnorm + size_t(off) * D;
+    if (sW != (long long)DD(ctx) || sQ != sW) {
+        // the QR kernels use one stride for A and Q
+        ctx->err = "udt_decompose: work and Q must be contiguous batches";
+        return DQMC_ERR_STATE;
+    }
+    CKL(qrcp_factor_launch(work, D, sW, tau, perm, cn, batch, ctx->stream));
+    CKL(qr_form_q_launch(work, tau, Qout, D, sW, batch, ctx->stream));
+    // d and T' go to contiguous scratch first (extract kernel uses the A stride), then are copied
+    // with the requested strides
+    cplx* Ttmp = ctx->W[3] + size_t(off) * DD(ctx);
+    double* dtmp = ctx->dtmp + size_t(off) * D;
+    CKL(qr_extract_dt_launch(work, perm, dtmp, Ttmp, D, sW, batch, ctx->stream));
+    CK(cudaMemcpy2DAsync(dout, size_t(sd) * sizeof(double), dtmp, size_t(D) * sizeof(double),
+                         size_t(D) * sizeof(double), batch, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (Tout) {
+        CK(cudaMemcpy2DAsync(Tout, size_t(sT) * sizeof(cplx), Ttmp, DD(ctx) * sizeof(cplx), DD(ctx) * sizeof(cplx),
+                             batch, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    return DQMC_OK;
+}
+
+// one stabilised chain step: (Q, d, T) -> (Q', d', T' T) with M = (op(B(k2,k1)) Q) diag(d).
+// op = LEFT for right chains B(tau,0) = Q d T, LEFT_ADJ for left chains B(beta,tau) = T^+ d Q^+.
+// in == nullptr means the identity UDT.  Output strides are element strides between replicas.
+int chain_step(dqmc_ctx* ctx, int op, const UdtView* in, int k2, int k1, cplx* Qout, long long sQo, double* dout,
+               long long sdo, cplx* Tout, long long sTo, int off, int batch) {
+    const size_t dd = DD(ctx);
+    cplx* work = ctx->W[0] + size_t(off) * dd;
+    cplx* qtmp = ctx->W[1] + size_t(off) * dd;
+    if (in) {
+        CK(cudaMemcpy2DAsync(work, dd * sizeof(cplx), in->Q, size_t(in->sQ) * sizeof(cplx), dd * sizeof(cplx), batch,
+                             cudaMemcpyDeviceToDevice, ctx->stream));
+        RET(sdw_bmult(ctx, op, work, (long long)dd, k2, k1, in->d, in->sd, off, batch));
+    } else {
+        CKL(launch_set_identity(work, ctx->D, (long long)dd, batch, ctx->stream));
+        RET(sdw_bmult(ctx, op, work, (long long)dd, k2, k1, nullptr, 0, off, batch));
+    }
+    cplx* tprime = ctx->W[2] + size_t(off) * dd;
+    RET(udt_decompose(ctx, work, (long long)dd, qtmp, (long long)dd, dout, sdo, in ? tprime : Tout,
+                      in ? (long long)dd : sTo, off, batch));
+    CK(cudaMemcpy2DAsync(Qout, size_t(sQo) * sizeof(cplx), qtmp, dd * sizeof(cplx), dd * sizeof(cplx), batch,
+                         cudaMemcpyDeviceToDevice, ctx->stream));
+    if (in) {
+        // T_new = T' T_old; computed into scratch first because Tout may alias in->T
+        cplx* tnew = ctx->W[3] + size_t(off) * dd;
+        RET(gemm(ctx, 0, 0, tprime, (long long)dd, in->T, in->sT, tnew, (long long)dd, nullptr, 0, nullptr, 0, nullptr, 0,
+                 0.0, batch));
+        CK(cudaMemcpy2DAsync(Tout, size_t(sTo) * sizeof(cplx), tnew, dd * sizeof(cplx), dd * sizeof(cplx), batch,
+                             cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    return DQMC_OK;
+}
+
+// G = [1 + (Q_r d_r T_r)(T_l^+ d_l Q_l^+)]^-1, logdet = log|det G^-1|   (greenFromUdV's role)
+int green_from_udts(dqmc_ctx* ctx, const UdtView& r, const UdtView& l, cplx* Gout, long long sG, double* logdet,
+                    int off, int batch) {
+    const size_t dd = DD(ctx);
+    const int D = ctx->D;
+    cplx* H = ctx->W[0] + size_t(off) * dd;
+    cplx* Qh = ctx->W[1] + size_t(off) * dd;
+    cplx* Yw = ctx->W[2] + size_t(off) * dd;
+    cplx* Zw = ctx->W[3] + size_t(off) * dd;
+    double* rInvBig = ctx->vecA + size_t(off) * D;
+    double* rSmall = ctx->vecB + size_t(off) * D;
+    double* lInvBig = ctx->vecC + size_t(off) * D;
+    double* lSmall = ctx->vecD + size_t(off) * D;
+    cplx* tau = ctx->tau + size_t(off) * D;
+    int* perm = ctx->perm + size_t(off) * D;
+    double* cn = ctx->colnorm + size_t(off) * D;
+    CK(cudaMemsetAsync(logdet, 0, sizeof(double) * batch, ctx->stream));
+    // scale splitting d = d_big * d_small
+    if (r.sd == 0) {
+        // shared (identity) scales: replicate once per replica so the kernels can use a stride
+        for (int b = 0; b < batch; ++b)
+            CK(cudaMemcpyAsync(ctx->dtmp + size_t(off + b) * D, r.d, sizeof(double) * D, cudaMemcpyDeviceToDevice,
+                               ctx->stream));
+        CKL(scale_split_launch(ctx->dtmp + size_t(off) * D, rInvBig, rSmall, logdet, D, batch, ctx->stream));
+    } else {
+        // gather with stride into contiguous scratch
+        CK(cudaMemcpy2DAsync(ctx->dtmp + size_t(off) * D, sizeof(double) * D, r.d, sizeof(double) * size_t(r.sd),
+                             sizeof(double) * D, batch, cudaMemcpyDeviceToDevice, ctx->stream));
+        CKL(scale_split_launch(ctx->dtmp + size_t(off) * D, rInvBig, rSmall, logdet, D, batch, ctx->stream));
+    }
+    if (l.sd == 0) {
+        for (int b = 0; b < batch; ++b)
+            CK(cudaMemcpyAsync(ctx->dtmp + size_t(off + b) * D, l.d, sizeof(double) * D, cudaMemcpyDeviceToDevice,
+                               ctx->stream));
+    } else {
+        CK(cudaMemcpy2DAsync(ctx->dtmp + size_t(off) * D, sizeof(double) * D, l.d, sizeof(double) * size_t(l.sd),
+                             sizeof(double) * D, batch, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    CKL(scale_split_launch(ctx->dtmp + size_t(off) * D, lInvBig, lSmall, logdet, D, batch, ctx->stream));
+    // H = (1/d_r^b) (Q_r^+ Q_l) (1/d_l^b) + d_r^s (T_r T_l^+) d_l^s
+    RET(gemm(ctx, 1, 0, r.Q, r.sQ, l.Q, l.sQ, H, (long long)dd, rInvBig, D, lInvBig, D, nullptr, 0, 0.0, batch));
+    RET(gemm(ctx, 0, 1, r.T, r.sT, l.T, l.sT, H, (long long)dd, rSmall, D, lSmall, D, nullptr, 0, 1.0, batch));
+    // H P = Q_h R_h
+    CKL(qrcp_factor_launch(H, D, (long long)dd, tau, perm, cn, batch, ctx->stream));
+    CKL(logdiag_accumulate_launch(H, logdet, D, (long long)dd, batch, ctx->stream));
+    CKL(qr_form_q_launch(H, tau, Qh, D, (long long)dd, batch, ctx->stream));
+    // Y = Q_h^+ (1/d_r^b) Q_r^+
+    RET(gemm(ctx, 1, 1, Qh, (long long)dd, r.Q, r.sQ, Yw, (long long)dd, nullptr, 0, nullptr, 0, rInvBig, D, 0.0,
+             batch));
+    // Z = P R_h^-1 Y
+    CKL(trsm_upper_launch(H, Yw, Zw, perm, D, (long long)dd, batch, ctx->stream));
+    // G = Q_l (1/d_l^b) Z
+    RET(gemm(ctx, 0, 0, l.Q, l.sQ, Zw, (long long)dd, Gout, sG, nullptr, 0, nullptr, 0, lInvBig, D, 0.0, batch));
+    return DQMC_OK;
+}
+
+UdtView storage_view(dqmc_ctx* ctx, int l, int off) {
+    UdtView v;
+    v.Q = stQ(ctx, l) + size_t(off) * st_stride(ctx); v.sQ = st_stride(ctx);
+    v.T = stT(ctx, l) + size_t(off) * st_stride(ctx); v.sT = st_stride(ctx);
+    v.d = stD(ctx, l) + size_t(off) * std_stride(ctx); v.sd = std_stride(ctx);
+    return v;
+}
+
+UdtView identity_view(dqmc_ctx* ctx) {
+    UdtView v;
+    v.Q = ctx->eyeM; v.sQ = 0;
+    v.T = ctx->eyeM; v.sT = 0;
+    v.d = ctx->onesV; v.sd = 0;
+    return v;
+}
+
+int set_storage_identity(dqmc_ctx* ctx, int l, int off, int batch) {
+    CKL(launch_set_identity(stQ(ctx, l) + size_t(off) * st_stride(ctx), ctx->D, st_stride(ctx), batch, ctx->stream));
+    CKL(launch_set_identity(stT(ctx, l) + size_t(off) * st_stride(ctx), ctx->D, st_stride(ctx), batch, ctx->stream));
+    for (int b = 0; b < batch; ++b)
+        CK(cudaMemcpyAsync(stD(ctx, l) + size_t(off + b) * std_stride(ctx), ctx->onesV, sizeof(double) * ctx->D,
+                           cudaMemcpyDeviceToDevice, ctx->stream));
+    return DQMC_OK;
+}
+
+inline int slice_of(const dqmc_ctx* ctx, int l) { return l < ctx->n ? ctx->s * l : ctx->m; }
+
+int setup_storage(dqmc_ctx* ctx, int off, int batch) {
+    const int n = ctx->n;
+    RET(set_storage_identity(ctx, 0, off, batch));
+    for (int l = 0; l < n; ++l) {
+        const int k_l = slice_of(ctx, l), k_lp1 = slice_of(ctx, l + 1);
+        UdtView in = storage_view(ctx, l, off);
+        RET(chain_step(ctx, DQMC_OP_LEFT, l == 0 ? nullptr : &in, k_lp1, k_l,
+                       stQ(ctx, l + 1) + size_t(off) * st_stride(ctx), st_stride(ctx),
+                       stD(ctx, l + 1) + size_t(off) * std_stride(ctx), std_stride(ctx),
+                       stT(ctx, l + 1) + size_t(off) * st_stride(ctx), st_stride(ctx), off, batch));
+    }
+    UdtView r = storage_view(ctx, n, off);
+    UdtView l = identity_view(ctx);
+    RET(green_from_udts(ctx, r, l, ctx->G + size_t(off) * DD(ctx), (long long)DD(ctx), ctx->logdet + off, off, batch));
+    return DQMC_OK;
+}
+
+int record_wrapped(dqmc_ctx* ctx) {
+    CK(cudaMemcpyAsync(ctx->Gwrapped, ctx->G, sizeof(cplx) * DD(ctx) * ctx->nmat, cudaMemcpyDeviceToDevice, ctx->stream));
+    return DQMC_OK;
+}
+int record_consistency(dqmc_ctx* ctx) {
+    CKL(launch_max_abs_diff(ctx->Gwrapped, ctx->G, ctx->D, (long long)DD(ctx), ctx->nmat, ctx->consistency, ctx->stream));
+    return DQMC_OK;
+}
+
+// advanceUpGreen(l), detmodel.h:1106-1163
+int advance_up(dqmc_ctx* ctx, int l) {
+    const int R = ctx->nmat;
+    const int k_l = ctx->s * l, k_lp1 = slice_of(ctx, l + 1);
+    if (ctx->currentTimeslice != k_lp1) { ctx->err = "advance_up: currentTimeslice mismatch"; return DQMC_ERR_STATE; }
+    RET(record_wrapped(ctx));
+    UdtView in = storage_view(ctx, l, 0);
+    // new right chain B(k_lp1, 0) into the temporary UDT
+    // storage[0] is the identity UdV during an up-sweep (detmodel.h:1292-1295)
+    RET(chain_step(ctx, DQMC_OP_LEFT, l == 0 ? nullptr : &in, k_lp1, k_l, ctx->tQ, (long long)DD(ctx), ctx->tD, ctx->D, ctx->tT,
+                   (long long)DD(ctx), 0, R));
+    UdtView rnew{ctx->tQ, (long long)DD(ctx), ctx->tD, ctx->D, ctx->tT, (long long)DD(ctx)};
+    if (k_lp1 != ctx->m) {
+        UdtView left = storage_view(ctx, l + 1, 0);          // B(beta, k_lp1) from the last down-sweep
+        RET(green_from_udts(ctx, rnew, left, ctx->G, (long long)DD(ctx), ctx->logdet, 0, R));
+    } else {
+        UdtView left = identity_view(ctx);
+        RET(green_from_udts(ctx, rnew, left, ctx->G, (long long)DD(ctx), ctx->logdet, 0, R));
+    }
+    const size_t dd = DD(ctx);
+    CK(cudaMemcpy2DAsync(stQ(ctx, l + 1), size_t(st_stride(ctx)) * sizeof(cplx), ctx->tQ, dd * sizeof(cplx),
+                         dd * sizeof(cplx), R, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaMemcpy2DAsync(stT(ctx, l + 1), size_t(st_stride(ctx)) * sizeof(cplx), ctx->tT, dd * sizeof(cplx),
+                         dd * sizeof(cplx), R, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaMemcpy2DAsync(stD(ctx, l + 1), size_t(std_stride(ctx)) * sizeof(double), ctx->tD, ctx->D * sizeof(double),
+                         ctx->D * sizeof(double), R, cudaMemcpyDeviceToDevice, ctx->stream));
+    RET(record_consistency(ctx));
+    ctx->currentTimeslice = k_lp1;
+    return DQMC_OK;
+}
+
+// advanceDownGreen(l), detmodel.h:953-1017
+int advance_down(dqmc_ctx* ctx, int l) {
+    const int R = ctx->nmat;
+    const int n = ctx->n;
+    const int k_l = slice_of(ctx, l), k_lm1 = ctx->s * (l - 1);
+    RET(record_wrapped(ctx));
+    UdtView in = storage_view(ctx, l, 0);
+    RET(chain_step(ctx, DQMC_OP_LEFT_ADJ, l < n ? &in : nullptr, k_l, k_lm1, ctx->tQ, (long long)DD(ctx), ctx->tD,
+                   ctx->D, ctx->tT, (long long)DD(ctx), 0, R));
+    UdtView lnew{ctx->tQ, (long long)DD(ctx), ctx->tD, ctx->D, ctx->tT, (long long)DD(ctx)};
+    if (l - 1 > 0) {
+        UdtView right = storage_view(ctx, l - 1, 0);         // B(k_lm1, 0) from the last up-sweep
+        RET(green_from_udts(ctx, right, lnew, ctx->G, (long long)DD(ctx), ctx->logdet, 0, R));
+    } else {
+        UdtView right = identity_view(ctx);
+        RET(green_from_udts(ctx, right, lnew, ctx->G, (long long)DD(ctx), ctx->logdet, 0, R));
+    }
+    const size_t dd = DD(ctx);
+    CK(cudaMemcpy2DAsync(stQ(ctx, l - 1), size_t(st_stride(ctx)) * sizeof(cplx), ctx->tQ, dd * sizeof(cplx),
+                         dd * sizeof(cplx), R, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaMemcpy2DAsync(stT(ctx, l - 1), size_t(st_stride(ctx)) * sizeof(cplx), ctx->tT, dd * sizeof(cplx),
+                         dd * sizeof(cplx), R, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaMemcpy2DAsync(stD(ctx, l - 1), size_t(std_stride(ctx)) * sizeof(double), ctx->tD, ctx->D * sizeof(double),
+                         ctx->D * sizeof(double), R, cudaMemcpyDeviceToDevice, ctx->stream));
+    RET(record_consistency(ctx));
+    ctx->currentTimeslice = k_lm1;
+    return DQMC_OK;
+}
+
+int wrap_up(dqmc_ctx* ctx, int k) {
+    if (ctx->currentTimeslice != k) { ctx->err = "wrap_up: currentTimeslice mismatch"; return DQMC_ERR_STATE; }
+    RET(sdw_bmult(ctx, DQMC_OP_RIGHT_INV, ctx->G, (long long)DD(ctx), k + 1, k, nullptr, 0, 0, ctx->nmat));
+    RET(sdw_bmult(ctx, DQMC_OP_LEFT, ctx->G, (long long)DD(ctx), k + 1, k, nullptr, 0, 0, ctx->nmat));
+    ctx->currentTimeslice = k + 1;
+    return DQMC_OK;
+}
+
+int wrap_down(dqmc_ctx* ctx, int k) {
+    if (ctx->currentTimeslice != k) { ctx->err = "wrap_down: currentTimeslice mismatch"; return DQMC_ERR_STATE; }
+    RET(sdw_bmult(ctx, DQMC_OP_RIGHT, ctx->G, (long long)DD(ctx), k, k - 1, nullptr, 0, 0, ctx->nmat));
+    RET(sdw_bmult(ctx, DQMC_OP_LEFT_INV, ctx->G, (long long)DD(ctx), k, k - 1, nullptr, 0, 0, ctx->nmat));
+    ctx->currentTimeslice = k - 1;
+    return DQMC_OK;
+}
+
+// ---- random-number window --------------------------------------------------------------------
+int upload_rng_window(dqmc_ctx* ctx, size_t per_replica) {
+    if (per_replica > ctx->rngCap) { ctx->err = "rng window larger than capacity"; return DQMC_ERR_STATE; }
+    for (int r = 0; r < ctx->R; ++r) {
+        const double* src = ctx->rng[r].peek(per_replica);
+        std::memcpy(ctx->h_rng + size_t(r) * ctx->rngCap, src, per_replica * sizeof(double));
+    }
+    CK(cudaMemcpy2DAsync(ctx->rngbuf, ctx->rngCap * sizeof(double), ctx->h_rng, ctx->rngCap * sizeof(double),
+                         per_replica * sizeof(double), ctx->R, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(ctx->cursor, 0, sizeof(int) * ctx->R, ctx->stream));
+    ctx->rngWindow = (int)per_replica;
+    return DQMC_OK;
+}
+
+// read back cursors (+ control data), advance the host streams
+int finish_rng_window(dqmc_ctx* ctx) {
+    CK(cudaMemcpyAsync(ctx->h_cursor, ctx->cursor, sizeof(int) * ctx->R, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_ctrl, ctx->ctrl, sizeof(dqmc_control_data) * ctx->R, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_err, ctx->errflag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (*ctx->h_err) {
+        ctx->err = "device error flag set (random-number window exhausted)";
+        return DQMC_ERR_STATE;
+    }
+    for (int r = 0; r < ctx->R; ++r) {
+        ctx->rng[r].skip((size_t)ctx->h_cursor[r]);
+        // counters of the global moves live on the host; everything else comes from the device
+        const uint32_t acc = ctx->ctrl_host[r].acceptedGlobalShifts, att = ctx->ctrl_host[r].attemptedGlobalShifts;
+        ctx->ctrl_host[r] = ctx->h_ctrl[r];
+        ctx->ctrl_host[r].acceptedGlobalShifts = acc;
+        ctx->ctrl_host[r].attemptedGlobalShifts = att;
+    }
+    ctx->rngWindow = 0;
+    return DQMC_OK;
+}
+
+int launch_update(dqmc_ctx* ctx, int k, int therm) {
+    UpdateArgs a;
+    a.G = ctx->G; a.strideG = (long long)DD(ctx);
+    a.phi = ctx->phi; a.coshT = ctx->coshT; a.sinhT = ctx->sinhT;
+    a.stridePhi = (long long)phi_stride(ctx); a.strideTab = (long long)tab_stride(ctx);
+    a.rvals = ctx->rvals;
+    a.X = ctx->X; a.Y = ctx->Y; a.strideXY = (long long)ctx->D * ctx->kmax;
+    a.rng = ctx->rngbuf; a.strideRng = (long long)ctx->rngCap; a.rngWindow = ctx->rngWindow;
+    a.cursor = ctx->cursor;
+    a.ctrl = ctx->ctrl;
+    a.accepted = ctx->accepted;
+    a.errflag = ctx->errflag;
+    a.k = k;
+    a.thermalization = therm;
+    a.batch = ctx->R;
+    CKL(update_slice_launch(ctx->umodel, a, ctx->stream));
+    return DQMC_OK;
+}
+
+int upload_ctrl(dqmc_ctx* ctx) {
+    std::memcpy(ctx->h_ctrl, ctx->ctrl_host.data(), sizeof(dqmc_control_data) * ctx->R);
+    CK(cudaMemcpyAsync(ctx->ctrl, ctx->h_ctrl, sizeof(dqmc_control_data) * ctx->R, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return DQMC_OK;
+}
+
+int upload_rvals(dqmc_ctx* ctx) {
+    CK(cudaMemcpyAsync(ctx->rvals, ctx->h_r.data(), sizeof(double) * ctx->R, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return DQMC_OK;
+}
+
+// attemptGlobalShiftMove for the whole batch, detsdwopdim.cpp:3564-3645
+int global_shift_move(dqmc_ctx* ctx, int32_t* accepted_out) {
+    const int R = ctx->R, D = ctx->D;
+    if (ctx->currentTimeslice != ctx->m) { ctx->err = "global shift: currentTimeslice != m"; return DQMC_ERR_STATE; }
+    double* h = ctx->h_scalars;      // [0,R): old action, [R,2R): new action, [2R,3R) old logdet, [3R,4R) new
+    CKL(launch_phi_action(ctx->phi, ctx->rvals, ctx->actions, ctx->p.L, ctx->opdim, ctx->m, ctx->p.dtau, ctx->p.c,
+                          ctx->p.u, (long long)phi_stride(ctx), R, ctx->stream));
+    CK(cudaMemcpyAsync(h, ctx->actions, sizeof(double) * R, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(h + 2 * R, ctx->logdet, sizeof(double) * R, cudaMemcpyDeviceToHost, ctx->stream));
+    // backups (globalMoveStoreBackups, :3885-3900): copy the fields, swap everything that is recomputed
+    CK(cudaMemcpyAsync(ctx->bkPhi, ctx->phi, sizeof(double) * phi_stride(ctx) * R, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->bkCosh, ctx->coshT, sizeof(double) * tab_stride(ctx) * R, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->bkSinh, ctx->sinhT, sizeof(double) * tab_stride(ctx) * R, cudaMemcpyDeviceToDevice, ctx->stream));
+    std::swap(ctx->G, ctx->bkG);
+    std::swap(ctx->stQ, ctx->bkQ);
+    std::swap(ctx->stT, ctx->bkT);
+    std::swap(ctx->stD, ctx->bkD);
+    std::swap(ctx->logdet, ctx->bkLogdet);
+    // addGlobalRandomDisplacement (:3755-3763): OPDIM draws of randRange(-phiDelta, +phiDelta)
+    for (int r = 0; r < R; ++r) {
+        const double pd = ctx->ctrl_host[r].phiDelta;
+        for (int d = 0; d < 3; ++d) h[4 * R + 3 * r + d] = 0.0;
+        for (int d = 0; d < ctx->opdim; ++d) h[4 * R + 3 * r + d] = ctx->rng[r].draw_range(-pd, +pd);
+    }
+    CK(cudaMemcpyAsync(ctx->shiftbuf, h + 4 * R, sizeof(double) * 3 * R, cudaMemcpyHostToDevice, ctx->stream));
+    CKL(launch_shift_fields(ctx->phi, ctx->shiftbuf, ctx->N, ctx->opdim, ctx->m, (long long)phi_stride(ctx), R, ctx->stream));
+    CKL(launch_update_tables(ctx->phi, ctx->coshT, ctx->sinhT, ctx->N, ctx->opdim, ctx->m, ctx->p.lambda * ctx->p.dtau,
+                             (long long)phi_stride(ctx), (long long)tab_stride(ctx), R, ctx->stream));
+    RET(setup_storage(ctx, 0, R));
+    CKL(launch_phi_action(ctx->phi, ctx->rvals, ctx->actions, ctx->p.L, ctx->opdim, ctx->m, ctx->p.dtau, ctx->p.c,
+                          ctx->p.u, (long long)phi_stride(ctx), R, ctx->stream));
+    CK(cudaMemcpyAsync(h + R, ctx->actions, sizeof(double) * R, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(h + 3 * R, ctx->logdet, sizeof(double) * R, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const size_t dd = DD(ctx);
+    for (int r = 0; r < R; ++r) {
+        const double probScalar = std::exp(-(h[R + r] - h[r]));
+        double probFermion = std::exp(h[3 * R + r] - h[2 * R + r]);
+        if (ctx->opdim < 3) probFermion = probFermion * probFermion;
+        const double prob = probScalar * probFermion;
+        ctx->lastGlobalProb[r] = prob;
+        ctx->ctrl_host[r].attemptedGlobalShifts += 1;
+        bool acc = prob >= 1.0 || ctx->rng[r].draw() < prob;
+        if (accepted_out) accepted_out[r] = acc ? 1 : 0;
+        if (acc) {
+            ctx->ctrl_host[r].acceptedGlobalShifts += 1;
+        } else {
+            // globalMoveRestoreBackups (:3902-3917) for this replica
+            CK(cudaMemcpyAsync(ctx->phi + size_t(r) * phi_stride(ctx), ctx->bkPhi + size_t(r) * phi_stride(ctx),
+                               sizeof(double) * phi_stride(ctx), cudaMemcpyDeviceToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(ctx->coshT + size_t(r) * tab_stride(ctx), ctx->bkCosh + size_t(r) * tab_stride(ctx),
+                               sizeof(double) * tab_stride(ctx), cudaMemcpyDeviceToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(ctx->sinhT + size_t(r) * tab_stride(ctx), ctx->bkSinh + size_t(r) * tab_stride(ctx),
+                               sizeof(double) * tab_stride(ctx), cudaMemcpyDeviceToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(ctx->G + size_t(r) * dd, ctx->bkG + size_t(r) * dd, sizeof(cplx) * dd,
+                               cudaMemcpyDeviceToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(ctx->stQ + size_t(r) * st_stride(ctx), ctx->bkQ + size_t(r) * st_stride(ctx),
+                               sizeof(cplx) * st_stride(ctx), cudaMemcpyDeviceToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(ctx->stT + size_t(r) * st_stride(ctx), ctx->bkT + size_t(r) * st_stride(ctx),
+                               sizeof(cplx) * st_stride(ctx), cudaMemcpyDeviceToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(ctx->stD + size_t(r) * std_stride(ctx), ctx->bkD + size_t(r) * std_stride(ctx),
+                               sizeof(double) * std_stride(ctx), cudaMemcpyDeviceToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(ctx->logdet + r, ctx->bkLogdet + r, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+    }
+    (void)D;
+    ctx->currentTimeslice = ctx->m;
+    ctx->lastSweepDir = +1;
+    return DQMC_OK;
+}
+
+// sweepDown / sweepUp, detmodel.h:1261-1399
+int sweep_down(dqmc_ctx* ctx, int therm) {
+    const int n = ctx->n, s = ctx->s, m = ctx->m;
+    for (int k = m; k >= (n - 1) * s + 1; --k) {
+        RET(launch_update(ctx, k, therm));
+        RET(wrap_down(ctx, k));
+    }
+    for (int l = n - 1; l >= 1; --l) {
+        RET(advance_down(ctx, l + 1));
+        for (int k = l * s; k >= (l - 1) * s + 1; --k) {
+            RET(launch_update(ctx, k, therm));
+            RET(wrap_down(ctx, k));
+        }
+    }
+    RET(advance_down(ctx, 1));
+    return DQMC_OK;
+}
+
+int sweep_up(dqmc_ctx* ctx, int therm) {
+    const int n = ctx->n, s = ctx->s, m = ctx->m;
+    RET(set_storage_identity(ctx, 0, 0, ctx->nmat));
+    for (int l = 0; l <= n - 2; ++l) {
+        for (int k = l * s + 1; k <= (l + 1) * s; ++k) {
+            RET(wrap_up(ctx, k - 1));
+            RET(launch_update(ctx, k, therm));
+        }
+        RET(advance_up(ctx, l));
+    }
+    for (int k = (n - 1) * s + 1; k <= m; ++k) {
+        RET(wrap_up(ctx, k - 1));
+        RET(launch_update(ctx, k, therm));
+    }
+    RET(advance_up(ctx, n - 1));
+    return DQMC_OK;
+}
+
+bool valid_rep(const dqmc_ctx* ctx, int rep) { return ctx && rep >= 0 && rep < ctx->R; }
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+int dqmc_create(const dqmc_params* params, int n_replicas, int device, dqmc_ctx** out) {
+    if (!params || !out || n_replicas <= 0) return DQMC_ERR_PARAM;
+    *out = nullptr;
+    dqmc_ctx* ctx = new (std::nothrow) dqmc_ctx();
+    if (!ctx) return DQMC_ERR_PARAM;
+    *out = ctx;                      // returned even on failure so the caller can read the error text
+    ctx->p = *params;
+    const dqmc_params& p = ctx->p;
+    if (p.model != DQMC_MODEL_SDW) { ctx->err = "only DQMC_MODEL_SDW is implemented in this build"; return DQMC_ERR_PARAM; }
+    if (p.opdim < 1 || p.opdim > 3) { ctx->err = "opdim must be 1, 2 or 3"; return DQMC_ERR_PARAM; }
+    if (p.L < 2 || p.L % 2) { ctx->err = "checkerboard decomposition needs an even L >= 2"; return DQMC_ERR_PARAM; }
+    if (p.weakZflux && p.opdim == 3) { ctx->err = "weakZflux is only supported for opdim < 3"; return DQMC_ERR_PARAM; }
+    if (p.m < 2 || p.s < 1 || p.dtau <= 0) { ctx->err = "need m >= 2, s >= 1, dtau > 0"; return DQMC_ERR_PARAM; }
+    if (p.delaySteps < 1 || p.delaySteps > p.L * p.L) { ctx->err = "delaySteps out of range"; return DQMC_ERR_PARAM; }
+    if (p.globalShift && p.globalUpdateInterval < 1) { ctx->err = "globalUpdateInterval must be >= 1"; return DQMC_ERR_PARAM; }
+    ctx->R = n_replicas;
+    ctx->opdim = p.opdim;
+    ctx->N = p.L * p.L;
+    ctx->msf = p.opdim == 3 ? 4 : 2;
+    ctx->D = ctx->msf * ctx->N;
+    ctx->m = p.m;
+    ctx->s = p.s;
+    while (ctx->m <= ctx->s) ctx->s -= 1;                  // updateTemperatureParameters, detmodelparams.h:108-113
+    ctx->n = (ctx->m + ctx->s - 1) / ctx->s;
+    ctx->ngc = 1;
+    ctx->nmat = ctx->R * ctx->ngc;
+    ctx->device = device;
+    ctx->launches = 0;
+    ctx->currentTimeslice = 0;
+    ctx->lastSweepDir = +1;
+    ctx->performedSweeps = 0;
+    ctx->rngWindow = 0;
+
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) { ctx->err = "no such CUDA device (this library has no CPU fallback)"; return DQMC_ERR_CUDA; }
+    CK(cudaSetDevice(device));
+    CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    ctx->own_stream = true;
+
+    ctx->geom.L = p.L; ctx->geom.N = ctx->N; ctx->geom.msf = ctx->msf; ctx->geom.D = ctx->D;
+    ctx->geom.nplaq = ctx->N / 4; ctx->geom.opdim = p.opdim; ctx->geom.m = ctx->m;
+    ctx->geom.lambda_dtau = p.lambda * p.dtau;
+    ctx->umodel.L = p.L; ctx->umodel.N = ctx->N; ctx->umodel.msf = ctx->msf; ctx->umodel.D = ctx->D;
+    ctx->umodel.opdim = p.opdim; ctx->umodel.m = ctx->m; ctx->umodel.delaySteps = p.delaySteps;
+    ctx->umodel.dtau = p.dtau; ctx->umodel.c = p.c; ctx->umodel.u = p.u; ctx->umodel.lambda = p.lambda;
+    ctx->umodel.accRatio = p.accRatio;
+
+    const size_t dd = DD(ctx), nm = ctx->nmat, D = ctx->D, R = ctx->R;
+    CK(dmalloc(&ctx->G, dd * nm));
+    CK(dmalloc(&ctx->bkG, dd * nm));
+    CK(dmalloc(&ctx->Gwrapped, dd * nm));
+    for (int i = 0; i < 4; ++i) CK(dmalloc(&ctx->W[i], dd * nm));
+    CK(dmalloc(&ctx->tQ, dd * nm));
+    CK(dmalloc(&ctx->tT, dd * nm));
+    CK(dmalloc(&ctx->tD, D * nm));
+    CK(dmalloc(&ctx->stQ, dd * nm * (ctx->n + 1)));
+    CK(dmalloc(&ctx->stT, dd * nm * (ctx->n + 1)));
+    CK(dmalloc(&ctx->stD, D * nm * (ctx->n + 1)));
+    CK(dmalloc(&ctx->bkQ, dd * nm * (ctx->n + 1)));
+    CK(dmalloc(&ctx->bkT, dd * nm * (ctx->n + 1)));
+    CK(dmalloc(&ctx->bkD, D * nm * (ctx->n + 1)));
+    CK(dmalloc(&ctx->phi, phi_stride(ctx) * R));
+    CK(dmalloc(&ctx->coshT, tab_stride(ctx) * R));
+    CK(dmalloc(&ctx->sinhT, tab_stride(ctx) * R));
+    CK(dmalloc(&ctx->bkPhi, phi_stride(ctx) * R));
+    CK(dmalloc(&ctx->bkCosh, tab_stride(ctx) * R));
+    CK(dmalloc(&ctx->bkSinh, tab_stride(ctx) * R));
+    CK(dmalloc(&ctx->rvals, R));
+    CK(dmalloc(&ctx->tau, D * nm));
+    CK(dmalloc(&ctx->perm, D * nm));
+    CK(dmalloc(&ctx->colnorm, D * nm));
+    CK(dmalloc(&ctx->vecA, D * nm));
+    CK(dmalloc(&ctx->vecB, D * nm));
+    CK(dmalloc(&ctx->vecC, D * nm));
+    CK(dmalloc(&ctx->vecD, D * nm));
+    CK(dmalloc(&ctx->dtmp, D * nm));
+    CK(dmalloc(&ctx->logdet, nm));
+    CK(dmalloc(&ctx->bkLogdet, nm));
+    CK(dmalloc(&ctx->consistency, nm));
+    CK(dmalloc(&ctx->eyeM, dd));
+    CK(dmalloc(&ctx->onesV, D));
+    ctx->kmax = ctx->msf * p.delaySteps;
+    CK(dmalloc(&ctx->X, D * ctx->kmax * R));
+    CK(dmalloc(&ctx->Y, D * ctx->kmax * R));
+    ctx->rngCap = size_t(ctx->m) * ctx->N * (p.opdim + 1);
+    CK(dmalloc(&ctx->rngbuf, ctx->rngCap * R));
+    CK(dmalloc(&ctx->cursor, R));
+    CK(dmalloc(&ctx->ctrl, R));
+    CK(dmalloc(&ctx->accepted, R));
+    CK(dmalloc(&ctx->errflag, 1));
+    CK(dmalloc(&ctx->actions, R));
+    CK(dmalloc(&ctx->shiftbuf, 3 * R));
+    CK(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_rng), ctx->rngCap * R * sizeof(double)));
+    CK(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_cursor), R * sizeof(int)));
+    CK(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_scalars), (8 * R + 16) * sizeof(double)));
+    CK(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_ctrl), R * sizeof(dqmc_control_data)));
+    CK(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_err), sizeof(int)));
+    CK(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_acc), R * sizeof(uint32_t)));
+
+    std::vector<cplx> tab;
+    cb_build_tables(p, tab);
+    CK(dmalloc(&ctx->cbtab, tab.size()));
+    CK(cudaMemcpyAsync(ctx->cbtab, tab.data(), tab.size() * sizeof(cplx), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(ctx->phi, 0, sizeof(double) * phi_stride(ctx) * R, ctx->stream));
+    CK(cudaMemsetAsync(ctx->coshT, 0, sizeof(double) * tab_stride(ctx) * R, ctx->stream));
+    CK(cudaMemsetAsync(ctx->sinhT, 0, sizeof(double) * tab_stride(ctx) * R, ctx->stream));
+    CK(cudaMemsetAsync(ctx->errflag, 0, sizeof(int), ctx->stream));
+    CK(cudaMemsetAsync(ctx->G, 0, sizeof(cplx) * dd * nm, ctx->stream));
+    CKL(launch_set_identity(ctx->eyeM, ctx->D, 0, 1, ctx->stream));
+    {
+        std::vector<double> ones(D, 1.0);
+        CK(cudaMemcpyAsync(ctx->onesV, ones.data(), sizeof(double) * D, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    ctx->rng.resize(R);
+    ctx->h_r.assign(R, p.r);
+    ctx->lastGlobalProb.assign(R, 0.0);
+    ctx->ctrl_host.resize(R);
+    for (size_t r = 0; r < R; ++r) {
+        ctx->rng[r].seed(0, (uint32_t)r);
+        dqmc_control_data& c = ctx->ctrl_host[r];
+        std::memset(&c, 0, sizeof c);
+        c.phiDelta = 0.5;                                   // AdjustmentData::InitialPhiDelta
+    }
+    RET(upload_ctrl(ctx));
+    RET(upload_rvals(ctx));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return DQMC_OK;
+}
+
+void dqmc_destroy(dqmc_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    void* dev[] = {ctx->G, ctx->bkG, ctx->Gwrapped, ctx->W[0], ctx->W[1], ctx->W[2], ctx->W[3], ctx->tQ, ctx->tT, ctx->tD,
+                   ctx->stQ, ctx->stT, ctx->stD, ctx->bkQ, ctx->bkT, ctx->bkD, ctx->phi, ctx->coshT, ctx->sinhT,
+                   ctx->bkPhi, ctx->bkCosh, ctx->bkSinh, ctx->rvals, ctx->tau, ctx->perm, ctx->colnorm, ctx->vecA,
+                   ctx->vecB, ctx->vecC, ctx->vecD, ctx->dtmp, ctx->logdet, ctx->bkLogdet, ctx->consistency, ctx->eyeM,
+                   ctx->onesV, ctx->X, ctx->Y, ctx->rngbuf, ctx->cursor, ctx->ctrl, ctx->accepted, ctx->errflag,
+                   ctx->actions, ctx->shiftbuf, ctx->cbtab};
+    for (void* p : dev) if (p) cudaFree(p);
+    void* host[] = {ctx->h_rng, ctx->h_cursor, ctx->h_scalars, ctx->h_ctrl, ctx->h_err, ctx->h_acc};
+    for (void* p : host) if (p) cudaFreeHost(p);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* dqmc_last_error(const dqmc_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int dqmc_set_stream(dqmc_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return DQMC_ERR_PARAM;
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->own_stream) { cudaStreamDestroy(ctx->stream); ctx->own_stream = false; }
+    if (cuda_stream) {
+        ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+    } else {
+        CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        ctx->own_stream = true;
+    }
+    return DQMC_OK;
+}
+
+int dqmc_synchronize(dqmc_ctx* ctx) {
+    if (!ctx) return DQMC_ERR_PARAM;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return DQMC_OK;
+}
+
+int dqmc_dims(const dqmc_ctx* ctx, int32_t* out) {
+    if (!ctx || !out) return DQMC_ERR_PARAM;
+    out[0] = ctx->N; out[1] = ctx->D; out[2] = ctx->m; out[3] = ctx->n; out[4] = ctx->s; out[5] = ctx->ngc;
+    out[6] = ctx->R; out[7] = ctx->opdim;
+    return DQMC_OK;
+}
+
+uint64_t dqmc_launch_count(const dqmc_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---- RNG ---------------------------------------------------------------------------------------
+int dqmc_rng_seed(dqmc_ctx* ctx, int rep, uint32_t seed, uint32_t process_index) {
+    if (!valid_rep(ctx, rep)) return DQMC_ERR_PARAM;
+    ctx->rng[rep].seed(seed, process_index);
+    return DQMC_OK;
+}
+int dqmc_rng_set_source(dqmc_ctx* ctx, int rep, dqmc_rng_fill_fn fill, void* user) {
+    if (!valid_rep(ctx, rep) || !fill) return DQMC_ERR_PARAM;
+    ctx->rng[rep].set_source(fill, user);
+    return DQMC_OK;
+}
+int dqmc_rng_draw(dqmc_ctx* ctx, int rep, size_t n, double* out) {
+    if (!valid_rep(ctx, rep) || (n && !out)) return DQMC_ERR_PARAM;
+    for (size_t i = 0; i < n; ++i) out[i] = ctx->rng[rep].draw();
+    return DQMC_OK;
+}
+int dqmc_rng_peek(dqmc_ctx* ctx, int rep, size_t n, double* out) {
+    if (!valid_rep(ctx, rep) || (n && !out)) return DQMC_ERR_PARAM;
+    const double* p = ctx->rng[rep].peek(n);
+    std::memcpy(out, p, n * sizeof(double));
+    return DQMC_OK;
+}
+int dqmc_rng_skip(dqmc_ctx* ctx, int rep, size_t n) {
+    if (!valid_rep(ctx, rep)) return DQMC_ERR_PARAM;
+    ctx->rng[rep].skip(n);
+    return DQMC_OK;
+}
+uint64_t dqmc_rng_consumed(const dqmc_ctx* ctx, int rep) { return valid_rep(ctx, rep) ? ctx->rng[rep].consumed() : 0; }
+
+// ---- state -------------------------------------------------------------------------------------
+int dqmc_upload_fields(dqmc_ctx* ctx, int rep, const void* fields) {
+    if (!valid_rep(ctx, rep) || !fields) return DQMC_ERR_PARAM;
+    CK(cudaMemcpyAsync(ctx->phi + size_t(rep) * phi_stride(ctx), fields, sizeof(double) * phi_stride(ctx),
+                       cudaMemcpyHostToDevice, ctx->stream));
+    CKL(launch_update_tables(ctx->phi + size_t(rep) * phi_stride(ctx), ctx->coshT + size_t(rep) * tab_stride(ctx),
+                             ctx->sinhT + size_t(rep) * tab_stride(ctx), ctx->N, ctx->opdim, ctx->m,
+                             ctx->p.lambda * ctx->p.dtau, (long long)phi_stride(ctx), (long long)tab_stride(ctx), 1,
+                             ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return DQMC_OK;
+}
+
+int dqmc_init_random_fields(dqmc_ctx* ctx, int rep) {
+    if (!valid_rep(ctx, rep)) return DQMC_ERR_PARAM;
+    // setupRandomField, detsdwopdim.cpp:1098-1113: per (k, site): OPDIM x randRange(-1, 1), then one
+    // rand01() for cdwl (drawn even though cdwU == 0)
+    std::vector<double> phi(phi_stride(ctx), 0.0);
+    RngStream& g = ctx->rng[rep];
+    for (int k = 1; k <= ctx->m; ++k)
+        for (int site = 0; site < ctx->N; ++site) {
+            for (int d = 0; d < ctx->opdim; ++d)
+                phi[(size_t(k) * ctx->opdim + d) * ctx->N + site] = g.draw_range(-1.0, 1.0);
+            (void)g.draw();
+        }
+    return dqmc_upload_fields(ctx, rep, phi.data());
+}
+
+int dqmc_download_fields(dqmc_ctx* ctx, int rep, void* fields) {
+    if (!valid_rep(ctx, rep) || !fields) return DQMC_ERR_PARAM;
+    CK(cudaMemcpyAsync(fields, ctx->phi + size_t(rep) * phi_stride(ctx), sizeof(double) * phi_stride(ctx),
+                       cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return DQMC_OK;
+}
+
+int dqmc_download_green(dqmc_ctx* ctx, int rep, int gc, double* out) {
+    if (!valid_rep(ctx, rep) || gc != 0 || !out) return DQMC_ERR_PARAM;
+    CK(cudaMemcpyAsync(out, ctx->G + size_t(rep) * DD(ctx), sizeof(cplx) * DD(ctx), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return DQMC_OK;
+}
+
+int dqmc_upload_green(dqmc_ctx* ctx, int rep, int gc, const double* in) {
+    if (!valid_rep(ctx, rep) || gc != 0 || !in) return DQMC_ERR_PARAM;
+    CK(cudaMemcpyAsync(ctx->G + size_t(rep) * DD(ctx), in, sizeof(cplx) * DD(ctx), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return DQMC_OK;
+}
+
+int dqmc_set_exchange_parameter(dqmc_ctx* ctx, int rep, double r) {
+    if (!valid_rep(ctx, rep)) return DQMC_ERR_PARAM;
+    ctx->h_r[rep] = r;
+    return upload_rvals(ctx);
+}
+int dqmc_get_exchange_parameter(dqmc_ctx* ctx, int rep, double* r) {
+    if (!valid_rep(ctx, rep) || !r) return DQMC_ERR_PARAM;
+    *r = ctx->h_r[rep];
+    return DQMC_OK;
+}
+int dqmc_get_control_data(dqmc_ctx* ctx, int rep, dqmc_control_data* out) {
+    if (!valid_rep(ctx, rep) || !out) return DQMC_ERR_PARAM;
+    *out = ctx->ctrl_host[rep];
+    return DQMC_OK;
+}
+int dqmc_set_control_data(dqmc_ctx* ctx, int rep, const dqmc_control_data* in) {
+    if (!valid_rep(ctx, rep) || !in) return DQMC_ERR_PARAM;
+    ctx->ctrl_host[rep] = *in;
+    return upload_ctrl(ctx);
+}
+int dqmc_get_sweep_state(const dqmc_ctx* ctx, int32_t* out) {
+    if (!ctx || !out) return DQMC_ERR_PARAM;
+    out[0] = ctx->currentTimeslice; out[1] = ctx->lastSweepDir; out[2] = ctx->performedSweeps;
+    return DQMC_OK;
+}
+
+// ---- operators ---------------------------------------------------------------------------------
+int dqmc_bmat_mult(dqmc_ctx* ctx, int rep, int gc, int op, double* A_host, uint32_t k2, uint32_t k1) {
+    if (!valid_rep(ctx, rep) || gc != 0 || op < 0 || op > 4 || !A_host || k2 <= k1 || (int)k2 > ctx->m) return DQMC_ERR_PARAM;
+    cplx* buf = ctx->W[0] + size_t(rep) * DD(ctx);
+    CK(cudaMemcpyAsync(buf, A_host, sizeof(cplx) * DD(ctx), cudaMemcpyHostToDevice, ctx->stream));
+    RET(sdw_bmult(ctx, op, buf, (long long)DD(ctx), (int)k2, (int)k1, nullptr, 0, rep, 1));
+    CK(cudaMemcpyAsync(A_host, buf, sizeof(cplx) * DD(ctx), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return DQMC_OK;
+}
+
+int dqmc_bmat_mult_device(dqmc_ctx* ctx, int gc, int op, void* A_dev, uint32_t k2, uint32_t k1) {
+    if (!ctx || gc != 0 || op < 0 || op > 4 || !A_dev || k2 <= k1 || (int)k2 > ctx->m) return DQMC_ERR_PARAM;
+    return sdw_bmult(ctx, op, static_cast<cplx*>(A_dev), (long long)DD(ctx), (int)k2, (int)k1, nullptr, 0, 0, ctx->nmat);
+}
+
+int dqmc_bench_bmat_mult(dqmc_ctx* ctx, int op, void* A_dev, uint32_t k2, uint32_t k1, int reps, float* ms_per_launch) {
+    if (!ctx || !A_dev || reps < 1 || !ms_per_launch) return DQMC_ERR_PARAM;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0, ctx->stream));
+    for (int i = 0; i < reps; ++i) RET(dqmc_bmat_mult_device(ctx, 0, op, A_dev, k2, k1));
+    CK(cudaEventRecord(e1, ctx->stream));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    *ms_per_launch = ms / reps;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return DQMC_OK;
+}
+
+int dqmc_setup_storage(dqmc_ctx* ctx) {
+    if (!ctx) return DQMC_ERR_PARAM;
+    RET(setup_storage(ctx, 0, ctx->nmat));
+    ctx->currentTimeslice = ctx->m;
+    ctx->lastSweepDir = +1;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return DQMC_OK;
+}
+
+int dqmc_wrap_up(dqmc_ctx* ctx, uint32_t k) { return ctx ? wrap_up(ctx, (int)k) : DQMC_ERR_PARAM; }
+int dqmc_wrap_down(dqmc_ctx* ctx, uint32_t k) { return ctx ? wrap_down(ctx, (int)k) : DQMC_ERR_PARAM; }
+int dqmc_advance_up(dqmc_ctx* ctx, uint32_t l) { return ctx ? advance_up(ctx, (int)l) : DQMC_ERR_PARAM; }
+int dqmc_advance_down(dqmc_ctx* ctx, uint32_t l) { return ctx ? advance_down(ctx, (int)l) : DQMC_ERR_PARAM; }
+
+int dqmc_get_green_consistency(dqmc_ctx* ctx, double* out) {
+    if (!ctx || !out) return DQMC_ERR_PARAM;
+    CK(cudaMemcpyAsync(out, ctx->consistency, sizeof(double) * ctx->nmat, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return DQMC_OK;
+}
+
+int dqmc_logdet(dqmc_ctx* ctx, int rep, int gc, double* out) {
+    if (!valid_rep(ctx, rep) || gc != 0 || !out) return DQMC_ERR_PARAM;
+    CK(cudaMemcpyAsync(out, ctx->logdet + rep, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return DQMC_OK;
+}
+
+int dqmc_green_for_timeslice(dqmc_ctx* ctx, int rep, int gc, uint32_t kk, double* out) {
+    if (!valid_rep(ctx, rep) || gc != 0 || !out || (int)kk > ctx->m) return DQMC_ERR_PARAM;
+    const int k = (int)kk, s = ctx->s, m = ctx->m;
+    const size_t dd = DD(ctx);
+    const int D = ctx->D;
+    // right chain B(k, 0) and left chain B(beta, k), each in steps of <= s slices, in private scratch
+    cplx* buf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // rQ, rT, lQ, lT, G
+    double* dv[3] = {nullptr, nullptr, nullptr};                    // rD, lD, logdet
+    for (int i = 0; i < 5; ++i) CK(dmalloc(&buf[i], dd));
+    for (int i = 0; i < 3; ++i) CK(dmalloc(&dv[i], (size_t)D));
+    bool haveR = false, haveL = false;
+    int rc = DQMC_OK;
+    for (int k1 = 0; k1 < k && rc == DQMC_OK;) {
+        const int k2 = std::min(k, k1 + s);
+        UdtView in{buf[0], (long long)dd, dv[0], D, buf[1], (long long)dd};
+        rc = chain_step(ctx, DQMC_OP_LEFT, haveR ? &in : nullptr, k2, k1, buf[0], (long long)dd, dv[0], D, buf[1],
+                        (long long)dd, rep, 1);
+        haveR = true;
+        k1 = k2;
+    }
+    for (int k2 = m; k2 > k && rc == DQMC_OK;) {
+        const int k1 = std::max(k, k2 - s);
+        UdtView in{buf[2], (long long)dd, dv[1], D, buf[3], (long long)dd};
+        rc = chain_step(ctx, DQMC_OP_LEFT_ADJ, haveL ? &in : nullptr, k2, k1, buf[2], (long long)dd, dv[1], D, buf[3],
+                        (long long)dd, rep, 1);
+        haveL = true;
+        k2 = k1;
+    }
+    if (rc == DQMC_OK) {
+        UdtView rv = haveR ? UdtView{buf[0], (long long)dd, dv[0], D, buf[1], (long long)dd} : identity_view(ctx);
+        UdtView lv = haveL ? UdtView{buf[2], (long long)dd, dv[1], D, buf[3], (long long)dd} : identity_view(ctx);
+        rc = green_from_udts(ctx, rv, lv, buf[4], (long long)dd, dv[2], rep, 1);
+    }
+    if (rc == DQMC_OK) {
+        cudaError_t e = cudaMemcpyAsync(out, buf[4], sizeof(cplx) * dd, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); rc = DQMC_ERR_CUDA; }
+    }
+    cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < 5; ++i) cudaFree(buf[i]);
+    for (int i = 0; i < 3; ++i) cudaFree(dv[i]);
+    return rc;
+}
+
+int dqmc_green_from_udt_host(dqmc_ctx* ctx, const double* Qr, const double* dr, const double* Tr, const double* Ql,
+                             const double* dl, const double* Tl, double* G_out, double* logdet_out) {
+    if (!ctx || !Qr || !dr || !Tr || !Ql || !dl || !Tl || !G_out) return DQMC_ERR_PARAM;
+    const size_t dd = DD(ctx);
+    const int D = ctx->D;
+    cplx* bufs[4];
+    double* dv[2];
+    for (int i = 0; i < 4; ++i) CK(dmalloc(&bufs[i], dd));
+    for (int i = 0; i < 2; ++i) CK(dmalloc(&dv[i], (size_t)D));
+    cplx* g = nullptr; double* ld = nullptr;
+    CK(dmalloc(&g, dd));
+    CK(dmalloc(&ld, 1));
+    const double* src[4] = {Qr, Tr, Ql, Tl};
+    for (int i = 0; i < 4; ++i) CK(cudaMemcpyAsync(bufs[i], src[i], sizeof(cplx) * dd, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(dv[0], dr, sizeof(double) * D, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(dv[1], dl, sizeof(double) * D, cudaMemcpyHostToDevice, ctx->stream));
+    UdtView rv{bufs[0], (long long)dd, dv[0], D, bufs[1], (long long)dd};
+    UdtView lv{bufs[2], (long long)dd, dv[1], D, bufs[3], (long long)dd};
+    int rc = green_from_udts(ctx, rv, lv, g, (long long)dd, ld, 0, 1);
+    if (rc == DQMC_OK) {
+        CK(cudaMemcpyAsync(G_out, g, sizeof(cplx) * dd, cudaMemcpyDeviceToHost, ctx->stream));
+        if (logdet_out) CK(cudaMemcpyAsync(logdet_out, ld, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < 4; ++i) cudaFree(bufs[i]);
+    cudaFree(dv[0]); cudaFree(dv[1]); cudaFree(g); cudaFree(ld);
+    return rc;
+}
+
+int dqmc_udt_decompose_host(dqmc_ctx* ctx, const double* M, double* Q, double* d, double* T) {
+    if (!ctx || !M || !Q || !d || !T) return DQMC_ERR_PARAM;
+    const size_t dd = DD(ctx);
+    const int D = ctx->D;
+    cplx* work = ctx->W[0];
+    cplx* q = ctx->W[1];
+    cplx* t = ctx->W[2];
+    CK(cudaMemcpyAsync(work, M, sizeof(cplx) * dd, cudaMemcpyHostToDevice, ctx->stream));
+    RET(udt_decompose(ctx, work, (long long)dd, q, (long long)dd, ctx->vecA, D, t, (long long)dd, 0, 1));
+    CK(cudaMemcpyAsync(Q, q, sizeof(cplx) * dd, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(T, t, sizeof(cplx) * dd, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(d, ctx->vecA, sizeof(double) * D, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return DQMC_OK;
+}
+
+int dqmc_gemm_host(dqmc_ctx* ctx, int transa, int transb, int M, int N, int K, const double* A, const double* B,
+                   double* C) {
+    if (!ctx || !A || !B || !C || M < 1 || N < 1 || K < 1) return DQMC_ERR_PARAM;
+    const int ar = transa ? K : M, ac = transa ? M : K, br = transb ? N : K, bc = transb ? K : N;
+    cplx *dA, *dB, *dC;
+    CK(dmalloc(&dA, size_t(ar) * ac));
+    CK(dmalloc(&dB, size_t(br) * bc));
+    CK(dmalloc(&dC, size_t(M) * N));
+    CK(cudaMemcpyAsync(dA, A, sizeof(cplx) * ar * ac, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(dB, B, sizeof(cplx) * br * bc, cudaMemcpyHostToDevice, ctx->stream));
+    GemmArgs g;
+    g.M = M; g.N = N; g.K = K; g.transa = transa; g.transb = transb;
+    g.A = dA; g.lda = ar; g.strideA = 0;
+    g.B = dB; g.ldb = br; g.strideB = 0;
+    g.C = dC; g.ldc = M; g.strideC = 0;
+    g.rowscale = g.colscale = g.kscale = nullptr;
+    g.strideRow = g.strideCol = g.strideK = 0;
+    g.beta = 0.0;
+    g.batch = 1;
+    CKL(gemm_launch(g, ctx->stream));
+    CK(cudaMemcpyAsync(C, dC, sizeof(cplx) * M * N, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(dA); cudaFree(dB); cudaFree(dC);
+    return DQMC_OK;
+}
+
+// ---- Monte Carlo -------------------------------------------------------------------------------
+int dqmc_update_slice(dqmc_ctx* ctx, uint32_t k, int thermalization, uint32_t* n_accepted) {
+    if (!ctx || k < 1 || (int)k > ctx->m) return DQMC_ERR_PARAM;
+    RET(upload_rng_window(ctx, size_t(ctx->N) * (ctx->opdim + 1)));
+    RET(launch_update(ctx, (int)k, thermalization));
+    if (n_accepted)
+        CK(cudaMemcpyAsync(ctx->h_acc, ctx->accepted, sizeof(uint32_t) * ctx->R, cudaMemcpyDeviceToHost, ctx->stream));
+    RET(finish_rng_window(ctx));
+    if (n_accepted) std::memcpy(n_accepted, ctx->h_acc, sizeof(uint32_t) * ctx->R);
+    return DQMC_OK;
+}
+
+int dqmc_global_shift_move(dqmc_ctx* ctx, int32_t* accepted) {
+    if (!ctx) return DQMC_ERR_PARAM;
+    RET(global_shift_move(ctx, accepted));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return DQMC_OK;
+}
+
+int dqmc_phi_action(dqmc_ctx* ctx, double* out) {
+    if (!ctx || !out) return DQMC_ERR_PARAM;
+    CKL(launch_phi_action(ctx->phi, ctx->rvals, ctx->actions, ctx->p.L, ctx->opdim, ctx->m, ctx->p.dtau, ctx->p.c,
+                          ctx->p.u, (long long)phi_stride(ctx), ctx->R, ctx->stream));
+    CK(cudaMemcpyAsync(out, ctx->actions, sizeof(double) * ctx->R, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return DQMC_OK;
+}
+
+int dqmc_sweep(dqmc_ctx* ctx, int thermalization) {
+    if (!ctx) return DQMC_ERR_PARAM;
+    if (ctx->lastSweepDir == +1) {
+        // globalMove() before a down-sweep, detmodel.h:1422-1424 + detsdwopdim.cpp:3460-3485
+        if (ctx->p.globalShift && (ctx->performedSweeps % ctx->p.globalUpdateInterval == 0))
+            RET(global_shift_move(ctx, nullptr));
+        RET(upload_rng_window(ctx, ctx->rngCap));
+        RET(sweep_down(ctx, thermalization));
+        ctx->lastSweepDir = -1;
+    } else {
+        RET(upload_rng_window(ctx, ctx->rngCap));
+        RET(sweep_up(ctx, thermalization));
+        ctx->lastSweepDir = +1;
+    }
+    RET(finish_rng_window(ctx));
+    ctx->performedSweeps += 1;
+    return DQMC_OK;
+}
+
+// ---- replica exchange --------------------------------------------------------------------------
+int dqmc_exchange_actions(dqmc_ctx* ctx, double* actions_dev, double* actions_host) {
+    if (!ctx) return DQMC_ERR_PARAM;
+    double* dst = actions_dev ? actions_dev : ctx->actions;
+    CKL(launch_exchange_action(ctx->phi, dst, ctx->N, ctx->opdim, ctx->m, ctx->p.dtau, (long long)phi_stride(ctx),
+                               ctx->R, ctx->stream));
+    if (actions_host) {
+        CK(cudaMemcpyAsync(actions_host, dst, sizeof(double) * ctx->R, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return DQMC_OK;
+}
+
+double dqmc_exchange_probability(double par1, double action1, double par2, double action2) {
+    const double delta = (par1 - par2) * (action2 - action1);
+    return delta <= 0.0 ? 1.0 : std::exp(-delta);
+}
+
+int dqmc_exchange_walk(int n, const double* control_values, int32_t* par_process, int32_t* process_par,
+                       const double* actions, const double* uniforms, int32_t* n_used, int32_t* swapped) {
+    if (n < 1 || !control_values || !par_process || !process_par || !actions || !n_used) return DQMC_ERR_PARAM;
+    int used = 0;
+    for (int cpi1 = 0; cpi1 < n - 1; ++cpi1) {
+        const int cpi2 = cpi1 + 1;
+        const int p1 = par_process[cpi1], p2 = par_process[cpi2];
+        const double prob = dqmc_exchange_probability(control_values[cpi1], actions[p1], control_values[cpi2], actions[p2]);
+        bool acc = prob >= 1.0;
+        if (!acc) {
+            if (!uniforms) return DQMC_ERR_PARAM;
+            acc = uniforms[used++] <= prob;
+        }
+        if (acc) {
+            process_par[p1] = cpi2;
+            process_par[p2] = cpi1;
+            par_process[cpi1] = p2;
+            par_process[cpi2] = p1;
+        }
+        if (swapped) swapped[cpi1] = acc ? 1 : 0;
+    }
+    *n_used = used;
+    return DQMC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,220 @@
+// Internal declarations shared by the CUDA translation units of libdqmc_b200.so.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/dqmc_gpu.h"
+#include "rng_stream.h"
+
+namespace dqmc {
+
+typedef double2 cplx;
+
+// ------------------------------------------------------------------------------------------------
+// Checkerboard / B-matrix multiply (cb_kernels.cu)
+// ------------------------------------------------------------------------------------------------
+struct CbGeom {
+    int L, N, msf, D, nplaq, opdim;
+    int m;                 // slices
+    double lambda_dtau;    // lambda * dtau (only used when tables are rebuilt on device)
+};
+
+// One launch applies a chain of single-slice factors to every vector (column or row) of a batch
+// of D x D matrices.
+struct CbLaunch {
+    cplx* A;               // [batch][D*D] in place
+    long long strideA;     // elements between consecutive matrices
+    const double* phi;     // [batch][(m+1)*opdim*N]
+    const double* coshT;   // [batch][(m+1)*N]
+    const double* sinhT;   // [batch][(m+1)*N]
+    long long stridePhi, strideTab;
+    const cplx* cbtab;     // plaquette tables, see cb_table_index()
+    int kfirst, kstep, kcount;   // slices kfirst, kfirst+kstep, ...
+    int rows;              // 0: vectors are columns (left multiply), 1: vectors are rows (right multiply)
+    int k_then_v;          // 1: hopping stage first, then potential stage; 0: the other order
+    int sign_idx;          // 0: e^{-dtau .} (B), 1: e^{+dtau .} (B^-1)
+    int transposed;        // 0: M v, 1: M^T v (right multiplies act on rows)
+    const double* colscale;  // optional [batch][D]: scale vector v (column v) by colscale[v] on store
+    long long strideScale;
+    int batch;
+};
+
+int cb_table_count(const CbGeom& g);                    // number of cplx in the table
+// host-side construction of the plaquette tables from the model parameters
+void cb_build_tables(const dqmc_params& p, std::vector<cplx>& out);
+cudaError_t cb_launch(const CbGeom& g, const CbLaunch& a, cudaStream_t st);
+
+// dense elementwise helpers (misc_kernels.cu)
+cudaError_t launch_set_identity(cplx* A, int D, long long stride, int batch, cudaStream_t st);
+cudaError_t launch_conj_transpose(const cplx* A, cplx* B, int D, long long stride, int batch, cudaStream_t st);
+cudaError_t launch_max_abs_diff(const cplx* A, const cplx* B, int D, long long stride, int batch,
+                                double* out, cudaStream_t st);
+cudaError_t launch_update_tables(const double* phi, double* coshT, double* sinhT, int N, int opdim, int m,
+                                 double lambda_dtau, long long stridePhi, long long strideTab, int batch,
+                                 cudaStream_t st);
+cudaError_t launch_shift_fields(double* phi, const double* shift, int N, int opdim, int m,
+                                long long stridePhi, int batch, cudaStream_t st);
+cudaError_t launch_phi_action(const double* phi, const double* rvals, double* out, int L, int opdim, int m,
+                              double dtau, double c, double u, long long stridePhi, int batch,
+                              cudaStream_t st);
+cudaError_t launch_exchange_action(const double* phi, double* out, int N, int opdim, int m, double dtau,
+                                   long long stridePhi, int batch, cudaStream_t st);
+
+// ------------------------------------------------------------------------------------------------
+// Batched complex GEMM on FP64 tensor cores (gemm_kernels.cu)
+//   C = rowscale .* (op(A) * diag(kscale) * op(B)) .* colscale + beta * C
+// ------------------------------------------------------------------------------------------------
+struct GemmArgs {
+    int M, N, K;
+    int transa, transb;           // 0: N, 1: conjugate transpose
+    const cplx* A; int lda; long long strideA;
+    const cplx* B; int ldb; long long strideB;
+    cplx* C; int ldc; long long strideC;
+    const double* rowscale; long long strideRow;   // optional, length M
+    const double* colscale; long long strideCol;   // optional, length N
+    const double* kscale; long long strideK;       // optional, length K
+    double beta;                  // 0 or 1
+    int batch;
+};
+cudaError_t gemm_launch(const GemmArgs& g, cudaStream_t st);
+
+// ------------------------------------------------------------------------------------------------
+// Pivoted Householder QR and friends (qr_kernels.cu)
+// ------------------------------------------------------------------------------------------------
+// In place: A -> R in the upper triangle, Householder vectors below; tau[D]; perm[D] with
+// A_in[:, perm[j]] = (Q R)[:, j].
+cudaError_t qrcp_factor_launch(cplx* A, int D, long long strideA, cplx* tau, int* perm, double* colnorm,
+                               int batch, cudaStream_t st);
+// Q (explicit D x D) from the factored A / tau.
+cudaError_t qr_form_q_launch(const cplx* A, const cplx* tau, cplx* Q, int D, long long strideA, int batch,
+                             cudaStream_t st);
+// d[i] = |R[i,i]|,  T[i, perm[j]] = R[i,j] / d[i] (j >= i), 0 elsewhere.
+cudaError_t qr_extract_dt_launch(const cplx* A, const int* perm, double* d, cplx* T, int D, long long strideA,
+                                 int batch, cudaStream_t st);
+// Solve R Z = Y for upper-triangular R (from a factored A), writing row j of Z to row perm[j] of Zout
+// (perm may be null = identity).  Y is overwritten.
+cudaError_t trsm_upper_launch(const cplx* A, cplx* Y, cplx* Zout, const int* perm, int D, long long strideA,
+                              int batch, cudaStream_t st);
+// split scales: big[i] = 1/max(d,1), small[i] = min(d,1); also sum log max(d,1) -> logacc (+=)
+cudaError_t scale_split_launch(const double* d, double* inv_big, double* small_, double* logacc, int D,
+                               int batch, cudaStream_t st);
+cudaError_t logdiag_accumulate_launch(const cplx* A, double* logacc, int D, long long strideA, int batch,
+                                      cudaStream_t st);
+
+// ------------------------------------------------------------------------------------------------
+// Delayed local updates (update_kernels.cu)
+// ------------------------------------------------------------------------------------------------
+struct UpdateModel {
+    int L, N, msf, D, opdim, m;
+    int delaySteps;
+    double dtau, c, u, lambda, accRatio;
+};
+struct UpdateArgs {
+    cplx* G; long long strideG;
+    double* phi; double* coshT; double* sinhT;
+    long long stridePhi, strideTab;
+    const double* rvals;          // [batch] exchange parameter r
+    cplx* X; cplx* Y;             // delayed-update workspaces [batch][D*KMAX]
+    long long strideXY;
+    const double* rng;            // [batch][rngWindow]
+    long long strideRng;
+    int rngWindow;
+    int* cursor;                  // [batch] read position in the window
+    dqmc_control_data* ctrl;      // [batch] step size + running average (device copy)
+    uint32_t* accepted;           // [batch] accepted proposals in this slice
+    int* errflag;                 // device error flag (rng window overrun, NaN)
+    int k;                        // time slice
+    int thermalization;
+    int batch;
+};
+cudaError_t update_slice_launch(const UpdateModel& m, const UpdateArgs& a, cudaStream_t st);
+
+}  // namespace dqmc
+
+// ------------------------------------------------------------------------------------------------
+// The context
+// ------------------------------------------------------------------------------------------------
+struct dqmc_ctx {
+    dqmc_params p;
+    int R;                 // replicas
+    int N, D, msf, m, s, n, ngc, opdim;
+    int nmat;              // R * ngc matrices per batched operator
+    int device;
+    cudaStream_t stream;
+    bool own_stream;
+    std::string err;
+    uint64_t launches;
+
+    // sweep state (detmodel.h:463, 481; detsdwopdim.h performedSweeps)
+    int currentTimeslice;
+    int lastSweepDir;      // +1 up, -1 down
+    int performedSweeps;
+
+    dqmc::CbGeom geom;
+    dqmc::UpdateModel umodel;
+
+    // device buffers
+    dqmc::cplx* G;         // [nmat][D*D]
+    dqmc::cplx* Gwrapped;  // copy of G before an advance (green consistency)
+    dqmc::cplx* W[4];      // scratch [nmat][D*D]
+    dqmc::cplx* tQ; dqmc::cplx* tT; double* tD;   // temporary UDT of an advance step
+    dqmc::cplx* eyeM; double* onesV;              // shared identity UDT (batch stride 0)
+    dqmc::cplx* stQ;       // UDT storage [nmat][n+1][D*D]
+    dqmc::cplx* stT;
+    double* stD;           // [nmat][n+1][D]
+    dqmc::cplx* bkQ;       // backups for the global move (swapped by pointer)
+    dqmc::cplx* bkT;
+    double* bkD;
+    dqmc::cplx* bkG;
+    double* bkPhi; double* bkCosh; double* bkSinh;
+    double* phi;           // [R][(m+1)*opdim*N]
+    double* coshT; double* sinhT;   // [R][(m+1)*N]
+    double* rvals;         // [R]
+    dqmc::cplx* cbtab;
+    dqmc::cplx* tau;       // [nmat][D]
+    int* perm;             // [nmat][D]
+    double* colnorm;       // [nmat][D]
+    double* vecA; double* vecB; double* vecC; double* vecD;   // [nmat][D] scale vectors
+    double* dtmp;          // [nmat][D]
+    double* logdet;        // [nmat] log|det G^-1| from the last from-scratch evaluation
+    double* bkLogdet;
+    double* consistency;   // [nmat]
+    dqmc::cplx* X; dqmc::cplx* Y;   // [R][D*KMAX]
+    int kmax;
+    double* rngbuf;        // [R][rngCap]
+    size_t rngCap;
+    int* cursor;           // [R]
+    int rngWindow;         // number of values per replica in the uploaded window
+    dqmc_control_data* ctrl;      // [R] device
+    uint32_t* accepted;    // [R]
+    int* errflag;
+    double* actions;       // [R]
+    double* shiftbuf;      // [R][3]
+
+    // pinned host staging
+    double* h_rng;         // [R][rngCap]
+    int* h_cursor;
+    double* h_scalars;     // generic staging [max(R*8, ...)]
+    dqmc_control_data* h_ctrl;
+    int* h_err;
+    uint32_t* h_acc;
+    std::vector<double> lastGlobalProb;
+
+    // Hubbard
+    int32_t* aux;          // [R][(m+1)*N]
+    dqmc::cplx* propT;     // e^{-dtau T} as complex D x D
+    dqmc::cplx* propTinv;
+    double* hubScale;      // [nmat][D] scratch row/col scales
+
+    std::vector<dqmc::RngStream> rng;
+    std::vector<double> h_r;
+    std::vector<dqmc_control_data> ctrl_host;
+
+    // which storage entries hold a left chain (B(beta,tau) = T^+ d Q^+) vs right chain (Q d T)
+    // is implied by the sweep direction exactly as in the reference; nothing to track.
+};

@@ -1,0 +1,217 @@
+// Batched complex GEMM on the FP64 tensor-core path of sm_100a (DMMA, mma.sync m8n8k4.f64).
+//
+// Replaces every dense `*` on D x D matrices in the stabilisation path of the reference
+// (Armadillo -> zgemm): the UdV chain products (detmodel.h:699-700, 983-987, 1141-1143), the five
+// products of greenFromUdV (detmodel.h:784-815) and, for DetHubbard, the dense B-matrix products
+// (dethubbard.h:299-337).  tcgen05 has no f64 kind; on Blackwell FP64 matrix math is the warp-level
+// mma.sync DMMA path (SASS: DMMA.8x8x4).
+//
+//   C = rowscale .* ( op(A) * diag(kscale) * op(B) ) .* colscale + beta * C,   op = N | conj-transpose
+//
+// Complex arithmetic = 4 real DMMAs per k-step on planar (re / im) shared-memory tiles; the planar
+// split, the conjugation, the transposition and the three diagonal scalings are fused into the
+// global->shared load and the epilogue, so no intermediate matrices are materialised.
+// One CTA computes a (8*MB*WM) x (8*NB*WN) tile, one warp an (8*MB) x (8*NB) sub-tile of DMMA blocks.
+// Bound: FP64 tensor pipe.  Algorithmic flops: 8 * M * N * K per matrix.
+#include "dqmc_internal.h"
+
+namespace dqmc {
+namespace {
+
+constexpr int BK = 8;
+
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+template <int WM, int WN, int MB, int NB>
+struct GemmCfg {
+    static constexpr int TM = 8 * MB * WM, TN = 8 * NB * WN;
+    static constexpr int LDM = TM + 8, LDN = TN + 8;        // == 8 (mod 16): conflict-free fragment loads
+    static constexpr int NT = 32 * WM * WN;
+    static constexpr int A_PER = (TM * BK + NT - 1) / NT;
+    static constexpr int B_PER = (TN * BK + NT - 1) / NT;
+    static constexpr int SMEM_DOUBLES = 2 * (2 * BK * LDM + 2 * BK * LDN);   // two stages, re+im
+};
+
+template <int WM, int WN, int MB, int NB>
+__global__ void __launch_bounds__(32 * WM * WN) zgemm_dmma_kernel(GemmArgs g) {
+    typedef GemmCfg<WM, WN, MB, NB> C;
+    extern __shared__ __align__(16) double smem[];
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int wm = warp % WM, wn = warp / WM;
+    const int grp = lane >> 2, t4 = lane & 3;
+    const int b = blockIdx.z;
+    const int m0 = blockIdx.x * C::TM, n0 = blockIdx.y * C::TN;
+
+    const cplx* __restrict__ A = g.A + size_t(b) * g.strideA;
+    const cplx* __restrict__ B = g.B + size_t(b) * g.strideB;
+    const double* __restrict__ ks = g.kscale ? g.kscale + size_t(b) * g.strideK : nullptr;
+
+    double acc_re[MB][NB][2], acc_im[MB][NB][2];
+#pragma unroll
+    for (int i = 0; i < MB; ++i)
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+            acc_re[i][j][0] = acc_re[i][j][1] = 0.0;
+            acc_im[i][j][0] = acc_im[i][j][1] = 0.0;
+        }
+
+    cplx ra[C::A_PER], rb[C::B_PER];
+
+    auto load_tiles = [&](int k0) {
+#pragma unroll
+        for (int i = 0; i < C::A_PER; ++i) {
+            const int idx = tid + i * C::NT;
+            cplx v = make_double2(0, 0);
+            if (idx < C::TM * BK) {
+                int mm, kk;
+                if (!g.transa) { mm = idx % C::TM; kk = idx / C::TM; }
+                else { kk = idx % BK; mm = idx / BK; }
+                const int gm = m0 + mm, gk = k0 + kk;
+                if (gm < g.M && gk < g.K) {
+                    if (!g.transa) v = A[size_t(gk) * g.lda + gm];
+                    else { v = A[size_t(gm) * g.lda + gk]; v.y = -v.y; }
+                    if (ks) { const double sc = ks[gk]; v.x *= sc; v.y *= sc; }
+                }
+            }
+            ra[i] = v;
+        }
+#pragma unroll
+        for (int i = 0; i < C::B_PER; ++i) {
+            const int idx = tid + i * C::NT;
+            cplx v = make_double2(0, 0);
+            if (idx < C::TN * BK) {
+                int nn, kk;
+                if (!g.transb) { kk = idx % BK; nn = idx / BK; }
+                else { nn = idx % C::TN; kk = idx / C::TN; }
+                const int gn = n0 + nn, gk = k0 + kk;
+                if (gn < g.N && gk < g.K) {
+                    if (!g.transb) v = B[size_t(gn) * g.ldb + gk];
+                    else { v = B[size_t(gk) * g.ldb + gn]; v.y = -v.y; }
+                }
+            }
+            rb[i] = v;
+        }
+    };
+    auto store_tiles = [&](int stage) {
+        double* As_re = smem + stage * (C::SMEM_DOUBLES / 2);
+        double* As_im = As_re + BK * C::LDM;
+        double* Bs_re = As_im + BK * C::LDM;
+        double* Bs_im = Bs_re + BK * C::LDN;
+#pragma unroll
+        for (int i = 0; i < C::A_PER; ++i) {
+            const int idx = tid + i * C::NT;
+            if (idx < C::TM * BK) {
+                int mm, kk;
+                if (!g.transa) { mm = idx % C::TM; kk = idx / C::TM; }
+                else { kk = idx % BK; mm = idx / BK; }
+                As_re[kk * C::LDM + mm] = ra[i].x;
+                As_im[kk * C::LDM + mm] = ra[i].y;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < C::B_PER; ++i) {
+            const int idx = tid + i * C::NT;
+            if (idx < C::TN * BK) {
+                int nn, kk;
+                if (!g.transb) { kk = idx % BK; nn = idx / BK; }
+                else { nn = idx % C::TN; kk = idx / C::TN; }
+                Bs_re[kk * C::LDN + nn] = rb[i].x;
+                Bs_im[kk * C::LDN + nn] = rb[i].y;
+            }
+        }
+    };
+
+    const int nk = (g.K + BK - 1) / BK;
+    load_tiles(0);
+    store_tiles(0);
+    __syncthreads();
+
+    for (int kt = 0; kt < nk; ++kt) {
+        const int stage = kt & 1;
+        if (kt + 1 < nk) load_tiles((kt + 1) * BK);          // global loads in flight during the math
+        const double* As_re = smem + stage * (C::SMEM_DOUBLES / 2);
+        const double* As_im = As_re + BK * C::LDM;
+        const double* Bs_re = As_im + BK * C::LDM;
+        const double* Bs_im = Bs_re + BK * C::LDN;
+#pragma unroll
+        for (int k4 = 0; k4 < BK; k4 += 4) {
+            double ar[MB], ai[MB], nai[MB], br[NB], bi[NB];
+#pragma unroll
+            for (int mb = 0; mb < MB; ++mb) {
+                const int off = (k4 + t4) * C::LDM + wm * (8 * MB) + mb * 8 + grp;
+                ar[mb] = As_re[off];
+                ai[mb] = As_im[off];
+                nai[mb] = -ai[mb];
+            }
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb) {
+                const int off = (k4 + t4) * C::LDN + wn * (8 * NB) + nb * 8 + grp;
+                br[nb] = Bs_re[off];
+                bi[nb] = Bs_im[off];
+            }
+#pragma unroll
+            for (int mb = 0; mb < MB; ++mb)
+#pragma unroll
+                for (int nb = 0; nb < NB; ++nb) {
+                    dmma(acc_re[mb][nb][0], acc_re[mb][nb][1], ar[mb], br[nb]);
+                    dmma(acc_re[mb][nb][0], acc_re[mb][nb][1], nai[mb], bi[nb]);
+                    dmma(acc_im[mb][nb][0], acc_im[mb][nb][1], ar[mb], bi[nb]);
+                    dmma(acc_im[mb][nb][0], acc_im[mb][nb][1], ai[mb], br[nb]);
+                }
+        }
+        if (kt + 1 < nk) store_tiles(stage ^ 1);
+        __syncthreads();
+    }
+
+    // ---- epilogue
+    cplx* __restrict__ Cm = g.C + size_t(b) * g.strideC;
+    const double* __restrict__ rs = g.rowscale ? g.rowscale + size_t(b) * g.strideRow : nullptr;
+    const double* __restrict__ cs = g.colscale ? g.colscale + size_t(b) * g.strideCol : nullptr;
+#pragma unroll
+    for (int mb = 0; mb < MB; ++mb) {
+        const int gm = m0 + wm * (8 * MB) + mb * 8 + grp;
+        if (gm >= g.M) continue;
+        const double rsc = rs ? rs[gm] : 1.0;
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int gn = n0 + wn * (8 * NB) + nb * 8 + 2 * t4 + e;
+                if (gn >= g.N) continue;
+                const double sc = rsc * (cs ? cs[gn] : 1.0);
+                cplx v = make_double2(acc_re[mb][nb][e] * sc, acc_im[mb][nb][e] * sc);
+                cplx* dst = Cm + size_t(gn) * g.ldc + gm;
+                if (g.beta != 0.0) { const cplx o = *dst; v.x += o.x; v.y += o.y; }
+                *dst = v;
+            }
+    }
+}
+
+template <int WM, int WN, int MB, int NB>
+cudaError_t launch_cfg(const GemmArgs& g, cudaStream_t st) {
+    typedef GemmCfg<WM, WN, MB, NB> C;
+    const size_t smem = C::SMEM_DOUBLES * sizeof(double);
+    cudaError_t e = cudaFuncSetAttribute(zgemm_dmma_kernel<WM, WN, MB, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem);
+    if (e != cudaSuccess) return e;
+    dim3 grid((g.M + C::TM - 1) / C::TM, (g.N + C::TN - 1) / C::TN, g.batch);
+    zgemm_dmma_kernel<WM, WN, MB, NB><<<grid, C::NT, smem, st>>>(g);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t gemm_launch(const GemmArgs& g, cudaStream_t st) {
+    if (g.batch <= 0 || g.M <= 0 || g.N <= 0) return cudaSuccess;
+    // 96 x 96 tiles when they fit the problem exactly (D = 288), otherwise 64 x 64
+    if (g.M % 96 == 0 && g.N % 96 == 0) return launch_cfg<4, 3, 3, 4>(g, st);   // 12 warps, 24 x 32 each
+    if (g.M <= 32 || g.N <= 32) return launch_cfg<1, 1, 4, 4>(g, st);
+    return launch_cfg<2, 2, 4, 4>(g, st);
+}
+
+}  // namespace dqmc

@@ -1,0 +1,323 @@
+"""Host-side mirror of the reference's model interface for the DQMC sweep hot path.
+
+`DetSDWBatch` plays the role of DetSDW<CB_ASSAAD_BERG, OPDIM> (detsdwopdim.h:62-153) for a batch of
+replicas resident on one GPU; method names follow the reference (sweep, sweepThermalization,
+get_exchange_action_contribution, set_exchange_parameter_value, get/set_control_data ...).  All
+numerics happen in libdqmc_b200.so through the C ABI; this file only marshals NumPy buffers.
+
+`ReplicaExchangeLadder` plays the role of DetQMCPT::replicaExchangeStep (detqmcpt.h:962-1118) with
+replicas partitioned contiguously over ranks: one all-gather of (action, look-ahead uniforms of
+replica 0) per exchange step, then the identical serial ladder walk on every rank.
+"""
+import ctypes
+
+import numpy as np
+
+from .lib import load_library, DqmcParams, ControlData, DqmcError, c_i32, c_vp, c_f64
+
+OP_LEFT, OP_RIGHT, OP_LEFT_INV, OP_RIGHT_INV, OP_LEFT_ADJ = range(5)
+
+_DEFAULTS = dict(opdim=2, L=4, m=20, s=10, dtau=0.1, r=-1.0, c=3.0, u=1.0, lam=1.0, txhor=-1.0, txver=-0.5,
+                 tyhor=0.5, tyver=1.0, cdwU=0.0, mu=-0.5, accRatio=0.5, weakZflux=True, bc=0, updateMethod=2,
+                 delaySteps=16, globalShift=True, globalUpdateInterval=10, repeatUpdateInSlice=1,
+                 seed=1020304050, rngIndex=1)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(c_vp)
+
+
+def make_params(pars=None, **kw):
+    """Build the C struct from an object / dict with the reference's parameter names
+    (ModelParamsDetSDW, detsdwparams.h:30-120).  Unsupported settings raise, as check() does."""
+    d = dict(_DEFAULTS)
+    if pars is not None:
+        src = pars if isinstance(pars, dict) else vars(pars)
+        d.update({k: v for k, v in src.items() if k in d})
+    d.update(kw)
+    if d["cdwU"] != 0.0:
+        raise DqmcError("cdwU != 0 is outside the accelerated path")
+    if d["updateMethod"] not in (1, 2):
+        raise DqmcError("updateMethod must be 'woodbury' (1) or 'delayed' (2)")
+    if d["repeatUpdateInSlice"] != 1:
+        raise DqmcError("repeatUpdateInSlice != 1 is outside the accelerated path")
+    p = DqmcParams()
+    p.model = 0
+    p.opdim, p.L, p.m, p.s, p.bc = d["opdim"], d["L"], d["m"], d["s"], d["bc"]
+    p.weakZflux = int(bool(d["weakZflux"]))
+    p.delaySteps = d["delaySteps"] if d["updateMethod"] == 2 else 1     # woodbury == delayed with 1 step
+    p.globalShift = int(bool(d["globalShift"]))
+    p.globalUpdateInterval = d["globalUpdateInterval"]
+    p.dtau, p.r, p.c, p.u, p.lambda_ = d["dtau"], d["r"], d["c"], d["u"], d["lam"]
+    p.txhor, p.txver, p.tyhor, p.tyver = d["txhor"], d["txver"], d["tyhor"], d["tyver"]
+    p.mux = p.muy = d["mu"]
+    p.accRatio = d["accRatio"]
+    return p, d
+
+
+class DetSDWBatch:
+    """A batch of DetSDW replicas on one B200."""
+
+    def __init__(self, pars=None, n_replicas=1, device=0, rng_indices=None, r_values=None, init="random",
+                 stream=None, **kw):
+        self.lib = load_library()
+        self.cpars, self.pars = make_params(pars, **kw)
+        self.R = int(n_replicas)
+        h = c_vp()
+        rc = self.lib.dqmc_create(ctypes.byref(self.cpars), self.R, int(device), ctypes.byref(h))
+        self.h = h
+        if rc != 0:
+            msg = self.lib.dqmc_last_error(h).decode() if h else "dqmc_create failed"
+            if h:
+                self.lib.dqmc_destroy(h)
+                self.h = None
+            raise DqmcError(msg)
+        dims = (c_i32 * 8)()
+        self._ck(self.lib.dqmc_dims(self.h, dims))
+        self.N, self.D, self.m, self.n, self.s, self.ngc, _, self.opdim = list(dims)
+        if stream is not None:
+            self.set_stream(stream)
+        if rng_indices is None:
+            rng_indices = [self.pars["rngIndex"] + i for i in range(self.R)]
+        for rep, idx in enumerate(rng_indices):
+            self._ck(self.lib.dqmc_rng_seed(self.h, rep, self.pars["seed"], int(idx)))
+        if r_values is not None:
+            for rep, r in enumerate(r_values):
+                self.set_exchange_parameter_value(r, rep)
+        if init == "random":
+            # createReplica -> ctor: setupRandomField, then setupUdVStorage_and_calculateGreen
+            for rep in range(self.R):
+                self._ck(self.lib.dqmc_init_random_fields(self.h, rep))
+            self.setup_storage()
+
+    # ------------------------------------------------------------------ plumbing
+    def _ck(self, rc):
+        if rc != 0:
+            raise DqmcError(self.lib.dqmc_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.dqmc_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream_ptr):
+        self._ck(self.lib.dqmc_set_stream(self.h, c_vp(int(cuda_stream_ptr) if cuda_stream_ptr else None)))
+
+    def synchronize(self):
+        self._ck(self.lib.dqmc_synchronize(self.h))
+
+    @property
+    def launch_count(self):
+        return int(self.lib.dqmc_launch_count(self.h))
+
+    # ------------------------------------------------------------------ state
+    def phi(self, rep=0):
+        out = np.zeros((self.m + 1, self.opdim, self.N))
+        self._ck(self.lib.dqmc_download_fields(self.h, rep, _ptr(out)))
+        return out
+
+    def set_phi(self, phi, rep=0):
+        phi = np.ascontiguousarray(phi, dtype=np.float64)
+        assert phi.shape == (self.m + 1, self.opdim, self.N)
+        self._ck(self.lib.dqmc_upload_fields(self.h, rep, _ptr(phi)))
+
+    def green(self, rep=0):
+        out = np.zeros((self.D, self.D), dtype=np.complex128, order="F")
+        self._ck(self.lib.dqmc_download_green(self.h, rep, 0, _ptr(out)))
+        return out
+
+    def set_green(self, g, rep=0):
+        g = np.asfortranarray(g, dtype=np.complex128)
+        self._ck(self.lib.dqmc_upload_green(self.h, rep, 0, _ptr(g)))
+
+    def logdet(self, rep=0):
+        out = c_f64()
+        self._ck(self.lib.dqmc_logdet(self.h, rep, 0, ctypes.byref(out)))
+        return out.value
+
+    def control_data(self, rep=0):
+        cd = ControlData()
+        self._ck(self.lib.dqmc_get_control_data(self.h, rep, ctypes.byref(cd)))
+        return cd
+
+    def set_control_data(self, cd, rep=0):
+        self._ck(self.lib.dqmc_set_control_data(self.h, rep, ctypes.byref(cd)))
+
+    def phi_delta(self, rep=0):
+        return self.control_data(rep).phiDelta
+
+    def sweep_state(self):
+        out = (c_i32 * 3)()
+        self._ck(self.lib.dqmc_get_sweep_state(self.h, out))
+        return dict(currentTimeslice=out[0], lastSweepDir=out[1], performedSweeps=out[2])
+
+    # ------------------------------------------------------------------ RNG
+    def rng_draw(self, n, rep=0):
+        out = np.zeros(n)
+        self._ck(self.lib.dqmc_rng_draw(self.h, rep, n, _ptr(out)))
+        return out
+
+    def rng_peek(self, n, rep=0):
+        out = np.zeros(n)
+        self._ck(self.lib.dqmc_rng_peek(self.h, rep, n, _ptr(out)))
+        return out
+
+    def rng_skip(self, n, rep=0):
+        self._ck(self.lib.dqmc_rng_skip(self.h, rep, n))
+
+    # ------------------------------------------------------------------ operators
+    def bmat_mult(self, op, A, k2, k1, rep=0):
+        a = np.array(A, dtype=np.complex128, order="F", copy=True)
+        self._ck(self.lib.dqmc_bmat_mult(self.h, rep, 0, op, _ptr(a), k2, k1))
+        return a
+
+    def setup_storage(self):
+        """setupUdVStorage_and_calculateGreen (detmodel.h:678-713)."""
+        self._ck(self.lib.dqmc_setup_storage(self.h))
+
+    def wrap_up(self, k):
+        self._ck(self.lib.dqmc_wrap_up(self.h, k))
+
+    def wrap_down(self, k):
+        self._ck(self.lib.dqmc_wrap_down(self.h, k))
+
+    def advance_up(self, l):
+        self._ck(self.lib.dqmc_advance_up(self.h, l))
+
+    def advance_down(self, l):
+        self._ck(self.lib.dqmc_advance_down(self.h, l))
+
+    def green_consistency(self):
+        out = np.zeros(self.R)
+        self._ck(self.lib.dqmc_get_green_consistency(self.h, _ptr(out)))
+        return out
+
+    def green_for_timeslice(self, k, rep=0):
+        out = np.zeros((self.D, self.D), dtype=np.complex128, order="F")
+        self._ck(self.lib.dqmc_green_for_timeslice(self.h, rep, 0, k, _ptr(out)))
+        return out
+
+    def green_from_udt(self, Qr, dr, Tr, Ql, dl, Tl):
+        f = lambda a: np.asfortranarray(a, dtype=np.complex128)
+        Qr, Tr, Ql, Tl = f(Qr), f(Tr), f(Ql), f(Tl)
+        dr = np.ascontiguousarray(dr, dtype=np.float64)
+        dl = np.ascontiguousarray(dl, dtype=np.float64)
+        G = np.zeros((self.D, self.D), dtype=np.complex128, order="F")
+        ld = c_f64()
+        self._ck(self.lib.dqmc_green_from_udt_host(self.h, _ptr(Qr), _ptr(dr), _ptr(Tr), _ptr(Ql), _ptr(dl),
+                                                   _ptr(Tl), _ptr(G), ctypes.byref(ld)))
+        return G, ld.value
+
+    def udt_decompose(self, M):
+        M = np.asfortranarray(M, dtype=np.complex128)
+        Q = np.zeros_like(M, order="F")
+        T = np.zeros_like(M, order="F")
+        d = np.zeros(self.D)
+        self._ck(self.lib.dqmc_udt_decompose_host(self.h, _ptr(M), _ptr(Q), _ptr(d), _ptr(T)))
+        return Q, d, T
+
+    def gemm(self, A, B, transa=False, transb=False):
+        A = np.asfortranarray(A, dtype=np.complex128)
+        B = np.asfortranarray(B, dtype=np.complex128)
+        M = A.shape[1] if transa else A.shape[0]
+        K = A.shape[0] if transa else A.shape[1]
+        N = B.shape[0] if transb else B.shape[1]
+        C = np.zeros((M, N), dtype=np.complex128, order="F")
+        self._ck(self.lib.dqmc_gemm_host(self.h, int(transa), int(transb), M, N, K, _ptr(A), _ptr(B), _ptr(C)))
+        return C
+
+    # ------------------------------------------------------------------ Monte Carlo
+    def update_in_slice(self, k, thermalization=False):
+        """updateInSlice(k) for every replica; returns the accepted counts."""
+        acc = np.zeros(self.R, dtype=np.uint32)
+        self._ck(self.lib.dqmc_update_slice(self.h, k, int(thermalization), _ptr(acc)))
+        return acc
+
+    def global_shift_move(self):
+        acc = np.zeros(self.R, dtype=np.int32)
+        self._ck(self.lib.dqmc_global_shift_move(self.h, _ptr(acc)))
+        return acc
+
+    def phi_action(self):
+        out = np.zeros(self.R)
+        self._ck(self.lib.dqmc_phi_action(self.h, _ptr(out)))
+        return out
+
+    def sweep(self, takeMeasurements=False):
+        if takeMeasurements:
+            raise DqmcError("fermionic measurements are outside the accelerated path (SURVEY 8f)")
+        self._ck(self.lib.dqmc_sweep(self.h, 0))
+
+    def sweepThermalization(self):
+        self._ck(self.lib.dqmc_sweep(self.h, 1))
+
+    # ------------------------------------------------------------------ replica exchange interface
+    def get_exchange_parameter_value(self, rep=0):
+        out = c_f64()
+        self._ck(self.lib.dqmc_get_exchange_parameter(self.h, rep, ctypes.byref(out)))
+        return out.value
+
+    def set_exchange_parameter_value(self, r, rep=0):
+        self._ck(self.lib.dqmc_set_exchange_parameter(self.h, rep, float(r)))
+
+    def get_exchange_action_contribution(self, device_ptr=None):
+        out = np.zeros(self.R)
+        self._ck(self.lib.dqmc_exchange_actions(self.h, c_vp(device_ptr) if device_ptr else None, _ptr(out)))
+        return out
+
+
+def exchange_walk(control_values, par_process, process_par, actions, uniforms):
+    """Serial ladder walk (detqmcpt.h:1031-1079) through the C ABI; returns (n_used, swapped)."""
+    lib = load_library()
+    cv = np.ascontiguousarray(control_values, dtype=np.float64)
+    ac = np.ascontiguousarray(actions, dtype=np.float64)
+    un = np.ascontiguousarray(uniforms, dtype=np.float64)
+    n = len(cv)
+    used = c_i32()
+    swapped = np.zeros(max(n - 1, 1), dtype=np.int32)
+    rc = lib.dqmc_exchange_walk(n, _ptr(cv), _ptr(par_process), _ptr(process_par), _ptr(ac), _ptr(un),
+                                ctypes.byref(used), _ptr(swapped))
+    if rc != 0:
+        raise DqmcError("dqmc_exchange_walk failed")
+    return used.value, swapped[:n - 1]
+
+
+class ReplicaExchangeLadder:
+    """Replica-exchange bookkeeping over `world` ranks, `n_local` replicas each (contiguous
+    partition of the ladder).  `gather(vec)` must return the concatenation of every rank's vector in
+    rank order (torch.distributed all_gather in production, identity for one rank)."""
+
+    def __init__(self, control_values, n_local, rank=0, world=1, gather=None):
+        self.values = np.ascontiguousarray(control_values, dtype=np.float64)
+        self.P = len(self.values)
+        assert self.P == n_local * world
+        self.n_local, self.rank, self.world = n_local, rank, world
+        self.gather = gather if gather is not None else (lambda v: v)
+        self.par_process = np.arange(self.P, dtype=np.int32)     # current_par_process
+        self.process_par = np.arange(self.P, dtype=np.int32)     # current_process_par
+        self.proposed = np.zeros(self.P - 1, dtype=np.int64)
+        self.accepted = np.zeros(self.P - 1, dtype=np.int64)
+
+    def local_parameters(self):
+        lo = self.rank * self.n_local
+        return self.values[self.process_par[lo:lo + self.n_local]]
+
+    def step(self, local_actions, uniforms_of_replica0):
+        """local_actions: [n_local]; uniforms_of_replica0: P-1 look-ahead values of global replica 0's
+        stream (only rank 0's are used).  Returns (n_uniforms_used, old process->par map)."""
+        payload = np.concatenate([np.asarray(local_actions, dtype=np.float64),
+                                  np.asarray(uniforms_of_replica0, dtype=np.float64)])
+        allp = np.asarray(self.gather(payload)).reshape(self.world, -1)
+        actions = np.ascontiguousarray(allp[:, :self.n_local].reshape(-1))
+        uniforms = np.ascontiguousarray(allp[0, self.n_local:])
+        old = self.process_par.copy()
+        used, swapped = exchange_walk(self.values, self.par_process, self.process_par, actions, uniforms)
+        self.proposed += 1
+        self.accepted += swapped
+        return used, old

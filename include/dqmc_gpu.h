@@ -1,0 +1,224 @@
+/*
+ * dqmc_gpu.h -- C ABI of the B200-native DQMC sweep hot path (libdqmc_b200.so).
+ *
+ * This is the lower seam described in SURVEY.md section 8(b): an `extern "C"` layer with an opaque
+ * context, int status codes, plain pointers and sizes.  A context owns a BATCH of replicas that
+ * live on one GPU (struct-of-arrays in HBM); every operator below acts on all replicas of the
+ * batch at once unless it takes a `rep` index.  All calls are ordered on the context's CUDA stream
+ * and a context must be driven from one host thread at a time (same contract as the reference:
+ * one thread per replica, no re-entrancy; detqmc.h:183-218).
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to the reference's
+ * src/ directory).  The reference has no FFI of its own -- models are C++ template parameters --
+ * so "replaces" means: the C++ shim in detqmc_b200/csrc/detsdw_gpu.h implements the reference's
+ * Model duck-type (detqmc.h:183-218, 441-491; detqmcpt.h:316, 857-900, 971-1115) by calling
+ * these functions.  See INTEGRATION.md for the binding a maintainer would add.
+ *
+ * Matrix layout: column-major, complex numbers interleaved (re, im) as in Armadillo's
+ * Mat<std::complex<double>>, so buffers can be handed to/from the reference without conversion.
+ * Field layout: phi[(m+1)][OPDIM][N] doubles == memory of arma::Cube<double>(N, OPDIM, m+1)
+ * (detsdwopdim.h:455-461); slice k = 0 is unused.
+ *
+ * Status codes: 0 = ok; non-zero = error, text available from dqmc_last_error().  The C++ shim
+ * turns a non-zero status into the reference's GeneralError exception (exceptions.h).
+ */
+#ifndef DQMC_GPU_H_
+#define DQMC_GPU_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dqmc_ctx dqmc_ctx;
+
+enum { DQMC_OK = 0, DQMC_ERR_PARAM = 1, DQMC_ERR_CUDA = 2, DQMC_ERR_STATE = 3, DQMC_ERR_NUMERIC = 4 };
+
+enum { DQMC_MODEL_SDW = 0, DQMC_MODEL_HUBBARD = 1 };
+
+/* B-matrix operator selector for dqmc_bmat_mult*: B = B(k2, k1) = B_{k2} ... B_{k1+1}. */
+enum {
+    DQMC_OP_LEFT = 0,      /* B * A        leftMultiplyBmat     detsdwopdim.cpp:2074-2090 */
+    DQMC_OP_RIGHT = 1,     /* A * B        rightMultiplyBmat    detsdwopdim.cpp:2305-2324 */
+    DQMC_OP_LEFT_INV = 2,  /* B^-1 * A     leftMultiplyBmatInv  detsdwopdim.cpp:2170-2186 */
+    DQMC_OP_RIGHT_INV = 3, /* A * B^-1     rightMultiplyBmatInv detsdwopdim.cpp:2404-2420 */
+    DQMC_OP_LEFT_ADJ = 4   /* B^dagger * A (used by the left-chain stabilisation; no reference twin) */
+};
+
+/* Model parameters: the fields of ModelParamsDetSDW (detsdwparams.h:30-120) and
+ * ModelParams<DetHubbard> (dethubbardparams.h:25-60) that the hot path reads.  The exchange
+ * parameter r is per replica (dqmc_set_exchange_parameter). */
+typedef struct dqmc_params {
+    int32_t model;                /* DQMC_MODEL_* */
+    int32_t opdim;                /* SDW: 1, 2, 3 */
+    int32_t L;                    /* linear lattice size, N = L*L */
+    int32_t m;                    /* number of time slices */
+    int32_t s;                    /* stabilisation interval */
+    int32_t bc;                   /* SDW: 0 pbc, 1 apbc-x, 2 apbc-y, 3 apbc-xy */
+    int32_t weakZflux;            /* SDW: weakest magnetic flux (O(1), O(2) only) */
+    int32_t delaySteps;           /* SDW: delayed-update block size (1 == Woodbury) */
+    int32_t globalShift;          /* SDW: attempt global shift moves */
+    int32_t globalUpdateInterval; /* SDW: every # sweeps */
+    int32_t checkerboard;         /* Hubbard: checkerboard form of e^{-dtau T} (dethubbard.cpp:768-821) */
+    int32_t reserved0;
+    double dtau;
+    double r;                     /* SDW: initial value of the exchange parameter for all replicas */
+    double c, u, lambda;          /* SDW bosonic action + coupling */
+    double txhor, txver, tyhor, tyver;
+    double mux, muy;              /* SDW chemical potentials (the reference sets both to mu) */
+    double accRatio;              /* SDW: target acceptance for the box-size adaptation */
+    double t, U, mu;              /* Hubbard */
+} dqmc_params;
+
+/* Per-replica control data that follows the exchange parameter in a replica exchange
+ * (UpdateStatistics + AdjustmentData, detsdwopdim.h:283-300, 479-560; blob exchanged by
+ * get/set_control_data, detsdwopdim.cpp:5218-5242). */
+typedef struct dqmc_control_data {
+    double phiDelta;
+    double lastAccRatioLocal_phi;
+    double ra_average;            /* RunningAverage state of accRatioLocal_box_RA */
+    int32_t ra_samples_added;
+    int32_t ra_count;             /* number of valid entries in ra_values */
+    double ra_values[100];
+    uint32_t acceptedGlobalShifts;
+    uint32_t attemptedGlobalShifts;
+} dqmc_control_data;
+
+/* ---- lifecycle ------------------------------------------------------------------------------ */
+
+/* Replaces createReplica(...) (detsdwopdim.cpp:48-84, dethubbard.cpp:30-43) for a batch of
+ * n_replicas on CUDA device `device`.  Fails (never falls back to a CPU path) when no device. */
+int dqmc_create(const dqmc_params* params, int n_replicas, int device, dqmc_ctx** out);
+void dqmc_destroy(dqmc_ctx* ctx);
+const char* dqmc_last_error(const dqmc_ctx* ctx);
+/* Use an existing CUDA stream (cudaStream_t) for all work of this context; NULL = own stream. */
+int dqmc_set_stream(dqmc_ctx* ctx, void* cuda_stream);
+int dqmc_synchronize(dqmc_ctx* ctx);
+/* out[0..7] = {N, D (Green's-function dimension), m, n, s, n_green_components, n_replicas, opdim} */
+int dqmc_dims(const dqmc_ctx* ctx, int32_t* out);
+/* Number of kernels launched by this context so far (for bench.py's gpu_launches). */
+uint64_t dqmc_launch_count(const dqmc_ctx* ctx);
+
+/* ---- random numbers: RngWrapper (rngwrapper.h:43-119) ---------------------------------------- */
+
+/* Seed replica `rep`'s stream exactly like RngWrapper(seed, processIndex) (rngwrapper.cpp:30-50). */
+int dqmc_rng_seed(dqmc_ctx* ctx, int rep, uint32_t seed, uint32_t process_index);
+/* Alternatively feed the stream from the host program's own generator (e.g. the reference's
+ * RngWrapper): fill(user, out, n) must write the next n rand01() values. */
+typedef void (*dqmc_rng_fill_fn)(void* user, double* out, size_t n);
+int dqmc_rng_set_source(dqmc_ctx* ctx, int rep, dqmc_rng_fill_fn fill, void* user);
+/* Consume n values from the head of replica rep's stream (rand01()). */
+int dqmc_rng_draw(dqmc_ctx* ctx, int rep, size_t n, double* out);
+/* Look at the next n values without consuming them / consume n values. */
+int dqmc_rng_peek(dqmc_ctx* ctx, int rep, size_t n, double* out);
+int dqmc_rng_skip(dqmc_ctx* ctx, int rep, size_t n);
+/* Total number of values consumed from replica rep's stream so far. */
+uint64_t dqmc_rng_consumed(const dqmc_ctx* ctx, int rep);
+
+/* ---- state ----------------------------------------------------------------------------------- */
+
+/* setupRandomField (detsdwopdim.cpp:1098-1113) / setupRandomAuxfield (dethubbard.cpp:741-751):
+ * draws the initial configuration from the replica's stream in the reference's order. */
+int dqmc_init_random_fields(dqmc_ctx* ctx, int rep);
+/* phi (SDW; doubles) or auxfield (Hubbard; int32 +-1, layout [(m+1)][N]).  Host pointers. */
+int dqmc_upload_fields(dqmc_ctx* ctx, int rep, const void* fields);
+int dqmc_download_fields(dqmc_ctx* ctx, int rep, void* fields);
+/* g / green[gc] (detmodel.h:462): D*D values (complex interleaved for SDW, real for Hubbard). */
+int dqmc_download_green(dqmc_ctx* ctx, int rep, int gc, double* out);
+int dqmc_upload_green(dqmc_ctx* ctx, int rep, int gc, const double* in);
+/* get/set_exchange_parameter_value (detsdwopdim.cpp:5189-5197). */
+int dqmc_set_exchange_parameter(dqmc_ctx* ctx, int rep, double r);
+int dqmc_get_exchange_parameter(dqmc_ctx* ctx, int rep, double* r);
+/* get/set_control_data (detsdwopdim.cpp:5218-5242). */
+int dqmc_get_control_data(dqmc_ctx* ctx, int rep, dqmc_control_data* out);
+int dqmc_set_control_data(dqmc_ctx* ctx, int rep, const dqmc_control_data* in);
+/* out = {currentTimeslice, lastSweepDir (+1 up, -1 down), performedSweeps} (detmodel.h:463,481). */
+int dqmc_get_sweep_state(const dqmc_ctx* ctx, int32_t* out);
+
+/* ---- operators (each one is parity-tested in isolation) -------------------------------------- */
+
+/* checkerboard{Left,Right}MultiplyBmat[Inv](A, k2, k1) on a host matrix of replica rep, in place
+ * (detsdwopdim.cpp:2074-2420); Hubbard: the dense functors of dethubbard.h:281-337. */
+int dqmc_bmat_mult(dqmc_ctx* ctx, int rep, int gc, int op, double* A_host, uint32_t k2, uint32_t k1);
+/* Same on device memory for the whole batch: A_dev = [n_replicas][D*D] values, in place. */
+int dqmc_bmat_mult_device(dqmc_ctx* ctx, int gc, int op, void* A_dev, uint32_t k2, uint32_t k1);
+/* Batched device-to-device copy of the operator's input for benchmarking: times `reps`
+ * back-to-back launches of op on A_dev and returns the average kernel time in ms. */
+int dqmc_bench_bmat_mult(dqmc_ctx* ctx, int op, void* A_dev, uint32_t k2, uint32_t k1, int reps,
+                         float* ms_per_launch);
+
+/* setupUdVStorage_and_calculateGreen (detmodel.h:678-713): rebuilds the stabilisation storage
+ * from the fields and computes G(beta) for every replica; currentTimeslice = m, lastSweepDir = Up. */
+int dqmc_setup_storage(dqmc_ctx* ctx);
+/* wrapUpGreen(k): G(k+1) = B_{k+1} G(k) B_{k+1}^-1 (detmodel.h:1234-1259). */
+int dqmc_wrap_up(dqmc_ctx* ctx, uint32_t k);
+/* wrapDownGreen(k): G(k-1) = B_k^-1 G(k) B_k (detmodel.h:1064-1095). */
+int dqmc_wrap_down(dqmc_ctx* ctx, uint32_t k);
+/* advanceUpGreen(l) / advanceDownGreen(l) (detmodel.h:1106-1163 / 953-1017). */
+int dqmc_advance_up(dqmc_ctx* ctx, uint32_t l);
+int dqmc_advance_down(dqmc_ctx* ctx, uint32_t l);
+/* max_ij |G_wrapped - G_advanced| recorded by the last advance (the reference's
+ * --logGreenConsistency check, detmodel.h:993-1010); one value per replica. */
+int dqmc_get_green_consistency(dqmc_ctx* ctx, double* out);
+/* log|det G^-1| of replica rep's current G as computed by the last from-scratch evaluation;
+ * equals sum_j log(green_inv_sv[j]) of the reference (detsdwopdim.cpp:3613-3620). */
+int dqmc_logdet(dqmc_ctx* ctx, int rep, int gc, double* out);
+/* G at an arbitrary slice from scratch into a host buffer, leaving the sweep state untouched
+ * (computeGreenFromScratch, detsdwopdim.cpp:4905-4933). */
+int dqmc_green_for_timeslice(dqmc_ctx* ctx, int rep, int gc, uint32_t k, double* out);
+/* Numerical kernel under greenFromUdV (detmodel.h:768-818): G = [1 + M_r M_l]^-1 for two host
+ * D x D matrices given as M_r = Q_r diag(d_r) T_r and M_l = T_l^dagger diag(d_l) Q_l^dagger
+ * (all column-major; see DESIGN.md "UDT").  Test surface. */
+int dqmc_green_from_udt_host(dqmc_ctx* ctx, const double* Qr, const double* dr, const double* Tr,
+                             const double* Ql, const double* dl, const double* Tl,
+                             double* G_out, double* logdet_out);
+/* Pivoted-QR "UDT" factorisation of a host D x D matrix: M = Q diag(d) T (udvDecompose's role,
+ * udv.h:68-90).  Test surface. */
+int dqmc_udt_decompose_host(dqmc_ctx* ctx, const double* M, double* Q, double* d, double* T);
+/* Batched C = op(A) op(B) on host matrices through the FP64 tensor-core GEMM.  Test surface.
+ * transa/transb: 0 = N, 1 = conjugate transpose. */
+int dqmc_gemm_host(dqmc_ctx* ctx, int transa, int transb, int M, int N, int K,
+                   const double* A, const double* B, double* C);
+
+/* ---- Monte Carlo updates ---------------------------------------------------------------------- */
+
+/* updateInSlice(k) / updateInSliceThermalization(k) for every replica
+ * (detsdwopdim.cpp:2427-2489, 3021-3175, 3293-3375; dethubbard.cpp:141-171).  Random numbers are
+ * taken from each replica's stream in the reference's order; n_accepted (may be NULL) receives
+ * the per-replica number of accepted proposals. */
+int dqmc_update_slice(dqmc_ctx* ctx, uint32_t k, int thermalization, uint32_t* n_accepted);
+/* attemptGlobalShiftMove() (detsdwopdim.cpp:3564-3645) for every replica; requires
+ * currentTimeslice == m.  accepted (may be NULL): per-replica 0/1. */
+int dqmc_global_shift_move(dqmc_ctx* ctx, int32_t* accepted);
+/* phiAction() (detsdwopdim.cpp:4242-4299) per replica. */
+int dqmc_phi_action(dqmc_ctx* ctx, double* out);
+
+/* sweep(takeMeasurements=false) / sweepThermalization() for every replica of the batch
+ * (detsdwopdim.cpp:4422-4502 -> detmodel.h:1401-1478): one direction (down or up) including
+ * the global move before a down-sweep. */
+int dqmc_sweep(dqmc_ctx* ctx, int thermalization);
+
+/* ---- replica exchange ------------------------------------------------------------------------- */
+
+/* get_exchange_action_contribution() (detsdwopdim.cpp:5204-5216) of every local replica.
+ * actions_dev (may be NULL): device buffer of n_replicas doubles -- the NCCL all-gather send
+ * buffer; actions_host (may be NULL): host copy. */
+int dqmc_exchange_actions(dqmc_ctx* ctx, double* actions_dev, double* actions_host);
+/* get_replica_exchange_probability (detsdwopdim.cpp:5251-5264). */
+double dqmc_exchange_probability(double par1, double action1, double par2, double action2);
+/* Serial ladder walk of DetQMCPT::replicaExchangeStep on the gathered actions
+ * (detqmcpt.h:1031-1079).  n = ladder length; par_process / process_par are updated in place;
+ * uniforms[0..n-2] are the next values of replica 0's stream (dqmc_rng_peek), *n_used returns how
+ * many were consumed (dqmc_rng_skip that many on the owner); swapped[cpi] = 1 if the pair
+ * (cpi, cpi+1) was exchanged. */
+int dqmc_exchange_walk(int n, const double* control_values, int32_t* par_process,
+                       int32_t* process_par, const double* actions, const double* uniforms,
+                       int32_t* n_used, int32_t* swapped);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* DQMC_GPU_H_ */

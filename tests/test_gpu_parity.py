@@ -1,0 +1,296 @@
+"""GPU parity tests (run on the B200 box): every operator of the C ABI against the CPU oracle
+(oracle/dqmc_oracle.py, pinned to the reference) and against the golden vectors generated from the
+unmodified reference (tests/golden, tools/make_golden.py).
+
+Tolerances: the north star asks for G, log-determinants and acceptance ratios within 1e-10
+relative (FP64) and identical accept/reject trajectories; operators that are plain sums of
+products are held to 1e-12."""
+import numpy as np
+import pytest
+
+from helpers import load_golden, sdw_params_of, maxabs, relerr
+
+pytestmark = pytest.mark.gpu
+
+SDW_CASES = ["sdw_o2_flux_L4", "sdw_o2_noflux_apbcxy_L4", "sdw_o3_L4", "sdw_o1_apbcx_L4",
+             "sdw_o2_flux_L4_delay3_s7", "sdw_o2_flux_L6"]
+
+TOL_G = 1e-10
+
+
+def make_batch(p, **kw):
+    from detqmc_b200 import DetSDWBatch
+    return DetSDWBatch(p, n_replicas=kw.pop("n_replicas", 1), **kw)
+
+
+def rand_cplx(shape, seed):
+    g = np.random.default_rng(seed)
+    return g.standard_normal(shape) + 1j * g.standard_normal(shape)
+
+
+# ------------------------------------------------------------------------------------------------
+def test_library_refuses_without_fallback():
+    """The product path must fail loudly rather than fall back: a bogus device id is an error."""
+    from detqmc_b200 import DetSDWBatch, DqmcError
+    from dqmc_oracle import SdwParams
+    with pytest.raises(DqmcError):
+        DetSDWBatch(SdwParams(), n_replicas=1, device=4096)
+
+
+@pytest.mark.parametrize("shape", [(288, 288, 288), (128, 128, 128), (100, 37, 53), (32, 32, 32), (196, 784, 64)])
+@pytest.mark.parametrize("trans", [(False, False), (True, False), (False, True), (True, True)])
+def test_gemm_dmma(shape, trans):
+    from dqmc_oracle import SdwParams
+    b = make_batch(SdwParams(), init="none")
+    M, N, K = shape
+    ta, tb = trans
+    A = rand_cplx((K, M) if ta else (M, K), 1)
+    B = rand_cplx((N, K) if tb else (K, N), 2)
+    ref = (A.conj().T if ta else A) @ (B.conj().T if tb else B)
+    C = b.gemm(A, B, ta, tb)
+    assert relerr(C, ref) < 1e-13
+
+
+@pytest.mark.parametrize("name", SDW_CASES)
+def test_bmat_mult_vs_golden(name):
+    g = load_golden(name)
+    p = sdw_params_of(g)
+    b = make_batch(p)
+    assert maxabs(b.phi(), g["phi0"]) == 0.0          # same dSFMT stream, same construction order
+    A = g["A"]
+    k2, k1 = [int(v) for v in g["chain"]]
+    for op in range(4):
+        r1 = g["bmult_op%d_single" % op]
+        rc = g["bmult_op%d_chain" % op]
+        assert relerr(b.bmat_mult(op, A, 3, 2), r1) < 1e-12, (name, op)
+        assert relerr(b.bmat_mult(op, A, k2, k1), rc) < 1e-12, (name, op)
+
+
+@pytest.mark.parametrize("name", ["sdw_o2_flux_L4", "sdw_o3_L4"])
+def test_bmat_adjoint_and_inverse_identities(name):
+    from dqmc_oracle import SdwOracle
+    g = load_golden(name)
+    p = sdw_params_of(g)
+    o = SdwOracle(p)
+    b = make_batch(p)
+    A = g["A"]
+    eye = np.eye(o.sz, dtype=np.complex128)
+    Bd = o.left_multiply_bmat(0, eye, 9, 4)
+    assert relerr(b.bmat_mult(4, A, 9, 4), Bd.conj().T @ A) < 1e-12          # LEFT_ADJ
+    back = b.bmat_mult(2, b.bmat_mult(0, A, 9, 4), 9, 4)                     # B^-1 (B A) = A
+    assert relerr(back, A) < 1e-12
+    back = b.bmat_mult(3, b.bmat_mult(1, A, 9, 4), 9, 4)                     # (A B) B^-1 = A
+    assert relerr(back, A) < 1e-12
+
+
+@pytest.mark.parametrize("name", ["sdw_o2_flux_L4", "sdw_o3_L4", "sdw_o2_flux_L6"])
+def test_udt_decompose(name):
+    g = load_golden(name)
+    p = sdw_params_of(g)
+    b = make_batch(p, init="none")
+    D = b.D
+    # graded matrix like the ones in the chain: (random) * diag(scales over 20 decades)
+    M = rand_cplx((D, D), 5) * np.logspace(8, -12, D)[None, :]
+    Q, d, T = b.udt_decompose(M)
+    assert maxabs(Q.conj().T @ Q, np.eye(D)) < 1e-13
+    assert np.all(d > 0) and np.all(np.diff(d) <= 1e-12 * d[:-1])           # pivoting sorts |R_ii|
+    rec = (Q * d[None, :]) @ T
+    colnorm = np.linalg.norm(M, axis=0)
+    assert np.max(np.linalg.norm(rec - M, axis=0) / colnorm) < 1e-12        # column-wise backward error
+    # T = D^-1 R P^T: row-wise |T_ij| <= ~1 after pivoting
+    assert np.abs(T).max() < 1.0 + 1e-12
+
+
+@pytest.mark.parametrize("name", ["sdw_o2_flux_L4", "sdw_o3_L4", "sdw_o2_flux_L6"])
+def test_green_from_udt_vs_reference(name):
+    g = load_golden(name)
+    p = sdw_params_of(g)
+    b = make_batch(p, init="none")
+    # reference UdV (M = U d V_t^+): right chain Q d T with T = V_t^+, left chain T^+ d Q^+ with
+    # T = U^+, Q = V_t
+    Qr, dr, Tr = g["udv1_U"], g["udv1_d"], g["udv1_V"].conj().T
+    Ql, dl, Tl = g["udv2_V"], g["udv2_d"], g["udv2_U"].conj().T
+    G, logdet = b.green_from_udt(Qr, dr, Tr, Ql, dl, Tl)
+    ref = g["green_from_udv_l2_r1"]
+    assert relerr(G, ref) < TOL_G
+    ref_logdet = np.log(g["sv_from_udv_l2_r1"]).sum()
+    assert abs(logdet - ref_logdet) < 1e-10 * max(1.0, abs(ref_logdet))
+
+
+@pytest.mark.parametrize("name", SDW_CASES)
+def test_setup_green_and_logdet(name):
+    g = load_golden(name)
+    p = sdw_params_of(g)
+    b = make_batch(p)
+    assert relerr(b.green(), g["green0"]) < TOL_G
+    ref_logdet = np.log(g["sv0"]).sum()
+    assert abs(b.logdet() - ref_logdet) < 1e-10 * abs(ref_logdet)
+    assert abs(b.phi_action()[0] - float(g["phiAction0"])) < 1e-10 * abs(float(g["phiAction0"]))
+    assert abs(b.get_exchange_action_contribution()[0] - float(g["exchangeAction0"])) < 1e-11 * float(g["exchangeAction0"])
+    assert relerr(b.green_for_timeslice(3), g["green_slice_3"]) < TOL_G
+    s = int(p.s)
+    assert relerr(b.green_for_timeslice(s), g["green_slice_%d" % s]) < TOL_G
+
+
+@pytest.mark.parametrize("name", ["sdw_o2_flux_L4", "sdw_o3_L4", "sdw_o2_flux_L4_delay3_s7"])
+def test_wrap_and_advance_without_updates(name):
+    """The stabilised skeleton alone: a full down- and up-sweep with no field updates, G compared
+    with the oracle after every wrap and every advance."""
+    from dqmc_oracle import SdwOracle
+    g = load_golden(name)
+    p = sdw_params_of(g)
+    o = SdwOracle(p)
+    b = make_batch(p)
+    n, s, m = o.n, o.s, o.m
+    worst = 0.0
+
+    def check():
+        nonlocal worst
+        worst = max(worst, relerr(b.green(), o.green[0]))
+
+    for k in range(m, (n - 1) * s, -1):
+        o.wrap_down_green(k, 0); b.wrap_down(k); check()
+    for l in range(n - 1, 0, -1):
+        o.advance_down_green(l + 1, 0); b.advance_down(l + 1); check()
+        for k in range(l * s, (l - 1) * s, -1):
+            o.wrap_down_green(k, 0); b.wrap_down(k); check()
+    o.advance_down_green(1, 0); b.advance_down(1); check()
+    assert b.green_consistency()[0] < 1e-9
+    # up-sweep (sweepUp resets storage[0] to the identity UdV; advance_up(0) does the same)
+    from dqmc_oracle import UdV
+    o.storage[0][0] = UdV.eye(o.sz, o.dtype)
+    for l in range(0, n - 1):
+        for k in range(l * s + 1, (l + 1) * s + 1):
+            o.wrap_up_green(k - 1, 0); b.wrap_up(k - 1); check()
+        o.advance_up_green(l, 0); b.advance_up(l); check()
+    for k in range((n - 1) * s + 1, m + 1):
+        o.wrap_up_green(k - 1, 0); b.wrap_up(k - 1); check()
+    o.advance_up_green(n - 1, 0); b.advance_up(n - 1); check()
+    assert b.green_consistency()[0] < 1e-9
+    assert worst < TOL_G
+
+
+@pytest.mark.parametrize("name", ["sdw_o2_flux_L4", "sdw_o3_L4", "sdw_o1_apbcx_L4", "sdw_o2_flux_L4_delay3_s7"])
+def test_update_in_slice_vs_oracle(name):
+    from dqmc_oracle import SdwOracle
+    g = load_golden(name)
+    p = sdw_params_of(g)
+    o = SdwOracle(p)
+    o.decisions = []
+    b = make_batch(p)
+    acc = b.update_in_slice(p.m)
+    ratio = o.update_in_slice(p.m)
+    assert acc[0] == round(ratio * p.N)
+    assert maxabs(b.phi()[1:], o.phi[1:]) < 1e-13
+    assert relerr(b.green(), o.green[0]) < TOL_G
+    assert b.rng_draw(4)[0] == o.rng.rand01()           # same number of values consumed
+
+
+@pytest.mark.parametrize("name", SDW_CASES)
+def test_sweeps_vs_golden(name):
+    g = load_golden(name)
+    p = sdw_params_of(g)
+    b = make_batch(p)
+    n = int(g["n_sweeps"])
+    for sw in range(n):
+        b.sweepThermalization()
+        cd = b.control_data()
+        assert cd.lastAccRatioLocal_phi == g["lastAccRatio"][sw], (name, sw)
+        assert cd.acceptedGlobalShifts == g["acceptedGlobalShifts"][sw], (name, sw)
+        assert abs(cd.phiDelta - g["phiDelta"][sw]) < 1e-14
+        key = "phi_after_%d" % (sw + 1)
+        if key in g.files:
+            assert maxabs(b.phi()[1:], g[key][1:]) < 1e-12
+            assert relerr(b.green(), g["green_after_%d" % (sw + 1)]) < TOL_G
+    assert maxabs(b.phi()[1:], g["phi_final"][1:]) < 1e-12
+    assert np.array_equal(b.rng_draw(8), g["rng_next"])
+
+
+def test_trajectory_100_sweeps():
+    """Identical accept/reject trajectory over the first 100 sweeps with the same dSFMT seed."""
+    g = load_golden("sdw_o2_flux_L4_traj100")
+    p = sdw_params_of(g)
+    b = make_batch(p)
+    for sw in range(100):
+        b.sweepThermalization()
+        cd = b.control_data()
+        assert cd.lastAccRatioLocal_phi == g["lastAccRatio"][sw], sw
+        assert cd.acceptedGlobalShifts == g["acceptedGlobalShifts"][sw], sw
+    assert abs(b.phi_delta() - g["phiDelta"][-1]) < 1e-13
+    assert maxabs(b.phi()[1:], g["phi_final"][1:]) < 1e-11
+    assert relerr(b.green(), g["green_final"]) < TOL_G
+    assert np.array_equal(b.rng_draw(8), g["rng_next"])
+
+
+def test_measurement_sweeps_do_not_adapt_step_size():
+    from dqmc_oracle import SdwOracle
+    g = load_golden("sdw_o2_flux_L4")
+    p = sdw_params_of(g)
+    o = SdwOracle(p)
+    b = make_batch(p)
+    for _ in range(3):
+        o.sweep(); b.sweep()
+        assert b.control_data().lastAccRatioLocal_phi == o.last_acc_ratio
+    assert b.phi_delta() == 0.5
+    assert maxabs(b.phi()[1:], o.phi[1:]) < 1e-12
+
+
+def test_batch_of_replicas_matches_single_replicas():
+    """Replicas of one batch are independent: each equals its own single-replica oracle run."""
+    from dqmc_oracle import SdwOracle, SdwParams
+    rs = [-1.5, -0.5, 0.3]
+    idx = [1, 2, 3]
+    base = dict(L=4, m=20, s=10)
+    b = make_batch(SdwParams(**base), n_replicas=3, rng_indices=idx, r_values=rs)
+    oracles = [SdwOracle(SdwParams(r=r, rngIndex=i, **base)) for r, i in zip(rs, idx)]
+    for _ in range(3):
+        b.sweepThermalization()
+        for o in oracles:
+            o.sweep_thermalization()
+    act = b.get_exchange_action_contribution()
+    for rep, o in enumerate(oracles):
+        assert maxabs(b.phi(rep)[1:], o.phi[1:]) < 1e-12
+        assert relerr(b.green(rep), o.green[0]) < TOL_G
+        assert abs(act[rep] - o.exchange_action()) < 1e-11 * o.exchange_action()
+        assert b.control_data(rep).lastAccRatioLocal_phi == o.last_acc_ratio
+
+
+def test_global_shift_move_vs_oracle():
+    from dqmc_oracle import SdwOracle
+    g = load_golden("sdw_o2_flux_L4")
+    p = sdw_params_of(g)
+    o = SdwOracle(p)
+    b = make_batch(p)
+    for _ in range(4):
+        o.attempt_global_shift_move()
+        acc = b.global_shift_move()
+        assert bool(acc[0]) == o.last_global_shift["accepted"]
+        assert maxabs(b.phi()[1:], o.phi[1:]) < 1e-13
+        assert relerr(b.green(), o.green[0]) < TOL_G
+        assert abs(b.logdet() - np.log(o.green_inv_sv[0]).sum()) < 1e-9
+
+
+# ---------------------------------------------------------------- full-size, size-independent checks
+@pytest.mark.parametrize("kw", [dict(L=12, m=100, s=10), dict(L=8, m=80, s=10)])
+def test_full_size_properties(kw):
+    """BASELINE configs C3 (one replica of the L=12, beta=10 ladder) and C2: properties that need no
+    oracle -- B^-1 B = 1, wrap up/down round trip, G (1 + B(beta,0)) = 1, wrapped == recomputed G."""
+    from dqmc_oracle import SdwParams
+    p = SdwParams(**kw)
+    b = make_batch(p, n_replicas=2, rng_indices=[1, 2])
+    D = b.D
+    A = rand_cplx((D, D), 3)
+    assert relerr(b.bmat_mult(2, b.bmat_mult(0, A, 17, 7), 17, 7), A) < 1e-11
+    assert relerr(b.bmat_mult(3, b.bmat_mult(1, A, 17, 7), 17, 7), A) < 1e-11
+    for rep in range(2):
+        G = b.green(rep)
+        GB = b.bmat_mult(1, G, p.m, 0, rep=rep)                     # G B(beta, 0)
+        assert maxabs(G + GB, np.eye(D)) < 1e-9
+    G0 = b.green(0)
+    b.wrap_down(p.m)
+    b.wrap_up(p.m - 1)
+    assert relerr(b.green(0), G0) < 1e-10
+    b.sweep()                                                       # a full down-sweep with updates
+    assert np.all(b.green_consistency() < 1e-8)                     # wrapped vs advanced G at the last advance
+    G = b.green(0)
+    assert maxabs(G, b.green_for_timeslice(0, rep=0)) < 1e-9        # G(0) after the sweep == from scratch

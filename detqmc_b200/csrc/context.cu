@@ -23,10 +23,23 @@ namespace {
         }                                                                                          \
     } while (0)
 
+// kernel launch: counted, and (in profiling mode) bracketed by events on the context's stream
 #define CKL(call)                                                                                  \
     do {                                                                                           \
         ctx->launches += 1;                                                                        \
-        CK(call);                                                                                  \
+        if (ctx->profiling) {                                                                      \
+            cudaEvent_t e0__ = prof_event(ctx), e1__ = prof_event(ctx);                            \
+            cudaEventRecord(e0__, ctx->stream);                                                    \
+            cudaError_t el__ = (call);                                                             \
+            cudaEventRecord(e1__, ctx->stream);                                                    \
+            ctx->profPending.push_back({prof_category(#call), e0__, e1__});                        \
+            if (el__ != cudaSuccess) {                                                             \
+                ctx->err = std::string(#call) + ": " + cudaGetErrorString(el__);                   \
+                return DQMC_ERR_CUDA;                                                              \
+            }                                                                                      \
+        } else {                                                                                   \
+            CK(call);                                                                              \
+        }                                                                                          \
     } while (0)
 
 #define RET(call)                                                                                  \
@@ -34,6 +47,41 @@ namespace {
         int r__ = (call);                                                                          \
         if (r__ != DQMC_OK) return r__;                                                            \
     } while (0)
+
+// profiling categories (dqmc_profile_get): one per kernel family
+const char* const kProfNames[DQMC_PROF_NCAT] = {"cb_mult", "gemm_dmma", "qrcp_factor", "qr_form_q", "trsm_upper",
+                                                "update_slice", "other"};
+int prof_category(const char* call) {
+    if (!std::strncmp(call, "cb_launch", 9)) return 0;
+    if (!std::strncmp(call, "gemm_launch", 11)) return 1;
+    if (!std::strncmp(call, "qrcp_factor", 11)) return 2;
+    if (!std::strncmp(call, "qr_form_q", 9)) return 3;
+    if (!std::strncmp(call, "trsm_upper", 10)) return 4;
+    if (!std::strncmp(call, "update_slice", 12)) return 5;
+    return 6;
+}
+cudaEvent_t prof_event(dqmc_ctx* ctx) {
+    if (!ctx->profPool.empty()) {
+        cudaEvent_t e = ctx->profPool.back();
+        ctx->profPool.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+void prof_collect(dqmc_ctx* ctx) {
+    for (auto& p : ctx->profPending) {
+        float ms = 0;
+        if (cudaEventSynchronize(p.e1) == cudaSuccess && cudaEventElapsedTime(&ms, p.e0, p.e1) == cudaSuccess) {
+            ctx->profMs[p.cat] += ms;
+            ctx->profCount[p.cat] += 1;
+        }
+        ctx->profPool.push_back(p.e0);
+        ctx->profPool.push_back(p.e1);
+    }
+    ctx->profPending.clear();
+}
 
 template <class T>
 cudaError_t dmalloc(T** p, size_t n) {
@@ -359,7 +407,9 @@ int wrap_down(dqmc_ctx* ctx, int k) {
 
 // ---- random-number window --------------------------------------------------------------------
 int upload_rng_window(dqmc_ctx* ctx, size_t per_replica) {
+    if (ctx->rngResident) { ctx->err = "release the resident random numbers first (dqmc_rng_release)"; return DQMC_ERR_STATE; }
     if (per_replica > ctx->rngCap) { ctx->err = "rng window larger than capacity"; return DQMC_ERR_STATE; }
+    ctx->rngStride = ctx->rngCap;
     for (int r = 0; r < ctx->R; ++r) {
         const double* src = ctx->rng[r].peek(per_replica);
         std::memcpy(ctx->h_rng + size_t(r) * ctx->rngCap, src, per_replica * sizeof(double));
@@ -383,11 +433,7 @@ int finish_rng_window(dqmc_ctx* ctx) {
     }
     for (int r = 0; r < ctx->R; ++r) {
         ctx->rng[r].skip((size_t)ctx->h_cursor[r]);
-        // counters of the global moves live on the host; everything else comes from the device
-        const uint32_t acc = ctx->ctrl_host[r].acceptedGlobalShifts, att = ctx->ctrl_host[r].attemptedGlobalShifts;
         ctx->ctrl_host[r] = ctx->h_ctrl[r];
-        ctx->ctrl_host[r].acceptedGlobalShifts = acc;
-        ctx->ctrl_host[r].attemptedGlobalShifts = att;
     }
     ctx->rngWindow = 0;
     return DQMC_OK;
@@ -400,7 +446,8 @@ int launch_update(dqmc_ctx* ctx, int k, int therm) {
     a.stridePhi = (long long)phi_stride(ctx); a.strideTab = (long long)tab_stride(ctx);
     a.rvals = ctx->rvals;
     a.X = ctx->X; a.Y = ctx->Y; a.strideXY = (long long)ctx->D * ctx->kmax;
-    a.rng = ctx->rngbuf; a.strideRng = (long long)ctx->rngCap; a.rngWindow = ctx->rngWindow;
+    a.rng = ctx->rngbuf; a.strideRng = (long long)ctx->rngStride; a.rngWindow = ctx->rngWindow;
+    a.acceptedTotal = ctx->acceptedTotal;
     a.cursor = ctx->cursor;
     a.ctrl = ctx->ctrl;
     a.accepted = ctx->accepted;
@@ -422,6 +469,23 @@ int upload_ctrl(dqmc_ctx* ctx) {
 int upload_rvals(dqmc_ctx* ctx) {
     CK(cudaMemcpyAsync(ctx->rvals, ctx->h_r.data(), sizeof(double) * ctx->R, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    return DQMC_OK;
+}
+
+// resident mode: bring the host streams up to date with the device cursors (needed before the host
+// itself draws, e.g. for a global move), and afterwards re-upload the window from the new head
+int sync_resident_cursor(dqmc_ctx* ctx) {
+    RET(finish_rng_window(ctx));
+    return DQMC_OK;
+}
+int reupload_resident(dqmc_ctx* ctx) {
+    const size_t per = ctx->rngStride;
+    for (int r = 0; r < ctx->R; ++r)
+        std::memcpy(ctx->h_rng + size_t(r) * per, ctx->rng[r].peek(per), per * sizeof(double));
+    CK(cudaMemcpyAsync(ctx->rngbuf, ctx->h_rng, per * ctx->R * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(ctx->cursor, 0, sizeof(int) * ctx->R, ctx->stream));
+    ctx->rngWindow = (int)per;
+    ctx->rngResidentUsedBound = 0;
     return DQMC_OK;
 }
 
@@ -491,6 +555,7 @@ int global_shift_move(dqmc_ctx* ctx, int32_t* accepted_out) {
         }
     }
     (void)D;
+    RET(upload_ctrl(ctx));           // the device copy of the control data carries the move counters too
     ctx->currentTimeslice = ctx->m;
     ctx->lastSweepDir = +1;
     return DQMC_OK;
@@ -575,6 +640,7 @@ int dqmc_create(const dqmc_params* params, int n_replicas, int device, dqmc_ctx*
     ctx->rngWindow = 0;
 
     int ndev = 0;
+    (void)cudaGetLastError();        // do not inherit a stale error from an earlier failed call
     CK(cudaGetDeviceCount(&ndev));
     if (device < 0 || device >= ndev) { ctx->err = "no such CUDA device (this library has no CPU fallback)"; return DQMC_ERR_CUDA; }
     CK(cudaSetDevice(device));
@@ -627,7 +693,14 @@ int dqmc_create(const dqmc_params* params, int n_replicas, int device, dqmc_ctx*
     CK(dmalloc(&ctx->X, D * ctx->kmax * R));
     CK(dmalloc(&ctx->Y, D * ctx->kmax * R));
     ctx->rngCap = size_t(ctx->m) * ctx->N * (p.opdim + 1);
+    ctx->rngAlloc = ctx->rngCap;
+    ctx->rngStride = ctx->rngCap;
+    ctx->rngResident = false;
+    ctx->rngResidentUsedBound = 0;
+    ctx->profiling = false;
     CK(dmalloc(&ctx->rngbuf, ctx->rngCap * R));
+    CK(dmalloc(&ctx->acceptedTotal, R));
+    CK(cudaMemsetAsync(ctx->acceptedTotal, 0, sizeof(unsigned long long) * R, ctx->stream));
     CK(dmalloc(&ctx->cursor, R));
     CK(dmalloc(&ctx->ctrl, R));
     CK(dmalloc(&ctx->accepted, R));
@@ -674,17 +747,21 @@ int dqmc_create(const dqmc_params* params, int n_replicas, int device, dqmc_ctx*
 
 void dqmc_destroy(dqmc_ctx* ctx) {
     if (!ctx) return;
-    cudaSetDevice(ctx->device);
-    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->stream) {
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+    }
     void* dev[] = {ctx->G, ctx->bkG, ctx->Gwrapped, ctx->W[0], ctx->W[1], ctx->W[2], ctx->W[3], ctx->tQ, ctx->tT, ctx->tD,
                    ctx->stQ, ctx->stT, ctx->stD, ctx->bkQ, ctx->bkT, ctx->bkD, ctx->phi, ctx->coshT, ctx->sinhT,
                    ctx->bkPhi, ctx->bkCosh, ctx->bkSinh, ctx->rvals, ctx->tau, ctx->perm, ctx->colnorm, ctx->vecA,
                    ctx->vecB, ctx->vecC, ctx->vecD, ctx->dtmp, ctx->logdet, ctx->bkLogdet, ctx->consistency, ctx->eyeM,
                    ctx->onesV, ctx->X, ctx->Y, ctx->rngbuf, ctx->cursor, ctx->ctrl, ctx->accepted, ctx->errflag,
-                   ctx->actions, ctx->shiftbuf, ctx->cbtab};
+                   ctx->actions, ctx->shiftbuf, ctx->cbtab, ctx->acceptedTotal};
     for (void* p : dev) if (p) cudaFree(p);
     void* host[] = {ctx->h_rng, ctx->h_cursor, ctx->h_scalars, ctx->h_ctrl, ctx->h_err, ctx->h_acc};
     for (void* p : host) if (p) cudaFreeHost(p);
+    prof_collect(ctx);
+    for (cudaEvent_t e : ctx->profPool) cudaEventDestroy(e);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -1029,20 +1106,95 @@ int dqmc_phi_action(dqmc_ctx* ctx, double* out) {
 
 int dqmc_sweep(dqmc_ctx* ctx, int thermalization) {
     if (!ctx) return DQMC_ERR_PARAM;
+    const bool resident = ctx->rngResident;
+    if (resident && size_t(ctx->rngWindow) < ctx->rngResidentUsedBound + ctx->rngCap + 8) {
+        ctx->err = "resident random-number window too small for another sweep";
+        return DQMC_ERR_STATE;
+    }
     if (ctx->lastSweepDir == +1) {
         // globalMove() before a down-sweep, detmodel.h:1422-1424 + detsdwopdim.cpp:3460-3485
-        if (ctx->p.globalShift && (ctx->performedSweeps % ctx->p.globalUpdateInterval == 0))
+        if (ctx->p.globalShift && (ctx->performedSweeps % ctx->p.globalUpdateInterval == 0)) {
+            if (resident) RET(sync_resident_cursor(ctx));     // the host draws must come after the device's
             RET(global_shift_move(ctx, nullptr));
-        RET(upload_rng_window(ctx, ctx->rngCap));
+            if (resident) RET(reupload_resident(ctx));
+        }
+        if (!resident) RET(upload_rng_window(ctx, ctx->rngCap));
         RET(sweep_down(ctx, thermalization));
         ctx->lastSweepDir = -1;
     } else {
-        RET(upload_rng_window(ctx, ctx->rngCap));
+        if (!resident) RET(upload_rng_window(ctx, ctx->rngCap));
         RET(sweep_up(ctx, thermalization));
         ctx->lastSweepDir = +1;
     }
-    RET(finish_rng_window(ctx));
+    if (!resident) RET(finish_rng_window(ctx));
+    else ctx->rngResidentUsedBound += ctx->rngCap;
     ctx->performedSweeps += 1;
+    return DQMC_OK;
+}
+
+// Resident random numbers: upload the next `n_sweeps` sweeps' worth of every replica's stream once;
+// sweeps then run without any host<->device traffic or synchronisation (cursors live on the
+// device).  dqmc_rng_release() reads the cursors back and advances the host streams.
+int dqmc_rng_preload(dqmc_ctx* ctx, int n_sweeps) {
+    if (!ctx || n_sweeps < 1) return DQMC_ERR_PARAM;
+    if (ctx->rngResident) RET(dqmc_rng_release(ctx));
+    const size_t per = ctx->rngCap * size_t(n_sweeps) + 16;
+    if (per > ctx->rngAlloc) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->rngbuf);
+        cudaFreeHost(ctx->h_rng);
+        ctx->rngbuf = nullptr; ctx->h_rng = nullptr;
+        CK(dmalloc(&ctx->rngbuf, per * ctx->R));
+        CK(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_rng), per * ctx->R * sizeof(double)));
+        ctx->rngAlloc = per;
+    }
+    ctx->rngStride = per;
+    for (int r = 0; r < ctx->R; ++r)
+        std::memcpy(ctx->h_rng + size_t(r) * per, ctx->rng[r].peek(per), per * sizeof(double));
+    CK(cudaMemcpyAsync(ctx->rngbuf, ctx->h_rng, per * ctx->R * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(ctx->cursor, 0, sizeof(int) * ctx->R, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->rngWindow = (int)per;
+    ctx->rngResident = true;
+    ctx->rngResidentUsedBound = 0;
+    return DQMC_OK;
+}
+
+int dqmc_rng_release(dqmc_ctx* ctx) {
+    if (!ctx) return DQMC_ERR_PARAM;
+    if (!ctx->rngResident) return DQMC_OK;
+    RET(finish_rng_window(ctx));
+    ctx->rngResident = false;
+    ctx->rngStride = ctx->rngCap;
+    return DQMC_OK;
+}
+
+int dqmc_profile_enable(dqmc_ctx* ctx, int on) {
+    if (!ctx) return DQMC_ERR_PARAM;
+    prof_collect(ctx);
+    ctx->profiling = on != 0;
+    for (int i = 0; i < DQMC_PROF_NCAT; ++i) { ctx->profMs[i] = 0; ctx->profCount[i] = 0; }
+    return DQMC_OK;
+}
+
+int dqmc_profile_get(dqmc_ctx* ctx, double* ms, uint64_t* counts) {
+    if (!ctx || !ms || !counts) return DQMC_ERR_PARAM;
+    CK(cudaStreamSynchronize(ctx->stream));
+    prof_collect(ctx);
+    for (int i = 0; i < DQMC_PROF_NCAT; ++i) { ms[i] = ctx->profMs[i]; counts[i] = ctx->profCount[i]; }
+    return DQMC_OK;
+}
+
+const char* dqmc_profile_name(int category) {
+    return (category >= 0 && category < DQMC_PROF_NCAT) ? kProfNames[category] : "";
+}
+
+int dqmc_accepted_total(dqmc_ctx* ctx, uint64_t* out) {
+    if (!ctx || !out) return DQMC_ERR_PARAM;
+    CK(cudaMemcpyAsync(ctx->h_scalars, ctx->acceptedTotal, sizeof(unsigned long long) * ctx->R, cudaMemcpyDeviceToHost,
+                       ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    std::memcpy(out, ctx->h_scalars, sizeof(uint64_t) * ctx->R);
     return DQMC_OK;
 }
 
@@ -1056,6 +1208,38 @@ int dqmc_exchange_actions(dqmc_ctx* ctx, double* actions_dev, double* actions_ho
         CK(cudaMemcpyAsync(actions_host, dst, sizeof(double) * ctx->R, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
     }
+    return DQMC_OK;
+}
+
+int dqmc_exchange_pack(dqmc_ctx* ctx, double* payload_dev, int n_uniforms) {
+    if (!ctx || !payload_dev || n_uniforms < 0) return DQMC_ERR_PARAM;
+    const int R = ctx->R;
+    CKL(launch_exchange_action(ctx->phi, payload_dev, ctx->N, ctx->opdim, ctx->m, ctx->p.dtau,
+                               (long long)phi_stride(ctx), R, ctx->stream));
+    double* uni = payload_dev + R;
+    double* blobs = uni + n_uniforms;
+    if (!ctx->rngResident && n_uniforms > 0) {
+        const double* src = ctx->rng[0].peek((size_t)n_uniforms);
+        std::memcpy(ctx->h_scalars, src, sizeof(double) * n_uniforms);      // h_scalars holds >= 8R+16 doubles
+        CK(cudaMemcpyAsync(uni, ctx->h_scalars, sizeof(double) * n_uniforms, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CKL(launch_exchange_pack(ctx->rngbuf, ctx->cursor, ctx->rngWindow, uni, n_uniforms, ctx->ctrl, blobs, R,
+                             ctx->rngResident ? 1 : 0, ctx->stream));
+    return DQMC_OK;
+}
+
+int dqmc_exchange_apply(dqmc_ctx* ctx, const double* r_new, const dqmc_control_data* ctrl_new, int n_uniforms_used) {
+    if (!ctx || !r_new || !ctrl_new || n_uniforms_used < 0) return DQMC_ERR_PARAM;
+    for (int r = 0; r < ctx->R; ++r) {
+        ctx->h_r[r] = r_new[r];
+        ctx->ctrl_host[r] = ctrl_new[r];
+    }
+    if (n_uniforms_used > 0) {
+        if (ctx->rngResident) CKL(launch_cursor_advance(ctx->cursor, 0, n_uniforms_used, ctx->stream));
+        else ctx->rng[0].skip((size_t)n_uniforms_used);
+    }
+    RET(upload_ctrl(ctx));
+    RET(upload_rvals(ctx));
     return DQMC_OK;
 }
 

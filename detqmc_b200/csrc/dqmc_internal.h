@@ -65,6 +65,11 @@ cudaError_t launch_phi_action(const double* phi, const double* rvals, double* ou
 cudaError_t launch_exchange_action(const double* phi, double* out, int N, int opdim, int m, double dtau,
                                    long long stridePhi, int batch, cudaStream_t st);
 
+cudaError_t launch_exchange_pack(const double* rng, const int* cursor, int window, double* uni_out, int n_uni,
+                                 const dqmc_control_data* ctrl, double* ctrl_out, int R, int copy_uniforms,
+                                 cudaStream_t st);
+cudaError_t launch_cursor_advance(int* cursor, int rep, int n, cudaStream_t st);
+
 // ------------------------------------------------------------------------------------------------
 // Batched complex GEMM on FP64 tensor cores (gemm_kernels.cu)
 //   C = rowscale .* (op(A) * diag(kscale) * op(B)) .* colscale + beta * C
@@ -127,6 +132,7 @@ struct UpdateArgs {
     int* cursor;                  // [batch] read position in the window
     dqmc_control_data* ctrl;      // [batch] step size + running average (device copy)
     uint32_t* accepted;           // [batch] accepted proposals in this slice
+    unsigned long long* acceptedTotal;   // [batch] running total (for flop accounting)
     int* errflag;                 // device error flag (rng window overrun, NaN)
     int k;                        // time slice
     int thermalization;
@@ -190,6 +196,16 @@ struct dqmc_ctx {
     size_t rngCap;
     int* cursor;           // [R]
     int rngWindow;         // number of values per replica in the uploaded window
+    size_t rngAlloc, rngStride;
+    bool rngResident;      // window pre-loaded for several sweeps (dqmc_rng_preload)
+    size_t rngResidentUsedBound;
+    unsigned long long* acceptedTotal;
+    bool profiling;
+    struct ProfRec { int cat; cudaEvent_t e0, e1; };
+    std::vector<ProfRec> profPending;
+    std::vector<cudaEvent_t> profPool;
+    double profMs[DQMC_PROF_NCAT];
+    uint64_t profCount[DQMC_PROF_NCAT];
     dqmc_control_data* ctrl;      // [R] device
     uint32_t* accepted;    // [R]
     int* errflag;

@@ -135,7 +135,34 @@ __global__ void exchange_action_kernel(const double* phi, double* out, int N, in
     if (threadIdx.x == 0) out[b] = 0.5 * dtau * acc;
 }
 
+// replica-exchange payload: look-ahead uniforms of local replica 0 taken at its device cursor
+// (resident mode), and the control-data blobs of all local replicas
+__global__ void exchange_pack_kernel(const double* rng, const int* cursor, int window, double* uni_out, int n_uni,
+                                     const dqmc_control_data* ctrl, double* ctrl_out, int R, int copy_uniforms) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nth = gridDim.x * blockDim.x;
+    if (copy_uniforms) {
+        const int c0 = cursor[0];
+        for (int i = tid; i < n_uni; i += nth) uni_out[i] = (c0 + i < window) ? rng[c0 + i] : -1.0;
+    }
+    const int words = int(sizeof(dqmc_control_data) / sizeof(double));
+    const double* src = reinterpret_cast<const double*>(ctrl);
+    for (int i = tid; i < R * words; i += nth) ctrl_out[i] = src[i];
+}
+__global__ void cursor_advance_kernel(int* cursor, int rep, int n) { cursor[rep] += n; }
+
 }  // namespace
+
+cudaError_t launch_exchange_pack(const double* rng, const int* cursor, int window, double* uni_out, int n_uni,
+                                 const dqmc_control_data* ctrl, double* ctrl_out, int R, int copy_uniforms,
+                                 cudaStream_t st) {
+    exchange_pack_kernel<<<8, 256, 0, st>>>(rng, cursor, window, uni_out, n_uni, ctrl, ctrl_out, R, copy_uniforms);
+    return cudaGetLastError();
+}
+cudaError_t launch_cursor_advance(int* cursor, int rep, int n, cudaStream_t st) {
+    cursor_advance_kernel<<<1, 1, 0, st>>>(cursor, rep, n);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_set_identity(cplx* A, int D, long long stride, int batch, cudaStream_t st) {
     dim3 grid((unsigned)((size_t(D) * D + 255) / 256), batch);

@@ -381,6 +381,7 @@ __global__ void __launch_bounds__(kUpdThreads) update_slice_kernel(UpdateModel m
         if (sAbort) atomicExch(a.errflag, 1);
         a.cursor[b] = cursor;
         a.accepted[b] = accepted;
+        if (a.acceptedTotal) a.acceptedTotal[b] += accepted;
         dqmc_control_data* cd = a.ctrl + b;
         const double ratio = double(accepted) / double(N);
         cd->lastAccRatioLocal_phi = ratio;

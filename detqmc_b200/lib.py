@@ -72,7 +72,15 @@ SYMBOLS = [
     ("dqmc_global_shift_move", c_i32, [c_vp, c_vp]),
     ("dqmc_phi_action", c_i32, [c_vp, c_vp]),
     ("dqmc_sweep", c_i32, [c_vp, c_i32]),
+    ("dqmc_rng_preload", c_i32, [c_vp, c_i32]),
+    ("dqmc_rng_release", c_i32, [c_vp]),
+    ("dqmc_profile_enable", c_i32, [c_vp, c_i32]),
+    ("dqmc_profile_get", c_i32, [c_vp, c_vp, c_vp]),
+    ("dqmc_profile_name", ctypes.c_char_p, [c_i32]),
+    ("dqmc_accepted_total", c_i32, [c_vp, c_vp]),
     ("dqmc_exchange_actions", c_i32, [c_vp, c_vp, c_vp]),
+    ("dqmc_exchange_pack", c_i32, [c_vp, c_vp, c_i32]),
+    ("dqmc_exchange_apply", c_i32, [c_vp, c_vp, c_vp, c_i32]),
     ("dqmc_exchange_probability", c_f64, [c_f64, c_f64, c_f64, c_f64]),
     ("dqmc_exchange_walk", c_i32, [c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, _P(c_i32), c_vp]),
 ]

@@ -266,6 +266,36 @@ class DetSDWBatch:
     def set_exchange_parameter_value(self, r, rep=0):
         self._ck(self.lib.dqmc_set_exchange_parameter(self.h, rep, float(r)))
 
+    def exchange_pack(self, payload_dev_ptr, n_uniforms):
+        self._ck(self.lib.dqmc_exchange_pack(self.h, c_vp(int(payload_dev_ptr)), int(n_uniforms)))
+
+    def exchange_apply(self, r_new, ctrl_new, n_used):
+        r_new = np.ascontiguousarray(r_new, dtype=np.float64)
+        ctrl_new = np.ascontiguousarray(ctrl_new, dtype=np.float64)
+        assert r_new.shape == (self.R,) and ctrl_new.size == self.R * (ctypes.sizeof(ControlData) // 8)
+        self._ck(self.lib.dqmc_exchange_apply(self.h, _ptr(r_new), _ptr(ctrl_new), int(n_used)))
+
+    def rng_preload(self, n_sweeps):
+        self._ck(self.lib.dqmc_rng_preload(self.h, int(n_sweeps)))
+
+    def rng_release(self):
+        self._ck(self.lib.dqmc_rng_release(self.h))
+
+    def profile_enable(self, on=True):
+        self._ck(self.lib.dqmc_profile_enable(self.h, int(on)))
+
+    def profile_get(self):
+        ms = np.zeros(7)
+        cnt = np.zeros(7, dtype=np.uint64)
+        self._ck(self.lib.dqmc_profile_get(self.h, _ptr(ms), _ptr(cnt)))
+        names = [self.lib.dqmc_profile_name(i).decode() for i in range(7)]
+        return {n: (float(m), int(c)) for n, m, c in zip(names, ms, cnt)}
+
+    def accepted_total(self):
+        out = np.zeros(self.R, dtype=np.uint64)
+        self._ck(self.lib.dqmc_accepted_total(self.h, _ptr(out)))
+        return out
+
     def get_exchange_action_contribution(self, device_ptr=None):
         out = np.zeros(self.R)
         self._ck(self.lib.dqmc_exchange_actions(self.h, c_vp(device_ptr) if device_ptr else None, _ptr(out)))
@@ -288,36 +318,58 @@ def exchange_walk(control_values, par_process, process_par, actions, uniforms):
     return used.value, swapped[:n - 1]
 
 
-class ReplicaExchangeLadder:
-    """Replica-exchange bookkeeping over `world` ranks, `n_local` replicas each (contiguous
-    partition of the ladder).  `gather(vec)` must return the concatenation of every rank's vector in
-    rank order (torch.distributed all_gather in production, identity for one rank)."""
+CTRL_WORDS = ctypes.sizeof(ControlData) // 8      # 105 doubles per control-data blob
 
-    def __init__(self, control_values, n_local, rank=0, world=1, gather=None):
+
+class ReplicaExchangeLadder:
+    """DetQMCPT::replicaExchangeStep (detqmcpt.h:962-1118) for a ladder of P control-parameter
+    values partitioned contiguously over `world` ranks with `n_local` replicas each.
+
+    Per exchange step every rank contributes one payload vector
+        [ n_local actions | P-1 look-ahead uniforms of its local replica 0 | n_local control blobs ]
+    (dqmc_exchange_pack writes it on the device); the payloads of all ranks are all-gathered (NCCL
+    in production, gloo / identity in tests) and every rank then performs the identical serial ladder
+    walk with rank 0's uniforms -- the reference walks on MPI rank 0 with rank 0's RngWrapper
+    (detqmcpt.h:1031-1079) and scatters the result; here nothing needs to be scattered."""
+
+    def __init__(self, control_values, n_local, rank=0, world=1):
         self.values = np.ascontiguousarray(control_values, dtype=np.float64)
         self.P = len(self.values)
-        assert self.P == n_local * world
+        assert self.P == n_local * world, "ladder length must equal world * n_local"
         self.n_local, self.rank, self.world = n_local, rank, world
-        self.gather = gather if gather is not None else (lambda v: v)
         self.par_process = np.arange(self.P, dtype=np.int32)     # current_par_process
         self.process_par = np.arange(self.P, dtype=np.int32)     # current_process_par
-        self.proposed = np.zeros(self.P - 1, dtype=np.int64)
-        self.accepted = np.zeros(self.P - 1, dtype=np.int64)
+        self.proposed = np.zeros(max(self.P - 1, 1), dtype=np.int64)
+        self.accepted = np.zeros(max(self.P - 1, 1), dtype=np.int64)
+
+    @property
+    def n_uniforms(self):
+        return self.P - 1
+
+    @property
+    def payload_len(self):
+        return self.n_local + self.n_uniforms + self.n_local * CTRL_WORDS
 
     def local_parameters(self):
         lo = self.rank * self.n_local
         return self.values[self.process_par[lo:lo + self.n_local]]
 
-    def step(self, local_actions, uniforms_of_replica0):
-        """local_actions: [n_local]; uniforms_of_replica0: P-1 look-ahead values of global replica 0's
-        stream (only rank 0's are used).  Returns (n_uniforms_used, old process->par map)."""
-        payload = np.concatenate([np.asarray(local_actions, dtype=np.float64),
-                                  np.asarray(uniforms_of_replica0, dtype=np.float64)])
-        allp = np.asarray(self.gather(payload)).reshape(self.world, -1)
-        actions = np.ascontiguousarray(allp[:, :self.n_local].reshape(-1))
-        uniforms = np.ascontiguousarray(allp[0, self.n_local:])
-        old = self.process_par.copy()
+    def walk(self, gathered):
+        """gathered: array [world, payload_len].  Returns (r_new[n_local], ctrl_new[n_local, 105],
+        n_uniforms_used_by_this_rank)."""
+        g = np.asarray(gathered, dtype=np.float64).reshape(self.world, self.payload_len)
+        nl, nu = self.n_local, self.n_uniforms
+        actions = np.ascontiguousarray(g[:, :nl].reshape(-1))
+        uniforms = np.ascontiguousarray(g[0, nl:nl + nu])
+        blobs = g[:, nl + nu:].reshape(self.P, CTRL_WORDS)
+        old_par_process = self.par_process.copy()
         used, swapped = exchange_walk(self.values, self.par_process, self.process_par, actions, uniforms)
-        self.proposed += 1
-        self.accepted += swapped
-        return used, old
+        self.proposed[:self.P - 1] += 1
+        self.accepted[:self.P - 1] += swapped
+        lo = self.rank * nl
+        new_par = self.process_par[lo:lo + nl]
+        r_new = self.values[new_par]
+        # control data follow the parameter (std::swap of the buffers, detqmcpt.h:1052-1053): replica pi
+        # gets the blob of whoever held its new parameter before the walk
+        ctrl_new = np.ascontiguousarray(blobs[old_par_process[new_par]])
+        return np.ascontiguousarray(r_new), ctrl_new, (used if self.rank == 0 else 0)

@@ -200,12 +200,43 @@ int dqmc_phi_action(dqmc_ctx* ctx, double* out);
  * the global move before a down-sweep. */
 int dqmc_sweep(dqmc_ctx* ctx, int thermalization);
 
+/* Resident random numbers: upload the next n_sweeps sweeps' worth of every replica's stream once;
+ * dqmc_sweep then runs without per-sweep host<->device copies or synchronisation (the consumption
+ * cursors live on the device).  dqmc_rng_release reads the cursors back and advances the host
+ * streams; it must be called before anything else consumes from them (dqmc_rng_draw ...). */
+int dqmc_rng_preload(dqmc_ctx* ctx, int n_sweeps);
+int dqmc_rng_release(dqmc_ctx* ctx);
+
+/* ---- measurement hooks (no reference twin; the reference's -DTIMING timers, timing.h:32-78) ---- */
+#define DQMC_PROF_NCAT 7
+/* Bracket every kernel launch with CUDA events on the context's stream and accumulate device
+ * time per kernel family. */
+int dqmc_profile_enable(dqmc_ctx* ctx, int on);
+int dqmc_profile_get(dqmc_ctx* ctx, double* ms /*[DQMC_PROF_NCAT]*/, uint64_t* counts /*[DQMC_PROF_NCAT]*/);
+const char* dqmc_profile_name(int category);
+/* Running total of accepted local updates per replica (flop accounting of the delayed updates). */
+int dqmc_accepted_total(dqmc_ctx* ctx, uint64_t* out);
+
 /* ---- replica exchange ------------------------------------------------------------------------- */
 
 /* get_exchange_action_contribution() (detsdwopdim.cpp:5204-5216) of every local replica.
  * actions_dev (may be NULL): device buffer of n_replicas doubles -- the NCCL all-gather send
  * buffer; actions_host (may be NULL): host copy. */
 int dqmc_exchange_actions(dqmc_ctx* ctx, double* actions_dev, double* actions_host);
+/* One-shot packing of everything replicaExchangeStep gathers (detqmcpt.h:968-1012) into a device
+ * buffer that can be handed to ncclAllGather as is:
+ *   payload[0 .. R)                      exchange action of every local replica
+ *   payload[R .. R+n_uniforms)           the next n_uniforms values of LOCAL replica 0's stream
+ *                                        (look-ahead only; meaningful on the rank that owns ladder
+ *                                        replica 0)
+ *   payload[R+n_uniforms .. +R*105)      the control-data blobs (dqmc_control_data, 840 bytes each)
+ * No host synchronisation. */
+int dqmc_exchange_pack(dqmc_ctx* ctx, double* payload_dev, int n_uniforms);
+/* Scatter side of replicaExchangeStep (detqmcpt.h:1082-1115): install the new exchange parameter
+ * and control data of every local replica and consume n_uniforms_used values from local replica
+ * 0's stream (pass 0 on ranks that do not own ladder replica 0). */
+int dqmc_exchange_apply(dqmc_ctx* ctx, const double* r_new, const dqmc_control_data* ctrl_new,
+                        int n_uniforms_used);
 /* get_replica_exchange_probability (detsdwopdim.cpp:5251-5264). */
 double dqmc_exchange_probability(double par1, double action1, double par2, double action2);
 /* Serial ladder walk of DetQMCPT::replicaExchangeStep on the gathered actions

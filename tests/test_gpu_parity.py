@@ -270,27 +270,31 @@ def test_global_shift_move_vs_oracle():
         assert abs(b.logdet() - np.log(o.green_inv_sv[0]).sum()) < 1e-9
 
 
-# ---------------------------------------------------------------- full-size, size-independent checks
+# ---------------------------------------------------------------- full-size checks
 @pytest.mark.parametrize("kw", [dict(L=12, m=100, s=10), dict(L=8, m=80, s=10)])
 def test_full_size_properties(kw):
-    """BASELINE configs C3 (one replica of the L=12, beta=10 ladder) and C2: properties that need no
-    oracle -- B^-1 B = 1, wrap up/down round trip, G (1 + B(beta,0)) = 1, wrapped == recomputed G."""
-    from dqmc_oracle import SdwParams
+    """BASELINE configs C3 (replicas of the L=12, beta=10 ladder) and C2 at full size: G after setup
+    and after one sweep against the oracle, plus properties that need no oracle -- B^-1 B = 1, wrap
+    up/down round trip, wrapped == recomputed G, G(0) after the sweep == from scratch."""
+    from dqmc_oracle import SdwOracle, SdwParams
     p = SdwParams(**kw)
+    o = SdwOracle(p)
     b = make_batch(p, n_replicas=2, rng_indices=[1, 2])
     D = b.D
     A = rand_cplx((D, D), 3)
     assert relerr(b.bmat_mult(2, b.bmat_mult(0, A, 17, 7), 17, 7), A) < 1e-11
     assert relerr(b.bmat_mult(3, b.bmat_mult(1, A, 17, 7), 17, 7), A) < 1e-11
-    for rep in range(2):
-        G = b.green(rep)
-        GB = b.bmat_mult(1, G, p.m, 0, rep=rep)                     # G B(beta, 0)
-        assert maxabs(G + GB, np.eye(D)) < 1e-9
+    assert relerr(b.green(0), o.green[0]) < TOL_G
+    assert abs(b.logdet(0) - np.log(o.green_inv_sv[0]).sum()) < 1e-10 * abs(b.logdet(0))
     G0 = b.green(0)
     b.wrap_down(p.m)
     b.wrap_up(p.m - 1)
     assert relerr(b.green(0), G0) < 1e-10
-    b.sweep()                                                       # a full down-sweep with updates
+    b.sweepThermalization()                                         # global move + full down-sweep
+    o.sweep_thermalization()
+    assert b.control_data(0).lastAccRatioLocal_phi == o.last_acc_ratio
+    assert b.control_data(0).acceptedGlobalShifts == o.accepted_global_shifts
+    assert maxabs(b.phi(0)[1:], o.phi[1:]) < 1e-12
+    assert relerr(b.green(0), o.green[0]) < TOL_G
     assert np.all(b.green_consistency() < 1e-8)                     # wrapped vs advanced G at the last advance
-    G = b.green(0)
-    assert maxabs(G, b.green_for_timeslice(0, rep=0)) < 1e-9        # G(0) after the sweep == from scratch
+    assert relerr(b.green(1), b.green_for_timeslice(0, rep=1)) < 1e-9

@@ -824,6 +824,13 @@ int dqmc_rng_skip(dqmc_ctx* ctx, int rep, size_t n) {
     return DQMC_OK;
 }
 uint64_t dqmc_rng_consumed(const dqmc_ctx* ctx, int rep) { return valid_rep(ctx, rep) ? ctx->rng[rep].consumed() : 0; }
+int dqmc_rng_stream_sample(uint32_t seed, uint32_t process_index, size_t n, double* out) {
+    if (n && !out) return DQMC_ERR_PARAM;
+    RngStream g;
+    g.seed(seed, process_index);
+    for (size_t i = 0; i < n; ++i) out[i] = g.draw();
+    return DQMC_OK;
+}
 
 // ---- state -------------------------------------------------------------------------------------
 int dqmc_upload_fields(dqmc_ctx* ctx, int rep, const void* fields) {

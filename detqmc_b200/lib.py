@@ -44,6 +44,7 @@ SYMBOLS = [
     ("dqmc_rng_peek", c_i32, [c_vp, c_i32, c_sz, c_vp]),
     ("dqmc_rng_skip", c_i32, [c_vp, c_i32, c_sz]),
     ("dqmc_rng_consumed", c_u64, [c_vp, c_i32]),
+    ("dqmc_rng_stream_sample", c_i32, [c_u32, c_u32, c_sz, c_vp]),
     ("dqmc_init_random_fields", c_i32, [c_vp, c_i32]),
     ("dqmc_upload_fields", c_i32, [c_vp, c_i32, c_vp]),
     ("dqmc_download_fields", c_i32, [c_vp, c_i32, c_vp]),

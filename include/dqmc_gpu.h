@@ -116,6 +116,10 @@ int dqmc_rng_peek(dqmc_ctx* ctx, int rep, size_t n, double* out);
 int dqmc_rng_skip(dqmc_ctx* ctx, int rep, size_t n);
 /* Total number of values consumed from replica rep's stream so far. */
 uint64_t dqmc_rng_consumed(const dqmc_ctx* ctx, int rep);
+/* Context-free: the first n rand01() values of RngWrapper(seed, process_index) (rngwrapper.cpp:30-50,
+ * rngwrapper.h:54-57).  Host only; lets a host program (and the CPU tests) check that its own
+ * generator and this library's restatement of dSFMT-19937 produce the same stream. */
+int dqmc_rng_stream_sample(uint32_t seed, uint32_t process_index, size_t n, double* out);
 
 /* ---- state ----------------------------------------------------------------------------------- */
 

@@ -47,5 +47,19 @@ def build(force=False, verbose=False):
     return OUT
 
 
+def build_kbench():
+    """Development tool: kernel micro-benchmarks linked against the object files."""
+    build(force=False)
+    objdir = os.path.join(HERE, "build")
+    objs = [os.path.join(objdir, os.path.splitext(f)[0] + ".o") for f in SOURCES
+            if os.path.exists(os.path.join(CSRC, f))]
+    out = os.path.join(HERE, "..", "tools", "kbench")
+    subprocess.check_call(["nvcc"] + NVCC_FLAGS + [os.path.join(HERE, "..", "tools", "kbench.cu")] + objs + ["-o", out])
+    return out
+
+
 if __name__ == "__main__":
+    if "--kbench" in sys.argv:
+        print(build_kbench())
+        sys.exit(0)
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

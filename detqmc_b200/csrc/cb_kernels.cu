@@ -9,13 +9,23 @@
 //
 // B_k = e^{-dtau V_k} * blockdiag_bandspin( e^{dtau mu_b} E1(1/2) E0(1) E1(1/2) ),  E_g = product of
 // the 4-site plaquette exponentials of subgroup g.  A left multiply acts on every COLUMN of A
-// independently, a right multiply on every ROW, so a CTA stages a tile of TV vectors (each of
-// length D = msf*N) in shared memory, applies all slices of the chain there, and writes the tile
+// independently, a right multiply on every ROW, so a CTA stages a tile of kCbTileVecs vectors (each
+// of length D = msf*N) in shared memory, applies all slices of the chain there, and writes the tile
 // back: HBM traffic is one read + one write of the matrix per chain, whatever its length.  The
 // reference recomputes every checkerboard block 2x (O(2)) / 3x (O(3)) and copies the matrix per
 // pass; here all band blocks of a vector are transformed once.
 //
-// Bound: HBM (algorithmic bytes = 2 * D^2 * 16 per launch and matrix).
+// Shared-memory layout: inside every band-spin block the N sites are stored in 4-sublattice order
+// (x parity, y parity, then plaquette index), so the four corners of consecutive plaquettes are four
+// unit-stride streams -- conflict-free 16-byte accesses for both plaquette subgroups -- and the
+// per-site potential stage is unit stride as well.  A thread owns one (plaquette, band-spin) pair
+// and keeps that plaquette's 4x4 matrix in registers while it walks over the vectors of the tile;
+// the matrices are Hermitian (exponentials of Hermitian hopping blocks), stored as 4 real diagonal
+// + 6 complex upper entries, and real symmetric without magnetic flux (REALM variant: half the
+// flops).  The transposed matrices needed by the right multiplies are the complex conjugates.
+//
+// Bound: HBM for single-slice launches (algorithmic bytes = 2 * D^2 * 16 per launch and matrix),
+// FP64 pipe for long chains.
 #include "dqmc_internal.h"
 
 #include <cmath>
@@ -26,9 +36,11 @@ namespace dqmc {
 // ------------------------------------------------------------------------------------------------
 // host: plaquette tables
 // ------------------------------------------------------------------------------------------------
-// index: ((((band*2 + sign_idx)*2 + transposed)*2 + pass) * nplaq + q) * 16 + r*4 + c
+// One Hermitian 4x4 matrix = 8 cplx: {(d0,d1), (d2,d3), o01, o02, o03, o12, o13, o23}.
+// index: (((band*2 + sign_idx)*2 + pass) * nplaq + q) * 8
 // pass 0: subgroup 1, half step; pass 1: subgroup 0, full step times e^{-+dtau mu_band}.
-int cb_table_count(const CbGeom& g) { return 2 * 2 * 2 * 2 * g.nplaq * 16; }
+// Plaquette q of subgroup g sits at x = 2*(q % (L/2)) + g, y = 2*(q / (L/2)) + g.
+int cb_table_count(const CbGeom& g) { return 2 * 2 * 2 * g.nplaq * 8; }
 
 namespace {
 
@@ -70,7 +82,7 @@ void expm4(const zc* A, zc* out) {
 
 void cb_build_tables(const dqmc_params& p, std::vector<cplx>& out) {
     const int L = p.L, N = L * L, nplaq = N / 4, half = L / 2;
-    out.assign(size_t(2) * 2 * 2 * 2 * nplaq * 16, make_double2(0, 0));
+    out.assign(size_t(2) * 2 * 2 * nplaq * 8, make_double2(0, 0));
     const double pi = M_PI;
     for (int band = 0; band < 2; ++band) {
         const double th = band == 0 ? p.txhor : p.tyhor;
@@ -119,14 +131,18 @@ void cb_build_tables(const dqmc_params& p, std::vector<cplx>& out) {
                                 Hs[r * 4 + c] = -pf * (H[r * 4 + c] + std::conj(H[c * 4 + r]));
                         expm4(Hs, M);
                     }
-                    for (int tr = 0; tr < 2; ++tr) {
-                        size_t base = ((((size_t(band) * 2 + si) * 2 + tr) * 2 + pass) * nplaq + q) * 16;
-                        for (int r = 0; r < 4; ++r)
-                            for (int c = 0; c < 4; ++c) {
-                                zc v = (tr ? M[c * 4 + r] : M[r * 4 + c]) * ovfac;
-                                out[base + r * 4 + c] = make_double2(v.real(), v.imag());
-                            }
-                    }
+                    // exp of a Hermitian block is Hermitian; symmetrise the round-off and compress
+                    cplx* dst = out.data() + (((size_t(band) * 2 + si) * 2 + pass) * nplaq + q) * 8;
+                    double dg[4];
+                    for (int r = 0; r < 4; ++r) dg[r] = M[r * 4 + r].real() * ovfac;
+                    dst[0] = make_double2(dg[0], dg[1]);
+                    dst[1] = make_double2(dg[2], dg[3]);
+                    int o = 2;
+                    for (int r = 0; r < 4; ++r)
+                        for (int c = r + 1; c < 4; ++c) {
+                            const zc v = 0.5 * (M[r * 4 + c] + std::conj(M[c * 4 + r])) * ovfac;
+                            dst[o++] = make_double2(v.real(), v.imag());
+                        }
                 }
             }
         }
@@ -138,143 +154,153 @@ void cb_build_tables(const dqmc_params& p, std::vector<cplx>& out) {
 // ------------------------------------------------------------------------------------------------
 namespace {
 
-__device__ __forceinline__ cplx cmul(cplx a, cplx b) {
-    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
-}
-__device__ __forceinline__ cplx cfma(cplx a, cplx b, cplx c) {   // a*b + c
+constexpr int kCbTileVecs = 8;      // vectors per CTA tile
+constexpr int kCbMaxThreads = 256;
+
+__device__ __forceinline__ cplx cfma(cplx a, cplx b, cplx c) {    // a*b + c
     return make_double2(fma(a.x, b.x, fma(-a.y, b.y, c.x)), fma(a.x, b.y, fma(a.y, b.x, c.y)));
 }
+__device__ __forceinline__ cplx cfmac(cplx a, cplx b, cplx c) {   // conj(a)*b + c
+    return make_double2(fma(a.x, b.x, fma(a.y, b.y, c.x)), fma(a.x, b.y, fma(-a.y, b.x, c.y)));
+}
+__device__ __forceinline__ cplx rfma(double a, cplx b, cplx c) {  // a*b + c, a real
+    return make_double2(fma(a, b.x, c.x), fma(a, b.y, c.y));
+}
+__device__ __forceinline__ cplx rmul(double a, cplx b) { return make_double2(a * b.x, a * b.y); }
 
-constexpr int kCbThreads = 256;
-constexpr int kCbTileVecs = 8;
-
-template <int MSF>
-__device__ __forceinline__ void hopping_pass(cplx* tile, int ldt, int nv, const cplx* __restrict__ tab,
-                                             const CbGeom& g, int sign_idx, int transposed, int pass) {
-    const int pairs = MSF * g.nplaq;
-    const int nthreads = blockDim.x;
-    const int tid = threadIdx.x;
-    const int half = g.L / 2;
-    const int subgroup = pass == 0 ? 1 : 0;
-    int p, pstep, v0, vstep;
-    if (pairs <= nthreads) {
-        const int ngrp = nthreads / pairs;
-        p = tid % pairs;
-        pstep = pairs;                 // single iteration
-        v0 = tid / pairs;
-        vstep = ngrp;
-        if (v0 >= ngrp) return;
-    } else {
-        p = tid;
-        pstep = nthreads;
-        v0 = 0;
-        vstep = 1;
+// One plaquette matrix in registers.
+template <bool REALM>
+struct PlaqMat {
+    double d[4];
+    cplx o[6];      // o01 o02 o03 o12 o13 o23 (imaginary parts unused when REALM)
+    __device__ __forceinline__ void load(const cplx* __restrict__ M, bool conj) {
+        const cplx t0 = __ldg(M), t1 = __ldg(M + 1);
+        d[0] = t0.x; d[1] = t0.y; d[2] = t1.x; d[3] = t1.y;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            o[i] = __ldg(M + 2 + i);
+            if (!REALM && conj) o[i].y = -o[i].y;
+        }
     }
-    for (; p < pairs; p += pstep) {
+    __device__ __forceinline__ void apply(cplx& a, cplx& b, cplx& c, cplx& e) const {
+        cplx r0 = rmul(d[0], a), r1 = rmul(d[1], b), r2 = rmul(d[2], c), r3 = rmul(d[3], e);
+        if (REALM) {
+            r0 = rfma(o[0].x, b, r0); r0 = rfma(o[1].x, c, r0); r0 = rfma(o[2].x, e, r0);
+            r1 = rfma(o[0].x, a, r1); r1 = rfma(o[3].x, c, r1); r1 = rfma(o[4].x, e, r1);
+            r2 = rfma(o[1].x, a, r2); r2 = rfma(o[3].x, b, r2); r2 = rfma(o[5].x, e, r2);
+            r3 = rfma(o[2].x, a, r3); r3 = rfma(o[4].x, b, r3); r3 = rfma(o[5].x, c, r3);
+        } else {
+            r0 = cfma(o[0], b, r0);  r0 = cfma(o[1], c, r0);  r0 = cfma(o[2], e, r0);
+            r1 = cfmac(o[0], a, r1); r1 = cfma(o[3], c, r1);  r1 = cfma(o[4], e, r1);
+            r2 = cfmac(o[1], a, r2); r2 = cfmac(o[3], b, r2); r2 = cfma(o[5], e, r2);
+            r3 = cfmac(o[2], a, r3); r3 = cfmac(o[4], b, r3); r3 = cfmac(o[5], c, r3);
+        }
+        a = r0; b = r1; c = r2; e = r3;
+    }
+};
+
+struct CbShape {
+    int half, quarter;      // L/2, N/4
+    int pairs;              // msf * nplaq
+    int G;                  // vector groups of the hopping passes (divides kCbTileVecs)
+    int Gp;                 // vector groups of the potential stage
+};
+
+// position of site s inside its band-spin block of the shared-memory tile
+__device__ __forceinline__ int perm_site(int s, int L, int half, int quarter) {
+    const int x = s % L, y = s / L;
+    return ((x & 1) | ((y & 1) << 1)) * quarter + (y >> 1) * half + (x >> 1);
+}
+
+template <int MSF, bool REALM>
+__device__ __forceinline__ void hopping_pass(cplx* tile, int ldt, int nv, const cplx* __restrict__ tab,
+                                             const CbGeom& g, const CbShape& sh, int sign_idx, int transposed,
+                                             int pass) {
+    const int items = sh.pairs * sh.G;
+    for (int item = threadIdx.x; item < items; item += blockDim.x) {
+        const int grp = item / sh.pairs;
+        const int p = item - grp * sh.pairs;
         const int bs = p / g.nplaq;
         const int q = p - bs * g.nplaq;
         const int band = bs & 1;       // XUP, YDOWN, XDOWN, YUP -> x, y, x, y
-        const cplx* M = tab + ((((size_t(band) * 2 + sign_idx) * 2 + transposed) * 2 + pass) * g.nplaq + q) * 16;
-        cplx mm[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) mm[i] = __ldg(M + i);
-        const int i1 = 2 * (q % half) + subgroup;
-        const int i2 = 2 * (q / half) + subgroup;
-        const int i1p = (i1 + 1 == g.L) ? 0 : i1 + 1;
-        const int i2p = (i2 + 1 == g.L) ? 0 : i2 + 1;
+        PlaqMat<REALM> M;
+        M.load(tab + (((size_t(band) * 2 + sign_idx) * 2 + pass) * g.nplaq + q) * 8, transposed != 0);
+        int oi, oj, ok, ol;
         const int base = bs * g.N;
-        const int si = base + i2 * g.L + i1;
-        const int sj = base + i2 * g.L + i1p;
-        const int sk = base + i2p * g.L + i1;
-        const int sl = base + i2p * g.L + i1p;
-        for (int v = v0; v < nv; v += vstep) {
+        if (pass == 1) {               // subgroup 0: (even, even) corner
+            oi = base + q; oj = oi + sh.quarter; ok = oj + sh.quarter; ol = ok + sh.quarter;
+        } else {                       // subgroup 1: (odd, odd) corner, neighbours wrap around
+            const int py = q / sh.half, px = q - py * sh.half;
+            const int pxp = px + 1 == sh.half ? 0 : px + 1;
+            const int pyp = py + 1 == sh.half ? 0 : py + 1;
+            oi = base + 3 * sh.quarter + q;
+            oj = base + 2 * sh.quarter + py * sh.half + pxp;
+            ok = base + 1 * sh.quarter + pyp * sh.half + px;
+            ol = base + pyp * sh.half + pxp;
+        }
+        for (int v = grp; v < nv; v += sh.G) {
             cplx* t = tile + v * ldt;
-            const cplx a = t[si], b = t[sj], c = t[sk], d = t[sl];
-            cplx r0 = cmul(mm[0], a), r1 = cmul(mm[4], a), r2 = cmul(mm[8], a), r3 = cmul(mm[12], a);
-            r0 = cfma(mm[1], b, r0); r1 = cfma(mm[5], b, r1); r2 = cfma(mm[9], b, r2); r3 = cfma(mm[13], b, r3);
-            r0 = cfma(mm[2], c, r0); r1 = cfma(mm[6], c, r1); r2 = cfma(mm[10], c, r2); r3 = cfma(mm[14], c, r3);
-            r0 = cfma(mm[3], d, r0); r1 = cfma(mm[7], d, r1); r2 = cfma(mm[11], d, r2); r3 = cfma(mm[15], d, r3);
-            t[si] = r0; t[sj] = r1; t[sk] = r2; t[sl] = r3;
+            cplx a = t[oi], b = t[oj], c = t[ok], e = t[ol];
+            M.apply(a, b, c, e);
+            t[oi] = a; t[oj] = b; t[ok] = c; t[ol] = e;
         }
     }
 }
 
-template <int MSF>
+template <int MSF, bool REALM>
 __device__ __forceinline__ void hopping_stage(cplx* tile, int ldt, int nv, const cplx* __restrict__ tab,
-                                              const CbGeom& g, int sign_idx, int transposed) {
-    hopping_pass<MSF>(tile, ldt, nv, tab, g, sign_idx, transposed, 0);
+                                              const CbGeom& g, const CbShape& sh, int sign_idx, int transposed) {
+    hopping_pass<MSF, REALM>(tile, ldt, nv, tab, g, sh, sign_idx, transposed, 0);
     __syncthreads();
-    hopping_pass<MSF>(tile, ldt, nv, tab, g, sign_idx, transposed, 1);
+    hopping_pass<MSF, REALM>(tile, ldt, nv, tab, g, sh, sign_idx, transposed, 1);
     __syncthreads();
-    hopping_pass<MSF>(tile, ldt, nv, tab, g, sign_idx, transposed, 0);
+    hopping_pass<MSF, REALM>(tile, ldt, nv, tab, g, sh, sign_idx, transposed, 0);
     __syncthreads();
 }
 
-// per-site blocks of e^{sign*dtau*V} (evMatrix, detsdwopdim.cpp:3188-3229 with cdwU == 0)
+// coefficients of the per-site block of e^{sign*dtau*V} (evMatrix, detsdwopdim.cpp:3188-3229 with
+// cdwU == 0): c on the diagonal, e01 = sign x (phi0 - i phi1), e10 = conj(e01), a = sign x phi2
+struct PotCoef { double c, ex, ey, a; };
+
 template <int MSF>
-__device__ __forceinline__ void potential_coeffs(cplx* ev, const double* __restrict__ phi_k,
-                                                 const double* __restrict__ cosh_k,
-                                                 const double* __restrict__ sinh_k, const CbGeom& g,
-                                                 int sign_idx, int transposed) {
-    const double sg = sign_idx == 0 ? -1.0 : 1.0;
-    for (int s = threadIdx.x; s < g.N; s += blockDim.x) {
-        const double c = cosh_k[s], x = sinh_k[s] * sg;
-        const double p0 = phi_k[s];
-        const double p1 = g.opdim > 1 ? phi_k[g.N + s] : 0.0;
-        cplx e01 = make_double2(x * p0, -x * p1);     // sign * x * (phi0 - i phi1)
-        cplx e10 = make_double2(x * p0, x * p1);
-        if (transposed) { cplx t = e01; e01 = e10; e10 = t; }
-        if (MSF == 2) {
-            ev[0 * g.N + s] = make_double2(c, 0);
-            ev[1 * g.N + s] = e01;
-            ev[2 * g.N + s] = e10;
-            ev[3 * g.N + s] = make_double2(c, 0);
-        } else {
-            const double p2 = phi_k[2 * g.N + s];
-            const cplx z = make_double2(0, 0);
-            const cplx cc = make_double2(c, 0);
-            const cplx a = make_double2(x * p2, 0);       //  sign * phi2 * x
-            const cplx ma = make_double2(-x * p2, 0);
-            // rows of e^{sign dtau V}: see detsdwopdim.cpp:3198-3224
-            cplx E[16] = {cc, e01, z, a,
-                          e10, cc, ma, z,
-                          z, ma, cc, e10,
-                          a, z, e01, cc};
-            // (2,3) = sign x (phi0 + i phi1), (3,2) = sign x (phi0 - i phi1); in the transposed case
-            // e01/e10 were swapped above, which is exactly the transpose of those four entries too.
-#pragma unroll
-            for (int i = 0; i < 16; ++i) ev[i * g.N + s] = E[i];
-        }
+__device__ __forceinline__ PotCoef potential_coef(const double* __restrict__ phi_k, const double* __restrict__ cosh_k,
+                                                  const double* __restrict__ sinh_k, const CbGeom& g, int s,
+                                                  int sign_idx, int transposed) {
+    PotCoef pc;
+    const double x = sign_idx == 0 ? -__ldg(sinh_k + s) : __ldg(sinh_k + s);
+    pc.c = __ldg(cosh_k + s);
+    pc.ex = x * __ldg(phi_k + s);
+    const double p1 = g.opdim > 1 ? __ldg(phi_k + g.N + s) : 0.0;
+    pc.ey = transposed ? x * p1 : -x * p1;          // imaginary part of e01 (e10 is its conjugate)
+    pc.a = MSF == 4 ? x * __ldg(phi_k + 2 * g.N + s) : 0.0;
+    return pc;
+}
+
+template <int MSF>
+__device__ __forceinline__ void potential_apply(cplx* t, int N, int pos, const PotCoef& pc) {
+    const cplx e01 = make_double2(pc.ex, pc.ey);
+    if (MSF == 2) {
+        const cplx v0 = t[pos], v1 = t[N + pos];
+        t[pos] = cfma(e01, v1, rmul(pc.c, v0));
+        t[N + pos] = cfmac(e01, v0, rmul(pc.c, v1));
+    } else {
+        // rows of e^{sign dtau V}: (c, e01, 0, a), (e10, c, -a, 0), (0, -a, c, e10), (a, 0, e01, c)
+        const cplx v0 = t[pos], v1 = t[N + pos], v2 = t[2 * N + pos], v3 = t[3 * N + pos];
+        t[pos] = rfma(pc.a, v3, cfma(e01, v1, rmul(pc.c, v0)));
+        t[N + pos] = rfma(-pc.a, v2, cfmac(e01, v0, rmul(pc.c, v1)));
+        t[2 * N + pos] = rfma(-pc.a, v1, cfmac(e01, v3, rmul(pc.c, v2)));
+        t[3 * N + pos] = rfma(pc.a, v0, cfma(e01, v2, rmul(pc.c, v3)));
     }
 }
 
-template <int MSF>
-__device__ __forceinline__ void potential_stage(cplx* tile, int ldt, int nv, const cplx* ev, const CbGeom& g) {
-    const int items = nv * g.N;
-    for (int idx = threadIdx.x; idx < items; idx += blockDim.x) {
-        const int v = idx / g.N;
-        const int s = idx - v * g.N;
-        cplx* t = tile + v * ldt;
-        cplx old[MSF];
-#pragma unroll
-        for (int c = 0; c < MSF; ++c) old[c] = t[c * g.N + s];
-#pragma unroll
-        for (int r = 0; r < MSF; ++r) {
-            cplx acc = make_double2(0, 0);
-#pragma unroll
-            for (int c = 0; c < MSF; ++c) acc = cfma(ev[(r * MSF + c) * g.N + s], old[c], acc);
-            t[r * g.N + s] = acc;
-        }
-    }
-}
-
-template <int MSF>
-__global__ void __launch_bounds__(kCbThreads) cb_mult_kernel(CbGeom g, CbLaunch a) {
+template <int MSF, bool REALM>
+__global__ void __launch_bounds__(kCbMaxThreads) cb_mult_kernel(CbGeom g, CbLaunch a, CbShape sh) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int D = g.D;
+    const int D = g.D, N = g.N;
     const int ldt = D + 1;
     cplx* tile = reinterpret_cast<cplx*>(smem_raw);
-    cplx* ev = tile + kCbTileVecs * ldt;
+    int* sperm = reinterpret_cast<int*>(tile + kCbTileVecs * ldt);      // [D] matrix index -> tile position
+    int* sinv = sperm + D;                                               // [N] tile position -> site
 
     const int b = blockIdx.y;
     const int v0 = blockIdx.x * kCbTileVecs;
@@ -284,68 +310,114 @@ __global__ void __launch_bounds__(kCbThreads) cb_mult_kernel(CbGeom g, CbLaunch 
     const double* coshT = a.coshT + size_t(b) * a.strideTab;
     const double* sinhT = a.sinhT + size_t(b) * a.strideTab;
 
+    for (int e = threadIdx.x; e < D; e += blockDim.x) {
+        const int bs = e / N, s = e - bs * N;
+        const int pos = perm_site(s, g.L, sh.half, sh.quarter);
+        sperm[e] = bs * N + pos;
+        if (bs == 0) sinv[pos] = s;
+    }
+    __syncthreads();
+
     // ---- load the tile (coalesced along the contiguous direction of the column-major matrix)
     if (!a.rows) {
-        for (int idx = threadIdx.x; idx < nv * D; idx += blockDim.x) {
-            const int v = idx / D, e = idx - v * D;
-            tile[v * ldt + e] = A[size_t(v0 + v) * D + e];
+        for (int v = 0; v < nv; ++v) {
+            const cplx* src = A + size_t(v0 + v) * D;
+            cplx* t = tile + v * ldt;
+            for (int e = threadIdx.x; e < D; e += blockDim.x) t[sperm[e]] = src[e];
+        }
+    } else if (nv == kCbTileVecs) {
+        for (int idx = threadIdx.x; idx < kCbTileVecs * D; idx += blockDim.x) {
+            const int e = idx / kCbTileVecs, v = idx % kCbTileVecs;
+            tile[v * ldt + sperm[e]] = A[size_t(e) * D + v0 + v];
         }
     } else {
         for (int idx = threadIdx.x; idx < nv * D; idx += blockDim.x) {
             const int e = idx / nv, v = idx - e * nv;
-            tile[v * ldt + e] = A[size_t(e) * D + v0 + v];
+            tile[v * ldt + sperm[e]] = A[size_t(e) * D + v0 + v];
         }
     }
     __syncthreads();
 
+    // potential stage: item = (site position, vector group)
+    const int pot_items = N * sh.Gp;
     for (int step = 0; step < a.kcount; ++step) {
         const int k = a.kfirst + step * a.kstep;
-        potential_coeffs<MSF>(ev, phi + size_t(k) * g.opdim * g.N, coshT + size_t(k) * g.N,
-                              sinhT + size_t(k) * g.N, g, a.sign_idx, a.transposed);
-        if (a.k_then_v) {
-            hopping_stage<MSF>(tile, ldt, nv, a.cbtab, g, a.sign_idx, a.transposed);   // ends with a sync
-            potential_stage<MSF>(tile, ldt, nv, ev, g);
-            __syncthreads();
-        } else {
-            __syncthreads();
-            potential_stage<MSF>(tile, ldt, nv, ev, g);
-            __syncthreads();
-            hopping_stage<MSF>(tile, ldt, nv, a.cbtab, g, a.sign_idx, a.transposed);
+        const double* phi_k = phi + size_t(k) * g.opdim * N;
+        const double* cosh_k = coshT + size_t(k) * N;
+        const double* sinh_k = sinhT + size_t(k) * N;
+        // the first item's coefficients are fetched before the hopping stage so that their latency
+        // overlaps with it
+        PotCoef pc0;
+        const int it0 = threadIdx.x;
+        const int pos0 = it0 % N, grp0 = it0 / N;
+        if (it0 < pot_items) pc0 = potential_coef<MSF>(phi_k, cosh_k, sinh_k, g, sinv[pos0], a.sign_idx, a.transposed);
+        if (a.k_then_v) hopping_stage<MSF, REALM>(tile, ldt, nv, a.cbtab, g, sh, a.sign_idx, a.transposed);
+        if (it0 < pot_items)
+            for (int v = grp0; v < nv; v += sh.Gp) potential_apply<MSF>(tile + v * ldt, N, pos0, pc0);
+        for (int it = it0 + blockDim.x; it < pot_items; it += blockDim.x) {
+            const int pos = it % N, grp = it / N;
+            const PotCoef pc = potential_coef<MSF>(phi_k, cosh_k, sinh_k, g, sinv[pos], a.sign_idx, a.transposed);
+            for (int v = grp; v < nv; v += sh.Gp) potential_apply<MSF>(tile + v * ldt, N, pos, pc);
         }
+        __syncthreads();
+        if (!a.k_then_v) hopping_stage<MSF, REALM>(tile, ldt, nv, a.cbtab, g, sh, a.sign_idx, a.transposed);
     }
 
     // ---- store
     if (!a.rows) {
         const double* cs = a.colscale ? a.colscale + size_t(b) * a.strideScale : nullptr;
-        for (int idx = threadIdx.x; idx < nv * D; idx += blockDim.x) {
-            const int v = idx / D, e = idx - v * D;
-            cplx val = tile[v * ldt + e];
-            if (cs) { const double sc = cs[v0 + v]; val.x *= sc; val.y *= sc; }
-            A[size_t(v0 + v) * D + e] = val;
+        for (int v = 0; v < nv; ++v) {
+            cplx* dst = A + size_t(v0 + v) * D;
+            const cplx* t = tile + v * ldt;
+            const double sc = cs ? cs[v0 + v] : 1.0;
+            for (int e = threadIdx.x; e < D; e += blockDim.x) {
+                cplx val = t[sperm[e]];
+                if (cs) { val.x *= sc; val.y *= sc; }
+                dst[e] = val;
+            }
+        }
+    } else if (nv == kCbTileVecs) {
+        for (int idx = threadIdx.x; idx < kCbTileVecs * D; idx += blockDim.x) {
+            const int e = idx / kCbTileVecs, v = idx % kCbTileVecs;
+            A[size_t(e) * D + v0 + v] = tile[v * ldt + sperm[e]];
         }
     } else {
         for (int idx = threadIdx.x; idx < nv * D; idx += blockDim.x) {
             const int e = idx / nv, v = idx - e * nv;
-            A[size_t(e) * D + v0 + v] = tile[v * ldt + e];
+            A[size_t(e) * D + v0 + v] = tile[v * ldt + sperm[e]];
         }
     }
 }
 
+int pow2_floor(int x) { int p = 1; while (2 * p <= x) p *= 2; return p; }
+
 }  // namespace
 
 cudaError_t cb_launch(const CbGeom& g, const CbLaunch& a, cudaStream_t st) {
-    const size_t smem = (size_t(kCbTileVecs) * (g.D + 1) + size_t(g.msf) * g.msf * g.N) * sizeof(cplx);
+    CbShape sh;
+    sh.half = g.L / 2;
+    sh.quarter = g.N / 4;
+    sh.pairs = g.msf * g.nplaq;
+    sh.G = std::max(1, std::min(kCbTileVecs, pow2_floor(std::max(1, kCbMaxThreads / sh.pairs))));
+    int nthreads = std::min(kCbMaxThreads, ((sh.pairs * sh.G + 31) / 32) * 32);
+    nthreads = std::max(nthreads, 64);
+    sh.Gp = std::max(1, std::min(kCbTileVecs, pow2_floor(std::max(1, nthreads / g.N))));
+    const size_t smem = size_t(kCbTileVecs) * (g.D + 1) * sizeof(cplx) + size_t(g.D + g.N) * sizeof(int);
     dim3 grid((g.D + kCbTileVecs - 1) / kCbTileVecs, a.batch);
-    cudaError_t e;
-    if (g.msf == 2) {
-        e = cudaFuncSetAttribute(cb_mult_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        cb_mult_kernel<2><<<grid, kCbThreads, smem, st>>>(g, a);
-    } else {
-        e = cudaFuncSetAttribute(cb_mult_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        cb_mult_kernel<4><<<grid, kCbThreads, smem, st>>>(g, a);
+    const bool realm = a.real_tables != 0;
+#define CB_LAUNCH(MSF, RM)                                                                                    \
+    {                                                                                                         \
+        cudaError_t e = cudaFuncSetAttribute(cb_mult_kernel<MSF, RM>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                             (int)smem);                                                      \
+        if (e != cudaSuccess) return e;                                                                       \
+        cb_mult_kernel<MSF, RM><<<grid, nthreads, smem, st>>>(g, a, sh);                                      \
     }
+    if (g.msf == 2) {
+        if (realm) CB_LAUNCH(2, true) else CB_LAUNCH(2, false)
+    } else {
+        if (realm) CB_LAUNCH(4, true) else CB_LAUNCH(4, false)
+    }
+#undef CB_LAUNCH
     return cudaGetLastError();
 }
 

@@ -54,8 +54,9 @@ const char* const kProfNames[DQMC_PROF_NCAT] = {"cb_mult", "gemm_dmma", "qrcp_fa
 int prof_category(const char* call) {
     if (!std::strncmp(call, "cb_launch", 9)) return 0;
     if (!std::strncmp(call, "gemm_launch", 11)) return 1;
-    if (!std::strncmp(call, "qrcp_factor", 11)) return 2;
-    if (!std::strncmp(call, "qr_form_q", 9)) return 3;
+    if (!std::strncmp(call, "qrcp_factor", 11) || !std::strncmp(call, "qr_blocked_factor", 17)) return 2;
+    if (!std::strncmp(call, "qr_form_q", 9) || !std::strncmp(call, "qr_blocked_form_q", 17) ||
+        !std::strncmp(call, "qr_blocked_apply_qh", 19)) return 3;
     if (!std::strncmp(call, "trsm_upper", 10)) return 4;
     if (!std::strncmp(call, "update_slice", 12)) return 5;
     return 6;
@@ -128,6 +129,7 @@ int sdw_bmult(dqmc_ctx* ctx, int op, cplx* A, long long strideA, int k2, int k1,
     a.stridePhi = (long long)phi_stride(ctx);
     a.strideTab = (long long)tab_stride(ctx);
     a.cbtab = ctx->cbtab;
+    a.real_tables = ctx->p.weakZflux ? 0 : 1;
     a.kcount = k2 - k1;
     if (o.ascending) { a.kfirst = k1 + 1; a.kstep = +1; }
     else { a.kfirst = k2; a.kstep = -1; }
@@ -154,6 +156,7 @@ int gemm(dqmc_ctx* ctx, int ta, int tb, const cplx* A, long long sA, const cplx*
     g.rowscale = rows; g.strideRow = sRow;
     g.colscale = cols; g.strideCol = sCol;
     g.kscale = ks; g.strideK = sK;
+    g.alpha = 1.0;
     g.beta = beta;
     g.batch = batch;
     CKL(gemm_launch(g, ctx->stream));
@@ -172,13 +175,22 @@ int udt_decompose(dqmc_ctx* ctx, cplx* work, long long sW, cplx* Qout, long long
         ctx->err = "udt_decompose: work and Q must be contiguous batches";
         return DQMC_ERR_STATE;
     }
-    CKL(qrcp_factor_launch(work, D, sW, tau, perm, cn, batch, ctx->stream));
-    CKL(qr_form_q_launch(work, tau, Qout, D, sW, batch, ctx->stream));
-    // d and T' go to contiguous scratch first (extract kernel uses the A stride), then are copied
-    // with the requested strides
     cplx* Ttmp = ctx->W[3] + size_t(off) * DD(ctx);
     double* dtmp = ctx->dtmp + size_t(off) * D;
-    CKL(qr_extract_dt_launch(work, perm, dtmp, Ttmp, D, sW, batch, ctx->stream));
+    if (ctx->stabilizer == 0) {
+        // column pre-pivoting into W[4], blocked Householder QR there, explicit Q from the block reflectors
+        cplx* ap = ctx->W[4] + size_t(off) * DD(ctx);
+        CKL(qr_prepivot_launch(work, sW, ap, sW, perm, cn, D, batch, ctx->stream));
+        CKL(qr_blocked_factor(ctx->qr, ap, D, sW, off, batch, ctx->stream));
+        CKL(qr_blocked_form_q(ctx->qr, Qout, D, sQ, off, batch, ctx->stream));
+        CKL(qr_extract_dt_launch(ap, perm, dtmp, Ttmp, D, sW, batch, ctx->stream));
+    } else {
+        CKL(qrcp_factor_launch(work, D, sW, tau, perm, cn, batch, ctx->stream));
+        CKL(qr_form_q_launch(work, tau, Qout, D, sW, batch, ctx->stream));
+        // d and T' go to contiguous scratch first (extract kernel uses the A stride), then are copied
+        // with the requested strides
+        CKL(qr_extract_dt_launch(work, perm, dtmp, Ttmp, D, sW, batch, ctx->stream));
+    }
     CK(cudaMemcpy2DAsync(dout, size_t(sd) * sizeof(double), dtmp, size_t(D) * sizeof(double),
                          size_t(D) * sizeof(double), batch, cudaMemcpyDeviceToDevice, ctx->stream));
     if (Tout) {
@@ -262,15 +274,29 @@ int green_from_udts(dqmc_ctx* ctx, const UdtView& r, const UdtView& l, cplx* Gou
     // H = (1/d_r^b) (Q_r^+ Q_l) (1/d_l^b) + d_r^s (T_r T_l^+) d_l^s
     RET(gemm(ctx, 1, 0, r.Q, r.sQ, l.Q, l.sQ, H, (long long)dd, rInvBig, D, lInvBig, D, nullptr, 0, 0.0, batch));
     RET(gemm(ctx, 0, 1, r.T, r.sT, l.T, l.sT, H, (long long)dd, rSmall, D, lSmall, D, nullptr, 0, 1.0, batch));
-    // H P = Q_h R_h
-    CKL(qrcp_factor_launch(H, D, (long long)dd, tau, perm, cn, batch, ctx->stream));
-    CKL(logdiag_accumulate_launch(H, logdet, D, (long long)dd, batch, ctx->stream));
-    CKL(qr_form_q_launch(H, tau, Qh, D, (long long)dd, batch, ctx->stream));
-    // Y = Q_h^+ (1/d_r^b) Q_r^+
-    RET(gemm(ctx, 1, 1, Qh, (long long)dd, r.Q, r.sQ, Yw, (long long)dd, nullptr, 0, nullptr, 0, rInvBig, D, 0.0,
-             batch));
-    // Z = P R_h^-1 Y
-    CKL(trsm_upper_launch(H, Yw, Zw, perm, D, (long long)dd, batch, ctx->stream));
+    if (ctx->stabilizer == 0) {
+        // H P = Q_h R_h with P fixed up front (columns by decreasing norm), blocked Householder QR
+        cplx* Hp = ctx->W[4] + size_t(off) * dd;
+        CKL(qr_prepivot_launch(H, (long long)dd, Hp, (long long)dd, perm, cn, D, batch, ctx->stream));
+        CKL(qr_blocked_factor(ctx->qr, Hp, D, (long long)dd, off, batch, ctx->stream));
+        CKL(logdiag_accumulate_launch(Hp, logdet, D, (long long)dd, batch, ctx->stream));
+        // Y = Q_h^+ ((1/d_r^b) Q_r^+): the block reflectors are applied directly, Q_h is never formed
+        CKL(launch_scaled_conj_transpose(r.Q, r.sQ, Yw, (long long)dd, rInvBig, D, D, batch, ctx->stream));
+        CKL(qr_blocked_apply_qh(ctx->qr, Yw, D, D, (long long)dd, off, batch, ctx->stream));
+        // Z = P R_h^-1 Y
+        CKL(trsm_upper_blocked(ctx->qr, Hp, Yw, Qh, D, (long long)dd, off, batch, ctx->stream));
+        CKL(permute_rows_launch(Qh, (long long)dd, Zw, (long long)dd, perm, D, batch, ctx->stream));
+    } else {
+        // H P = Q_h R_h
+        CKL(qrcp_factor_launch(H, D, (long long)dd, tau, perm, cn, batch, ctx->stream));
+        CKL(logdiag_accumulate_launch(H, logdet, D, (long long)dd, batch, ctx->stream));
+        CKL(qr_form_q_launch(H, tau, Qh, D, (long long)dd, batch, ctx->stream));
+        // Y = Q_h^+ (1/d_r^b) Q_r^+
+        RET(gemm(ctx, 1, 1, Qh, (long long)dd, r.Q, r.sQ, Yw, (long long)dd, nullptr, 0, nullptr, 0, rInvBig, D, 0.0,
+                 batch));
+        // Z = P R_h^-1 Y
+        CKL(trsm_upper_launch(H, Yw, Zw, perm, D, (long long)dd, batch, ctx->stream));
+    }
     // G = Q_l (1/d_l^b) Z
     RET(gemm(ctx, 0, 0, l.Q, l.sQ, Zw, (long long)dd, Gout, sG, nullptr, 0, nullptr, 0, lInvBig, D, 0.0, batch));
     return DQMC_OK;
@@ -659,7 +685,9 @@ int dqmc_create(const dqmc_params* params, int n_replicas, int device, dqmc_ctx*
     CK(dmalloc(&ctx->G, dd * nm));
     CK(dmalloc(&ctx->bkG, dd * nm));
     CK(dmalloc(&ctx->Gwrapped, dd * nm));
-    for (int i = 0; i < 4; ++i) CK(dmalloc(&ctx->W[i], dd * nm));
+    for (int i = 0; i < 5; ++i) CK(dmalloc(&ctx->W[i], dd * nm));
+    CK(qr_workspace_create(&ctx->qr, ctx->D, (int)nm));
+    ctx->stabilizer = std::getenv("DQMC_STABILIZER_FULL_PIVOT") ? 1 : 0;
     CK(dmalloc(&ctx->tQ, dd * nm));
     CK(dmalloc(&ctx->tT, dd * nm));
     CK(dmalloc(&ctx->tD, D * nm));
@@ -751,13 +779,14 @@ void dqmc_destroy(dqmc_ctx* ctx) {
         cudaSetDevice(ctx->device);
         cudaStreamSynchronize(ctx->stream);
     }
-    void* dev[] = {ctx->G, ctx->bkG, ctx->Gwrapped, ctx->W[0], ctx->W[1], ctx->W[2], ctx->W[3], ctx->tQ, ctx->tT, ctx->tD,
+    void* dev[] = {ctx->G, ctx->bkG, ctx->Gwrapped, ctx->W[0], ctx->W[1], ctx->W[2], ctx->W[3], ctx->W[4], ctx->tQ, ctx->tT, ctx->tD,
                    ctx->stQ, ctx->stT, ctx->stD, ctx->bkQ, ctx->bkT, ctx->bkD, ctx->phi, ctx->coshT, ctx->sinhT,
                    ctx->bkPhi, ctx->bkCosh, ctx->bkSinh, ctx->rvals, ctx->tau, ctx->perm, ctx->colnorm, ctx->vecA,
                    ctx->vecB, ctx->vecC, ctx->vecD, ctx->dtmp, ctx->logdet, ctx->bkLogdet, ctx->consistency, ctx->eyeM,
                    ctx->onesV, ctx->X, ctx->Y, ctx->rngbuf, ctx->cursor, ctx->ctrl, ctx->accepted, ctx->errflag,
                    ctx->actions, ctx->shiftbuf, ctx->cbtab, ctx->acceptedTotal};
     for (void* p : dev) if (p) cudaFree(p);
+    qr_workspace_destroy(&ctx->qr);
     void* host[] = {ctx->h_rng, ctx->h_cursor, ctx->h_scalars, ctx->h_ctrl, ctx->h_err, ctx->h_acc};
     for (void* p : host) if (p) cudaFreeHost(p);
     prof_collect(ctx);
@@ -794,7 +823,17 @@ int dqmc_dims(const dqmc_ctx* ctx, int32_t* out) {
     return DQMC_OK;
 }
 
-uint64_t dqmc_launch_count(const dqmc_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int dqmc_set_option(dqmc_ctx* ctx, int option, int value) {
+    if (!ctx) return DQMC_ERR_PARAM;
+    if (option == DQMC_OPT_STABILIZER && (value == DQMC_STAB_PREPIVOT_BLOCKED || value == DQMC_STAB_FULL_PIVOT)) {
+        ctx->stabilizer = value;
+        return DQMC_OK;
+    }
+    ctx->err = "dqmc_set_option: unknown option or value";
+    return DQMC_ERR_PARAM;
+}
+
+uint64_t dqmc_launch_count(const dqmc_ctx* ctx) { return ctx ? ctx->launches + ctx->qr.launches : 0; }
 
 // ---- RNG ---------------------------------------------------------------------------------------
 int dqmc_rng_seed(dqmc_ctx* ctx, int rep, uint32_t seed, uint32_t process_index) {
@@ -1074,6 +1113,7 @@ int dqmc_gemm_host(dqmc_ctx* ctx, int transa, int transb, int M, int N, int K, c
     g.C = dC; g.ldc = M; g.strideC = 0;
     g.rowscale = g.colscale = g.kscale = nullptr;
     g.strideRow = g.strideCol = g.strideK = 0;
+    g.alpha = 1.0;
     g.beta = 0.0;
     g.batch = 1;
     CKL(gemm_launch(g, ctx->stream));

@@ -33,7 +33,8 @@ struct CbLaunch {
     const double* coshT;   // [batch][(m+1)*N]
     const double* sinhT;   // [batch][(m+1)*N]
     long long stridePhi, strideTab;
-    const cplx* cbtab;     // plaquette tables, see cb_table_index()
+    const cplx* cbtab;     // Hermitian-compressed plaquette tables (cb_build_tables)
+    int real_tables;       // 1: all plaquette matrices are real (no magnetic flux)
     int kfirst, kstep, kcount;   // slices kfirst, kfirst+kstep, ...
     int rows;              // 0: vectors are columns (left multiply), 1: vectors are rows (right multiply)
     int k_then_v;          // 1: hopping stage first, then potential stage; 0: the other order
@@ -52,6 +53,8 @@ cudaError_t cb_launch(const CbGeom& g, const CbLaunch& a, cudaStream_t st);
 // dense elementwise helpers (misc_kernels.cu)
 cudaError_t launch_set_identity(cplx* A, int D, long long stride, int batch, cudaStream_t st);
 cudaError_t launch_conj_transpose(const cplx* A, cplx* B, int D, long long stride, int batch, cudaStream_t st);
+cudaError_t launch_scaled_conj_transpose(const cplx* A, long long strideA, cplx* B, long long strideB,
+                                         const double* rowscale, long long strideS, int D, int batch, cudaStream_t st);
 cudaError_t launch_max_abs_diff(const cplx* A, const cplx* B, int D, long long stride, int batch,
                                 double* out, cudaStream_t st);
 cudaError_t launch_update_tables(const double* phi, double* coshT, double* sinhT, int N, int opdim, int m,
@@ -72,7 +75,7 @@ cudaError_t launch_cursor_advance(int* cursor, int rep, int n, cudaStream_t st);
 
 // ------------------------------------------------------------------------------------------------
 // Batched complex GEMM on FP64 tensor cores (gemm_kernels.cu)
-//   C = rowscale .* (op(A) * diag(kscale) * op(B)) .* colscale + beta * C
+//   C = alpha * rowscale .* (op(A) * diag(kscale) * op(B)) .* colscale + beta * C
 // ------------------------------------------------------------------------------------------------
 struct GemmArgs {
     int M, N, K;
@@ -83,6 +86,7 @@ struct GemmArgs {
     const double* rowscale; long long strideRow;   // optional, length M
     const double* colscale; long long strideCol;   // optional, length N
     const double* kscale; long long strideK;       // optional, length K
+    double alpha;                 // scalar factor of the product
     double beta;                  // 0 or 1
     int batch;
 };
@@ -105,6 +109,31 @@ cudaError_t qr_extract_dt_launch(const cplx* A, const int* perm, double* d, cplx
 // (perm may be null = identity).  Y is overwritten.
 cudaError_t trsm_upper_launch(const cplx* A, cplx* Y, cplx* Zout, const int* perm, int D, long long strideA,
                               int batch, cudaStream_t st);
+// ---- blocked QR with column pre-pivoting (compact WY, trailing updates on the DMMA GEMM) ----------
+struct QrWorkspace {
+    int D, batch, nb;
+    cplx* V;       // [batch][D*D] explicit unit-lower-trapezoidal reflectors of the last factorisation
+    cplx* VT;      // [batch][D*D] V * T of every panel
+    cplx* W;       // [batch][nb*D] panel products
+    cplx* Rinv;    // [batch][nb*(D+nb)] inverted diagonal blocks of R
+    uint64_t launches;   // kernels launched by the drivers below (for dqmc_launch_count)
+};
+int qr_choose_nb(int D);
+cudaError_t qr_workspace_create(QrWorkspace* ws, int D, int batch);
+void qr_workspace_destroy(QrWorkspace* ws);
+// perm = columns by decreasing norm (ties by index); Aout[:, j] = A[:, perm[j]]
+cudaError_t qr_prepivot_launch(const cplx* A, long long strideA, cplx* Aout, long long strideOut, int* perm,
+                               double* norms, int D, int batch, cudaStream_t st);
+// out[perm[j], :] = in[j, :]
+cudaError_t permute_rows_launch(const cplx* in, long long strideIn, cplx* out, long long strideOut, const int* perm,
+                                int D, int batch, cudaStream_t st);
+// `off` = index of the first matrix of this call inside the workspace
+cudaError_t qr_blocked_factor(QrWorkspace& ws, cplx* A, int D, long long strideA, int off, int batch, cudaStream_t st);
+cudaError_t qr_blocked_form_q(QrWorkspace& ws, cplx* Q, int D, long long strideQ, int off, int batch, cudaStream_t st);
+cudaError_t qr_blocked_apply_qh(QrWorkspace& ws, cplx* C, int D, int ncols, long long strideC, int off, int batch,
+                                cudaStream_t st);
+cudaError_t trsm_upper_blocked(QrWorkspace& ws, const cplx* A, cplx* Y, cplx* Zout, int D, long long strideA, int off,
+                               int batch, cudaStream_t st);
 // split scales: big[i] = 1/max(d,1), small[i] = min(d,1); also sum log max(d,1) -> logacc (+=)
 cudaError_t scale_split_launch(const double* d, double* inv_big, double* small_, double* logacc, int D,
                                int batch, cudaStream_t st);
@@ -167,7 +196,9 @@ struct dqmc_ctx {
     // device buffers
     dqmc::cplx* G;         // [nmat][D*D]
     dqmc::cplx* Gwrapped;  // copy of G before an advance (green consistency)
-    dqmc::cplx* W[4];      // scratch [nmat][D*D]
+    dqmc::cplx* W[5];      // scratch [nmat][D*D]
+    dqmc::QrWorkspace qr;  // blocked-QR workspace (V, V*T, panel products)
+    int stabilizer;        // 0: blocked QR with column pre-pivoting (default), 1: fully pivoted one-CTA QR
     dqmc::cplx* tQ; dqmc::cplx* tT; double* tD;   // temporary UDT of an advance step
     dqmc::cplx* eyeM; double* onesV;              // shared identity UDT (batch stride 0)
     dqmc::cplx* stQ;       // UDT storage [nmat][n+1][D*D]

@@ -6,7 +6,7 @@
 // (dethubbard.h:299-337).  tcgen05 has no f64 kind; on Blackwell FP64 matrix math is the warp-level
 // mma.sync DMMA path (SASS: DMMA.8x8x4).
 //
-//   C = rowscale .* ( op(A) * diag(kscale) * op(B) ) .* colscale + beta * C,   op = N | conj-transpose
+//   C = alpha * rowscale .* ( op(A) * diag(kscale) * op(B) ) .* colscale + beta * C,   op = N | conj-transpose
 //
 // Complex arithmetic = 4 real DMMAs per k-step on planar (re / im) shared-memory tiles; the planar
 // split, the conjugation, the transposition and the three diagonal scalings are fused into the
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(32 * WM * WN) zgemm_dmma_kernel(GemmArgs g) {
             for (int e = 0; e < 2; ++e) {
                 const int gn = n0 + wn * (8 * NB) + nb * 8 + 2 * t4 + e;
                 if (gn >= g.N) continue;
-                const double sc = rsc * (cs ? cs[gn] : 1.0);
+                const double sc = g.alpha * rsc * (cs ? cs[gn] : 1.0);
                 cplx v = make_double2(acc_re[mb][nb][e] * sc, acc_im[mb][nb][e] * sc);
                 cplx* dst = Cm + size_t(gn) * g.ldc + gm;
                 if (g.beta != 0.0) { const cplx o = *dst; v.x += o.x; v.y += o.y; }
@@ -208,9 +208,12 @@ cudaError_t launch_cfg(const GemmArgs& g, cudaStream_t st) {
 
 cudaError_t gemm_launch(const GemmArgs& g, cudaStream_t st) {
     if (g.batch <= 0 || g.M <= 0 || g.N <= 0) return cudaSuccess;
-    // 96 x 96 tiles when they fit the problem exactly (D = 288), otherwise 64 x 64
-    if (g.M % 96 == 0 && g.N % 96 == 0) return launch_cfg<4, 3, 3, 4>(g, st);   // 12 warps, 24 x 32 each
-    if (g.M <= 32 || g.N <= 32) return launch_cfg<1, 1, 4, 4>(g, st);
+    // 96 x 96 tiles when they fit the problem exactly (D = 288), otherwise 64 x 64; skinny shapes
+    // (the panel products of the blocked QR / triangular solve) get 32 x 64 and 64 x 32 tiles
+    if (g.M % 96 == 0 && g.N % 96 == 0 && g.K >= 64) return launch_cfg<4, 3, 3, 4>(g, st);   // 12 warps, 24 x 32 each
+    if (g.M <= 32 && g.N <= 32) return launch_cfg<1, 1, 4, 4>(g, st);
+    if (g.M <= 32) return launch_cfg<1, 4, 4, 2>(g, st);                       // 32 x 64, 4 warps
+    if (g.N <= 32) return launch_cfg<4, 1, 2, 4>(g, st);                       // 64 x 32, 4 warps
     return launch_cfg<2, 2, 4, 4>(g, st);
 }
 

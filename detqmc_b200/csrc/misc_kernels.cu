@@ -56,6 +56,29 @@ __global__ void conj_transpose_kernel(const cplx* A, cplx* B, int D, long long s
     }
 }
 
+// B[j, i] = rowscale[j] * conj(A[i, j])   (separate batch strides; strideA = 0 shares one input)
+__global__ void scaled_conj_transpose_kernel(const cplx* A, long long strideA, cplx* B, long long strideB,
+                                             const double* rowscale, long long strideS, int D) {
+    __shared__ cplx tile[32][33];
+    const cplx* a = A + size_t(blockIdx.z) * strideA;
+    cplx* bm = B + size_t(blockIdx.z) * strideB;
+    const double* rs = rowscale ? rowscale + size_t(blockIdx.z) * strideS : nullptr;
+    const int i0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
+    for (int jj = threadIdx.y; jj < 32; jj += blockDim.y) {
+        const int i = i0 + threadIdx.x, j = j0 + jj;
+        if (i < D && j < D) tile[jj][threadIdx.x] = a[size_t(j) * D + i];
+    }
+    __syncthreads();
+    for (int ii = threadIdx.y; ii < 32; ii += blockDim.y) {
+        const int j = j0 + threadIdx.x, i = i0 + ii;
+        if (i < D && j < D) {
+            cplx v = tile[threadIdx.x][ii];
+            const double sc = rs ? rs[j] : 1.0;
+            bm[size_t(i) * D + j] = make_double2(v.x * sc, -v.y * sc);
+        }
+    }
+}
+
 __global__ void max_abs_diff_kernel(const cplx* A, const cplx* B, int D, long long stride, double* out) {
     __shared__ double red[32];
     const cplx* a = A + size_t(blockIdx.x) * stride;
@@ -169,6 +192,13 @@ cudaError_t launch_set_identity(cplx* A, int D, long long stride, int batch, cud
     set_identity_kernel<<<grid, 256, 0, st>>>(A, D, stride);
     return cudaGetLastError();
 }
+cudaError_t launch_scaled_conj_transpose(const cplx* A, long long strideA, cplx* B, long long strideB,
+                                         const double* rowscale, long long strideS, int D, int batch, cudaStream_t st) {
+    dim3 grid((D + 31) / 32, (D + 31) / 32, batch), block(32, 8);
+    scaled_conj_transpose_kernel<<<grid, block, 0, st>>>(A, strideA, B, strideB, rowscale, strideS, D);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_conj_transpose(const cplx* A, cplx* B, int D, long long stride, int batch, cudaStream_t st) {
     dim3 grid((D + 31) / 32, (D + 31) / 32, batch);
     conj_transpose_kernel<<<grid, dim3(32, 8), 0, st>>>(A, B, D, stride);

@@ -12,6 +12,8 @@
 // norm exactly (no down-dating, so no cancellation).  Matrices are L2 resident (D x D x 16 B).
 #include "dqmc_internal.h"
 
+#include <algorithm>
+
 namespace dqmc {
 namespace {
 
@@ -335,7 +337,420 @@ __global__ void logdiag_kernel(const cplx* Aall, double* logacc, int D, long lon
     }
 }
 
+
+// =================================================================================================
+// Blocked Householder QR (compact WY) with column PRE-pivoting
+// =================================================================================================
+// Columns are ordered once by decreasing norm (the matrices of the stabilised chains, (B Q) diag(d),
+// are column graded, which is what pivoting has to catch; Bai, Lee, Li, Xu, "Stable solutions of
+// linear systems involving long chain of matrix multiplications", LAA 2011, sec. 3.2 "pre-pivoting"),
+// then a blocked QR without further column exchanges runs as
+//     panel factorisation (one CTA per matrix, panel resident in shared memory)
+//   + trailing update  A2 -= V (V T)^H A2  as two batched DMMA GEMMs over all SMs.
+// The panel kernel leaves R in A, and writes the explicit unit-lower-trapezoidal V and the product
+// V*T of every panel to the workspace, so that forming Q, applying Q^H and the trailing updates are
+// pure GEMMs.  The fully pivoted one-CTA kernels above stay as the cross-check of the tests.
+
+constexpr int kPanelThreads = 1024;
+constexpr int kPanelMaxNb = 32;
+
+__device__ __forceinline__ cplx cfma_(cplx a, cplx b, cplx c) {      // a*b + c
+    return make_double2(fma(a.x, b.x, fma(-a.y, b.y, c.x)), fma(a.x, b.y, fma(a.y, b.x, c.y)));
+}
+__device__ __forceinline__ cplx cfmac_(cplx a, cplx b, cplx c) {     // conj(a)*b + c
+    return make_double2(fma(a.x, b.x, fma(a.y, b.y, c.x)), fma(a.x, b.y, fma(-a.y, b.x, c.y)));
+}
+
+// squared column norms, then rank by counting: perm[rank] = column (descending, ties by index)
+__global__ void __launch_bounds__(1024) colnorm_rank_kernel(const cplx* Aall, int D, long long strideA, int* permAll,
+                                                            double* normAll) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* nrm = reinterpret_cast<double*>(smem_raw);            // [D]
+    const int b = blockIdx.x;
+    const cplx* A = Aall + size_t(b) * strideA;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    for (int c = warp; c < D; c += nwarps) {
+        const cplx* col = A + size_t(c) * D;
+        double s = 0;
+        for (int i = lane; i < D; i += 32) { const cplx v = col[i]; s = fma(v.x, v.x, fma(v.y, v.y, s)); }
+        s = warp_sum(s);
+        if (lane == 0) nrm[c] = s;
+    }
+    __syncthreads();
+    for (int j = tid; j < D; j += blockDim.x) {
+        const double nj = nrm[j];
+        int rank = 0;
+        for (int i = 0; i < D; ++i) {
+            const double ni = nrm[i];
+            rank += (ni > nj || (ni == nj && i < j)) ? 1 : 0;
+        }
+        permAll[size_t(b) * D + rank] = j;
+        if (normAll) normAll[size_t(b) * D + j] = nj;
+    }
+}
+
+// out[:, j] = in[:, perm[j]]
+__global__ void permute_columns_kernel(const cplx* inAll, cplx* outAll, const int* permAll, int D, long long strideIn,
+                                       long long strideOut) {
+    const int b = blockIdx.y, j = blockIdx.x;
+    const cplx* src = inAll + size_t(b) * strideIn + size_t(permAll[size_t(b) * D + j]) * D;
+    cplx* dst = outAll + size_t(b) * strideOut + size_t(j) * D;
+    for (int i = threadIdx.x; i < D; i += blockDim.x) dst[i] = src[i];
+}
+
+// out[perm[j], :] = in[j, :]
+__global__ void permute_rows_kernel(const cplx* inAll, cplx* outAll, const int* permAll, int D, long long strideIn,
+                                    long long strideOut) {
+    const int b = blockIdx.y, c = blockIdx.x;
+    const cplx* src = inAll + size_t(b) * strideIn + size_t(c) * D;
+    cplx* dst = outAll + size_t(b) * strideOut + size_t(c) * D;
+    const int* perm = permAll + size_t(b) * D;
+    for (int i = threadIdx.x; i < D; i += blockDim.x) dst[perm[i]] = src[i];
+}
+
+// Householder QR of the panel A[j0:D, j0:j0+nbc] of every matrix of the batch.
+__global__ void __launch_bounds__(kPanelThreads) qr_panel_kernel(cplx* Aall, long long strideA, int D, int j0, int nbc,
+                                                                 cplx* Vall, cplx* VTall, long long strideV) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int m = D - j0;
+    const int ldp = m | 1;                                          // odd leading dimension
+    cplx* P = reinterpret_cast<cplx*>(smem_raw);                    // [nbc][ldp]
+    cplx* Gm = P + size_t(nbc) * ldp;                               // [32][33] strict upper Gram of V
+    cplx* Tm = Gm + 32 * 33;                                        // [32][33] T factor
+    __shared__ cplx s_tau[kPanelMaxNb];
+    __shared__ double s_part[32];
+    __shared__ double s_norm;                                       // |x|^2 below the diagonal of the next column
+
+    const int b = blockIdx.x;
+    cplx* A = Aall + size_t(b) * strideA;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+
+    for (int idx = tid; idx < nbc * m; idx += blockDim.x) {
+        const int c = idx / m, i = idx - c * m;
+        P[c * ldp + i] = A[size_t(j0 + c) * D + j0 + i];
+    }
+    __syncthreads();
+    // norm^2 of rows 1.. of column 0
+    {
+        double xn = 0;
+        for (int i = 1 + tid; i < m; i += blockDim.x) { const cplx v = P[i]; xn = fma(v.x, v.x, fma(v.y, v.y, xn)); }
+        xn = warp_sum(xn);
+        if (lane == 0) s_part[warp] = xn;
+        __syncthreads();
+        if (warp == 0) {
+            xn = lane < nwarps ? s_part[lane] : 0.0;
+            xn = warp_sum(xn);
+            if (lane == 0) s_norm = xn;
+        }
+        __syncthreads();
+    }
+
+    for (int c = 0; c < nbc; ++c) {
+        cplx* colc = P + c * ldp;
+        // ---- reflector (zlarfg conventions); every thread computes the same scalars
+        const double xn = (c + 1 < m) ? s_norm : 0.0;
+        const cplx alpha = colc[c];
+        cplx tau, sc;
+        double beta;
+        if (xn == 0.0 && alpha.y == 0.0) {
+            tau = make_double2(0, 0);
+            sc = make_double2(0, 0);
+            beta = alpha.x;
+        } else {
+            const double nrm = sqrt(alpha.x * alpha.x + alpha.y * alpha.y + xn);
+            beta = alpha.x >= 0 ? -nrm : nrm;
+            tau = make_double2((beta - alpha.x) / beta, -alpha.y / beta);
+            const double dr = alpha.x - beta, di = alpha.y;
+            const double den = dr * dr + di * di;
+            sc = make_double2(dr / den, -di / den);
+        }
+        __syncthreads();                                            // everyone has read alpha / s_norm
+        for (int i = c + 1 + tid; i < m; i += blockDim.x) colc[i] = cmul(colc[i], sc);
+        if (tid == 0) { colc[c] = make_double2(beta, 0); s_tau[c] = tau; }
+        __syncthreads();
+        // ---- apply H_c^H = I - conj(tau) v v^H to the remaining panel columns, one warp per column;
+        // the warp that owns column c+1 also produces the norm for the next reflector
+        if (tau.x != 0.0 || tau.y != 0.0) {
+            const cplx ct = make_double2(tau.x, -tau.y);
+            for (int k = c + 1 + warp; k < nbc; k += nwarps) {
+                cplx* colk = P + k * ldp;
+                double wr = 0, wi = 0;
+                for (int i = c + lane; i < m; i += 32) {
+                    const cplx v = (i == c) ? make_double2(1, 0) : colc[i];
+                    const cplx w = cmulc(v, colk[i]);
+                    wr += w.x;
+                    wi += w.y;
+                }
+                wr = warp_sum(wr);
+                wi = warp_sum(wi);
+                const cplx fw = cmul(ct, make_double2(wr, wi));
+                double nn = 0;
+                for (int i = c + lane; i < m; i += 32) {
+                    const cplx v = (i == c) ? make_double2(1, 0) : colc[i];
+                    cplx a = colk[i];
+                    const cplx d = cmul(fw, v);
+                    a.x -= d.x;
+                    a.y -= d.y;
+                    colk[i] = a;
+                    if (i > c + 1) nn = fma(a.x, a.x, fma(a.y, a.y, nn));
+                }
+                if (k == c + 1) {
+                    nn = warp_sum(nn);
+                    if (lane == 0) s_norm = nn;
+                }
+            }
+        } else if (c + 1 < nbc && warp == 0) {
+            const cplx* colk = P + (c + 1) * ldp;
+            double nn = 0;
+            for (int i = c + 2 + lane; i < m; i += 32) { const cplx a = colk[i]; nn = fma(a.x, a.x, fma(a.y, a.y, nn)); }
+            nn = warp_sum(nn);
+            if (lane == 0) s_norm = nn;
+        }
+        __syncthreads();
+    }
+
+    // ---- Gram matrix of the reflectors, strict upper part: G[i][j] = v_i^H v_j  (i < j)
+    for (int i = warp; i < nbc; i += nwarps) {
+        const int j = lane;
+        if (j > i && j < nbc) {
+            const cplx* vi = P + i * ldp;
+            const cplx* vj = P + j * ldp;
+            cplx s = make_double2(vi[j].x, -vi[j].y);               // row j: conj(v_i[j]) * 1
+            for (int r = j + 1; r < m; ++r) s = cfmac_(vi[r], vj[r], s);
+            Gm[i * 33 + j] = s;
+        }
+    }
+    __syncthreads();
+    // ---- T = (diag(1/tau) + strict_upper(G))^-1, column by column (zlarft, forward / columnwise)
+    if (tid < nbc) {
+        const int c = tid;
+        Tm[c * 33 + c] = s_tau[c];
+        for (int i = c - 1; i >= 0; --i) {
+            cplx s = make_double2(0, 0);
+            for (int l = i + 1; l <= c; ++l) s = cfma_(Gm[i * 33 + l], Tm[l * 33 + c], s);
+            const cplx ti = s_tau[i];
+            Tm[i * 33 + c] = make_double2(-(ti.x * s.x - ti.y * s.y), -(ti.x * s.y + ti.y * s.x));
+        }
+    }
+    __syncthreads();
+    // ---- write back: R (and v below it) to A, explicit V and V*T to the workspace
+    cplx* V = Vall + size_t(b) * strideV;
+    cplx* VT = VTall + size_t(b) * strideV;
+    for (int idx = tid; idx < nbc * m; idx += blockDim.x) {
+        const int c = idx / m, r = idx - c * m;
+        const cplx pv = P[c * ldp + r];
+        A[size_t(j0 + c) * D + j0 + r] = pv;
+        V[size_t(j0 + c) * D + j0 + r] = r > c ? pv : make_double2(r == c ? 1.0 : 0.0, 0.0);
+        // (V T)[r, c] = sum_{l <= min(c, r)} V[r, l] T[l, c]
+        cplx s = make_double2(0, 0);
+        const int lmax = min(c, r);
+        for (int l = 0; l <= lmax; ++l) {
+            const cplx vl = (l == r) ? make_double2(1, 0) : P[l * ldp + r];
+            s = cfma_(vl, Tm[l * 33 + c], s);
+        }
+        VT[size_t(j0 + c) * D + j0 + r] = s;
+    }
+}
+
+// inverse of every nb x nb diagonal block of the upper-triangular R (stored in A): out [batch][P][nb*nb]
+__global__ void trtri_blocks_kernel(const cplx* Aall, long long strideA, int D, int nb, cplx* outAll, long long strideOut) {
+    __shared__ cplx Rs[32 * 33], Xs[32 * 33];
+    const int b = blockIdx.y, p = blockIdx.x;
+    const int j0 = p * nb, nbc = min(nb, D - j0);
+    const cplx* A = Aall + size_t(b) * strideA;
+    for (int idx = threadIdx.x; idx < nbc * nbc; idx += blockDim.x) {
+        const int c = idx / nbc, r = idx - c * nbc;
+        Rs[r * 33 + c] = A[size_t(j0 + c) * D + j0 + r];
+    }
+    __syncthreads();
+    if (threadIdx.x < nbc) {
+        const int c = threadIdx.x;
+        for (int i = nbc - 1; i > c; --i) Xs[i * 33 + c] = make_double2(0, 0);
+        const cplx rc = Rs[c * 33 + c];
+        const double dc = rc.x * rc.x + rc.y * rc.y;
+        Xs[c * 33 + c] = make_double2(rc.x / dc, -rc.y / dc);
+        for (int i = c - 1; i >= 0; --i) {
+            cplx s = make_double2(0, 0);
+            for (int l = i + 1; l <= c; ++l) s = cfma_(Rs[i * 33 + l], Xs[l * 33 + c], s);
+            const cplx ri = Rs[i * 33 + i];
+            const double di = ri.x * ri.x + ri.y * ri.y;
+            // -s / r_ii
+            Xs[i * 33 + c] = make_double2(-(s.x * ri.x + s.y * ri.y) / di, -(s.y * ri.x - s.x * ri.y) / di);
+        }
+    }
+    __syncthreads();
+    cplx* out = outAll + size_t(b) * strideOut + size_t(p) * nb * nb;
+    for (int idx = threadIdx.x; idx < nbc * nbc; idx += blockDim.x) {
+        const int c = idx / nbc, r = idx - c * nbc;
+        out[c * nb + r] = Xs[r * 33 + c];
+    }
+}
+
+inline GemmArgs gemm_args(int M, int N, int K, int ta, int tb, const cplx* A, int lda, long long sA, const cplx* B,
+                          int ldb, long long sB, cplx* C, int ldc, long long sC, double alpha, double beta, int batch) {
+    GemmArgs g;
+    g.M = M; g.N = N; g.K = K; g.transa = ta; g.transb = tb;
+    g.A = A; g.lda = lda; g.strideA = sA;
+    g.B = B; g.ldb = ldb; g.strideB = sB;
+    g.C = C; g.ldc = ldc; g.strideC = sC;
+    g.rowscale = g.colscale = g.kscale = nullptr;
+    g.strideRow = g.strideCol = g.strideK = 0;
+    g.alpha = alpha; g.beta = beta; g.batch = batch;
+    return g;
+}
+
+#define QR_TRY(call)                                  \
+    do {                                              \
+        cudaError_t e__ = (call);                     \
+        if (e__ != cudaSuccess) return e__;           \
+    } while (0)
+
 }  // namespace
+
+// ---- blocked QR host drivers --------------------------------------------------------------------
+int qr_choose_nb(int D) {
+    // the panel (D x nb complex) plus the two 32 x 33 factors must fit the 227 KB of one CTA
+    for (int nb : {32, 16, 8, 4}) {
+        const size_t need = size_t(nb) * (D | 1) * sizeof(cplx) + 2 * 32 * 33 * sizeof(cplx) + 1024;
+        if (need <= 220 * 1024) return nb;
+    }
+    return 2;
+}
+
+cudaError_t qr_workspace_create(QrWorkspace* ws, int D, int batch) {
+    ws->D = D; ws->batch = batch; ws->nb = qr_choose_nb(D);
+    ws->launches = 0;
+    const size_t dd = size_t(D) * D;
+    QR_TRY(cudaMalloc(reinterpret_cast<void**>(&ws->V), sizeof(cplx) * dd * batch));
+    QR_TRY(cudaMalloc(reinterpret_cast<void**>(&ws->VT), sizeof(cplx) * dd * batch));
+    QR_TRY(cudaMalloc(reinterpret_cast<void**>(&ws->W), sizeof(cplx) * size_t(ws->nb) * D * batch));
+    QR_TRY(cudaMalloc(reinterpret_cast<void**>(&ws->Rinv), sizeof(cplx) * size_t(ws->nb) * (D + ws->nb) * batch));
+    QR_TRY(cudaMemset(ws->V, 0, sizeof(cplx) * dd * batch));
+    QR_TRY(cudaMemset(ws->VT, 0, sizeof(cplx) * dd * batch));
+    return cudaSuccess;
+}
+
+void qr_workspace_destroy(QrWorkspace* ws) {
+    cudaFree(ws->V); cudaFree(ws->VT); cudaFree(ws->W); cudaFree(ws->Rinv);
+    ws->V = ws->VT = ws->W = ws->Rinv = nullptr;
+}
+
+cudaError_t qr_prepivot_launch(const cplx* A, long long strideA, cplx* Aout, long long strideOut, int* perm,
+                               double* norms, int D, int batch, cudaStream_t st) {
+    colnorm_rank_kernel<<<batch, 1024, size_t(D) * sizeof(double), st>>>(A, D, strideA, perm, norms);
+    QR_TRY(cudaGetLastError());
+    dim3 grid(D, batch);
+    permute_columns_kernel<<<grid, 128, 0, st>>>(A, Aout, perm, D, strideA, strideOut);
+    return cudaGetLastError();
+}
+
+cudaError_t permute_rows_launch(const cplx* in, long long strideIn, cplx* out, long long strideOut, const int* perm,
+                                int D, int batch, cudaStream_t st) {
+    dim3 grid(D, batch);
+    permute_rows_kernel<<<grid, 128, 0, st>>>(in, out, perm, D, strideIn, strideOut);
+    return cudaGetLastError();
+}
+
+// A (already column-ordered) -> R in the upper triangle; V, V*T of all panels in ws (slices off ..)
+cudaError_t qr_blocked_factor(QrWorkspace& ws, cplx* A, int D, long long strideA, int off, int batch, cudaStream_t st) {
+    const int nb = ws.nb;
+    const size_t dd = size_t(D) * D;
+    cplx* V = ws.V + size_t(off) * dd;
+    cplx* VT = ws.VT + size_t(off) * dd;
+    cplx* W = ws.W + size_t(off) * nb * D;
+    const size_t smem = size_t(nb) * (D | 1) * sizeof(cplx) + 2 * 32 * 33 * sizeof(cplx);
+    QR_TRY(cudaFuncSetAttribute(qr_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (int j0 = 0; j0 < D; j0 += nb) {
+        const int nbc = std::min(nb, D - j0), m = D - j0, n2 = D - j0 - nbc;
+        const size_t sm = size_t(nbc) * (m | 1) * sizeof(cplx) + 2 * 32 * 33 * sizeof(cplx);
+        qr_panel_kernel<<<batch, kPanelThreads, sm, st>>>(A, strideA, D, j0, nbc, V, VT, (long long)dd);
+        QR_TRY(cudaGetLastError());
+        ws.launches += 1;
+        if (n2 > 0) {
+            const size_t po = size_t(j0) * D + j0;                  // panel origin
+            const size_t co = size_t(j0 + nbc) * D + j0;            // trailing block origin
+            // W = (V T)^H C ;  C -= V W
+            QR_TRY(gemm_launch(gemm_args(nbc, n2, m, 1, 0, VT + po, D, (long long)dd, A + co, D, strideA, W, nb,
+                                         (long long)nb * D, 1.0, 0.0, batch), st));
+            QR_TRY(gemm_launch(gemm_args(m, n2, nbc, 0, 0, V + po, D, (long long)dd, W, nb, (long long)nb * D, A + co, D,
+                                         strideA, -1.0, 1.0, batch), st));
+            ws.launches += 2;
+        }
+    }
+    return cudaSuccess;
+}
+
+// Q = H_0 H_1 ... H_{P-1} explicitly (zungqr, backward accumulation of the block reflectors)
+cudaError_t qr_blocked_form_q(QrWorkspace& ws, cplx* Q, int D, long long strideQ, int off, int batch, cudaStream_t st) {
+    const int nb = ws.nb;
+    const size_t dd = size_t(D) * D;
+    const cplx* V = ws.V + size_t(off) * dd;
+    const cplx* VT = ws.VT + size_t(off) * dd;
+    cplx* W = ws.W + size_t(off) * nb * D;
+    QR_TRY(launch_set_identity(Q, D, strideQ, batch, st));
+    ws.launches += 1;
+    const int np = (D + nb - 1) / nb;
+    for (int p = np - 1; p >= 0; --p) {
+        const int j0 = p * nb, nbc = std::min(nb, D - j0), m = D - j0;
+        const size_t po = size_t(j0) * D + j0;
+        // W = V^H Q[j0:, j0:] ;  Q[j0:, j0:] -= (V T) W
+        QR_TRY(gemm_launch(gemm_args(nbc, m, m, 1, 0, V + po, D, (long long)dd, Q + po, D, strideQ, W, nb, (long long)nb * D,
+                                     1.0, 0.0, batch), st));
+        QR_TRY(gemm_launch(gemm_args(m, m, nbc, 0, 0, VT + po, D, (long long)dd, W, nb, (long long)nb * D, Q + po, D, strideQ,
+                                     -1.0, 1.0, batch), st));
+        ws.launches += 2;
+    }
+    return cudaSuccess;
+}
+
+// C <- Q^H C for a D x ncols matrix C (ldc = D), panel by panel: C[j0:, :] -= V ((V T)^H C[j0:, :])
+cudaError_t qr_blocked_apply_qh(QrWorkspace& ws, cplx* C, int D, int ncols, long long strideC, int off, int batch,
+                                cudaStream_t st) {
+    const int nb = ws.nb;
+    const size_t dd = size_t(D) * D;
+    const cplx* V = ws.V + size_t(off) * dd;
+    const cplx* VT = ws.VT + size_t(off) * dd;
+    cplx* W = ws.W + size_t(off) * nb * D;
+    for (int j0 = 0; j0 < D; j0 += nb) {
+        const int nbc = std::min(nb, D - j0), m = D - j0;
+        const size_t po = size_t(j0) * D + j0;
+        QR_TRY(gemm_launch(gemm_args(nbc, ncols, m, 1, 0, VT + po, D, (long long)dd, C + j0, D, strideC, W, nb,
+                                     (long long)nb * D, 1.0, 0.0, batch), st));
+        QR_TRY(gemm_launch(gemm_args(m, ncols, nbc, 0, 0, V + po, D, (long long)dd, W, nb, (long long)nb * D, C + j0, D,
+                                     strideC, -1.0, 1.0, batch), st));
+        ws.launches += 2;
+    }
+    return cudaSuccess;
+}
+
+// Solve R Z = Y (R = upper triangle of A, D x D right-hand sides).  Y is destroyed, Z is written
+// to Zout.  Diagonal blocks are inverted once, everything else is GEMM.
+cudaError_t trsm_upper_blocked(QrWorkspace& ws, const cplx* A, cplx* Y, cplx* Zout, int D, long long strideA, int off,
+                               int batch, cudaStream_t st) {
+    const int nb = ws.nb;
+    const int np = (D + nb - 1) / nb;
+    const long long sR = (long long)nb * (D + nb);
+    cplx* Rinv = ws.Rinv + size_t(off) * sR;
+    dim3 grid(np, batch);
+    trtri_blocks_kernel<<<grid, 128, 0, st>>>(A, strideA, D, nb, Rinv, sR);
+    QR_TRY(cudaGetLastError());
+    ws.launches += 1;
+    for (int p = np - 1; p >= 0; --p) {
+        const int j0 = p * nb, nbc = std::min(nb, D - j0);
+        // Z_p = R_pp^-1 Y_p
+        QR_TRY(gemm_launch(gemm_args(nbc, D, nbc, 0, 0, Rinv + size_t(p) * nb * nb, nb, sR, Y + j0, D, strideA, Zout + j0, D,
+                                     strideA, 1.0, 0.0, batch), st));
+        ws.launches += 1;
+        if (j0 > 0) {
+            // Y[0:j0, :] -= R[0:j0, blk] Z_p
+            QR_TRY(gemm_launch(gemm_args(j0, D, nbc, 0, 0, A + size_t(j0) * D, D, strideA, Zout + j0, D, strideA, Y, D, strideA,
+                                         -1.0, 1.0, batch), st));
+            ws.launches += 1;
+        }
+    }
+    return cudaSuccess;
+}
+
 
 cudaError_t qrcp_factor_launch(cplx* A, int D, long long strideA, cplx* tau, int* perm, double* colnorm,
                                int batch, cudaStream_t st) {

@@ -59,7 +59,7 @@ class DetSDWBatch:
     """A batch of DetSDW replicas on one B200."""
 
     def __init__(self, pars=None, n_replicas=1, device=0, rng_indices=None, r_values=None, init="random",
-                 stream=None, **kw):
+                 stream=None, full_pivot=False, **kw):
         self.lib = load_library()
         self.cpars, self.pars = make_params(pars, **kw)
         self.R = int(n_replicas)
@@ -77,6 +77,8 @@ class DetSDWBatch:
         self.N, self.D, self.m, self.n, self.s, self.ngc, _, self.opdim = list(dims)
         if stream is not None:
             self.set_stream(stream)
+        if full_pivot:
+            self.set_stabilizer(True)
         if rng_indices is None:
             rng_indices = [self.pars["rngIndex"] + i for i in range(self.R)]
         for rep, idx in enumerate(rng_indices):
@@ -108,6 +110,10 @@ class DetSDWBatch:
 
     def set_stream(self, cuda_stream_ptr):
         self._ck(self.lib.dqmc_set_stream(self.h, c_vp(int(cuda_stream_ptr) if cuda_stream_ptr else None)))
+
+    def set_stabilizer(self, full_pivot):
+        """False (default): blocked QR with column pre-pivoting; True: fully pivoted one-CTA QR."""
+        self._ck(self.lib.dqmc_set_option(self.h, 0, 1 if full_pivot else 0))
 
     def synchronize(self):
         self._ck(self.lib.dqmc_synchronize(self.h))

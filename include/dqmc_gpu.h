@@ -98,6 +98,15 @@ int dqmc_set_stream(dqmc_ctx* ctx, void* cuda_stream);
 int dqmc_synchronize(dqmc_ctx* ctx);
 /* out[0..7] = {N, D (Green's-function dimension), m, n, s, n_green_components, n_replicas, opdim} */
 int dqmc_dims(const dqmc_ctx* ctx, int32_t* out);
+/* Numerical options (no reference twin).  DQMC_OPT_STABILIZER selects the factorisation behind the
+ * UDT chains (udvDecompose's role, udv.h:68-90):
+ *   DQMC_STAB_PREPIVOT_BLOCKED (default)  columns ordered once by decreasing norm, then blocked
+ *                                         Householder QR with tensor-core trailing updates;
+ *   DQMC_STAB_FULL_PIVOT                  Householder QR with full column pivoting, one CTA per matrix
+ *                                         (slow; kept as the cross-check of the tests). */
+enum { DQMC_OPT_STABILIZER = 0 };
+enum { DQMC_STAB_PREPIVOT_BLOCKED = 0, DQMC_STAB_FULL_PIVOT = 1 };
+int dqmc_set_option(dqmc_ctx* ctx, int option, int value);
 /* Number of kernels launched by this context so far (for bench.py's gpu_launches). */
 uint64_t dqmc_launch_count(const dqmc_ctx* ctx);
 

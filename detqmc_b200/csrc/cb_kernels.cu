@@ -36,8 +36,9 @@ namespace dqmc {
 // ------------------------------------------------------------------------------------------------
 // host: plaquette tables
 // ------------------------------------------------------------------------------------------------
-// One Hermitian 4x4 matrix = 8 cplx: {(d0,d1), (d2,d3), o01, o02, o03, o12, o13, o23}.
-// index: (((band*2 + sign_idx)*2 + pass) * nplaq + q) * 8
+// One Hermitian 4x4 matrix = 8 cplx components: {(d0,d1), (d2,d3), o01, o02, o03, o12, o13, o23}, stored
+// component-major so that consecutive threads (consecutive plaquettes q) read consecutive addresses:
+// index: (((band*2 + sign_idx)*2 + pass) * 8 + component) * nplaq + q
 // pass 0: subgroup 1, half step; pass 1: subgroup 0, full step times e^{-+dtau mu_band}.
 // Plaquette q of subgroup g sits at x = 2*(q % (L/2)) + g, y = 2*(q / (L/2)) + g.
 int cb_table_count(const CbGeom& g) { return 2 * 2 * 2 * g.nplaq * 8; }
@@ -132,16 +133,16 @@ void cb_build_tables(const dqmc_params& p, std::vector<cplx>& out) {
                         expm4(Hs, M);
                     }
                     // exp of a Hermitian block is Hermitian; symmetrise the round-off and compress
-                    cplx* dst = out.data() + (((size_t(band) * 2 + si) * 2 + pass) * nplaq + q) * 8;
+                    cplx* dst = out.data() + ((size_t(band) * 2 + si) * 2 + pass) * 8 * nplaq + q;
                     double dg[4];
                     for (int r = 0; r < 4; ++r) dg[r] = M[r * 4 + r].real() * ovfac;
-                    dst[0] = make_double2(dg[0], dg[1]);
-                    dst[1] = make_double2(dg[2], dg[3]);
+                    dst[0 * nplaq] = make_double2(dg[0], dg[1]);
+                    dst[1 * nplaq] = make_double2(dg[2], dg[3]);
                     int o = 2;
                     for (int r = 0; r < 4; ++r)
                         for (int c = r + 1; c < 4; ++c) {
                             const zc v = 0.5 * (M[r * 4 + c] + std::conj(M[c * 4 + r])) * ovfac;
-                            dst[o++] = make_double2(v.real(), v.imag());
+                            dst[size_t(o++) * nplaq] = make_double2(v.real(), v.imag());
                         }
                 }
             }
@@ -173,12 +174,13 @@ template <bool REALM>
 struct PlaqMat {
     double d[4];
     cplx o[6];      // o01 o02 o03 o12 o13 o23 (imaginary parts unused when REALM)
-    __device__ __forceinline__ void load(const cplx* __restrict__ M, bool conj) {
-        const cplx t0 = __ldg(M), t1 = __ldg(M + 1);
+    // M points at component 0 of this thread's plaquette; components are `stride` apart
+    __device__ __forceinline__ void load(const cplx* __restrict__ M, int stride, bool conj) {
+        const cplx t0 = __ldg(M), t1 = __ldg(M + stride);
         d[0] = t0.x; d[1] = t0.y; d[2] = t1.x; d[3] = t1.y;
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
-            o[i] = __ldg(M + 2 + i);
+            o[i] = __ldg(M + (2 + i) * stride);
             if (!REALM && conj) o[i].y = -o[i].y;
         }
     }
@@ -224,7 +226,7 @@ __device__ __forceinline__ void hopping_pass(cplx* tile, int ldt, int nv, const 
         const int q = p - bs * g.nplaq;
         const int band = bs & 1;       // XUP, YDOWN, XDOWN, YUP -> x, y, x, y
         PlaqMat<REALM> M;
-        M.load(tab + (((size_t(band) * 2 + sign_idx) * 2 + pass) * g.nplaq + q) * 8, transposed != 0);
+        M.load(tab + ((size_t(band) * 2 + sign_idx) * 2 + pass) * 8 * g.nplaq + q, g.nplaq, transposed != 0);
         int oi, oj, ok, ol;
         const int base = bs * g.N;
         if (pass == 1) {               // subgroup 0: (even, even) corner
@@ -318,17 +320,39 @@ __global__ void __launch_bounds__(kCbMaxThreads) cb_mult_kernel(CbGeom g, CbLaun
     }
     __syncthreads();
 
-    // ---- load the tile (coalesced along the contiguous direction of the column-major matrix)
+    // ---- load the tile (coalesced along the contiguous direction of the column-major matrix); the
+    // global loads of a thread are issued back to back (8 in flight) before the shared-memory stores
     if (!a.rows) {
-        for (int v = 0; v < nv; ++v) {
-            const cplx* src = A + size_t(v0 + v) * D;
-            cplx* t = tile + v * ldt;
-            for (int e = threadIdx.x; e < D; e += blockDim.x) t[sperm[e]] = src[e];
+        if (nv == kCbTileVecs) {
+            for (int e = threadIdx.x; e < D; e += blockDim.x) {
+                cplx buf[kCbTileVecs];
+#pragma unroll
+                for (int v = 0; v < kCbTileVecs; ++v) buf[v] = A[size_t(v0 + v) * D + e];
+                const int pos = sperm[e];
+#pragma unroll
+                for (int v = 0; v < kCbTileVecs; ++v) tile[v * ldt + pos] = buf[v];
+            }
+        } else {
+            for (int v = 0; v < nv; ++v) {
+                const cplx* src = A + size_t(v0 + v) * D;
+                cplx* t = tile + v * ldt;
+                for (int e = threadIdx.x; e < D; e += blockDim.x) t[sperm[e]] = src[e];
+            }
         }
     } else if (nv == kCbTileVecs) {
-        for (int idx = threadIdx.x; idx < kCbTileVecs * D; idx += blockDim.x) {
-            const int e = idx / kCbTileVecs, v = idx % kCbTileVecs;
-            tile[v * ldt + sperm[e]] = A[size_t(e) * D + v0 + v];
+        constexpr int U = 8;
+        for (int base = 0; base < kCbTileVecs * D; base += U * blockDim.x) {
+            cplx buf[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int idx = base + u * blockDim.x + threadIdx.x;
+                if (idx < kCbTileVecs * D) buf[u] = A[size_t(idx / kCbTileVecs) * D + v0 + idx % kCbTileVecs];
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int idx = base + u * blockDim.x + threadIdx.x;
+                if (idx < kCbTileVecs * D) tile[(idx % kCbTileVecs) * ldt + sperm[idx / kCbTileVecs]] = buf[u];
+            }
         }
     } else {
         for (int idx = threadIdx.x; idx < nv * D; idx += blockDim.x) {
@@ -366,14 +390,29 @@ __global__ void __launch_bounds__(kCbMaxThreads) cb_mult_kernel(CbGeom g, CbLaun
     // ---- store
     if (!a.rows) {
         const double* cs = a.colscale ? a.colscale + size_t(b) * a.strideScale : nullptr;
-        for (int v = 0; v < nv; ++v) {
-            cplx* dst = A + size_t(v0 + v) * D;
-            const cplx* t = tile + v * ldt;
-            const double sc = cs ? cs[v0 + v] : 1.0;
+        if (nv == kCbTileVecs) {
+            double sc[kCbTileVecs];
+#pragma unroll
+            for (int v = 0; v < kCbTileVecs; ++v) sc[v] = cs ? cs[v0 + v] : 1.0;
             for (int e = threadIdx.x; e < D; e += blockDim.x) {
-                cplx val = t[sperm[e]];
-                if (cs) { val.x *= sc; val.y *= sc; }
-                dst[e] = val;
+                const int pos = sperm[e];
+                cplx buf[kCbTileVecs];
+#pragma unroll
+                for (int v = 0; v < kCbTileVecs; ++v) buf[v] = tile[v * ldt + pos];
+#pragma unroll
+                for (int v = 0; v < kCbTileVecs; ++v)
+                    A[size_t(v0 + v) * D + e] = cs ? make_double2(buf[v].x * sc[v], buf[v].y * sc[v]) : buf[v];
+            }
+        } else {
+            for (int v = 0; v < nv; ++v) {
+                cplx* dst = A + size_t(v0 + v) * D;
+                const cplx* t = tile + v * ldt;
+                const double sc = cs ? cs[v0 + v] : 1.0;
+                for (int e = threadIdx.x; e < D; e += blockDim.x) {
+                    cplx val = t[sperm[e]];
+                    if (cs) { val.x *= sc; val.y *= sc; }
+                    dst[e] = val;
+                }
             }
         }
     } else if (nv == kCbTileVecs) {

@@ -58,7 +58,7 @@ int prof_category(const char* call) {
     if (!std::strncmp(call, "qr_form_q", 9) || !std::strncmp(call, "qr_blocked_form_q", 17) ||
         !std::strncmp(call, "qr_blocked_apply_qh", 19)) return 3;
     if (!std::strncmp(call, "trsm_upper", 10)) return 4;
-    if (!std::strncmp(call, "update_slice", 12)) return 5;
+    if (!std::strncmp(call, "update_", 7)) return 5;
     return 6;
 }
 cudaEvent_t prof_event(dqmc_ctx* ctx) {
@@ -156,7 +156,7 @@ int gemm(dqmc_ctx* ctx, int ta, int tb, const cplx* A, long long sA, const cplx*
     g.rowscale = rows; g.strideRow = sRow;
     g.colscale = cols; g.strideCol = sCol;
     g.kscale = ks; g.strideK = sK;
-    g.alpha = 1.0;
+    g.alpha = 1.0; g.kvec = nullptr; g.b_kmajor = 0;
     g.beta = beta;
     g.batch = batch;
     CKL(gemm_launch(g, ctx->stream));
@@ -164,6 +164,9 @@ int gemm(dqmc_ctx* ctx, int ta, int tb, const cplx* A, long long sA, const cplx*
 }
 
 // M (in `work`, destroyed) -> Q, d, T' with M = Q diag(d) T'
+// the rank-K flush of the delayed updates is accounted to the update family, not to the GEMMs
+inline cudaError_t update_flush_gemm(const GemmArgs& g, cudaStream_t st) { return gemm_launch(g, st); }
+
 int udt_decompose(dqmc_ctx* ctx, cplx* work, long long sW, cplx* Qout, long long sQ, double* dout, long long sd,
                   cplx* Tout, long long sT, int off, int batch) {
     const int D = ctx->D;
@@ -481,7 +484,29 @@ int launch_update(dqmc_ctx* ctx, int k, int therm) {
     a.k = k;
     a.thermalization = therm;
     a.batch = ctx->R;
-    CKL(update_slice_launch(ctx->umodel, a, ctx->stream));
+    a.site_state = ctx->siteState;
+    a.kvec = ctx->kvec;
+    // small delay blocks (Woodbury = 1) are flushed inside the kernel; otherwise every round is
+    // followed by the rank-K update G += X Y on all SMs
+    a.inline_flush = ctx->p.delaySteps < 8 ? 1 : 0;
+    const int rounds = update_rounds_per_slice(ctx->umodel, a.inline_flush);
+    for (int rd = 0; rd < rounds; ++rd) {
+        a.round = rd;
+        CKL(update_round_launch(ctx->umodel, a, ctx->stream));
+        if (!a.inline_flush) {
+            GemmArgs g;
+            g.M = g.N = ctx->D; g.K = ctx->kmax;
+            g.transa = g.transb = 0;
+            g.A = ctx->X; g.lda = ctx->D; g.strideA = a.strideXY;
+            g.B = ctx->Y; g.ldb = ctx->D; g.strideB = a.strideXY; g.b_kmajor = 1;
+            g.C = ctx->G; g.ldc = ctx->D; g.strideC = (long long)DD(ctx);
+            g.rowscale = g.colscale = g.kscale = nullptr;
+            g.strideRow = g.strideCol = g.strideK = 0;
+            g.alpha = 1.0; g.beta = 1.0; g.kvec = ctx->kvec;
+            g.batch = ctx->R;
+            CKL(update_flush_gemm(g, ctx->stream));
+        }
+    }
     return DQMC_OK;
 }
 
@@ -732,6 +757,8 @@ int dqmc_create(const dqmc_params* params, int n_replicas, int device, dqmc_ctx*
     CK(dmalloc(&ctx->cursor, R));
     CK(dmalloc(&ctx->ctrl, R));
     CK(dmalloc(&ctx->accepted, R));
+    CK(dmalloc(&ctx->siteState, R));
+    CK(dmalloc(&ctx->kvec, R));
     CK(dmalloc(&ctx->errflag, 1));
     CK(dmalloc(&ctx->actions, R));
     CK(dmalloc(&ctx->shiftbuf, 3 * R));
@@ -784,7 +811,7 @@ void dqmc_destroy(dqmc_ctx* ctx) {
                    ctx->bkPhi, ctx->bkCosh, ctx->bkSinh, ctx->rvals, ctx->tau, ctx->perm, ctx->colnorm, ctx->vecA,
                    ctx->vecB, ctx->vecC, ctx->vecD, ctx->dtmp, ctx->logdet, ctx->bkLogdet, ctx->consistency, ctx->eyeM,
                    ctx->onesV, ctx->X, ctx->Y, ctx->rngbuf, ctx->cursor, ctx->ctrl, ctx->accepted, ctx->errflag,
-                   ctx->actions, ctx->shiftbuf, ctx->cbtab, ctx->acceptedTotal};
+                   ctx->actions, ctx->shiftbuf, ctx->cbtab, ctx->acceptedTotal, ctx->siteState, ctx->kvec};
     for (void* p : dev) if (p) cudaFree(p);
     qr_workspace_destroy(&ctx->qr);
     void* host[] = {ctx->h_rng, ctx->h_cursor, ctx->h_scalars, ctx->h_ctrl, ctx->h_err, ctx->h_acc};
@@ -1113,7 +1140,7 @@ int dqmc_gemm_host(dqmc_ctx* ctx, int transa, int transb, int M, int N, int K, c
     g.C = dC; g.ldc = M; g.strideC = 0;
     g.rowscale = g.colscale = g.kscale = nullptr;
     g.strideRow = g.strideCol = g.strideK = 0;
-    g.alpha = 1.0;
+    g.alpha = 1.0; g.kvec = nullptr; g.b_kmajor = 0;
     g.beta = 0.0;
     g.batch = 1;
     CKL(gemm_launch(g, ctx->stream));

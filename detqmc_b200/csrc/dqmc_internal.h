@@ -87,6 +87,8 @@ struct GemmArgs {
     const double* colscale; long long strideCol;   // optional, length N
     const double* kscale; long long strideK;       // optional, length K
     double alpha;                 // scalar factor of the product
+    int b_kmajor;                 // rank-update path only: B element (k, n) is stored at B[k*ldb + n]
+    const int* kvec;              // optional per-matrix K (<= K; rank-update path only), device pointer
     double beta;                  // 0 or 1
     int batch;
 };
@@ -166,8 +168,15 @@ struct UpdateArgs {
     int k;                        // time slice
     int thermalization;
     int batch;
+    int round;                    // 0 .. rounds-1 within the slice
+    int inline_flush;             // 1: the CTA applies G += X Y itself and finishes the slice in one launch
+    int* site_state;              // [batch] next site to visit (carried from round to round)
+    int* kvec;                    // [batch] K = MSF * (#accepted in this round) for the rank-K flush
 };
-cudaError_t update_slice_launch(const UpdateModel& m, const UpdateArgs& a, cudaStream_t st);
+// one round of the delayed local updates; with inline_flush == 0 the caller applies
+// G += X[:, :kvec] Y[:kvec, :] (rank-K update GEMM) after every round
+int update_rounds_per_slice(const UpdateModel& m, int inline_flush);
+cudaError_t update_round_launch(const UpdateModel& m, const UpdateArgs& a, cudaStream_t st);
 
 }  // namespace dqmc
 
@@ -239,6 +248,8 @@ struct dqmc_ctx {
     uint64_t profCount[DQMC_PROF_NCAT];
     dqmc_control_data* ctrl;      // [R] device
     uint32_t* accepted;    // [R]
+    int* siteState;        // [R] delayed-update rounds: next site
+    int* kvec;             // [R] delayed-update rounds: pending rank
     int* errflag;
     double* actions;       // [R]
     double* shiftbuf;      // [R][3]

@@ -192,6 +192,140 @@ __global__ void __launch_bounds__(32 * WM * WN) zgemm_dmma_kernel(GemmArgs g) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Rank-K update  C += alpha * A(M x K) * B(K x N)  for small K (one shared-memory pass per 32): the delayed-update flush G += X*Y
+// (detsdwopdim.cpp:3156), the block-reflector updates of the QR (A2 -= V W) and the triangular
+// solve.  The whole K extent of both panels is staged in shared memory once (one barrier), the
+// accumulators START from the C tile (its global loads are in flight while the panels are staged)
+// and the epilogue is a plain store.  `kvec` (optional) gives a per-matrix K <= g.K; K = 0 skips
+// the matrix.  Algorithmic traffic is dominated by C (read + write): the kernel is HBM/L2 bound.
+// ------------------------------------------------------------------------------------------------
+constexpr int KT = 32;
+
+template <int WM, int WN, int MB, int NB>
+__global__ void __launch_bounds__(32 * WM * WN) zgemm_rank_update_kernel(GemmArgs g) {
+    constexpr int TM = 8 * MB * WM, TN = 8 * NB * WN, LDM = TM + 8, LDN = TN + 8, NT = 32 * WM * WN;
+    extern __shared__ __align__(16) double smem[];
+    double* As_re = smem;
+    double* As_im = As_re + KT * LDM;
+    double* Bs_re = As_im + KT * LDM;
+    double* Bs_im = Bs_re + KT * LDN;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int wm = warp % WM, wn = warp / WM;
+    const int grp = lane >> 2, t4 = lane & 3;
+    const int b = blockIdx.z;
+    const int m0 = blockIdx.x * TM, n0 = blockIdx.y * TN;
+    const int K = g.kvec ? min(g.kvec[b], g.K) : g.K;
+    if (K <= 0) return;
+
+    const cplx* __restrict__ A = g.A + size_t(b) * g.strideA;
+    const cplx* __restrict__ B = g.B + size_t(b) * g.strideB;
+    cplx* __restrict__ Cm = g.C + size_t(b) * g.strideC;
+
+    // accumulators start from C
+    double acc_re[MB][NB][2], acc_im[MB][NB][2];
+#pragma unroll
+    for (int mb = 0; mb < MB; ++mb) {
+        const int gm = m0 + wm * (8 * MB) + mb * 8 + grp;
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int gn = n0 + wn * (8 * NB) + nb * 8 + 2 * t4 + e;
+                cplx c = make_double2(0, 0);
+                if (gm < g.M && gn < g.N) c = Cm[size_t(gn) * g.ldc + gm];
+                acc_re[mb][nb][e] = c.x;
+                acc_im[mb][nb][e] = c.y;
+            }
+    }
+    // stage alpha * A[m0: , kc:kc+KT] and B[kc:kc+KT, n0: ] (planar, zero padded to a multiple of 4 in k);
+    // K <= KT (the common case) needs a single pass and a single barrier
+    for (int kc = 0; kc < K; kc += KT) {
+        const int Kc = min(KT, K - kc);
+        const int K4 = (Kc + 3) & ~3;
+        if (kc > 0) __syncthreads();
+        for (int idx = tid; idx < TM * K4; idx += NT) {
+            const int mm = idx % TM, kk = idx / TM;
+            const int gm = m0 + mm;
+            cplx v = make_double2(0, 0);
+            if (gm < g.M && kk < Kc) v = A[size_t(kc + kk) * g.lda + gm];
+            As_re[kk * LDM + mm] = g.alpha * v.x;
+            As_im[kk * LDM + mm] = g.alpha * v.y;
+        }
+        if (g.b_kmajor) {
+            for (int idx = tid; idx < TN * K4; idx += NT) {
+                const int nn = idx % TN, kk = idx / TN;
+                const int gn = n0 + nn;
+                cplx v = make_double2(0, 0);
+                if (gn < g.N && kk < Kc) v = B[size_t(kc + kk) * g.ldb + gn];
+                Bs_re[kk * LDN + nn] = v.x;
+                Bs_im[kk * LDN + nn] = v.y;
+            }
+        } else {
+            for (int idx = tid; idx < TN * K4; idx += NT) {
+                const int kk = idx % K4, nn = idx / K4;
+                const int gn = n0 + nn;
+                cplx v = make_double2(0, 0);
+                if (gn < g.N && kk < Kc) v = B[size_t(gn) * g.ldb + kc + kk];
+                Bs_re[kk * LDN + nn] = v.x;
+                Bs_im[kk * LDN + nn] = v.y;
+            }
+        }
+        __syncthreads();
+        for (int k4 = 0; k4 < K4; k4 += 4) {
+            double ar[MB], ai[MB], nai[MB], br[NB], bi[NB];
+#pragma unroll
+            for (int mb = 0; mb < MB; ++mb) {
+                const int off = (k4 + t4) * LDM + wm * (8 * MB) + mb * 8 + grp;
+                ar[mb] = As_re[off];
+                ai[mb] = As_im[off];
+                nai[mb] = -ai[mb];
+            }
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb) {
+                const int off = (k4 + t4) * LDN + wn * (8 * NB) + nb * 8 + grp;
+                br[nb] = Bs_re[off];
+                bi[nb] = Bs_im[off];
+            }
+#pragma unroll
+            for (int mb = 0; mb < MB; ++mb)
+#pragma unroll
+                for (int nb = 0; nb < NB; ++nb) {
+                    dmma(acc_re[mb][nb][0], acc_re[mb][nb][1], ar[mb], br[nb]);
+                    dmma(acc_re[mb][nb][0], acc_re[mb][nb][1], nai[mb], bi[nb]);
+                    dmma(acc_im[mb][nb][0], acc_im[mb][nb][1], ar[mb], bi[nb]);
+                    dmma(acc_im[mb][nb][0], acc_im[mb][nb][1], ai[mb], br[nb]);
+                }
+        }
+    }
+#pragma unroll
+    for (int mb = 0; mb < MB; ++mb) {
+        const int gm = m0 + wm * (8 * MB) + mb * 8 + grp;
+        if (gm >= g.M) continue;
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int gn = n0 + wn * (8 * NB) + nb * 8 + 2 * t4 + e;
+                if (gn >= g.N) continue;
+                Cm[size_t(gn) * g.ldc + gm] = make_double2(acc_re[mb][nb][e], acc_im[mb][nb][e]);
+            }
+    }
+}
+
+template <int WM, int WN, int MB, int NB>
+cudaError_t launch_rank_update(const GemmArgs& g, cudaStream_t st) {
+    constexpr int TM = 8 * MB * WM, TN = 8 * NB * WN;
+    const size_t smem = size_t(2) * KT * (TM + 8 + TN + 8) * sizeof(double);
+    cudaError_t e = cudaFuncSetAttribute(zgemm_rank_update_kernel<WM, WN, MB, NB>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    dim3 grid((g.M + TM - 1) / TM, (g.N + TN - 1) / TN, g.batch);
+    zgemm_rank_update_kernel<WM, WN, MB, NB><<<grid, 32 * WM * WN, smem, st>>>(g);
+    return cudaGetLastError();
+}
+
 template <int WM, int WN, int MB, int NB>
 cudaError_t launch_cfg(const GemmArgs& g, cudaStream_t st) {
     typedef GemmCfg<WM, WN, MB, NB> C;
@@ -208,6 +342,11 @@ cudaError_t launch_cfg(const GemmArgs& g, cudaStream_t st) {
 
 cudaError_t gemm_launch(const GemmArgs& g, cudaStream_t st) {
     if (g.batch <= 0 || g.M <= 0 || g.N <= 0) return cudaSuccess;
+    if ((g.K <= KT || g.kvec) && !g.transa && !g.transb && g.beta == 1.0 && !g.rowscale && !g.colscale && !g.kscale) {
+        if (g.M % 96 == 0 && g.N % 96 == 0) return launch_rank_update<4, 3, 3, 4>(g, st);
+        if ((g.M > 32 && g.N > 32) || g.kvec) return launch_rank_update<2, 2, 4, 4>(g, st);
+    }
+    if (g.kvec || g.b_kmajor) return cudaErrorInvalidValue;           // per-matrix K exists on the rank-update path only
     // 96 x 96 tiles when they fit the problem exactly (D = 288), otherwise 64 x 64; skinny shapes
     // (the panel products of the blocked QR / triangular solve) get 32 x 64 and 64 x 32 tiles
     if (g.M % 96 == 0 && g.N % 96 == 0 && g.K >= 64) return launch_cfg<4, 3, 3, 4>(g, st);   // 12 warps, 24 x 32 each

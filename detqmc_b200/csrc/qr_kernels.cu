@@ -595,7 +595,7 @@ inline GemmArgs gemm_args(int M, int N, int K, int ta, int tb, const cplx* A, in
     g.C = C; g.ldc = ldc; g.strideC = sC;
     g.rowscale = g.colscale = g.kscale = nullptr;
     g.strideRow = g.strideCol = g.strideK = 0;
-    g.alpha = alpha; g.beta = beta; g.batch = batch;
+    g.alpha = alpha; g.beta = beta; g.batch = batch; g.kvec = nullptr; g.b_kmajor = 0;
     return g;
 }
 

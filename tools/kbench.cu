@@ -162,7 +162,7 @@ int main(int argc, char** argv) {
                     ga.C = C; ga.ldc = D; ga.strideC = (long long)dd;
                     ga.rowscale = ga.colscale = ga.kscale = nullptr;
                     ga.strideRow = ga.strideCol = ga.strideK = 0;
-                    ga.alpha = 1.0; ga.beta = 0.0; ga.batch = R;
+                    ga.kvec = nullptr; ga.b_kmajor = 0; ga.alpha = 1.0; ga.beta = 0.0; ga.batch = R;
                     CHECK(gemm_launch(ga, st));
                 };
                 const double ms = time_ms(fn, reps);
@@ -179,7 +179,7 @@ int main(int argc, char** argv) {
                 ga.C = C; ga.ldc = nb; ga.strideC = (long long)dd;
                 ga.rowscale = ga.colscale = ga.kscale = nullptr;
                 ga.strideRow = ga.strideCol = ga.strideK = 0;
-                ga.alpha = 1.0; ga.beta = 0.0; ga.batch = R;
+                ga.kvec = nullptr; ga.b_kmajor = 0; ga.alpha = 1.0; ga.beta = 0.0; ga.batch = R;
                 CHECK(gemm_launch(ga, st));
             };
             auto fn2 = [&](int i) {
@@ -191,7 +191,7 @@ int main(int argc, char** argv) {
                 ga.C = A + size_t(i % ncopies) * dd * R; ga.ldc = D; ga.strideC = (long long)dd;
                 ga.rowscale = ga.colscale = ga.kscale = nullptr;
                 ga.strideRow = ga.strideCol = ga.strideK = 0;
-                ga.alpha = -1.0; ga.beta = 1.0; ga.batch = R;
+                ga.kvec = nullptr; ga.b_kmajor = 0; ga.alpha = -1.0; ga.beta = 1.0; ga.batch = R;
                 CHECK(gemm_launch(ga, st));
             };
             const double ms1 = time_ms(fn1, reps), ms2 = time_ms(fn2, reps);

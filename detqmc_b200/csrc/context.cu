@@ -485,6 +485,7 @@ int launch_update(dqmc_ctx* ctx, int k, int therm) {
     a.thermalization = therm;
     a.batch = ctx->R;
     a.site_state = ctx->siteState;
+    a.debug = std::getenv("DQMC_UPD_DEBUG") ? std::atoi(std::getenv("DQMC_UPD_DEBUG")) : 0;
     a.kvec = ctx->kvec;
     // small delay blocks (Woodbury = 1) are flushed inside the kernel; otherwise every round is
     // followed by the rank-K update G += X Y on all SMs
@@ -742,9 +743,11 @@ int dqmc_create(const dqmc_params* params, int n_replicas, int device, dqmc_ctx*
     CK(dmalloc(&ctx->consistency, nm));
     CK(dmalloc(&ctx->eyeM, dd));
     CK(dmalloc(&ctx->onesV, D));
-    ctx->kmax = ctx->msf * p.delaySteps;
+    ctx->kmax = (ctx->msf * p.delaySteps + 3) & ~3;        // padded to the 4-term chunks of the update kernel
     CK(dmalloc(&ctx->X, D * ctx->kmax * R));
     CK(dmalloc(&ctx->Y, D * ctx->kmax * R));
+    CK(cudaMemsetAsync(ctx->X, 0, sizeof(cplx) * D * ctx->kmax * R, ctx->stream));   // finite everywhere (see extend_xy)
+    CK(cudaMemsetAsync(ctx->Y, 0, sizeof(cplx) * D * ctx->kmax * R, ctx->stream));
     ctx->rngCap = size_t(ctx->m) * ctx->N * (p.opdim + 1);
     ctx->rngAlloc = ctx->rngCap;
     ctx->rngStride = ctx->rngCap;

@@ -172,6 +172,7 @@ struct UpdateArgs {
     int inline_flush;             // 1: the CTA applies G += X Y itself and finishes the slice in one launch
     int* site_state;              // [batch] next site to visit (carried from round to round)
     int* kvec;                    // [batch] K = MSF * (#accepted in this round) for the rank-K flush
+    int debug;                    // print per-phase clock counts of replica 0 (development)
 };
 // one round of the delayed local updates; with inline_flush == 0 the caller applies
 // G += X[:, :kvec] Y[:kvec, :] (rank-K update GEMM) after every round

@@ -168,15 +168,130 @@ struct UpdSmem {
     double* ck;        // [N] cosh table of this slice
     double* xk;        // [N] sinh table of this slice
     double* rng;       // [N*(OPDIM+1)] window of the replica's random numbers, starting at the cursor
-    cplx* S;           // [MSF*MSF] site block of the effective Green's function (column c, row r at c*MSF+r)
+    cplx* Gblk;        // [2][MSF*MSF] site block of G (row r, column c at r*MSF+c), this site / next site
+    cplx* Spart;       // [MSF*MSF] site block of the pending terms already in X, Y (computed by the stager)
     cplx* Delta;       // [MSF*MSF]
     cplx* Minv;        // [MSF*MSF]
     cplx* xrow;        // [2][MSF][KMAX] pending X rows `site + rN`  (double buffered: this site / next site)
     cplx* ycol;        // [2][MSF][KMAX] pending Y columns `site + cN`
 };
 
-constexpr int kDecWarps = 4;        // warp 0: exp(-dS) + decision, 1: cosh, 2: sinh, 3: stager for the next site
+constexpr int kDecWarps = 2;        // warp 0: proposal + decision, warp 1: stager for the pending rows / columns
 constexpr int kDecThreads = 32 * kDecWarps;
+
+// cosh(x) and sinh(x)/x for the small arguments of the model (x = lambda*dtau*|phi|): Horner
+// evaluation of the Taylor series in x^2 (error < 1 ulp for x <= 1); library functions otherwise.
+__device__ __forceinline__ void cosh_sinhc(double x, double& c, double& sc) {
+    if (x <= 1.0) {
+        const double z = x * x;
+        double pc = 1.0 / 2432902008176640000.0;       // 1/20!
+        double ps = 1.0 / 51090942171709440000.0;      // 1/21!
+        pc = fma(pc, z, 1.0 / 6402373705728000.0);     // 1/18!
+        ps = fma(ps, z, 1.0 / 121645100408832000.0);   // 1/19!
+        pc = fma(pc, z, 1.0 / 20922789888000.0);       // 1/16!
+        ps = fma(ps, z, 1.0 / 355687428096000.0);      // 1/17!
+        pc = fma(pc, z, 1.0 / 87178291200.0);          // 1/14!
+        ps = fma(ps, z, 1.0 / 1307674368000.0);        // 1/15!
+        pc = fma(pc, z, 1.0 / 479001600.0);            // 1/12!
+        ps = fma(ps, z, 1.0 / 6227020800.0);           // 1/13!
+        pc = fma(pc, z, 1.0 / 3628800.0);              // 1/10!
+        ps = fma(ps, z, 1.0 / 39916800.0);             // 1/11!
+        pc = fma(pc, z, 1.0 / 40320.0);                // 1/8!
+        ps = fma(ps, z, 1.0 / 362880.0);               // 1/9!
+        pc = fma(pc, z, 1.0 / 720.0);                  // 1/6!
+        ps = fma(ps, z, 1.0 / 5040.0);                 // 1/7!
+        pc = fma(pc, z, 1.0 / 24.0);
+        ps = fma(ps, z, 1.0 / 120.0);
+        pc = fma(pc, z, 0.5);
+        ps = fma(ps, z, 1.0 / 6.0);
+        c = fma(pc, z, 1.0);
+        sc = fma(ps, z, 1.0);
+    } else {
+        c = cosh(x);
+        sc = sinh(x) / x;
+    }
+}
+
+__device__ __forceinline__ cplx lds_cplx(uint32_t addr) {
+    cplx v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+
+// row / column `site` entries of G for matrix index t (row access is strided in the column-major G)
+template <int MSF>
+__device__ __forceinline__ void load_g_rowcol(const cplx* __restrict__ G, int D, int N, int site, int t, cplx* Gr, cplx* Gc) {
+#pragma unroll
+    for (int r = 0; r < MSF; ++r) {
+        Gr[r] = G[size_t(t) * D + site + r * N];
+        Gc[r] = G[size_t(site + r * N) * D + t];
+    }
+}
+
+// Gather row / column `site` of the effective Green's function G + X Y (K pending terms) for matrix
+// index t and turn them into the new column of X and row of Y:
+//   X_j = C_j Delta,  Y_j = M^-1 (R_j - 1_j)      (detsdwopdim.cpp:3123-3138)
+template <int MSF>
+__device__ __forceinline__ void extend_xy(cplx* __restrict__ X, cplx* __restrict__ Y, const cplx* __restrict__ G,
+                                          int D, int N, int KMAX, int K, int site, int t, const cplx* xrow,
+                                          const cplx* ycol, const cplx* sDelta, const cplx* sMinv, cplx* xnext,
+                                          cplx* ynext, bool have_next, const cplx* Gr, const cplx* Gc) {
+    cplx Rr[MSF], Cc[MSF];
+#pragma unroll
+    for (int r = 0; r < MSF; ++r) { Rr[r] = make_double2(0, 0); Cc[r] = make_double2(0, 0); }
+    // Pending terms in chunks of 4 without per-term predicates: the staged rows / columns are zero
+    // beyond K (kept so by the kernel) and X, Y hold finite values in all KMAX columns, so the padded
+    // terms contribute exactly zero.  Shared memory is addressed through 32-bit shared addresses.
+    constexpr int CH = 4;
+    const uint32_t xs = (uint32_t)__cvta_generic_to_shared(xrow);
+    const uint32_t ys = (uint32_t)__cvta_generic_to_shared(ycol);
+    const cplx* __restrict__ xp = X + t;
+    const cplx* __restrict__ yp = Y + t;
+    for (int l0 = 0; l0 < K; l0 += CH) {
+        cplx yv[CH], xv[CH];
+#pragma unroll
+        for (int u = 0; u < CH; ++u) {
+            yv[u] = yp[size_t(l0 + u) * D];
+            xv[u] = xp[size_t(l0 + u) * D];
+        }
+#pragma unroll
+        for (int u = 0; u < CH; ++u) {
+#pragma unroll
+            for (int r = 0; r < MSF; ++r) {
+                const cplx xr = lds_cplx(xs + uint32_t((r * KMAX + l0 + u) * sizeof(cplx)));
+                const cplx yc = lds_cplx(ys + uint32_t((r * KMAX + l0 + u) * sizeof(cplx)));
+                Rr[r] = cfma(xr, yv[u], Rr[r]);
+                Cc[r] = cfma(xv[u], yc, Cc[r]);
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < MSF; ++r) {
+        Rr[r] = cadd(Rr[r], Gr[r]);
+        Cc[r] = cadd(Cc[r], Gc[r]);
+        if (t == site + r * N) Rr[r].x -= 1.0;
+    }
+    cplx ynew[MSF], xnew[MSF];
+#pragma unroll
+    for (int r = 0; r < MSF; ++r) {
+        cplx yn = make_double2(0, 0), xn = make_double2(0, 0);
+#pragma unroll
+        for (int q = 0; q < MSF; ++q) {
+            yn = cfma(sMinv[r * MSF + q], Rr[q], yn);
+            xn = cfma(Cc[q], sDelta[q * MSF + r], xn);
+        }
+        ynew[r] = yn; xnew[r] = xn;
+        Y[size_t(K + r) * D + t] = yn;
+        X[size_t(K + r) * D + t] = xn;
+    }
+    // new entries of the staged rows / columns of the next site
+    const int rel = t - (site + 1);
+    if (have_next && rel >= 0 && rel % N == 0 && rel / N < MSF) {
+        const int rr = rel / N;
+#pragma unroll
+        for (int r = 0; r < MSF; ++r) { xnext[rr * KMAX + K + r] = xnew[r]; ynext[rr * KMAX + K + r] = ynew[r]; }
+    }
+}
 
 // One ROUND of updateInSlice_delayed for every replica: propose/decide site by site until
 // `delaySteps` proposals have been accepted (or the slice ends), appending to X, Y.  With
@@ -185,32 +300,34 @@ constexpr int kDecThreads = 32 * kDecWarps;
 // host launches the rank-K update on all SMs before the next round.
 //
 // The Metropolis chain is strictly sequential, so the kernel is organised around the latency of one
-// site.  Warps 0-2 evaluate the three transcendental functions of the proposal in parallel (bosonic
-// action difference, cosh, sinh); warp 3 stages the pending X rows / Y columns of the NEXT site into
-// shared memory; the remaining warps (thread <-> matrix index t) gather row / column `site` of the
-// effective Green's function G + X Y, with the G entries of the next site prefetched one site
-// ahead (G is constant during a round) and the pending terms read in batches so that their loads
-// overlap.  The site block S = G_eff[site rows, site cols] is a by-product of the row gather; the
-// part of the decision that needs it follows after one barrier.
+// site and software-pipelined over two barriers per site:
+//   phase 1   warp 0   proposal for `site`: new field, bosonic action difference, cosh / sinh, Delta
+//             warp 1   stages the pending X rows / Y columns of `site` in shared memory and prefetches
+//                      the G site block of the next site
+//             others   (thread <-> matrix index t) finish the PREVIOUS site if it was accepted: gather
+//                      its row / column of G + X Y and append X_j, Y_j
+//   phase 2   warp 0   site block S of the effective Green's function (lanes over the pending terms),
+//                      determinant ratio, Metropolis decision
+// so the O(K D) work of an accepted update overlaps with the proposal of the next site, and only the
+// O(K) site block sits between the two barriers.
 template <int MSF, int OPDIM, int TPT, int MAXT>
 __global__ void __launch_bounds__(MAXT) update_round_kernel(UpdateModel md, UpdateArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int D = md.D, N = md.N, L = md.L;
-    const int KMAX = MSF * md.delaySteps;
+    const int KMAX = (MSF * md.delaySteps + 3) & ~3;
     UpdSmem sm;
     sm.phik = reinterpret_cast<double*>(smem_raw);
     sm.tsum = sm.phik + OPDIM * N;
     sm.ck = sm.tsum + OPDIM * N;
     sm.xk = sm.ck + N;
     sm.rng = sm.xk + N;
-    sm.S = reinterpret_cast<cplx*>(sm.rng + ((N * (OPDIM + 1) + 1) & ~1));
-    sm.Delta = sm.S + MSF * MSF;
+    sm.Gblk = reinterpret_cast<cplx*>(sm.rng + ((N * (OPDIM + 1) + 1) & ~1));
+    sm.Spart = sm.Gblk + 2 * MSF * MSF;
+    sm.Delta = sm.Spart + MSF * MSF;
     sm.Minv = sm.Delta + MSF * MSF;
     sm.xrow = sm.Minv + MSF * MSF;
     sm.ycol = sm.xrow + 2 * MSF * KMAX;
     __shared__ int sAccept, sAbort, sNload;
-    __shared__ double sTrans[4];                           // probSPhi, cNew, xNew
-    __shared__ double sNewp[3];
 
     const int b = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -251,279 +368,265 @@ __global__ void __launch_bounds__(MAXT) update_round_kernel(UpdateModel md, Upda
         const int want = (N - site0) * (OPDIM + 1);
         const int have = max(0, min(want, a.rngWindow - cursor0));
         for (int i = tid; i < have; i += blockDim.x) sm.rng[i] = rng[cursor0 + i];
-        if (tid == 0) { sAbort = 0; sNload = have; }
+        if (tid < MSF * MSF) {
+            const int r = tid / MSF, c = tid % MSF;
+            sm.Gblk[(site0 & 1) * MSF * MSF + tid] = G[size_t(site0 + c * N) * D + site0 + r * N];
+        }
+        for (int i = tid; i < 2 * MSF * KMAX; i += blockDim.x) {
+            sm.xrow[i] = make_double2(0, 0);
+            sm.ycol[i] = make_double2(0, 0);
+        }
+        if (tid == 0) { sAbort = 0; sNload = have; sAccept = 0; }
     }
     __syncthreads();
 
-    int cur = 0;                                           // offset into sm.rng (tracked identically by warps 0-2)
-    unsigned accepted = 0;                                 // thread 0
-    int j = 0;                                             // accepted updates pending in X, Y (uniform)
+    int cur = 0;                                           // lane 0 of warp 0: offset into sm.rng
+    unsigned accepted = 0;                                 // lane 0 of warp 0
+    int j = 0;                                             // accepted updates whose X, Y columns exist or are in flight
     int delayNow = min(md.delaySteps, N - site0);
     int site = site0;
+    bool prev_acc = false;                                 // previous site accepted, its X_j / Y_j still to be appended
+    cplx Gr[TPT][MSF], Gc[TPT][MSF];                       // gather threads: row / column entries of G for the last decided site
 
-    // G entries of the first site (later sites are prefetched one iteration ahead)
-    cplx Gr[TPT][MSF], Gc[TPT][MSF];
-    if (warp >= kDecWarps) {
-#pragma unroll
-        for (int q = 0; q < TPT; ++q) {
-            const int t = gt + q * gthreads;
-            if (t < D) {
-#pragma unroll
-                for (int r = 0; r < MSF; ++r) {
-                    Gr[q][r] = G[size_t(t) * D + site + r * N];
-                    Gc[q][r] = G[size_t(site + r * N) * D + t];
-                }
-            }
-        }
-    }
-    // proposal state carried by thread 0 across the barrier
-    double oldp[3] = {0, 0, 0}, newp[3] = {0, 0, 0};
+    // proposal state carried by lane 0 of warp 0 across the barrier
+    double newp[3] = {0, 0, 0}, cNew = 0, xNew = 0, probSPhi = 0;
+    cplx Dl[MSF * MSF];
     bool have_rng = true;
+    long long tq[6] = {0, 0, 0, 0, 0, 0};
+    long long tmark = clock64();
+#define TICK(i) if (a.debug) { long long now__; asm volatile("mov.u64 %0, %%clock64;" : "=l"(now__) :: "memory"); tq[i] += now__ - tmark; tmark = now__; }
 
     for (; site < N; ++site) {
-        const int K = MSF * j;
+        // K_done: pending terms already in X, Y;  the update of site-1 (if accepted) adds MSF more in phase 1
+        const int K_done = MSF * (j - (prev_acc ? 1 : 0));
         const int buf = site & 1;
-        const cplx* xrow = sm.xrow + buf * MSF * KMAX;
-        const cplx* ycol = sm.ycol + buf * MSF * KMAX;
-        cplx Rr[TPT][MSF], Cc[TPT][MSF];
-        if (warp < 3) {
-            // ---------------------------------------------- proposal (independent of G), lane 0 of warps 0-2
+        cplx* xrow = sm.xrow + buf * MSF * KMAX;
+        cplx* ycol = sm.ycol + buf * MSF * KMAX;
+        TICK(5)
+        // ================================================================== phase 1
+        if (warp == 0) {
             if (lane == 0) {
+                // ---------------------------------------------- proposal (independent of G)
                 have_rng = cur + OPDIM + 1 <= sNload;
                 if (have_rng) {
-                    double newSq = 0;
+                    double oldp[3] = {0, 0, 0};
+                    double oldSq = 0, newSq = 0, tdot = 0, sdot = 0;
+                    const int x = site % L, y = site / L;
+                    const int nb0 = y * L + (x + 1 == L ? 0 : x + 1);
+                    const int nb1 = y * L + (x == 0 ? L - 1 : x - 1);
+                    const int nb2 = (y + 1 == L ? 0 : y + 1) * L + x;
+                    const int nb3 = (y == 0 ? L - 1 : y - 1) * L + x;
 #pragma unroll
                     for (int d = 0; d < OPDIM; ++d) {
                         oldp[d] = sm.phik[d * N + site];
                         const double u = sm.rng[cur + d];
                         newp[d] = oldp[d] + (-phiDelta + (phiDelta - (-phiDelta)) * u);   // randRange(-delta, +delta)
-                        newSq += newp[d] * newp[d];
-                    }
-                    if (warp == 0) {
                         // deltaSPhi (detsdwopdim.cpp:4185-4239)
-                        double oldSq = 0, tdot = 0, sdot = 0;
-                        const int x = site % L, y = site / L;
-                        const int nb0 = y * L + (x + 1 == L ? 0 : x + 1);
-                        const int nb1 = y * L + (x == 0 ? L - 1 : x - 1);
-                        const int nb2 = (y + 1 == L ? 0 : y + 1) * L + x;
-                        const int nb3 = (y == 0 ? L - 1 : y - 1) * L + x;
-#pragma unroll
-                        for (int d = 0; d < OPDIM; ++d) {
-                            const double diff = newp[d] - oldp[d];
-                            oldSq += oldp[d] * oldp[d];
-                            const double* pk = sm.phik + d * N;
-                            const double sn = ((pk[nb0] + pk[nb1]) + pk[nb2]) + pk[nb3];
-                            tdot += sm.tsum[d * N + site] * diff;
-                            sdot += sn * diff;
-                        }
-                        const double sqDiff = newSq - oldSq;
-                        const double pow4Diff = newSq * newSq - oldSq * oldSq;
-                        const double d1 = (1.0 / (md.c * md.c * dtau)) * (sqDiff - tdot);
-                        const double d2 = 0.5 * dtau * (4.0 * sqDiff - 2.0 * sdot);
-                        const double d3 = dtau * (0.5 * rpar * sqDiff + 0.25 * md.u * pow4Diff);
-                        sTrans[0] = exp(-(d1 + d2 + d3));
-                    } else if (warp == 1) {
-                        sTrans[1] = cosh(md.lambda * dtau * sqrt(newSq));
-                    } else {
-                        const double nrm = sqrt(newSq);
-                        sTrans[2] = sinh(md.lambda * dtau * nrm) / nrm;
+                        const double diff = newp[d] - oldp[d];
+                        oldSq += oldp[d] * oldp[d];
+                        newSq += newp[d] * newp[d];
+                        const double* pk = sm.phik + d * N;
+                        const double sn = ((pk[nb0] + pk[nb1]) + pk[nb2]) + pk[nb3];
+                        tdot += sm.tsum[d * N + site] * diff;
+                        sdot += sn * diff;
                     }
+                    const double sqDiff = newSq - oldSq;
+                    const double pow4Diff = newSq * newSq - oldSq * oldSq;
+                    const double d1 = (1.0 / (md.c * md.c * dtau)) * (sqDiff - tdot);
+                    const double d2 = 0.5 * dtau * (4.0 * sqDiff - 2.0 * sdot);
+                    const double d3 = dtau * (0.5 * rpar * sqDiff + 0.25 * md.u * pow4Diff);
+                    probSPhi = exp(-(d1 + d2 + d3));
+                    // get_delta_forsite: Delta = e^{-dtau V(new)} e^{+dtau V(old)} - 1
+                    const double nrm = sqrt(newSq);
+                    double sc;
+                    cosh_sinhc(md.lambda * dtau * nrm, cNew, sc);
+                    xNew = md.lambda * dtau * sc;                   // sinh(lambda dtau |phi|) / |phi|
+                    cplx evOld[MSF * MSF], emvNew[MSF * MSF];
+                    ev_block<MSF, OPDIM>(evOld, +1.0, oldp, sm.ck[site], sm.xk[site]);
+                    ev_block<MSF, OPDIM>(emvNew, -1.0, newp, cNew, xNew);
+#pragma unroll
+                    for (int r = 0; r < MSF; ++r)
+#pragma unroll
+                        for (int c = 0; c < MSF; ++c) {
+                            cplx sacc = make_double2(r == c ? -1.0 : 0.0, 0.0);
+#pragma unroll
+                            for (int t = 0; t < MSF; ++t) sacc = cfma(emvNew[r * MSF + t], evOld[t * MSF + c], sacc);
+                            Dl[r * MSF + c] = sacc;
+                        }
                 }
             }
-        } else if (warp == 3) {
-            // ---------------------------------------------- stage the pending X rows / Y columns of the NEXT site
-            if (site + 1 < N) {
-                cplx* xn = sm.xrow + (buf ^ 1) * MSF * KMAX;
-                cplx* yn = sm.ycol + (buf ^ 1) * MSF * KMAX;
-                for (int i = lane; i < MSF * K; i += 32) {
-                    const int r = i / K, l = i - r * K;
-                    xn[r * KMAX + l] = X[size_t(l) * D + site + 1 + r * N];
-                    yn[r * KMAX + l] = Y[size_t(l) * D + site + 1 + r * N];
+        } else if (warp == 1) {
+            // ---------------------------------------------- stage the pending rows / columns of `site`
+            cplx xs[MSF], ys[MSF];
+            cplx part[MSF * MSF];
+#pragma unroll
+            for (int i = 0; i < MSF * MSF; ++i) part[i] = make_double2(0, 0);
+            for (int l = lane; l < K_done; l += 32) {
+#pragma unroll
+                for (int r = 0; r < MSF; ++r) {
+                    xs[r] = X[size_t(l) * D + site + r * N];
+                    ys[r] = Y[size_t(l) * D + site + r * N];
+                    xrow[r * KMAX + l] = xs[r];
+                    ycol[r * KMAX + l] = ys[r];
                 }
+#pragma unroll
+                for (int r = 0; r < MSF; ++r)
+#pragma unroll
+                    for (int c = 0; c < MSF; ++c) part[r * MSF + c] = cfma(xs[r], ys[c], part[r * MSF + c]);
             }
-        } else {
-            // ---------------------------------------------- gather rows / columns `site` of G + X Y
+            // site block of the terms already in X, Y (fixed-order butterfly: deterministic)
+#pragma unroll
+            for (int i = 0; i < MSF * MSF; ++i) {
+                part[i].x = warp_sum(part[i].x);
+                part[i].y = warp_sum(part[i].y);
+            }
+            if (lane == 0) {
+#pragma unroll
+                for (int i = 0; i < MSF * MSF; ++i) sm.Spart[i] = part[i];
+            }
+            if (lane < MSF * MSF && site + 1 < N) {
+                const int r = lane / MSF, c = lane % MSF;
+                sm.Gblk[(buf ^ 1) * MSF * MSF + lane] = G[size_t(site + 1 + c * N) * D + site + 1 + r * N];
+            }
+        } else if (prev_acc) {
+            // ---------------------------------------------- finish the previous (accepted) site
+            const int pb = buf ^ 1;
 #pragma unroll
             for (int q = 0; q < TPT; ++q) {
                 const int t = gt + q * gthreads;
-                if (t < D) {
-#pragma unroll
-                    for (int r = 0; r < MSF; ++r) { Rr[q][r] = Gr[q][r]; Cc[q][r] = Gc[q][r]; }
-                    if (site + 1 < N) {
-                        // prefetch for the next site; consumed one iteration later
-#pragma unroll
-                        for (int r = 0; r < MSF; ++r) {
-                            Gr[q][r] = G[size_t(t) * D + site + 1 + r * N];
-                            Gc[q][r] = G[size_t(site + 1 + r * N) * D + t];
-                        }
-                    }
-                    constexpr int CH = 4;
-                    for (int l0 = 0; l0 < K; l0 += CH) {
-                        cplx yv[CH], xv[CH];
-#pragma unroll
-                        for (int u = 0; u < CH; ++u) {
-                            const int l = l0 + u;
-                            if (l < K) {
-                                yv[u] = Y[size_t(l) * D + t];
-                                xv[u] = X[size_t(l) * D + t];
-                            }
-                        }
-#pragma unroll
-                        for (int u = 0; u < CH; ++u) {
-                            const int l = l0 + u;
-                            if (l < K) {
-#pragma unroll
-                                for (int r = 0; r < MSF; ++r) {
-                                    Rr[q][r] = cfma(xrow[r * KMAX + l], yv[u], Rr[q][r]);
-                                    Cc[q][r] = cfma(xv[u], ycol[r * KMAX + l], Cc[q][r]);
-                                }
-                            }
-                        }
-                    }
-                    // the site block is rows `site + rN` of the columns `site + cN`
-                    const int rel = t - site;
-                    if (rel >= 0 && rel % N == 0) {
-                        const int c = rel / N;
-                        if (c < MSF) {
-#pragma unroll
-                            for (int r = 0; r < MSF; ++r) sm.S[c * MSF + r] = Rr[q][r];
-                        }
-                    }
-                }
+                if (t < D)
+                    extend_xy<MSF>(X, Y, G, D, N, KMAX, (a.debug >= 6 ? 0 : K_done), site - 1, t, sm.xrow + pb * MSF * KMAX,
+                                   sm.ycol + pb * MSF * KMAX, sm.Delta, sm.Minv, xrow, ycol, true, Gr[q], Gc[q]);
             }
         }
+        TICK(0)
         __syncthreads();
-        // -------------------------------------------------- decision, thread 0
-        bool consumed_extra = false;                       // set identically in lane 0 of warps 0-2 below
-        if (tid == 0) {
-            if (!have_rng) {
-                sAbort = 1;
-                sAccept = 0;
-            } else {
-                const double probSPhi = sTrans[0], cNew = sTrans[1], xNew = sTrans[2];
-                // get_delta_forsite: Delta = e^{-dtau V(new)} e^{+dtau V(old)} - 1
-                cplx evOld[MSF * MSF], emvNew[MSF * MSF], Dl[MSF * MSF];
-                ev_block<MSF, OPDIM>(evOld, +1.0, oldp, sm.ck[site], sm.xk[site]);
-                ev_block<MSF, OPDIM>(emvNew, -1.0, newp, cNew, xNew);
-#pragma unroll
-                for (int r = 0; r < MSF; ++r)
-#pragma unroll
-                    for (int c = 0; c < MSF; ++c) {
-                        cplx sacc = make_double2(r == c ? -1.0 : 0.0, 0.0);
-#pragma unroll
-                        for (int t = 0; t < MSF; ++t) sacc = cfma(emvNew[r * MSF + t], evOld[t * MSF + c], sacc);
-                        Dl[r * MSF + c] = sacc;
-                    }
-                cplx S[MSF * MSF], M[MSF * MSF], Minv[MSF * MSF];
-#pragma unroll
-                for (int r = 0; r < MSF; ++r)
-#pragma unroll
-                    for (int c = 0; c < MSF; ++c) S[r * MSF + c] = sm.S[c * MSF + r];
-                // M = 1 - S Delta + Delta
-#pragma unroll
-                for (int r = 0; r < MSF; ++r)
-#pragma unroll
-                    for (int c = 0; c < MSF; ++c) {
-                        cplx sacc = make_double2(r == c ? 1.0 : 0.0, 0.0);
-#pragma unroll
-                        for (int t = 0; t < MSF; ++t) sacc = csub(sacc, cmul(S[r * MSF + t], Dl[t * MSF + c]));
-                        M[r * MSF + c] = cadd(sacc, Dl[r * MSF + c]);
-                    }
-                const cplx det = small_det_inv<MSF>(M, Minv);
-                const double probFermion = (OPDIM == 3) ? det.x : (det.x * det.x + det.y * det.y);
-                const double prob = probSPhi * probFermion;
-                bool acc;
-                int used = OPDIM;
-                if (prob > 1.0) {
-                    acc = true;
+        TICK(1)
+        // ================================================================== phase 2: decision (warp 0)
+        const int K = MSF * j;
+        if (warp == 0) {
+            // site block of the effective Green's function: S = G[blk] + (terms staged in phase 1) + (the
+            // terms of the update appended in phase 1, if any)
+            TICK(4)
+            if (lane == 0) {
+                if (!have_rng) {
+                    sAbort = 1;
+                    sAccept = 0;
                 } else {
-                    acc = sm.rng[cur + OPDIM] < prob;
-                    used += 1;
-                }
-                if (acc) {
-                    accepted += 1;
+                    cplx S[MSF * MSF], M[MSF * MSF];
 #pragma unroll
-                    for (int d = 0; d < OPDIM; ++d) {
-                        sm.phik[d * N + site] = newp[d];
-                        phik_g[d * N + site] = newp[d];
+                    for (int r = 0; r < MSF; ++r)
+#pragma unroll
+                        for (int c = 0; c < MSF; ++c) {
+                            cplx sacc = cadd(sm.Gblk[buf * MSF * MSF + r * MSF + c], sm.Spart[r * MSF + c]);
+                            for (int l = K_done; l < K; ++l) sacc = cfma(xrow[r * KMAX + l], ycol[c * KMAX + l], sacc);
+                            S[r * MSF + c] = sacc;
+                        }
+                    // M = 1 - S Delta + Delta
+#pragma unroll
+                    for (int r = 0; r < MSF; ++r)
+#pragma unroll
+                        for (int c = 0; c < MSF; ++c) {
+                            cplx sacc = make_double2(r == c ? 1.0 : 0.0, 0.0);
+#pragma unroll
+                            for (int t = 0; t < MSF; ++t) sacc = csub(sacc, cmul(S[r * MSF + t], Dl[t * MSF + c]));
+                            M[r * MSF + c] = cadd(sacc, Dl[r * MSF + c]);
+                        }
+                    cplx Minv[MSF * MSF];
+                    const cplx det = small_det_inv<MSF>(M, Minv);
+                    const double probFermion = (OPDIM == 3) ? det.x : (det.x * det.x + det.y * det.y);
+                    const double prob = probSPhi * probFermion;
+                    cur += OPDIM;
+                    bool acc;
+                    if (prob > 1.0) {
+                        acc = true;
+                    } else {
+                        acc = sm.rng[cur] < prob;
+                        cur += 1;
                     }
-                    sm.ck[site] = cNew;
-                    sm.xk[site] = xNew;
-                    coshT[size_t(k) * N + site] = cNew;
-                    sinhT[size_t(k) * N + site] = xNew;
+                    if (acc) {
+                        accepted += 1;
 #pragma unroll
-                    for (int i = 0; i < MSF * MSF; ++i) { sm.Delta[i] = Dl[i]; sm.Minv[i] = Minv[i]; }
+                        for (int d = 0; d < OPDIM; ++d) {
+                            sm.phik[d * N + site] = newp[d];
+                            phik_g[d * N + site] = newp[d];
+                        }
+                        sm.ck[site] = cNew;
+                        sm.xk[site] = xNew;
+                        coshT[size_t(k) * N + site] = cNew;
+                        sinhT[size_t(k) * N + site] = xNew;
+#pragma unroll
+                        for (int i = 0; i < MSF * MSF; ++i) { sm.Delta[i] = Dl[i]; sm.Minv[i] = Minv[i]; }
+                    }
+                    sAccept = acc ? 1 : 0;
                 }
-                sAccept = acc ? (used > OPDIM ? 3 : 1) : (used > OPDIM ? 2 : 0);    // bit 0: accepted, bit 1: extra draw
             }
         }
-        __syncthreads();
-        if (sAbort) break;
-        const int decision = sAccept;
-        consumed_extra = (decision & 2) != 0;
-        cur += OPDIM + (consumed_extra ? 1 : 0);           // every thread tracks the cursor (warps 0-2 use it)
-        if (decision & 1) {
-            // ---------------------------------------------- extend X, Y:  X_j = C_j Delta,  Y_j = M^-1 (R_j - 1_j)
-            if (warp >= kDecWarps) {
+        else if (warp >= kDecWarps) {
+            // idle otherwise: request row / column `site` of G now, so that the update of an accepted site
+            // does not wait for them in the next phase 1
 #pragma unroll
-                for (int q = 0; q < TPT; ++q) {
-                    const int t = gt + q * gthreads;
-                    if (t < D) {
-#pragma unroll
-                        for (int r = 0; r < MSF; ++r)
-                            if (t == site + r * N) Rr[q][r].x -= 1.0;
-                        cplx ynew[MSF], xnew[MSF];
-#pragma unroll
-                        for (int r = 0; r < MSF; ++r) {
-                            cplx yn = make_double2(0, 0), xn = make_double2(0, 0);
-#pragma unroll
-                            for (int qq = 0; qq < MSF; ++qq) {
-                                yn = cfma(sm.Minv[r * MSF + qq], Rr[q][qq], yn);
-                                xn = cfma(Cc[q][qq], sm.Delta[qq * MSF + r], xn);
-                            }
-                            ynew[r] = yn; xnew[r] = xn;
-                            Y[size_t(K + r) * D + t] = yn;
-                            X[size_t(K + r) * D + t] = xn;
-                        }
-                        // the new entries of the next site's staged rows / columns
-                        const int rel = t - (site + 1);
-                        if (site + 1 < N && rel >= 0 && rel % N == 0 && rel / N < MSF) {
-                            const int rr = rel / N;
-                            cplx* xn2 = sm.xrow + (buf ^ 1) * MSF * KMAX + rr * KMAX;
-                            cplx* yn2 = sm.ycol + (buf ^ 1) * MSF * KMAX + rr * KMAX;
-#pragma unroll
-                            for (int r = 0; r < MSF; ++r) { xn2[K + r] = xnew[r]; yn2[K + r] = ynew[r]; }
-                        }
-                    }
-                }
+            for (int q = 0; q < TPT; ++q) {
+                const int t = gt + q * gthreads;
+                if (t < D) load_g_rowcol<MSF>(G, D, N, site, t, Gr[q], Gc[q]);
             }
+        }
+        TICK(2)
+        __syncthreads();
+        TICK(3)
+        if (sAbort) break;
+        prev_acc = sAccept != 0;
+        if (prev_acc) {
             j += 1;
             if (j == delayNow) {
+                // the delay block is full: append the last update now, then flush (in the kernel or on the host)
+                if (warp >= kDecWarps) {
+#pragma unroll
+                    for (int q = 0; q < TPT; ++q) {
+                        const int t = gt + q * gthreads;
+                        if (t < D)
+                            extend_xy<MSF>(X, Y, G, D, N, KMAX, MSF * (j - 1), site, t, xrow, ycol, sm.Delta, sm.Minv,
+                                           nullptr, nullptr, false, Gr[q], Gc[q]);
+                    }
+                }
+                prev_acc = false;
                 if (!a.inline_flush) { ++site; break; }
                 __syncthreads();
                 flush_delayed(G, X, Y, D, MSF * j, KMAX);
                 j = 0;
                 delayNow = min(md.delaySteps, N - (site + 1));
                 __syncthreads();
-                // G changed: refresh the prefetched entries of the next site
-                if (warp >= kDecWarps && site + 1 < N) {
-#pragma unroll
-                    for (int q = 0; q < TPT; ++q) {
-                        const int t = gt + q * gthreads;
-                        if (t < D) {
-#pragma unroll
-                            for (int r = 0; r < MSF; ++r) {
-                                Gr[q][r] = G[size_t(t) * D + site + 1 + r * N];
-                                Gc[q][r] = G[size_t(site + 1 + r * N) * D + t];
-                            }
-                        }
-                    }
+                // pending terms are gone: clear the staged rows / columns; G changed: refresh the prefetched
+                // site block of the next site
+                for (int i = tid; i < 2 * MSF * KMAX; i += blockDim.x) {
+                    sm.xrow[i] = make_double2(0, 0);
+                    sm.ycol[i] = make_double2(0, 0);
                 }
+                if (tid < MSF * MSF && site + 1 < N) {
+                    const int r = tid / MSF, c = tid % MSF;
+                    sm.Gblk[(buf ^ 1) * MSF * MSF + tid] = G[size_t(site + 1 + c * N) * D + site + 1 + r * N];
+                }
+                __syncthreads();
             }
-            __syncthreads();
+        }
+    }
+    if (prev_acc && !sAbort) {
+        // the slice ended right after an accepted site: append its update
+        if (warp >= kDecWarps) {
+            const int pb = (site - 1) & 1;
+#pragma unroll
+            for (int q = 0; q < TPT; ++q) {
+                const int t = gt + q * gthreads;
+                if (t < D)
+                    extend_xy<MSF>(X, Y, G, D, N, KMAX, MSF * (j - 1), site - 1, t, sm.xrow + pb * MSF * KMAX,
+                                   sm.ycol + pb * MSF * KMAX, sm.Delta, sm.Minv, nullptr, nullptr, false, Gr[q], Gc[q]);
+            }
         }
     }
     __syncthreads();
+    if (a.debug && b == 0 && (tid == 0 || tid == 32 || tid == kDecThreads))
+        printf("upd dbg round %d tid %3d sites %d: ph1 %lld waitA %lld ph2(dec) %lld waitB %lld Sred %lld top %lld\n", a.round, tid,
+               site - site0, tq[0], tq[1], tq[2], tq[3], tq[4], tq[5]);
     if (a.inline_flush && j > 0 && !sAbort) {
         flush_delayed(G, X, Y, D, MSF * j, KMAX);
         j = 0;
@@ -571,7 +674,7 @@ cudaError_t update_round_launch(const UpdateModel& m, const UpdateArgs& a, cudaS
     const int gth = ((((m.D + tpt - 1) / tpt) + 31) / 32) * 32;
     const int threads = kDecThreads + gth;
     const size_t smem = size_t((2 * m.opdim + 2) * m.N + ((m.N * (m.opdim + 1) + 1) & ~1)) * sizeof(double) +
-                        size_t(3) * m.msf * m.msf * sizeof(cplx) + size_t(4) * m.msf * m.msf * m.delaySteps * sizeof(cplx);
+                        size_t(5) * m.msf * m.msf * sizeof(cplx) + size_t(4) * m.msf * ((m.msf * m.delaySteps + 3) & ~3) * sizeof(cplx);
 #define LAUNCH(MSF, OPD, TPT, MAXT)                                                                         \
     {                                                                                                       \
         cudaError_t e = cudaFuncSetAttribute(update_round_kernel<MSF, OPD, TPT, MAXT>,                      \
@@ -581,7 +684,7 @@ cudaError_t update_round_launch(const UpdateModel& m, const UpdateArgs& a, cudaS
     }
 #define LAUNCH3(MSF, OPD)                                                                                   \
     {                                                                                                       \
-        if (threads <= 416) LAUNCH(MSF, OPD, 1, 416)                                                        \
+        if (threads <= 352) LAUNCH(MSF, OPD, 1, 352)                                                        \
         else if (tpt == 1) LAUNCH(MSF, OPD, 1, 1024)                                                        \
         else LAUNCH(MSF, OPD, 2, 1024)                                                                      \
     }

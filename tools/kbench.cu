@@ -54,15 +54,65 @@ static void fill_random(std::vector<double>& v, unsigned seed, double scale = 1.
     for (auto& x : v) x = scale * u(g);
 }
 
+__global__ void dfma_peak_kernel(double* out, int iters, double a, double b) {
+    double c[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) c[i] = threadIdx.x * 1e-3 + i;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) c[i] = fma(c[i], a, b);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += c[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+template <int NCH>
+__global__ void dfma_latency_kernel(double* out, long long* cyc, int iters, double a, double b) {
+    double c[NCH];
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) c[i] = threadIdx.x * 1e-3 + i;
+    long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < NCH; ++i) c[i] = fma(c[i], a, b);
+    }
+    long long t1 = clock64();
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) s += c[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    if (threadIdx.x == 0 && blockIdx.x == 0) *cyc = t1 - t0;
+}
+
+__global__ void dmma_peak_kernel(double* out, int iters, double a, double b) {
+    double c[8][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { c[i][0] = threadIdx.x * 1e-3 + i; c[i][1] = i; }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                         : "+d"(c[i][0]), "+d"(c[i][1])
+                         : "d"(a), "d"(b));
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 int main(int argc, char** argv) {
     int R = 64, L = 12, reps = 20, opdim = 2, m = 100;
-    bool do_cb = false, do_gemm = false, do_qr = false;
+    bool do_cb = false, do_gemm = false, do_qr = false, do_peak = false;
     int flux = 1;
     for (int i = 1; i < argc; ++i) {
         std::string s = argv[i];
         if (s == "cb") do_cb = true;
         else if (s == "gemm") do_gemm = true;
         else if (s == "qr") do_qr = true;
+        else if (s == "peak") do_peak = true;
         else if (s == "all") do_cb = do_gemm = do_qr = true;
         else if (s == "--R") R = std::atoi(argv[++i]);
         else if (s == "--L") L = std::atoi(argv[++i]);
@@ -85,6 +135,41 @@ int main(int argc, char** argv) {
         fill_random(h, 1);
         for (int c = 0; c < ncopies; ++c)
             CHECK(cudaMemcpy(A + size_t(c) * dd * R, h.data(), sizeof(cplx) * dd * R, cudaMemcpyHostToDevice));
+    }
+
+    if (do_peak) {
+        double* out;
+        CHECK(cudaMalloc(&out, sizeof(double) * 148 * 8 * 1024));
+        {
+            long long* dcyc;
+            CHECK(cudaMalloc(&dcyc, 8));
+            long long h = 0;
+            const int iters = 4096;
+            for (int warps : {1, 2, 4, 8, 16}) {
+                dfma_latency_kernel<1><<<1, 32 * warps, 0, st>>>(out, dcyc, iters, 0.999, 1e-3);
+                CHECK(cudaMemcpyAsync(&h, dcyc, 8, cudaMemcpyDeviceToHost, st)); CHECK(cudaStreamSynchronize(st));
+                const double c1 = double(h) / iters;
+                dfma_latency_kernel<2><<<1, 32 * warps, 0, st>>>(out, dcyc, iters, 0.999, 1e-3);
+                CHECK(cudaMemcpyAsync(&h, dcyc, 8, cudaMemcpyDeviceToHost, st)); CHECK(cudaStreamSynchronize(st));
+                const double c2 = double(h) / iters;
+                dfma_latency_kernel<8><<<1, 32 * warps, 0, st>>>(out, dcyc, iters, 0.999, 1e-3);
+                CHECK(cudaMemcpyAsync(&h, dcyc, 8, cudaMemcpyDeviceToHost, st)); CHECK(cudaStreamSynchronize(st));
+                const double c8 = double(h) / iters;
+                std::printf("dfma on ONE SM, %2d warps: cycles per loop iteration with 1 / 2 / 8 independent chains per thread: %6.1f %6.1f %6.1f\n",
+                            warps, c1, c2, c8);
+            }
+        }
+        for (int threads : {128, 256, 512, 1024}) {
+            const int blocks = 148 * (2048 / threads);
+            const int iters = 4096;
+            auto f1 = [&](int) { dfma_peak_kernel<<<blocks, threads, 0, st>>>(out, iters, 0.999, 1e-3); };
+            auto f2 = [&](int) { dmma_peak_kernel<<<blocks, threads, 0, st>>>(out, iters, 0.999, 1e-3); };
+            const double ms1 = time_ms(f1, 5), ms2 = time_ms(f2, 5);
+            const double fl1 = 2.0 * 8 * iters * double(blocks) * threads;
+            const double fl2 = 2.0 * 8 * iters * double(blocks) * (threads / 32) * 256;
+            std::printf("fp64 peak threads/CTA=%4d  DFMA %6.2f TFLOP/s   DMMA m8n8k4 %6.2f TFLOP/s\n", threads,
+                        fl1 / (ms1 * 1e-3) / 1e12, fl2 / (ms2 * 1e-3) / 1e12);
+        }
     }
 
     if (do_cb) {

@@ -1,0 +1,253 @@
+// detsdw_gpu.h -- C++ host shim: the reference's Model duck-type for DetSDW, served by libdqmc_b200.so.
+//
+// This is the upper seam of SURVEY.md section 8(b).  `DetSDWGpu<OPDIM>` is a drop-in for
+// `DetSDW<CB_ASSAAD_BERG, OPDIM>` (detsdwopdim.h:62-153) as a template argument of the reference's
+// drivers `DetQMC<Model, ModelParams>` (detqmc.h:56-159) and `DetQMCPT<Model, ModelParams>`
+// (detqmcpt.h): same member names, same argument meaning, errors surface as the reference's
+// GeneralError (exceptions.h).  It compiles against the reference's own headers (add the reference's
+// src/ and this directory to the include path, link libdqmc_b200.so); nothing of the reference is
+// copied here.  The sweep itself -- checkerboard multiplies, wraps, UDT chains, Green's functions,
+// delayed updates, global shift moves -- runs on the GPU through include/dqmc_gpu.h.
+//
+// Differences a maintainer has to know:
+//   * fermionic measurements (measure(k)) are not part of the accelerated path: run with
+//     turnoffFermionMeasurements = true; the bosonic observables below are evaluated on the host from
+//     the downloaded field after every measurement sweep.
+//   * random numbers: the replica consumes the driver's RngWrapper through a pre-drawn FIFO
+//     (dqmc_rng_set_source).  Values drawn ahead but not yet consumed are part of the model's state
+//     and are saved / restored by saveContents / loadContents.
+#ifndef DETSDW_GPU_H_
+#define DETSDW_GPU_H_
+
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "dqmc_gpu.h"
+
+// reference headers (crstnbr/detqmc, src/)
+#include "detmodel.h"
+#include "detmodelloggingparams.h"
+#include "detsdwparams.h"
+#include "detsdwsystemconfig.h"
+#include "detsdwsystemconfigfilehandle.h"
+#include "exceptions.h"
+#include "metadata.h"
+#include "observable.h"
+#include "rngwrapper.h"
+
+template <int OPDIM>
+class DetSDWGpu : public DetModel {
+public:
+    typedef ModelParamsDetSDW ModelParams;
+    typedef DetSDW_SystemConfig SystemConfig;
+    typedef DetSDW_SystemConfig_FileHandle SystemConfig_FileHandle;
+
+    DetSDWGpu(RngWrapper& rng_, const ModelParams& pars_, int device = 0)
+        : rng(rng_), pars(pars_), ctx(nullptr), normMeanPhi(0), meanPhiSquared(0), phiActionValue(0),
+          performedSweeps(0) {
+        if (pars.opdim != (uint32_t)OPDIM) throw_GeneralError("DetSDWGpu: opdim mismatch");
+        if (!pars.checkerboard) throw_GeneralError("DetSDWGpu: the GPU path implements the checkerboard break-up only");
+        if (pars.turnoffFermions) throw_GeneralError("DetSDWGpu: turnoffFermions is a pure-boson run, use the reference");
+        if (!pars.turnoffFermionMeasurements)
+            throw_GeneralError("DetSDWGpu: fermionic measurements are outside the accelerated path; set "
+                               "turnoffFermionMeasurements");
+        if (pars.cdwU != 0.0) throw_GeneralError("DetSDWGpu: cdwU != 0 is outside the accelerated path");
+        if (pars.wolffClusterUpdate || pars.wolffClusterShiftUpdate)
+            throw_GeneralError("DetSDWGpu: Wolff cluster moves are outside the accelerated path");
+        if (pars.repeatUpdateInSlice != 1) throw_GeneralError("DetSDWGpu: repeatUpdateInSlice != 1 is not implemented");
+        if (pars.updateMethod_string != "delayed" && pars.updateMethod_string != "woodbury")
+            throw_GeneralError("DetSDWGpu: updateMethod must be delayed or woodbury");
+        if (pars.spinProposalMethod_string != "box")
+            throw_GeneralError("DetSDWGpu: only box proposals are implemented");
+        dqmc_params p;
+        std::memset(&p, 0, sizeof p);
+        p.model = DQMC_MODEL_SDW;
+        p.opdim = OPDIM;
+        p.L = (int32_t)pars.L;
+        p.m = (int32_t)pars.m;
+        p.s = (int32_t)pars.s;
+        p.bc = pars.bc_string == "pbc" ? 0 : pars.bc_string == "apbc-x" ? 1 : pars.bc_string == "apbc-y" ? 2 : 3;
+        p.weakZflux = pars.weakZflux ? 1 : 0;
+        p.delaySteps = pars.updateMethod_string == "delayed" ? (int32_t)pars.delaySteps : 1;
+        p.globalShift = pars.globalShift ? 1 : 0;
+        p.globalUpdateInterval = (int32_t)pars.globalUpdateInterval;
+        p.dtau = pars.dtau;
+        p.r = pars.r; p.c = pars.c; p.u = pars.u; p.lambda = pars.lambda;
+        p.txhor = pars.txhor; p.txver = pars.txver; p.tyhor = pars.tyhor; p.tyver = pars.tyver;
+        // mux and muy supersede mu only when both are given (createReplica, detsdwopdim.cpp:76-80)
+        const bool sep = pars.specified.count("mux") && pars.specified.count("muy");
+        p.mux = sep ? pars.mux : pars.mu;
+        p.muy = sep ? pars.muy : pars.mu;
+        p.accRatio = pars.accRatio;
+        check(dqmc_create(&p, 1, device, &ctx), "dqmc_create");
+        // the driver's generator is THE stream of this replica
+        check(dqmc_rng_set_source(ctx, 0, &DetSDWGpu::fillFromRng, this), "dqmc_rng_set_source");
+        check(dqmc_init_random_fields(ctx, 0), "dqmc_init_random_fields");   // setupRandomField
+        check(dqmc_setup_storage(ctx), "dqmc_setup_storage");                // setupUdVStorage_and_calculateGreen
+    }
+    virtual ~DetSDWGpu() { dqmc_destroy(ctx); }
+
+    virtual uint32_t getSystemN() const { return pars.L * pars.L; }
+    virtual MetadataMap prepareModelMetadataMap() const {
+        MetadataMap meta = pars.prepareMetadataMap();
+        dqmc_control_data cd;
+        dqmc_get_control_data(ctx, 0, &cd);
+        meta["phiDelta"] = numToString(cd.phiDelta);
+        meta["globalShiftAccRatio"] =
+            numToString(cd.attemptedGlobalShifts ? double(cd.acceptedGlobalShifts) / cd.attemptedGlobalShifts : 0.0);
+        meta["backend"] = "libdqmc_b200 (sm_100a)";
+        return meta;
+    }
+
+    virtual void thermalizationOver() {
+        dqmc_control_data cd;
+        dqmc_get_control_data(ctx, 0, &cd);
+        std::cout << "After thermalization: phiDelta = " << cd.phiDelta << '\n'
+                  << "recent local accRatio = " << cd.lastAccRatioLocal_phi << std::endl;
+    }
+    virtual void thermalizationOver(int processIndex) {
+        std::cout << "[" << processIndex << "] ";
+        thermalizationOver();
+    }
+
+    virtual void sweep(bool takeMeasurements) {
+        check(dqmc_sweep(ctx, 0), "dqmc_sweep");
+        ++performedSweeps;
+        if (takeMeasurements) measureBosonic();
+    }
+    virtual void sweepThermalization() {
+        check(dqmc_sweep(ctx, 1), "dqmc_sweep");
+        ++performedSweeps;
+    }
+    virtual void sweepSimple(bool) {
+        throw_GeneralError("DetSDWGpu: greenUpdate=simple is not served by the GPU path (use stabilized)");
+    }
+    virtual void sweepSimpleThermalization() { sweepSimple(false); }
+
+    virtual std::vector<ScalarObservable> getScalarObservables() {
+        std::vector<ScalarObservable> obs;
+        obs.push_back(ScalarObservable(std::cref(normMeanPhi), "normMeanPhi", "nmp"));
+        obs.push_back(ScalarObservable(std::cref(meanPhiSquared), "meanPhiSquared", "mps"));
+        obs.push_back(ScalarObservable(std::cref(phiActionValue), "phiAction", "sphi"));
+        return obs;
+    }
+    virtual std::vector<VectorObservable> getVectorObservables() { return std::vector<VectorObservable>(); }
+    virtual std::vector<KeyValueObservable> getKeyValueObservables() { return std::vector<KeyValueObservable>(); }
+
+    // configuration streams: host I/O, outside the accelerated path
+    void saveConfigurationStreamText(const std::string& = ".") {}
+    void saveConfigurationStreamBinary(const std::string& = ".") {}
+    void saveConfigurationStreamTextHeader(const std::string&, const std::string& = ".") {}
+    void saveConfigurationStreamBinaryHeaderfile(const std::string&, const std::string& = ".") {}
+
+    // replica exchange interface (detsdwopdim.cpp:5189-5242)
+    num get_exchange_parameter_value() const {
+        double r = 0;
+        dqmc_get_exchange_parameter(ctx, 0, &r);
+        return r;
+    }
+    void set_exchange_parameter_value(num r) {
+        pars.r = r;
+        check(dqmc_set_exchange_parameter(ctx, 0, r), "dqmc_set_exchange_parameter");
+    }
+    const char* get_exchange_parameter_name() const { return "r"; }
+    num get_exchange_action_contribution() const {
+        double a = 0;
+        const_cast<DetSDWGpu*>(this)->check(dqmc_exchange_actions(ctx, nullptr, &a), "dqmc_exchange_actions");
+        return a;
+    }
+    void get_control_data(std::string& buffer) const {
+        dqmc_control_data cd;
+        dqmc_get_control_data(ctx, 0, &cd);
+        buffer.assign(reinterpret_cast<const char*>(&cd), sizeof cd);
+    }
+    void set_control_data(const std::string& buffer) {
+        if (buffer.size() != sizeof(dqmc_control_data)) throw_GeneralError("DetSDWGpu: bad control data blob");
+        dqmc_control_data cd;
+        std::memcpy(&cd, buffer.data(), sizeof cd);
+        check(dqmc_set_control_data(ctx, 0, &cd), "dqmc_set_control_data");
+    }
+
+    // checkpointing: fields + control data (G and the UDT storage are rebuilt, as in the reference:
+    // detsdwopdim.h:1117-1148, detmodel.h:493-502)
+    template <class Archive>
+    void saveContents(Archive& ar) {
+        std::vector<double> phi = downloadPhi();
+        dqmc_control_data cd;
+        dqmc_get_control_data(ctx, 0, &cd);
+        std::string blob(reinterpret_cast<const char*>(&cd), sizeof cd);
+        ar & phi & blob & performedSweeps;
+    }
+    template <class Archive>
+    void loadContents(Archive& ar) {
+        std::vector<double> phi;
+        std::string blob;
+        ar & phi & blob & performedSweeps;
+        check(dqmc_upload_fields(ctx, 0, phi.data()), "dqmc_upload_fields");
+        set_control_data(blob);
+        check(dqmc_setup_storage(ctx), "dqmc_setup_storage");
+    }
+
+    dqmc_ctx* context() { return ctx; }
+
+private:
+    static void fillFromRng(void* self, double* out, size_t n) {
+        RngWrapper& g = static_cast<DetSDWGpu*>(self)->rng;
+        for (size_t i = 0; i < n; ++i) out[i] = g.rand01();
+    }
+    void check(int status, const char* what) {
+        if (status != DQMC_OK)
+            throw_GeneralError(std::string(what) + " failed: " + dqmc_last_error(ctx));
+    }
+    std::vector<double> downloadPhi() {
+        std::vector<double> phi(size_t(pars.m + 1) * OPDIM * pars.L * pars.L);
+        check(dqmc_download_fields(ctx, 0, phi.data()), "dqmc_download_fields");
+        return phi;
+    }
+    // bosonic observables of DetSDW::measure (detsdwopdim.cpp:440-506): |mean phi|, mean phi^2, action
+    void measureBosonic() {
+        const std::vector<double> phi = downloadPhi();
+        const size_t N = size_t(pars.L) * pars.L;
+        double mean[3] = {0, 0, 0}, sq = 0;
+        for (uint32_t k = 1; k <= pars.m; ++k)
+            for (int d = 0; d < OPDIM; ++d)
+                for (size_t s = 0; s < N; ++s) {
+                    const double v = phi[(size_t(k) * OPDIM + d) * N + s];
+                    mean[d] += v;
+                    sq += v * v;
+                }
+        double nrm = 0;
+        for (int d = 0; d < OPDIM; ++d) { mean[d] /= double(N * pars.m); nrm += mean[d] * mean[d]; }
+        normMeanPhi = std::sqrt(nrm);
+        meanPhiSquared = sq / double(N * pars.m);
+        double act = 0;
+        check(dqmc_phi_action(ctx, &act), "dqmc_phi_action");
+        phiActionValue = act / double(N * pars.m);
+    }
+
+    RngWrapper& rng;
+    ModelParams pars;
+    dqmc_ctx* ctx;
+    num normMeanPhi, meanPhiSquared, phiActionValue;
+    uint32_t performedSweeps;
+};
+
+// same signature as the reference's createReplica (detsdwopdim.cpp:48-84)
+template <int OPDIM>
+void createReplica(std::unique_ptr<DetSDWGpu<OPDIM>>& replica_out, RngWrapper& rng, ModelParamsDetSDW pars,
+                   DetModelLoggingParams /*loggingPars*/ = DetModelLoggingParams(), const std::string& /*logfiledir*/ = "") {
+    pars = updateTemperatureParameters(pars);
+    pars.check();
+    replica_out = std::unique_ptr<DetSDWGpu<OPDIM>>(new DetSDWGpu<OPDIM>(rng, pars));
+}
+
+// replica-exchange probability (detsdwopdim.cpp:5251-5264) for the PT driver
+template <int OPDIM>
+inline num get_replica_exchange_probability_gpu(num r1, num action1, num r2, num action2) {
+    return dqmc_exchange_probability(r1, action1, r2, action2);
+}
+
+#endif  // DETSDW_GPU_H_

@@ -324,3 +324,33 @@ def test_full_size_properties(kw):
     assert relerr(b.green(0), o.green[0]) < TOL_G
     assert np.all(b.green_consistency() < 1e-8)                     # wrapped vs advanced G at the last advance
     assert relerr(b.green(1), b.green_for_timeslice(0, rep=1)) < 1e-9
+
+
+# ---------------------------------------------------------------- the reference's own driver on top of the C ABI
+def test_reference_driver_with_gpu_shim(tmp_path):
+    """host/_build/detqmcsdw_gpu = the reference's DetQMC<Model, ModelParams> driver (compiled unmodified from
+    the reference tree in the development container) instantiated with include/detsdw_gpu.h.  Its
+    thermalised step size, acceptance and time series must equal the oracle's trajectory for the same seed."""
+    import os
+    import subprocess
+    from dqmc_oracle import SdwOracle, SdwParams
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "host", "_build", "detqmcsdw_gpu")
+    if not os.path.exists(exe):
+        pytest.skip("host/_build/detqmcsdw_gpu not built (needs the reference tree: make -C host)")
+    therm, sweeps = 10, 10
+    out = subprocess.run([exe, "L=4", "beta=2", "dtau=0.1", "s=10", "r=-1", "thermalization=%d" % therm,
+                          "sweeps=%d" % sweeps, "rngSeed=1020304050", "simindex=0"], cwd=str(tmp_path),
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    series = [float(x) for x in open(os.path.join(str(tmp_path), "normMeanPhi.series")) if x.strip() and x[0] != "#"]
+    assert len(series) == sweeps
+    o = SdwOracle(SdwParams(L=4, m=20, s=10, r=-1.0))
+    for _ in range(therm):
+        o.sweep_thermalization()
+    ref = []
+    for _ in range(sweeps):
+        o.sweep()
+        ref.append(float(np.linalg.norm(o.phi[1:].mean(axis=(0, 2)))))
+    assert np.allclose(series, ref, rtol=0, atol=2e-6)               # the driver writes 6 significant digits
+    info = open(os.path.join(str(tmp_path), "info.dat")).read()
+    assert "libdqmc_b200" in info

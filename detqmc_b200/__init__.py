@@ -8,3 +8,4 @@ fails loudly when the shared library is missing, and creating a context fails wi
 """
 from .lib import load_library, DqmcParams, ControlData, DqmcError          # noqa: F401
 from .sdw import DetSDWBatch, ReplicaExchangeLadder                          # noqa: F401
+from .hubbard import DetHubbardBatch                                         # noqa: F401

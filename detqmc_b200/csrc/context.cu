@@ -58,7 +58,7 @@ int prof_category(const char* call) {
     if (!std::strncmp(call, "qr_form_q", 9) || !std::strncmp(call, "qr_blocked_form_q", 17) ||
         !std::strncmp(call, "qr_blocked_apply_qh", 19)) return 3;
     if (!std::strncmp(call, "trsm_upper", 10)) return 4;
-    if (!std::strncmp(call, "update_", 7)) return 5;
+    if (!std::strncmp(call, "update_", 7) || !std::strncmp(call, "hub_update", 10)) return 5;
     return 6;
 }
 cudaEvent_t prof_event(dqmc_ctx* ctx) {
@@ -116,9 +116,17 @@ const OpSpec kOps[5] = {
 
 // ---- batched building blocks; `off` selects the first replica, `batch` how many ---------------
 
+int gemm(dqmc_ctx* ctx, int ta, int tb, const cplx* A, long long sA, const cplx* B, long long sB, cplx* C,
+         long long sC, const double* rows, long long sRow, const double* cols, long long sCol,
+         const double* ks, long long sK, double beta, int batch);
+int hub_bmult(dqmc_ctx* ctx, int op, cplx* A, long long strideA, int k2, int k1, const double* colscale,
+              long long strideScale, int off, int batch);
+
+// B-matrix multiply of the model: `off` / `batch` count MATRICES (== replicas for DetSDW)
 int sdw_bmult(dqmc_ctx* ctx, int op, cplx* A, long long strideA, int k2, int k1, const double* colscale,
               long long strideScale, int off, int batch) {
     if (k2 <= k1) return DQMC_OK;
+    if (ctx->p.model == DQMC_MODEL_HUBBARD) return hub_bmult(ctx, op, A, strideA, k2, k1, colscale, strideScale, off, batch);
     const OpSpec& o = kOps[op];
     CbLaunch a;
     a.A = A;
@@ -144,6 +152,9 @@ int sdw_bmult(dqmc_ctx* ctx, int op, cplx* A, long long strideA, int k2, int k1,
     return DQMC_OK;
 }
 
+int hub_bmult(dqmc_ctx* ctx, int op, cplx* A, long long strideA, int k2, int k1, const double* colscale,
+              long long strideScale, int off, int batch);
+
 int gemm(dqmc_ctx* ctx, int ta, int tb, const cplx* A, long long sA, const cplx* B, long long sB, cplx* C,
          long long sC, const double* rows, long long sRow, const double* cols, long long sCol,
          const double* ks, long long sK, double beta, int batch) {
@@ -164,6 +175,53 @@ int gemm(dqmc_ctx* ctx, int ta, int tb, const cplx* A, long long sA, const cplx*
 }
 
 // M (in `work`, destroyed) -> Q, d, T' with M = Q diag(d) T'
+// DetHubbard: B_sigma(k2, k1) applied slice by slice; every slice is one propagator GEMM with the diagonal
+// e^{+-sigma alpha s_k} fused as a row / k / column scaling (dethubbard.cpp:823-851, dethubbard.h:281-337)
+int hub_bmult(dqmc_ctx* ctx, int op, cplx* A, long long strideA, int k2, int k1, const double* colscale,
+              long long strideScale, int off, int batch) {
+    const size_t dd = DD(ctx);
+    const int N = ctx->N;
+    cplx* cur = A;
+    long long sCur = strideA;
+    cplx* other = ctx->hubTmp + size_t(off) * dd;
+    long long sOther = (long long)dd;
+    double* sc = ctx->hubScale + size_t(off) * N;
+    const bool ascending = (op == DQMC_OP_LEFT || op == DQMC_OP_RIGHT_INV);
+    const bool inverse = (op == DQMC_OP_LEFT_INV || op == DQMC_OP_RIGHT_INV);
+    const int count = k2 - k1;
+    for (int i = 0; i < count; ++i) {
+        const int k = ascending ? k1 + 1 + i : k2 - i;
+        const bool last = i == count - 1;
+        CKL(hub_scales_launch(ctx->aux, (long long)tab_stride(ctx), N, k, ctx->hubAlpha, inverse ? -1.0 : 1.0, sc, off,
+                              batch, ctx->stream));
+        const double* cs = last ? colscale : nullptr;
+        const long long scs = last ? strideScale : 0;
+        switch (op) {
+            case DQMC_OP_LEFT:        // diag_k (P in)
+                RET(gemm(ctx, 0, 0, ctx->propT, 0, cur, sCur, other, sOther, sc, N, cs, scs, nullptr, 0, 0.0, batch));
+                break;
+            case DQMC_OP_RIGHT:       // (in diag_k) P
+                RET(gemm(ctx, 0, 0, cur, sCur, ctx->propT, 0, other, sOther, nullptr, 0, nullptr, 0, sc, N, 0.0, batch));
+                break;
+            case DQMC_OP_LEFT_INV:    // P^-1 (diag_k^-1 in)
+                RET(gemm(ctx, 0, 0, ctx->propTinv, 0, cur, sCur, other, sOther, nullptr, 0, nullptr, 0, sc, N, 0.0, batch));
+                break;
+            case DQMC_OP_RIGHT_INV:   // (in P^-1) diag_k^-1
+                RET(gemm(ctx, 0, 0, cur, sCur, ctx->propTinv, 0, other, sOther, nullptr, 0, sc, N, nullptr, 0, 0.0, batch));
+                break;
+            default:                  // LEFT_ADJ: P^T (diag_k in)
+                RET(gemm(ctx, 1, 0, ctx->propT, 0, cur, sCur, other, sOther, nullptr, 0, cs, scs, sc, N, 0.0, batch));
+                break;
+        }
+        std::swap(cur, other);
+        std::swap(sCur, sOther);
+    }
+    if (cur != A)
+        CK(cudaMemcpy2DAsync(A, size_t(strideA) * sizeof(cplx), cur, size_t(sCur) * sizeof(cplx), dd * sizeof(cplx), batch,
+                             cudaMemcpyDeviceToDevice, ctx->stream));
+    return DQMC_OK;
+}
+
 // the rank-K flush of the delayed updates is accounted to the update family, not to the GEMMs
 inline cudaError_t update_flush_gemm(const GemmArgs& g, cudaStream_t st) { return gemm_launch(g, st); }
 
@@ -469,6 +527,12 @@ int finish_rng_window(dqmc_ctx* ctx) {
 }
 
 int launch_update(dqmc_ctx* ctx, int k, int therm) {
+    if (ctx->p.model == DQMC_MODEL_HUBBARD) {
+        CKL(hub_update_slice_launch(ctx->G, (long long)DD(ctx), ctx->N, ctx->aux, (long long)tab_stride(ctx), k,
+                                    ctx->hubAlpha, ctx->rngbuf, (long long)ctx->rngStride, ctx->rngWindow, ctx->cursor,
+                                    ctx->accepted, ctx->acceptedTotal, ctx->errflag, ctx->R, ctx->stream));
+        return DQMC_OK;
+    }
     UpdateArgs a;
     a.G = ctx->G; a.strideG = (long long)DD(ctx);
     a.phi = ctx->phi; a.coshT = ctx->coshT; a.sinhT = ctx->sinhT;
@@ -666,9 +730,16 @@ int dqmc_create(const dqmc_params* params, int n_replicas, int device, dqmc_ctx*
     *out = ctx;                      // returned even on failure so the caller can read the error text
     ctx->p = *params;
     const dqmc_params& p = ctx->p;
-    if (p.model != DQMC_MODEL_SDW) { ctx->err = "only DQMC_MODEL_SDW is implemented in this build"; return DQMC_ERR_PARAM; }
+    const bool hub = p.model == DQMC_MODEL_HUBBARD;
+    if (p.model != DQMC_MODEL_SDW && !hub) { ctx->err = "unknown model"; return DQMC_ERR_PARAM; }
+    if (hub) {
+        // DetHubbard: real N x N Green's functions, two components; fields are the +-1 auxiliary spins
+        ctx->p.opdim = 1; ctx->p.delaySteps = 1; ctx->p.globalShift = 0; ctx->p.weakZflux = 0;
+        if (p.U < 0) { ctx->err = "DetHubbard needs U >= 0"; return DQMC_ERR_PARAM; }
+        if (p.checkerboard && (p.L % 2)) { ctx->err = "checkerboard propagator needs an even L"; return DQMC_ERR_PARAM; }
+    }
     if (p.opdim < 1 || p.opdim > 3) { ctx->err = "opdim must be 1, 2 or 3"; return DQMC_ERR_PARAM; }
-    if (p.L < 2 || p.L % 2) { ctx->err = "checkerboard decomposition needs an even L >= 2"; return DQMC_ERR_PARAM; }
+    if (p.L < 2 || (!hub && p.L % 2)) { ctx->err = "checkerboard decomposition needs an even L >= 2"; return DQMC_ERR_PARAM; }
     if (p.weakZflux && p.opdim == 3) { ctx->err = "weakZflux is only supported for opdim < 3"; return DQMC_ERR_PARAM; }
     if (p.m < 2 || p.s < 1 || p.dtau <= 0) { ctx->err = "need m >= 2, s >= 1, dtau > 0"; return DQMC_ERR_PARAM; }
     if (p.delaySteps < 1 || p.delaySteps > p.L * p.L) { ctx->err = "delaySteps out of range"; return DQMC_ERR_PARAM; }
@@ -676,13 +747,13 @@ int dqmc_create(const dqmc_params* params, int n_replicas, int device, dqmc_ctx*
     ctx->R = n_replicas;
     ctx->opdim = p.opdim;
     ctx->N = p.L * p.L;
-    ctx->msf = p.opdim == 3 ? 4 : 2;
+    ctx->msf = hub ? 1 : (p.opdim == 3 ? 4 : 2);
     ctx->D = ctx->msf * ctx->N;
     ctx->m = p.m;
     ctx->s = p.s;
     while (ctx->m <= ctx->s) ctx->s -= 1;                  // updateTemperatureParameters, detmodelparams.h:108-113
     ctx->n = (ctx->m + ctx->s - 1) / ctx->s;
-    ctx->ngc = 1;
+    ctx->ngc = hub ? 2 : 1;
     ctx->nmat = ctx->R * ctx->ngc;
     ctx->device = device;
     ctx->launches = 0;
@@ -743,12 +814,12 @@ int dqmc_create(const dqmc_params* params, int n_replicas, int device, dqmc_ctx*
     CK(dmalloc(&ctx->consistency, nm));
     CK(dmalloc(&ctx->eyeM, dd));
     CK(dmalloc(&ctx->onesV, D));
-    ctx->kmax = (ctx->msf * p.delaySteps + 3) & ~3;        // padded to the 4-term chunks of the update kernel
+    ctx->kmax = (ctx->msf * ctx->p.delaySteps + 3) & ~3;        // padded to the 4-term chunks of the update kernel
     CK(dmalloc(&ctx->X, D * ctx->kmax * R));
     CK(dmalloc(&ctx->Y, D * ctx->kmax * R));
     CK(cudaMemsetAsync(ctx->X, 0, sizeof(cplx) * D * ctx->kmax * R, ctx->stream));   // finite everywhere (see extend_xy)
     CK(cudaMemsetAsync(ctx->Y, 0, sizeof(cplx) * D * ctx->kmax * R, ctx->stream));
-    ctx->rngCap = size_t(ctx->m) * ctx->N * (p.opdim + 1);
+    ctx->rngCap = size_t(ctx->m) * ctx->N * (ctx->p.opdim + 1);      // Hubbard: <= 2 values per attempt
     ctx->rngAlloc = ctx->rngCap;
     ctx->rngStride = ctx->rngCap;
     ctx->rngResident = false;
@@ -772,10 +843,30 @@ int dqmc_create(const dqmc_params* params, int n_replicas, int device, dqmc_ctx*
     CK(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_err), sizeof(int)));
     CK(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_acc), R * sizeof(uint32_t)));
 
+    ctx->aux = nullptr; ctx->propT = nullptr; ctx->propTinv = nullptr; ctx->hubScale = nullptr; ctx->hubTmp = nullptr;
+    ctx->hubReal = nullptr; ctx->cbtab = nullptr; ctx->hubAlpha = 0;
     std::vector<cplx> tab;
-    cb_build_tables(p, tab);
-    CK(dmalloc(&ctx->cbtab, tab.size()));
-    CK(cudaMemcpyAsync(ctx->cbtab, tab.data(), tab.size() * sizeof(cplx), cudaMemcpyHostToDevice, ctx->stream));
+    if (!hub) {
+        cb_build_tables(p, tab);
+        CK(dmalloc(&ctx->cbtab, tab.size()));
+        CK(cudaMemcpyAsync(ctx->cbtab, tab.data(), tab.size() * sizeof(cplx), cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        ctx->hubAlpha = std::acosh(std::exp(p.dtau * p.U * 0.5));           // dethubbard.cpp:55
+        std::vector<double> P, Pinv;
+        hub_build_propagators(p, P, Pinv);
+        std::vector<cplx> pc(dd), pic(dd);
+        for (size_t i = 0; i < dd; ++i) { pc[i] = make_double2(P[i], 0); pic[i] = make_double2(Pinv[i], 0); }
+        CK(dmalloc(&ctx->propT, dd));
+        CK(dmalloc(&ctx->propTinv, dd));
+        CK(dmalloc(&ctx->hubScale, D * nm));
+        CK(dmalloc(&ctx->hubTmp, dd * nm));
+        CK(dmalloc(&ctx->hubReal, dd));
+        CK(dmalloc(&ctx->aux, tab_stride(ctx) * R));
+        CK(cudaMemsetAsync(ctx->aux, 0, sizeof(int32_t) * tab_stride(ctx) * R, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->propT, pc.data(), dd * sizeof(cplx), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->propTinv, pic.data(), dd * sizeof(cplx), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
     CK(cudaMemsetAsync(ctx->phi, 0, sizeof(double) * phi_stride(ctx) * R, ctx->stream));
     CK(cudaMemsetAsync(ctx->coshT, 0, sizeof(double) * tab_stride(ctx) * R, ctx->stream));
     CK(cudaMemsetAsync(ctx->sinhT, 0, sizeof(double) * tab_stride(ctx) * R, ctx->stream));
@@ -814,7 +905,8 @@ void dqmc_destroy(dqmc_ctx* ctx) {
                    ctx->bkPhi, ctx->bkCosh, ctx->bkSinh, ctx->rvals, ctx->tau, ctx->perm, ctx->colnorm, ctx->vecA,
                    ctx->vecB, ctx->vecC, ctx->vecD, ctx->dtmp, ctx->logdet, ctx->bkLogdet, ctx->consistency, ctx->eyeM,
                    ctx->onesV, ctx->X, ctx->Y, ctx->rngbuf, ctx->cursor, ctx->ctrl, ctx->accepted, ctx->errflag,
-                   ctx->actions, ctx->shiftbuf, ctx->cbtab, ctx->acceptedTotal, ctx->siteState, ctx->kvec};
+                   ctx->actions, ctx->shiftbuf, ctx->cbtab, ctx->acceptedTotal, ctx->siteState, ctx->kvec, ctx->aux,
+                   ctx->propT, ctx->propTinv, ctx->hubScale, ctx->hubTmp, ctx->hubReal};
     for (void* p : dev) if (p) cudaFree(p);
     qr_workspace_destroy(&ctx->qr);
     void* host[] = {ctx->h_rng, ctx->h_cursor, ctx->h_scalars, ctx->h_ctrl, ctx->h_err, ctx->h_acc};
@@ -904,6 +996,12 @@ int dqmc_rng_stream_sample(uint32_t seed, uint32_t process_index, size_t n, doub
 // ---- state -------------------------------------------------------------------------------------
 int dqmc_upload_fields(dqmc_ctx* ctx, int rep, const void* fields) {
     if (!valid_rep(ctx, rep) || !fields) return DQMC_ERR_PARAM;
+    if (ctx->p.model == DQMC_MODEL_HUBBARD) {
+        CK(cudaMemcpyAsync(ctx->aux + size_t(rep) * tab_stride(ctx), fields, sizeof(int32_t) * tab_stride(ctx),
+                           cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        return DQMC_OK;
+    }
     CK(cudaMemcpyAsync(ctx->phi + size_t(rep) * phi_stride(ctx), fields, sizeof(double) * phi_stride(ctx),
                        cudaMemcpyHostToDevice, ctx->stream));
     CKL(launch_update_tables(ctx->phi + size_t(rep) * phi_stride(ctx), ctx->coshT + size_t(rep) * tab_stride(ctx),
@@ -916,6 +1014,14 @@ int dqmc_upload_fields(dqmc_ctx* ctx, int rep, const void* fields) {
 
 int dqmc_init_random_fields(dqmc_ctx* ctx, int rep) {
     if (!valid_rep(ctx, rep)) return DQMC_ERR_PARAM;
+    if (ctx->p.model == DQMC_MODEL_HUBBARD) {
+        // setupRandomAuxfield, dethubbard.cpp:741-751: per (k, site) one rand01(), <= 0.5 -> +1
+        std::vector<int32_t> aux(tab_stride(ctx), 0);
+        RngStream& g = ctx->rng[rep];
+        for (int k = 1; k <= ctx->m; ++k)
+            for (int site = 0; site < ctx->N; ++site) aux[size_t(k) * ctx->N + site] = g.draw() <= 0.5 ? +1 : -1;
+        return dqmc_upload_fields(ctx, rep, aux.data());
+    }
     // setupRandomField, detsdwopdim.cpp:1098-1113: per (k, site): OPDIM x randRange(-1, 1), then one
     // rand01() for cdwl (drawn even though cdwU == 0)
     std::vector<double> phi(phi_stride(ctx), 0.0);
@@ -931,6 +1037,12 @@ int dqmc_init_random_fields(dqmc_ctx* ctx, int rep) {
 
 int dqmc_download_fields(dqmc_ctx* ctx, int rep, void* fields) {
     if (!valid_rep(ctx, rep) || !fields) return DQMC_ERR_PARAM;
+    if (ctx->p.model == DQMC_MODEL_HUBBARD) {
+        CK(cudaMemcpyAsync(fields, ctx->aux + size_t(rep) * tab_stride(ctx), sizeof(int32_t) * tab_stride(ctx),
+                           cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        return DQMC_OK;
+    }
     CK(cudaMemcpyAsync(fields, ctx->phi + size_t(rep) * phi_stride(ctx), sizeof(double) * phi_stride(ctx),
                        cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -938,15 +1050,27 @@ int dqmc_download_fields(dqmc_ctx* ctx, int rep, void* fields) {
 }
 
 int dqmc_download_green(dqmc_ctx* ctx, int rep, int gc, double* out) {
-    if (!valid_rep(ctx, rep) || gc != 0 || !out) return DQMC_ERR_PARAM;
-    CK(cudaMemcpyAsync(out, ctx->G + size_t(rep) * DD(ctx), sizeof(cplx) * DD(ctx), cudaMemcpyDeviceToHost, ctx->stream));
+    if (!valid_rep(ctx, rep) || gc < 0 || gc >= ctx->ngc || !out) return DQMC_ERR_PARAM;
+    const cplx* src = ctx->G + (size_t(rep) * ctx->ngc + gc) * DD(ctx);
+    if (ctx->p.model == DQMC_MODEL_HUBBARD) {
+        CKL(hub_real_part_launch(src, ctx->hubReal, DD(ctx), ctx->stream));
+        CK(cudaMemcpyAsync(out, ctx->hubReal, sizeof(double) * DD(ctx), cudaMemcpyDeviceToHost, ctx->stream));
+    } else {
+        CK(cudaMemcpyAsync(out, src, sizeof(cplx) * DD(ctx), cudaMemcpyDeviceToHost, ctx->stream));
+    }
     CK(cudaStreamSynchronize(ctx->stream));
     return DQMC_OK;
 }
 
 int dqmc_upload_green(dqmc_ctx* ctx, int rep, int gc, const double* in) {
-    if (!valid_rep(ctx, rep) || gc != 0 || !in) return DQMC_ERR_PARAM;
-    CK(cudaMemcpyAsync(ctx->G + size_t(rep) * DD(ctx), in, sizeof(cplx) * DD(ctx), cudaMemcpyHostToDevice, ctx->stream));
+    if (!valid_rep(ctx, rep) || gc < 0 || gc >= ctx->ngc || !in) return DQMC_ERR_PARAM;
+    cplx* dst = ctx->G + (size_t(rep) * ctx->ngc + gc) * DD(ctx);
+    if (ctx->p.model == DQMC_MODEL_HUBBARD) {
+        CK(cudaMemcpyAsync(ctx->hubReal, in, sizeof(double) * DD(ctx), cudaMemcpyHostToDevice, ctx->stream));
+        CKL(hub_to_complex_launch(ctx->hubReal, dst, DD(ctx), ctx->stream));
+    } else {
+        CK(cudaMemcpyAsync(dst, in, sizeof(cplx) * DD(ctx), cudaMemcpyHostToDevice, ctx->stream));
+    }
     CK(cudaStreamSynchronize(ctx->stream));
     return DQMC_OK;
 }
@@ -979,11 +1103,24 @@ int dqmc_get_sweep_state(const dqmc_ctx* ctx, int32_t* out) {
 
 // ---- operators ---------------------------------------------------------------------------------
 int dqmc_bmat_mult(dqmc_ctx* ctx, int rep, int gc, int op, double* A_host, uint32_t k2, uint32_t k1) {
-    if (!valid_rep(ctx, rep) || gc != 0 || op < 0 || op > 4 || !A_host || k2 <= k1 || (int)k2 > ctx->m) return DQMC_ERR_PARAM;
-    cplx* buf = ctx->W[0] + size_t(rep) * DD(ctx);
-    CK(cudaMemcpyAsync(buf, A_host, sizeof(cplx) * DD(ctx), cudaMemcpyHostToDevice, ctx->stream));
-    RET(sdw_bmult(ctx, op, buf, (long long)DD(ctx), (int)k2, (int)k1, nullptr, 0, rep, 1));
-    CK(cudaMemcpyAsync(A_host, buf, sizeof(cplx) * DD(ctx), cudaMemcpyDeviceToHost, ctx->stream));
+    if (!valid_rep(ctx, rep) || gc < 0 || gc >= ctx->ngc || op < 0 || op > 4 || !A_host || k2 <= k1 || (int)k2 > ctx->m)
+        return DQMC_ERR_PARAM;
+    const int mat = rep * ctx->ngc + gc;
+    cplx* buf = ctx->W[0] + size_t(mat) * DD(ctx);
+    const bool hub = ctx->p.model == DQMC_MODEL_HUBBARD;
+    if (hub) {
+        CK(cudaMemcpyAsync(ctx->hubReal, A_host, sizeof(double) * DD(ctx), cudaMemcpyHostToDevice, ctx->stream));
+        CKL(hub_to_complex_launch(ctx->hubReal, buf, DD(ctx), ctx->stream));
+    } else {
+        CK(cudaMemcpyAsync(buf, A_host, sizeof(cplx) * DD(ctx), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    RET(sdw_bmult(ctx, op, buf, (long long)DD(ctx), (int)k2, (int)k1, nullptr, 0, mat, 1));
+    if (hub) {
+        CKL(hub_real_part_launch(buf, ctx->hubReal, DD(ctx), ctx->stream));
+        CK(cudaMemcpyAsync(A_host, ctx->hubReal, sizeof(double) * DD(ctx), cudaMemcpyDeviceToHost, ctx->stream));
+    } else {
+        CK(cudaMemcpyAsync(A_host, buf, sizeof(cplx) * DD(ctx), cudaMemcpyDeviceToHost, ctx->stream));
+    }
     CK(cudaStreamSynchronize(ctx->stream));
     return DQMC_OK;
 }
@@ -1032,14 +1169,15 @@ int dqmc_get_green_consistency(dqmc_ctx* ctx, double* out) {
 }
 
 int dqmc_logdet(dqmc_ctx* ctx, int rep, int gc, double* out) {
-    if (!valid_rep(ctx, rep) || gc != 0 || !out) return DQMC_ERR_PARAM;
-    CK(cudaMemcpyAsync(out, ctx->logdet + rep, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (!valid_rep(ctx, rep) || gc < 0 || gc >= ctx->ngc || !out) return DQMC_ERR_PARAM;
+    CK(cudaMemcpyAsync(out, ctx->logdet + rep * ctx->ngc + gc, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return DQMC_OK;
 }
 
 int dqmc_green_for_timeslice(dqmc_ctx* ctx, int rep, int gc, uint32_t kk, double* out) {
-    if (!valid_rep(ctx, rep) || gc != 0 || !out || (int)kk > ctx->m) return DQMC_ERR_PARAM;
+    if (!valid_rep(ctx, rep) || gc < 0 || gc >= ctx->ngc || !out || (int)kk > ctx->m) return DQMC_ERR_PARAM;
+    const int mat = rep * ctx->ngc + gc;
     const int k = (int)kk, s = ctx->s, m = ctx->m;
     const size_t dd = DD(ctx);
     const int D = ctx->D;
@@ -1054,7 +1192,7 @@ int dqmc_green_for_timeslice(dqmc_ctx* ctx, int rep, int gc, uint32_t kk, double
         const int k2 = std::min(k, k1 + s);
         UdtView in{buf[0], (long long)dd, dv[0], D, buf[1], (long long)dd};
         rc = chain_step(ctx, DQMC_OP_LEFT, haveR ? &in : nullptr, k2, k1, buf[0], (long long)dd, dv[0], D, buf[1],
-                        (long long)dd, rep, 1);
+                        (long long)dd, mat, 1);
         haveR = true;
         k1 = k2;
     }
@@ -1062,17 +1200,24 @@ int dqmc_green_for_timeslice(dqmc_ctx* ctx, int rep, int gc, uint32_t kk, double
         const int k1 = std::max(k, k2 - s);
         UdtView in{buf[2], (long long)dd, dv[1], D, buf[3], (long long)dd};
         rc = chain_step(ctx, DQMC_OP_LEFT_ADJ, haveL ? &in : nullptr, k2, k1, buf[2], (long long)dd, dv[1], D, buf[3],
-                        (long long)dd, rep, 1);
+                        (long long)dd, mat, 1);
         haveL = true;
         k2 = k1;
     }
     if (rc == DQMC_OK) {
         UdtView rv = haveR ? UdtView{buf[0], (long long)dd, dv[0], D, buf[1], (long long)dd} : identity_view(ctx);
         UdtView lv = haveL ? UdtView{buf[2], (long long)dd, dv[1], D, buf[3], (long long)dd} : identity_view(ctx);
-        rc = green_from_udts(ctx, rv, lv, buf[4], (long long)dd, dv[2], rep, 1);
+        rc = green_from_udts(ctx, rv, lv, buf[4], (long long)dd, dv[2], mat, 1);
     }
     if (rc == DQMC_OK) {
-        cudaError_t e = cudaMemcpyAsync(out, buf[4], sizeof(cplx) * dd, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaError_t e;
+        if (ctx->p.model == DQMC_MODEL_HUBBARD) {
+            e = hub_real_part_launch(buf[4], ctx->hubReal, dd, ctx->stream);
+            if (e == cudaSuccess)
+                e = cudaMemcpyAsync(out, ctx->hubReal, sizeof(double) * dd, cudaMemcpyDeviceToHost, ctx->stream);
+        } else {
+            e = cudaMemcpyAsync(out, buf[4], sizeof(cplx) * dd, cudaMemcpyDeviceToHost, ctx->stream);
+        }
         if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); rc = DQMC_ERR_CUDA; }
     }
     cudaStreamSynchronize(ctx->stream);
@@ -1156,7 +1301,7 @@ int dqmc_gemm_host(dqmc_ctx* ctx, int transa, int transb, int M, int N, int K, c
 // ---- Monte Carlo -------------------------------------------------------------------------------
 int dqmc_update_slice(dqmc_ctx* ctx, uint32_t k, int thermalization, uint32_t* n_accepted) {
     if (!ctx || k < 1 || (int)k > ctx->m) return DQMC_ERR_PARAM;
-    RET(upload_rng_window(ctx, size_t(ctx->N) * (ctx->opdim + 1)));
+    RET(upload_rng_window(ctx, size_t(ctx->N) * (ctx->p.opdim + 1)));
     RET(launch_update(ctx, (int)k, thermalization));
     if (n_accepted)
         CK(cudaMemcpyAsync(ctx->h_acc, ctx->accepted, sizeof(uint32_t) * ctx->R, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1167,6 +1312,7 @@ int dqmc_update_slice(dqmc_ctx* ctx, uint32_t k, int thermalization, uint32_t* n
 
 int dqmc_global_shift_move(dqmc_ctx* ctx, int32_t* accepted) {
     if (!ctx) return DQMC_ERR_PARAM;
+    if (ctx->p.model != DQMC_MODEL_SDW) { ctx->err = "only defined for DetSDW"; return DQMC_ERR_STATE; }
     RET(global_shift_move(ctx, accepted));
     CK(cudaStreamSynchronize(ctx->stream));
     return DQMC_OK;
@@ -1174,6 +1320,7 @@ int dqmc_global_shift_move(dqmc_ctx* ctx, int32_t* accepted) {
 
 int dqmc_phi_action(dqmc_ctx* ctx, double* out) {
     if (!ctx || !out) return DQMC_ERR_PARAM;
+    if (ctx->p.model != DQMC_MODEL_SDW) { ctx->err = "only defined for DetSDW"; return DQMC_ERR_STATE; }
     CKL(launch_phi_action(ctx->phi, ctx->rvals, ctx->actions, ctx->p.L, ctx->opdim, ctx->m, ctx->p.dtau, ctx->p.c,
                           ctx->p.u, (long long)phi_stride(ctx), ctx->R, ctx->stream));
     CK(cudaMemcpyAsync(out, ctx->actions, sizeof(double) * ctx->R, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1278,6 +1425,7 @@ int dqmc_accepted_total(dqmc_ctx* ctx, uint64_t* out) {
 // ---- replica exchange --------------------------------------------------------------------------
 int dqmc_exchange_actions(dqmc_ctx* ctx, double* actions_dev, double* actions_host) {
     if (!ctx) return DQMC_ERR_PARAM;
+    if (ctx->p.model != DQMC_MODEL_SDW) { ctx->err = "only defined for DetSDW"; return DQMC_ERR_STATE; }
     double* dst = actions_dev ? actions_dev : ctx->actions;
     CKL(launch_exchange_action(ctx->phi, dst, ctx->N, ctx->opdim, ctx->m, ctx->p.dtau, (long long)phi_stride(ctx),
                                ctx->R, ctx->stream));
@@ -1290,6 +1438,7 @@ int dqmc_exchange_actions(dqmc_ctx* ctx, double* actions_dev, double* actions_ho
 
 int dqmc_exchange_pack(dqmc_ctx* ctx, double* payload_dev, int n_uniforms) {
     if (!ctx || !payload_dev || n_uniforms < 0) return DQMC_ERR_PARAM;
+    if (ctx->p.model != DQMC_MODEL_SDW) { ctx->err = "only defined for DetSDW"; return DQMC_ERR_STATE; }
     const int R = ctx->R;
     CKL(launch_exchange_action(ctx->phi, payload_dev, ctx->N, ctx->opdim, ctx->m, ctx->p.dtau,
                                (long long)phi_stride(ctx), R, ctx->stream));

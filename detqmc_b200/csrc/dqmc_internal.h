@@ -179,6 +179,19 @@ struct UpdateArgs {
 int update_rounds_per_slice(const UpdateModel& m, int inline_flush);
 cudaError_t update_round_launch(const UpdateModel& m, const UpdateArgs& a, cudaStream_t st);
 
+// ------------------------------------------------------------------------------------------------
+// DetHubbard (hubbard_kernels.cu)
+// ------------------------------------------------------------------------------------------------
+void hub_build_propagators(const dqmc_params& p, std::vector<double>& P, std::vector<double>& Pinv);
+cudaError_t hub_scales_launch(const int32_t* aux, long long strideAux, int N, int k, double alpha, double sign,
+                              double* out, int off, int batch, cudaStream_t st);
+cudaError_t hub_real_part_launch(const cplx* in, double* out, size_t n, cudaStream_t st);
+cudaError_t hub_to_complex_launch(const double* in, cplx* out, size_t n, cudaStream_t st);
+cudaError_t hub_update_slice_launch(cplx* G, long long strideG, int N, int32_t* aux, long long strideAux, int k,
+                                    double alpha, const double* rng, long long strideRng, int rngWindow, int* cursor,
+                                    uint32_t* accepted, unsigned long long* acceptedTotal, int* errflag, int batch,
+                                    cudaStream_t st);
+
 }  // namespace dqmc
 
 // ------------------------------------------------------------------------------------------------
@@ -269,6 +282,9 @@ struct dqmc_ctx {
     dqmc::cplx* propT;     // e^{-dtau T} as complex D x D
     dqmc::cplx* propTinv;
     double* hubScale;      // [nmat][D] scratch row/col scales
+    dqmc::cplx* hubTmp;    // [nmat][D*D] ping-pong buffer of the dense B chains
+    double* hubReal;       // [D*D] staging for real <-> complex conversion
+    double hubAlpha;       // cosh(alpha) = exp(dtau U / 2)
 
     std::vector<dqmc::RngStream> rng;
     std::vector<double> h_r;

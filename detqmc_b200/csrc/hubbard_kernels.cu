@@ -1,0 +1,278 @@
+// DetHubbard on the GPU: dense B matrices through the DMMA GEMM, single-flip local updates.
+//
+// Replaces DetHubbard::computeBmat and the dense functors (dethubbard.cpp:823-851, dethubbard.h:281-337),
+// setupPropTmat (dethubbard.cpp:753-821; detmodel.cpp:21-39), setupRandomAuxfield (:741-751) and
+// updateInSlice / weightRatioSingleFlip / updateGreenFunctionWithFlip (:141-171, 892-933).
+//
+// B_sigma(k) = diag(exp(sigma * alpha * s_k)) * e^{-dtau T}.  The reference multiplies with the dense
+// chain product and LU-inverts it on every call; here a chain is applied slice by slice as
+// "propagator GEMM with the diagonal fused as a row / column / k scaling", and the inverse propagator
+// e^{+dtau T} is precomputed once.  The two Green's-function components (up, down) are two matrices of
+// the batch (matrix index = 2 * replica + gc), stored as complex with zero imaginary part so that the
+// whole stabilisation code (GEMM, blocked QR, Green's function) is shared with DetSDW.
+#include "dqmc_internal.h"
+
+#include <cmath>
+
+namespace dqmc {
+
+// ------------------------------------------------------------------------------------------------
+// host: e^{-dtau T} and e^{+dtau T}
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+// cyclic Jacobi eigenvalue iteration for a real symmetric n x n matrix (row-major a, destroyed);
+// eigenvectors in the columns of v.  n <= a few hundred, called once per context.
+void jacobi_eigh(std::vector<double>& a, std::vector<double>& v, int n) {
+    v.assign(size_t(n) * n, 0.0);
+    for (int i = 0; i < n; ++i) v[size_t(i) * n + i] = 1.0;
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        double off = 0;
+        for (int p = 0; p < n; ++p)
+            for (int q = p + 1; q < n; ++q) off += a[size_t(p) * n + q] * a[size_t(p) * n + q];
+        if (off < 1e-30) break;
+        for (int p = 0; p < n - 1; ++p)
+            for (int q = p + 1; q < n; ++q) {
+                const double apq = a[size_t(p) * n + q];
+                if (std::fabs(apq) < 1e-300) continue;
+                const double app = a[size_t(p) * n + p], aqq = a[size_t(q) * n + q];
+                const double theta = (aqq - app) / (2.0 * apq);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+                const double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
+                for (int k = 0; k < n; ++k) {
+                    const double akp = a[size_t(k) * n + p], akq = a[size_t(k) * n + q];
+                    a[size_t(k) * n + p] = c * akp - s * akq;
+                    a[size_t(k) * n + q] = s * akp + c * akq;
+                }
+                for (int k = 0; k < n; ++k) {
+                    const double apk = a[size_t(p) * n + k], aqk = a[size_t(q) * n + k];
+                    a[size_t(p) * n + k] = c * apk - s * aqk;
+                    a[size_t(q) * n + k] = s * apk + c * aqk;
+                }
+                for (int k = 0; k < n; ++k) {
+                    const double vkp = v[size_t(k) * n + p], vkq = v[size_t(k) * n + q];
+                    v[size_t(k) * n + p] = c * vkp - s * vkq;
+                    v[size_t(k) * n + q] = s * vkp + c * vkq;
+                }
+            }
+    }
+}
+
+void matmul(const std::vector<double>& A, const std::vector<double>& B, std::vector<double>& C, int n) {
+    C.assign(size_t(n) * n, 0.0);
+    for (int i = 0; i < n; ++i)
+        for (int k = 0; k < n; ++k) {
+            const double aik = A[size_t(i) * n + k];
+            if (aik == 0.0) continue;
+            for (int j = 0; j < n; ++j) C[size_t(i) * n + j] += aik * B[size_t(k) * n + j];
+        }
+}
+
+}  // namespace
+
+// P = e^{-dtau T}, Pinv = e^{+dtau T}  (symmetric; row-major == column-major)
+void hub_build_propagators(const dqmc_params& p, std::vector<double>& P, std::vector<double>& Pinv) {
+    const int L = p.L, N = L * L;
+    auto nb = [&](int dir, int s) {
+        const int x = s % L, y = s / L;
+        switch (dir) {
+            case 0: return y * L + (x + 1) % L;
+            case 1: return y * L + (x + L - 1) % L;
+            case 2: return ((y + 1) % L) * L + x;
+            default: return ((y + L - 1) % L) * L + x;
+        }
+    };
+    if (!p.checkerboard) {
+        // T = -t * adjacency - mu * 1;  e^{-+dtau T} = V e^{-+dtau w} V^T   (detmodel.cpp:21-39)
+        std::vector<double> tm(size_t(N) * N, 0.0), v;
+        for (int s = 0; s < N; ++s) {
+            tm[size_t(s) * N + s] -= p.mu;
+            for (int d = 0; d < 4; ++d) tm[size_t(nb(d, s)) * N + s] -= p.t;
+        }
+        jacobi_eigh(tm, v, N);
+        P.assign(size_t(N) * N, 0.0);
+        Pinv.assign(size_t(N) * N, 0.0);
+        for (int k = 0; k < N; ++k) {
+            const double w = tm[size_t(k) * N + k];
+            const double em = std::exp(-p.dtau * w), ep = std::exp(+p.dtau * w);
+            for (int i = 0; i < N; ++i) {
+                const double vik = v[size_t(i) * N + k];
+                for (int j = 0; j < N; ++j) {
+                    const double x = vik * v[size_t(j) * N + k];
+                    P[size_t(i) * N + j] += em * x;
+                    Pinv[size_t(i) * N + j] += ep * x;
+                }
+            }
+        }
+    } else {
+        // product of the four bond-group exponentials, each (cosh + sinh * k) with k a perfect matching
+        // (dethubbard.cpp:768-821; no chemical potential in this form); the inverse reverses the order
+        std::vector<double> k4[4];
+        for (auto& k : k4) k.assign(size_t(N) * N, 0.0);
+        for (int y = 0; y < L; ++y)
+            for (int x = 0; x < L; x += 2) {
+                const int a = y * L + x, na = nb(0, a), nbb = nb(0, na);
+                k4[0][size_t(a) * N + na] = k4[0][size_t(na) * N + a] = 1.0;
+                k4[1][size_t(na) * N + nbb] = k4[1][size_t(nbb) * N + na] = 1.0;
+            }
+        for (int x = 0; x < L; ++x)
+            for (int y = 0; y < L; y += 2) {
+                const int a = y * L + x, na = nb(2, a), nbb = nb(2, na);
+                k4[2][size_t(a) * N + na] = k4[2][size_t(na) * N + a] = 1.0;
+                k4[3][size_t(na) * N + nbb] = k4[3][size_t(nbb) * N + na] = 1.0;
+            }
+        const double ch = std::cosh(p.dtau * p.t), sh = std::sinh(p.dtau * p.t);
+        auto factor = [&](int g, double sgn) {
+            std::vector<double> e(size_t(N) * N, 0.0);
+            for (int i = 0; i < N; ++i) e[size_t(i) * N + i] = ch;
+            for (size_t i = 0; i < e.size(); ++i) e[i] += sgn * sh * k4[g][i];
+            return e;
+        };
+        std::vector<double> acc = factor(0, +1.0), tmp;
+        for (int g = 1; g < 4; ++g) { matmul(acc, factor(g, +1.0), tmp, N); acc.swap(tmp); }
+        P = acc;
+        acc = factor(3, -1.0);
+        for (int g = 2; g >= 0; --g) { matmul(acc, factor(g, -1.0), tmp, N); acc.swap(tmp); }
+        Pinv = acc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// device
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+// out[mat][i] = exp(sign * sigma(gc) * alpha * aux[rep][k][i]),  mat = off + blockIdx.y, rep = mat / 2
+__global__ void hub_scales_kernel(const int32_t* aux, long long strideAux, int N, int k, double alpha, double sign,
+                                  double* out, int off) {
+    const int mat = off + blockIdx.y;
+    const int rep = mat >> 1, gc = mat & 1;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const double sigma = gc == 0 ? 1.0 : -1.0;
+    const double s = double(aux[size_t(rep) * strideAux + size_t(k) * N + i]);
+    out[size_t(blockIdx.y) * N + i] = exp(sign * sigma * alpha * s);
+}
+
+__global__ void hub_real_part_kernel(const cplx* in, double* out, size_t n) {
+    const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i].x;
+}
+__global__ void hub_to_complex_kernel(const double* in, cplx* out, size_t n) {
+    const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = make_double2(in[i], 0.0);
+}
+
+// updateInSlice (dethubbard.cpp:141-171): N attempts at random sites, in the reference's draw order
+// (site = randInt(0, N-1); a further rand01() only if ratio <= 1).  One CTA per replica; the rank-1
+// update of both components (dethubbard.cpp:910-933) is applied immediately by the whole CTA.
+__global__ void __launch_bounds__(1024) hub_update_slice_kernel(cplx* Gall, long long strideG, int N, int32_t* auxAll,
+                                                                long long strideAux, int k, double alpha,
+                                                                const double* rngAll, long long strideRng, int rngWindow,
+                                                                int* cursorAll, uint32_t* acceptedAll,
+                                                                unsigned long long* acceptedTotal, int* errflag) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* colU = reinterpret_cast<double*>(smem_raw);     // [N] G_up[:, site]
+    double* rowU = colU + N;                                // [N] factor * (1 - G_up)[site, :]
+    double* colD = rowU + N;
+    double* rowD = colD + N;
+    __shared__ int sSite, sAcc, sAbort;
+    __shared__ double sFacU, sFacD;
+    const int b = blockIdx.x, tid = threadIdx.x;
+    cplx* Gu = Gall + size_t(2 * b) * strideG;
+    cplx* Gd = Gall + size_t(2 * b + 1) * strideG;
+    int32_t* aux = auxAll + size_t(b) * strideAux + size_t(k) * N;
+    const double* rng = rngAll + size_t(b) * strideRng;
+    int cursor = cursorAll[b];
+    unsigned accepted = 0;
+    if (tid == 0) sAbort = 0;
+    __syncthreads();
+    for (int attempt = 0; attempt < N; ++attempt) {
+        if (tid == 0) {
+            if (cursor + 2 > rngWindow) {
+                sAbort = 1;
+                sAcc = 0;
+            } else {
+                const int site = int(double(N) * rng[cursor]);          // randInt(0, N-1), rngwrapper.h:60-68
+                cursor += 1;
+                const double a = double(aux[site]);
+                const double dU = exp(-2.0 * alpha * a) - 1.0, dD = exp(+2.0 * alpha * a) - 1.0;
+                const double gu = Gu[size_t(site) * N + site].x, gd = Gd[size_t(site) * N + site].x;
+                const double ratio = (1.0 + dU * (1.0 - gu)) * (1.0 + dD * (1.0 - gd));
+                bool acc;
+                if (ratio > 1.0) {
+                    acc = true;
+                } else {
+                    acc = rng[cursor] < ratio;
+                    cursor += 1;
+                }
+                if (acc) {
+                    accepted += 1;
+                    aux[site] = -aux[site];
+                    sFacU = dU / (1.0 + dU * (1.0 - gu));
+                    sFacD = dD / (1.0 + dD * (1.0 - gd));
+                }
+                sSite = site;
+                sAcc = acc ? 1 : 0;
+            }
+        }
+        __syncthreads();
+        if (sAbort) break;
+        if (sAcc) {
+            const int site = sSite;
+            const double fU = sFacU, fD = sFacD;
+            for (int i = tid; i < N; i += blockDim.x) {
+                colU[i] = Gu[size_t(site) * N + i].x;
+                colD[i] = Gd[size_t(site) * N + i].x;
+                const double du = (i == site ? 1.0 : 0.0) - Gu[size_t(i) * N + site].x;
+                const double dd = (i == site ? 1.0 : 0.0) - Gd[size_t(i) * N + site].x;
+                rowU[i] = fU * du;
+                rowD[i] = fD * dd;
+            }
+            __syncthreads();
+            for (size_t idx = tid; idx < size_t(N) * N; idx += blockDim.x) {
+                const int i = int(idx % N), j = int(idx / N);
+                Gu[idx].x -= colU[i] * rowU[j];
+                Gd[idx].x -= colD[i] * rowD[j];
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        if (sAbort) atomicExch(errflag, 1);
+        cursorAll[b] = cursor;
+        acceptedAll[b] = accepted;
+        if (acceptedTotal) acceptedTotal[b] += accepted;
+    }
+}
+
+}  // namespace
+
+cudaError_t hub_scales_launch(const int32_t* aux, long long strideAux, int N, int k, double alpha, double sign,
+                              double* out, int off, int batch, cudaStream_t st) {
+    dim3 grid((N + 127) / 128, batch);
+    hub_scales_kernel<<<grid, 128, 0, st>>>(aux, strideAux, N, k, alpha, sign, out, off);
+    return cudaGetLastError();
+}
+
+cudaError_t hub_real_part_launch(const cplx* in, double* out, size_t n, cudaStream_t st) {
+    hub_real_part_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, out, n);
+    return cudaGetLastError();
+}
+cudaError_t hub_to_complex_launch(const double* in, cplx* out, size_t n, cudaStream_t st) {
+    hub_to_complex_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, out, n);
+    return cudaGetLastError();
+}
+
+cudaError_t hub_update_slice_launch(cplx* G, long long strideG, int N, int32_t* aux, long long strideAux, int k,
+                                    double alpha, const double* rng, long long strideRng, int rngWindow, int* cursor,
+                                    uint32_t* accepted, unsigned long long* acceptedTotal, int* errflag, int batch,
+                                    cudaStream_t st) {
+    const size_t smem = size_t(4) * N * sizeof(double);
+    const int threads = N >= 256 ? 1024 : 256;
+    hub_update_slice_kernel<<<batch, threads, smem, st>>>(G, strideG, N, aux, strideAux, k, alpha, rng, strideRng,
+                                                          rngWindow, cursor, accepted, acceptedTotal, errflag);
+    return cudaGetLastError();
+}
+
+}  // namespace dqmc

@@ -354,3 +354,56 @@ def test_reference_driver_with_gpu_shim(tmp_path):
     assert np.allclose(series, ref, rtol=0, atol=2e-6)               # the driver writes 6 significant digits
     info = open(os.path.join(str(tmp_path), "info.dat")).read()
     assert "libdqmc_b200" in info
+
+
+# ---------------------------------------------------------------- DetHubbard (BASELINE configs C1, C5)
+@pytest.mark.parametrize("name", ["hubbard_L4_U4_b4", "hubbard_L4_cb"])
+def test_hubbard_vs_golden(name):
+    from detqmc_b200 import DetHubbardBatch
+    from helpers import hubbard_params_of
+    g = load_golden(name)
+    p = hubbard_params_of(g)
+    b = DetHubbardBatch(p)
+    assert np.array_equal(b.auxfield()[1:], g["aux0"])                 # same dSFMT stream, same draw order
+    N = p.N
+    eye = np.eye(N)
+    for gc in (0, 1):
+        assert maxabs(b.bmat_mult(0, eye, 9, 4, gc=gc), g["bmat_%d_9_4" % gc]) < 1e-12      # B(9,4) I
+        assert maxabs(b.bmat_mult(1, eye, 9, 4, gc=gc), g["bmat_%d_9_4" % gc]) < 1e-12      # I B(9,4)
+        A = np.random.default_rng(gc).standard_normal((N, N))
+        assert relerr(b.bmat_mult(2, b.bmat_mult(0, A, 9, 4, gc=gc), 9, 4, gc=gc), A) < 1e-11   # B^-1 B A
+        assert relerr(b.bmat_mult(3, b.bmat_mult(1, A, 9, 4, gc=gc), 9, 4, gc=gc), A) < 1e-11   # A B B^-1
+        assert relerr(b.green(0, gc), g["green0_%d" % gc]) < TOL_G
+        assert abs(b.logdet(0, gc) - np.log(g["sv0_%d" % gc]).sum()) < 1e-9 * max(1.0, abs(b.logdet(0, gc)))
+    n = int(g["n_sweeps"])
+    for sw in range(n):
+        b.sweep()
+        key = "aux_after_%d" % (sw + 1)
+        if key in g.files:
+            assert np.array_equal(b.auxfield()[1:], g[key])
+            for gc in (0, 1):
+                assert relerr(b.green(0, gc), g["green_after_%d_%d" % (sw + 1, gc)]) < 1e-9
+    assert np.array_equal(b.rng_draw(8), g["rng_next"])                # the stream was consumed exactly as in the reference
+    if p.mu == 0.0 and not p.checkerboard:
+        assert abs(b.total_occupation() - 1.0) < 1e-10                 # half filling
+
+
+def test_hubbard_full_size_properties():
+    """BASELINE config C5 (L=20, U=8, beta=20, m=200, s=10) at full size: properties that need no oracle --
+    half-filling identity <n> = 1 for every auxiliary-field configuration, wrapped vs recomputed G at the
+    stabilisation points, G(0) after a sweep vs from scratch, batch == single replica."""
+    from detqmc_b200 import DetHubbardBatch
+    p = dict(L=20, m=200, s=10, dtau=0.1, U=8.0, mu=0.0, t=1.0)
+    b = DetHubbardBatch(p, n_replicas=2, rng_indices=[1, 2])
+    assert abs(b.total_occupation(0) - 1.0) < 1e-9 and abs(b.total_occupation(1) - 1.0) < 1e-9
+    b.sweep()                                                            # full down-sweep
+    # wrapping over s = 10 slices at U = 8 amplifies round-off by ~cond(B)^10 ~ 1e11: 1e-5 is the expected size
+    assert np.all(b.green_consistency() < 1e-3)
+    for rep in (0, 1):
+        assert abs(b.total_occupation(rep) - 1.0) < 1e-9
+        for gc in (0, 1):
+            assert relerr(b.green(rep, gc), b.green_for_timeslice(0, rep=rep, gc=gc)) < 1e-8
+    single = DetHubbardBatch(p, n_replicas=1, rng_indices=[2])
+    single.sweep()
+    assert np.array_equal(single.auxfield(0), b.auxfield(1))
+    assert relerr(single.green(0, 1), b.green(1, 1)) < 1e-12

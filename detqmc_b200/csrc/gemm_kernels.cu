@@ -15,6 +15,8 @@
 // Bound: FP64 tensor pipe.  Algorithmic flops: 8 * M * N * K per matrix.
 #include "dqmc_internal.h"
 
+#include <cstdlib>
+
 namespace dqmc {
 namespace {
 
@@ -203,7 +205,8 @@ __global__ void __launch_bounds__(32 * WM * WN) zgemm_dmma_kernel(GemmArgs g) {
 constexpr int KT = 32;
 
 template <int WM, int WN, int MB, int NB>
-__global__ void __launch_bounds__(32 * WM * WN) zgemm_rank_update_kernel(GemmArgs g) {
+__global__ void __launch_bounds__(32 * WM * WN, (WM * WN <= 4 ? 3 : (WM * WN <= 8 ? 2 : 1)))
+zgemm_rank_update_kernel(GemmArgs g) {
     constexpr int TM = 8 * MB * WM, TN = 8 * NB * WN, LDM = TM + 8, LDN = TN + 8, NT = 32 * WM * WN;
     extern __shared__ __align__(16) double smem[];
     double* As_re = smem;
@@ -343,6 +346,11 @@ cudaError_t launch_cfg(const GemmArgs& g, cudaStream_t st) {
 cudaError_t gemm_launch(const GemmArgs& g, cudaStream_t st) {
     if (g.batch <= 0 || g.M <= 0 || g.N <= 0) return cudaSuccess;
     if ((g.K <= KT || g.kvec) && !g.transa && !g.transb && g.beta == 1.0 && !g.rowscale && !g.colscale && !g.kscale) {
+        static const int cfg = std::getenv("DQMC_RANKUPD_CFG") ? std::atoi(std::getenv("DQMC_RANKUPD_CFG")) : 2;
+        if (g.M % 48 == 0 && g.N % 48 == 0 && cfg == 1) return launch_rank_update<2, 2, 3, 3>(g, st);   // 48 x 48
+        if (g.M % 96 == 0 && g.N % 48 == 0 && cfg == 2) return launch_rank_update<4, 2, 3, 3>(g, st);   // 96 x 48
+        if (g.M % 48 == 0 && g.N % 96 == 0 && cfg == 3) return launch_rank_update<2, 4, 3, 3>(g, st);   // 48 x 96
+        if (g.M % 96 == 0 && g.N % 96 == 0 && cfg == 4) return launch_rank_update<4, 4, 3, 3>(g, st);   // 96 x 96, 16 warps
         if (g.M % 96 == 0 && g.N % 96 == 0) return launch_rank_update<4, 3, 3, 4>(g, st);
         if ((g.M > 32 && g.N > 32) || g.kvec) return launch_rank_update<2, 2, 4, 4>(g, st);
     }

@@ -13,6 +13,7 @@
 #include "dqmc_internal.h"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace dqmc {
 namespace {
@@ -552,6 +553,229 @@ __global__ void __launch_bounds__(kPanelThreads) qr_panel_kernel(cplx* Aall, lon
     }
 }
 
+// 1/sqrt(x) and 1/x to (almost) full double precision from the SFU seeds + Newton-Raphson; used where the
+// latency of the correctly rounded FP64 sqrt / division would sit on a serial critical path
+__device__ __forceinline__ double fast_rsqrt(double x) {
+    // scale into the float range first (|x|^2 of a column can exceed it for the graded chain matrices)
+    int e;
+    const double mnt = frexp(x, &e);                     // x = mnt * 2^e, mnt in [0.5, 1)
+    const int eh = e >> 1;                               // x = (mnt * 2^(e - 2 eh)) * 4^eh
+    const double xs = ldexp(mnt, e - 2 * eh);
+    double y = double(rsqrtf(float(xs)));
+    y = y * (1.5 - 0.5 * xs * y * y);
+    y = y * (1.5 - 0.5 * xs * y * y);
+    y = y * (1.5 - 0.5 * xs * y * y);
+    return ldexp(y, -eh);
+}
+__device__ __forceinline__ double fast_rcp(double x) {
+    int e;
+    const double mnt = frexp(x, &e);
+    double y = double(__frcp_rn(float(mnt)));
+    y = y * (2.0 - mnt * y);
+    y = y * (2.0 - mnt * y);
+    y = y * (2.0 - mnt * y);
+    return ldexp(y, -e);
+}
+
+// Register-resident variant of the panel factorisation for m <= 32 * MAXT rows: warp w owns panel column
+// w in registers (lane l holds rows l, l+32, ...), the current reflector is broadcast through a
+// double-buffered shared-memory vector, so a column step is one barrier, one dot product and one update
+// per warp.  The warps whose columns are already factored (w < c) use the same dot product to build the
+// Gram matrix of the reflectors, and warp c-1 folds its column into the compact-WY factor T while the
+// others work, so T costs no extra pass.  ~3x fewer instructions per column than qr_panel_kernel, which
+// stays as the fallback for taller panels.
+__device__ int getenv_dbg_panel = 0;
+constexpr int kPanelRegThreads = 512;      // 16 warps, two panel columns per warp
+
+template <int MAXT>
+__global__ void __launch_bounds__(kPanelRegThreads) qr_panel_reg_kernel(cplx* Aall, long long strideA, int D, int j0,
+                                                                        int nbc, cplx* Vall, cplx* VTall, long long strideV) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int m = D - j0;
+    const int ldp = m | 1;
+    cplx* P = reinterpret_cast<cplx*>(smem_raw);                    // [nbc][ldp] panel (written after the factorisation)
+    cplx* Gm = P + size_t(nbc) * ldp;                               // [32][33] strict upper Gram of V
+    cplx* Tm = Gm + 32 * 33;                                        // [32][33] T factor
+    cplx* vbuf = Tm + 32 * 33;                                      // [2][m] current reflector
+    __shared__ cplx s_tau[kPanelMaxNb];
+
+    const int b = blockIdx.x;
+    cplx* A = Aall + size_t(b) * strideA;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;     // w in [0, 16): columns w and w + 16
+
+    cplx col[2][MAXT];
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int t = 0; t < MAXT; ++t) {
+            const int row = lane + 32 * t, cw = w + 16 * h;
+            col[h][t] = (cw < nbc && row < m) ? A[size_t(j0 + cw) * D + j0 + row] : make_double2(0, 0);
+        }
+    for (int i = tid; i < 32 * 33; i += blockDim.x) { Gm[i] = make_double2(0, 0); Tm[i] = make_double2(0, 0); }
+    __syncthreads();
+
+    long long tq[5] = {0, 0, 0, 0, 0};
+    long long tmark;
+    const bool dbg = getenv_dbg_panel != 0;
+#define PTICK(i) if (dbg) { long long n__; asm volatile("mov.u64 %0, %%clock64;" : "=l"(n__) :: "memory"); tq[i] += n__ - tmark; tmark = n__; }
+    if (dbg) asm volatile("mov.u64 %0, %%clock64;" : "=l"(tmark) :: "memory");
+    for (int c = 0; c < nbc; ++c) {
+        cplx* vb = vbuf + (c & 1) * m;
+        PTICK(4)
+        if (w == (c & 15)) {
+            // ---- reflector of the own column (zlarfg conventions); h selects which of the two columns
+            const int h = c >> 4;
+            double xn = 0;
+            cplx alpha = make_double2(0, 0);
+#pragma unroll
+            for (int t = 0; t < MAXT; ++t) {
+                const int row = lane + 32 * t;
+                const cplx a = h ? col[1][t] : col[0][t];
+                if (row > c && row < m) xn = fma(a.x, a.x, fma(a.y, a.y, xn));
+                if (row == c) alpha = a;
+            }
+            xn = warp_sum(xn);
+            alpha.x = __shfl_sync(0xffffffffu, alpha.x, c & 31);
+            alpha.y = __shfl_sync(0xffffffffu, alpha.y, c & 31);
+            cplx tau, sc;
+            double beta;
+            if (xn == 0.0 && alpha.y == 0.0) {
+                tau = make_double2(0, 0);
+                sc = make_double2(0, 0);
+                beta = alpha.x;
+            } else {
+                // this warp is the serial critical path of the column step: one rsqrt + one reciprocal
+                // instead of sqrt + divisions
+                const double x2 = alpha.x * alpha.x + alpha.y * alpha.y + xn;
+                const double inrm = rsqrt(x2);
+                const double nrm = x2 * inrm;
+                beta = alpha.x >= 0 ? -nrm : nrm;
+                const double ib = alpha.x >= 0 ? -inrm : inrm;                  // 1 / beta
+                tau = make_double2((beta - alpha.x) * ib, -alpha.y * ib);
+                const double dr = alpha.x - beta, di = alpha.y;
+                const double iden = __drcp_rn(dr * dr + di * di);
+                sc = make_double2(dr * iden, -di * iden);
+            }
+#pragma unroll
+            for (int t = 0; t < MAXT; ++t) {
+                const int row = lane + 32 * t;
+                if (row < m) {
+                    cplx a = h ? col[1][t] : col[0][t];
+                    if (row > c) {
+                        a = cmul(a, sc);
+                        vb[row] = a;
+                    } else if (row == c) {
+                        a = make_double2(beta, 0);                   // R diagonal
+                        vb[row] = make_double2(1, 0);
+                    }
+                    if (h) col[1][t] = a; else col[0][t] = a;
+                }
+            }
+            if (lane == 0) s_tau[c] = tau;
+            PTICK(0)
+        }
+        __syncthreads();
+        PTICK(1)
+        const cplx tau = s_tau[c];
+        if (tau.x != 0.0 || tau.y != 0.0) {
+            // dot_h = v_c^H x_h over rows >= c for both own columns (a_w for w > c, v_w for w < c)
+            double dr[2] = {0, 0}, di[2] = {0, 0};
+#pragma unroll
+            for (int t = 0; t < MAXT; ++t) {
+                const int row = lane + 32 * t;
+                const cplx v = (row >= c && row < m) ? vb[row] : make_double2(0, 0);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    dr[h] = fma(v.x, col[h][t].x, fma(v.y, col[h][t].y, dr[h]));
+                    di[h] = fma(v.x, col[h][t].y, fma(-v.y, col[h][t].x, di[h]));
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    dr[h] += __shfl_xor_sync(0xffffffffu, dr[h], o);
+                    di[h] += __shfl_xor_sync(0xffffffffu, di[h], o);
+                }
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int cw = w + 16 * h;
+                if (cw >= nbc || cw == c) continue;
+                if (cw > c) {
+                    // a -= conj(tau) (v^H a) v
+                    const cplx fw = cmul(make_double2(tau.x, -tau.y), make_double2(dr[h], di[h]));
+#pragma unroll
+                    for (int t = 0; t < MAXT; ++t) {
+                        const int row = lane + 32 * t;
+                        const cplx v = (row >= c && row < m) ? vb[row] : make_double2(0, 0);
+                        col[h][t].x -= fw.x * v.x - fw.y * v.y;
+                        col[h][t].y -= fw.x * v.y + fw.y * v.x;
+                    }
+                } else if (lane == 0) {
+                    Gm[cw * 33 + c] = make_double2(dr[h], -di[h]);   // v_cw^H v_c = conj(v_c^H v_cw)
+                }
+            }
+        }
+        PTICK(2)
+        // ---- compact-WY factor: column c-1 of T (its Gram column was completed in the previous step)
+        if (c > 0 && w == ((c - 1) & 15)) {
+            const int cc = c - 1;
+            const cplx tcc = s_tau[cc];
+            if (lane == cc) Tm[cc * 33 + cc] = tcc;
+            if (lane < cc) {
+                cplx sacc = make_double2(0, 0);
+                for (int l = lane; l < cc; ++l) sacc = cfma_(Tm[lane * 33 + l], Gm[l * 33 + cc], sacc);
+                Tm[lane * 33 + cc] = make_double2(-(tcc.x * sacc.x - tcc.y * sacc.y), -(tcc.x * sacc.y + tcc.y * sacc.x));
+            }
+            PTICK(3)
+        }
+    }
+    if (dbg && b == 0 && lane == 0 && (w < 3))
+        printf("panel dbg j0 %d warp %d: reflector %lld barrier %lld apply %lld tcol %lld other %lld\n", j0, w, tq[0], tq[1], tq[2],
+               tq[3], tq[4]);
+    __syncthreads();
+    if (w == ((nbc - 1) & 15)) {
+        const int cc = nbc - 1;
+        const cplx tcc = s_tau[cc];
+        if (lane == cc) Tm[cc * 33 + cc] = tcc;
+        if (lane < cc) {
+            cplx sacc = make_double2(0, 0);
+            for (int l = lane; l < cc; ++l) sacc = cfma_(Tm[lane * 33 + l], Gm[l * 33 + cc], sacc);
+            Tm[lane * 33 + cc] = make_double2(-(tcc.x * sacc.x - tcc.y * sacc.y), -(tcc.x * sacc.y + tcc.y * sacc.x));
+        }
+    }
+    // ---- panel to shared memory (R on / above the diagonal, v below)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int cw = w + 16 * h;
+        if (cw < nbc) {
+#pragma unroll
+            for (int t = 0; t < MAXT; ++t) {
+                const int row = lane + 32 * t;
+                if (row < m) P[cw * ldp + row] = col[h][t];
+            }
+        }
+    }
+    __syncthreads();
+    // ---- write back: R (and v below it) to A, explicit V and V*T to the workspace
+    cplx* V = Vall + size_t(b) * strideV;
+    cplx* VT = VTall + size_t(b) * strideV;
+    for (int idx = tid; idx < nbc * m; idx += blockDim.x) {
+        const int c = idx / m, r = idx - c * m;
+        const cplx pv = P[c * ldp + r];
+        A[size_t(j0 + c) * D + j0 + r] = pv;
+        V[size_t(j0 + c) * D + j0 + r] = r > c ? pv : make_double2(r == c ? 1.0 : 0.0, 0.0);
+        cplx sacc = make_double2(0, 0);
+        const int lmax = min(c, r);
+        for (int l = 0; l <= lmax; ++l) {
+            const cplx vl = (l == r) ? make_double2(1, 0) : P[l * ldp + r];
+            sacc = cfma_(vl, Tm[l * 33 + c], sacc);
+        }
+        VT[size_t(j0 + c) * D + j0 + r] = sacc;
+    }
+}
+
 // inverse of every nb x nb diagonal block of the upper-triangular R (stored in A): out [batch][P][nb*nb]
 __global__ void trtri_blocks_kernel(const cplx* Aall, long long strideA, int D, int nb, cplx* outAll, long long strideOut) {
     __shared__ cplx Rs[32 * 33], Xs[32 * 33];
@@ -660,10 +884,20 @@ cudaError_t qr_blocked_factor(QrWorkspace& ws, cplx* A, int D, long long strideA
     cplx* W = ws.W + size_t(off) * nb * D;
     const size_t smem = size_t(nb) * (D | 1) * sizeof(cplx) + 2 * 32 * 33 * sizeof(cplx);
     QR_TRY(cudaFuncSetAttribute(qr_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    QR_TRY(cudaFuncSetAttribute(qr_panel_reg_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)(smem + size_t(2) * D * sizeof(cplx))));
     for (int j0 = 0; j0 < D; j0 += nb) {
         const int nbc = std::min(nb, D - j0), m = D - j0, n2 = D - j0 - nbc;
         const size_t sm = size_t(nbc) * (m | 1) * sizeof(cplx) + 2 * 32 * 33 * sizeof(cplx);
-        qr_panel_kernel<<<batch, kPanelThreads, sm, st>>>(A, strideA, D, j0, nbc, V, VT, (long long)dd);
+        static const bool force_smem_panel = std::getenv("DQMC_QR_SMEM_PANEL") != nullptr;
+        static bool dbg_set = false;
+        if (!dbg_set) { const int v = std::getenv("DQMC_QR_DEBUG") ? 1 : 0; cudaMemcpyToSymbol(getenv_dbg_panel, &v, sizeof v); dbg_set = true; }
+        if (m <= 320 && nb == 32 && !force_smem_panel) {
+            qr_panel_reg_kernel<10><<<batch, kPanelRegThreads, sm + size_t(2) * m * sizeof(cplx), st>>>(A, strideA, D, j0, nbc, V,
+                                                                                                  VT, (long long)dd);
+        } else {
+            qr_panel_kernel<<<batch, kPanelThreads, sm, st>>>(A, strideA, D, j0, nbc, V, VT, (long long)dd);
+        }
         QR_TRY(cudaGetLastError());
         ws.launches += 1;
         if (n2 > 0) {

@@ -276,6 +276,8 @@ def run_b200(args):
     d2h = n_local * (4 + 840) + 4 + world * lad.payload_len * 8
 
     # ---------------------------------------------------------------- per-kernel-family device time
+    lanes_default = 2 if n_local >= 8 else 1
+    batch.set_lanes(1)                                      # per-kernel times are only meaningful without overlap
     batch.profile_enable(True)
     acc0 = batch.accepted_total().astype(np.float64).sum()
     prof_steps = 2
@@ -284,6 +286,7 @@ def run_b200(args):
     prof = batch.profile_get()
     acc_per_step = (batch.accepted_total().astype(np.float64).sum() - acc0) / prof_steps
     batch.profile_enable(False)
+    batch.set_lanes(lanes_default)
 
     if rank != 0:
         if world > 1:
@@ -310,21 +313,37 @@ def run_b200(args):
         entry = {"launches_per_step": cnt / prof_steps, "ms_per_step": ms / prof_steps, "avg_launch_ms": per,
                  "share_of_kernel_time": ms / total_kernel_ms}
         if name == "cb_mult":
-            by = 2.0 * D * D * 16 * R                       # one read + one write of every matrix per launch
+            # single-slice launches (the wraps): one read + one write of every matrix per launch
+            by = 2.0 * D * D * 16 * R
             entry.update(bound="hbm", achieved=by / (per * 1e-3) / 1e9, peak=hbm_peak, unit="GB/s")
+        elif name == "cb_chain":
+            # s-slice chains of the advance steps: 48 FP64 instructions (96 flop) per complex element and slice
+            fl = 96.0 * D * D * WORKLOAD["s"] * R
+            entry.update(bound="tensor", achieved=fl / (per * 1e-3) / 1e12, peak=fp64_peak, unit="TFLOP/s",
+                         note="FP64 vector pipe / shared-memory bound, not a tensor-core kernel")
         elif name == "gemm_dmma":
             fl = 8.0 * D ** 3 * R
             entry.update(bound="tensor", achieved=fl / (per * 1e-3) / 1e12, peak=fp64_peak, unit="TFLOP/s")
-        elif name in ("qrcp_factor", "qr_form_q"):
+        elif name == "qrcp_factor":
             fl = 16.0 / 3.0 * D ** 3 * R
+            entry.update(bound="tensor", achieved=fl / (per * 1e-3) / 1e12, peak=fp64_peak, unit="TFLOP/s")
+        elif name == "qr_form_q":
+            # explicit Q (16/3 D^3) in the chain steps, Q^H C (8 D^3) in the Green's functions: ~ (16/3 * 15 + 8 * 10.5) / 25.5
+            fl = (16.0 / 3.0 * 15.0 + 8.0 * 10.5) / 25.5 * D ** 3 * R
             entry.update(bound="tensor", achieved=fl / (per * 1e-3) / 1e12, peak=fp64_peak, unit="TFLOP/s")
         elif name == "trsm_upper":
             fl = 4.0 * D ** 3 * R
             entry.update(bound="tensor", achieved=fl / (per * 1e-3) / 1e12, peak=fp64_peak, unit="TFLOP/s")
         elif name == "update_slice":
-            # flush 8 D^2 MSF per accepted update + row/column gathers ~ 2 * 8 * MSF * D * (MSF*delay/2)
-            fl_step = acc_per_step * (8.0 * D * D * msf + 16.0 * msf * D * (msf * WORKLOAD["delaySteps"] / 2.0))
+            # propose/decide rounds: row/column gathers ~ 2 * 8 * MSF * D * K per accepted update, K ~ MSF*delay/2;
+            # a strictly sequential Metropolis chain: latency bound by construction
+            fl_step = acc_per_step * 16.0 * msf * D * (msf * WORKLOAD["delaySteps"] / 2.0)
             fl = fl_step / (cnt / prof_steps)
+            entry.update(bound="tensor", achieved=fl / (per * 1e-3) / 1e12, peak=fp64_peak, unit="TFLOP/s",
+                         note="sequential Metropolis chain: latency bound")
+        elif name == "update_flush":
+            # rank-K flush G += X Y: 8 D^2 MSF flop per accepted update (launches of finished rounds are empty)
+            fl = acc_per_step * 8.0 * D * D * msf / (cnt / prof_steps)
             entry.update(bound="tensor", achieved=fl / (per * 1e-3) / 1e12, peak=fp64_peak, unit="TFLOP/s")
         if "achieved" in entry:
             entry["frac"] = entry["achieved"] / entry["peak"]
@@ -358,7 +377,8 @@ def run_b200(args):
                        "ladder_sweeps_per_s": K / (ms_total * 1e-3),
                        "cache": "working set per step (G, UDT storage, fields of %d replicas: %.1f GB) exceeds "
                                 "the 126 MB L2; no flush needed" % (n_local, n_local * (2 * 11 + 8) * D * D * 16 / 1e9),
-                       "parallelism": "replicas partitioned contiguously, %d per GPU" % n_local},
+                       "parallelism": "replicas partitioned contiguously, %d per GPU, issued as %d lanes (CUDA streams) per GPU"
+                                      % (n_local, lanes_default)},
             "clocks": clocks, "gpu_launches": int(gpu_launches),
             "e2e": {"value": P * K / wall_e2e, "unit": "replica-sweeps/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "device_ms_per_step": f0.elapsed_time(f1) / K},

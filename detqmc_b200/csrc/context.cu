@@ -32,7 +32,7 @@ namespace {
             cudaEventRecord(e0__, ctx->stream);                                                    \
             cudaError_t el__ = (call);                                                             \
             cudaEventRecord(e1__, ctx->stream);                                                    \
-            ctx->profPending.push_back({prof_category(#call), e0__, e1__});                        \
+            ctx->profPending.push_back({ctx->profForce >= 0 ? ctx->profForce : prof_category(#call), e0__, e1__});                        \
             if (el__ != cudaSuccess) {                                                             \
                 ctx->err = std::string(#call) + ": " + cudaGetErrorString(el__);                   \
                 return DQMC_ERR_CUDA;                                                              \
@@ -50,7 +50,7 @@ namespace {
 
 // profiling categories (dqmc_profile_get): one per kernel family
 const char* const kProfNames[DQMC_PROF_NCAT] = {"cb_mult", "gemm_dmma", "qrcp_factor", "qr_form_q", "trsm_upper",
-                                                "update_slice", "other"};
+                                                "update_slice", "other", "cb_chain", "update_flush"};
 int prof_category(const char* call) {
     if (!std::strncmp(call, "cb_launch", 9)) return 0;
     if (!std::strncmp(call, "gemm_launch", 11)) return 1;
@@ -148,7 +148,9 @@ int sdw_bmult(dqmc_ctx* ctx, int op, cplx* A, long long strideA, int k2, int k1,
     a.colscale = colscale;
     a.strideScale = strideScale;
     a.batch = batch;
+    ctx->profForce = a.kcount > 1 ? 7 : -1;          // chains (advance) are accounted separately from the wraps
     CKL(cb_launch(ctx->geom, a, ctx->stream));
+    ctx->profForce = -1;
     return DQMC_OK;
 }
 
@@ -390,6 +392,10 @@ int set_storage_identity(dqmc_ctx* ctx, int l, int off, int batch) {
 
 inline int slice_of(const dqmc_ctx* ctx, int l) { return l < ctx->n ? ctx->s * l : ctx->m; }
 
+// current lane (sub-batch) of the sweep primitives: replicas [laneOff, laneOff + laneCnt) on ctx->stream
+inline int lane_mo(const dqmc_ctx* c) { return c->laneOff * c->ngc; }      // first matrix
+inline int lane_mc(const dqmc_ctx* c) { return c->laneCnt * c->ngc; }      // matrix count
+
 int setup_storage(dqmc_ctx* ctx, int off, int batch) {
     const int n = ctx->n;
     RET(set_storage_identity(ctx, 0, off, batch));
@@ -408,69 +414,79 @@ int setup_storage(dqmc_ctx* ctx, int off, int batch) {
 }
 
 int record_wrapped(dqmc_ctx* ctx) {
-    CK(cudaMemcpyAsync(ctx->Gwrapped, ctx->G, sizeof(cplx) * DD(ctx) * ctx->nmat, cudaMemcpyDeviceToDevice, ctx->stream));
+    const size_t o = size_t(lane_mo(ctx)) * DD(ctx);
+    CK(cudaMemcpyAsync(ctx->Gwrapped + o, ctx->G + o, sizeof(cplx) * DD(ctx) * lane_mc(ctx), cudaMemcpyDeviceToDevice,
+                       ctx->stream));
     return DQMC_OK;
 }
 int record_consistency(dqmc_ctx* ctx) {
-    CKL(launch_max_abs_diff(ctx->Gwrapped, ctx->G, ctx->D, (long long)DD(ctx), ctx->nmat, ctx->consistency, ctx->stream));
+    const size_t o = size_t(lane_mo(ctx)) * DD(ctx);
+    CKL(launch_max_abs_diff(ctx->Gwrapped + o, ctx->G + o, ctx->D, (long long)DD(ctx), lane_mc(ctx),
+                            ctx->consistency + lane_mo(ctx), ctx->stream));
     return DQMC_OK;
 }
 
-// advanceUpGreen(l), detmodel.h:1106-1163
+// advanceUpGreen(l), detmodel.h:1106-1163 (for the replicas of the current lane)
 int advance_up(dqmc_ctx* ctx, int l) {
-    const int R = ctx->nmat;
+    const int mo = lane_mo(ctx), R = lane_mc(ctx);
+    const size_t dd = DD(ctx);
     const int k_l = ctx->s * l, k_lp1 = slice_of(ctx, l + 1);
     if (ctx->currentTimeslice != k_lp1) { ctx->err = "advance_up: currentTimeslice mismatch"; return DQMC_ERR_STATE; }
     RET(record_wrapped(ctx));
-    UdtView in = storage_view(ctx, l, 0);
+    cplx* tQ = ctx->tQ + size_t(mo) * dd;
+    cplx* tT = ctx->tT + size_t(mo) * dd;
+    double* tD = ctx->tD + size_t(mo) * ctx->D;
+    cplx* G = ctx->G + size_t(mo) * dd;
+    UdtView in = storage_view(ctx, l, mo);
     // new right chain B(k_lp1, 0) into the temporary UDT
     // storage[0] is the identity UdV during an up-sweep (detmodel.h:1292-1295)
-    RET(chain_step(ctx, DQMC_OP_LEFT, l == 0 ? nullptr : &in, k_lp1, k_l, ctx->tQ, (long long)DD(ctx), ctx->tD, ctx->D, ctx->tT,
-                   (long long)DD(ctx), 0, R));
-    UdtView rnew{ctx->tQ, (long long)DD(ctx), ctx->tD, ctx->D, ctx->tT, (long long)DD(ctx)};
+    RET(chain_step(ctx, DQMC_OP_LEFT, l == 0 ? nullptr : &in, k_lp1, k_l, tQ, (long long)dd, tD, ctx->D, tT, (long long)dd, mo, R));
+    UdtView rnew{tQ, (long long)dd, tD, ctx->D, tT, (long long)dd};
     if (k_lp1 != ctx->m) {
-        UdtView left = storage_view(ctx, l + 1, 0);          // B(beta, k_lp1) from the last down-sweep
-        RET(green_from_udts(ctx, rnew, left, ctx->G, (long long)DD(ctx), ctx->logdet, 0, R));
+        UdtView left = storage_view(ctx, l + 1, mo);         // B(beta, k_lp1) from the last down-sweep
+        RET(green_from_udts(ctx, rnew, left, G, (long long)dd, ctx->logdet + mo, mo, R));
     } else {
         UdtView left = identity_view(ctx);
-        RET(green_from_udts(ctx, rnew, left, ctx->G, (long long)DD(ctx), ctx->logdet, 0, R));
+        RET(green_from_udts(ctx, rnew, left, G, (long long)dd, ctx->logdet + mo, mo, R));
     }
-    const size_t dd = DD(ctx);
-    CK(cudaMemcpy2DAsync(stQ(ctx, l + 1), size_t(st_stride(ctx)) * sizeof(cplx), ctx->tQ, dd * sizeof(cplx),
-                         dd * sizeof(cplx), R, cudaMemcpyDeviceToDevice, ctx->stream));
-    CK(cudaMemcpy2DAsync(stT(ctx, l + 1), size_t(st_stride(ctx)) * sizeof(cplx), ctx->tT, dd * sizeof(cplx),
-                         dd * sizeof(cplx), R, cudaMemcpyDeviceToDevice, ctx->stream));
-    CK(cudaMemcpy2DAsync(stD(ctx, l + 1), size_t(std_stride(ctx)) * sizeof(double), ctx->tD, ctx->D * sizeof(double),
-                         ctx->D * sizeof(double), R, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaMemcpy2DAsync(stQ(ctx, l + 1) + size_t(mo) * st_stride(ctx), size_t(st_stride(ctx)) * sizeof(cplx), tQ,
+                         dd * sizeof(cplx), dd * sizeof(cplx), R, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaMemcpy2DAsync(stT(ctx, l + 1) + size_t(mo) * st_stride(ctx), size_t(st_stride(ctx)) * sizeof(cplx), tT,
+                         dd * sizeof(cplx), dd * sizeof(cplx), R, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaMemcpy2DAsync(stD(ctx, l + 1) + size_t(mo) * std_stride(ctx), size_t(std_stride(ctx)) * sizeof(double), tD,
+                         ctx->D * sizeof(double), ctx->D * sizeof(double), R, cudaMemcpyDeviceToDevice, ctx->stream));
     RET(record_consistency(ctx));
     ctx->currentTimeslice = k_lp1;
     return DQMC_OK;
 }
 
-// advanceDownGreen(l), detmodel.h:953-1017
+// advanceDownGreen(l), detmodel.h:953-1017 (for the replicas of the current lane)
 int advance_down(dqmc_ctx* ctx, int l) {
-    const int R = ctx->nmat;
+    const int mo = lane_mo(ctx), R = lane_mc(ctx);
+    const size_t dd = DD(ctx);
     const int n = ctx->n;
     const int k_l = slice_of(ctx, l), k_lm1 = ctx->s * (l - 1);
     RET(record_wrapped(ctx));
-    UdtView in = storage_view(ctx, l, 0);
-    RET(chain_step(ctx, DQMC_OP_LEFT_ADJ, l < n ? &in : nullptr, k_l, k_lm1, ctx->tQ, (long long)DD(ctx), ctx->tD,
-                   ctx->D, ctx->tT, (long long)DD(ctx), 0, R));
-    UdtView lnew{ctx->tQ, (long long)DD(ctx), ctx->tD, ctx->D, ctx->tT, (long long)DD(ctx)};
+    cplx* tQ = ctx->tQ + size_t(mo) * dd;
+    cplx* tT = ctx->tT + size_t(mo) * dd;
+    double* tD = ctx->tD + size_t(mo) * ctx->D;
+    cplx* G = ctx->G + size_t(mo) * dd;
+    UdtView in = storage_view(ctx, l, mo);
+    RET(chain_step(ctx, DQMC_OP_LEFT_ADJ, l < n ? &in : nullptr, k_l, k_lm1, tQ, (long long)dd, tD, ctx->D, tT, (long long)dd, mo, R));
+    UdtView lnew{tQ, (long long)dd, tD, ctx->D, tT, (long long)dd};
     if (l - 1 > 0) {
-        UdtView right = storage_view(ctx, l - 1, 0);         // B(k_lm1, 0) from the last up-sweep
-        RET(green_from_udts(ctx, right, lnew, ctx->G, (long long)DD(ctx), ctx->logdet, 0, R));
+        UdtView right = storage_view(ctx, l - 1, mo);        // B(k_lm1, 0) from the last up-sweep
+        RET(green_from_udts(ctx, right, lnew, G, (long long)dd, ctx->logdet + mo, mo, R));
     } else {
         UdtView right = identity_view(ctx);
-        RET(green_from_udts(ctx, right, lnew, ctx->G, (long long)DD(ctx), ctx->logdet, 0, R));
+        RET(green_from_udts(ctx, right, lnew, G, (long long)dd, ctx->logdet + mo, mo, R));
     }
-    const size_t dd = DD(ctx);
-    CK(cudaMemcpy2DAsync(stQ(ctx, l - 1), size_t(st_stride(ctx)) * sizeof(cplx), ctx->tQ, dd * sizeof(cplx),
-                         dd * sizeof(cplx), R, cudaMemcpyDeviceToDevice, ctx->stream));
-    CK(cudaMemcpy2DAsync(stT(ctx, l - 1), size_t(st_stride(ctx)) * sizeof(cplx), ctx->tT, dd * sizeof(cplx),
-                         dd * sizeof(cplx), R, cudaMemcpyDeviceToDevice, ctx->stream));
-    CK(cudaMemcpy2DAsync(stD(ctx, l - 1), size_t(std_stride(ctx)) * sizeof(double), ctx->tD, ctx->D * sizeof(double),
-                         ctx->D * sizeof(double), R, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaMemcpy2DAsync(stQ(ctx, l - 1) + size_t(mo) * st_stride(ctx), size_t(st_stride(ctx)) * sizeof(cplx), tQ,
+                         dd * sizeof(cplx), dd * sizeof(cplx), R, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaMemcpy2DAsync(stT(ctx, l - 1) + size_t(mo) * st_stride(ctx), size_t(st_stride(ctx)) * sizeof(cplx), tT,
+                         dd * sizeof(cplx), dd * sizeof(cplx), R, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaMemcpy2DAsync(stD(ctx, l - 1) + size_t(mo) * std_stride(ctx), size_t(std_stride(ctx)) * sizeof(double), tD,
+                         ctx->D * sizeof(double), ctx->D * sizeof(double), R, cudaMemcpyDeviceToDevice, ctx->stream));
     RET(record_consistency(ctx));
     ctx->currentTimeslice = k_lm1;
     return DQMC_OK;
@@ -478,16 +494,18 @@ int advance_down(dqmc_ctx* ctx, int l) {
 
 int wrap_up(dqmc_ctx* ctx, int k) {
     if (ctx->currentTimeslice != k) { ctx->err = "wrap_up: currentTimeslice mismatch"; return DQMC_ERR_STATE; }
-    RET(sdw_bmult(ctx, DQMC_OP_RIGHT_INV, ctx->G, (long long)DD(ctx), k + 1, k, nullptr, 0, 0, ctx->nmat));
-    RET(sdw_bmult(ctx, DQMC_OP_LEFT, ctx->G, (long long)DD(ctx), k + 1, k, nullptr, 0, 0, ctx->nmat));
+    cplx* G = ctx->G + size_t(lane_mo(ctx)) * DD(ctx);
+    RET(sdw_bmult(ctx, DQMC_OP_RIGHT_INV, G, (long long)DD(ctx), k + 1, k, nullptr, 0, lane_mo(ctx), lane_mc(ctx)));
+    RET(sdw_bmult(ctx, DQMC_OP_LEFT, G, (long long)DD(ctx), k + 1, k, nullptr, 0, lane_mo(ctx), lane_mc(ctx)));
     ctx->currentTimeslice = k + 1;
     return DQMC_OK;
 }
 
 int wrap_down(dqmc_ctx* ctx, int k) {
     if (ctx->currentTimeslice != k) { ctx->err = "wrap_down: currentTimeslice mismatch"; return DQMC_ERR_STATE; }
-    RET(sdw_bmult(ctx, DQMC_OP_RIGHT, ctx->G, (long long)DD(ctx), k, k - 1, nullptr, 0, 0, ctx->nmat));
-    RET(sdw_bmult(ctx, DQMC_OP_LEFT_INV, ctx->G, (long long)DD(ctx), k, k - 1, nullptr, 0, 0, ctx->nmat));
+    cplx* G = ctx->G + size_t(lane_mo(ctx)) * DD(ctx);
+    RET(sdw_bmult(ctx, DQMC_OP_RIGHT, G, (long long)DD(ctx), k, k - 1, nullptr, 0, lane_mo(ctx), lane_mc(ctx)));
+    RET(sdw_bmult(ctx, DQMC_OP_LEFT_INV, G, (long long)DD(ctx), k, k - 1, nullptr, 0, lane_mo(ctx), lane_mc(ctx)));
     ctx->currentTimeslice = k - 1;
     return DQMC_OK;
 }
@@ -527,30 +545,36 @@ int finish_rng_window(dqmc_ctx* ctx) {
 }
 
 int launch_update(dqmc_ctx* ctx, int k, int therm) {
+    const int ro = ctx->laneOff, rc = ctx->laneCnt;           // replicas of the current lane
+    const size_t dd = DD(ctx);
     if (ctx->p.model == DQMC_MODEL_HUBBARD) {
-        CKL(hub_update_slice_launch(ctx->G, (long long)DD(ctx), ctx->N, ctx->aux, (long long)tab_stride(ctx), k,
-                                    ctx->hubAlpha, ctx->rngbuf, (long long)ctx->rngStride, ctx->rngWindow, ctx->cursor,
-                                    ctx->accepted, ctx->acceptedTotal, ctx->errflag, ctx->R, ctx->stream));
+        CKL(hub_update_slice_launch(ctx->G + size_t(2 * ro) * dd, (long long)dd, ctx->N, ctx->aux + size_t(ro) * tab_stride(ctx),
+                                    (long long)tab_stride(ctx), k, ctx->hubAlpha, ctx->rngbuf + size_t(ro) * ctx->rngStride,
+                                    (long long)ctx->rngStride, ctx->rngWindow, ctx->cursor + ro, ctx->accepted + ro,
+                                    ctx->acceptedTotal + ro, ctx->errflag, rc, ctx->stream));
         return DQMC_OK;
     }
     UpdateArgs a;
-    a.G = ctx->G; a.strideG = (long long)DD(ctx);
-    a.phi = ctx->phi; a.coshT = ctx->coshT; a.sinhT = ctx->sinhT;
+    a.G = ctx->G + size_t(ro) * dd; a.strideG = (long long)dd;
+    a.phi = ctx->phi + size_t(ro) * phi_stride(ctx);
+    a.coshT = ctx->coshT + size_t(ro) * tab_stride(ctx);
+    a.sinhT = ctx->sinhT + size_t(ro) * tab_stride(ctx);
     a.stridePhi = (long long)phi_stride(ctx); a.strideTab = (long long)tab_stride(ctx);
-    a.rvals = ctx->rvals;
-    a.X = ctx->X; a.Y = ctx->Y; a.strideXY = (long long)ctx->D * ctx->kmax;
-    a.rng = ctx->rngbuf; a.strideRng = (long long)ctx->rngStride; a.rngWindow = ctx->rngWindow;
-    a.acceptedTotal = ctx->acceptedTotal;
-    a.cursor = ctx->cursor;
-    a.ctrl = ctx->ctrl;
-    a.accepted = ctx->accepted;
+    a.rvals = ctx->rvals + ro;
+    a.strideXY = (long long)ctx->D * ctx->kmax;
+    a.X = ctx->X + size_t(ro) * a.strideXY; a.Y = ctx->Y + size_t(ro) * a.strideXY;
+    a.rng = ctx->rngbuf + size_t(ro) * ctx->rngStride; a.strideRng = (long long)ctx->rngStride; a.rngWindow = ctx->rngWindow;
+    a.acceptedTotal = ctx->acceptedTotal + ro;
+    a.cursor = ctx->cursor + ro;
+    a.ctrl = ctx->ctrl + ro;
+    a.accepted = ctx->accepted + ro;
     a.errflag = ctx->errflag;
     a.k = k;
     a.thermalization = therm;
-    a.batch = ctx->R;
-    a.site_state = ctx->siteState;
+    a.batch = rc;
+    a.site_state = ctx->siteState + ro;
     a.debug = std::getenv("DQMC_UPD_DEBUG") ? std::atoi(std::getenv("DQMC_UPD_DEBUG")) : 0;
-    a.kvec = ctx->kvec;
+    a.kvec = ctx->kvec + ro;
     // small delay blocks (Woodbury = 1) are flushed inside the kernel; otherwise every round is
     // followed by the rank-K update G += X Y on all SMs
     a.inline_flush = ctx->p.delaySteps < 8 ? 1 : 0;
@@ -562,14 +586,16 @@ int launch_update(dqmc_ctx* ctx, int k, int therm) {
             GemmArgs g;
             g.M = g.N = ctx->D; g.K = ctx->kmax;
             g.transa = g.transb = 0;
-            g.A = ctx->X; g.lda = ctx->D; g.strideA = a.strideXY;
-            g.B = ctx->Y; g.ldb = ctx->D; g.strideB = a.strideXY; g.b_kmajor = 1;
-            g.C = ctx->G; g.ldc = ctx->D; g.strideC = (long long)DD(ctx);
+            g.A = a.X; g.lda = ctx->D; g.strideA = a.strideXY;
+            g.B = a.Y; g.ldb = ctx->D; g.strideB = a.strideXY; g.b_kmajor = 1;
+            g.C = a.G; g.ldc = ctx->D; g.strideC = (long long)dd;
             g.rowscale = g.colscale = g.kscale = nullptr;
             g.strideRow = g.strideCol = g.strideK = 0;
-            g.alpha = 1.0; g.beta = 1.0; g.kvec = ctx->kvec;
-            g.batch = ctx->R;
+            g.alpha = 1.0; g.beta = 1.0; g.kvec = a.kvec;
+            g.batch = rc;
+            ctx->profForce = 8;
             CKL(update_flush_gemm(g, ctx->stream));
+            ctx->profForce = -1;
         }
     }
     return DQMC_OK;
@@ -677,39 +703,79 @@ int global_shift_move(dqmc_ctx* ctx, int32_t* accepted_out) {
     return DQMC_OK;
 }
 
+// Run one sweep primitive for every lane (sub-batch) on the lane's own stream.  The lanes are independent
+// groups of replicas; issuing them on separate streams lets the latency-bound kernels of one lane (the
+// sequential update rounds, the QR panels: one CTA per replica) overlap with the throughput-bound kernels
+// of the other (rank-K flushes, GEMMs, checkerboard multiplies) instead of leaving most SMs idle.
+template <class F>
+int for_each_lane(dqmc_ctx* ctx, F fn) {
+    const int ts = ctx->currentTimeslice;
+    cudaStream_t main = ctx->stream;
+    int rc = DQMC_OK, ts_after = ts;
+    for (int ln = 0; ln < ctx->nlanes && rc == DQMC_OK; ++ln) {
+        ctx->laneOff = ctx->laneStart[ln];
+        ctx->laneCnt = ctx->laneStart[ln + 1] - ctx->laneStart[ln];
+        ctx->stream = ln == 0 ? main : ctx->laneStream[ln];
+        ctx->currentTimeslice = ts;
+        rc = fn();
+        ts_after = ctx->currentTimeslice;
+    }
+    ctx->stream = main;
+    ctx->laneOff = 0;
+    ctx->laneCnt = ctx->R;
+    ctx->currentTimeslice = ts_after;
+    return rc;
+}
+
+// fork: the extra lane streams wait for everything issued on the main stream so far; join: the reverse
+int lanes_fork(dqmc_ctx* ctx) {
+    for (int ln = 1; ln < ctx->nlanes; ++ln) {
+        CK(cudaEventRecord(ctx->laneEvent[0], ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->laneStream[ln], ctx->laneEvent[0], 0));
+    }
+    return DQMC_OK;
+}
+int lanes_join(dqmc_ctx* ctx) {
+    for (int ln = 1; ln < ctx->nlanes; ++ln) {
+        CK(cudaEventRecord(ctx->laneEvent[ln], ctx->laneStream[ln]));
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->laneEvent[ln], 0));
+    }
+    return DQMC_OK;
+}
+
 // sweepDown / sweepUp, detmodel.h:1261-1399
 int sweep_down(dqmc_ctx* ctx, int therm) {
     const int n = ctx->n, s = ctx->s, m = ctx->m;
+    RET(lanes_fork(ctx));
     for (int k = m; k >= (n - 1) * s + 1; --k) {
-        RET(launch_update(ctx, k, therm));
-        RET(wrap_down(ctx, k));
+        RET(for_each_lane(ctx, [&] { RET(launch_update(ctx, k, therm)); return wrap_down(ctx, k); }));
     }
     for (int l = n - 1; l >= 1; --l) {
-        RET(advance_down(ctx, l + 1));
+        RET(for_each_lane(ctx, [&] { return advance_down(ctx, l + 1); }));
         for (int k = l * s; k >= (l - 1) * s + 1; --k) {
-            RET(launch_update(ctx, k, therm));
-            RET(wrap_down(ctx, k));
+            RET(for_each_lane(ctx, [&] { RET(launch_update(ctx, k, therm)); return wrap_down(ctx, k); }));
         }
     }
-    RET(advance_down(ctx, 1));
+    RET(for_each_lane(ctx, [&] { return advance_down(ctx, 1); }));
+    RET(lanes_join(ctx));
     return DQMC_OK;
 }
 
 int sweep_up(dqmc_ctx* ctx, int therm) {
     const int n = ctx->n, s = ctx->s, m = ctx->m;
     RET(set_storage_identity(ctx, 0, 0, ctx->nmat));
+    RET(lanes_fork(ctx));
     for (int l = 0; l <= n - 2; ++l) {
         for (int k = l * s + 1; k <= (l + 1) * s; ++k) {
-            RET(wrap_up(ctx, k - 1));
-            RET(launch_update(ctx, k, therm));
+            RET(for_each_lane(ctx, [&] { RET(wrap_up(ctx, k - 1)); return launch_update(ctx, k, therm); }));
         }
-        RET(advance_up(ctx, l));
+        RET(for_each_lane(ctx, [&] { return advance_up(ctx, l); }));
     }
     for (int k = (n - 1) * s + 1; k <= m; ++k) {
-        RET(wrap_up(ctx, k - 1));
-        RET(launch_update(ctx, k, therm));
+        RET(for_each_lane(ctx, [&] { RET(wrap_up(ctx, k - 1)); return launch_update(ctx, k, therm); }));
     }
-    RET(advance_up(ctx, n - 1));
+    RET(for_each_lane(ctx, [&] { return advance_up(ctx, n - 1); }));
+    RET(lanes_join(ctx));
     return DQMC_OK;
 }
 
@@ -825,6 +891,17 @@ int dqmc_create(const dqmc_params* params, int n_replicas, int device, dqmc_ctx*
     ctx->rngResident = false;
     ctx->rngResidentUsedBound = 0;
     ctx->profiling = false;
+    ctx->profForce = -1;
+    ctx->laneOff = 0;
+    ctx->laneCnt = ctx->R;
+    ctx->nlanes = 1;
+    ctx->laneStart[0] = 0; ctx->laneStart[1] = ctx->R; ctx->laneStart[2] = ctx->R;
+    for (int i = 0; i < 2; ++i) { ctx->laneStream[i] = nullptr; CK(cudaEventCreateWithFlags(&ctx->laneEvent[i], cudaEventDisableTiming)); }
+    CK(cudaStreamCreateWithFlags(&ctx->laneStream[1], cudaStreamNonBlocking));
+    if (ctx->R >= 8 && !std::getenv("DQMC_SINGLE_LANE")) {
+        ctx->nlanes = 2;
+        ctx->laneStart[1] = ctx->R / 2;
+    }
     CK(dmalloc(&ctx->rngbuf, ctx->rngCap * R));
     CK(dmalloc(&ctx->acceptedTotal, R));
     CK(cudaMemsetAsync(ctx->acceptedTotal, 0, sizeof(unsigned long long) * R, ctx->stream));
@@ -913,6 +990,8 @@ void dqmc_destroy(dqmc_ctx* ctx) {
     for (void* p : host) if (p) cudaFreeHost(p);
     prof_collect(ctx);
     for (cudaEvent_t e : ctx->profPool) cudaEventDestroy(e);
+    if (ctx->laneStream[1]) { cudaStreamSynchronize(ctx->laneStream[1]); cudaStreamDestroy(ctx->laneStream[1]); }
+    for (int i = 0; i < 2; ++i) if (ctx->laneEvent[i]) cudaEventDestroy(ctx->laneEvent[i]);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -949,6 +1028,12 @@ int dqmc_set_option(dqmc_ctx* ctx, int option, int value) {
     if (!ctx) return DQMC_ERR_PARAM;
     if (option == DQMC_OPT_STABILIZER && (value == DQMC_STAB_PREPIVOT_BLOCKED || value == DQMC_STAB_FULL_PIVOT)) {
         ctx->stabilizer = value;
+        return DQMC_OK;
+    }
+    if (option == DQMC_OPT_LANES && (value == 1 || value == 2)) {
+        if (value == 2 && ctx->R < 2) { ctx->err = "two lanes need at least two replicas"; return DQMC_ERR_PARAM; }
+        ctx->nlanes = value;
+        ctx->laneStart[1] = value == 2 ? ctx->R / 2 : ctx->R;
         return DQMC_OK;
     }
     ctx->err = "dqmc_set_option: unknown option or value";

@@ -254,7 +254,11 @@ struct dqmc_ctx {
     bool rngResident;      // window pre-loaded for several sweeps (dqmc_rng_preload)
     size_t rngResidentUsedBound;
     unsigned long long* acceptedTotal;
+    // lanes: the replicas are split into up to two groups whose sweeps are issued on separate streams
+    int nlanes; int laneStart[3]; int laneOff, laneCnt;
+    cudaStream_t laneStream[2]; cudaEvent_t laneEvent[2];
     bool profiling;
+    int profForce;         // >= 0: category of the next timed launch (overrides the name-based one)
     struct ProfRec { int cat; cudaEvent_t e0, e1; };
     std::vector<ProfRec> profPending;
     std::vector<cudaEvent_t> profPool;

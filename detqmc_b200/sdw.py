@@ -115,6 +115,10 @@ class DetSDWBatch:
         """False (default): blocked QR with column pre-pivoting; True: fully pivoted one-CTA QR."""
         self._ck(self.lib.dqmc_set_option(self.h, 0, 1 if full_pivot else 0))
 
+    def set_lanes(self, n):
+        """1 or 2 independent lanes (CUDA streams) per context; results do not depend on it."""
+        self._ck(self.lib.dqmc_set_option(self.h, 1, int(n)))
+
     def synchronize(self):
         self._ck(self.lib.dqmc_synchronize(self.h))
 
@@ -291,10 +295,11 @@ class DetSDWBatch:
         self._ck(self.lib.dqmc_profile_enable(self.h, int(on)))
 
     def profile_get(self):
-        ms = np.zeros(7)
-        cnt = np.zeros(7, dtype=np.uint64)
+        ncat = 9                                      # DQMC_PROF_NCAT
+        ms = np.zeros(ncat)
+        cnt = np.zeros(ncat, dtype=np.uint64)
         self._ck(self.lib.dqmc_profile_get(self.h, _ptr(ms), _ptr(cnt)))
-        names = [self.lib.dqmc_profile_name(i).decode() for i in range(7)]
+        names = [self.lib.dqmc_profile_name(i).decode() for i in range(ncat)]
         return {n: (float(m), int(c)) for n, m, c in zip(names, ms, cnt)}
 
     def accepted_total(self):

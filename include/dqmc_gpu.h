@@ -103,8 +103,11 @@ int dqmc_dims(const dqmc_ctx* ctx, int32_t* out);
  *   DQMC_STAB_PREPIVOT_BLOCKED (default)  columns ordered once by decreasing norm, then blocked
  *                                         Householder QR with tensor-core trailing updates;
  *   DQMC_STAB_FULL_PIVOT                  Householder QR with full column pivoting, one CTA per matrix
- *                                         (slow; kept as the cross-check of the tests). */
-enum { DQMC_OPT_STABILIZER = 0 };
+ *                                         (slow; kept as the cross-check of the tests).
+ * DQMC_OPT_LANES (1 or 2; default 2 for >= 8 replicas): the replicas of a context are split into lanes whose
+ * sweeps are issued on separate CUDA streams, so that the latency-bound kernels of one lane (sequential update
+ * rounds, QR panels) overlap with the throughput-bound kernels of the other.  Results do not depend on it. */
+enum { DQMC_OPT_STABILIZER = 0, DQMC_OPT_LANES = 1 };
 enum { DQMC_STAB_PREPIVOT_BLOCKED = 0, DQMC_STAB_FULL_PIVOT = 1 };
 int dqmc_set_option(dqmc_ctx* ctx, int option, int value);
 /* Number of kernels launched by this context so far (for bench.py's gpu_launches). */
@@ -221,7 +224,7 @@ int dqmc_rng_preload(dqmc_ctx* ctx, int n_sweeps);
 int dqmc_rng_release(dqmc_ctx* ctx);
 
 /* ---- measurement hooks (no reference twin; the reference's -DTIMING timers, timing.h:32-78) ---- */
-#define DQMC_PROF_NCAT 7
+#define DQMC_PROF_NCAT 9
 /* Bracket every kernel launch with CUDA events on the context's stream and accumulate device
  * time per kernel family. */
 int dqmc_profile_enable(dqmc_ctx* ctx, int on);

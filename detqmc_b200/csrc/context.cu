@@ -106,6 +106,8 @@ struct UdtView {
 };
 
 struct OpSpec { int rows, k_then_v, sign_idx, transposed, ascending; };
+constexpr int kStreamSweeps = 8;      // capacity of the streamed random-number buffer, in sweeps
+
 const OpSpec kOps[5] = {
     {0, 1, 0, 0, 1},   // LEFT       B A
     {1, 0, 0, 1, 0},   // RIGHT      A B
@@ -116,6 +118,7 @@ const OpSpec kOps[5] = {
 
 // ---- batched building blocks; `off` selects the first replica, `batch` how many ---------------
 
+int host_sync_rng(dqmc_ctx* ctx);
 int gemm(dqmc_ctx* ctx, int ta, int tb, const cplx* A, long long sA, const cplx* B, long long sB, cplx* C,
          long long sC, const double* rows, long long sRow, const double* cols, long long sCol,
          const double* ks, long long sK, double beta, int batch);
@@ -544,6 +547,72 @@ int finish_rng_window(dqmc_ctx* ctx) {
     return DQMC_OK;
 }
 
+// ---- streamed random numbers (the default of dqmc_sweep) -------------------------------------------
+// The device keeps a linear buffer of kStreamSweeps sweeps' worth of every replica's stream; the cursors
+// stay on the device from sweep to sweep.  While a sweep runs, the host generates the next chunk, stages it
+// in pinned memory and copies it on a separate stream, so that the per-sweep host->device transfer and the
+// dSFMT generation overlap with the kernels instead of preceding them.  The host streams are reconciled
+// (cursors read back, FIFOs advanced) when the buffer is exhausted or the host itself needs to draw.
+int stream_chunk_upload(dqmc_ctx* ctx, size_t first, size_t count, cudaStream_t st, int half) {
+    double* stage = ctx->h_rng + size_t(half) * ctx->rngCap * ctx->R;
+    for (int r = 0; r < ctx->R; ++r) {
+        const double* src = ctx->rng[r].peek(first + count) + first;
+        std::memcpy(stage + size_t(r) * count, src, count * sizeof(double));
+    }
+    CK(cudaMemcpy2DAsync(ctx->rngbuf + first, ctx->rngStride * sizeof(double), stage, count * sizeof(double),
+                         count * sizeof(double), ctx->R, cudaMemcpyHostToDevice, st));
+    return DQMC_OK;
+}
+
+int host_sync_rng(dqmc_ctx* ctx) {
+    if (!(ctx->rngAuto && ctx->rngResident)) return DQMC_OK;
+    CK(cudaStreamSynchronize(ctx->copyStream));
+    RET(finish_rng_window(ctx));
+    ctx->rngResident = false;
+    ctx->rngAuto = false;
+    ctx->rngStride = ctx->rngCap;
+    return DQMC_OK;
+}
+
+int stream_begin_sweep(dqmc_ctx* ctx) {
+    if (ctx->rngResident && ctx->rngResidentUsedBound + ctx->rngCap > ctx->rngStride) RET(host_sync_rng(ctx));   // buffer exhausted
+    if (!ctx->rngResident) {
+        ctx->rngStride = ctx->rngAlloc < ctx->rngCap * kStreamSweeps ? ctx->rngCap : ctx->rngCap * kStreamSweeps;
+        ctx->rngResident = true;
+        ctx->rngAuto = true;
+        ctx->rngWindow = (int)ctx->rngStride;              // constant bound: the graphs are keyed on it
+        ctx->rngResidentUsedBound = 0;
+        ctx->rngUploaded = 0;
+        CK(cudaMemsetAsync(ctx->cursor, 0, sizeof(int) * ctx->R, ctx->stream));
+    }
+    const size_t need = ctx->rngResidentUsedBound + ctx->rngCap;
+    if (ctx->rngUploaded < need) {
+        // not prefetched (first sweep after a restart): upload on the main stream
+        CK(cudaEventSynchronize(ctx->copyEvent[ctx->copyHalf]));
+        RET(stream_chunk_upload(ctx, ctx->rngUploaded, need - ctx->rngUploaded, ctx->stream, ctx->copyHalf));
+        CK(cudaEventRecord(ctx->copyEvent[ctx->copyHalf], ctx->stream));
+        ctx->copyHalf ^= 1;
+        ctx->rngUploaded = need;
+    } else {
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->copyEvent[ctx->copyHalf ^ 1], 0));    // the prefetched chunk
+    }
+    return DQMC_OK;
+}
+
+int stream_end_sweep(dqmc_ctx* ctx) {
+    ctx->rngResidentUsedBound += ctx->rngCap;
+    const size_t need = ctx->rngResidentUsedBound + ctx->rngCap;
+    if (need <= ctx->rngStride && ctx->rngUploaded < need) {
+        // the device is busy with the sweep just issued: generate, stage and copy the next chunk now
+        CK(cudaEventSynchronize(ctx->copyEvent[ctx->copyHalf]));                        // staging half free again
+        RET(stream_chunk_upload(ctx, ctx->rngUploaded, need - ctx->rngUploaded, ctx->copyStream, ctx->copyHalf));
+        CK(cudaEventRecord(ctx->copyEvent[ctx->copyHalf], ctx->copyStream));
+        ctx->copyHalf ^= 1;
+        ctx->rngUploaded = need;
+    }
+    return DQMC_OK;
+}
+
 int launch_update(dqmc_ctx* ctx, int k, int therm) {
     const int ro = ctx->laneOff, rc = ctx->laneCnt;           // replicas of the current lane
     const size_t dd = DD(ctx);
@@ -644,11 +713,16 @@ int global_shift_move(dqmc_ctx* ctx, int32_t* accepted_out) {
     CK(cudaMemcpyAsync(ctx->bkPhi, ctx->phi, sizeof(double) * phi_stride(ctx) * R, cudaMemcpyDeviceToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->bkCosh, ctx->coshT, sizeof(double) * tab_stride(ctx) * R, cudaMemcpyDeviceToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->bkSinh, ctx->sinhT, sizeof(double) * tab_stride(ctx) * R, cudaMemcpyDeviceToDevice, ctx->stream));
-    std::swap(ctx->G, ctx->bkG);
-    std::swap(ctx->stQ, ctx->bkQ);
-    std::swap(ctx->stT, ctx->bkT);
-    std::swap(ctx->stD, ctx->bkD);
-    std::swap(ctx->logdet, ctx->bkLogdet);
+    // everything that is recomputed is copied, not pointer-swapped: the device addresses stay fixed, which the
+    // captured sweep graphs rely on (≈ 2 GB of device-to-device copies per attempt at the headline size)
+    {
+        const size_t nm = ctx->nmat;
+        CK(cudaMemcpyAsync(ctx->bkG, ctx->G, sizeof(cplx) * DD(ctx) * nm, cudaMemcpyDeviceToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->bkQ, ctx->stQ, sizeof(cplx) * size_t(st_stride(ctx)) * nm, cudaMemcpyDeviceToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->bkT, ctx->stT, sizeof(cplx) * size_t(st_stride(ctx)) * nm, cudaMemcpyDeviceToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->bkD, ctx->stD, sizeof(double) * size_t(std_stride(ctx)) * nm, cudaMemcpyDeviceToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->bkLogdet, ctx->logdet, sizeof(double) * nm, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
     // addGlobalRandomDisplacement (:3755-3763): OPDIM draws of randRange(-phiDelta, +phiDelta)
     for (int r = 0; r < R; ++r) {
         const double pd = ctx->ctrl_host[r].phiDelta;
@@ -779,6 +853,53 @@ int sweep_up(dqmc_ctx* ctx, int therm) {
     return DQMC_OK;
 }
 
+// One sweep direction as a CUDA graph: the launch sequence of a sweep is static (slice / round / panel loops
+// with fixed trip counts, fixed device addresses), so it is captured once per (direction, thermalisation,
+// random-number window, lanes, stabiliser) and replayed -- ~5000 kernel launches per sweep become one graph
+// launch, which removes the host's launch-issue time from the step.
+int run_sweep(dqmc_ctx* ctx, int dir, int therm) {
+    auto direct = [&]() { return dir < 0 ? sweep_down(ctx, therm) : sweep_up(ctx, therm); };
+    if (ctx->profiling || ctx->graphsOff) return direct();
+    for (auto& g : ctx->graphs) {
+        if (g.dir == dir && g.therm == therm && g.rngWindow == ctx->rngWindow && g.rngStride == (long long)ctx->rngStride &&
+            g.nlanes == ctx->nlanes && g.stab == ctx->stabilizer && g.stream == ctx->stream) {
+            CK(cudaGraphLaunch(g.exec, ctx->stream));
+            ctx->launches += g.launches;
+            ctx->currentTimeslice = dir < 0 ? 0 : ctx->m;
+            return DQMC_OK;
+        }
+    }
+    // capture
+    const uint64_t l0 = ctx->launches + ctx->qr.launches;
+    const int ts0 = ctx->currentTimeslice;
+    if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        (void)cudaGetLastError();
+        ctx->graphsOff = true;
+        return direct();
+    }
+    const int rc = direct();
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ee = cudaStreamEndCapture(ctx->stream, &graph);
+    cudaGraphExec_t exec = nullptr;
+    if (rc != DQMC_OK || ee != cudaSuccess || !graph || cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
+        (void)cudaGetLastError();
+        if (graph) cudaGraphDestroy(graph);
+        std::fprintf(stderr, "libdqmc_b200: sweep graph capture failed (rc=%d, %s); issuing launches directly\n", rc,
+                     cudaGetErrorString(ee));
+        ctx->graphsOff = true;                 // fall back to direct issue (same kernels, same order)
+        ctx->currentTimeslice = ts0;
+        return direct();
+    }
+    cudaGraphDestroy(graph);
+    dqmc_ctx::SweepGraph sg;
+    sg.dir = dir; sg.therm = therm; sg.rngWindow = ctx->rngWindow; sg.rngStride = (long long)ctx->rngStride;
+    sg.nlanes = ctx->nlanes; sg.stab = ctx->stabilizer; sg.stream = ctx->stream; sg.exec = exec;
+    sg.launches = ctx->launches + ctx->qr.launches - l0;
+    ctx->graphs.push_back(sg);
+    CK(cudaGraphLaunch(exec, ctx->stream));
+    return DQMC_OK;
+}
+
 bool valid_rep(const dqmc_ctx* ctx, int rep) { return ctx && rep >= 0 && rep < ctx->R; }
 
 }  // namespace
@@ -886,23 +1007,35 @@ int dqmc_create(const dqmc_params* params, int n_replicas, int device, dqmc_ctx*
     CK(cudaMemsetAsync(ctx->X, 0, sizeof(cplx) * D * ctx->kmax * R, ctx->stream));   // finite everywhere (see extend_xy)
     CK(cudaMemsetAsync(ctx->Y, 0, sizeof(cplx) * D * ctx->kmax * R, ctx->stream));
     ctx->rngCap = size_t(ctx->m) * ctx->N * (ctx->p.opdim + 1);      // Hubbard: <= 2 values per attempt
-    ctx->rngAlloc = ctx->rngCap;
+    ctx->rngAlloc = ctx->rngCap * kStreamSweeps;               // streamed mode keeps several sweeps' worth on the device
     ctx->rngStride = ctx->rngCap;
+    ctx->rngAuto = false;
+    ctx->rngUploaded = 0;
+    ctx->copyHalf = 0;
     ctx->rngResident = false;
     ctx->rngResidentUsedBound = 0;
     ctx->profiling = false;
     ctx->profForce = -1;
+    ctx->graphsOff = std::getenv("DQMC_NO_GRAPHS") != nullptr;
     ctx->laneOff = 0;
     ctx->laneCnt = ctx->R;
     ctx->nlanes = 1;
-    ctx->laneStart[0] = 0; ctx->laneStart[1] = ctx->R; ctx->laneStart[2] = ctx->R;
-    for (int i = 0; i < 2; ++i) { ctx->laneStream[i] = nullptr; CK(cudaEventCreateWithFlags(&ctx->laneEvent[i], cudaEventDisableTiming)); }
-    CK(cudaStreamCreateWithFlags(&ctx->laneStream[1], cudaStreamNonBlocking));
-    if (ctx->R >= 8 && !std::getenv("DQMC_SINGLE_LANE")) {
-        ctx->nlanes = 2;
-        ctx->laneStart[1] = ctx->R / 2;
+    for (int i = 0; i <= DQMC_MAX_LANES; ++i) ctx->laneStart[i] = i == 0 ? 0 : ctx->R;
+    for (int i = 0; i < DQMC_MAX_LANES; ++i) {
+        ctx->laneStream[i] = nullptr;
+        CK(cudaEventCreateWithFlags(&ctx->laneEvent[i], cudaEventDisableTiming));
+        if (i > 0) CK(cudaStreamCreateWithFlags(&ctx->laneStream[i], cudaStreamNonBlocking));
     }
-    CK(dmalloc(&ctx->rngbuf, ctx->rngCap * R));
+    {
+        int want = ctx->R >= 32 ? 4 : (ctx->R >= 8 ? 2 : 1);
+        if (const char* e = std::getenv("DQMC_LANES")) want = std::atoi(e);
+        want = std::max(1, std::min(want, std::min(DQMC_MAX_LANES, ctx->R)));
+        ctx->nlanes = want;
+        for (int i = 0; i <= DQMC_MAX_LANES; ++i) ctx->laneStart[i] = i >= want ? ctx->R : (ctx->R * i) / want;
+    }
+    CK(dmalloc(&ctx->rngbuf, ctx->rngAlloc * R));
+    CK(cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) CK(cudaEventCreateWithFlags(&ctx->copyEvent[i], cudaEventDisableTiming));
     CK(dmalloc(&ctx->acceptedTotal, R));
     CK(cudaMemsetAsync(ctx->acceptedTotal, 0, sizeof(unsigned long long) * R, ctx->stream));
     CK(dmalloc(&ctx->cursor, R));
@@ -913,7 +1046,7 @@ int dqmc_create(const dqmc_params* params, int n_replicas, int device, dqmc_ctx*
     CK(dmalloc(&ctx->errflag, 1));
     CK(dmalloc(&ctx->actions, R));
     CK(dmalloc(&ctx->shiftbuf, 3 * R));
-    CK(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_rng), ctx->rngCap * R * sizeof(double)));
+    CK(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_rng), 2 * ctx->rngCap * R * sizeof(double)));   // two staging chunks
     CK(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_cursor), R * sizeof(int)));
     CK(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_scalars), (8 * R + 16) * sizeof(double)));
     CK(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_ctrl), R * sizeof(dqmc_control_data)));
@@ -988,10 +1121,15 @@ void dqmc_destroy(dqmc_ctx* ctx) {
     qr_workspace_destroy(&ctx->qr);
     void* host[] = {ctx->h_rng, ctx->h_cursor, ctx->h_scalars, ctx->h_ctrl, ctx->h_err, ctx->h_acc};
     for (void* p : host) if (p) cudaFreeHost(p);
+    if (ctx->copyStream) { cudaStreamSynchronize(ctx->copyStream); cudaStreamDestroy(ctx->copyStream); }
+    for (int i = 0; i < 2; ++i) if (ctx->copyEvent[i]) cudaEventDestroy(ctx->copyEvent[i]);
+    for (auto& g : ctx->graphs) cudaGraphExecDestroy(g.exec);
+    ctx->graphs.clear();
     prof_collect(ctx);
     for (cudaEvent_t e : ctx->profPool) cudaEventDestroy(e);
-    if (ctx->laneStream[1]) { cudaStreamSynchronize(ctx->laneStream[1]); cudaStreamDestroy(ctx->laneStream[1]); }
-    for (int i = 0; i < 2; ++i) if (ctx->laneEvent[i]) cudaEventDestroy(ctx->laneEvent[i]);
+    for (int i = 1; i < DQMC_MAX_LANES; ++i)
+        if (ctx->laneStream[i]) { cudaStreamSynchronize(ctx->laneStream[i]); cudaStreamDestroy(ctx->laneStream[i]); }
+    for (int i = 0; i < DQMC_MAX_LANES; ++i) if (ctx->laneEvent[i]) cudaEventDestroy(ctx->laneEvent[i]);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -1030,10 +1168,10 @@ int dqmc_set_option(dqmc_ctx* ctx, int option, int value) {
         ctx->stabilizer = value;
         return DQMC_OK;
     }
-    if (option == DQMC_OPT_LANES && (value == 1 || value == 2)) {
-        if (value == 2 && ctx->R < 2) { ctx->err = "two lanes need at least two replicas"; return DQMC_ERR_PARAM; }
+    if (option == DQMC_OPT_LANES && value >= 1 && value <= DQMC_MAX_LANES) {
+        if (value > ctx->R) { ctx->err = "more lanes than replicas"; return DQMC_ERR_PARAM; }
         ctx->nlanes = value;
-        ctx->laneStart[1] = value == 2 ? ctx->R / 2 : ctx->R;
+        for (int i = 0; i <= DQMC_MAX_LANES; ++i) ctx->laneStart[i] = i >= value ? ctx->R : (ctx->R * i) / value;
         return DQMC_OK;
     }
     ctx->err = "dqmc_set_option: unknown option or value";
@@ -1045,31 +1183,40 @@ uint64_t dqmc_launch_count(const dqmc_ctx* ctx) { return ctx ? ctx->launches + c
 // ---- RNG ---------------------------------------------------------------------------------------
 int dqmc_rng_seed(dqmc_ctx* ctx, int rep, uint32_t seed, uint32_t process_index) {
     if (!valid_rep(ctx, rep)) return DQMC_ERR_PARAM;
+    RET(host_sync_rng(ctx));
     ctx->rng[rep].seed(seed, process_index);
     return DQMC_OK;
 }
 int dqmc_rng_set_source(dqmc_ctx* ctx, int rep, dqmc_rng_fill_fn fill, void* user) {
     if (!valid_rep(ctx, rep) || !fill) return DQMC_ERR_PARAM;
+    RET(host_sync_rng(ctx));
     ctx->rng[rep].set_source(fill, user);
     return DQMC_OK;
 }
 int dqmc_rng_draw(dqmc_ctx* ctx, int rep, size_t n, double* out) {
     if (!valid_rep(ctx, rep) || (n && !out)) return DQMC_ERR_PARAM;
+    RET(host_sync_rng(ctx));
     for (size_t i = 0; i < n; ++i) out[i] = ctx->rng[rep].draw();
     return DQMC_OK;
 }
 int dqmc_rng_peek(dqmc_ctx* ctx, int rep, size_t n, double* out) {
     if (!valid_rep(ctx, rep) || (n && !out)) return DQMC_ERR_PARAM;
+    RET(host_sync_rng(ctx));
     const double* p = ctx->rng[rep].peek(n);
     std::memcpy(out, p, n * sizeof(double));
     return DQMC_OK;
 }
 int dqmc_rng_skip(dqmc_ctx* ctx, int rep, size_t n) {
     if (!valid_rep(ctx, rep)) return DQMC_ERR_PARAM;
+    RET(host_sync_rng(ctx));
     ctx->rng[rep].skip(n);
     return DQMC_OK;
 }
-uint64_t dqmc_rng_consumed(const dqmc_ctx* ctx, int rep) { return valid_rep(ctx, rep) ? ctx->rng[rep].consumed() : 0; }
+uint64_t dqmc_rng_consumed(const dqmc_ctx* ctx, int rep) {
+    if (!valid_rep(ctx, rep)) return 0;
+    if (host_sync_rng(const_cast<dqmc_ctx*>(ctx)) != DQMC_OK) return 0;
+    return ctx->rng[rep].consumed();
+}
 int dqmc_rng_stream_sample(uint32_t seed, uint32_t process_index, size_t n, double* out) {
     if (n && !out) return DQMC_ERR_PARAM;
     RngStream g;
@@ -1099,6 +1246,7 @@ int dqmc_upload_fields(dqmc_ctx* ctx, int rep, const void* fields) {
 
 int dqmc_init_random_fields(dqmc_ctx* ctx, int rep) {
     if (!valid_rep(ctx, rep)) return DQMC_ERR_PARAM;
+    RET(host_sync_rng(ctx));
     if (ctx->p.model == DQMC_MODEL_HUBBARD) {
         // setupRandomAuxfield, dethubbard.cpp:741-751: per (k, site) one rand01(), <= 0.5 -> +1
         std::vector<int32_t> aux(tab_stride(ctx), 0);
@@ -1172,11 +1320,13 @@ int dqmc_get_exchange_parameter(dqmc_ctx* ctx, int rep, double* r) {
 }
 int dqmc_get_control_data(dqmc_ctx* ctx, int rep, dqmc_control_data* out) {
     if (!valid_rep(ctx, rep) || !out) return DQMC_ERR_PARAM;
+    RET(host_sync_rng(ctx));
     *out = ctx->ctrl_host[rep];
     return DQMC_OK;
 }
 int dqmc_set_control_data(dqmc_ctx* ctx, int rep, const dqmc_control_data* in) {
     if (!valid_rep(ctx, rep) || !in) return DQMC_ERR_PARAM;
+    RET(host_sync_rng(ctx));
     ctx->ctrl_host[rep] = *in;
     return upload_ctrl(ctx);
 }
@@ -1386,6 +1536,7 @@ int dqmc_gemm_host(dqmc_ctx* ctx, int transa, int transb, int M, int N, int K, c
 // ---- Monte Carlo -------------------------------------------------------------------------------
 int dqmc_update_slice(dqmc_ctx* ctx, uint32_t k, int thermalization, uint32_t* n_accepted) {
     if (!ctx || k < 1 || (int)k > ctx->m) return DQMC_ERR_PARAM;
+    RET(host_sync_rng(ctx));
     RET(upload_rng_window(ctx, size_t(ctx->N) * (ctx->p.opdim + 1)));
     RET(launch_update(ctx, (int)k, thermalization));
     if (n_accepted)
@@ -1397,6 +1548,7 @@ int dqmc_update_slice(dqmc_ctx* ctx, uint32_t k, int thermalization, uint32_t* n
 
 int dqmc_global_shift_move(dqmc_ctx* ctx, int32_t* accepted) {
     if (!ctx) return DQMC_ERR_PARAM;
+    RET(host_sync_rng(ctx));
     if (ctx->p.model != DQMC_MODEL_SDW) { ctx->err = "only defined for DetSDW"; return DQMC_ERR_STATE; }
     RET(global_shift_move(ctx, accepted));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -1415,27 +1567,24 @@ int dqmc_phi_action(dqmc_ctx* ctx, double* out) {
 
 int dqmc_sweep(dqmc_ctx* ctx, int thermalization) {
     if (!ctx) return DQMC_ERR_PARAM;
-    const bool resident = ctx->rngResident;
-    if (resident && size_t(ctx->rngWindow) < ctx->rngResidentUsedBound + ctx->rngCap + 8) {
+    const bool preloaded = ctx->rngResident && !ctx->rngAuto;          // explicit dqmc_rng_preload
+    if (preloaded && size_t(ctx->rngWindow) < ctx->rngResidentUsedBound + ctx->rngCap + 8) {
         ctx->err = "resident random-number window too small for another sweep";
         return DQMC_ERR_STATE;
     }
-    if (ctx->lastSweepDir == +1) {
+    const bool global_now = ctx->lastSweepDir == +1 && ctx->p.globalShift &&
+                            (ctx->performedSweeps % ctx->p.globalUpdateInterval == 0);
+    if (global_now) {
         // globalMove() before a down-sweep, detmodel.h:1422-1424 + detsdwopdim.cpp:3460-3485
-        if (ctx->p.globalShift && (ctx->performedSweeps % ctx->p.globalUpdateInterval == 0)) {
-            if (resident) RET(sync_resident_cursor(ctx));     // the host draws must come after the device's
-            RET(global_shift_move(ctx, nullptr));
-            if (resident) RET(reupload_resident(ctx));
-        }
-        if (!resident) RET(upload_rng_window(ctx, ctx->rngCap));
-        RET(sweep_down(ctx, thermalization));
-        ctx->lastSweepDir = -1;
-    } else {
-        if (!resident) RET(upload_rng_window(ctx, ctx->rngCap));
-        RET(sweep_up(ctx, thermalization));
-        ctx->lastSweepDir = +1;
+        if (preloaded) RET(sync_resident_cursor(ctx));        // the host draws must come after the device's
+        else RET(host_sync_rng(ctx));
+        RET(global_shift_move(ctx, nullptr));
+        if (preloaded) RET(reupload_resident(ctx));
     }
-    if (!resident) RET(finish_rng_window(ctx));
+    if (!preloaded) RET(stream_begin_sweep(ctx));
+    RET(run_sweep(ctx, ctx->lastSweepDir == +1 ? -1 : +1, thermalization));
+    ctx->lastSweepDir = -ctx->lastSweepDir;
+    if (!preloaded) RET(stream_end_sweep(ctx));
     else ctx->rngResidentUsedBound += ctx->rngCap;
     ctx->performedSweeps += 1;
     return DQMC_OK;
@@ -1447,8 +1596,9 @@ int dqmc_sweep(dqmc_ctx* ctx, int thermalization) {
 int dqmc_rng_preload(dqmc_ctx* ctx, int n_sweeps) {
     if (!ctx || n_sweeps < 1) return DQMC_ERR_PARAM;
     if (ctx->rngResident) RET(dqmc_rng_release(ctx));
-    const size_t per = ctx->rngCap * size_t(n_sweeps) + 16;
-    if (per > ctx->rngAlloc) {
+    RET(host_sync_rng(ctx));
+    const size_t per = ctx->rngCap * size_t(std::max(n_sweeps, 2)) + 16;
+    if (per > ctx->rngAlloc || true) {
         CK(cudaStreamSynchronize(ctx->stream));
         cudaFree(ctx->rngbuf);
         cudaFreeHost(ctx->h_rng);
@@ -1471,6 +1621,7 @@ int dqmc_rng_preload(dqmc_ctx* ctx, int n_sweeps) {
 
 int dqmc_rng_release(dqmc_ctx* ctx) {
     if (!ctx) return DQMC_ERR_PARAM;
+    if (ctx->rngAuto) return host_sync_rng(ctx);
     if (!ctx->rngResident) return DQMC_OK;
     RET(finish_rng_window(ctx));
     ctx->rngResident = false;
@@ -1525,6 +1676,11 @@ int dqmc_exchange_pack(dqmc_ctx* ctx, double* payload_dev, int n_uniforms) {
     if (!ctx || !payload_dev || n_uniforms < 0) return DQMC_ERR_PARAM;
     if (ctx->p.model != DQMC_MODEL_SDW) { ctx->err = "only defined for DetSDW"; return DQMC_ERR_STATE; }
     const int R = ctx->R;
+    if (ctx->rngAuto && ctx->rngResident) {
+        // streamed random numbers: the look-ahead uniforms must already be on the device
+        if (ctx->rngUploaded < ctx->rngResidentUsedBound + size_t(n_uniforms)) RET(host_sync_rng(ctx));
+        else CK(cudaStreamWaitEvent(ctx->stream, ctx->copyEvent[ctx->copyHalf ^ 1], 0));
+    }
     CKL(launch_exchange_action(ctx->phi, payload_dev, ctx->N, ctx->opdim, ctx->m, ctx->p.dtau,
                                (long long)phi_stride(ctx), R, ctx->stream));
     double* uni = payload_dev + R;
@@ -1546,7 +1702,10 @@ int dqmc_exchange_apply(dqmc_ctx* ctx, const double* r_new, const dqmc_control_d
         ctx->ctrl_host[r] = ctrl_new[r];
     }
     if (n_uniforms_used > 0) {
-        if (ctx->rngResident) CKL(launch_cursor_advance(ctx->cursor, 0, n_uniforms_used, ctx->stream));
+        if (ctx->rngResident) {
+            CKL(launch_cursor_advance(ctx->cursor, 0, n_uniforms_used, ctx->stream));
+            ctx->rngResidentUsedBound += size_t(n_uniforms_used);
+        }
         else ctx->rng[0].skip((size_t)n_uniforms_used);
     }
     RET(upload_ctrl(ctx));

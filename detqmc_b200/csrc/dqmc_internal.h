@@ -11,6 +11,8 @@
 #include "../../include/dqmc_gpu.h"
 #include "rng_stream.h"
 
+#define DQMC_MAX_LANES 4
+
 namespace dqmc {
 
 typedef double2 cplx;
@@ -251,12 +253,20 @@ struct dqmc_ctx {
     int* cursor;           // [R]
     int rngWindow;         // number of values per replica in the uploaded window
     size_t rngAlloc, rngStride;
-    bool rngResident;      // window pre-loaded for several sweeps (dqmc_rng_preload)
+    bool rngResident;      // window pre-loaded for several sweeps (dqmc_rng_preload) or streamed (rngAuto)
+    bool rngAuto;          // streamed mode of dqmc_sweep: chunks are uploaded one sweep ahead on copyStream
+    size_t rngUploaded;    // values per replica present in the device buffer (streamed mode)
+    cudaStream_t copyStream; cudaEvent_t copyEvent[2]; int copyHalf;
     size_t rngResidentUsedBound;
     unsigned long long* acceptedTotal;
     // lanes: the replicas are split into up to two groups whose sweeps are issued on separate streams
-    int nlanes; int laneStart[3]; int laneOff, laneCnt;
-    cudaStream_t laneStream[2]; cudaEvent_t laneEvent[2];
+    int nlanes; int laneStart[DQMC_MAX_LANES + 1]; int laneOff, laneCnt;
+    cudaStream_t laneStream[DQMC_MAX_LANES]; cudaEvent_t laneEvent[DQMC_MAX_LANES];
+    // captured sweeps (run_sweep)
+    struct SweepGraph { int dir, therm, rngWindow; long long rngStride; int nlanes, stab; cudaStream_t stream;
+                        cudaGraphExec_t exec; uint64_t launches; };
+    std::vector<SweepGraph> graphs;
+    bool graphsOff;
     bool profiling;
     int profForce;         // >= 0: category of the next timed launch (overrides the name-based one)
     struct ProfRec { int cat; cudaEvent_t e0, e1; };

@@ -553,30 +553,6 @@ __global__ void __launch_bounds__(kPanelThreads) qr_panel_kernel(cplx* Aall, lon
     }
 }
 
-// 1/sqrt(x) and 1/x to (almost) full double precision from the SFU seeds + Newton-Raphson; used where the
-// latency of the correctly rounded FP64 sqrt / division would sit on a serial critical path
-__device__ __forceinline__ double fast_rsqrt(double x) {
-    // scale into the float range first (|x|^2 of a column can exceed it for the graded chain matrices)
-    int e;
-    const double mnt = frexp(x, &e);                     // x = mnt * 2^e, mnt in [0.5, 1)
-    const int eh = e >> 1;                               // x = (mnt * 2^(e - 2 eh)) * 4^eh
-    const double xs = ldexp(mnt, e - 2 * eh);
-    double y = double(rsqrtf(float(xs)));
-    y = y * (1.5 - 0.5 * xs * y * y);
-    y = y * (1.5 - 0.5 * xs * y * y);
-    y = y * (1.5 - 0.5 * xs * y * y);
-    return ldexp(y, -eh);
-}
-__device__ __forceinline__ double fast_rcp(double x) {
-    int e;
-    const double mnt = frexp(x, &e);
-    double y = double(__frcp_rn(float(mnt)));
-    y = y * (2.0 - mnt * y);
-    y = y * (2.0 - mnt * y);
-    y = y * (2.0 - mnt * y);
-    return ldexp(y, -e);
-}
-
 // Register-resident variant of the panel factorisation for m <= 32 * MAXT rows: warp w owns panel column
 // w in registers (lane l holds rows l, l+32, ...), the current reflector is broadcast through a
 // double-buffered shared-memory vector, so a column step is one barrier, one dot product and one update
@@ -584,7 +560,6 @@ __device__ __forceinline__ double fast_rcp(double x) {
 // Gram matrix of the reflectors, and warp c-1 folds its column into the compact-WY factor T while the
 // others work, so T costs no extra pass.  ~3x fewer instructions per column than qr_panel_kernel, which
 // stays as the fallback for taller panels.
-__device__ int getenv_dbg_panel = 0;
 constexpr int kPanelRegThreads = 512;      // 16 warps, two panel columns per warp
 
 template <int MAXT>
@@ -614,14 +589,8 @@ __global__ void __launch_bounds__(kPanelRegThreads) qr_panel_reg_kernel(cplx* Aa
     for (int i = tid; i < 32 * 33; i += blockDim.x) { Gm[i] = make_double2(0, 0); Tm[i] = make_double2(0, 0); }
     __syncthreads();
 
-    long long tq[5] = {0, 0, 0, 0, 0};
-    long long tmark;
-    const bool dbg = getenv_dbg_panel != 0;
-#define PTICK(i) if (dbg) { long long n__; asm volatile("mov.u64 %0, %%clock64;" : "=l"(n__) :: "memory"); tq[i] += n__ - tmark; tmark = n__; }
-    if (dbg) asm volatile("mov.u64 %0, %%clock64;" : "=l"(tmark) :: "memory");
     for (int c = 0; c < nbc; ++c) {
         cplx* vb = vbuf + (c & 1) * m;
-        PTICK(4)
         if (w == (c & 15)) {
             // ---- reflector of the own column (zlarfg conventions); h selects which of the two columns
             const int h = c >> 4;
@@ -672,10 +641,8 @@ __global__ void __launch_bounds__(kPanelRegThreads) qr_panel_reg_kernel(cplx* Aa
                 }
             }
             if (lane == 0) s_tau[c] = tau;
-            PTICK(0)
         }
         __syncthreads();
-        PTICK(1)
         const cplx tau = s_tau[c];
         if (tau.x != 0.0 || tau.y != 0.0) {
             // dot_h = v_c^H x_h over rows >= c for both own columns (a_w for w > c, v_w for w < c)
@@ -717,7 +684,6 @@ __global__ void __launch_bounds__(kPanelRegThreads) qr_panel_reg_kernel(cplx* Aa
                 }
             }
         }
-        PTICK(2)
         // ---- compact-WY factor: column c-1 of T (its Gram column was completed in the previous step)
         if (c > 0 && w == ((c - 1) & 15)) {
             const int cc = c - 1;
@@ -728,12 +694,8 @@ __global__ void __launch_bounds__(kPanelRegThreads) qr_panel_reg_kernel(cplx* Aa
                 for (int l = lane; l < cc; ++l) sacc = cfma_(Tm[lane * 33 + l], Gm[l * 33 + cc], sacc);
                 Tm[lane * 33 + cc] = make_double2(-(tcc.x * sacc.x - tcc.y * sacc.y), -(tcc.x * sacc.y + tcc.y * sacc.x));
             }
-            PTICK(3)
         }
     }
-    if (dbg && b == 0 && lane == 0 && (w < 3))
-        printf("panel dbg j0 %d warp %d: reflector %lld barrier %lld apply %lld tcol %lld other %lld\n", j0, w, tq[0], tq[1], tq[2],
-               tq[3], tq[4]);
     __syncthreads();
     if (w == ((nbc - 1) & 15)) {
         const int cc = nbc - 1;
@@ -890,8 +852,6 @@ cudaError_t qr_blocked_factor(QrWorkspace& ws, cplx* A, int D, long long strideA
         const int nbc = std::min(nb, D - j0), m = D - j0, n2 = D - j0 - nbc;
         const size_t sm = size_t(nbc) * (m | 1) * sizeof(cplx) + 2 * 32 * 33 * sizeof(cplx);
         static const bool force_smem_panel = std::getenv("DQMC_QR_SMEM_PANEL") != nullptr;
-        static bool dbg_set = false;
-        if (!dbg_set) { const int v = std::getenv("DQMC_QR_DEBUG") ? 1 : 0; cudaMemcpyToSymbol(getenv_dbg_panel, &v, sizeof v); dbg_set = true; }
         if (m <= 320 && nb == 32 && !force_smem_panel) {
             qr_panel_reg_kernel<10><<<batch, kPanelRegThreads, sm + size_t(2) * m * sizeof(cplx), st>>>(A, strideA, D, j0, nbc, V,
                                                                                                   VT, (long long)dd);

@@ -58,6 +58,8 @@ public:
     double draw_range(double lo, double hi) { return lo + (hi - lo) * draw(); }
     int draw_int(int lo, int hi) { return lo + static_cast<int>((hi - lo + 1.0) * draw()); }
     uint64_t consumed() const { return consumed_; }
+    // make sure at least n values are buffered (generation can then overlap with device work)
+    void prefetch(size_t n) { ensure(n); }
 private:
     void ensure(size_t n);
     Dsfmt19937 gen_;

@@ -495,7 +495,7 @@ __global__ void __launch_bounds__(MAXT) update_round_kernel(UpdateModel md, Upda
             for (int q = 0; q < TPT; ++q) {
                 const int t = gt + q * gthreads;
                 if (t < D)
-                    extend_xy<MSF>(X, Y, G, D, N, KMAX, (a.debug >= 6 ? 0 : K_done), site - 1, t, sm.xrow + pb * MSF * KMAX,
+                    extend_xy<MSF>(X, Y, G, D, N, KMAX, K_done, site - 1, t, sm.xrow + pb * MSF * KMAX,
                                    sm.ycol + pb * MSF * KMAX, sm.Delta, sm.Minv, xrow, ycol, true, Gr[q], Gc[q]);
             }
         }

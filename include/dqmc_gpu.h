@@ -104,7 +104,7 @@ int dqmc_dims(const dqmc_ctx* ctx, int32_t* out);
  *                                         Householder QR with tensor-core trailing updates;
  *   DQMC_STAB_FULL_PIVOT                  Householder QR with full column pivoting, one CTA per matrix
  *                                         (slow; kept as the cross-check of the tests).
- * DQMC_OPT_LANES (1 or 2; default 2 for >= 8 replicas): the replicas of a context are split into lanes whose
+ * DQMC_OPT_LANES (1..4; default 4 for >= 32 replicas, 2 for >= 8, else 1): the replicas of a context are split into lanes whose
  * sweeps are issued on separate CUDA streams, so that the latency-bound kernels of one lane (sequential update
  * rounds, QR panels) overlap with the throughput-bound kernels of the other.  Results do not depend on it. */
 enum { DQMC_OPT_STABILIZER = 0, DQMC_OPT_LANES = 1 };

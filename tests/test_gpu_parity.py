@@ -424,3 +424,27 @@ def test_hubbard_full_size_properties():
     single.sweep()
     assert np.array_equal(single.auxfield(0), b.auxfield(1))
     assert relerr(single.green(0, 1), b.green(1, 1)) < 1e-12
+
+
+def test_o3_full_size_properties():
+    """BASELINE config C4 (DetSDW O(3), L=14, beta=14, s=10: D = 784, m = 140) at full size through properties
+    that need no oracle: B^-1 B = 1, wrap round trip, wrapped vs recomputed G at the stabilisation points,
+    G(0) after a full sweep vs from scratch, log|det| consistency between setup and from-scratch."""
+    from dqmc_oracle import SdwParams
+    p = SdwParams(opdim=3, L=14, m=140, s=10, weakZflux=False)
+    b = make_batch(p, n_replicas=1)
+    D = b.D
+    assert D == 784
+    A = rand_cplx((D, D), 3)
+    assert relerr(b.bmat_mult(2, b.bmat_mult(0, A, 17, 7), 17, 7), A) < 1e-10
+    assert relerr(b.bmat_mult(3, b.bmat_mult(1, A, 17, 7), 17, 7), A) < 1e-10
+    G0 = b.green(0)
+    assert relerr(G0, b.green_for_timeslice(p.m)) < 1e-8
+    b.wrap_down(p.m)
+    b.wrap_up(p.m - 1)
+    assert relerr(b.green(0), G0) < 1e-9
+    b.sweepThermalization()                                         # global move + full down-sweep
+    acc = b.control_data(0).lastAccRatioLocal_phi
+    assert 0.05 < acc < 0.99
+    assert np.all(b.green_consistency() < 1e-6)
+    assert relerr(b.green(0), b.green_for_timeslice(0)) < 1e-7

@@ -352,6 +352,10 @@ cudaError_t gemm_launch(const GemmArgs& g, cudaStream_t st) {
         if (g.M % 48 == 0 && g.N % 96 == 0 && cfg == 3) return launch_rank_update<2, 4, 3, 3>(g, st);   // 48 x 96
         if (g.M % 96 == 0 && g.N % 96 == 0 && cfg == 4) return launch_rank_update<4, 4, 3, 3>(g, st);   // 96 x 96, 16 warps
         if (g.M % 96 == 0 && g.N % 96 == 0) return launch_rank_update<4, 3, 3, 4>(g, st);
+        static const int cfg2 = std::getenv("DQMC_RANKUPD_CFG2") ? std::atoi(std::getenv("DQMC_RANKUPD_CFG2")) : 3;
+        if (cfg2 == 1 && g.M > 32 && g.N > 32) return launch_rank_update<4, 4, 2, 2>(g, st);            // 64 x 64, 16 warps
+        if (cfg2 == 2 && g.M > 32 && g.N > 32) return launch_rank_update<4, 2, 2, 2>(g, st);            // 64 x 32, 8 warps
+        if (cfg2 == 3 && g.M > 32 && g.N > 32) return launch_rank_update<2, 2, 2, 2>(g, st);            // 32 x 32, 4 warps
         if ((g.M > 32 && g.N > 32) || g.kvec) return launch_rank_update<2, 2, 4, 4>(g, st);
     }
     if (g.kvec || g.b_kmajor) return cudaErrorInvalidValue;           // per-matrix K exists on the rank-update path only
@@ -359,6 +363,10 @@ cudaError_t gemm_launch(const GemmArgs& g, cudaStream_t st) {
     // (the panel products of the blocked QR / triangular solve) get 32 x 64 and 64 x 32 tiles
     if (g.M % 96 == 0 && g.N % 96 == 0 && g.K >= 64) return launch_cfg<4, 3, 3, 4>(g, st);   // 12 warps, 24 x 32 each
     if (g.M <= 32 && g.N <= 32) return launch_cfg<1, 1, 4, 4>(g, st);
+    static const int cfgw = std::getenv("DQMC_WGEMM_CFG") ? std::atoi(std::getenv("DQMC_WGEMM_CFG")) : 3;
+    if (g.M <= 32 && cfgw == 1) return launch_cfg<2, 4, 2, 2>(g, st);          // 32 x 64, 8 warps
+    if (g.M <= 32 && cfgw == 2) return launch_cfg<2, 2, 2, 2>(g, st);          // 32 x 32, 4 warps
+    if (g.M <= 32 && cfgw == 3) return launch_cfg<2, 4, 2, 1>(g, st);          // 32 x 32, 8 warps
     if (g.M <= 32) return launch_cfg<1, 4, 4, 2>(g, st);                       // 32 x 64, 4 warps
     if (g.N <= 32) return launch_cfg<4, 1, 2, 4>(g, st);                       // 64 x 32, 4 warps
     return launch_cfg<2, 2, 4, 4>(g, st);

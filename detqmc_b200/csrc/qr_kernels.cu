@@ -592,55 +592,45 @@ __global__ void __launch_bounds__(kPanelRegThreads) qr_panel_reg_kernel(cplx* Aa
     for (int c = 0; c < nbc; ++c) {
         cplx* vb = vbuf + (c & 1) * m;
         if (w == (c & 15)) {
-            // ---- reflector of the own column (zlarfg conventions); h selects which of the two columns
-            const int h = c >> 4;
-            double xn = 0;
-            cplx alpha = make_double2(0, 0);
+            // ---- reflector of the own column (zlarfg conventions).  This warp is the serial critical path of
+            // the column step, so the code is straight-line: the slot (which of the two columns) is a
+            // warp-uniform branch around two copies, rsqrt + one reciprocal replace sqrt + divisions.
+            auto reflect = [&](cplx (&a)[MAXT]) {
+                double xn = 0;
+                cplx alpha = make_double2(0, 0);
 #pragma unroll
-            for (int t = 0; t < MAXT; ++t) {
-                const int row = lane + 32 * t;
-                const cplx a = h ? col[1][t] : col[0][t];
-                if (row > c && row < m) xn = fma(a.x, a.x, fma(a.y, a.y, xn));
-                if (row == c) alpha = a;
-            }
-            xn = warp_sum(xn);
-            alpha.x = __shfl_sync(0xffffffffu, alpha.x, c & 31);
-            alpha.y = __shfl_sync(0xffffffffu, alpha.y, c & 31);
-            cplx tau, sc;
-            double beta;
-            if (xn == 0.0 && alpha.y == 0.0) {
-                tau = make_double2(0, 0);
-                sc = make_double2(0, 0);
-                beta = alpha.x;
-            } else {
-                // this warp is the serial critical path of the column step: one rsqrt + one reciprocal
-                // instead of sqrt + divisions
-                const double x2 = alpha.x * alpha.x + alpha.y * alpha.y + xn;
-                const double inrm = rsqrt(x2);
-                const double nrm = x2 * inrm;
-                beta = alpha.x >= 0 ? -nrm : nrm;
-                const double ib = alpha.x >= 0 ? -inrm : inrm;                  // 1 / beta
-                tau = make_double2((beta - alpha.x) * ib, -alpha.y * ib);
-                const double dr = alpha.x - beta, di = alpha.y;
-                const double iden = __drcp_rn(dr * dr + di * di);
-                sc = make_double2(dr * iden, -di * iden);
-            }
-#pragma unroll
-            for (int t = 0; t < MAXT; ++t) {
-                const int row = lane + 32 * t;
-                if (row < m) {
-                    cplx a = h ? col[1][t] : col[0][t];
-                    if (row > c) {
-                        a = cmul(a, sc);
-                        vb[row] = a;
-                    } else if (row == c) {
-                        a = make_double2(beta, 0);                   // R diagonal
-                        vb[row] = make_double2(1, 0);
-                    }
-                    if (h) col[1][t] = a; else col[0][t] = a;
+                for (int t = 0; t < MAXT; ++t) {
+                    const int row = lane + 32 * t;
+                    const double n2 = fma(a[t].x, a[t].x, a[t].y * a[t].y);
+                    xn += (row > c && row < m) ? n2 : 0.0;
+                    alpha.x = row == c ? a[t].x : alpha.x;
+                    alpha.y = row == c ? a[t].y : alpha.y;
                 }
-            }
-            if (lane == 0) s_tau[c] = tau;
+                xn = warp_sum(xn);
+                alpha.x = __shfl_sync(0xffffffffu, alpha.x, c & 31);
+                alpha.y = __shfl_sync(0xffffffffu, alpha.y, c & 31);
+                const bool trivial = xn == 0.0 && alpha.y == 0.0;
+                const double x2 = alpha.x * alpha.x + alpha.y * alpha.y + xn;
+                const double inrm = trivial ? 0.0 : rsqrt(x2);
+                const double nrm = x2 * inrm;
+                const double beta = trivial ? alpha.x : (alpha.x >= 0 ? -nrm : nrm);
+                const double ib = alpha.x >= 0 ? -inrm : inrm;                    // 1 / beta
+                const cplx tau = trivial ? make_double2(0, 0) : make_double2((beta - alpha.x) * ib, -alpha.y * ib);
+                const double dr = alpha.x - beta, di = alpha.y;
+                const double iden = trivial ? 0.0 : __drcp_rn(dr * dr + di * di);
+                const cplx sc = make_double2(dr * iden, -di * iden);
+#pragma unroll
+                for (int t = 0; t < MAXT; ++t) {
+                    const int row = lane + 32 * t;
+                    const cplx scaled = cmul(a[t], sc);
+                    const cplx vnew = row > c ? scaled : make_double2(row == c ? 1.0 : 0.0, 0.0);
+                    if (row < m) vb[row] = vnew;                                  // rows < c are never read
+                    a[t].x = row > c ? scaled.x : (row == c ? beta : a[t].x);     // row c keeps the R diagonal
+                    a[t].y = row > c ? scaled.y : (row == c ? 0.0 : a[t].y);
+                }
+                if (lane == 0) s_tau[c] = tau;
+            };
+            if (c < 16) reflect(col[0]); else reflect(col[1]);
         }
         __syncthreads();
         const cplx tau = s_tau[c];

@@ -174,6 +174,7 @@ struct UpdSmem {
     cplx* Minv;        // [MSF*MSF]
     cplx* xrow;        // [2][MSF][KMAX] pending X rows `site + rN`  (double buffered: this site / next site)
     cplx* ycol;        // [2][MSF][KMAX] pending Y columns `site + cN`
+    cplx* Ys;          // [KMAX][D] shared-memory copy of the pending Y rows (nullptr when it does not fit)
 };
 
 constexpr int kDecWarps = 2;        // warp 0: proposal + decision, warp 1: stager for the pending rows / columns
@@ -235,7 +236,7 @@ template <int MSF>
 __device__ __forceinline__ void extend_xy(cplx* __restrict__ X, cplx* __restrict__ Y, const cplx* __restrict__ G,
                                           int D, int N, int KMAX, int K, int site, int t, const cplx* xrow,
                                           const cplx* ycol, const cplx* sDelta, const cplx* sMinv, cplx* xnext,
-                                          cplx* ynext, bool have_next, const cplx* Gr, const cplx* Gc) {
+                                          cplx* ynext, bool have_next, const cplx* Gr, const cplx* Gc, cplx* Ys) {
     cplx Rr[MSF], Cc[MSF];
 #pragma unroll
     for (int r = 0; r < MSF; ++r) { Rr[r] = make_double2(0, 0); Cc[r] = make_double2(0, 0); }
@@ -246,7 +247,8 @@ __device__ __forceinline__ void extend_xy(cplx* __restrict__ X, cplx* __restrict
     const uint32_t xs = (uint32_t)__cvta_generic_to_shared(xrow);
     const uint32_t ys = (uint32_t)__cvta_generic_to_shared(ycol);
     const cplx* __restrict__ xp = X + t;
-    const cplx* __restrict__ yp = Y + t;
+    // pending Y rows of this thread: from the shared-memory copy when the CTA keeps one (Ys), else from global
+    const cplx* yp = (Ys ? Ys : Y) + t;
     for (int l0 = 0; l0 < K; l0 += CH) {
         cplx yv[CH], xv[CH];
 #pragma unroll
@@ -282,6 +284,7 @@ __device__ __forceinline__ void extend_xy(cplx* __restrict__ X, cplx* __restrict
         }
         ynew[r] = yn; xnew[r] = xn;
         Y[size_t(K + r) * D + t] = yn;
+        if (Ys) Ys[size_t(K + r) * D + t] = yn;
         X[size_t(K + r) * D + t] = xn;
     }
     // new entries of the staged rows / columns of the next site
@@ -327,6 +330,7 @@ __global__ void __launch_bounds__(MAXT) update_round_kernel(UpdateModel md, Upda
     sm.Minv = sm.Delta + MSF * MSF;
     sm.xrow = sm.Minv + MSF * MSF;
     sm.ycol = sm.xrow + 2 * MSF * KMAX;
+    sm.Ys = a.y_in_smem ? sm.ycol + 2 * MSF * KMAX : nullptr;
     __shared__ int sAccept, sAbort, sNload;
 
     const int b = blockIdx.x;
@@ -376,6 +380,8 @@ __global__ void __launch_bounds__(MAXT) update_round_kernel(UpdateModel md, Upda
             sm.xrow[i] = make_double2(0, 0);
             sm.ycol[i] = make_double2(0, 0);
         }
+        if (sm.Ys)
+            for (int i = tid; i < KMAX * D; i += blockDim.x) sm.Ys[i] = make_double2(0, 0);   // finite beyond K
         if (tid == 0) { sAbort = 0; sNload = have; sAccept = 0; }
     }
     __syncthreads();
@@ -465,7 +471,7 @@ __global__ void __launch_bounds__(MAXT) update_round_kernel(UpdateModel md, Upda
 #pragma unroll
                 for (int r = 0; r < MSF; ++r) {
                     xs[r] = X[size_t(l) * D + site + r * N];
-                    ys[r] = Y[size_t(l) * D + site + r * N];
+                    ys[r] = (sm.Ys ? sm.Ys : Y)[size_t(l) * D + site + r * N];
                     xrow[r * KMAX + l] = xs[r];
                     ycol[r * KMAX + l] = ys[r];
                 }
@@ -496,7 +502,7 @@ __global__ void __launch_bounds__(MAXT) update_round_kernel(UpdateModel md, Upda
                 const int t = gt + q * gthreads;
                 if (t < D)
                     extend_xy<MSF>(X, Y, G, D, N, KMAX, K_done, site - 1, t, sm.xrow + pb * MSF * KMAX,
-                                   sm.ycol + pb * MSF * KMAX, sm.Delta, sm.Minv, xrow, ycol, true, Gr[q], Gc[q]);
+                                   sm.ycol + pb * MSF * KMAX, sm.Delta, sm.Minv, xrow, ycol, true, Gr[q], Gc[q], sm.Ys);
             }
         }
         TICK(0)
@@ -586,7 +592,7 @@ __global__ void __launch_bounds__(MAXT) update_round_kernel(UpdateModel md, Upda
                         const int t = gt + q * gthreads;
                         if (t < D)
                             extend_xy<MSF>(X, Y, G, D, N, KMAX, MSF * (j - 1), site, t, xrow, ycol, sm.Delta, sm.Minv,
-                                           nullptr, nullptr, false, Gr[q], Gc[q]);
+                                           nullptr, nullptr, false, Gr[q], Gc[q], sm.Ys);
                     }
                 }
                 prev_acc = false;
@@ -619,7 +625,7 @@ __global__ void __launch_bounds__(MAXT) update_round_kernel(UpdateModel md, Upda
                 const int t = gt + q * gthreads;
                 if (t < D)
                     extend_xy<MSF>(X, Y, G, D, N, KMAX, MSF * (j - 1), site - 1, t, sm.xrow + pb * MSF * KMAX,
-                                   sm.ycol + pb * MSF * KMAX, sm.Delta, sm.Minv, nullptr, nullptr, false, Gr[q], Gc[q]);
+                                   sm.ycol + pb * MSF * KMAX, sm.Delta, sm.Minv, nullptr, nullptr, false, Gr[q], Gc[q], sm.Ys);
             }
         }
     }
@@ -673,14 +679,19 @@ cudaError_t update_round_launch(const UpdateModel& m, const UpdateArgs& a, cudaS
     if (m.D > 2 * 896) return cudaErrorInvalidValue;
     const int gth = ((((m.D + tpt - 1) / tpt) + 31) / 32) * 32;
     const int threads = kDecThreads + gth;
-    const size_t smem = size_t((2 * m.opdim + 2) * m.N + ((m.N * (m.opdim + 1) + 1) & ~1)) * sizeof(double) +
-                        size_t(5) * m.msf * m.msf * sizeof(cplx) + size_t(4) * m.msf * ((m.msf * m.delaySteps + 3) & ~3) * sizeof(cplx);
+    const int kmaxp = (m.msf * m.delaySteps + 3) & ~3;
+    size_t smem = size_t((2 * m.opdim + 2) * m.N + ((m.N * (m.opdim + 1) + 1) & ~1)) * sizeof(double) +
+                        size_t(5) * m.msf * m.msf * sizeof(cplx) + size_t(4) * m.msf * kmaxp * sizeof(cplx);
+    UpdateArgs aa = a;
+    const size_t ybytes = size_t(kmaxp) * m.D * sizeof(cplx);
+    aa.y_in_smem = (!a.inline_flush && smem + ybytes <= 200 * 1024) ? 1 : 0;     // pending Y rows in shared memory
+    if (aa.y_in_smem) smem += ybytes;
 #define LAUNCH(MSF, OPD, TPT, MAXT)                                                                         \
     {                                                                                                       \
         cudaError_t e = cudaFuncSetAttribute(update_round_kernel<MSF, OPD, TPT, MAXT>,                      \
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
         if (e != cudaSuccess) return e;                                                                     \
-        update_round_kernel<MSF, OPD, TPT, MAXT><<<a.batch, threads, smem, st>>>(m, a);                     \
+        update_round_kernel<MSF, OPD, TPT, MAXT><<<a.batch, threads, smem, st>>>(m, aa);                     \
     }
 #define LAUNCH3(MSF, OPD)                                                                                   \
     {                                                                                                       \

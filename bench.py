@@ -112,13 +112,17 @@ def _ref_worker(args):
     import ref_bindings as rb
     from dqmc_oracle import SdwOracle, SdwParams
     p = SdwParams(r=float(r), rngIndex=int(idx), **WORKLOAD)
+    # the first sweep of a replica contains a global-shift move (performedSweeps % interval == 0): it runs
+    # untimed, so that the timed window starts one sweep after a global move like the GPU arm's windows
     if rb.available():
         rep = rb.RefSdw(p)
+        rep.sweep(therm=True)
         t0 = time.perf_counter()
         for _ in range(sweeps):
             rep.sweep(therm=True)
         return "reference", sweeps, time.perf_counter() - t0
     rep = SdwOracle(p)
+    rep.sweep_thermalization()
     t0 = time.perf_counter()
     for _ in range(sweeps):
         rep.sweep_thermalization()
@@ -140,7 +144,8 @@ def cpu_baseline(n_procs, sweeps_each, P):
     total = sum(r[1] for r in res)
     return {"value": total / sweep_time, "unit": "replica-sweeps/s", "cores": n_procs, "kind": kind,
             "sample": "%d replicas of the ladder x %d sweeps each, one single-threaded process per replica "
-                      "(OPENBLAS_NUM_THREADS=1), construction excluded; wall %.1f s" % (n_procs, sweeps_each, wall)}
+                      "(OPENBLAS_NUM_THREADS=1), construction and one warm-up sweep (the one with the global-shift move) "
+                      "excluded; wall %.1f s" % (n_procs, sweeps_each, wall)}
 
 
 def run_reference(args):
@@ -152,7 +157,7 @@ def run_reference(args):
     steps = max(1, min(args.steps, 2))                      # each step = one sweep per sampled replica
     base = cpu_baseline(n_procs, steps, args.replicas)
     line = {"impl": "reference", "metric": "DetSDW O(2) L=12 beta=10 sweeps/sec", "value": base["value"],
-            "unit": "replica-sweeps/s", "n_gpus": args.gpus, "steps": steps, "warmup": 0,
+            "unit": "replica-sweeps/s", "n_gpus": args.gpus, "steps": steps, "warmup": 1,
             "ms_per_step": 1e3 * args.replicas / base["value"], "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64 (complex128)", "data": "synthetic",
             "config": {"workload": workload_name(args.replicas), "replicas": args.replicas},
@@ -241,10 +246,27 @@ def run_b200(args):
         return float(t.item())
 
     W, K = args.warmup, args.steps
+    gint = WORKLOAD["globalUpdateInterval"]
+
+    def align():
+        """Every timed window (value, e2e, and the reference arm's) starts one sweep after a global-shift move
+        (DetSDW::globalMove runs before every `globalUpdateInterval`-th sweep and costs a full re-setup), so
+        that the windows hold the same number of them: floor((K - 1 + 1) / interval) for K steps."""
+        n = 0
+        while batch.sweep_state()["performedSweeps"] % gint != 1:
+            step()
+            n += 1
+        return n
+
+    def global_moves_between(s0, s1):
+        return sum(1 for x in range(s0, s1) if x % gint == 0)
+
     # ---------------------------------------------------------------- value: stream resident in HBM
-    batch.rng_preload(W + K + 2)
+    batch.rng_preload(W + K + 2 + gint)
     for _ in range(W):
         step()
+    align()
+    sweeps0 = batch.sweep_state()["performedSweeps"]
     launches0 = batch.launch_count
     sampler = ClockSampler(local_rank)
     barrier()
@@ -258,10 +280,13 @@ def run_b200(args):
     clocks = sampler.stop()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     gpu_launches = batch.launch_count - launches0
+    gm_value = global_moves_between(sweeps0, batch.sweep_state()["performedSweeps"])
     batch.rng_release()
 
     # ---------------------------------------------------------------- e2e: host buffers every step
     step()                                                   # warm the non-resident path
+    align()
+    sweeps0 = batch.sweep_state()["performedSweeps"]
     barrier()
     t0 = time.perf_counter()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -271,12 +296,13 @@ def run_b200(args):
     f1.record(stream)
     barrier()
     wall_e2e = max_over_ranks(time.perf_counter() - t0)
+    gm_e2e = global_moves_between(sweeps0, batch.sweep_state()["performedSweeps"])
     rng_cap = batch.m * batch.N * (batch.opdim + 1)
     h2d = n_local * rng_cap * 8 + n_local * (8 + 840)
     d2h = n_local * (4 + 840) + 4 + world * lad.payload_len * 8
 
     # ---------------------------------------------------------------- per-kernel-family device time
-    lanes_default = int(os.environ.get("DQMC_LANES", "4" if n_local >= 32 else ("2" if n_local >= 8 else "1")))
+    lanes_default = int(os.environ.get("DQMC_LANES", str(min(n_local, 64))))
     batch.set_lanes(1)                                      # per-kernel times are only meaningful without overlap
     batch.profile_enable(True)
     acc0 = batch.accepted_total().astype(np.float64).sum()
@@ -378,7 +404,10 @@ def run_b200(args):
                        "cache": "working set per step (G, UDT storage, fields of %d replicas: %.1f GB) exceeds "
                                 "the 126 MB L2; no flush needed" % (n_local, n_local * (2 * 11 + 8) * D * D * 16 / 1e9),
                        "parallelism": "replicas partitioned contiguously, %d per GPU, issued as %d lanes (CUDA streams) per GPU"
-                                      % (n_local, lanes_default)},
+                                      % (n_local, lanes_default),
+                       "global_shift_moves_in_timed_steps": {"value": gm_value, "e2e": gm_e2e,
+                                                             "note": "every timed window starts one sweep after a "
+                                                                     "global-shift move (1 per %d sweeps)" % gint}},
             "clocks": clocks, "gpu_launches": int(gpu_launches),
             "e2e": {"value": P * K / wall_e2e, "unit": "replica-sweeps/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "device_ms_per_step": f0.elapsed_time(f1) / K},

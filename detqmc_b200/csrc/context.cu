@@ -1027,7 +1027,10 @@ int dqmc_create(const dqmc_params* params, int n_replicas, int device, dqmc_ctx*
         if (i > 0) CK(cudaStreamCreateWithFlags(&ctx->laneStream[i], cudaStreamNonBlocking));
     }
     {
-        int want = ctx->R >= 32 ? 4 : (ctx->R >= 8 ? 2 : 1);
+        // one lane per replica (up to DQMC_MAX_LANES): replicas of a lane advance in lockstep, so a round or a
+        // panel takes as long as its slowest replica; separate lanes remove that coupling and let the latency-
+        // bound kernels of one replica overlap with the throughput-bound kernels of the others
+        int want = std::min(ctx->R, DQMC_MAX_LANES);
         if (const char* e = std::getenv("DQMC_LANES")) want = std::atoi(e);
         want = std::max(1, std::min(want, std::min(DQMC_MAX_LANES, ctx->R)));
         ctx->nlanes = want;

@@ -11,7 +11,7 @@
 #include "../../include/dqmc_gpu.h"
 #include "rng_stream.h"
 
-#define DQMC_MAX_LANES 4
+#define DQMC_MAX_LANES 64
 
 namespace dqmc {
 

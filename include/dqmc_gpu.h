@@ -104,9 +104,11 @@ int dqmc_dims(const dqmc_ctx* ctx, int32_t* out);
  *                                         Householder QR with tensor-core trailing updates;
  *   DQMC_STAB_FULL_PIVOT                  Householder QR with full column pivoting, one CTA per matrix
  *                                         (slow; kept as the cross-check of the tests).
- * DQMC_OPT_LANES (1..4; default 4 for >= 32 replicas, 2 for >= 8, else 1): the replicas of a context are split into lanes whose
- * sweeps are issued on separate CUDA streams, so that the latency-bound kernels of one lane (sequential update
- * rounds, QR panels) overlap with the throughput-bound kernels of the other.  Results do not depend on it. */
+ * DQMC_OPT_LANES (1..64; default one lane per replica, at most 64): the replicas of a context are split into
+ * lanes whose sweeps are issued on separate CUDA streams (inside one CUDA graph).  Replicas of a lane advance in
+ * lockstep (a delayed-update round or a QR panel takes as long as its slowest replica); separate lanes remove
+ * that coupling and let the latency-bound kernels of one replica (sequential update rounds, QR panels) overlap
+ * with the throughput-bound kernels of the others.  Results do not depend on it. */
 enum { DQMC_OPT_STABILIZER = 0, DQMC_OPT_LANES = 1 };
 enum { DQMC_STAB_PREPIVOT_BLOCKED = 0, DQMC_STAB_FULL_PIVOT = 1 };
 int dqmc_set_option(dqmc_ctx* ctx, int option, int value);

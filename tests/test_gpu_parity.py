@@ -281,21 +281,25 @@ def test_batch_of_replicas_matches_single_replicas():
         assert b.control_data(rep).lastAccRatioLocal_phi == o.last_acc_ratio
 
 
-def test_two_lanes_equal_one_lane():
-    """Issuing the replicas as two lanes on two CUDA streams must not change any result."""
+def test_lanes_do_not_change_results():
+    """Issuing the replicas as lanes on separate CUDA streams (default: one lane per replica; here also an
+    uneven split into 3 lanes) must not change any result compared with a single lane."""
     from dqmc_oracle import SdwParams
     p = SdwParams(L=4, m=20, s=10)
     idx = list(range(1, 9))
-    b2 = make_batch(p, n_replicas=8, rng_indices=idx)
+    bd = make_batch(p, n_replicas=8, rng_indices=idx)         # default: 8 lanes
+    b3 = make_batch(p, n_replicas=8, rng_indices=idx)
+    b3.set_lanes(3)
     b1 = make_batch(p, n_replicas=8, rng_indices=idx)
     b1.set_lanes(1)
     for _ in range(3):
-        b1.sweepThermalization()
-        b2.sweepThermalization()
-    for rep in range(8):
-        assert maxabs(b1.phi(rep), b2.phi(rep)) == 0.0
-        assert maxabs(b1.green(rep), b2.green(rep)) == 0.0
-        assert b1.control_data(rep).lastAccRatioLocal_phi == b2.control_data(rep).lastAccRatioLocal_phi
+        for b in (b1, b3, bd):
+            b.sweepThermalization()
+    for b in (b3, bd):
+        for rep in range(8):
+            assert maxabs(b1.phi(rep), b.phi(rep)) == 0.0
+            assert maxabs(b1.green(rep), b.green(rep)) == 0.0
+            assert b1.control_data(rep).lastAccRatioLocal_phi == b.control_data(rep).lastAccRatioLocal_phi
 
 
 def test_global_shift_move_vs_oracle():

@@ -1031,6 +1031,7 @@ int dqmc_create(const dqmc_params* params, int n_replicas, int device, dqmc_ctx*
         // panel takes as long as its slowest replica; separate lanes remove that coupling and let the latency-
         // bound kernels of one replica overlap with the throughput-bound kernels of the others
         int want = std::min(ctx->R, DQMC_MAX_LANES);
+        gemm_set_matrices_in_flight(ctx->R * ctx->ngc);
         if (const char* e = std::getenv("DQMC_LANES")) want = std::atoi(e);
         want = std::max(1, std::min(want, std::min(DQMC_MAX_LANES, ctx->R)));
         ctx->nlanes = want;

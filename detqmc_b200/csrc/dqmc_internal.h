@@ -95,6 +95,7 @@ struct GemmArgs {
     int batch;
 };
 cudaError_t gemm_launch(const GemmArgs& g, cudaStream_t st);
+void gemm_set_matrices_in_flight(int n);   // tile-shape hint: matrices of all lanes that are in flight on the device
 
 // ------------------------------------------------------------------------------------------------
 // Pivoted Householder QR and friends (qr_kernels.cu)

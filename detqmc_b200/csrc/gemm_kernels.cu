@@ -343,10 +343,17 @@ cudaError_t launch_cfg(const GemmArgs& g, cudaStream_t st) {
 
 }  // namespace
 
+// Matrices in flight on the device (set by dqmc_create): with few of them a launch cannot fill the SMs with
+// 96-wide tiles (9 CTAs per 288 x 288 matrix), so smaller tiles are chosen -- more CTAs, shorter latency per
+// launch, same arithmetic in the same order (results do not depend on the tile shape).
+static int g_matrices_in_flight = 1 << 30;
+void gemm_set_matrices_in_flight(int n) { g_matrices_in_flight = n > 0 ? n : 1 << 30; }
+
 cudaError_t gemm_launch(const GemmArgs& g, cudaStream_t st) {
     if (g.batch <= 0 || g.M <= 0 || g.N <= 0) return cudaSuccess;
     if ((g.K <= KT || g.kvec) && !g.transa && !g.transb && g.beta == 1.0 && !g.rowscale && !g.colscale && !g.kscale) {
-        static const int cfg = std::getenv("DQMC_RANKUPD_CFG") ? std::atoi(std::getenv("DQMC_RANKUPD_CFG")) : 2;
+        static const int cfgEnv = std::getenv("DQMC_RANKUPD_CFG") ? std::atoi(std::getenv("DQMC_RANKUPD_CFG")) : 0;
+        const int cfg = cfgEnv ? cfgEnv : (g_matrices_in_flight <= 16 ? 1 : 2);
         if (g.M % 48 == 0 && g.N % 48 == 0 && cfg == 1) return launch_rank_update<2, 2, 3, 3>(g, st);   // 48 x 48
         if (g.M % 96 == 0 && g.N % 48 == 0 && cfg == 2) return launch_rank_update<4, 2, 3, 3>(g, st);   // 96 x 48
         if (g.M % 48 == 0 && g.N % 96 == 0 && cfg == 3) return launch_rank_update<2, 4, 3, 3>(g, st);   // 48 x 96
@@ -361,6 +368,10 @@ cudaError_t gemm_launch(const GemmArgs& g, cudaStream_t st) {
     if (g.kvec || g.b_kmajor) return cudaErrorInvalidValue;           // per-matrix K exists on the rank-update path only
     // 96 x 96 tiles when they fit the problem exactly (D = 288), otherwise 64 x 64; skinny shapes
     // (the panel products of the blocked QR / triangular solve) get 32 x 64 and 64 x 32 tiles
+    static const int smallEnv = std::getenv("DQMC_GEMM_SMALL") ? std::atoi(std::getenv("DQMC_GEMM_SMALL")) : -1;
+    const int small = smallEnv >= 0 ? smallEnv : (g_matrices_in_flight <= 8 ? 2 : 0);
+    if (small == 1 && g.M % 48 == 0 && g.N % 48 == 0 && g.K >= 64) return launch_cfg<2, 2, 3, 3>(g, st);   // 48 x 48, 4 warps
+    if (small == 2 && g.M % 96 == 0 && g.N % 48 == 0 && g.K >= 64) return launch_cfg<4, 2, 3, 3>(g, st);   // 96 x 48, 8 warps
     if (g.M % 96 == 0 && g.N % 96 == 0 && g.K >= 64) return launch_cfg<4, 3, 3, 4>(g, st);   // 12 warps, 24 x 32 each
     if (g.M <= 32 && g.N <= 32) return launch_cfg<1, 1, 4, 4>(g, st);
     static const int cfgw = std::getenv("DQMC_WGEMM_CFG") ? std::atoi(std::getenv("DQMC_WGEMM_CFG")) : 3;

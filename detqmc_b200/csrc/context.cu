@@ -1118,7 +1118,7 @@ void dqmc_destroy(dqmc_ctx* ctx) {
                    ctx->stQ, ctx->stT, ctx->stD, ctx->bkQ, ctx->bkT, ctx->bkD, ctx->phi, ctx->coshT, ctx->sinhT,
                    ctx->bkPhi, ctx->bkCosh, ctx->bkSinh, ctx->rvals, ctx->tau, ctx->perm, ctx->colnorm, ctx->vecA,
                    ctx->vecB, ctx->vecC, ctx->vecD, ctx->dtmp, ctx->logdet, ctx->bkLogdet, ctx->consistency, ctx->eyeM,
-                   ctx->onesV, ctx->X, ctx->Y, ctx->rngbuf, ctx->cursor, ctx->ctrl, ctx->accepted, ctx->errflag,
+                   ctx->onesV, ctx->X, ctx->Y, ctx->cfgStream, ctx->rngbuf, ctx->cursor, ctx->ctrl, ctx->accepted, ctx->errflag,
                    ctx->actions, ctx->shiftbuf, ctx->cbtab, ctx->acceptedTotal, ctx->siteState, ctx->kvec, ctx->aux,
                    ctx->propT, ctx->propTinv, ctx->hubScale, ctx->hubTmp, ctx->hubReal};
     for (void* p : dev) if (p) cudaFree(p);
@@ -1282,6 +1282,21 @@ int dqmc_download_fields(dqmc_ctx* ctx, int rep, void* fields) {
     }
     CK(cudaMemcpyAsync(fields, ctx->phi + size_t(rep) * phi_stride(ctx), sizeof(double) * phi_stride(ctx),
                        cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return DQMC_OK;
+}
+
+// getCurrentSystemConfiguration / saveConfigurationStream* (detsdwopdim.cpp:4943-5036, 5116-5122): the fields of
+// one replica (rep >= 0) or of all replicas (rep = -1, replica-major) in the order of the configuration streams
+int dqmc_download_config_stream(dqmc_ctx* ctx, int rep, double* out) {
+    if (!ctx || !out || rep < -1 || rep >= ctx->R) return DQMC_ERR_PARAM;
+    if (ctx->p.model != DQMC_MODEL_SDW) { ctx->err = "configuration streams are defined for DetSDW"; return DQMC_ERR_STATE; }
+    const size_t len = size_t(ctx->N) * ctx->m * ctx->opdim;
+    if (!ctx->cfgStream) CK(dmalloc(&ctx->cfgStream, len * ctx->R));
+    const int first = rep < 0 ? 0 : rep, count = rep < 0 ? ctx->R : 1;
+    CKL(launch_config_stream(ctx->phi + size_t(first) * phi_stride(ctx), ctx->cfgStream + size_t(first) * len, ctx->p.L, ctx->opdim,
+                             ctx->m, (long long)phi_stride(ctx), (long long)len, count, ctx->stream));
+    CK(cudaMemcpyAsync(out, ctx->cfgStream + size_t(first) * len, sizeof(double) * len * count, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return DQMC_OK;
 }

@@ -67,6 +67,8 @@ cudaError_t launch_shift_fields(double* phi, const double* shift, int N, int opd
 cudaError_t launch_phi_action(const double* phi, const double* rvals, double* out, int L, int opdim, int m,
                               double dtau, double c, double u, long long stridePhi, int batch,
                               cudaStream_t st);
+cudaError_t launch_config_stream(const double* phi, double* out, int L, int opdim, int m, long long stridePhi,
+                                 long long strideOut, int batch, cudaStream_t st);
 cudaError_t launch_exchange_action(const double* phi, double* out, int N, int opdim, int m, double dtau,
                                    long long stridePhi, int batch, cudaStream_t st);
 
@@ -249,6 +251,7 @@ struct dqmc_ctx {
     double* bkLogdet;
     double* consistency;   // [nmat]
     dqmc::cplx* X; dqmc::cplx* Y;   // [R][D*KMAX]
+    double* cfgStream;               // [R][N*m*opdim] configuration-stream staging (allocated on first use)
     int kmax;
     double* rngbuf;        // [R][rngCap]
     size_t rngCap;

@@ -31,7 +31,10 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 template <int WM, int WN, int MB, int NB>
 struct GemmCfg {
     static constexpr int TM = 8 * MB * WM, TN = 8 * NB * WN;
-    static constexpr int LDM = TM + 8, LDN = TN + 8;        // == 8 (mod 16): conflict-free fragment loads
+    // Leading dimensions == 4 or 12 (mod 16): the 16 lanes of a half warp (grp 0..3 x t4 0..3) read the doubles
+    // t4 * LD + grp, which then fall into 16 different 8-byte bank pairs (with LD == 8 (mod 16) rows t4 and t4 + 2
+    // collide: 2-way conflicts on every fragment load)
+    static constexpr int LDM = TM + 4, LDN = TN + 4;
     static constexpr int NT = 32 * WM * WN;
     static constexpr int A_PER = (TM * BK + NT - 1) / NT;
     static constexpr int B_PER = (TN * BK + NT - 1) / NT;
@@ -207,7 +210,7 @@ constexpr int KT = 32;
 template <int WM, int WN, int MB, int NB>
 __global__ void __launch_bounds__(32 * WM * WN, (WM * WN <= 4 ? 3 : (WM * WN <= 8 ? 2 : 1)))
 zgemm_rank_update_kernel(GemmArgs g) {
-    constexpr int TM = 8 * MB * WM, TN = 8 * NB * WN, LDM = TM + 8, LDN = TN + 8, NT = 32 * WM * WN;
+    constexpr int TM = 8 * MB * WM, TN = 8 * NB * WN, LDM = TM + 4, LDN = TN + 4, NT = 32 * WM * WN;
     extern __shared__ __align__(16) double smem[];
     double* As_re = smem;
     double* As_im = As_re + KT * LDM;
@@ -320,7 +323,7 @@ zgemm_rank_update_kernel(GemmArgs g) {
 template <int WM, int WN, int MB, int NB>
 cudaError_t launch_rank_update(const GemmArgs& g, cudaStream_t st) {
     constexpr int TM = 8 * MB * WM, TN = 8 * NB * WN;
-    const size_t smem = size_t(2) * KT * (TM + 8 + TN + 8) * sizeof(double);
+    const size_t smem = size_t(2) * KT * (TM + 4 + TN + 4) * sizeof(double);
     cudaError_t e = cudaFuncSetAttribute(zgemm_rank_update_kernel<WM, WN, MB, NB>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

@@ -146,6 +146,24 @@ __global__ void phi_action_kernel(const double* phi, const double* rvals, double
     if (threadIdx.x == 0) out[b] = acc;
 }
 
+// Configuration-stream order of the fields (DetSDW::saveConfigurationStreamBinary, detsdwopdim.cpp:5000-5010):
+// out[((ix*L + iy)*m + (k-1))*opdim + dim] = phi(site = iy*L + ix, dim, k), k = 1..m; one CTA row per replica.
+__global__ void config_stream_kernel(const double* __restrict__ phi, double* __restrict__ out, int L, int opdim, int m,
+                                     long long stridePhi, long long strideOut) {
+    const int N = L * L;
+    const double* p = phi + size_t(blockIdx.y) * stridePhi;
+    double* o = out + size_t(blockIdx.y) * strideOut;
+    const int total = N * m * opdim;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int dim = idx % opdim;
+        const int k = (idx / opdim) % m + 1;
+        const int col = idx / (opdim * m);          // ix*L + iy
+        const int ix = col / L, iy = col % L;
+        o[idx] = p[(size_t(k) * opdim + dim) * N + iy * L + ix];
+    }
+}
+
+
 // get_exchange_action_contribution (detsdwopdim.cpp:5204-5216)
 __global__ void exchange_action_kernel(const double* phi, double* out, int N, int opdim, int m, double dtau,
                                        long long stridePhi) {
@@ -225,6 +243,12 @@ cudaError_t launch_shift_fields(double* phi, const double* shift, int N, int opd
 cudaError_t launch_phi_action(const double* phi, const double* rvals, double* out, int L, int opdim, int m,
                               double dtau, double c, double u, long long stridePhi, int batch, cudaStream_t st) {
     phi_action_kernel<<<batch, 512, 0, st>>>(phi, rvals, out, L, opdim, m, dtau, c, u, stridePhi);
+    return cudaGetLastError();
+}
+cudaError_t launch_config_stream(const double* phi, double* out, int L, int opdim, int m, long long stridePhi,
+                                 long long strideOut, int batch, cudaStream_t st) {
+    dim3 grid(std::max(1, std::min(64, (L * L * m * opdim + 255) / 256)), batch);
+    config_stream_kernel<<<grid, 256, 0, st>>>(phi, out, L, opdim, m, stridePhi, strideOut);
     return cudaGetLastError();
 }
 cudaError_t launch_exchange_action(const double* phi, double* out, int N, int opdim, int m, double dtau,

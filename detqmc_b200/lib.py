@@ -38,6 +38,7 @@ SYMBOLS = [
     ("dqmc_synchronize", c_i32, [c_vp]),
     ("dqmc_dims", c_i32, [c_vp, _P(c_i32)]),
     ("dqmc_set_option", c_i32, [c_vp, c_i32, c_i32]),
+    ("dqmc_download_config_stream", c_i32, [c_vp, c_i32, c_vp]),
     ("dqmc_launch_count", c_u64, [c_vp]),
     ("dqmc_rng_seed", c_i32, [c_vp, c_i32, c_u32, c_u32]),
     ("dqmc_rng_set_source", c_i32, [c_vp, c_i32, c_vp, c_vp]),

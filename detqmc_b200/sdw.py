@@ -10,6 +10,7 @@ replicas partitioned contiguously over ranks: one all-gather of (action, look-ah
 replica 0) per exchange step, then the identical serial ladder walk on every rank.
 """
 import ctypes
+import os
 
 import numpy as np
 
@@ -136,6 +137,25 @@ class DetSDWBatch:
         phi = np.ascontiguousarray(phi, dtype=np.float64)
         assert phi.shape == (self.m + 1, self.opdim, self.N)
         self._ck(self.lib.dqmc_upload_fields(self.h, rep, _ptr(phi)))
+
+    # ------------------------------------------------------------------ configuration streams
+    def config_stream(self, rep=0):
+        """getCurrentSystemConfiguration in the order of the reference's configuration streams
+        (detsdwopdim.cpp:5000-5010): for ix, iy, k = 1..m, dim.  rep = -1: all replicas, shape [R][N*m*opdim]."""
+        n = self.N * self.m * self.opdim
+        out = np.zeros((self.R, n) if rep < 0 else n)
+        self._ck(self.lib.dqmc_download_config_stream(self.h, int(rep), _ptr(out)))
+        return out
+
+    def saveConfigurationStreamBinary(self, directory=".", rep=0):
+        """DetSDW::saveConfigurationStreamBinary (detsdwopdim.cpp:4991-5012): append to configs-phi.binarystream."""
+        with open(os.path.join(directory, "configs-phi.binarystream"), "ab") as f:
+            f.write(self.config_stream(rep).tobytes())
+
+    def saveConfigurationStreamText(self, directory=".", rep=0):
+        """DetSDW::saveConfigurationStreamText (detsdwopdim.cpp:4943-4966): precision 14, scientific, one value per line."""
+        with open(os.path.join(directory, "configs-phi.textstream"), "a") as f:
+            f.write("".join("%.14e\n" % v for v in self.config_stream(rep)))
 
     def green(self, rep=0):
         out = np.zeros((self.D, self.D), dtype=np.complex128, order="F")

@@ -87,6 +87,11 @@ int main(int argc, char** argv) {
         take(kv, pq.specified, "rngSeed", pq.rngSeed, uint32_t(1020304050));
         take(kv, pq.specified, "simindex", pq.simindex, uint32_t(0));
         take(kv, pq.specified, "timeseries", pq.timeseries, true);
+        if (kv.count("saveConfigurationStreamInterval")) {
+            take(kv, pq.specified, "saveConfigurationStreamInterval", pq.saveConfigurationStreamInterval, uint32_t(0));
+            take(kv, pq.specified, "saveConfigurationStreamText", pq.saveConfigurationStreamText, false);
+            take(kv, pq.specified, "saveConfigurationStreamBinary", pq.saveConfigurationStreamBinary, false);
+        }
         take(kv, pq.specified, "state", pq.stateFileName, std::string("simulation.state"));
         if (!kv.empty()) {
             std::cerr << "unknown option: " << kv.begin()->first << "\n";

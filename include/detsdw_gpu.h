@@ -21,6 +21,8 @@
 
 #include <cmath>
 #include <cstring>
+#include <fstream>
+#include <iostream>
 #include <memory>
 #include <string>
 #include <vector>
@@ -137,11 +139,48 @@ public:
     virtual std::vector<VectorObservable> getVectorObservables() { return std::vector<VectorObservable>(); }
     virtual std::vector<KeyValueObservable> getKeyValueObservables() { return std::vector<KeyValueObservable>(); }
 
-    // configuration streams: host I/O, outside the accelerated path
-    void saveConfigurationStreamText(const std::string& = ".") {}
-    void saveConfigurationStreamBinary(const std::string& = ".") {}
-    void saveConfigurationStreamTextHeader(const std::string&, const std::string& = ".") {}
-    void saveConfigurationStreamBinaryHeaderfile(const std::string&, const std::string& = ".") {}
+    // configuration streams (detsdwopdim.cpp:4943-5114): the device reorders the fields into the on-disk order
+    // (ix, iy, k, dim), the files are written exactly like the reference's (names, append mode, number format)
+    std::vector<double> currentConfigurationStream() {
+        std::vector<double> cfg(size_t(pars.L) * pars.L * pars.m * OPDIM);
+        check(dqmc_download_config_stream(ctx, 0, cfg.data()), "dqmc_download_config_stream");
+        return cfg;
+    }
+    void saveConfigurationStreamText(const std::string& directory = ".") {
+        const std::string path = directory + "/configs-phi.textstream";
+        std::ofstream out(path.c_str(), std::ios::app);
+        if (!out) { std::cerr << "Could not open file " << path << " for writing.\n"; return; }
+        out.precision(14);
+        out.setf(std::ios::scientific, std::ios::floatfield);
+        const std::vector<double> cfg = currentConfigurationStream();
+        for (size_t i = 0; i < cfg.size(); ++i) out << cfg[i] << "\n";
+        out.flush();
+    }
+    void saveConfigurationStreamBinary(const std::string& directory = ".") {
+        const std::string path = directory + "/configs-phi.binarystream";
+        std::ofstream out(path.c_str(), std::ios::binary | std::ios::app);
+        if (!out) { std::cerr << "Could not open file " << path << " for writing.\n"; return; }
+        const std::vector<double> cfg = currentConfigurationStream();
+        out.write(reinterpret_cast<const char*>(cfg.data()), std::streamsize(cfg.size() * sizeof(double)));
+        out.flush();
+    }
+    void saveConfigurationStreamTextHeader(const std::string& simInfoHeaderText, const std::string& directory = ".") {
+        const std::string path = directory + "/configs-phi.textstream";
+        if (std::ifstream(path.c_str())) return;               // only if the file does not exist yet (:5043)
+        std::ofstream out(path.c_str(), std::ios::out);
+        if (!out) { std::cerr << "Could not open file " << path << " for writing.\n"; return; }
+        out << simInfoHeaderText << "## phi configuration stream\n";
+        out.flush();
+    }
+    void saveConfigurationStreamBinaryHeaderfile(const std::string& simInfoHeaderText, const std::string& directory = ".") {
+        const std::string path = directory + "/configs-phi.infoheader";
+        if (std::ifstream(path.c_str())) return;
+        std::ofstream out(path.c_str(), std::ios::out);
+        if (!out) { std::cerr << "Could not open file " << path << " for writing.\n"; return; }
+        out << simInfoHeaderText
+            << "## binary phi configuration stream (64 bit double precision floats) in file configs-phi.binarystream\n";
+        out.flush();
+    }
 
     // replica exchange interface (detsdwopdim.cpp:5189-5242)
     num get_exchange_parameter_value() const {

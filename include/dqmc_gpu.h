@@ -143,6 +143,12 @@ int dqmc_init_random_fields(dqmc_ctx* ctx, int rep);
 /* phi (SDW; doubles) or auxfield (Hubbard; int32 +-1, layout [(m+1)][N]).  Host pointers. */
 int dqmc_upload_fields(dqmc_ctx* ctx, int rep, const void* fields);
 int dqmc_download_fields(dqmc_ctx* ctx, int rep, void* fields);
+/* getCurrentSystemConfiguration / saveConfigurationStreamBinary (detsdwopdim.cpp:5116-5122, 4991-5012;
+ * DetSDW_SystemConfig::write_to_disk_phi_binary, detsdwsystemconfig.cpp:123-134): the fields of replica `rep` in
+ * the order of the reference's configuration streams, out[((ix*L + iy)*m + (k-1))*opdim + dim] = phi(iy*L + ix, dim, k)
+ * for k = 1..m (N*m*opdim doubles, reordered on the device); rep = -1: all replicas, replica-major (what the
+ * parallel-tempering driver gathers per exchange-parameter index, detqmcpt.h:702-757). */
+int dqmc_download_config_stream(dqmc_ctx* ctx, int rep, double* out);
 /* g / green[gc] (detmodel.h:462): D*D values (complex interleaved for SDW, real for Hubbard). */
 int dqmc_download_green(dqmc_ctx* ctx, int rep, int gc, double* out);
 int dqmc_upload_green(dqmc_ctx* ctx, int rep, int gc, const double* in);

@@ -265,6 +265,31 @@ class SweepSkeleton:
         pass
 
 
+def config_stream(phi):
+    """One configuration in the order of the reference's configuration streams
+    (DetSDW::saveConfigurationStreamBinary, detsdwopdim.cpp:5000-5010; DetSDW_SystemConfig::write_to_disk_phi_*,
+    detsdwsystemconfig.cpp:100-134): for ix, for iy (site i = iy*L + ix), for k = 1..m, for dim: phi(i, dim, k).
+    `phi` is the [m+1][opdim][N] array of this module; returns a flat float64 array of N*m*opdim values."""
+    m1, opdim, N = phi.shape
+    L = int(round(np.sqrt(N)))
+    out = np.empty(N * (m1 - 1) * opdim)
+    pos = 0
+    for ix in range(L):
+        for iy in range(L):
+            i = iy * L + ix
+            for k in range(1, m1):
+                for dim in range(opdim):
+                    out[pos] = phi[k, dim, i]
+                    pos += 1
+    return out
+
+
+def config_stream_text(phi):
+    """The same configuration as the lines the text stream appends (precision 14, scientific:
+    detsdwopdim.cpp:4952-4960)."""
+    return "".join("%.14e\n" % v for v in config_stream(phi))
+
+
 class SdwParams:
     """Subset of ModelParamsDetSDW (detsdwparams.h:30-120) that the hot path reads; defaults follow
     maindetqmcsdwopdim.cpp:93-135 where the reference has any."""

@@ -47,6 +47,8 @@ def lib():
         l.ref_sdw_exchange_probability.argtypes = [c_f64] * 4
         l.ref_sdw_set_r.argtypes = [c_vp, c_f64]
         l.ref_sdw_set_phi_delta.argtypes = [c_vp, c_f64]
+        if hasattr(l, "ref_sdw_save_config_stream"):
+            l.ref_sdw_save_config_stream.argtypes = [c_vp, ctypes.c_char_p, ctypes.c_int]
         _lib = l
     return _lib
 
@@ -172,6 +174,12 @@ class RefSdw:
         sv = np.zeros(self.D)
         lib().ref_sdw_green_from_storage(self.h, c_u32(l_left), c_u32(l_right), _p(out), _p(sv))
         return out, sv
+
+
+    def save_config_stream(self, directory, binary=True):
+        """Append the current configuration to configs-phi.{binary,text}stream in `directory` with the
+        reference's own writers (detsdwopdim.cpp:4943-5036)."""
+        lib().ref_sdw_save_config_stream(self.h, str(directory).encode(), 1 if binary else 0)
 
 
 def exchange_probability(par1, a1, par2, a2):

@@ -104,6 +104,7 @@ struct SdwBase {
     virtual void green_for_timeslice(uint32_t k, double* out) = 0;
     virtual void get_udv(uint32_t l, double* U, double* d, double* Vt) = 0;
     virtual void green_from_storage(uint32_t l_left, uint32_t l_right, double* out, double* sv) = 0;
+    virtual void save_config_stream(const char* dir, int binary) = 0;
 };
 
 template <int OPDIM>
@@ -230,6 +231,11 @@ struct SdwImpl : public SdwBase {
         std::memcpy(d, st.d.memptr(), sizeof(double) * st.d.n_elem);
         std::memcpy(Vt, st.V_t.memptr(), sizeof(cpx_t) * st.V_t.n_elem);
     }
+    void save_config_stream(const char* dir, int binary) {
+        // the reference's own writers (detsdwopdim.cpp:4943-5036): append one configuration to the stream files
+        if (binary) rep->saveConfigurationStreamBinary(dir);
+        else rep->saveConfigurationStreamText(dir);
+    }
     void green_from_storage(uint32_t l_left, uint32_t l_right, double* out, double* sv) {
         // G = [1 + UdV_r * UdV_l]^-1 evaluated by the reference's greenFromUdV (detmodel.h:768-818)
         typename Model::MatData g;
@@ -330,6 +336,9 @@ void ref_sdw_green_from_storage(void* h, uint32_t ll, uint32_t lr, double* out, 
 }
 
 // exchange probability, detsdwopdim.cpp:5251-5264
+void ref_sdw_save_config_stream(void* h, const char* dir, int binary) {
+    static_cast<SdwBase*>(h)->save_config_stream(dir, binary);
+}
 double ref_sdw_exchange_probability(double par1, double action1, double par2, double action2) {
     return get_replica_exchange_probability<DetSDW<CB_ASSAAD_BERG, 2> >(par1, action1, par2, action2);
 }

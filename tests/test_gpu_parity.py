@@ -317,6 +317,33 @@ def test_global_shift_move_vs_oracle():
         assert abs(b.logdet() - np.log(o.green_inv_sv[0]).sum()) < 1e-9
 
 
+def test_config_stream_vs_golden(tmp_path):
+    """dqmc_download_config_stream and the stream writers of the mirror against the bytes / lines the reference's
+    own writers produced for the same fields (tests/golden/config_streams.npz, detsdwopdim.cpp:4943-5036)."""
+    import json
+    import os
+    from dqmc_oracle import SdwParams, config_stream
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "config_streams.npz"))
+    for tag in ("o2", "o3", "o2_L6"):
+        d = json.loads(str(g[tag + "_pars"]))
+        for key in ("N", "beta"):
+            d.pop(key, None)
+        p = SdwParams(**d)
+        b = make_batch(p, n_replicas=2, rng_indices=[1, 2])
+        b.set_phi(g[tag + "_phi"], rep=1)
+        want = np.frombuffer(g[tag + "_binary"].tobytes(), dtype=np.float64)
+        assert np.array_equal(b.config_stream(1), want)
+        assert np.array_equal(b.config_stream(0), config_stream(b.phi(0)))
+        both = b.config_stream(-1)
+        assert both.shape == (2, want.size) and np.array_equal(both[1], want) and np.array_equal(both[0], b.config_stream(0))
+        out = tmp_path / tag
+        out.mkdir()
+        b.saveConfigurationStreamBinary(str(out), rep=1)
+        b.saveConfigurationStreamText(str(out), rep=1)
+        assert open(str(out / "configs-phi.binarystream"), "rb").read() == g[tag + "_binary"].tobytes()
+        assert open(str(out / "configs-phi.textstream"), "rb").read() == g[tag + "_text"].tobytes()
+
+
 # ---------------------------------------------------------------- full-size checks
 @pytest.mark.parametrize("kw", [dict(L=12, m=100, s=10), dict(L=8, m=80, s=10)])
 def test_full_size_properties(kw):
@@ -360,19 +387,30 @@ def test_reference_driver_with_gpu_shim(tmp_path):
         pytest.skip("host/_build/detqmcsdw_gpu not built (needs the reference tree: make -C host)")
     therm, sweeps = 10, 10
     out = subprocess.run([exe, "L=4", "beta=2", "dtau=0.1", "s=10", "r=-1", "thermalization=%d" % therm,
-                          "sweeps=%d" % sweeps, "rngSeed=1020304050", "simindex=0"], cwd=str(tmp_path),
+                          "sweeps=%d" % sweeps, "rngSeed=1020304050", "simindex=0", "saveConfigurationStreamInterval=5",
+                          "saveConfigurationStreamBinary=1", "saveConfigurationStreamText=1"], cwd=str(tmp_path),
                          capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     series = [float(x) for x in open(os.path.join(str(tmp_path), "normMeanPhi.series")) if x.strip() and x[0] != "#"]
     assert len(series) == sweeps
+    from dqmc_oracle import config_stream, config_stream_text
     o = SdwOracle(SdwParams(L=4, m=20, s=10, r=-1.0))
     for _ in range(therm):
         o.sweep_thermalization()
-    ref = []
-    for _ in range(sweeps):
+    ref, cfg_bin, cfg_txt = [], [], ""
+    for sw in range(1, sweeps + 1):
         o.sweep()
         ref.append(float(np.linalg.norm(o.phi[1:].mean(axis=(0, 2)))))
+        if sw % 5 == 0:                                              # saveConfigurationStreamInterval (detqmc.h:484-491)
+            cfg_bin.append(config_stream(o.phi))
+            cfg_txt += config_stream_text(o.phi)
     assert np.allclose(series, ref, rtol=0, atol=2e-6)               # the driver writes 6 significant digits
+    # configuration streams written by the shim through dqmc_download_config_stream
+    got = np.fromfile(os.path.join(str(tmp_path), "configs-phi.binarystream"))
+    assert got.shape == (2 * 16 * 20 * 2,) and maxabs(got, np.concatenate(cfg_bin)) < 1e-13
+    lines = [x for x in open(os.path.join(str(tmp_path), "configs-phi.textstream")) if x[0] != "#"]
+    assert len(lines) == got.size and np.allclose([float(x) for x in lines], got, rtol=1e-13, atol=0)
+    assert "binary phi configuration stream" in open(os.path.join(str(tmp_path), "configs-phi.infoheader")).read()
     info = open(os.path.join(str(tmp_path), "info.dat")).read()
     assert "libdqmc_b200" in info
 

@@ -143,3 +143,15 @@ def test_replica_exchange_walk_properties():
     draws0 = rng.draws
     replica_exchange_walk(ladder, par_proc, proc_par, np.ones(P), rng.rand01)
     assert rng.draws == draws0
+
+
+def test_config_stream_order_vs_reference_bytes():
+    """The restated configuration-stream order (oracle config_stream / config_stream_text) reproduces the bytes and
+    lines written by the reference's own saveConfigurationStreamBinary / Text for the same fields."""
+    import os
+    from dqmc_oracle import config_stream, config_stream_text
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "config_streams.npz"))
+    for tag in ("o2", "o3", "o2_L6"):
+        phi = g[tag + "_phi"]
+        assert config_stream(phi).tobytes() == g[tag + "_binary"].tobytes()
+        assert config_stream_text(phi).encode() == g[tag + "_text"].tobytes()

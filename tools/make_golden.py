@@ -116,8 +116,33 @@ def exchange_fixture():
     np.savez_compressed(os.path.join(OUT, "exchange_probability.npz"), rows=np.array(rows))
 
 
+def config_stream_fixture():
+    """Configuration streams: fields after two thermalisation sweeps and the bytes / lines the
+    reference's own writers append for them (DetSDW::saveConfigurationStreamBinary / Text,
+    detsdwopdim.cpp:4943-5036)."""
+    import tempfile
+    d = {}
+    for tag, kw in (("o2", dict()), ("o3", dict(opdim=3, weakZflux=False)), ("o2_L6", dict(L=6, m=10, s=5, rngIndex=4))):
+        p = SdwParams(**kw)
+        rep = rb.RefSdw(p)
+        for _ in range(2):
+            rep.sweep(therm=True)
+        tmp = tempfile.mkdtemp()
+        rep.save_config_stream(tmp, True)
+        rep.save_config_stream(tmp, False)
+        d[tag + "_pars"] = pars_json(p)
+        d[tag + "_phi"] = rep.phi()
+        d[tag + "_binary"] = np.fromfile(os.path.join(tmp, "configs-phi.binarystream"), dtype=np.uint8)
+        d[tag + "_text"] = np.frombuffer(open(os.path.join(tmp, "configs-phi.textstream"), "rb").read(), dtype=np.uint8)
+    np.savez_compressed(os.path.join(OUT, "config_streams.npz"), **d)
+    print("config_streams done")
+
+
 if __name__ == "__main__":
     assert rb.available(), "build oracle/_ref first: make -C oracle"
+    if len(sys.argv) > 1 and sys.argv[1] == "config_streams":
+        config_stream_fixture()
+        sys.exit(0)
     rng_fixture()
     exchange_fixture()
     sdw_fixture("sdw_o2_flux_L4", 6, dict())
@@ -129,3 +154,4 @@ if __name__ == "__main__":
     sdw_fixture("sdw_o2_flux_L6", 2, dict(L=6, m=30, rngIndex=5), chain=(20, 10))
     hubbard_fixture("hubbard_L4_U4_b4", 6, dict())                      # BASELINE config C1
     hubbard_fixture("hubbard_L4_cb", 4, dict(checkerboard=True, U=6.0, mu=0.3, m=24, s=5))
+    config_stream_fixture()

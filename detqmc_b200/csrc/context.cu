@@ -701,13 +701,90 @@ int reupload_resident(dqmc_ctx* ctx) {
 }
 
 // attemptGlobalShiftMove for the whole batch, detsdwopdim.cpp:3564-3645
-int global_shift_move(dqmc_ctx* ctx, int32_t* accepted_out) {
+// buildAndFlipCluster (detsdwopdim.cpp:3805-3883) on the host copy `phi` ([m+1][opdim][N]) of one replica: reflect
+// phi -> phi - 2 (phi . rd) rd on a cluster grown from a random seed over space (XPLUS, XMINUS, YPLUS, YMINUS) and
+// time (PLUS, MINUS) bonds with p = 1 - exp(min(0, bond_arg)).  The draws come from the replica's host stream in the
+// reference's order: direction, seed slice, seed site, then one uniform per bond with bond_arg < 0 (LIFO stack).
+int build_and_flip_cluster(dqmc_ctx* ctx, RngStream& rng, double* phi, std::vector<unsigned char>& visited,
+                           std::vector<int>& stack) {
+    const int N = ctx->N, L = ctx->p.L, m = ctx->m, od = ctx->opdim;
+    const double dtau = ctx->p.dtau;
+    double rd[3] = {0, 0, 0};
+    if (od == 1) {
+        rd[0] = rng.draw() <= 0.5 ? -1.0 : 1.0;                            // randomDirection<1>, :3775-3785
+    } else if (od == 2) {
+        const double ang = rng.draw_range(0.0, 2.0 * M_PI);                // randPointOnCircle, rngwrapper.h:82-87
+        rd[0] = std::cos(ang); rd[1] = std::sin(ang);
+    } else {
+        const double ang = rng.draw_range(0.0, 2.0 * M_PI);                // randPointOnSphere, rngwrapper.h:70-80
+        const double costheta = rng.draw_range(-1.0, 1.0);
+        const double sintheta = std::sqrt(1.0 - costheta * costheta);
+        rd[0] = std::cos(ang) * sintheta; rd[1] = std::sin(ang) * sintheta; rd[2] = costheta;
+    }
+    auto at = [&](int site, int k, int d) -> double& { return phi[(size_t(k) * od + d) * N + site]; };
+    auto proj = [&](int site, int k) {
+        double v = 0;
+        for (int d = 0; d < od; ++d) v += at(site, k, d) * rd[d];
+        return v;
+    };
+    auto flip = [&](int site, int k) {
+        const double pr = proj(site, k);
+        for (int d = 0; d < od; ++d) at(site, k, d) = at(site, k, d) - 2.0 * pr * rd[d];
+    };
+    visited.assign(size_t(N) * (m + 1), 0);
+    stack.clear();
+    int k = 1 + int((m - 1 + 1.0) * rng.draw());                            // randInt(1, m), rngwrapper.h:66-68
+    int site = int((N - 1 + 1.0) * rng.draw());                             // randInt(0, N-1)
+    flip(site, k);
+    visited[size_t(k) * N + site] = 1;
+    stack.push_back(k * N + site);
+    int size = 1;
+    while (!stack.empty()) {
+        const int top = stack.back();
+        stack.pop_back();
+        site = top % N; k = top / N;
+        const int x = site % L, y = site / L;
+        const int nbs[4] = {y * L + (x + 1) % L, y * L + (x + L - 1) % L, ((y + 1) % L) * L + x, ((y + L - 1) % L) * L + x};
+        for (int d = 0; d < 4; ++d) {
+            const int nb = nbs[d];
+            if (visited[size_t(k) * N + nb]) continue;
+            const double bond = 2.0 * dtau * proj(site, k) * proj(nb, k);
+            if (bond < 0 && rng.draw() <= (1.0 - std::exp(bond))) {
+                flip(nb, k);
+                visited[size_t(k) * N + nb] = 1;
+                stack.push_back(k * N + nb);
+                ++size;
+            }
+        }
+        const int kns[2] = {k < m ? k + 1 : 1, k > 1 ? k - 1 : m};
+        for (int t = 0; t < 2; ++t) {
+            const int kn = kns[t];
+            if (visited[size_t(kn) * N + site]) continue;
+            const double bond = (2.0 / dtau) * proj(site, k) * proj(site, kn);
+            if (bond < 0 && rng.draw() <= (1.0 - std::exp(bond))) {
+                flip(site, kn);
+                visited[size_t(kn) * N + site] = 1;
+                stack.push_back(kn * N + site);
+                ++size;
+            }
+        }
+    }
+    return size;
+}
+
+// attemptGlobalShiftMove (kind 0, detsdwopdim.cpp:3564-3645), attemptWolffClusterUpdate (kind 1, :3487-3562) and
+// attemptWolffClusterShiftUpdate (kind 2, :3647-3748) for the whole batch.  The cluster construction works on the
+// fields (O(N m) per replica, host side, with the replica's own random-number stream); everything that costs
+// O(D^3) -- the full re-setup of the UDT storage and G -- is the batched device path.
+int global_move_kind(dqmc_ctx* ctx, int kind, int32_t* accepted_out) {
     const int R = ctx->R, D = ctx->D;
-    if (ctx->currentTimeslice != ctx->m) { ctx->err = "global shift: currentTimeslice != m"; return DQMC_ERR_STATE; }
+    if (ctx->currentTimeslice != ctx->m) { ctx->err = "global move: currentTimeslice != m"; return DQMC_ERR_STATE; }
     double* h = ctx->h_scalars;      // [0,R): old action, [R,2R): new action, [2R,3R) old logdet, [3R,4R) new
-    CKL(launch_phi_action(ctx->phi, ctx->rvals, ctx->actions, ctx->p.L, ctx->opdim, ctx->m, ctx->p.dtau, ctx->p.c,
-                          ctx->p.u, (long long)phi_stride(ctx), R, ctx->stream));
-    CK(cudaMemcpyAsync(h, ctx->actions, sizeof(double) * R, cudaMemcpyDeviceToHost, ctx->stream));
+    if (kind == 0) {
+        CKL(launch_phi_action(ctx->phi, ctx->rvals, ctx->actions, ctx->p.L, ctx->opdim, ctx->m, ctx->p.dtau, ctx->p.c,
+                              ctx->p.u, (long long)phi_stride(ctx), R, ctx->stream));
+        CK(cudaMemcpyAsync(h, ctx->actions, sizeof(double) * R, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     CK(cudaMemcpyAsync(h + 2 * R, ctx->logdet, sizeof(double) * R, cudaMemcpyDeviceToHost, ctx->stream));
     // backups (globalMoveStoreBackups, :3885-3900): copy the fields, swap everything that is recomputed
     CK(cudaMemcpyAsync(ctx->bkPhi, ctx->phi, sizeof(double) * phi_stride(ctx) * R, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -723,14 +800,37 @@ int global_shift_move(dqmc_ctx* ctx, int32_t* accepted_out) {
         CK(cudaMemcpyAsync(ctx->bkD, ctx->stD, sizeof(double) * size_t(std_stride(ctx)) * nm, cudaMemcpyDeviceToDevice, ctx->stream));
         CK(cudaMemcpyAsync(ctx->bkLogdet, ctx->logdet, sizeof(double) * nm, cudaMemcpyDeviceToDevice, ctx->stream));
     }
-    // addGlobalRandomDisplacement (:3755-3763): OPDIM draws of randRange(-phiDelta, +phiDelta)
-    for (int r = 0; r < R; ++r) {
-        const double pd = ctx->ctrl_host[r].phiDelta;
-        for (int d = 0; d < 3; ++d) h[4 * R + 3 * r + d] = 0.0;
-        for (int d = 0; d < ctx->opdim; ++d) h[4 * R + 3 * r + d] = ctx->rng[r].draw_range(-pd, +pd);
+    std::vector<double> clusterSize(R, 0.0);
+    if (kind != 0) {
+        // cluster flips on the host copy of the fields (repeatWolffPerSweep clusters per replica), then back to the device
+        const size_t ps = phi_stride(ctx);
+        std::vector<double> hphi(ps * R);
+        CK(cudaMemcpyAsync(hphi.data(), ctx->phi, sizeof(double) * ps * R, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        std::vector<unsigned char> visited;
+        std::vector<int> stack;
+        for (int r = 0; r < R; ++r)
+            for (int c = 0; c < std::max(1, ctx->p.repeatWolffPerSweep); ++c)
+                clusterSize[r] += build_and_flip_cluster(ctx, ctx->rng[r], hphi.data() + ps * r, visited, stack);
+        CK(cudaMemcpyAsync(ctx->phi, hphi.data(), sizeof(double) * ps * R, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));            // hphi goes out of scope
     }
-    CK(cudaMemcpyAsync(ctx->shiftbuf, h + 4 * R, sizeof(double) * 3 * R, cudaMemcpyHostToDevice, ctx->stream));
-    CKL(launch_shift_fields(ctx->phi, ctx->shiftbuf, ctx->N, ctx->opdim, ctx->m, (long long)phi_stride(ctx), R, ctx->stream));
+    if (kind == 2) {
+        // the bosonic action difference of the combined move is that of the shift alone (:3684-3692)
+        CKL(launch_phi_action(ctx->phi, ctx->rvals, ctx->actions, ctx->p.L, ctx->opdim, ctx->m, ctx->p.dtau, ctx->p.c,
+                              ctx->p.u, (long long)phi_stride(ctx), R, ctx->stream));
+        CK(cudaMemcpyAsync(h, ctx->actions, sizeof(double) * R, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (kind != 1) {
+        // addGlobalRandomDisplacement (:3755-3763): OPDIM draws of randRange(-phiDelta, +phiDelta)
+        for (int r = 0; r < R; ++r) {
+            const double pd = ctx->ctrl_host[r].phiDelta;
+            for (int d = 0; d < 3; ++d) h[4 * R + 3 * r + d] = 0.0;
+            for (int d = 0; d < ctx->opdim; ++d) h[4 * R + 3 * r + d] = ctx->rng[r].draw_range(-pd, +pd);
+        }
+        CK(cudaMemcpyAsync(ctx->shiftbuf, h + 4 * R, sizeof(double) * 3 * R, cudaMemcpyHostToDevice, ctx->stream));
+        CKL(launch_shift_fields(ctx->phi, ctx->shiftbuf, ctx->N, ctx->opdim, ctx->m, (long long)phi_stride(ctx), R, ctx->stream));
+    }
     CKL(launch_update_tables(ctx->phi, ctx->coshT, ctx->sinhT, ctx->N, ctx->opdim, ctx->m, ctx->p.lambda * ctx->p.dtau,
                              (long long)phi_stride(ctx), (long long)tab_stride(ctx), R, ctx->stream));
     RET(setup_storage(ctx, 0, R));
@@ -741,16 +841,19 @@ int global_shift_move(dqmc_ctx* ctx, int32_t* accepted_out) {
     CK(cudaStreamSynchronize(ctx->stream));
     const size_t dd = DD(ctx);
     for (int r = 0; r < R; ++r) {
-        const double probScalar = std::exp(-(h[R + r] - h[r]));
+        const double probScalar = kind == 1 ? 1.0 : std::exp(-(h[R + r] - h[r]));
         double probFermion = std::exp(h[3 * R + r] - h[2 * R + r]);
         if (ctx->opdim < 3) probFermion = probFermion * probFermion;
         const double prob = probScalar * probFermion;
         ctx->lastGlobalProb[r] = prob;
-        ctx->ctrl_host[r].attemptedGlobalShifts += 1;
+        double* ws = ctx->wolffStats.data() + 5 * r;      // attempted, accepted, attemptedShift, acceptedShift, added size
+        if (kind == 0) ctx->ctrl_host[r].attemptedGlobalShifts += 1;
+        else ws[kind == 1 ? 0 : 2] += 1;
         bool acc = prob >= 1.0 || ctx->rng[r].draw() < prob;
         if (accepted_out) accepted_out[r] = acc ? 1 : 0;
         if (acc) {
-            ctx->ctrl_host[r].acceptedGlobalShifts += 1;
+            if (kind == 0) ctx->ctrl_host[r].acceptedGlobalShifts += 1;
+            else { ws[kind == 1 ? 1 : 3] += 1; ws[4] += clusterSize[r]; }
         } else {
             // globalMoveRestoreBackups (:3902-3917) for this replica
             CK(cudaMemcpyAsync(ctx->phi + size_t(r) * phi_stride(ctx), ctx->bkPhi + size_t(r) * phi_stride(ctx),
@@ -930,7 +1033,13 @@ int dqmc_create(const dqmc_params* params, int n_replicas, int device, dqmc_ctx*
     if (p.weakZflux && p.opdim == 3) { ctx->err = "weakZflux is only supported for opdim < 3"; return DQMC_ERR_PARAM; }
     if (p.m < 2 || p.s < 1 || p.dtau <= 0) { ctx->err = "need m >= 2, s >= 1, dtau > 0"; return DQMC_ERR_PARAM; }
     if (p.delaySteps < 1 || p.delaySteps > p.L * p.L) { ctx->err = "delaySteps out of range"; return DQMC_ERR_PARAM; }
-    if (p.globalShift && p.globalUpdateInterval < 1) { ctx->err = "globalUpdateInterval must be >= 1"; return DQMC_ERR_PARAM; }
+    if ((p.globalShift || p.wolffClusterUpdate || p.wolffClusterShiftUpdate) && p.globalUpdateInterval < 1) {
+        ctx->err = "globalUpdateInterval must be >= 1"; return DQMC_ERR_PARAM;
+    }
+    if (p.wolffClusterShiftUpdate && (p.globalShift || p.wolffClusterUpdate)) {       // detsdwparams.cpp:94-96
+        ctx->err = "either the combined wolffClusterShiftUpdate or the individual global updates"; return DQMC_ERR_PARAM;
+    }
+    if (hub && (p.wolffClusterUpdate || p.wolffClusterShiftUpdate)) { ctx->err = "Wolff cluster moves are defined for DetSDW"; return DQMC_ERR_PARAM; }
     ctx->R = n_replicas;
     ctx->opdim = p.opdim;
     ctx->N = p.L * p.L;
@@ -1095,6 +1204,7 @@ int dqmc_create(const dqmc_params* params, int n_replicas, int device, dqmc_ctx*
     ctx->rng.resize(R);
     ctx->h_r.assign(R, p.r);
     ctx->lastGlobalProb.assign(R, 0.0);
+    ctx->wolffStats.assign(size_t(5) * R, 0.0);
     ctx->ctrl_host.resize(R);
     for (size_t r = 0; r < R; ++r) {
         ctx->rng[r].seed(0, (uint32_t)r);
@@ -1569,8 +1679,23 @@ int dqmc_global_shift_move(dqmc_ctx* ctx, int32_t* accepted) {
     if (!ctx) return DQMC_ERR_PARAM;
     RET(host_sync_rng(ctx));
     if (ctx->p.model != DQMC_MODEL_SDW) { ctx->err = "only defined for DetSDW"; return DQMC_ERR_STATE; }
-    RET(global_shift_move(ctx, accepted));
+    RET(global_move_kind(ctx, 0, accepted));
     CK(cudaStreamSynchronize(ctx->stream));
+    return DQMC_OK;
+}
+
+int dqmc_wolff_cluster_move(dqmc_ctx* ctx, int with_shift, int32_t* accepted) {
+    if (!ctx) return DQMC_ERR_PARAM;
+    RET(host_sync_rng(ctx));
+    if (ctx->p.model != DQMC_MODEL_SDW) { ctx->err = "only defined for DetSDW"; return DQMC_ERR_STATE; }
+    RET(global_move_kind(ctx, with_shift ? 2 : 1, accepted));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return DQMC_OK;
+}
+
+int dqmc_get_wolff_statistics(dqmc_ctx* ctx, int rep, double* out) {
+    if (!valid_rep(ctx, rep) || !out) return DQMC_ERR_PARAM;
+    for (int i = 0; i < 5; ++i) out[i] = ctx->wolffStats[size_t(5) * rep + i];
     return DQMC_OK;
 }
 
@@ -1591,13 +1716,17 @@ int dqmc_sweep(dqmc_ctx* ctx, int thermalization) {
         ctx->err = "resident random-number window too small for another sweep";
         return DQMC_ERR_STATE;
     }
-    const bool global_now = ctx->lastSweepDir == +1 && ctx->p.globalShift &&
+    const bool global_now = ctx->lastSweepDir == +1 &&
+                            (ctx->p.globalShift || ctx->p.wolffClusterUpdate || ctx->p.wolffClusterShiftUpdate) &&
                             (ctx->performedSweeps % ctx->p.globalUpdateInterval == 0);
     if (global_now) {
         // globalMove() before a down-sweep, detmodel.h:1422-1424 + detsdwopdim.cpp:3460-3485
         if (preloaded) RET(sync_resident_cursor(ctx));        // the host draws must come after the device's
         else RET(host_sync_rng(ctx));
-        RET(global_shift_move(ctx, nullptr));
+        // DetSDW::globalMove, detsdwopdim.cpp:3460-3485: shift, Wolff cluster, Wolff cluster + shift, in this order
+        if (ctx->p.globalShift) RET(global_move_kind(ctx, 0, nullptr));
+        if (ctx->p.wolffClusterUpdate) RET(global_move_kind(ctx, 1, nullptr));
+        if (ctx->p.wolffClusterShiftUpdate) RET(global_move_kind(ctx, 2, nullptr));
         if (preloaded) RET(reupload_resident(ctx));
     }
     if (!preloaded) RET(stream_begin_sweep(ctx));

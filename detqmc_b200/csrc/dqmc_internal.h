@@ -295,6 +295,7 @@ struct dqmc_ctx {
     int* h_err;
     uint32_t* h_acc;
     std::vector<double> lastGlobalProb;
+    std::vector<double> wolffStats;   // [R][5] attempted, accepted, attemptedShift, acceptedShift, addedWolffClusterSize
 
     // Hubbard
     int32_t* aux;          // [R][(m+1)*N]

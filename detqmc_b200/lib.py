@@ -19,7 +19,9 @@ class DqmcParams(ctypes.Structure):
                 ("globalUpdateInterval", c_i32), ("checkerboard", c_i32), ("reserved0", c_i32),
                 ("dtau", c_f64), ("r", c_f64), ("c", c_f64), ("u", c_f64), ("lambda_", c_f64),
                 ("txhor", c_f64), ("txver", c_f64), ("tyhor", c_f64), ("tyver", c_f64),
-                ("mux", c_f64), ("muy", c_f64), ("accRatio", c_f64), ("t", c_f64), ("U", c_f64), ("mu", c_f64)]
+                ("mux", c_f64), ("muy", c_f64), ("accRatio", c_f64), ("t", c_f64), ("U", c_f64), ("mu", c_f64),
+                ("wolffClusterUpdate", c_i32), ("wolffClusterShiftUpdate", c_i32), ("repeatWolffPerSweep", c_i32),
+                ("reserved1", c_i32)]
 
 
 class ControlData(ctypes.Structure):
@@ -39,6 +41,8 @@ SYMBOLS = [
     ("dqmc_dims", c_i32, [c_vp, _P(c_i32)]),
     ("dqmc_set_option", c_i32, [c_vp, c_i32, c_i32]),
     ("dqmc_download_config_stream", c_i32, [c_vp, c_i32, c_vp]),
+    ("dqmc_wolff_cluster_move", c_i32, [c_vp, c_i32, c_vp]),
+    ("dqmc_get_wolff_statistics", c_i32, [c_vp, c_i32, c_vp]),
     ("dqmc_launch_count", c_u64, [c_vp]),
     ("dqmc_rng_seed", c_i32, [c_vp, c_i32, c_u32, c_u32]),
     ("dqmc_rng_set_source", c_i32, [c_vp, c_i32, c_vp, c_vp]),

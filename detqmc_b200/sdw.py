@@ -21,6 +21,7 @@ OP_LEFT, OP_RIGHT, OP_LEFT_INV, OP_RIGHT_INV, OP_LEFT_ADJ = range(5)
 _DEFAULTS = dict(opdim=2, L=4, m=20, s=10, dtau=0.1, r=-1.0, c=3.0, u=1.0, lam=1.0, txhor=-1.0, txver=-0.5,
                  tyhor=0.5, tyver=1.0, cdwU=0.0, mu=-0.5, accRatio=0.5, weakZflux=True, bc=0, updateMethod=2,
                  delaySteps=16, globalShift=True, globalUpdateInterval=10, repeatUpdateInSlice=1,
+                 wolffClusterUpdate=False, wolffClusterShiftUpdate=False, repeatWolffPerSweep=1,
                  seed=1020304050, rngIndex=1)
 
 
@@ -49,6 +50,9 @@ def make_params(pars=None, **kw):
     p.delaySteps = d["delaySteps"] if d["updateMethod"] == 2 else 1     # woodbury == delayed with 1 step
     p.globalShift = int(bool(d["globalShift"]))
     p.globalUpdateInterval = d["globalUpdateInterval"]
+    p.wolffClusterUpdate = int(bool(d["wolffClusterUpdate"]))
+    p.wolffClusterShiftUpdate = int(bool(d["wolffClusterShiftUpdate"]))
+    p.repeatWolffPerSweep = int(d["repeatWolffPerSweep"])
     p.dtau, p.r, p.c, p.u, p.lambda_ = d["dtau"], d["r"], d["c"], d["u"], d["lam"]
     p.txhor, p.txver, p.tyhor, p.tyver = d["txhor"], d["txver"], d["tyhor"], d["tyver"]
     p.mux = p.muy = d["mu"]
@@ -273,6 +277,19 @@ class DetSDWBatch:
         acc = np.zeros(self.R, dtype=np.int32)
         self._ck(self.lib.dqmc_global_shift_move(self.h, _ptr(acc)))
         return acc
+
+    def wolff_cluster_move(self, with_shift=False):
+        """attemptWolffClusterUpdate / attemptWolffClusterShiftUpdate (detsdwopdim.cpp:3487-3562, 3647-3748) for every
+        replica; returns the per-replica accept flags."""
+        acc = np.zeros(self.R, dtype=np.int32)
+        self._ck(self.lib.dqmc_wolff_cluster_move(self.h, int(bool(with_shift)), _ptr(acc)))
+        return acc
+
+    def wolff_statistics(self, rep=0):
+        """(attempted, accepted, attemptedShift, acceptedShift, addedWolffClusterSize), detsdwopdim.h:285-299."""
+        out = np.zeros(5)
+        self._ck(self.lib.dqmc_get_wolff_statistics(self.h, int(rep), _ptr(out)))
+        return out
 
     def phi_action(self):
         out = np.zeros(self.R)

@@ -57,8 +57,6 @@ public:
             throw_GeneralError("DetSDWGpu: fermionic measurements are outside the accelerated path; set "
                                "turnoffFermionMeasurements");
         if (pars.cdwU != 0.0) throw_GeneralError("DetSDWGpu: cdwU != 0 is outside the accelerated path");
-        if (pars.wolffClusterUpdate || pars.wolffClusterShiftUpdate)
-            throw_GeneralError("DetSDWGpu: Wolff cluster moves are outside the accelerated path");
         if (pars.repeatUpdateInSlice != 1) throw_GeneralError("DetSDWGpu: repeatUpdateInSlice != 1 is not implemented");
         if (pars.updateMethod_string != "delayed" && pars.updateMethod_string != "woodbury")
             throw_GeneralError("DetSDWGpu: updateMethod must be delayed or woodbury");
@@ -75,6 +73,9 @@ public:
         p.weakZflux = pars.weakZflux ? 1 : 0;
         p.delaySteps = pars.updateMethod_string == "delayed" ? (int32_t)pars.delaySteps : 1;
         p.globalShift = pars.globalShift ? 1 : 0;
+        p.wolffClusterUpdate = pars.wolffClusterUpdate ? 1 : 0;
+        p.wolffClusterShiftUpdate = pars.wolffClusterShiftUpdate ? 1 : 0;
+        p.repeatWolffPerSweep = (int32_t)pars.repeatWolffPerSweep;
         p.globalUpdateInterval = (int32_t)pars.globalUpdateInterval;
         p.dtau = pars.dtau;
         p.r = pars.r; p.c = pars.c; p.u = pars.u; p.lambda = pars.lambda;
@@ -100,6 +101,16 @@ public:
         meta["phiDelta"] = numToString(cd.phiDelta);
         meta["globalShiftAccRatio"] =
             numToString(cd.attemptedGlobalShifts ? double(cd.acceptedGlobalShifts) / cd.attemptedGlobalShifts : 0.0);
+        double ws[5] = {0, 0, 0, 0, 0};                      // detsdwopdim.cpp:406-435
+        dqmc_get_wolff_statistics(ctx, 0, ws);
+        if (pars.wolffClusterUpdate) {
+            meta["wolffClusterUpdateAccRatio"] = numToString(ws[0] > 0 ? ws[1] / ws[0] : 0.0);
+            meta["averageAcceptedWolffClusterSize"] = numToString(ws[1] > 0 ? ws[4] / ws[1] : 0.0);
+        }
+        if (pars.wolffClusterShiftUpdate) {
+            meta["wolffClusterShiftUpdateAccRatio"] = numToString(ws[2] > 0 ? ws[3] / ws[2] : 0.0);
+            meta["averageAcceptedWolffClusterSize"] = numToString(ws[3] > 0 ? ws[4] / ws[3] : 0.0);
+        }
         meta["backend"] = "libdqmc_b200 (sm_100a)";
         return meta;
     }

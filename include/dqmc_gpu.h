@@ -70,6 +70,10 @@ typedef struct dqmc_params {
     double mux, muy;              /* SDW chemical potentials (the reference sets both to mu) */
     double accRatio;              /* SDW: target acceptance for the box-size adaptation */
     double t, U, mu;              /* Hubbard */
+    int32_t wolffClusterUpdate;       /* SDW: Wolff single-cluster moves every globalUpdateInterval sweeps */
+    int32_t wolffClusterShiftUpdate;  /* SDW: combined cluster + global shift move (excludes the two others) */
+    int32_t repeatWolffPerSweep;      /* SDW: clusters per attempt (0 or 1: one) */
+    int32_t reserved1;
 } dqmc_params;
 
 /* Per-replica control data that follows the exchange parameter in a replica exchange
@@ -216,6 +220,16 @@ int dqmc_update_slice(dqmc_ctx* ctx, uint32_t k, int thermalization, uint32_t* n
 /* attemptGlobalShiftMove() (detsdwopdim.cpp:3564-3645) for every replica; requires
  * currentTimeslice == m.  accepted (may be NULL): per-replica 0/1. */
 int dqmc_global_shift_move(dqmc_ctx* ctx, int32_t* accepted);
+/* attemptWolffClusterUpdate() (with_shift = 0, detsdwopdim.cpp:3487-3562) / attemptWolffClusterShiftUpdate()
+ * (with_shift = 1, :3647-3748) for every replica; requires currentTimeslice == m.  The cluster is grown on the fields
+ * on the host with the replica's random-number stream in the reference's order (buildAndFlipCluster, :3805-3883),
+ * the re-setup of the UDT storage and the Green's function runs batched on the device.  dqmc_sweep calls them from
+ * globalMove (:3460-3485) when the parameters ask for them.  accepted (may be NULL): per-replica 0/1. */
+int dqmc_wolff_cluster_move(dqmc_ctx* ctx, int with_shift, int32_t* accepted);
+/* UpdateStatistics of the cluster moves (detsdwopdim.h:285-299): out[0..4] = attemptedWolffClusterUpdates,
+ * acceptedWolffClusterUpdates, attemptedWolffClusterShiftUpdates, acceptedWolffClusterShiftUpdates,
+ * addedWolffClusterSize. */
+int dqmc_get_wolff_statistics(dqmc_ctx* ctx, int rep, double* out);
 /* phiAction() (detsdwopdim.cpp:4242-4299) per replica. */
 int dqmc_phi_action(dqmc_ctx* ctx, double* out);
 

@@ -314,6 +314,9 @@ class SdwParams:
         self.delaySteps = 16
         self.globalShift = True
         self.globalUpdateInterval = 10
+        self.wolffClusterUpdate = False
+        self.wolffClusterShiftUpdate = False
+        self.repeatWolffPerSweep = 1
         self.repeatUpdateInSlice = 1
         self.seed = 1020304050
         self.rngIndex = 1
@@ -347,6 +350,7 @@ class SdwOracle(SweepSkeleton):
         self.performed_sweeps = 0
         self.accepted_global_shifts = 0
         self.attempted_global_shifts = 0
+        self.wolff_stats = dict(attempted=0, accepted=0, attempted_shift=0, accepted_shift=0, added_size=0.0)
         self.decisions = None                                # optional per-proposal log
         self._setup_lattice()
         if phi is None:
@@ -659,9 +663,131 @@ class SdwOracle(SweepSkeleton):
     # ------------------------------------------------------------------ global shift move
     # globalMove, attemptGlobalShiftMove; detsdwopdim.cpp:3460-3485, 3564-3645, 3755-3763
     def global_move(self):
+        """DetSDW::globalMove, detsdwopdim.cpp:3460-3485: shift, Wolff cluster, Wolff cluster + shift, in this order."""
         p = self.p
-        if self.performed_sweeps % p.globalUpdateInterval == 0 and p.globalShift:
-            self.attempt_global_shift_move()
+        if self.performed_sweeps % p.globalUpdateInterval == 0:
+            if p.globalShift:
+                self.attempt_global_shift_move()
+            if p.wolffClusterUpdate:
+                self.attempt_wolff_cluster_update()
+            if p.wolffClusterShiftUpdate:
+                self.attempt_wolff_cluster_shift_update()
+
+    # ------------------------------------------------------------------ Wolff cluster moves, cpp:3487-3562, 3647-3883
+    def random_direction(self):
+        """randomDirection<OPDIM>::give, cpp:3766-3803 (rngwrapper.h:70-87)."""
+        od = self.p.opdim
+        if od == 1:
+            return np.array([-1.0 if self.rng.rand01() <= 0.5 else 1.0])
+        if od == 2:
+            ang = self.rng.rand_range(0.0, 2.0 * np.pi)
+            return np.array([np.cos(ang), np.sin(ang)])
+        ang = self.rng.rand_range(0.0, 2.0 * np.pi)
+        costheta = self.rng.rand_range(-1.0, 1.0)
+        sintheta = np.sqrt(1.0 - costheta * costheta)
+        return np.array([np.cos(ang) * sintheta, np.sin(ang) * sintheta, costheta])
+
+    def build_and_flip_cluster(self, update_cosh_sinh):
+        """buildAndFlipCluster, cpp:3805-3883: reflect phi -> phi - 2 (phi.rd) rd on a cluster grown from a random
+        seed (site, slice) over space (XPLUS, XMINUS, YPLUS, YMINUS) and time (PLUS, MINUS) bonds with
+        p = 1 - exp(min(0, bond_arg)); the stack is LIFO; a uniform is drawn only for bond_arg < 0."""
+        p = self.p
+        rd = self.random_direction()
+
+        def proj(site, k):
+            return float(self.phi[k, :, site] @ rd)
+
+        def flip(site, k):
+            ph = self.phi[k, :, site].copy()
+            self.phi[k, :, site] = ph - 2.0 * float(ph @ rd) * rd
+            if update_cosh_sinh:
+                c, x = self.cosh_sinh_term(self.phi[k][:, site:site + 1])
+                self.cosh_term[k][site] = c[0]
+                self.sinh_term[k][site] = x[0]
+
+        visited = np.zeros((p.N, p.m + 1), dtype=bool)
+        k = self.rng.rand_int(1, p.m)
+        site = self.rng.rand_int(0, p.N - 1)
+        flip(site, k)
+        visited[site, k] = True
+        stack = [(site, k)]
+        size = 1
+        while stack:
+            site, k = stack.pop()
+            for d in range(4):
+                nb = int(self.neigh[d, site])
+                if not visited[nb, k]:
+                    bond = 2.0 * p.dtau * proj(site, k) * proj(nb, k)
+                    if bond < 0 and self.rng.rand01() <= (1.0 - np.exp(bond)):
+                        flip(nb, k)
+                        visited[nb, k] = True
+                        stack.append((nb, k))
+                        size += 1
+            for kn in (k + 1 if k < p.m else 1, k - 1 if k > 1 else p.m):
+                if not visited[site, kn]:
+                    bond = (2.0 / p.dtau) * proj(site, k) * proj(site, kn)
+                    if bond < 0 and self.rng.rand01() <= (1.0 - np.exp(bond)):
+                        flip(site, kn)
+                        visited[site, kn] = True
+                        stack.append((site, kn))
+                        size += 1
+        return size
+
+    def _global_backup(self):
+        return (self.phi.copy(), self.cosh_term.copy(), self.sinh_term.copy(), self.green[0],
+                self.green_inv_sv[0], self.storage[0])
+
+    def _global_restore(self, backup):
+        (self.phi, self.cosh_term, self.sinh_term, self.green[0], self.green_inv_sv[0], self.storage[0]) = backup
+
+    def _fermion_ratio(self, old_sv):
+        log_prob = float(np.sum(np.log(self.green_inv_sv[0]) - np.log(old_sv)))
+        prob = np.exp(log_prob)
+        return prob ** 2 if self.p.opdim < 3 else prob
+
+    def attempt_wolff_cluster_update(self):
+        """attemptWolffClusterUpdate, cpp:3487-3562."""
+        p = self.p
+        assert self.current_timeslice == p.m
+        backup = self._global_backup()
+        old_sv = self.green_inv_sv[0]
+        sizes = [self.build_and_flip_cluster(True) for _ in range(p.repeatWolffPerSweep)]
+        self.setup_udv_storage_and_calculate_green()
+        prob = self._fermion_ratio(old_sv)
+        self.wolff_stats["attempted"] += 1
+        acc = prob >= 1.0 or self.rng.rand01() < prob
+        if acc:
+            self.wolff_stats["accepted"] += 1
+            self.wolff_stats["added_size"] += float(sum(sizes))
+        else:
+            self._global_restore(backup)
+        self.last_wolff = dict(prob=float(prob), sizes=sizes, accepted=bool(acc))
+
+    def attempt_wolff_cluster_shift_update(self):
+        """attemptWolffClusterShiftUpdate, cpp:3647-3748: cluster flips, then a global shift; the bosonic action
+        difference is that of the shift alone (the cluster flips are rejection free for the bosonic part)."""
+        p = self.p
+        assert self.current_timeslice == p.m
+        backup = self._global_backup()
+        old_sv = self.green_inv_sv[0]
+        sizes = [self.build_and_flip_cluster(False) for _ in range(p.repeatWolffPerSweep)]
+        old_action = self.phi_action()
+        for dim in range(p.opdim):
+            r = self.rng.rand_range(-self.phi_delta, +self.phi_delta)
+            self.phi[:, dim, :] += r
+        new_action = self.phi_action()
+        prob_scalar = np.exp(-(new_action - old_action))
+        self.update_cosh_sinh_terms()
+        self.setup_udv_storage_and_calculate_green()
+        prob = prob_scalar * self._fermion_ratio(old_sv)
+        self.wolff_stats["attempted_shift"] += 1
+        acc = prob >= 1.0 or self.rng.rand01() < prob
+        if acc:
+            self.wolff_stats["accepted_shift"] += 1
+            self.wolff_stats["added_size"] += float(sum(sizes))
+        else:
+            self._global_restore(backup)
+        self.last_wolff = dict(prob=float(prob), sizes=sizes, accepted=bool(acc))
 
     def attempt_global_shift_move(self):
         p = self.p

@@ -19,7 +19,8 @@ class RefSdwParams(ctypes.Structure):
                 ("cdwU", c_f64), ("mu", c_f64), ("accRatio", c_f64),
                 ("weakZflux", c_i32), ("bc", c_i32), ("updateMethod", c_i32), ("delaySteps", c_i32),
                 ("globalShift", c_i32), ("globalUpdateInterval", c_i32), ("repeatUpdateInSlice", c_i32),
-                ("seed", c_u32), ("rngIndex", c_u32)]
+                ("seed", c_u32), ("rngIndex", c_u32),
+                ("wolffClusterUpdate", c_i32), ("wolffClusterShiftUpdate", c_i32), ("repeatWolffPerSweep", c_i32)]
 
 
 class RefHubParams(ctypes.Structure):
@@ -77,7 +78,9 @@ def sdw_params_from(p):
     return RefSdwParams(p.opdim, p.L, p.m, p.s, p.dtau, p.r, p.c, p.u, p.lam, p.txhor, p.txver,
                         p.tyhor, p.tyver, p.cdwU, p.mu, p.accRatio, int(p.weakZflux), p.bc,
                         p.updateMethod, p.delaySteps, int(p.globalShift), p.globalUpdateInterval,
-                        p.repeatUpdateInSlice, p.seed, p.rngIndex)
+                        p.repeatUpdateInSlice, p.seed, p.rngIndex,
+                        int(getattr(p, "wolffClusterUpdate", False)), int(getattr(p, "wolffClusterShiftUpdate", False)),
+                        int(getattr(p, "repeatWolffPerSweep", 1)))
 
 
 class RefSdw:
@@ -175,6 +178,13 @@ class RefSdw:
         lib().ref_sdw_green_from_storage(self.h, c_u32(l_left), c_u32(l_right), _p(out), _p(sv))
         return out, sv
 
+
+    def attempt_wolff(self, shift=False):
+        """attemptWolffClusterUpdate / attemptWolffClusterShiftUpdate (detsdwopdim.cpp:3487-3562, 3647-3748); returns
+        the update statistics (attempted, accepted, attemptedShift, acceptedShift, addedWolffClusterSize)."""
+        st = np.zeros(5)
+        lib().ref_sdw_attempt_wolff(self.h, 1 if shift else 0, _p(st))
+        return st
 
     def save_config_stream(self, directory, binary=True):
         """Append the current configuration to configs-phi.{binary,text}stream in `directory` with the

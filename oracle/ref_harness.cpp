@@ -61,6 +61,9 @@ struct ref_sdw_params {
     int32_t repeatUpdateInSlice;
     uint32_t seed;
     uint32_t rngIndex;
+    int32_t wolffClusterUpdate;
+    int32_t wolffClusterShiftUpdate;
+    int32_t repeatWolffPerSweep;
 };
 
 struct ref_hub_params {
@@ -105,6 +108,7 @@ struct SdwBase {
     virtual void get_udv(uint32_t l, double* U, double* d, double* Vt) = 0;
     virtual void green_from_storage(uint32_t l_left, uint32_t l_right, double* out, double* sv) = 0;
     virtual void save_config_stream(const char* dir, int binary) = 0;
+    virtual void attempt_wolff(int shift, double* stats) = 0;
 };
 
 template <int OPDIM>
@@ -136,8 +140,12 @@ struct SdwImpl : public SdwBase {
         SETP(checkerboard, true);
         SETP(delaySteps, (uint32_t)p.delaySteps);
         SETP(globalShift, p.globalShift != 0);
-        SETP(wolffClusterUpdate, false);
-        SETP(wolffClusterShiftUpdate, false);
+        SETP(wolffClusterUpdate, p.wolffClusterUpdate != 0);
+        SETP(wolffClusterShiftUpdate, p.wolffClusterShiftUpdate != 0);
+        if (p.repeatWolffPerSweep > 1) {
+            pars.repeatWolffPerSweep_string = std::to_string((long long)p.repeatWolffPerSweep);
+            pars.specified.insert("repeatWolffPerSweep");
+        }
         SETP(globalUpdateInterval, (uint32_t)p.globalUpdateInterval);
         SETP(repeatUpdateInSlice, (uint32_t)p.repeatUpdateInSlice);
         SETP(turnoffFermionMeasurements, true);
@@ -230,6 +238,16 @@ struct SdwImpl : public SdwBase {
         std::memcpy(U, st.U.memptr(), sizeof(cpx_t) * st.U.n_elem);
         std::memcpy(d, st.d.memptr(), sizeof(double) * st.d.n_elem);
         std::memcpy(Vt, st.V_t.memptr(), sizeof(cpx_t) * st.V_t.n_elem);
+    }
+    void attempt_wolff(int shift, double* stats) {
+        // attemptWolffClusterUpdate / attemptWolffClusterShiftUpdate (detsdwopdim.cpp:3487-3562, 3647-3748)
+        if (shift) rep->attemptWolffClusterShiftUpdate();
+        else rep->attemptWolffClusterUpdate();
+        stats[0] = rep->us.attemptedWolffClusterUpdates;
+        stats[1] = rep->us.acceptedWolffClusterUpdates;
+        stats[2] = rep->us.attemptedWolffClusterShiftUpdates;
+        stats[3] = rep->us.acceptedWolffClusterShiftUpdates;
+        stats[4] = rep->us.addedWolffClusterSize;
     }
     void save_config_stream(const char* dir, int binary) {
         // the reference's own writers (detsdwopdim.cpp:4943-5036): append one configuration to the stream files
@@ -336,6 +354,10 @@ void ref_sdw_green_from_storage(void* h, uint32_t ll, uint32_t lr, double* out, 
 }
 
 // exchange probability, detsdwopdim.cpp:5251-5264
+void ref_sdw_attempt_wolff(void* h, int shift, double* stats) {
+    CoutSilencer q;
+    static_cast<SdwBase*>(h)->attempt_wolff(shift, stats);
+}
 void ref_sdw_save_config_stream(void* h, const char* dir, int binary) {
     static_cast<SdwBase*>(h)->save_config_stream(dir, binary);
 }

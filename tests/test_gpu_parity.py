@@ -12,7 +12,8 @@ from helpers import load_golden, sdw_params_of, maxabs, relerr
 
 pytestmark = pytest.mark.gpu
 
-SDW_CASES = ["sdw_o2_flux_L4", "sdw_o2_noflux_apbcxy_L4", "sdw_o3_L4", "sdw_o1_apbcx_L4",
+SDW_CASES = ["sdw_o2_wolff_L4", "sdw_o2_wolffshift_L4",
+             "sdw_o2_flux_L4", "sdw_o2_noflux_apbcxy_L4", "sdw_o3_L4", "sdw_o1_apbcx_L4",
              "sdw_o2_flux_L4_delay3_s7", "sdw_o2_flux_L6"]
 
 TOL_G = 1e-10
@@ -315,6 +316,33 @@ def test_global_shift_move_vs_oracle():
         assert maxabs(b.phi()[1:], o.phi[1:]) < 1e-13
         assert relerr(b.green(), o.green[0]) < TOL_G
         assert abs(b.logdet() - np.log(o.green_inv_sv[0]).sum()) < 1e-9
+
+
+def test_wolff_cluster_moves_vs_reference_record():
+    """dqmc_wolff_cluster_move against the record of the reference's own attemptWolffClusterUpdate /
+    attemptWolffClusterShiftUpdate (tests/golden/wolff_moves.npz): identical clusters (fields),
+    accept decisions and statistics, Green's function within 1e-10, same position of the random-number stream."""
+    import json
+    import os
+    from dqmc_oracle import SdwParams
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "wolff_moves.npz"))
+    for tag in ("o2", "o2_shift", "o3_rep2", "o1"):
+        d = json.loads(str(g[tag + "_pars"]))
+        for key in ("N", "beta"):
+            d.pop(key, None)
+        p = SdwParams(**d)
+        b = make_batch(p, n_replicas=2, rng_indices=[p.rngIndex, p.rngIndex + 10])
+        shift = bool(g[tag + "_shift"])
+        prev = np.zeros(5)
+        for it in range(g[tag + "_phi"].shape[0]):
+            acc = b.wolff_cluster_move(shift)
+            st = g[tag + "_stats"][it]
+            assert list(b.wolff_statistics(0)) == list(st)
+            assert bool(acc[0]) == bool((st - prev)[3 if shift else 1])
+            prev = st
+            assert maxabs(b.phi(0)[1:], g[tag + "_phi"][it][1:]) < 1e-13
+            assert relerr(b.green(0), g[tag + "_green"][it]) < TOL_G
+        assert maxabs(b.rng_draw(4, rep=0), g[tag + "_rng_next"]) == 0.0
 
 
 def test_config_stream_vs_golden(tmp_path):

@@ -7,7 +7,8 @@ from dqmc_oracle import (SdwOracle, HubbardOracle, exchange_probability, replica
 from dsfmt_oracle import RngOracle
 from helpers import load_golden, sdw_params_of, hubbard_params_of, maxabs
 
-SDW_CASES = ["sdw_o2_flux_L4", "sdw_o2_noflux_apbcxy_L4", "sdw_o3_L4", "sdw_o1_apbcx_L4",
+SDW_CASES = ["sdw_o2_wolff_L4", "sdw_o2_wolffshift_L4",
+             "sdw_o2_flux_L4", "sdw_o2_noflux_apbcxy_L4", "sdw_o3_L4", "sdw_o1_apbcx_L4",
              "sdw_o2_flux_L4_delay3_s7", "sdw_o2_flux_L6"]
 
 
@@ -155,3 +156,30 @@ def test_config_stream_order_vs_reference_bytes():
         phi = g[tag + "_phi"]
         assert config_stream(phi).tobytes() == g[tag + "_binary"].tobytes()
         assert config_stream_text(phi).encode() == g[tag + "_text"].tobytes()
+
+
+def test_wolff_cluster_moves_vs_reference_record():
+    """attemptWolffClusterUpdate / attemptWolffClusterShiftUpdate of the oracle against the record of the reference's
+    own moves (tests/golden/wolff_moves.npz): fields, Green's function, statistics and the position of the
+    random-number stream after six attempts, for O(1), O(2), O(3), two clusters per attempt, and the shift variant."""
+    import json
+    import os
+    from dqmc_oracle import SdwParams
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "wolff_moves.npz"))
+    for tag in ("o2", "o2_shift", "o3_rep2", "o1"):
+        d = json.loads(str(g[tag + "_pars"]))
+        for key in ("N", "beta"):
+            d.pop(key, None)
+        o = SdwOracle(SdwParams(**d))
+        shift = bool(g[tag + "_shift"])
+        for it in range(g[tag + "_phi"].shape[0]):
+            if shift:
+                o.attempt_wolff_cluster_shift_update()
+            else:
+                o.attempt_wolff_cluster_update()
+            st = g[tag + "_stats"][it]
+            ws = o.wolff_stats
+            assert [ws["attempted"], ws["accepted"], ws["attempted_shift"], ws["accepted_shift"], ws["added_size"]] == list(st)
+            assert maxabs(o.phi[1:], g[tag + "_phi"][it][1:]) < 1e-13
+            assert maxabs(o.green[0], g[tag + "_green"][it]) < 1e-10
+        assert maxabs([o.rng.rand01() for _ in range(4)], g[tag + "_rng_next"]) == 0.0

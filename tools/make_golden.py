@@ -116,6 +116,34 @@ def exchange_fixture():
     np.savez_compressed(os.path.join(OUT, "exchange_probability.npz"), rows=np.array(rows))
 
 
+def wolff_fixture():
+    """Wolff cluster moves: attemptWolffClusterUpdate / attemptWolffClusterShiftUpdate
+    (detsdwopdim.cpp:3487-3562, 3647-3883) called directly on a freshly set-up replica, fields / statistics /
+    Green's function recorded after every attempt."""
+    d = {}
+    cases = (("o2", dict(wolffClusterUpdate=True), False),
+             ("o2_shift", dict(wolffClusterShiftUpdate=True, globalShift=False, rngIndex=2), True),
+             ("o3_rep2", dict(wolffClusterUpdate=True, opdim=3, weakZflux=False, repeatWolffPerSweep=2), False),
+             ("o1", dict(wolffClusterUpdate=True, opdim=1, weakZflux=False, rngIndex=3), False))
+    for tag, kw, shift in cases:
+        p = SdwParams(**kw)
+        rep = rb.RefSdw(p)
+        n = 6
+        phis, stats, greens = [], [], []
+        for _ in range(n):
+            stats.append(rep.attempt_wolff(shift))
+            phis.append(rep.phi())
+            greens.append(rep.green())
+        d[tag + "_pars"] = pars_json(p)
+        d[tag + "_shift"] = int(shift)
+        d[tag + "_phi"] = np.array(phis)
+        d[tag + "_stats"] = np.array(stats)
+        d[tag + "_green"] = np.array(greens)
+        d[tag + "_rng_next"] = rep.rng_draw(4)
+    np.savez_compressed(os.path.join(OUT, "wolff_moves.npz"), **d)
+    print("wolff_moves done")
+
+
 def config_stream_fixture():
     """Configuration streams: fields after two thermalisation sweeps and the bytes / lines the
     reference's own writers append for them (DetSDW::saveConfigurationStreamBinary / Text,
@@ -140,8 +168,18 @@ def config_stream_fixture():
 
 if __name__ == "__main__":
     assert rb.available(), "build oracle/_ref first: make -C oracle"
+
+    def wolff_all():
+        wolff_fixture()
+        sdw_fixture("sdw_o2_wolff_L4", 6, dict(wolffClusterUpdate=True, globalUpdateInterval=2, rngIndex=6))
+        sdw_fixture("sdw_o2_wolffshift_L4", 6, dict(wolffClusterShiftUpdate=True, globalShift=False, globalUpdateInterval=2,
+                                                    rngIndex=7))
+
     if len(sys.argv) > 1 and sys.argv[1] == "config_streams":
         config_stream_fixture()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "wolff":
+        wolff_all()
         sys.exit(0)
     rng_fixture()
     exchange_fixture()
@@ -155,3 +193,4 @@ if __name__ == "__main__":
     hubbard_fixture("hubbard_L4_U4_b4", 6, dict())                      # BASELINE config C1
     hubbard_fixture("hubbard_L4_cb", 4, dict(checkerboard=True, U=6.0, mu=0.3, m=24, s=5))
     config_stream_fixture()
+    wolff_all()

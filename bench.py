@@ -219,7 +219,11 @@ def run_b200(args):
     n_local = P // world
     vals = ladder_values(P)
     lo = rank * n_local
-    stream = torch.cuda.current_stream()
+    # one explicit CUDA stream for the library's kernels AND torch's copies, collectives and timing events: torch's
+    # default stream has the handle 0, which dqmc_set_stream reads as "own stream" -- the exchange payload copy and
+    # the all-gather would then not be ordered after the kernel that packs the payload
+    stream = torch.cuda.Stream(device=local_rank)
+    torch.cuda.set_stream(stream)
 
     # DetQMCPT seeds rank p with RngWrapper(seed, (simindex+1)*(p+1)) (detqmcpt.h:301)
     batch = DetSDWBatch(dict(WORKLOAD), n_replicas=n_local, device=local_rank,

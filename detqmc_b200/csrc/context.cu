@@ -587,7 +587,10 @@ int stream_begin_sweep(dqmc_ctx* ctx) {
     }
     const size_t need = ctx->rngResidentUsedBound + ctx->rngCap;
     if (ctx->rngUploaded < need) {
-        // not prefetched (first sweep after a restart): upload on the main stream
+        // not (completely) prefetched -- the first sweep after a restart, or an exchange step consumed look-ahead
+        // uniforms so that the bound moved past the prefetched chunk: upload the remainder on the main stream.  The
+        // chunk that is still in flight on the copy stream must land before the sweep reads it.
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->copyEvent[ctx->copyHalf ^ 1], 0));
         CK(cudaEventSynchronize(ctx->copyEvent[ctx->copyHalf]));
         RET(stream_chunk_upload(ctx, ctx->rngUploaded, need - ctx->rngUploaded, ctx->stream, ctx->copyHalf));
         CK(cudaEventRecord(ctx->copyEvent[ctx->copyHalf], ctx->stream));

@@ -1,0 +1,212 @@
+"""DetQMCPT without MPI: the parallel-tempering driver loop of the reference (DetQMCPT<Model, ModelParams>::run,
+detqmcpt.h:760-958) over replicas batched per GPU, SURVEY.md section 8(f) row 4.
+
+One process per GPU (torchrun) holds P / world replicas of the ladder in one DetSDWBatch; per exchange step the
+actions, the look-ahead uniforms of replica 0 and the control blobs are packed on the device, all-gathered
+(torch.distributed: NCCL over NVLink on the GPUs, gloo in the CPU tests of the host logic) and every rank performs the
+identical serial ladder walk (ReplicaExchangeLadder).  Observables are recorded per CONTROL-PARAMETER index, as the
+reference's ScalarObservableHandlerPT does (mpiobservablehandlerpt.cpp:80-192): a replica contributes to the series of
+the parameter it currently holds.  Output layout follows the reference: one sub-directory
+p<index>_<name><value> per control parameter (detqmcpt.h:655-660) with <observable>.series, results.values and the
+configuration streams, plus exchange-parameters.values / exchange-acceptance.values / exchange-diffusion.values
+(detqmcpt.h:596-651) in the working directory.
+
+Only bosonic observables are measured (normMeanPhi, meanPhiSquared, phiAction: what include/detsdw_gpu.h measures);
+fermionic measurements are row 1 of section 8(f).
+"""
+import os
+
+import numpy as np
+
+from .sdw import DetSDWBatch, ReplicaExchangeLadder
+
+OBSERVABLES = ("normMeanPhi", "meanPhiSquared", "phiAction")
+
+
+def num_to_string(v):
+    """tools.h:46-50 numToString: default ostream formatting (6 significant digits)."""
+    return "%g" % v
+
+
+def bosonic_observables(phi, phi_action, N, m):
+    """DetSDWGpu::measureBosonic (include/detsdw_gpu.h): norm of the mean field, mean squared field, action per
+    site and slice.  phi: [m+1][opdim][N]."""
+    mean = phi[1:].mean(axis=(0, 2))
+    return {"normMeanPhi": float(np.sqrt(np.sum(mean * mean))),
+            "meanPhiSquared": float(np.sum(phi[1:] ** 2) / (N * m)),
+            "phiAction": float(phi_action) / (N * m)}
+
+
+class DetQMCPT:
+    def __init__(self, model_pars, control_values, thermalization, sweeps, measureInterval=1, exchangeInterval=1,
+                 saveConfigurationStreamInterval=0, saveConfigurationStreamBinary=False,
+                 saveConfigurationStreamText=False, rngSeed=1020304050, simindex=0, outdir=".",
+                 controlParameterName="r", device=None, make_batch=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.values = np.ascontiguousarray(control_values, dtype=np.float64)
+        self.P = len(self.values)
+        if controlParameterName != "r":
+            raise ValueError("DetSDW exchanges the parameter r (detsdwopdim.cpp:5199-5202)")
+        if self.P % self.world:
+            raise ValueError("the ladder must divide evenly over the ranks")
+        self.n_local = self.P // self.world
+        self.lo = self.rank * self.n_local
+        self.thermalization, self.sweeps = int(thermalization), int(sweeps)
+        self.measureInterval, self.exchangeInterval = int(measureInterval), int(exchangeInterval)
+        self.cfgInterval = int(saveConfigurationStreamInterval)
+        self.cfgBinary, self.cfgText = bool(saveConfigurationStreamBinary), bool(saveConfigurationStreamText)
+        self.outdir = outdir
+        self.name = controlParameterName
+        pars = dict(model_pars if isinstance(model_pars, dict) else vars(model_pars))
+        pars["seed"] = rngSeed
+        # DetQMCPT seeds process p with RngWrapper(rngSeed, (simindex + 1) * (p + 1)) (detqmcpt.h:301)
+        idx = [(simindex + 1) * (self.lo + i + 1) for i in range(self.n_local)]
+        if device is None:
+            device = int(os.environ.get("LOCAL_RANK", "0"))
+        # one explicit CUDA stream shared by the library's kernels and torch's copies / collectives (torch's default
+        # stream has the handle 0, which dqmc_set_stream reads as "own stream": the two would not be ordered)
+        torch.cuda.set_device(device)
+        stream = torch.cuda.Stream(device=device)
+        make = make_batch or DetSDWBatch
+        self.batch = make(pars, n_replicas=self.n_local, device=device, rng_indices=idx,
+                          r_values=self.values[self.lo:self.lo + self.n_local], stream=stream.cuda_stream)
+        self.stream = stream
+        self.ladder = ReplicaExchangeLadder(self.values, self.n_local, self.rank, self.world)
+        L = self.ladder
+        self.payload = torch.zeros(L.payload_len, dtype=torch.float64, device="cuda")
+        self.gathered = torch.zeros(self.world * L.payload_len, dtype=torch.float64, device="cuda")
+        self.host_gathered = torch.zeros(self.world * L.payload_len, dtype=torch.float64).pin_memory()
+        torch.cuda.synchronize()
+        self.sweepsDone = 0
+        self.sweepsDoneThermalization = 0
+        self.swCounter = 0
+        # local records: (sweep index, control-parameter index, {observable: value}) and buffered configurations
+        self.records = []
+        self.configs = []
+
+    # ------------------------------------------------------------------ replicaExchangeStep, detqmcpt.h:962-1118
+    def replica_exchange_step(self):
+        L = self.ladder
+        self.batch.exchange_pack(self.payload.data_ptr(), L.n_uniforms)
+        with self.torch.cuda.stream(self.stream):
+            if self.world > 1:
+                self.dist.all_gather_into_tensor(self.gathered, self.payload)
+                self.host_gathered.copy_(self.gathered, non_blocking=True)
+            else:
+                self.host_gathered.copy_(self.payload, non_blocking=True)
+        self.stream.synchronize()
+        r_new, ctrl_new, used = L.walk(self.host_gathered.numpy())
+        self.batch.exchange_apply(r_new, ctrl_new, used)
+
+    def local_parameter_indices(self):
+        return self.ladder.process_par[self.lo:self.lo + self.n_local].copy()
+
+    def _measure(self):
+        b = self.batch
+        actions = b.phi_action()
+        cpis = self.local_parameter_indices()
+        for i in range(self.n_local):
+            self.records.append((self.sweepsDone, int(cpis[i]), bosonic_observables(b.phi(i), actions[i], b.N, b.m)))
+
+    def _buffer_configurations(self):
+        # buffer_local_system_configuration, detqmcpt.h:690-700: the configuration goes to the stream of the control
+        # parameter the replica holds NOW
+        streams = self.batch.config_stream(-1)
+        cpis = self.local_parameter_indices()
+        for i in range(self.n_local):
+            self.configs.append((int(cpis[i]), streams[i].copy()))
+
+    # ------------------------------------------------------------------ run, detqmcpt.h:760-958
+    def run(self):
+        b = self.batch
+        while self.sweepsDoneThermalization < self.thermalization or self.sweepsDone < self.sweeps:
+            if self.sweepsDoneThermalization < self.thermalization:
+                b.sweepThermalization()
+                self.sweepsDoneThermalization += 1
+                self.swCounter += 1
+                if self.sweepsDoneThermalization == self.thermalization:
+                    self.swCounter = 0
+            else:
+                self.swCounter += 1
+                take = self.swCounter % self.measureInterval == 0
+                b.sweep(False)                         # fermionic measurements: SURVEY 8(f) row 1
+                if take:
+                    self._measure()
+                    if (self.cfgBinary or self.cfgText) and self.cfgInterval and self.swCounter % self.cfgInterval == 0:
+                        self._buffer_configurations()
+                self.sweepsDone += 1
+            if self.exchangeInterval and (self.sweepsDone + self.sweepsDoneThermalization) % self.exchangeInterval == 0:
+                self.replica_exchange_step()
+            # replicaExchangeConsistencyCheck, detqmcpt.h:1120-1135
+            want = self.values[self.local_parameter_indices()]
+            have = np.array([b.get_exchange_parameter_value(i) for i in range(self.n_local)])
+            if np.abs(want - have).max() > 1e-10:
+                raise RuntimeError("replica exchange consistency check failed")
+        self.save()
+
+    # ------------------------------------------------------------------ gather to rank 0 and write
+    def _gather(self, obj):
+        if self.world == 1:
+            return [obj]
+        out = [None] * self.world if self.rank == 0 else None
+        self.dist.gather_object(obj, out, dst=0)
+        return out
+
+    def subdir(self, cpi):
+        return os.path.join(self.outdir, "p%d_%s%s" % (cpi, self.name, num_to_string(self.values[cpi])))
+
+    def save(self):
+        recs = self._gather(self.records)
+        cfgs = self._gather(self.configs)
+        if self.rank != 0:
+            return
+        series = {cpi: {o: [] for o in OBSERVABLES} for cpi in range(self.P)}
+        flat = sorted((r for part in recs for r in part), key=lambda r: (r[0], r[1]))
+        for _, cpi, obs in flat:
+            for o in OBSERVABLES:
+                series[cpi][o].append(obs[o])
+        header = "## %s = %s\n## thermalization = %d\n## sweeps = %d\n## exchangeInterval = %d\n"
+        for cpi in range(self.P):
+            d = self.subdir(cpi)
+            os.makedirs(d, exist_ok=True)
+            meta = header % (self.name, num_to_string(self.values[cpi]), self.thermalization, self.sweepsDone,
+                             self.exchangeInterval)
+            with open(os.path.join(d, "results.values"), "w") as res:
+                res.write(meta + "## observable \t value \t error\n")
+                for o in OBSERVABLES:
+                    v = np.asarray(series[cpi][o])
+                    with open(os.path.join(d, o + ".series"), "w") as f:
+                        f.write(meta + "## time series of %s\n" % o)
+                        f.write("".join("%.15g\n" % x for x in v))
+                    err = float(v.std(ddof=1) / np.sqrt(len(v))) if len(v) > 1 else 0.0
+                    res.write("%s\t%.15g\t%.15g\n" % (o, float(v.mean()) if len(v) else 0.0, err))
+        for part in cfgs:
+            for cpi, cfg in part:
+                d = self.subdir(cpi)
+                if self.cfgBinary:
+                    with open(os.path.join(d, "configs-phi.binarystream"), "ab") as f:
+                        f.write(cfg.tobytes())
+                if self.cfgText:
+                    with open(os.path.join(d, "configs-phi.textstream"), "a") as f:
+                        f.write("".join("%.14e\n" % v for v in cfg))
+        L = self.ladder
+        with open(os.path.join(self.outdir, "exchange-parameters.values"), "w") as f:
+            f.write("## Control parameter values\n## control parameter index \t control parameter value\n")
+            f.write("".join("%d\t%.15g\n" % (c, self.values[c]) for c in range(self.P)))
+        with open(os.path.join(self.outdir, "exchange-acceptance.values"), "w") as f:
+            f.write("## Acceptance ratio of exchanging replicas at control parameters (upwards)\n"
+                    "## control parameter index \t acceptance ratio\n")
+            for c in range(self.P):
+                prop = L.proposed[c] if c < self.P - 1 else 0
+                f.write("%d\t%.15g\n" % (c, (L.accepted[c] / prop) if prop else 0.0))
+        with open(os.path.join(self.outdir, "exchange-diffusion.values"), "w") as f:
+            f.write("## Diffusion fraction of replicas at control parameters: df = nUp / (nUp + nDown)\n"
+                    "## control parameter index \t diffusion fraction\n")
+            for c in range(self.P):
+                tot = L.count_up[c] + L.count_down[c]
+                f.write("%d\t%.15g\n" % (c, (L.count_up[c] / tot) if tot else 0.0))
+        self.records, self.configs = [], []

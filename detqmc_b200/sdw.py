@@ -39,15 +39,17 @@ def make_params(pars=None, **kw):
     d.update(kw)
     if d["cdwU"] != 0.0:
         raise DqmcError("cdwU != 0 is outside the accelerated path")
-    if d["updateMethod"] not in (1, 2):
-        raise DqmcError("updateMethod must be 'woodbury' (1) or 'delayed' (2)")
+    if d["updateMethod"] not in (0, 1, 2):
+        raise DqmcError("updateMethod must be 'iterative' (0), 'woodbury' (1) or 'delayed' (2)")
     if d["repeatUpdateInSlice"] != 1:
         raise DqmcError("repeatUpdateInSlice != 1 is outside the accelerated path")
     p = DqmcParams()
     p.model = 0
     p.opdim, p.L, p.m, p.s, p.bc = d["opdim"], d["L"], d["m"], d["s"], d["bc"]
     p.weakZflux = int(bool(d["weakZflux"]))
-    p.delaySteps = d["delaySteps"] if d["updateMethod"] == 2 else 1     # woodbury == delayed with 1 step
+    # woodbury == delayed with 1 step; iterative (detsdwopdim.cpp:2491-2880) evaluates the same ratio and the same
+    # rank-MSF update entry by entry (the reference's fields equal woodbury's sweep by sweep): same kernel
+    p.delaySteps = d["delaySteps"] if d["updateMethod"] == 2 else 1
     p.globalShift = int(bool(d["globalShift"]))
     p.globalUpdateInterval = d["globalUpdateInterval"]
     p.wolffClusterUpdate = int(bool(d["wolffClusterUpdate"]))
@@ -389,6 +391,10 @@ class ReplicaExchangeLadder:
         self.process_par = np.arange(self.P, dtype=np.int32)     # current_process_par
         self.proposed = np.zeros(max(self.P - 1, 1), dtype=np.int64)
         self.accepted = np.zeros(max(self.P - 1, 1), dtype=np.int64)
+        # ExchangeStatistics (detqmcpt.h:996-1010): replicas are labelled by the end of the ladder they visited last
+        self.going = np.zeros(self.P, dtype=np.int8)             # 0 none, +1 up (from index 0), -1 down (from P-1)
+        self.count_up = np.zeros(self.P, dtype=np.int64)
+        self.count_down = np.zeros(self.P, dtype=np.int64)
 
     @property
     def n_uniforms(self):
@@ -410,6 +416,16 @@ class ReplicaExchangeLadder:
         actions = np.ascontiguousarray(g[:, :nl].reshape(-1))
         uniforms = np.ascontiguousarray(g[0, nl:nl + nu])
         blobs = g[:, nl + nu:].reshape(self.P, CTRL_WORDS)
+        for pi in range(self.P):                                   # diffusion statistics, before the walk
+            npar = self.process_par[pi]
+            if npar == self.P - 1:
+                self.going[pi] = -1
+            elif npar == 0:
+                self.going[pi] = +1
+            if self.going[pi] < 0:
+                self.count_down[npar] += 1
+            elif self.going[pi] > 0:
+                self.count_up[npar] += 1
         old_par_process = self.par_process.copy()
         used, swapped = exchange_walk(self.values, self.par_process, self.process_par, actions, uniforms)
         self.proposed[:self.P - 1] += 1

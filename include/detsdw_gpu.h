@@ -58,8 +58,11 @@ public:
                                "turnoffFermionMeasurements");
         if (pars.cdwU != 0.0) throw_GeneralError("DetSDWGpu: cdwU != 0 is outside the accelerated path");
         if (pars.repeatUpdateInSlice != 1) throw_GeneralError("DetSDWGpu: repeatUpdateInSlice != 1 is not implemented");
-        if (pars.updateMethod_string != "delayed" && pars.updateMethod_string != "woodbury")
-            throw_GeneralError("DetSDWGpu: updateMethod must be delayed or woodbury");
+        // iterative (detsdwopdim.cpp:2491-2880) and woodbury (:2883-3019) evaluate the same ratio and apply the same
+        // rank-MSF update immediately: both are served as delayed updates with a block of one (identical decisions)
+        if (pars.updateMethod_string != "delayed" && pars.updateMethod_string != "woodbury" &&
+            pars.updateMethod_string != "iterative")
+            throw_GeneralError("DetSDWGpu: updateMethod must be iterative, woodbury or delayed");
         if (pars.spinProposalMethod_string != "box")
             throw_GeneralError("DetSDWGpu: only box proposals are implemented");
         dqmc_params p;

@@ -97,7 +97,9 @@ typedef struct dqmc_control_data {
 int dqmc_create(const dqmc_params* params, int n_replicas, int device, dqmc_ctx** out);
 void dqmc_destroy(dqmc_ctx* ctx);
 const char* dqmc_last_error(const dqmc_ctx* ctx);
-/* Use an existing CUDA stream (cudaStream_t) for all work of this context; NULL = own stream. */
+/* Use an existing CUDA stream (cudaStream_t) for all work of this context; NULL = own (non-blocking) stream.
+ * Note that the handle of CUDA's legacy default stream is NULL as well: a host program that wants its own copies,
+ * collectives or timing events ordered with the library's kernels must pass an explicitly created stream. */
 int dqmc_set_stream(dqmc_ctx* ctx, void* cuda_stream);
 int dqmc_synchronize(dqmc_ctx* ctx);
 /* out[0..7] = {N, D (Green's-function dimension), m, n, s, n_green_components, n_replicas, opdim} */

@@ -12,7 +12,7 @@ from helpers import load_golden, sdw_params_of, maxabs, relerr
 
 pytestmark = pytest.mark.gpu
 
-SDW_CASES = ["sdw_o2_wolff_L4", "sdw_o2_wolffshift_L4",
+SDW_CASES = ["sdw_o2_wolff_L4", "sdw_o2_wolffshift_L4", "sdw_o3_woodbury_L4",
              "sdw_o2_flux_L4", "sdw_o2_noflux_apbcxy_L4", "sdw_o3_L4", "sdw_o1_apbcx_L4",
              "sdw_o2_flux_L4_delay3_s7", "sdw_o2_flux_L6"]
 
@@ -370,6 +370,78 @@ def test_config_stream_vs_golden(tmp_path):
         b.saveConfigurationStreamText(str(out), rep=1)
         assert open(str(out / "configs-phi.binarystream"), "rb").read() == g[tag + "_binary"].tobytes()
         assert open(str(out / "configs-phi.textstream"), "rb").read() == g[tag + "_text"].tobytes()
+
+
+def test_parallel_tempering_driver_vs_oracle_loop(tmp_path):
+    """detqmc_b200.DetQMCPT (the MPI-free DetQMCPT::run, detqmcpt.h:760-958, SURVEY 8f row 4) against the same loop
+    over oracle replicas: thermalisation and measurement sweeps with a replica-exchange step after every sweep
+    (ladder walk with replica 0's stream, control data following the parameter), observables recorded per control
+    parameter, configuration streams written to the sub-directory of the parameter held at that time."""
+    import copy
+    import os
+    from detqmc_b200 import DetQMCPT
+    from detqmc_b200.pt import bosonic_observables, OBSERVABLES
+    from dqmc_oracle import SdwOracle, SdwParams, config_stream, exchange_probability
+    values = np.array([-1.6, -1.2, -0.8, -0.4])
+    P, therm, sweeps, cfg_interval = len(values), 3, 4, 2
+    kw = dict(L=4, m=20, s=10)
+    pt = DetQMCPT(SdwParams(**kw), values, thermalization=therm, sweeps=sweeps, exchangeInterval=1,
+                  saveConfigurationStreamInterval=cfg_interval, saveConfigurationStreamBinary=True, outdir=str(tmp_path))
+    pt.run()
+
+    reps = [SdwOracle(SdwParams(r=float(values[i]), rngIndex=i + 1, **kw)) for i in range(P)]
+    par_process, process_par = list(range(P)), list(range(P))
+    accepted = np.zeros(P - 1, dtype=int)
+    series = {c: {o: [] for o in OBSERVABLES} for c in range(P)}
+    cfgs = {c: [] for c in range(P)}
+
+    def get_ctrl(o):
+        return (o.phi_delta, o.last_acc_ratio, copy.deepcopy(o.ra_box), o.accepted_global_shifts, o.attempted_global_shifts)
+
+    def set_ctrl(o, c):
+        o.phi_delta, o.last_acc_ratio, o.ra_box, o.accepted_global_shifts, o.attempted_global_shifts = c
+
+    for step in range(therm + sweeps):
+        for o in reps:
+            if step < therm:
+                o.sweep_thermalization()
+            else:
+                o.sweep()
+        if step >= therm:
+            for pi, o in enumerate(reps):
+                ob = bosonic_observables(o.phi, o.phi_action(), o.p.N, o.p.m)
+                for name in OBSERVABLES:
+                    series[process_par[pi]][name].append(ob[name])
+                if (step - therm + 1) % cfg_interval == 0:
+                    cfgs[process_par[pi]].append(config_stream(o.phi))
+        actions = [o.exchange_action() for o in reps]
+        ctrl = [get_ctrl(o) for o in reps]
+        for c1 in range(P - 1):
+            p1, p2 = par_process[c1], par_process[c1 + 1]
+            prob = exchange_probability(values[c1], actions[p1], values[c1 + 1], actions[p2])
+            if prob >= 1 or reps[0].rng.rand01() <= prob:
+                accepted[c1] += 1
+                process_par[p1], process_par[p2] = c1 + 1, c1
+                par_process[c1], par_process[c1 + 1] = p2, p1
+                ctrl[p1], ctrl[p2] = ctrl[p2], ctrl[p1]
+        for pi, o in enumerate(reps):
+            o.p.r = float(values[process_par[pi]])
+            set_ctrl(o, ctrl[pi])
+
+    assert list(pt.ladder.process_par) == process_par
+    assert list(pt.ladder.accepted[:P - 1]) == list(accepted)
+    for c in range(P):
+        d = pt.subdir(c)
+        for name in OBSERVABLES:
+            got = [float(x) for x in open(os.path.join(d, name + ".series")) if x[0] != "#"]
+            assert len(got) == sweeps and np.allclose(got, series[c][name], rtol=1e-10, atol=1e-12)
+        want = np.concatenate(cfgs[c]) if cfgs[c] else np.zeros(0)
+        path = os.path.join(d, "configs-phi.binarystream")
+        got = np.fromfile(path) if os.path.exists(path) else np.zeros(0)
+        assert got.shape == want.shape and (got.size == 0 or maxabs(got, want) < 1e-12)
+    acc_file = [x.split() for x in open(os.path.join(str(tmp_path), "exchange-acceptance.values")) if x[0] != "#"]
+    assert np.allclose([float(a[1]) for a in acc_file][:P - 1], [accepted[c] / (therm + sweeps) for c in range(P - 1)],
+                       rtol=1e-12, atol=0)
 
 
 # ---------------------------------------------------------------- full-size checks

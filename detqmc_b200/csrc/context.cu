@@ -651,8 +651,10 @@ int launch_update(dqmc_ctx* ctx, int k, int therm) {
     // followed by the rank-K update G += X Y on all SMs
     a.inline_flush = ctx->p.delaySteps < 8 ? 1 : 0;
     const int rounds = update_rounds_per_slice(ctx->umodel, a.inline_flush);
-    for (int rd = 0; rd < rounds; ++rd) {
-        a.round = rd;
+    const int passes = std::max(1, ctx->p.repeatUpdateInSlice);       // updateInSlice repeats the pass, detsdwopdim.cpp:2438
+    for (int rd = 0; rd < rounds * passes; ++rd) {
+        a.round = rd % rounds;
+        a.final_pass = rd / rounds == passes - 1 ? 1 : 0;
         CKL(update_round_launch(ctx->umodel, a, ctx->stream));
         if (!a.inline_flush) {
             GemmArgs g;
@@ -1118,7 +1120,7 @@ int dqmc_create(const dqmc_params* params, int n_replicas, int device, dqmc_ctx*
     CK(dmalloc(&ctx->Y, D * ctx->kmax * R));
     CK(cudaMemsetAsync(ctx->X, 0, sizeof(cplx) * D * ctx->kmax * R, ctx->stream));   // finite everywhere (see extend_xy)
     CK(cudaMemsetAsync(ctx->Y, 0, sizeof(cplx) * D * ctx->kmax * R, ctx->stream));
-    ctx->rngCap = size_t(ctx->m) * ctx->N * (ctx->p.opdim + 1);      // Hubbard: <= 2 values per attempt
+    ctx->rngCap = size_t(ctx->m) * ctx->N * (ctx->p.opdim + 1) * size_t(std::max(1, hub ? 1 : ctx->p.repeatUpdateInSlice));   // Hubbard: <= 2 values per attempt
     ctx->rngAlloc = ctx->rngCap * kStreamSweeps;               // streamed mode keeps several sweeps' worth on the device
     ctx->rngStride = ctx->rngCap;
     ctx->rngAuto = false;
@@ -1669,7 +1671,8 @@ int dqmc_gemm_host(dqmc_ctx* ctx, int transa, int transb, int M, int N, int K, c
 int dqmc_update_slice(dqmc_ctx* ctx, uint32_t k, int thermalization, uint32_t* n_accepted) {
     if (!ctx || k < 1 || (int)k > ctx->m) return DQMC_ERR_PARAM;
     RET(host_sync_rng(ctx));
-    RET(upload_rng_window(ctx, size_t(ctx->N) * (ctx->p.opdim + 1)));
+    RET(upload_rng_window(ctx, size_t(ctx->N) * (ctx->p.opdim + 1) *
+                                   size_t(ctx->p.model == DQMC_MODEL_SDW ? std::max(1, ctx->p.repeatUpdateInSlice) : 1)));
     RET(launch_update(ctx, (int)k, thermalization));
     if (n_accepted)
         CK(cudaMemcpyAsync(ctx->h_acc, ctx->accepted, sizeof(uint32_t) * ctx->R, cudaMemcpyDeviceToHost, ctx->stream));

@@ -178,6 +178,7 @@ struct UpdateArgs {
     int* site_state;              // [batch] next site to visit (carried from round to round)
     int* kvec;                    // [batch] K = MSF * (#accepted in this round) for the rank-K flush
     int debug;                    // print per-phase clock counts of replica 0 (development)
+    int final_pass;               // last of the repeatUpdateInSlice passes: record the acceptance statistics / adapt the step
     int y_in_smem;                // set by the launcher: the CTA keeps the pending Y rows in shared memory
 };
 // one round of the delayed local updates; with inline_flush == 0 the caller applies

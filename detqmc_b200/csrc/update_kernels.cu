@@ -645,8 +645,8 @@ __global__ void __launch_bounds__(MAXT) update_round_kernel(UpdateModel md, Upda
         const unsigned total = (a.round == 0 ? 0u : a.accepted[b]) + accepted;
         a.accepted[b] = total;
         if (a.acceptedTotal) a.acceptedTotal[b] += accepted;
-        if (site >= N && !sAbort) {
-            // end of the slice: acceptance statistics and step-size adaptation
+        if (site >= N && !sAbort && a.final_pass) {
+            // end of the slice (last pass): acceptance statistics and step-size adaptation
             dqmc_control_data* cd = a.ctrl + b;
             const double ratio = double(total) / double(N);
             cd->lastAccRatioLocal_phi = ratio;

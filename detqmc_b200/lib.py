@@ -21,7 +21,7 @@ class DqmcParams(ctypes.Structure):
                 ("txhor", c_f64), ("txver", c_f64), ("tyhor", c_f64), ("tyver", c_f64),
                 ("mux", c_f64), ("muy", c_f64), ("accRatio", c_f64), ("t", c_f64), ("U", c_f64), ("mu", c_f64),
                 ("wolffClusterUpdate", c_i32), ("wolffClusterShiftUpdate", c_i32), ("repeatWolffPerSweep", c_i32),
-                ("reserved1", c_i32)]
+                ("repeatUpdateInSlice", c_i32)]
 
 
 class ControlData(ctypes.Structure):

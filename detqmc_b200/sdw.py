@@ -41,8 +41,6 @@ def make_params(pars=None, **kw):
         raise DqmcError("cdwU != 0 is outside the accelerated path")
     if d["updateMethod"] not in (0, 1, 2):
         raise DqmcError("updateMethod must be 'iterative' (0), 'woodbury' (1) or 'delayed' (2)")
-    if d["repeatUpdateInSlice"] != 1:
-        raise DqmcError("repeatUpdateInSlice != 1 is outside the accelerated path")
     p = DqmcParams()
     p.model = 0
     p.opdim, p.L, p.m, p.s, p.bc = d["opdim"], d["L"], d["m"], d["s"], d["bc"]
@@ -55,6 +53,7 @@ def make_params(pars=None, **kw):
     p.wolffClusterUpdate = int(bool(d["wolffClusterUpdate"]))
     p.wolffClusterShiftUpdate = int(bool(d["wolffClusterShiftUpdate"]))
     p.repeatWolffPerSweep = int(d["repeatWolffPerSweep"])
+    p.repeatUpdateInSlice = int(d["repeatUpdateInSlice"])
     p.dtau, p.r, p.c, p.u, p.lambda_ = d["dtau"], d["r"], d["c"], d["u"], d["lam"]
     p.txhor, p.txver, p.tyhor, p.tyver = d["txhor"], d["txver"], d["tyhor"], d["tyver"]
     p.mux = p.muy = d["mu"]

@@ -57,7 +57,6 @@ public:
             throw_GeneralError("DetSDWGpu: fermionic measurements are outside the accelerated path; set "
                                "turnoffFermionMeasurements");
         if (pars.cdwU != 0.0) throw_GeneralError("DetSDWGpu: cdwU != 0 is outside the accelerated path");
-        if (pars.repeatUpdateInSlice != 1) throw_GeneralError("DetSDWGpu: repeatUpdateInSlice != 1 is not implemented");
         // iterative (detsdwopdim.cpp:2491-2880) and woodbury (:2883-3019) evaluate the same ratio and apply the same
         // rank-MSF update immediately: both are served as delayed updates with a block of one (identical decisions)
         if (pars.updateMethod_string != "delayed" && pars.updateMethod_string != "woodbury" &&
@@ -79,6 +78,7 @@ public:
         p.wolffClusterUpdate = pars.wolffClusterUpdate ? 1 : 0;
         p.wolffClusterShiftUpdate = pars.wolffClusterShiftUpdate ? 1 : 0;
         p.repeatWolffPerSweep = (int32_t)pars.repeatWolffPerSweep;
+        p.repeatUpdateInSlice = (int32_t)pars.repeatUpdateInSlice;
         p.globalUpdateInterval = (int32_t)pars.globalUpdateInterval;
         p.dtau = pars.dtau;
         p.r = pars.r; p.c = pars.c; p.u = pars.u; p.lambda = pars.lambda;

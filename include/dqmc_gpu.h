@@ -73,7 +73,7 @@ typedef struct dqmc_params {
     int32_t wolffClusterUpdate;       /* SDW: Wolff single-cluster moves every globalUpdateInterval sweeps */
     int32_t wolffClusterShiftUpdate;  /* SDW: combined cluster + global shift move (excludes the two others) */
     int32_t repeatWolffPerSweep;      /* SDW: clusters per attempt (0 or 1: one) */
-    int32_t reserved1;
+    int32_t repeatUpdateInSlice;      /* SDW: passes over a slice per updateInSlice (0 or 1: one), detsdwopdim.cpp:2438 */
 } dqmc_params;
 
 /* Per-replica control data that follows the exchange parameter in a replica exchange

@@ -603,6 +603,14 @@ class SdwOracle(SweepSkeleton):
 
     # updateInSlice_delayed with proposeNewPhiBox; detsdwopdim.cpp:3021-3175, 3920-3931
     def update_in_slice(self, k):
+        """updateInSlice dispatcher, cpp:2427-2489: the pass over the slice is repeated repeatUpdateInSlice times; the
+        recorded acceptance ratio is that of the last pass."""
+        acc = None
+        for _ in range(max(1, self.p.repeatUpdateInSlice)):
+            acc = self.update_in_slice_once(k)
+        return acc
+
+    def update_in_slice_once(self, k):
         p, N, msf = self.p, self.N, self.msf
         g = self.green[0]
         rows_of = lambda site: site + N * np.arange(msf)

@@ -7,7 +7,7 @@ from dqmc_oracle import (SdwOracle, HubbardOracle, exchange_probability, replica
 from dsfmt_oracle import RngOracle
 from helpers import load_golden, sdw_params_of, hubbard_params_of, maxabs
 
-SDW_CASES = ["sdw_o2_wolff_L4", "sdw_o2_wolffshift_L4", "sdw_o3_woodbury_L4",
+SDW_CASES = ["sdw_o2_wolff_L4", "sdw_o2_wolffshift_L4", "sdw_o3_woodbury_L4", "sdw_o2_repeat2_L4",
              "sdw_o2_flux_L4", "sdw_o2_noflux_apbcxy_L4", "sdw_o3_L4", "sdw_o1_apbcx_L4",
              "sdw_o2_flux_L4_delay3_s7", "sdw_o2_flux_L6"]
 

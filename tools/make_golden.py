@@ -182,6 +182,7 @@ if __name__ == "__main__":
         # (no fixture for updateMethod=iterative: the reference's updateInSlice_iterative corrupts the heap in this
         # build -- "double free or corruption" at teardown -- although its fields equal woodbury's sweep by sweep)
         sdw_fixture("sdw_o3_woodbury_L4", 4, dict(updateMethod=1, opdim=3, weakZflux=False, rngIndex=9))
+        sdw_fixture("sdw_o2_repeat2_L4", 4, dict(repeatUpdateInSlice=2, rngIndex=10))
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "wolff":
         wolff_all()
@@ -199,4 +200,5 @@ if __name__ == "__main__":
     hubbard_fixture("hubbard_L4_cb", 4, dict(checkerboard=True, U=6.0, mu=0.3, m=24, s=5))
     config_stream_fixture()
     wolff_all()
+    sdw_fixture("sdw_o2_repeat2_L4", 4, dict(repeatUpdateInSlice=2, rngIndex=10))
     sdw_fixture("sdw_o3_woodbury_L4", 4, dict(updateMethod=1, opdim=3, weakZflux=False, rngIndex=9))

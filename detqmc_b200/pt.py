@@ -11,7 +11,8 @@ p<index>_<name><value> per control parameter (detqmcpt.h:655-660) with <observab
 configuration streams, plus exchange-parameters.values / exchange-acceptance.values / exchange-diffusion.values
 (detqmcpt.h:596-651) in the working directory.
 
-Only bosonic observables are measured (normMeanPhi, meanPhiSquared, phiAction: what include/detsdw_gpu.h measures);
+Only the bosonic observables are measured (normMeanPhi, associatedEnergy, phiRhoS_Gs, phiRhoS_Gc: the reference's list
+with turnoffFermionMeasurements, also what include/detsdw_gpu.h measures);
 fermionic measurements are row 1 of section 8(f).
 """
 import os
@@ -20,7 +21,7 @@ import numpy as np
 
 from .sdw import DetSDWBatch, ReplicaExchangeLadder
 
-OBSERVABLES = ("normMeanPhi", "meanPhiSquared", "phiAction")
+OBSERVABLES = ("normMeanPhi", "associatedEnergy", "phiRhoS_Gs", "phiRhoS_Gc")
 
 
 def num_to_string(v):
@@ -28,13 +29,24 @@ def num_to_string(v):
     return "%g" % v
 
 
-def bosonic_observables(phi, phi_action, N, m):
-    """DetSDWGpu::measureBosonic (include/detsdw_gpu.h): norm of the mean field, mean squared field, action per
-    site and slice.  phi: [m+1][opdim][N]."""
-    mean = phi[1:].mean(axis=(0, 2))
-    return {"normMeanPhi": float(np.sqrt(np.sum(mean * mean))),
-            "meanPhiSquared": float(np.sum(phi[1:] ** 2) / (N * m)),
-            "phiAction": float(phi_action) / (N * m)}
+def bosonic_observables(phi, dtau):
+    """The observables DetSDW measures with turnoffFermionMeasurements (initMeasurements / measure /
+    finishMeasurements, detsdwopdim.cpp:441-560, 903-918; same as DetSDWGpu::measureBosonic in include/detsdw_gpu.h):
+    normMeanPhi, associatedEnergy and, for opdim == 2, the bosonic spin stiffness sums phiRhoS_Gs / phiRhoS_Gc
+    (zero otherwise).  phi: [m+1][opdim][N]."""
+    m1, opdim, N = phi.shape
+    L = int(round(np.sqrt(N)))
+    ph = phi[1:]
+    out = {"normMeanPhi": float(np.linalg.norm(ph.sum(axis=(0, 2)) / (N * (m1 - 1)))),
+           "associatedEnergy": float(np.sum(ph * ph) / (2.0 * N * (m1 - 1))), "phiRhoS_Gs": 0.0, "phiRhoS_Gc": 0.0}
+    if opdim == 2:
+        sites = np.arange(N)
+        x, y = sites % L, sites // L
+        xp = y * L + (x + 1) % L
+        yp = ((y + 1) % L) * L + x
+        out["phiRhoS_Gc"] = float(0.5 * dtau * (np.sum(ph * ph[:, :, xp]) + np.sum(ph * ph[:, :, yp])))
+        out["phiRhoS_Gs"] = float(dtau * np.sum(ph[:, 0, xp] * ph[:, 1, :] - ph[:, 1, xp] * ph[:, 0, :]))
+    return out
 
 
 class DetQMCPT:
@@ -107,10 +119,9 @@ class DetQMCPT:
 
     def _measure(self):
         b = self.batch
-        actions = b.phi_action()
         cpis = self.local_parameter_indices()
         for i in range(self.n_local):
-            self.records.append((self.sweepsDone, int(cpis[i]), bosonic_observables(b.phi(i), actions[i], b.N, b.m)))
+            self.records.append((self.sweepsDone, int(cpis[i]), bosonic_observables(b.phi(i), b.pars["dtau"])))
 
     def _buffer_configurations(self):
         # buffer_local_system_configuration, detqmcpt.h:690-700: the configuration goes to the stream of the control

@@ -292,6 +292,11 @@ class DetSDWBatch:
         self._ck(self.lib.dqmc_get_wolff_statistics(self.h, int(rep), _ptr(out)))
         return out
 
+    def bosonic_observables(self, rep=0):
+        """normMeanPhi, associatedEnergy, phiRhoS_Gs, phiRhoS_Gc of the current fields (detsdwopdim.cpp:441-560, 903-918)."""
+        from .pt import bosonic_observables
+        return bosonic_observables(self.phi(rep), self.pars["dtau"])
+
     def phi_action(self):
         out = np.zeros(self.R)
         self._ck(self.lib.dqmc_phi_action(self.h, _ptr(out)))

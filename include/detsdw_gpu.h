@@ -48,7 +48,7 @@ public:
     typedef DetSDW_SystemConfig_FileHandle SystemConfig_FileHandle;
 
     DetSDWGpu(RngWrapper& rng_, const ModelParams& pars_, int device = 0)
-        : rng(rng_), pars(pars_), ctx(nullptr), normMeanPhi(0), meanPhiSquared(0), phiActionValue(0),
+        : rng(rng_), pars(pars_), ctx(nullptr), normMeanPhi(0), associatedEnergy(0), phiRhoS_Gs(0), phiRhoS_Gc(0),
           performedSweeps(0) {
         if (pars.opdim != (uint32_t)OPDIM) throw_GeneralError("DetSDWGpu: opdim mismatch");
         if (!pars.checkerboard) throw_GeneralError("DetSDWGpu: the GPU path implements the checkerboard break-up only");
@@ -145,9 +145,13 @@ public:
 
     virtual std::vector<ScalarObservable> getScalarObservables() {
         std::vector<ScalarObservable> obs;
+        // the reference's list for turnoffFermionMeasurements (detsdwopdim.cpp:270-276)
         obs.push_back(ScalarObservable(std::cref(normMeanPhi), "normMeanPhi", "nmp"));
-        obs.push_back(ScalarObservable(std::cref(meanPhiSquared), "meanPhiSquared", "mps"));
-        obs.push_back(ScalarObservable(std::cref(phiActionValue), "phiAction", "sphi"));
+        obs.push_back(ScalarObservable(std::cref(associatedEnergy), "associatedEnergy", ""));
+        if (OPDIM == 2) {
+            obs.push_back(ScalarObservable(std::cref(phiRhoS_Gs), "phiRhoS_Gs", ""));
+            obs.push_back(ScalarObservable(std::cref(phiRhoS_Gc), "phiRhoS_Gc", ""));
+        }
         return obs;
     }
     virtual std::vector<VectorObservable> getVectorObservables() { return std::vector<VectorObservable>(); }
@@ -261,30 +265,38 @@ private:
         return phi;
     }
     // bosonic observables of DetSDW::measure (detsdwopdim.cpp:440-506): |mean phi|, mean phi^2, action
+    // The observables the reference measures with turnoffFermionMeasurements (initMeasurements / measure /
+    // finishMeasurements, detsdwopdim.cpp:441-560, 903-918), from the fields of all slices k = 1..m.
     void measureBosonic() {
         const std::vector<double> phi = downloadPhi();
-        const size_t N = size_t(pars.L) * pars.L;
-        double mean[3] = {0, 0, 0}, sq = 0;
+        const uint32_t L = pars.L;
+        const size_t N = size_t(L) * L;
+        auto at = [&](uint32_t k, int d, size_t s) { return phi[(size_t(k) * OPDIM + d) * N + s]; };
+        double mean[3] = {0, 0, 0}, sq = 0, gc = 0, gs = 0;
         for (uint32_t k = 1; k <= pars.m; ++k)
-            for (int d = 0; d < OPDIM; ++d)
-                for (size_t s = 0; s < N; ++s) {
-                    const double v = phi[(size_t(k) * OPDIM + d) * N + s];
+            for (size_t s = 0; s < N; ++s) {
+                const size_t x = s % L, y = s / L;
+                const size_t xp = y * L + (x + 1) % L, yp = ((y + 1) % L) * L + x;
+                for (int d = 0; d < OPDIM; ++d) {
+                    const double v = at(k, d, s);
                     mean[d] += v;
                     sq += v * v;
+                    if (OPDIM == 2) gc += v * at(k, d, xp) + v * at(k, d, yp);
                 }
+                if (OPDIM == 2) gs += at(k, 0, xp) * at(k, 1, s) - at(k, 1, xp) * at(k, 0, s);
+            }
         double nrm = 0;
         for (int d = 0; d < OPDIM; ++d) { mean[d] /= double(N * pars.m); nrm += mean[d] * mean[d]; }
         normMeanPhi = std::sqrt(nrm);
-        meanPhiSquared = sq / double(N * pars.m);
-        double act = 0;
-        check(dqmc_phi_action(ctx, &act), "dqmc_phi_action");
-        phiActionValue = act / double(N * pars.m);
+        associatedEnergy = sq / (2.0 * double(N * pars.m));
+        phiRhoS_Gc = gc * (0.5 * pars.dtau);
+        phiRhoS_Gs = gs * pars.dtau;
     }
 
     RngWrapper& rng;
     ModelParams pars;
     dqmc_ctx* ctx;
-    num normMeanPhi, meanPhiSquared, phiActionValue;
+    num normMeanPhi, associatedEnergy, phiRhoS_Gs, phiRhoS_Gc;
     uint32_t performedSweeps;
 };
 

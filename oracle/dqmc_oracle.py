@@ -265,6 +265,29 @@ class SweepSkeleton:
         pass
 
 
+def bosonic_observables(phi, dtau):
+    """The observables DetSDW measures with turnoffFermionMeasurements (initMeasurements / measure /
+    finishMeasurements, detsdwopdim.cpp:441-560, 903-918), accumulated over the slices k = 1..m:
+      normMeanPhi       |sum phi| / (N m)
+      associatedEnergy  sum phi.phi / (2 N m)
+      phiRhoS_Gc        (dtau / 2) sum_site [phi(site).phi(site + x) + phi(site).phi(site + y)]          (opdim == 2)
+      phiRhoS_Gs        dtau sum_site [phi_0(site + x) phi_1(site) - phi_1(site + x) phi_0(site)]          (opdim == 2)
+    phi: [m+1][opdim][N]."""
+    m1, opdim, N = phi.shape
+    L = int(round(np.sqrt(N)))
+    ph = phi[1:]
+    out = {"normMeanPhi": float(np.linalg.norm(ph.sum(axis=(0, 2)) / (N * (m1 - 1)))),
+           "associatedEnergy": float(np.sum(ph * ph) / (2.0 * N * (m1 - 1)))}
+    if opdim == 2:
+        sites = np.arange(N)
+        x, y = sites % L, sites // L
+        xp = y * L + (x + 1) % L
+        yp = ((y + 1) % L) * L + x
+        out["phiRhoS_Gc"] = float(0.5 * dtau * (np.sum(ph * ph[:, :, xp]) + np.sum(ph * ph[:, :, yp])))
+        out["phiRhoS_Gs"] = float(dtau * np.sum(ph[:, 0, xp] * ph[:, 1, :] - ph[:, 1, xp] * ph[:, 0, :]))
+    return out
+
+
 def config_stream(phi):
     """One configuration in the order of the reference's configuration streams
     (DetSDW::saveConfigurationStreamBinary, detsdwopdim.cpp:5000-5010; DetSDW_SystemConfig::write_to_disk_phi_*,

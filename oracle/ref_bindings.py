@@ -179,6 +179,14 @@ class RefSdw:
         return out, sv
 
 
+    def measured_sweep(self):
+        """sweep(takeMeasurements=True): returns the bosonic observables normMeanPhi, associatedEnergy, phiRhoS_Gs,
+        phiRhoS_Gc (detsdwopdim.cpp:441-560, 903-918; the last two are zero unless opdim == 2)."""
+        out = np.zeros(4)
+        if lib().ref_sdw_measured_sweep(self.h, _p(out)) != 0:
+            raise RuntimeError("reference sweep failed")
+        return dict(normMeanPhi=out[0], associatedEnergy=out[1], phiRhoS_Gs=out[2], phiRhoS_Gc=out[3])
+
     def attempt_wolff(self, shift=False):
         """attemptWolffClusterUpdate / attemptWolffClusterShiftUpdate (detsdwopdim.cpp:3487-3562, 3647-3748); returns
         the update statistics (attempted, accepted, attemptedShift, acceptedShift, addedWolffClusterSize)."""

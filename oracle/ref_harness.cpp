@@ -109,6 +109,7 @@ struct SdwBase {
     virtual void green_from_storage(uint32_t l_left, uint32_t l_right, double* out, double* sv) = 0;
     virtual void save_config_stream(const char* dir, int binary) = 0;
     virtual void attempt_wolff(int shift, double* stats) = 0;
+    virtual void measured_sweep(double* obs) = 0;
 };
 
 template <int OPDIM>
@@ -239,6 +240,15 @@ struct SdwImpl : public SdwBase {
         std::memcpy(d, st.d.memptr(), sizeof(double) * st.d.n_elem);
         std::memcpy(Vt, st.V_t.memptr(), sizeof(cpx_t) * st.V_t.n_elem);
     }
+    void measured_sweep(double* obs) {
+        // sweep(takeMeasurements = true) with turnoffFermionMeasurements: the bosonic observables of
+        // initMeasurements / measure / finishMeasurements (detsdwopdim.cpp:441-560, 903-918)
+        rep->sweep(true);
+        obs[0] = rep->normMeanPhi;
+        obs[1] = rep->associatedEnergy;
+        obs[2] = OPDIM == 2 ? rep->phiRhoS_Gs : 0.0;
+        obs[3] = OPDIM == 2 ? rep->phiRhoS_Gc : 0.0;
+    }
     void attempt_wolff(int shift, double* stats) {
         // attemptWolffClusterUpdate / attemptWolffClusterShiftUpdate (detsdwopdim.cpp:3487-3562, 3647-3748)
         if (shift) rep->attemptWolffClusterShiftUpdate();
@@ -354,6 +364,16 @@ void ref_sdw_green_from_storage(void* h, uint32_t ll, uint32_t lr, double* out, 
 }
 
 // exchange probability, detsdwopdim.cpp:5251-5264
+int ref_sdw_measured_sweep(void* h, double* obs) {
+    CoutSilencer q;
+    try {
+        static_cast<SdwBase*>(h)->measured_sweep(obs);
+        return 0;
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "ref_sdw_measured_sweep: %s\n", e.what());
+        return 1;
+    }
+}
 void ref_sdw_attempt_wolff(void* h, int shift, double* stats) {
     CoutSilencer q;
     static_cast<SdwBase*>(h)->attempt_wolff(shift, stats);

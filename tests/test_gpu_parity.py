@@ -345,6 +345,25 @@ def test_wolff_cluster_moves_vs_reference_record():
         assert maxabs(b.rng_draw(4, rep=0), g[tag + "_rng_next"]) == 0.0
 
 
+def test_bosonic_observables_vs_golden():
+    """The observables of a measured sweep (normMeanPhi, associatedEnergy, phiRhoS_Gs, phiRhoS_Gc) from the fields
+    on the device against the values the reference measured for the same fields (tests/golden/bosonic_observables.npz)."""
+    import json
+    import os
+    from dqmc_oracle import SdwParams
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "bosonic_observables.npz"))
+    for tag in ("o2", "o3", "o2_L6"):
+        d = json.loads(str(g[tag + "_pars"]))
+        for key in ("N", "beta"):
+            d.pop(key, None)
+        b = make_batch(SdwParams(**d))
+        for it in range(g[tag + "_phi"].shape[0]):
+            b.set_phi(g[tag + "_phi"][it])
+            ob = b.bosonic_observables()
+            got = [ob["normMeanPhi"], ob["associatedEnergy"], ob["phiRhoS_Gs"], ob["phiRhoS_Gc"]]
+            assert np.allclose(got, g[tag + "_obs"][it], rtol=1e-12, atol=1e-13)
+
+
 def test_config_stream_vs_golden(tmp_path):
     """dqmc_download_config_stream and the stream writers of the mirror against the bytes / lines the reference's
     own writers produced for the same fields (tests/golden/config_streams.npz, detsdwopdim.cpp:4943-5036)."""
@@ -409,7 +428,7 @@ def test_parallel_tempering_driver_vs_oracle_loop(tmp_path):
                 o.sweep()
         if step >= therm:
             for pi, o in enumerate(reps):
-                ob = bosonic_observables(o.phi, o.phi_action(), o.p.N, o.p.m)
+                ob = bosonic_observables(o.phi, o.p.dtau)
                 for name in OBSERVABLES:
                     series[process_par[pi]][name].append(ob[name])
                 if (step - therm + 1) % cfg_interval == 0:
@@ -493,18 +512,27 @@ def test_reference_driver_with_gpu_shim(tmp_path):
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     series = [float(x) for x in open(os.path.join(str(tmp_path), "normMeanPhi.series")) if x.strip() and x[0] != "#"]
     assert len(series) == sweeps
+    others = {name: [float(x) for x in open(os.path.join(str(tmp_path), name + ".series")) if x.strip() and x[0] != "#"]
+              for name in ("associatedEnergy", "phiRhoS_Gs", "phiRhoS_Gc")}
     from dqmc_oracle import config_stream, config_stream_text
     o = SdwOracle(SdwParams(L=4, m=20, s=10, r=-1.0))
     for _ in range(therm):
         o.sweep_thermalization()
+    from dqmc_oracle import bosonic_observables as oracle_observables
     ref, cfg_bin, cfg_txt = [], [], ""
+    ref_others = {name: [] for name in others}
     for sw in range(1, sweeps + 1):
         o.sweep()
         ref.append(float(np.linalg.norm(o.phi[1:].mean(axis=(0, 2)))))
+        ob = oracle_observables(o.phi, o.p.dtau)
+        for name in others:
+            ref_others[name].append(ob[name])
         if sw % 5 == 0:                                              # saveConfigurationStreamInterval (detqmc.h:484-491)
             cfg_bin.append(config_stream(o.phi))
             cfg_txt += config_stream_text(o.phi)
     assert np.allclose(series, ref, rtol=0, atol=2e-6)               # the driver writes 6 significant digits
+    for name in others:                                               # the reference's bosonic observable list
+        assert len(others[name]) == sweeps and np.allclose(others[name], ref_others[name], rtol=2e-5, atol=2e-6)
     # configuration streams written by the shim through dqmc_download_config_stream
     got = np.fromfile(os.path.join(str(tmp_path), "configs-phi.binarystream"))
     assert got.shape == (2 * 16 * 20 * 2,) and maxabs(got, np.concatenate(cfg_bin)) < 1e-13

@@ -183,3 +183,16 @@ def test_wolff_cluster_moves_vs_reference_record():
             assert maxabs(o.phi[1:], g[tag + "_phi"][it][1:]) < 1e-13
             assert maxabs(o.green[0], g[tag + "_green"][it]) < 1e-10
         assert maxabs([o.rng.rand01() for _ in range(4)], g[tag + "_rng_next"]) == 0.0
+
+
+def test_bosonic_observables_vs_reference_values():
+    """bosonic_observables (oracle restatement and the host mirror's copy) against the values the reference's own
+    measured sweeps produced for the same fields."""
+    import os
+    from dqmc_oracle import bosonic_observables
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "bosonic_observables.npz"))
+    for tag in ("o2", "o3", "o2_L6"):
+        for it in range(g[tag + "_phi"].shape[0]):
+            ob = bosonic_observables(g[tag + "_phi"][it], 0.1)
+            got = [ob["normMeanPhi"], ob["associatedEnergy"], ob.get("phiRhoS_Gs", 0.0), ob.get("phiRhoS_Gc", 0.0)]
+            assert np.allclose(got, g[tag + "_obs"][it], rtol=1e-12, atol=1e-13)

@@ -144,6 +144,26 @@ def wolff_fixture():
     print("wolff_moves done")
 
 
+def observables_fixture():
+    """Bosonic observables of a measured sweep (sweep(true) with turnoffFermionMeasurements, detsdwopdim.cpp:441-560,
+    903-918): fields after the sweep and normMeanPhi, associatedEnergy, phiRhoS_Gs, phiRhoS_Gc."""
+    d = {}
+    for tag, kw in (("o2", dict(rngIndex=12)), ("o3", dict(opdim=3, weakZflux=False, rngIndex=13)),
+                    ("o2_L6", dict(L=6, m=10, s=5, rngIndex=14))):
+        p = SdwParams(**kw)
+        rep = rb.RefSdw(p)
+        obs, phis = [], []
+        for _ in range(3):
+            o = rep.measured_sweep()
+            obs.append([o["normMeanPhi"], o["associatedEnergy"], o["phiRhoS_Gs"], o["phiRhoS_Gc"]])
+            phis.append(rep.phi())
+        d[tag + "_pars"] = pars_json(p)
+        d[tag + "_obs"] = np.array(obs)
+        d[tag + "_phi"] = np.array(phis)
+    np.savez_compressed(os.path.join(OUT, "bosonic_observables.npz"), **d)
+    print("bosonic_observables done")
+
+
 def config_stream_fixture():
     """Configuration streams: fields after two thermalisation sweeps and the bytes / lines the
     reference's own writers append for them (DetSDW::saveConfigurationStreamBinary / Text,
@@ -178,6 +198,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "config_streams":
         config_stream_fixture()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "observables":
+        observables_fixture()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "woodbury":
         # (no fixture for updateMethod=iterative: the reference's updateInSlice_iterative corrupts the heap in this
         # build -- "double free or corruption" at teardown -- although its fields equal woodbury's sweep by sweep)
@@ -199,6 +222,7 @@ if __name__ == "__main__":
     hubbard_fixture("hubbard_L4_U4_b4", 6, dict())                      # BASELINE config C1
     hubbard_fixture("hubbard_L4_cb", 4, dict(checkerboard=True, U=6.0, mu=0.3, m=24, s=5))
     config_stream_fixture()
+    observables_fixture()
     wolff_all()
     sdw_fixture("sdw_o2_repeat2_L4", 4, dict(repeatUpdateInSlice=2, rngIndex=10))
     sdw_fixture("sdw_o3_woodbury_L4", 4, dict(updateMethod=1, opdim=3, weakZflux=False, rngIndex=9))

@@ -1544,17 +1544,29 @@ int dqmc_logdet(dqmc_ctx* ctx, int rep, int gc, double* out) {
     return DQMC_OK;
 }
 
-int dqmc_green_for_timeslice(dqmc_ctx* ctx, int rep, int gc, uint32_t kk, double* out) {
-    if (!valid_rep(ctx, rep) || gc < 0 || gc >= ctx->ngc || !out || (int)kk > ctx->m) return DQMC_ERR_PARAM;
-    const int mat = rep * ctx->ngc + gc;
-    const int k = (int)kk, s = ctx->s, m = ctx->m;
-    const size_t dd = DD(ctx);
-    const int D = ctx->D;
-    // right chain B(k, 0) and left chain B(beta, k), each in steps of <= s slices, in private scratch
+// scratch of a from-scratch Green's function evaluation (one matrix): right / left chains and the result
+struct ScratchG {
     cplx* buf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // rQ, rT, lQ, lT, G
     double* dv[3] = {nullptr, nullptr, nullptr};                    // rD, lD, logdet
-    for (int i = 0; i < 5; ++i) CK(dmalloc(&buf[i], dd));
-    for (int i = 0; i < 3; ++i) CK(dmalloc(&dv[i], (size_t)D));
+    int alloc(dqmc_ctx* ctx) {
+        for (int i = 0; i < 5; ++i) CK(dmalloc(&buf[i], DD(ctx)));
+        for (int i = 0; i < 3; ++i) CK(dmalloc(&dv[i], (size_t)ctx->D));
+        return DQMC_OK;
+    }
+    void release() {
+        for (int i = 0; i < 5; ++i) cudaFree(buf[i]);
+        for (int i = 0; i < 3; ++i) cudaFree(dv[i]);
+    }
+};
+
+// G(k) = [1 + B(k, 0) B(beta, k)]^-1 of matrix `mat` from the fields, stabilised (right chain B(k, 0) and left chain
+// B(beta, k), each in steps of <= s slices), into sc.buf[4]; the sweep state is left untouched
+// (computeGreenFromScratch, detsdwopdim.cpp:4905-4933; setupUdVStorage_and_calculateGreen_forTimeslice, detmodel.h:605-674)
+int green_for_timeslice_dev(dqmc_ctx* ctx, int mat, int k, ScratchG& sc) {
+    const int s = ctx->s, m = ctx->m, D = ctx->D;
+    const size_t dd = DD(ctx);
+    cplx** buf = sc.buf;
+    double** dv = sc.dv;
     bool haveR = false, haveL = false;
     int rc = DQMC_OK;
     for (int k1 = 0; k1 < k && rc == DQMC_OK;) {
@@ -1578,21 +1590,64 @@ int dqmc_green_for_timeslice(dqmc_ctx* ctx, int rep, int gc, uint32_t kk, double
         UdtView lv = haveL ? UdtView{buf[2], (long long)dd, dv[1], D, buf[3], (long long)dd} : identity_view(ctx);
         rc = green_from_udts(ctx, rv, lv, buf[4], (long long)dd, dv[2], mat, 1);
     }
+    return rc;
+}
+
+int dqmc_green_for_timeslice(dqmc_ctx* ctx, int rep, int gc, uint32_t kk, double* out) {
+    if (!valid_rep(ctx, rep) || gc < 0 || gc >= ctx->ngc || !out || (int)kk > ctx->m) return DQMC_ERR_PARAM;
+    const size_t dd = DD(ctx);
+    ScratchG sc;
+    RET(sc.alloc(ctx));
+    int rc = green_for_timeslice_dev(ctx, rep * ctx->ngc + gc, (int)kk, sc);
     if (rc == DQMC_OK) {
         cudaError_t e;
         if (ctx->p.model == DQMC_MODEL_HUBBARD) {
-            e = hub_real_part_launch(buf[4], ctx->hubReal, dd, ctx->stream);
+            e = hub_real_part_launch(sc.buf[4], ctx->hubReal, dd, ctx->stream);
             if (e == cudaSuccess)
                 e = cudaMemcpyAsync(out, ctx->hubReal, sizeof(double) * dd, cudaMemcpyDeviceToHost, ctx->stream);
         } else {
-            e = cudaMemcpyAsync(out, buf[4], sizeof(cplx) * dd, cudaMemcpyDeviceToHost, ctx->stream);
+            e = cudaMemcpyAsync(out, sc.buf[4], sizeof(cplx) * dd, cudaMemcpyDeviceToHost, ctx->stream);
         }
         if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); rc = DQMC_ERR_CUDA; }
     }
     cudaStreamSynchronize(ctx->stream);
-    for (int i = 0; i < 5; ++i) cudaFree(buf[i]);
-    for (int i = 0; i < 3; ++i) cudaFree(dv[i]);
+    sc.release();
     return rc;
+}
+
+// sweepSimple / sweepSimpleThermalization (detmodel.h:718-758, detsdwopdim.cpp:4366-4420): for every slice the
+// Green's function is recomputed from scratch, then the slice is updated.  The reference inverts the plain product
+// 1 + B(k, 0) B(beta, k); here the stabilised evaluation serves it (same G where the plain product is accurate).
+// O(m) from-scratch evaluations per sweep: a consistency tool for small systems, as in the reference.
+int dqmc_sweep_simple(dqmc_ctx* ctx, int thermalization) {
+    if (!ctx) return DQMC_ERR_PARAM;
+    if (ctx->p.model != DQMC_MODEL_SDW) { ctx->err = "sweepSimple is served for DetSDW"; return DQMC_ERR_STATE; }
+    RET(host_sync_rng(ctx));
+    const size_t dd = DD(ctx);
+    ScratchG sc;
+    RET(sc.alloc(ctx));
+    int rc = DQMC_OK;
+    const size_t window = size_t(ctx->N) * (ctx->p.opdim + 1) * size_t(std::max(1, ctx->p.repeatUpdateInSlice));
+    for (int k = 1; k <= ctx->m && rc == DQMC_OK; ++k) {
+        for (int mat = 0; mat < ctx->nmat && rc == DQMC_OK; ++mat) {
+            rc = green_for_timeslice_dev(ctx, mat, k, sc);
+            if (rc == DQMC_OK &&
+                cudaMemcpyAsync(ctx->G + size_t(mat) * dd, sc.buf[4], sizeof(cplx) * dd, cudaMemcpyDeviceToDevice,
+                                ctx->stream) != cudaSuccess) {
+                ctx->err = "cudaMemcpyAsync failed";
+                rc = DQMC_ERR_CUDA;
+            }
+        }
+        if (rc == DQMC_OK) rc = upload_rng_window(ctx, window);
+        if (rc == DQMC_OK) rc = launch_update(ctx, k, thermalization);
+        if (rc == DQMC_OK) rc = finish_rng_window(ctx);
+    }
+    cudaStreamSynchronize(ctx->stream);
+    sc.release();
+    if (rc != DQMC_OK) return rc;
+    ctx->currentTimeslice = ctx->m;
+    ctx->performedSweeps += 1;
+    return DQMC_OK;
 }
 
 int dqmc_green_from_udt_host(dqmc_ctx* ctx, const double* Qr, const double* dr, const double* Tr, const double* Ql,

@@ -42,6 +42,7 @@ SYMBOLS = [
     ("dqmc_set_option", c_i32, [c_vp, c_i32, c_i32]),
     ("dqmc_download_config_stream", c_i32, [c_vp, c_i32, c_vp]),
     ("dqmc_wolff_cluster_move", c_i32, [c_vp, c_i32, c_vp]),
+    ("dqmc_sweep_simple", c_i32, [c_vp, c_i32]),
     ("dqmc_get_wolff_statistics", c_i32, [c_vp, c_i32, c_vp]),
     ("dqmc_launch_count", c_u64, [c_vp]),
     ("dqmc_rng_seed", c_i32, [c_vp, c_i32, c_u32, c_u32]),

@@ -310,6 +310,15 @@ class DetSDWBatch:
     def sweepThermalization(self):
         self._ck(self.lib.dqmc_sweep(self.h, 1))
 
+    def sweepSimple(self, takeMeasurements=False):
+        """greenUpdate = simple (detsdwopdim.cpp:4366-4393): G from scratch at every slice, then the slice update."""
+        if takeMeasurements:
+            raise DqmcError("fermionic measurements are outside the accelerated path (SURVEY 8f)")
+        self._ck(self.lib.dqmc_sweep_simple(self.h, 0))
+
+    def sweepSimpleThermalization(self):
+        self._ck(self.lib.dqmc_sweep_simple(self.h, 1))
+
     # ------------------------------------------------------------------ replica exchange interface
     def get_exchange_parameter_value(self, rep=0):
         out = c_f64()

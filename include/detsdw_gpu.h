@@ -138,10 +138,16 @@ public:
         check(dqmc_sweep(ctx, 1), "dqmc_sweep");
         ++performedSweeps;
     }
-    virtual void sweepSimple(bool) {
-        throw_GeneralError("DetSDWGpu: greenUpdate=simple is not served by the GPU path (use stabilized)");
+    // greenUpdate = simple (detsdwopdim.cpp:4366-4420): G from scratch at every slice, then the slice update
+    virtual void sweepSimple(bool takeMeasurements) {
+        check(dqmc_sweep_simple(ctx, 0), "dqmc_sweep_simple");
+        ++performedSweeps;
+        if (takeMeasurements) measureBosonic();
     }
-    virtual void sweepSimpleThermalization() { sweepSimple(false); }
+    virtual void sweepSimpleThermalization() {
+        check(dqmc_sweep_simple(ctx, 1), "dqmc_sweep_simple");
+        ++performedSweeps;
+    }
 
     virtual std::vector<ScalarObservable> getScalarObservables() {
         std::vector<ScalarObservable> obs;

@@ -198,6 +198,15 @@ int dqmc_logdet(dqmc_ctx* ctx, int rep, int gc, double* out);
 /* G at an arbitrary slice from scratch into a host buffer, leaving the sweep state untouched
  * (computeGreenFromScratch, detsdwopdim.cpp:4905-4933). */
 int dqmc_green_for_timeslice(dqmc_ctx* ctx, int rep, int gc, uint32_t k, double* out);
+/* sweepSimple(false) / sweepSimpleThermalization() (greenUpdate = simple; detmodel.h:718-758,
+ * detsdwopdim.cpp:4366-4420): for every slice k = 1..m the Green's function is recomputed from scratch and the slice is
+ * updated.  The reference inverts the plain product 1 + B(k,0) B(beta,k) built from the DENSE hopping exponential
+ * (computeBmatSDW, even with checkerboard = true); here the stabilised evaluation with the checkerboard B of the
+ * regular sweeps serves it, so G differs from the reference's by the O(dtau^2) break-up error and equals the G of
+ * dqmc_sweep.  O(m) from-scratch evaluations per sweep: a consistency tool for
+ * small systems.  The UDT storage of the stabilised sweeps is not maintained; call dqmc_setup_storage before going back
+ * to dqmc_sweep. */
+int dqmc_sweep_simple(dqmc_ctx* ctx, int thermalization);
 /* Numerical kernel under greenFromUdV (detmodel.h:768-818): G = [1 + M_r M_l]^-1 for two host
  * D x D matrices given as M_r = Q_r diag(d_r) T_r and M_l = T_l^dagger diag(d_l) Q_l^dagger
  * (all column-major; see DESIGN.md "UDT").  Test surface. */

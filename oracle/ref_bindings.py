@@ -179,6 +179,11 @@ class RefSdw:
         return out, sv
 
 
+    def sweep_simple(self, therm=False):
+        """sweepSimple(false) / sweepSimpleThermalization() (greenUpdate = simple, detsdwopdim.cpp:4366-4420)."""
+        if lib().ref_sdw_sweep_simple(self.h, c_i32(int(therm))):
+            raise RuntimeError("reference sweep failed")
+
     def measured_sweep(self):
         """sweep(takeMeasurements=True): returns the bosonic observables normMeanPhi, associatedEnergy, phiRhoS_Gs,
         phiRhoS_Gc (detsdwopdim.cpp:441-560, 903-918; the last two are zero unless opdim == 2)."""

@@ -110,6 +110,7 @@ struct SdwBase {
     virtual void save_config_stream(const char* dir, int binary) = 0;
     virtual void attempt_wolff(int shift, double* stats) = 0;
     virtual void measured_sweep(double* obs) = 0;
+    virtual void sweep_simple(int therm) = 0;
 };
 
 template <int OPDIM>
@@ -240,6 +241,11 @@ struct SdwImpl : public SdwBase {
         std::memcpy(d, st.d.memptr(), sizeof(double) * st.d.n_elem);
         std::memcpy(Vt, st.V_t.memptr(), sizeof(cpx_t) * st.V_t.n_elem);
     }
+    void sweep_simple(int therm) {
+        // greenUpdate = simple (detsdwopdim.cpp:4366-4420)
+        if (therm) rep->sweepSimpleThermalization();
+        else rep->sweepSimple(false);
+    }
     void measured_sweep(double* obs) {
         // sweep(takeMeasurements = true) with turnoffFermionMeasurements: the bosonic observables of
         // initMeasurements / measure / finishMeasurements (detsdwopdim.cpp:441-560, 903-918)
@@ -364,6 +370,16 @@ void ref_sdw_green_from_storage(void* h, uint32_t ll, uint32_t lr, double* out, 
 }
 
 // exchange probability, detsdwopdim.cpp:5251-5264
+int ref_sdw_sweep_simple(void* h, int therm) {
+    CoutSilencer q;
+    try {
+        static_cast<SdwBase*>(h)->sweep_simple(therm);
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "ref_sdw_sweep_simple: %s\n", e.what());
+        return 1;
+    }
+    return 0;
+}
 int ref_sdw_measured_sweep(void* h, double* obs) {
     CoutSilencer q;
     try {

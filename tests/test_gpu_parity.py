@@ -345,6 +345,28 @@ def test_wolff_cluster_moves_vs_reference_record():
         assert maxabs(b.rng_draw(4, rep=0), g[tag + "_rng_next"]) == 0.0
 
 
+def test_sweep_simple_vs_oracle():
+    """greenUpdate = simple (dqmc_sweep_simple): G from scratch at every slice, then the slice update -- against the
+    oracle restatement (plain inverse of 1 + B(k,0) B(m,k) with the checkerboard B): identical decisions, fields and
+    step sizes, G within the accuracy of the unstabilised inverse at beta = 2."""
+    from dqmc_oracle import SdwOracle, SdwParams
+    p = SdwParams(L=4, m=20, s=10, rngIndex=15)
+    o = SdwOracle(p)
+    b = make_batch(p, rng_indices=[15])
+    for it in range(3):
+        if it < 2:
+            o.sweep_simple_thermalization()
+            b.sweepSimpleThermalization()
+        else:
+            o.sweep_simple()
+            b.sweepSimple(False)
+        assert maxabs(b.phi()[1:], o.phi[1:]) < 1e-13
+        assert relerr(b.green(), o.green[0]) < 1e-8
+        assert b.control_data().lastAccRatioLocal_phi == o.last_acc_ratio
+        assert b.phi_delta() == o.phi_delta
+    assert maxabs(b.rng_draw(4), [o.rng.rand01() for _ in range(4)]) == 0.0
+
+
 def test_bosonic_observables_vs_golden():
     """The observables of a measured sweep (normMeanPhi, associatedEnergy, phiRhoS_Gs, phiRhoS_Gc) from the fields
     on the device against the values the reference measured for the same fields (tests/golden/bosonic_observables.npz)."""

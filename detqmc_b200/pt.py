@@ -106,7 +106,13 @@ class DetQMCPT:
         self.batch.exchange_pack(self.payload.data_ptr(), L.n_uniforms)
         with self.torch.cuda.stream(self.stream):
             if self.world > 1:
-                self.dist.all_gather_into_tensor(self.gathered, self.payload)
+                if self.dist.get_backend() == "nccl":
+                    self.dist.all_gather_into_tensor(self.gathered, self.payload)
+                else:                                # gloo (tests of the multi-rank logic): through the host
+                    self.stream.synchronize()
+                    parts = [self.torch.zeros(L.payload_len, dtype=self.torch.float64) for _ in range(self.world)]
+                    self.dist.all_gather(parts, self.payload.cpu())
+                    self.gathered.copy_(self.torch.cat(parts))
                 self.host_gathered.copy_(self.gathered, non_blocking=True)
             else:
                 self.host_gathered.copy_(self.payload, non_blocking=True)
@@ -129,7 +135,7 @@ class DetQMCPT:
         streams = self.batch.config_stream(-1)
         cpis = self.local_parameter_indices()
         for i in range(self.n_local):
-            self.configs.append((int(cpis[i]), streams[i].copy()))
+            self.configs.append((self.sweepsDone, int(cpis[i]), streams[i].copy()))
 
     # ------------------------------------------------------------------ run, detqmcpt.h:760-958
     def run(self):
@@ -195,15 +201,15 @@ class DetQMCPT:
                         f.write("".join("%.15g\n" % x for x in v))
                     err = float(v.std(ddof=1) / np.sqrt(len(v))) if len(v) > 1 else 0.0
                     res.write("%s\t%.15g\t%.15g\n" % (o, float(v.mean()) if len(v) else 0.0, err))
-        for part in cfgs:
-            for cpi, cfg in part:
-                d = self.subdir(cpi)
-                if self.cfgBinary:
-                    with open(os.path.join(d, "configs-phi.binarystream"), "ab") as f:
-                        f.write(cfg.tobytes())
-                if self.cfgText:
-                    with open(os.path.join(d, "configs-phi.textstream"), "a") as f:
-                        f.write("".join("%.14e\n" % v for v in cfg))
+        # every stream in the order the configurations were buffered (detqmcpt.h:702-757), whichever rank held them
+        for _, cpi, cfg in sorted((c for part in cfgs for c in part), key=lambda c: (c[0], c[1])):
+            d = self.subdir(cpi)
+            if self.cfgBinary:
+                with open(os.path.join(d, "configs-phi.binarystream"), "ab") as f:
+                    f.write(cfg.tobytes())
+            if self.cfgText:
+                with open(os.path.join(d, "configs-phi.textstream"), "a") as f:
+                    f.write("".join("%.14e\n" % v for v in cfg))
         L = self.ladder
         with open(os.path.join(self.outdir, "exchange-parameters.values"), "w") as f:
             f.write("## Control parameter values\n## control parameter index \t control parameter value\n")
@@ -221,3 +227,55 @@ class DetQMCPT:
                 tot = L.count_up[c] + L.count_down[c]
                 f.write("%d\t%.15g\n" % (c, (L.count_up[c] / tot) if tot else 0.0))
         self.records, self.configs = [], []
+
+
+def main(argv=None):
+    """MPI-free launcher: `python -m torch.distributed.run --nproc-per-node G -m detqmc_b200.pt key=value ...` (or
+    plain `python -m detqmc_b200.pt ...` on one GPU).  Keys follow the reference's option names
+    (maindetqmcsdwopdim.cpp:93-135, detqmcptparams): model parameters of DetSDW, thermalization, sweeps,
+    measureInterval, exchangeInterval, controlParameterValues=v0,v1,..., rngSeed, simindex, outdir,
+    saveConfigurationStreamInterval / Binary / Text."""
+    import sys
+    import torch
+    import torch.distributed as dist
+    args = dict(a.split("=", 1) for a in (sys.argv[1:] if argv is None else argv))
+    if "WORLD_SIZE" in os.environ and int(os.environ["WORLD_SIZE"]) > 1 and not dist.is_initialized():
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    values = [float(v) for v in args.pop("controlParameterValues").split(",")]
+    mc = {}
+    for key, conv in (("thermalization", int), ("sweeps", int), ("measureInterval", int), ("exchangeInterval", int),
+                      ("saveConfigurationStreamInterval", int), ("rngSeed", int), ("simindex", int)):
+        if key in args:
+            mc[key] = conv(args.pop(key))
+    for key in ("saveConfigurationStreamBinary", "saveConfigurationStreamText"):
+        if key in args:
+            mc[key] = args.pop(key).lower() in ("1", "true", "yes")
+    outdir = args.pop("outdir", ".")
+    model = {}
+    for key, val in args.items():
+        if val.lower() in ("true", "false"):
+            model[key] = val.lower() == "true"
+        else:
+            try:
+                model[key] = int(val)
+            except ValueError:
+                model[key] = float(val)
+    if "beta" in model:                                   # the reference derives m from beta and dtau
+        model["m"] = int(round(model.pop("beta") / model.get("dtau", 0.1)))
+    mc.setdefault("thermalization", 10)
+    mc.setdefault("sweeps", 10)
+    pt = DetQMCPT(model, values, outdir=outdir, **mc)
+    pt.run()
+    if pt.rank == 0:
+        print("DetQMCPT finished: %d + %d sweeps of %d replicas on %d rank(s); exchange acceptance %s"
+              % (pt.sweepsDoneThermalization, pt.sweepsDone, pt.P, pt.world,
+                 ", ".join("%.2f" % (a / max(1, p)) for a, p in zip(pt.ladder.accepted[:pt.P - 1],
+                                                                    pt.ladder.proposed[:pt.P - 1]))))
+    if dist.is_initialized():
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -485,6 +485,57 @@ def test_parallel_tempering_driver_vs_oracle_loop(tmp_path):
                        rtol=1e-12, atol=0)
 
 
+def _pt_rank(rank, world, port, outdir):
+    import os
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from detqmc_b200 import DetQMCPT
+    from dqmc_oracle import SdwParams
+    values = np.array([-1.6, -1.2, -0.8, -0.4])
+    pt = DetQMCPT(SdwParams(L=4, m=20, s=10), values, thermalization=3, sweeps=3, exchangeInterval=1,
+                  saveConfigurationStreamInterval=1, saveConfigurationStreamBinary=True, outdir=outdir, device=0)
+    pt.run()
+    if rank == 0:
+        np.save(os.path.join(outdir, "process_par.npy"), pt.ladder.process_par)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_parallel_tempering_two_ranks_equal_one_rank(tmp_path):
+    """The ladder split over two processes (two contexts on the one GPU of the test box, payloads all-gathered with
+    gloo) gives the same files as a single process holding all replicas: the multi-rank path of DetQMCPT -- rank
+    offsets of the random-number streams, payload layout, identical ladder walk on every rank, gather of the records
+    and configuration streams to rank 0."""
+    import os
+    import socket
+    import torch.multiprocessing as mp
+    from detqmc_b200 import DetQMCPT
+    from dqmc_oracle import SdwParams
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    two = tmp_path / "two"
+    one = tmp_path / "one"
+    two.mkdir()
+    one.mkdir()
+    mp.spawn(_pt_rank, args=(2, port, str(two)), nprocs=2, join=True)
+    values = np.array([-1.6, -1.2, -0.8, -0.4])
+    pt = DetQMCPT(SdwParams(L=4, m=20, s=10), values, thermalization=3, sweeps=3, exchangeInterval=1,
+                  saveConfigurationStreamInterval=1, saveConfigurationStreamBinary=True, outdir=str(one))
+    pt.run()
+    assert list(np.load(str(two / "process_par.npy"))) == list(pt.ladder.process_par)
+    for c in range(len(values)):
+        sub = os.path.basename(pt.subdir(c))
+        for name in ("normMeanPhi.series", "associatedEnergy.series", "phiRhoS_Gs.series", "phiRhoS_Gc.series",
+                     "configs-phi.binarystream"):
+            assert open(str(one / sub / name), "rb").read() == open(str(two / sub / name), "rb").read(), (sub, name)
+    for name in ("exchange-acceptance.values", "exchange-diffusion.values", "exchange-parameters.values"):
+        assert open(str(one / name)).read() == open(str(two / name)).read()
+
+
 # ---------------------------------------------------------------- full-size checks
 @pytest.mark.parametrize("kw", [dict(L=12, m=100, s=10), dict(L=8, m=80, s=10)])
 def test_full_size_properties(kw):

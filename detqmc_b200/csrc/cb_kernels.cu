@@ -81,13 +81,93 @@ void expm4(const zc* A, zc* out) {
 
 }  // namespace
 
+// exp(pf * h_plaquette) for the plaquette (i, j = i + x, k = i + y, l = k + x) with lower-left corner (i1, i2) of
+// band `band`; pf = sign * dtau (/2): detsdwopdim.cpp:1597-1684 (flux), 1786-1826 (no flux)
+static void plaquette_matrix(const dqmc_params& p, int band, int i1, int i2, double pf, zc* M) {
+    const int L = p.L, N = L * L;
+    const double pi = M_PI;
+    double hh = band == 0 ? p.txhor : p.tyhor, hv = band == 0 ? p.txver : p.tyver;
+    if ((p.bc == 1 || p.bc == 3) && i1 == L - 1) hh = -hh;
+    if ((p.bc == 2 || p.bc == 3) && i2 == L - 1) hv = -hv;
+    if (!p.weakZflux) {
+        const double chh = std::cosh(pf * hh), shh = std::sinh(-pf * hh);
+        const double chv = std::cosh(pf * hv), shv = std::sinh(-pf * hv);
+        const double a = chh * chv, b = chv * shh, c = chh * shv, d = shh * shv;
+        const double m4[16] = {a, b, c, d, b, a, d, c, c, d, a, b, d, c, b, a};
+        for (int i = 0; i < 16; ++i) M[i] = m4[i];
+        return;
+    }
+    const double zmag = 1.0 / N;
+    const int j1 = (i1 + 1) % L, k2 = (i2 + 1) % L;
+    const zc ph_ij = std::exp(zc(0, -2.0 * pi * zmag * i2));
+    const zc ph_kl = std::exp(zc(0, -2.0 * pi * zmag * k2));
+    zc ph_ik = 1.0, ph_jl = 1.0;
+    if (i2 == L - 1) {
+        ph_ik = std::exp(zc(0, 2.0 * pi * zmag * L * i1));
+        ph_jl = std::exp(zc(0, 2.0 * pi * zmag * L * j1));
+    }
+    zc H[16];
+    for (int i = 0; i < 16; ++i) H[i] = 0;
+    H[0 * 4 + 1] = ph_ij * hh;
+    H[0 * 4 + 2] = ph_ik * hv;
+    H[1 * 4 + 3] = ph_jl * hv;
+    H[2 * 4 + 3] = ph_kl * hh;
+    zc Hs[16];
+    for (int r = 0; r < 4; ++r)
+        for (int c = 0; c < 4; ++c) Hs[r * 4 + c] = -pf * (H[r * 4 + c] + std::conj(H[c * 4 + r]));
+    expm4(Hs, M);
+}
+
+// Dense block-diagonal D x D matrices of shiftGreenSymmetric (detsdwopdim.cpp:4505-4612, CB_ASSAAD_BERG): block b
+// (band b % 2) of SL is E0(-dtau/2) E1(-dtau/2), of SR it is E1(+dtau/2) E0(+dtau/2), E_s = product of the disjoint
+// plaquette exponentials of subgroup s (no chemical potential: it cancels between the two sides).  Column-major.
+void cb_build_shift_matrices(const dqmc_params& p, int msf, std::vector<cplx>& SL, std::vector<cplx>& SR) {
+    const int L = p.L, N = L * L, D = msf * N;
+    SL.assign(size_t(D) * D, make_double2(0, 0));
+    SR.assign(size_t(D) * D, make_double2(0, 0));
+    auto subgroup = [&](int band, int sg, double pf, std::vector<zc>& E) {
+        E.assign(size_t(N) * N, zc(0));
+        for (int i2 = sg; i2 < L; i2 += 2)
+            for (int i1 = sg; i1 < L; i1 += 2) {
+                const int i = i2 * L + i1, j = i2 * L + (i1 + 1) % L, k = ((i2 + 1) % L) * L + i1,
+                          l = ((i2 + 1) % L) * L + (i1 + 1) % L;
+                const int idx[4] = {i, j, k, l};
+                zc M[16];
+                plaquette_matrix(p, band, i1, i2, pf, M);
+                for (int r = 0; r < 4; ++r)
+                    for (int c = 0; c < 4; ++c) E[size_t(idx[c]) * N + idx[r]] = M[r * 4 + c];     // column-major
+            }
+    };
+    auto matmul = [&](const std::vector<zc>& A, const std::vector<zc>& B, std::vector<zc>& C) {
+        C.assign(size_t(N) * N, zc(0));
+        for (int c = 0; c < N; ++c)
+            for (int k = 0; k < N; ++k) {
+                const zc b = B[size_t(c) * N + k];
+                if (b == zc(0)) continue;
+                for (int r = 0; r < N; ++r) C[size_t(c) * N + r] += A[size_t(k) * N + r] * b;
+            }
+    };
+    const double h = 0.5 * p.dtau;
+    for (int band = 0; band < 2; ++band) {
+        std::vector<zc> E0m, E1m, E0p, E1p, Lm, Rm;
+        subgroup(band, 0, -h, E0m); subgroup(band, 1, -h, E1m);
+        subgroup(band, 0, +h, E0p); subgroup(band, 1, +h, E1p);
+        matmul(E0m, E1m, Lm);
+        matmul(E1p, E0p, Rm);
+        for (int b = band; b < msf; b += 2)
+            for (int c = 0; c < N; ++c)
+                for (int r = 0; r < N; ++r) {
+                    const zc l = Lm[size_t(c) * N + r], rr = Rm[size_t(c) * N + r];
+                    SL[size_t(b * N + c) * D + b * N + r] = make_double2(l.real(), l.imag());
+                    SR[size_t(b * N + c) * D + b * N + r] = make_double2(rr.real(), rr.imag());
+                }
+    }
+}
+
 void cb_build_tables(const dqmc_params& p, std::vector<cplx>& out) {
     const int L = p.L, N = L * L, nplaq = N / 4, half = L / 2;
     out.assign(size_t(2) * 2 * 2 * nplaq * 8, make_double2(0, 0));
-    const double pi = M_PI;
     for (int band = 0; band < 2; ++band) {
-        const double th = band == 0 ? p.txhor : p.tyhor;
-        const double tv = band == 0 ? p.txver : p.tyver;
         const double mu = band == 0 ? p.mux : p.muy;
         for (int si = 0; si < 2; ++si) {
             const double sign = si == 0 ? -1.0 : +1.0;
@@ -98,40 +178,8 @@ void cb_build_tables(const dqmc_params& p, std::vector<cplx>& out) {
                 for (int q = 0; q < nplaq; ++q) {
                     const int i1 = 2 * (q % half) + subgroup;     // x
                     const int i2 = 2 * (q / half) + subgroup;     // y
-                    double hh = th, hv = tv;
-                    if ((p.bc == 1 || p.bc == 3) && i1 == L - 1) hh = -hh;
-                    if ((p.bc == 2 || p.bc == 3) && i2 == L - 1) hv = -hv;
                     zc M[16];
-                    if (!p.weakZflux) {
-                        // (2x2 horizontal) x (2x2 vertical), detsdwopdim.cpp:1817-1820
-                        const double chh = std::cosh(pf * hh), shh = std::sinh(-pf * hh);
-                        const double chv = std::cosh(pf * hv), shv = std::sinh(-pf * hv);
-                        const double a = chh * chv, b = chv * shh, c = chh * shv, d = shh * shv;
-                        const double m4[16] = {a, b, c, d, b, a, d, c, c, d, a, b, d, c, b, a};
-                        for (int i = 0; i < 16; ++i) M[i] = m4[i];
-                    } else {
-                        // Peierls phases, detsdwopdim.cpp:1647-1666; zmag = +1/N for both bands
-                        const double zmag = 1.0 / N;
-                        const int j1 = (i1 + 1) % L, k2 = (i2 + 1) % L;
-                        const zc ph_ij = std::exp(zc(0, -2.0 * pi * zmag * i2));
-                        const zc ph_kl = std::exp(zc(0, -2.0 * pi * zmag * k2));
-                        zc ph_ik = 1.0, ph_jl = 1.0;
-                        if (i2 == L - 1) {
-                            ph_ik = std::exp(zc(0, 2.0 * pi * zmag * L * i1));
-                            ph_jl = std::exp(zc(0, 2.0 * pi * zmag * L * j1));
-                        }
-                        zc H[16];
-                        for (int i = 0; i < 16; ++i) H[i] = 0;
-                        H[0 * 4 + 1] = ph_ij * hh;
-                        H[0 * 4 + 2] = ph_ik * hv;
-                        H[1 * 4 + 3] = ph_jl * hv;
-                        H[2 * 4 + 3] = ph_kl * hh;
-                        zc Hs[16];
-                        for (int r = 0; r < 4; ++r)
-                            for (int c = 0; c < 4; ++c)
-                                Hs[r * 4 + c] = -pf * (H[r * 4 + c] + std::conj(H[c * 4 + r]));
-                        expm4(Hs, M);
-                    }
+                    plaquette_matrix(p, band, i1, i2, pf, M);
                     // exp of a Hermitian block is Hermitian; symmetrise the round-off and compress
                     cplx* dst = out.data() + ((size_t(band) * 2 + si) * 2 + pass) * 8 * nplaq + q;
                     double dg[4];

@@ -926,16 +926,64 @@ int lanes_join(dqmc_ctx* ctx) {
 }
 
 // sweepDown / sweepUp, detmodel.h:1261-1399
+// ---- fermionic measurements (DetSDW::measure, detsdwopdim.cpp:540-900) ---------------------------------
+size_t fm_acc_len(const dqmc_ctx* ctx) {
+    const size_t nb = size_t(2 * ctx->p.L - 1) * (2 * ctx->p.L - 1);
+    return 3 + 4 * nb + 2 * size_t(ctx->N);
+}
+
+int fm_prepare(dqmc_ctx* ctx) {
+    if (ctx->fmAcc) return DQMC_OK;
+    std::vector<cplx> SL, SR;
+    cb_build_shift_matrices(ctx->p, ctx->msf, SL, SR);
+    CK(dmalloc(&ctx->shiftL, SL.size()));
+    CK(dmalloc(&ctx->shiftR, SR.size()));
+    CK(cudaMemcpy(ctx->shiftL, SL.data(), SL.size() * sizeof(cplx), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->shiftR, SR.data(), SR.size() * sizeof(cplx), cudaMemcpyHostToDevice));
+    ctx->fmAccLen = fm_acc_len(ctx);
+    CK(dmalloc(&ctx->fmAcc, ctx->fmAccLen * ctx->R));
+    return DQMC_OK;
+}
+
+// measure(k) for the replicas of the current lane: gs = shiftGreenSymmetric(G) as two products with the block-diagonal
+// half-step hopping matrices (:4505-4612), then the accumulation kernel
+int measure_slice(dqmc_ctx* ctx) {
+    const int ro = ctx->laneOff, rc = ctx->laneCnt, D = ctx->D;
+    const size_t dd = DD(ctx);
+    cplx* G = ctx->G + size_t(ro) * dd;
+    cplx* T = ctx->W[0] + size_t(ro) * dd;
+    cplx* gs = ctx->W[1] + size_t(ro) * dd;
+    GemmArgs g;
+    g.M = g.N = g.K = D;
+    g.transa = g.transb = 0;
+    g.rowscale = g.colscale = g.kscale = nullptr;
+    g.strideRow = g.strideCol = g.strideK = 0;
+    g.alpha = 1.0; g.beta = 0.0; g.kvec = nullptr; g.b_kmajor = 0;
+    g.batch = rc;
+    g.A = G; g.lda = D; g.strideA = (long long)dd;
+    g.B = ctx->shiftR; g.ldb = D; g.strideB = 0;
+    g.C = T; g.ldc = D; g.strideC = (long long)dd;
+    CKL(gemm_launch(g, ctx->stream));
+    g.A = ctx->shiftL; g.strideA = 0;
+    g.B = T; g.strideB = (long long)dd;
+    g.C = gs;
+    CKL(gemm_launch(g, ctx->stream));
+    CKL(launch_fermion_measure(gs, (long long)dd, ctx->N, ctx->p.L, ctx->msf, ctx->fmAcc + size_t(ro) * ctx->fmAccLen,
+                               (long long)ctx->fmAccLen, rc, ctx->stream));
+    return DQMC_OK;
+}
+
+// `mode`: 0 sweep, 1 thermalisation sweep (step-size adaptation), 2 sweep with fermionic measurements after every slice
 int sweep_down(dqmc_ctx* ctx, int therm) {
     const int n = ctx->n, s = ctx->s, m = ctx->m;
     RET(lanes_fork(ctx));
     for (int k = m; k >= (n - 1) * s + 1; --k) {
-        RET(for_each_lane(ctx, [&] { RET(launch_update(ctx, k, therm)); return wrap_down(ctx, k); }));
+        RET(for_each_lane(ctx, [&] { RET(launch_update(ctx, k, therm == 1)); if (therm == 2) RET(measure_slice(ctx)); return wrap_down(ctx, k); }));
     }
     for (int l = n - 1; l >= 1; --l) {
         RET(for_each_lane(ctx, [&] { return advance_down(ctx, l + 1); }));
         for (int k = l * s; k >= (l - 1) * s + 1; --k) {
-            RET(for_each_lane(ctx, [&] { RET(launch_update(ctx, k, therm)); return wrap_down(ctx, k); }));
+            RET(for_each_lane(ctx, [&] { RET(launch_update(ctx, k, therm == 1)); if (therm == 2) RET(measure_slice(ctx)); return wrap_down(ctx, k); }));
         }
     }
     RET(for_each_lane(ctx, [&] { return advance_down(ctx, 1); }));
@@ -949,12 +997,12 @@ int sweep_up(dqmc_ctx* ctx, int therm) {
     RET(lanes_fork(ctx));
     for (int l = 0; l <= n - 2; ++l) {
         for (int k = l * s + 1; k <= (l + 1) * s; ++k) {
-            RET(for_each_lane(ctx, [&] { RET(wrap_up(ctx, k - 1)); return launch_update(ctx, k, therm); }));
+            RET(for_each_lane(ctx, [&] { RET(wrap_up(ctx, k - 1)); RET(launch_update(ctx, k, therm == 1)); return therm == 2 ? measure_slice(ctx) : DQMC_OK; }));
         }
         RET(for_each_lane(ctx, [&] { return advance_up(ctx, l); }));
     }
     for (int k = (n - 1) * s + 1; k <= m; ++k) {
-        RET(for_each_lane(ctx, [&] { RET(wrap_up(ctx, k - 1)); return launch_update(ctx, k, therm); }));
+        RET(for_each_lane(ctx, [&] { RET(wrap_up(ctx, k - 1)); RET(launch_update(ctx, k, therm == 1)); return therm == 2 ? measure_slice(ctx) : DQMC_OK; }));
     }
     RET(for_each_lane(ctx, [&] { return advance_up(ctx, n - 1); }));
     RET(lanes_join(ctx));
@@ -1233,7 +1281,7 @@ void dqmc_destroy(dqmc_ctx* ctx) {
                    ctx->stQ, ctx->stT, ctx->stD, ctx->bkQ, ctx->bkT, ctx->bkD, ctx->phi, ctx->coshT, ctx->sinhT,
                    ctx->bkPhi, ctx->bkCosh, ctx->bkSinh, ctx->rvals, ctx->tau, ctx->perm, ctx->colnorm, ctx->vecA,
                    ctx->vecB, ctx->vecC, ctx->vecD, ctx->dtmp, ctx->logdet, ctx->bkLogdet, ctx->consistency, ctx->eyeM,
-                   ctx->onesV, ctx->X, ctx->Y, ctx->cfgStream, ctx->rngbuf, ctx->cursor, ctx->ctrl, ctx->accepted, ctx->errflag,
+                   ctx->onesV, ctx->X, ctx->Y, ctx->cfgStream, ctx->shiftL, ctx->shiftR, ctx->fmAcc, ctx->rngbuf, ctx->cursor, ctx->ctrl, ctx->accepted, ctx->errflag,
                    ctx->actions, ctx->shiftbuf, ctx->cbtab, ctx->acceptedTotal, ctx->siteState, ctx->kvec, ctx->aux,
                    ctx->propT, ctx->propTinv, ctx->hubScale, ctx->hubTmp, ctx->hubReal};
     for (void* p : dev) if (p) cudaFree(p);
@@ -1754,6 +1802,56 @@ int dqmc_wolff_cluster_move(dqmc_ctx* ctx, int with_shift, int32_t* accepted) {
     return DQMC_OK;
 }
 
+// finishMeasurements (detsdwopdim.cpp:903-1000, fermionic part) for one replica after dqmc_sweep(ctx, 2)
+int dqmc_get_fermionic_observables(dqmc_ctx* ctx, int rep, double* scalars, double* vectors) {
+    if (!valid_rep(ctx, rep) || !scalars || !vectors) return DQMC_ERR_PARAM;
+    if (!ctx->fmAcc || ctx->fmSlices != ctx->m) { ctx->err = "no measured sweep (dqmc_sweep(ctx, 2)) yet"; return DQMC_ERR_STATE; }
+    const int N = ctx->N, L = ctx->p.L, m = ctx->m, w = 2 * L - 1;
+    const size_t nb = size_t(w) * w;
+    std::vector<double> acc(ctx->fmAccLen);
+    CK(cudaMemcpyAsync(acc.data(), ctx->fmAcc + size_t(rep) * ctx->fmAccLen, sizeof(double) * ctx->fmAccLen,
+                       cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    scalars[0] = acc[0] / m;                             // greenK0
+    scalars[1] = acc[1] / m;                             // greenLocal
+    scalars[2] = acc[2] / m;                             // occDiffSq
+    const double* binsX = acc.data() + 3;
+    const double* binsY = binsX + 2 * nb;
+    const double* pairPlus = binsY + 2 * nb;
+    const double* pairMinus = pairPlus + N;
+    // momentum-space occupation: k = -pi + (index + offset) 2 pi / L, offset 1/2 along antiperiodic directions (:623-671)
+    const double offx = (ctx->p.bc == 1 || ctx->p.bc == 3) ? 0.5 : 0.0, offy = (ctx->p.bc == 2 || ctx->p.bc == 3) ? 0.5 : 0.0;
+    for (int ks = 0; ks < N; ++ks) {
+        const double ky = -M_PI + (double(ks / L) + offy) * 2.0 * M_PI / L;
+        const double kx = -M_PI + (double(ks % L) + offx) * 2.0 * M_PI / L;
+        double sx = 0, sy = 0;
+        for (int dy = 0; dy < w; ++dy)
+            for (int dx = 0; dx < w; ++dx) {
+                const double arg = kx * (dx - (L - 1)) + ky * (dy - (L - 1));
+                const double c = std::cos(arg), sn = std::sin(arg);
+                const size_t bi = size_t(dy) * w + dx;
+                sx += c * binsX[2 * bi] - sn * binsX[2 * bi + 1];
+                sy += c * binsY[2 * bi] - sn * binsY[2 * bi + 1];
+            }
+        vectors[ks] = 2.0 - sx / (double(m) * N);        // kOccX
+        vectors[N + ks] = 2.0 - sy / (double(m) * N);    // kOccY
+    }
+    for (int i = 0; i < N; ++i) {
+        vectors[2 * N + i] = pairPlus[i] / m;
+        vectors[3 * N + i] = pairMinus[i] / m;
+    }
+    // average over the nine sites around the maximum range (L/2, L/2), :973-987
+    double pp = 0, pm = 0;
+    for (int yy = L / 2 - 1; yy <= L / 2 + 1; ++yy)
+        for (int xx = L / 2 - 1; xx <= L / 2 + 1; ++xx) {
+            pp += vectors[2 * N + yy * L + xx];
+            pm += vectors[3 * N + yy * L + xx];
+        }
+    scalars[3] = pp / 9.0;
+    scalars[4] = pm / 9.0;
+    return DQMC_OK;
+}
+
 int dqmc_get_wolff_statistics(dqmc_ctx* ctx, int rep, double* out) {
     if (!valid_rep(ctx, rep) || !out) return DQMC_ERR_PARAM;
     for (int i = 0; i < 5; ++i) out[i] = ctx->wolffStats[size_t(5) * rep + i];
@@ -1772,6 +1870,12 @@ int dqmc_phi_action(dqmc_ctx* ctx, double* out) {
 
 int dqmc_sweep(dqmc_ctx* ctx, int thermalization) {
     if (!ctx) return DQMC_ERR_PARAM;
+    if (thermalization == 2) {                     // sweep(true): fermionic measurements after every slice
+        if (ctx->p.model != DQMC_MODEL_SDW) { ctx->err = "fermionic measurements are defined for DetSDW"; return DQMC_ERR_STATE; }
+        RET(fm_prepare(ctx));
+        CK(cudaMemsetAsync(ctx->fmAcc, 0, sizeof(double) * ctx->fmAccLen * ctx->R, ctx->stream));
+        ctx->fmSlices = ctx->m;
+    }
     const bool preloaded = ctx->rngResident && !ctx->rngAuto;          // explicit dqmc_rng_preload
     if (preloaded && size_t(ctx->rngWindow) < ctx->rngResidentUsedBound + ctx->rngCap + 8) {
         ctx->err = "resident random-number window too small for another sweep";

@@ -50,6 +50,7 @@ struct CbLaunch {
 int cb_table_count(const CbGeom& g);                    // number of cplx in the table
 // host-side construction of the plaquette tables from the model parameters
 void cb_build_tables(const dqmc_params& p, std::vector<cplx>& out);
+void cb_build_shift_matrices(const dqmc_params& p, int msf, std::vector<cplx>& SL, std::vector<cplx>& SR);
 cudaError_t cb_launch(const CbGeom& g, const CbLaunch& a, cudaStream_t st);
 
 // dense elementwise helpers (misc_kernels.cu)
@@ -67,6 +68,8 @@ cudaError_t launch_shift_fields(double* phi, const double* shift, int N, int opd
 cudaError_t launch_phi_action(const double* phi, const double* rvals, double* out, int L, int opdim, int m,
                               double dtau, double c, double u, long long stridePhi, int batch,
                               cudaStream_t st);
+cudaError_t launch_fermion_measure(const cplx* gs, long long strideG, int N, int L, int msf, double* acc, long long strideAcc,
+                                   int batch, cudaStream_t st);
 cudaError_t launch_config_stream(const double* phi, double* out, int L, int opdim, int m, long long stridePhi,
                                  long long strideOut, int batch, cudaStream_t st);
 cudaError_t launch_exchange_action(const double* phi, double* out, int N, int opdim, int m, double dtau,
@@ -253,6 +256,8 @@ struct dqmc_ctx {
     double* consistency;   // [nmat]
     dqmc::cplx* X; dqmc::cplx* Y;   // [R][D*KMAX]
     double* cfgStream;               // [R][N*m*opdim] configuration-stream staging (allocated on first use)
+    // fermionic measurements (allocated on first use): block-diagonal shift matrices, per-replica accumulators
+    dqmc::cplx* shiftL; dqmc::cplx* shiftR; double* fmAcc; size_t fmAccLen; int fmSlices;
     int kmax;
     double* rngbuf;        // [R][rngCap]
     size_t rngCap;

@@ -257,4 +257,137 @@ cudaError_t launch_exchange_action(const double* phi, double* out, int N, int op
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------
+// Fermionic measurements of one time slice (DetSDW::measure, detsdwopdim.cpp:540-900) from the symmetrically shifted
+// Green's function gs (column-major D x D): accumulates into the per-replica buffer
+//   acc = [ greenK0 | greenLocal | occDiffSq | binsX (cplx, (2L-1)^2) | binsY (cplx) | pairPlus (N) | pairMinus (N) ]
+// binsX/Y[dy][dx] = sum over site pairs with r_i - r_j = (dx, dy) of the band-diagonal, spin-summed Green's function:
+// the momentum-space occupation (an O(N^3) loop in the reference, :623-671) is their Fourier sum, taken at the end.
+// Band-spin blocks XUP = 0, YDOWN = 1, XDOWN = 2, YUP = 3; for MSF = 2 only XUP / YDOWN are stored and the
+// XDOWN / YUP sector is their complex conjugate (gl1, :598-615).  One CTA per replica.
+// ------------------------------------------------------------------------------------------------
+template <int MSF>
+__device__ __forceinline__ cplx fm_gl1(const cplx* __restrict__ gs, int D, int N, int s1, int bs1, int s2, int bs2) {
+    if (MSF == 4) return gs[size_t(s2 + N * bs2) * D + s1 + N * bs1];
+    if (bs1 < 2 && bs2 < 2) return gs[size_t(s2 + N * bs2) * D + s1 + N * bs1];
+    if (bs1 >= 2 && bs2 >= 2) {
+        const cplx v = gs[size_t(s2 + N * (bs2 - 2)) * D + s1 + N * (bs1 - 2)];
+        return make_double2(v.x, -v.y);
+    }
+    return make_double2(0, 0);
+}
+__device__ __forceinline__ cplx fm_mul(cplx a, cplx b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ cplx fm_add(cplx a, cplx b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ cplx fm_sub(cplx a, cplx b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ cplx fm_scale(double f, cplx a) { return make_double2(f * a.x, f * a.y); }
+
+__device__ __forceinline__ double fm_block_sum(double v, double* red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    double t = 0;
+    for (int w = 0; w < nw; ++w) t += red[w];
+    return t;
+}
+
+template <int MSF>
+__global__ void __launch_bounds__(256) fermion_measure_kernel(const cplx* __restrict__ gsAll, long long strideG, int N,
+                                                              int L, double* __restrict__ accAll, long long strideAcc) {
+    extern __shared__ double fm_smem[];
+    __shared__ double red[8];
+    const int D = MSF * N, nb = (2 * L - 1) * (2 * L - 1);
+    const cplx* gs = gsAll + size_t(blockIdx.x) * strideG;
+    double* acc = accAll + size_t(blockIdx.x) * strideAcc;
+    double* bins = fm_smem;                                  // [2][nb] complex
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 4 * nb; i += blockDim.x) bins[i] = 0.0;
+    // scalar functions of the Green's function (:569-593)
+    double sre = 0, tr = 0;
+    for (size_t e = tid; e < size_t(D) * D; e += blockDim.x) {
+        const cplx v = gs[e];
+        sre += v.x;
+        if (int(e / D) == int(e % D)) tr += v.x;
+    }
+    const double f = MSF == 4 ? 1.0 : 2.0;
+    const double ssum = fm_block_sum(sre, red), strace = fm_block_sum(tr, red);
+    // displacement bins of the band-diagonal, spin-summed Green's function
+    for (int e = tid; e < N * N; e += blockDim.x) {
+        const int i = e % N, j = e / N;
+        const int dx = i % L - j % L + L - 1, dy = i / L - j / L + L - 1;
+        const cplx gx = fm_add(fm_gl1<MSF>(gs, D, N, i, 0, j, 0), fm_gl1<MSF>(gs, D, N, i, 2, j, 2));
+        const cplx gy = fm_add(fm_gl1<MSF>(gs, D, N, i, 3, j, 3), fm_gl1<MSF>(gs, D, N, i, 1, j, 1));
+        const int bi = dy * (2 * L - 1) + dx;
+        atomicAdd(&bins[2 * bi], gx.x);
+        atomicAdd(&bins[2 * bi + 1], gx.y);
+        atomicAdd(&bins[2 * nb + 2 * bi], gy.x);
+        atomicAdd(&bins[2 * nb + 2 * bi + 1], gy.y);
+    }
+    __syncthreads();
+    for (int i = tid; i < 4 * nb; i += blockDim.x) acc[3 + i] += bins[i];
+    // equal-time pairing correlations (:673-718): band b, spin sp -> block (b == 0 ? (sp == 0 ? 0 : 2) : (sp == 0 ? 3 : 1))
+    double* pairPlus = acc + 3 + 4 * nb;
+    double* pairMinus = pairPlus + N;
+    for (int i = tid; i < N; i += blockDim.x) {
+        cplx pp = make_double2(0, 0), pm = make_double2(0, 0);
+#pragma unroll
+        for (int pr = 0; pr < 2; ++pr) {
+            const int a = pr == 0 ? i : 0, b = pr == 0 ? 0 : i;
+#pragma unroll
+            for (int b1 = 0; b1 < 2; ++b1)
+#pragma unroll
+                for (int b2 = 0; b2 < 2; ++b2) {
+                    const int u1 = b1 == 0 ? 0 : 3, d1 = b1 == 0 ? 2 : 1;       // up / down blocks of band b1
+                    const int u2 = b2 == 0 ? 0 : 3, d2 = b2 == 0 ? 2 : 1;
+                    const cplx t = fm_sub(fm_mul(fm_gl1<MSF>(gs, D, N, a, d1, b, u2), fm_gl1<MSF>(gs, D, N, a, u1, b, d2)),
+                                          fm_mul(fm_gl1<MSF>(gs, D, N, a, d1, b, d2), fm_gl1<MSF>(gs, D, N, a, u1, b, u2)));
+                    pp = fm_add(pp, fm_scale(-4.0, t));
+                    pm = fm_add(pm, fm_scale(b1 == b2 ? -4.0 : 4.0, t));
+                }
+        }
+        pairPlus[i] += pp.x;
+        pairMinus[i] += pm.x;
+    }
+    // occDiffSq (:744-776)
+    double occ = 0;
+    for (int i = tid; i < N; i += blockDim.x) {
+        // g(b1, s1, b2, s2) at site i; blocks: XU = 0, YD = 1, XD = 2, YU = 3
+        auto g = [&](int bs1, int bs2) { return fm_gl1<MSF>(gs, D, N, i, bs1, i, bs2); };
+        const int XU = 0, YD = 1, XD = 2, YU = 3;
+        cplx t = fm_scale(-2.0, fm_mul(g(XD, XU), g(XU, XD)));
+        t = fm_add(t, g(XU, XU));
+        t = fm_add(t, fm_scale(2.0, fm_mul(g(XD, YD), g(YD, XD))));
+        t = fm_add(t, fm_scale(2.0, fm_mul(g(XU, YD), g(YD, XU))));
+        t = fm_add(t, g(YD, YD));
+        t = fm_add(t, fm_scale(-2.0, fm_mul(g(XU, XU), g(YD, YD))));
+        t = fm_add(t, fm_scale(2.0, fm_mul(g(XD, YU), g(YU, XD))));
+        t = fm_add(t, fm_scale(2.0, fm_mul(g(XU, YU), g(YU, XU))));
+        t = fm_add(t, fm_scale(-2.0, fm_mul(g(YD, YU), g(YU, YD))));
+        cplx br = make_double2(1.0, 0.0);
+        br = fm_add(br, fm_scale(2.0, g(XU, XU)));
+        br = fm_add(br, fm_scale(-2.0, g(YD, YD)));
+        br = fm_add(br, fm_scale(-2.0, g(YU, YU)));
+        t = fm_add(t, fm_mul(g(XD, XD), br));
+        t = fm_add(t, g(YU, YU));
+        t = fm_add(t, fm_scale(-2.0, fm_mul(g(XU, XU), g(YU, YU))));
+        t = fm_add(t, fm_scale(2.0, fm_mul(g(YD, YD), g(YU, YU))));
+        occ += t.x;
+    }
+    const double socc = fm_block_sum(occ, red);
+    if (tid == 0) {
+        acc[0] += f * ssum;
+        acc[1] += f * strace / (4.0 * N);
+        acc[2] += socc / N;
+    }
+}
+
+cudaError_t launch_fermion_measure(const cplx* gs, long long strideG, int N, int L, int msf, double* acc, long long strideAcc,
+                                   int batch, cudaStream_t st) {
+    const size_t smem = size_t(4) * (2 * L - 1) * (2 * L - 1) * sizeof(double);
+    if (msf == 4) fermion_measure_kernel<4><<<batch, 256, smem, st>>>(gs, strideG, N, L, acc, strideAcc);
+    else fermion_measure_kernel<2><<<batch, 256, smem, st>>>(gs, strideG, N, L, acc, strideAcc);
+    return cudaGetLastError();
+}
+
 }  // namespace dqmc

@@ -43,6 +43,7 @@ SYMBOLS = [
     ("dqmc_download_config_stream", c_i32, [c_vp, c_i32, c_vp]),
     ("dqmc_wolff_cluster_move", c_i32, [c_vp, c_i32, c_vp]),
     ("dqmc_sweep_simple", c_i32, [c_vp, c_i32]),
+    ("dqmc_get_fermionic_observables", c_i32, [c_vp, c_i32, c_vp, c_vp]),
     ("dqmc_get_wolff_statistics", c_i32, [c_vp, c_i32, c_vp]),
     ("dqmc_launch_count", c_u64, [c_vp]),
     ("dqmc_rng_seed", c_i32, [c_vp, c_i32, c_u32, c_u32]),

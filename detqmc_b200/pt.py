@@ -150,7 +150,7 @@ class DetQMCPT:
             else:
                 self.swCounter += 1
                 take = self.swCounter % self.measureInterval == 0
-                b.sweep(False)                         # fermionic measurements: SURVEY 8(f) row 1
+                b.sweep(False)                         # bosonic observables only in this loop
                 if take:
                     self._measure()
                     if (self.cfgBinary or self.cfgText) and self.cfgInterval and self.swCounter % self.cfgInterval == 0:

@@ -303,9 +303,19 @@ class DetSDWBatch:
         return out
 
     def sweep(self, takeMeasurements=False):
-        if takeMeasurements:
-            raise DqmcError("fermionic measurements are outside the accelerated path (SURVEY 8f)")
-        self._ck(self.lib.dqmc_sweep(self.h, 0))
+        """sweep(takeMeasurements), detsdwopdim.cpp:4422-4460.  With takeMeasurements the fermionic observables are
+        accumulated on the device after every slice; read them with fermionic_observables()."""
+        self._ck(self.lib.dqmc_sweep(self.h, 2 if takeMeasurements else 0))
+
+    def fermionic_observables(self, rep=0):
+        """finishMeasurements (detsdwopdim.cpp:903-1000) of the last sweep(True): greenK0, greenLocal, occDiffSq,
+        pairPlusMax, pairMinusMax and the vectors kOccX, kOccY, pairPlus, pairMinus."""
+        sc, vec = np.zeros(5), np.zeros(4 * self.N)
+        self._ck(self.lib.dqmc_get_fermionic_observables(self.h, int(rep), _ptr(sc), _ptr(vec)))
+        N = self.N
+        return dict(greenK0=sc[0], greenLocal=sc[1], occDiffSq=sc[2], pairPlusMax=sc[3], pairMinusMax=sc[4],
+                    kOccX=vec[:N].copy(), kOccY=vec[N:2 * N].copy(), pairPlus=vec[2 * N:3 * N].copy(),
+                    pairMinus=vec[3 * N:].copy())
 
     def sweepThermalization(self):
         self._ck(self.lib.dqmc_sweep(self.h, 1))

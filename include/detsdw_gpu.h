@@ -49,13 +49,13 @@ public:
 
     DetSDWGpu(RngWrapper& rng_, const ModelParams& pars_, int device = 0)
         : rng(rng_), pars(pars_), ctx(nullptr), normMeanPhi(0), associatedEnergy(0), phiRhoS_Gs(0), phiRhoS_Gc(0),
+          greenK0(0), greenLocal(0), occDiffSq(0), pairPlusMax(0), pairMinusMax(0),
           performedSweeps(0) {
         if (pars.opdim != (uint32_t)OPDIM) throw_GeneralError("DetSDWGpu: opdim mismatch");
+        kOccX.zeros(pars.L * pars.L); kOccY.zeros(pars.L * pars.L);
+        pairPlus.zeros(pars.L * pars.L); pairMinus.zeros(pars.L * pars.L);
         if (!pars.checkerboard) throw_GeneralError("DetSDWGpu: the GPU path implements the checkerboard break-up only");
         if (pars.turnoffFermions) throw_GeneralError("DetSDWGpu: turnoffFermions is a pure-boson run, use the reference");
-        if (!pars.turnoffFermionMeasurements)
-            throw_GeneralError("DetSDWGpu: fermionic measurements are outside the accelerated path; set "
-                               "turnoffFermionMeasurements");
         if (pars.cdwU != 0.0) throw_GeneralError("DetSDWGpu: cdwU != 0 is outside the accelerated path");
         // iterative (detsdwopdim.cpp:2491-2880) and woodbury (:2883-3019) evaluate the same ratio and apply the same
         // rank-MSF update immediately: both are served as delayed updates with a block of one (identical decisions)
@@ -130,9 +130,11 @@ public:
     }
 
     virtual void sweep(bool takeMeasurements) {
-        check(dqmc_sweep(ctx, 0), "dqmc_sweep");
+        const bool fermionic = takeMeasurements && !pars.turnoffFermionMeasurements;
+        check(dqmc_sweep(ctx, fermionic ? 2 : 0), "dqmc_sweep");
         ++performedSweeps;
         if (takeMeasurements) measureBosonic();
+        if (fermionic) fetchFermionic();
     }
     virtual void sweepThermalization() {
         check(dqmc_sweep(ctx, 1), "dqmc_sweep");
@@ -140,6 +142,8 @@ public:
     }
     // greenUpdate = simple (detsdwopdim.cpp:4366-4420): G from scratch at every slice, then the slice update
     virtual void sweepSimple(bool takeMeasurements) {
+        if (takeMeasurements && !pars.turnoffFermionMeasurements)
+            throw_GeneralError("DetSDWGpu: fermionic measurements are served by the stabilized sweep only");
         check(dqmc_sweep_simple(ctx, 0), "dqmc_sweep_simple");
         ++performedSweeps;
         if (takeMeasurements) measureBosonic();
@@ -158,9 +162,26 @@ public:
             obs.push_back(ScalarObservable(std::cref(phiRhoS_Gs), "phiRhoS_Gs", ""));
             obs.push_back(ScalarObservable(std::cref(phiRhoS_Gc), "phiRhoS_Gc", ""));
         }
+        if (!pars.turnoffFermionMeasurements) {              // detsdwopdim.cpp:278-333
+            obs.push_back(ScalarObservable(std::cref(pairPlusMax), "pairPlusMax", "ppMax"));
+            obs.push_back(ScalarObservable(std::cref(pairMinusMax), "pairMinusMax", "pmMax"));
+            obs.push_back(ScalarObservable(std::cref(greenK0), "greenK0", ""));
+            obs.push_back(ScalarObservable(std::cref(greenLocal), "greenLocal", ""));
+            obs.push_back(ScalarObservable(std::cref(occDiffSq), "occDiffSq", ""));
+        }
         return obs;
     }
-    virtual std::vector<VectorObservable> getVectorObservables() { return std::vector<VectorObservable>(); }
+    virtual std::vector<VectorObservable> getVectorObservables() {
+        std::vector<VectorObservable> obs;
+        if (!pars.turnoffFermionMeasurements) {              // detsdwopdim.cpp:287-315
+            const uint32_t N = pars.L * pars.L;
+            obs.push_back(VectorObservable(std::cref(kOccX), N, "kOccX", "nkx"));
+            obs.push_back(VectorObservable(std::cref(kOccY), N, "kOccY", "nky"));
+            obs.push_back(VectorObservable(std::cref(pairPlus), N, "pairPlus", "pp"));
+            obs.push_back(VectorObservable(std::cref(pairMinus), N, "pairMinus", "pm"));
+        }
+        return obs;
+    }
     virtual std::vector<KeyValueObservable> getKeyValueObservables() { return std::vector<KeyValueObservable>(); }
 
     // configuration streams (detsdwopdim.cpp:4943-5114): the device reorders the fields into the on-disk order
@@ -271,6 +292,18 @@ private:
         return phi;
     }
     // bosonic observables of DetSDW::measure (detsdwopdim.cpp:440-506): |mean phi|, mean phi^2, action
+    // finishMeasurements of the fermionic observables accumulated on the device during dqmc_sweep(ctx, 2)
+    void fetchFermionic() {
+        const uint32_t N = pars.L * pars.L;
+        double sc[5];
+        std::vector<double> vec(size_t(4) * N);
+        check(dqmc_get_fermionic_observables(ctx, 0, sc, vec.data()), "dqmc_get_fermionic_observables");
+        greenK0 = sc[0]; greenLocal = sc[1]; occDiffSq = sc[2]; pairPlusMax = sc[3]; pairMinusMax = sc[4];
+        for (uint32_t i = 0; i < N; ++i) {
+            kOccX[i] = vec[i]; kOccY[i] = vec[N + i]; pairPlus[i] = vec[2 * N + i]; pairMinus[i] = vec[3 * N + i];
+        }
+    }
+
     // The observables the reference measures with turnoffFermionMeasurements (initMeasurements / measure /
     // finishMeasurements, detsdwopdim.cpp:441-560, 903-918), from the fields of all slices k = 1..m.
     void measureBosonic() {
@@ -303,6 +336,8 @@ private:
     ModelParams pars;
     dqmc_ctx* ctx;
     num normMeanPhi, associatedEnergy, phiRhoS_Gs, phiRhoS_Gc;
+    num greenK0, greenLocal, occDiffSq, pairPlusMax, pairMinusMax;
+    VecNum kOccX, kOccY, pairPlus, pairMinus;
     uint32_t performedSweeps;
 };
 

@@ -244,10 +244,18 @@ int dqmc_get_wolff_statistics(dqmc_ctx* ctx, int rep, double* out);
 /* phiAction() (detsdwopdim.cpp:4242-4299) per replica. */
 int dqmc_phi_action(dqmc_ctx* ctx, double* out);
 
-/* sweep(takeMeasurements=false) / sweepThermalization() for every replica of the batch
+/* sweep(takeMeasurements) / sweepThermalization() for every replica of the batch
  * (detsdwopdim.cpp:4422-4502 -> detmodel.h:1401-1478): one direction (down or up) including
- * the global move before a down-sweep. */
+ * the global move before a down-sweep.  thermalization: 0 = sweep(false), 1 = sweepThermalization() (step-size
+ * adaptation), 2 = sweep(true) for DetSDW: measure(k) after the update of every slice (detmodel.h:1277-1283) --
+ * the Green's function is shifted symmetrically by half a hopping step (shiftGreenSymmetric, detsdwopdim.cpp:4505-4612)
+ * and the fermionic observables of DetSDW::measure (:540-900) are accumulated on the device. */
 int dqmc_sweep(dqmc_ctx* ctx, int thermalization);
+/* finishMeasurements (detsdwopdim.cpp:903-1000) for replica `rep` after dqmc_sweep(ctx, 2):
+ * scalars[5] = greenK0, greenLocal, occDiffSq, pairPlusMax, pairMinusMax;
+ * vectors[4 N] = kOccX | kOccY | pairPlus | pairMinus (momentum-space occupation per band, equal-time pairing
+ * correlations between site 0 and site i). */
+int dqmc_get_fermionic_observables(dqmc_ctx* ctx, int rep, double* scalars, double* vectors);
 
 /* Resident random numbers: upload the next n_sweeps sweeps' worth of every replica's stream once;
  * dqmc_sweep then runs without per-sweep host<->device copies or synchronisation (the consumption

@@ -357,6 +357,7 @@ class SdwParams:
         self.wolffClusterUpdate = False
         self.wolffClusterShiftUpdate = False
         self.repeatWolffPerSweep = 1
+        self.fermionMeasurements = False    # not turnoffFermionMeasurements
         self.repeatUpdateInSlice = 1
         self.seed = 1020304050
         self.rngIndex = 1
@@ -875,6 +876,126 @@ class SdwOracle(SweepSkeleton):
     def sweep_thermalization(self):
         self.sweep_skeleton(self.update_in_slice_thermalization)
         self.performed_sweeps += 1
+
+    # ------------------------------------------------------------------ fermionic measurements, cpp:508-900, 903-1000
+    def shift_green_symmetric(self):
+        """shiftGreenSymmetric, cpp:4505-4612 (CB_ASSAAD_BERG): every N x N block (row, col) of g becomes
+        E0(-dtau/2) E1(-dtau/2) [band of the row block] . block . E1(+dtau/2) E0(+dtau/2) [band of the column block]
+        (two plaquette subgroups, half steps, no chemical potential); blocks 0..3 = XUP, YDOWN, XDOWN, YUP."""
+        N, h = self.N, 0.5 * self.p.dtau
+        if not hasattr(self, "_shift_mats"):
+            self._shift_mats = {b: (self._subgroup_matrix(b, 0, -h) @ self._subgroup_matrix(b, 1, -h),
+                                    self._subgroup_matrix(b, 1, +h) @ self._subgroup_matrix(b, 0, +h)) for b in (0, 1)}
+        g = self.green[0]
+        out = np.zeros_like(g)
+        for row in range(self.msf):
+            for col in range(self.msf):
+                blk = g[row * N:(row + 1) * N, col * N:(col + 1) * N]
+                out[row * N:(row + 1) * N, col * N:(col + 1) * N] = \
+                    self._shift_mats[row % 2][0] @ blk @ self._shift_mats[col % 2][1]
+        return out
+
+    def init_measurements(self):
+        N = self.N
+        self.fm = dict(greenK0=0.0, greenLocal=0.0, occDiffSq=0.0, kOccX=np.zeros(N), kOccY=np.zeros(N),
+                       pairPlus=np.zeros(N), pairMinus=np.zeros(N), slices=0)
+
+    def measure_fermionic(self, k):
+        """The fermionic part of measure(timeslice), cpp:540-900, from the symmetrically shifted Green's function of the
+        current slice.  Band-spin blocks: XUP = 0, YDOWN = 1, XDOWN = 2, YUP = 3; for opdim < 3 only the XUP / YDOWN
+        blocks are stored and the XDOWN / YUP sector is their complex conjugate (gl1, cpp:598-615)."""
+        p, N, L = self.p, self.N, self.L
+        gs = self.shift_green_symmetric()
+        fm = self.fm
+        fm["slices"] += 1
+        XUP, YDOWN, XDOWN, YUP = 0, 1, 2, 3
+        XB, YB, UP, DOWN = 0, 1, 0, 1
+        bandspin = {(XB, UP): XUP, (YB, DOWN): YDOWN, (XB, DOWN): XDOWN, (YB, UP): YUP}
+
+        def gl1(s1, bs1, s2, bs2):
+            if p.opdim == 3:
+                return gs[s1 + N * bs1, s2 + N * bs2]
+            if bs1 in (XUP, YDOWN) and bs2 in (XUP, YDOWN):
+                return gs[s1 + N * bs1, s2 + N * bs2]
+            if bs1 in (XDOWN, YUP) and bs2 in (XDOWN, YUP):
+                return np.conj(gs[s1 + N * (bs1 - 2), s2 + N * (bs2 - 2)])
+            return 0.0
+
+        def gl(s1, b1, sp1, s2, b2, sp2):
+            return gl1(s1, bandspin[(b1, sp1)], s2, bandspin[(b2, sp2)])
+
+        if p.opdim == 3:
+            fm["greenK0"] += float(np.real(np.sum(gs)))
+            fm["greenLocal"] += float(np.real(np.trace(gs))) / (4.0 * N)
+        else:
+            fm["greenK0"] += 2.0 * float(np.real(np.sum(gs)))
+            fm["greenLocal"] += 2.0 * float(np.real(np.trace(gs))) / (4.0 * N)
+        # momentum-space occupation, cpp:623-671
+        off_x = 0.5 if p.bc in (1, 3) else 0.0
+        off_y = 0.5 if p.bc in (2, 3) else 0.0
+        sites = np.arange(N)
+        ix, iy = (sites % L).astype(float), (sites // L).astype(float)
+        gx = np.array([[gl1(i, XUP, j, XUP) + gl1(i, XDOWN, j, XDOWN) for j in range(N)] for i in range(N)])
+        gy = np.array([[gl1(i, YUP, j, YUP) + gl1(i, YDOWN, j, YDOWN) for j in range(N)] for i in range(N)])
+        for ks in range(N):
+            ky = -np.pi + (float(ks // L) + off_y) * 2 * np.pi / L
+            kx = -np.pi + (float(ks % L) + off_x) * 2 * np.pi / L
+            phase = np.exp(1j * (kx * (ix[:, None] - ix[None, :]) + ky * (iy[:, None] - iy[None, :])))
+            fm["kOccX"][ks] += float(np.real(np.sum(phase * gx)))
+            fm["kOccY"][ks] += float(np.real(np.sum(phase * gy)))
+        # equal-time pairing correlations, cpp:673-718
+        for i in range(N):
+            pp = pm = 0.0
+            for a, b in ((i, 0), (0, i)):
+                for b1 in (XB, YB):
+                    for b2 in (XB, YB):
+                        t = gl(a, b1, DOWN, b, b2, UP) * gl(a, b1, UP, b, b2, DOWN) - \
+                            gl(a, b1, DOWN, b, b2, DOWN) * gl(a, b1, UP, b, b2, UP)
+                        pp += -4.0 * t
+                        pm += -4.0 * t * (1.0 if b1 == b2 else -1.0)
+            fm["pairPlus"][i] += float(np.real(pp))
+            fm["pairMinus"][i] += float(np.real(pm))
+        # occDiffSq, cpp:744-776
+        tot = 0.0
+        for i in range(N):
+            g = lambda b1, s1, b2, s2: gl(i, b1, s1, i, b2, s2)      # noqa: E731
+            tot += (-2.0 * g(XB, DOWN, XB, UP) * g(XB, UP, XB, DOWN) + g(XB, UP, XB, UP)
+                    + 2.0 * g(XB, DOWN, YB, DOWN) * g(YB, DOWN, XB, DOWN)
+                    + 2.0 * g(XB, UP, YB, DOWN) * g(YB, DOWN, XB, UP) + g(YB, DOWN, YB, DOWN)
+                    - 2.0 * g(XB, UP, XB, UP) * g(YB, DOWN, YB, DOWN)
+                    + 2.0 * g(XB, DOWN, YB, UP) * g(YB, UP, XB, DOWN)
+                    + 2.0 * g(XB, UP, YB, UP) * g(YB, UP, XB, UP)
+                    - 2.0 * g(YB, DOWN, YB, UP) * g(YB, UP, YB, DOWN)
+                    + g(XB, DOWN, XB, DOWN) * (1.0 + 2.0 * g(XB, UP, XB, UP) - 2.0 * g(YB, DOWN, YB, DOWN)
+                                               - 2.0 * g(YB, UP, YB, UP))
+                    + g(YB, UP, YB, UP) - 2.0 * g(XB, UP, XB, UP) * g(YB, UP, YB, UP)
+                    + 2.0 * g(YB, DOWN, YB, DOWN) * g(YB, UP, YB, UP))
+        fm["occDiffSq"] += float(np.real(tot)) / N
+
+    def finish_measurements(self):
+        """finishMeasurements, cpp:903-1000 (fermionic part)."""
+        p, N, L, m = self.p, self.N, self.L, self.p.m
+        fm = self.fm
+        assert fm["slices"] == m
+        out = dict(greenK0=fm["greenK0"] / m, greenLocal=fm["greenLocal"] / m,
+                   kOccX=2.0 - fm["kOccX"] / (m * N), kOccY=2.0 - fm["kOccY"] / (m * N),
+                   pairPlus=fm["pairPlus"] / m, pairMinus=fm["pairMinus"] / m)
+        far = [yy * L + xx for yy in (L // 2 - 1, L // 2, L // 2 + 1) for xx in (L // 2 - 1, L // 2, L // 2 + 1)]
+        out["pairPlusMax"] = float(np.mean(out["pairPlus"][far]))
+        out["pairMinusMax"] = float(np.mean(out["pairMinus"][far]))
+        out["occDiffSq"] = fm["occDiffSq"] / m
+        return out
+
+    def measured_sweep_fermionic(self):
+        """sweep(true) with fermionic measurements: measure(k) right after updateInSlice(k) (detmodel.h:1277-1283)."""
+        self.init_measurements()
+
+        def update_and_measure(k):
+            self.update_in_slice(k)
+            self.measure_fermionic(k)
+        self.sweep_skeleton(update_and_measure)
+        self.performed_sweeps += 1
+        return self.finish_measurements()
 
     # greenUpdate = simple, cpp:4366-4420
     def sweep_simple(self):

@@ -20,7 +20,8 @@ class RefSdwParams(ctypes.Structure):
                 ("weakZflux", c_i32), ("bc", c_i32), ("updateMethod", c_i32), ("delaySteps", c_i32),
                 ("globalShift", c_i32), ("globalUpdateInterval", c_i32), ("repeatUpdateInSlice", c_i32),
                 ("seed", c_u32), ("rngIndex", c_u32),
-                ("wolffClusterUpdate", c_i32), ("wolffClusterShiftUpdate", c_i32), ("repeatWolffPerSweep", c_i32)]
+                ("wolffClusterUpdate", c_i32), ("wolffClusterShiftUpdate", c_i32), ("repeatWolffPerSweep", c_i32),
+                ("fermionMeasurements", c_i32)]
 
 
 class RefHubParams(ctypes.Structure):
@@ -80,7 +81,7 @@ def sdw_params_from(p):
                         p.updateMethod, p.delaySteps, int(p.globalShift), p.globalUpdateInterval,
                         p.repeatUpdateInSlice, p.seed, p.rngIndex,
                         int(getattr(p, "wolffClusterUpdate", False)), int(getattr(p, "wolffClusterShiftUpdate", False)),
-                        int(getattr(p, "repeatWolffPerSweep", 1)))
+                        int(getattr(p, "repeatWolffPerSweep", 1)), int(getattr(p, "fermionMeasurements", False)))
 
 
 class RefSdw:
@@ -178,6 +179,23 @@ class RefSdw:
         lib().ref_sdw_green_from_storage(self.h, c_u32(l_left), c_u32(l_right), _p(out), _p(sv))
         return out, sv
 
+
+    def measured_sweep_fermionic(self):
+        """sweep(true) with fermionic measurements on (construct with fermionMeasurements=True): dict of the scalars
+        greenK0, greenLocal, occDiffSq, pairPlusMax, pairMinusMax and the vectors kOccX, kOccY, pairPlus, pairMinus."""
+        sc, vec = np.zeros(5), np.zeros(4 * self.N)
+        if lib().ref_sdw_measured_sweep_fermionic(self.h, _p(sc), _p(vec)):
+            raise RuntimeError("reference sweep failed")
+        N = self.N
+        return dict(greenK0=sc[0], greenLocal=sc[1], occDiffSq=sc[2], pairPlusMax=sc[3], pairMinusMax=sc[4],
+                    kOccX=vec[:N].copy(), kOccY=vec[N:2 * N].copy(), pairPlus=vec[2 * N:3 * N].copy(),
+                    pairMinus=vec[3 * N:].copy())
+
+    def shift_green_symmetric(self):
+        """shiftGreenSymmetric() of the current g (detsdwopdim.cpp:4505-4612)."""
+        out = np.zeros((self.D, self.D), dtype=np.complex128, order="F")
+        lib().ref_sdw_shift_green_symmetric(self.h, _p(out))
+        return out
 
     def sweep_simple(self, therm=False):
         """sweepSimple(false) / sweepSimpleThermalization() (greenUpdate = simple, detsdwopdim.cpp:4366-4420)."""

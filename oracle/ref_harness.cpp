@@ -64,6 +64,7 @@ struct ref_sdw_params {
     int32_t wolffClusterUpdate;
     int32_t wolffClusterShiftUpdate;
     int32_t repeatWolffPerSweep;
+    int32_t fermionMeasurements;   // 0: turnoffFermionMeasurements (default), 1: measure
 };
 
 struct ref_hub_params {
@@ -111,6 +112,8 @@ struct SdwBase {
     virtual void attempt_wolff(int shift, double* stats) = 0;
     virtual void measured_sweep(double* obs) = 0;
     virtual void sweep_simple(int therm) = 0;
+    virtual void measured_sweep_fermionic(double* scalars, double* vectors) = 0;
+    virtual void shift_green_symmetric(double* out) = 0;
 };
 
 template <int OPDIM>
@@ -150,7 +153,7 @@ struct SdwImpl : public SdwBase {
         }
         SETP(globalUpdateInterval, (uint32_t)p.globalUpdateInterval);
         SETP(repeatUpdateInSlice, (uint32_t)p.repeatUpdateInSlice);
-        SETP(turnoffFermionMeasurements, true);
+        SETP(turnoffFermionMeasurements, p.fermionMeasurements == 0);
 #undef SETP
         static const char* bcs[] = {"pbc", "apbc-x", "apbc-y", "apbc-xy"};
         pars.bc_string = bcs[p.bc];
@@ -240,6 +243,22 @@ struct SdwImpl : public SdwBase {
         std::memcpy(U, st.U.memptr(), sizeof(cpx_t) * st.U.n_elem);
         std::memcpy(d, st.d.memptr(), sizeof(double) * st.d.n_elem);
         std::memcpy(Vt, st.V_t.memptr(), sizeof(cpx_t) * st.V_t.n_elem);
+    }
+    void measured_sweep_fermionic(double* scalars, double* vectors) {
+        // sweep(true) with fermionic measurements (detsdwopdim.cpp:508-900, 903-1000): scalars = greenK0, greenLocal,
+        // occDiffSq, pairPlusMax, pairMinusMax; vectors = kOccX | kOccY | pairPlus | pairMinus (N each)
+        rep->sweep(true);
+        const uint32_t N = rep->pars.N;
+        scalars[0] = rep->greenK0; scalars[1] = rep->greenLocal; scalars[2] = rep->occDiffSq;
+        scalars[3] = rep->pairPlusMax; scalars[4] = rep->pairMinusMax;
+        for (uint32_t i = 0; i < N; ++i) {
+            vectors[i] = rep->kOccX[i]; vectors[N + i] = rep->kOccY[i];
+            vectors[2 * N + i] = rep->pairPlus[i]; vectors[3 * N + i] = rep->pairMinus[i];
+        }
+    }
+    void shift_green_symmetric(double* out) {
+        typename Model::MatData gs = rep->shiftGreenSymmetric();
+        std::memcpy(out, gs.memptr(), sizeof(cpx_t) * gs.n_elem);
     }
     void sweep_simple(int therm) {
         // greenUpdate = simple (detsdwopdim.cpp:4366-4420)
@@ -370,6 +389,17 @@ void ref_sdw_green_from_storage(void* h, uint32_t ll, uint32_t lr, double* out, 
 }
 
 // exchange probability, detsdwopdim.cpp:5251-5264
+int ref_sdw_measured_sweep_fermionic(void* h, double* scalars, double* vectors) {
+    CoutSilencer q;
+    try {
+        static_cast<SdwBase*>(h)->measured_sweep_fermionic(scalars, vectors);
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "ref_sdw_measured_sweep_fermionic: %s\n", e.what());
+        return 1;
+    }
+    return 0;
+}
+void ref_sdw_shift_green_symmetric(void* h, double* out) { static_cast<SdwBase*>(h)->shift_green_symmetric(out); }
 int ref_sdw_sweep_simple(void* h, int therm) {
     CoutSilencer q;
     try {

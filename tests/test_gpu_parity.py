@@ -367,6 +367,33 @@ def test_sweep_simple_vs_oracle():
     assert maxabs(b.rng_draw(4), [o.rng.rand01() for _ in range(4)]) == 0.0
 
 
+@pytest.mark.parametrize("tag", ["o2", "o2_apbc", "o3", "o2_L6"])
+def test_fermionic_observables_vs_golden(tag):
+    """dqmc_sweep(ctx, 2) + dqmc_get_fermionic_observables against the observables the reference
+    measured in its own sweep(true) for the same seed: greenK0, greenLocal, occDiffSq, pairPlusMax, pairMinusMax and the
+    vectors kOccX, kOccY, pairPlus, pairMinus after each of three measured sweeps."""
+    import json
+    import os
+    from dqmc_oracle import SdwParams
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fermion_observables.npz"))
+    d = json.loads(str(g[tag + "_pars"]))
+    for key in ("N", "beta", "fermionMeasurements"):
+        d.pop(key, None)
+    p = SdwParams(**d)
+    b = make_batch(p, n_replicas=2, rng_indices=[p.rngIndex, p.rngIndex + 20])
+    for it in range(3):
+        b.sweep(True)
+        ob = b.fermionic_observables(0)
+        sc = [ob["greenK0"], ob["greenLocal"], ob["occDiffSq"], ob["pairPlusMax"], ob["pairMinusMax"]]
+        vec = np.concatenate([ob["kOccX"], ob["kOccY"], ob["pairPlus"], ob["pairMinus"]])
+        assert np.allclose(sc, g[tag + "_scalars"][it], rtol=1e-8, atol=1e-10)
+        assert np.allclose(vec, g[tag + "_vectors"][it], rtol=1e-8, atol=1e-10)
+    assert maxabs(b.phi(0)[1:], g[tag + "_phi"][1:]) < 1e-12
+    assert relerr(b.green(0), g[tag + "_green"]) < TOL_G
+    other = b.fermionic_observables(1)                  # the second replica measured its own trajectory
+    assert abs(other["greenLocal"] - ob["greenLocal"]) > 0
+
+
 def test_bosonic_observables_vs_golden():
     """The observables of a measured sweep (normMeanPhi, associatedEnergy, phiRhoS_Gs, phiRhoS_Gc) from the fields
     on the device against the values the reference measured for the same fields (tests/golden/bosonic_observables.npz)."""
@@ -614,6 +641,35 @@ def test_reference_driver_with_gpu_shim(tmp_path):
     assert "binary phi configuration stream" in open(os.path.join(str(tmp_path), "configs-phi.infoheader")).read()
     info = open(os.path.join(str(tmp_path), "info.dat")).read()
     assert "libdqmc_b200" in info
+
+
+def test_reference_driver_with_gpu_shim_fermionic_measurements(tmp_path):
+    """The reference's DetQMC driver on the GPU shim with turnoffFermionMeasurements = false: its time series of the
+    fermionic observables (greenLocal, occDiffSq, pairPlusMax) must equal the oracle's measured sweeps for the same seed."""
+    import os
+    import subprocess
+    from dqmc_oracle import SdwOracle, SdwParams
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "host", "_build", "detqmcsdw_gpu")
+    if not os.path.exists(exe):
+        pytest.skip("host/_build/detqmcsdw_gpu not built (needs the reference tree: make -C host)")
+    therm, sweeps = 4, 4
+    out = subprocess.run([exe, "L=4", "beta=2", "dtau=0.1", "s=10", "r=-1", "thermalization=%d" % therm,
+                          "sweeps=%d" % sweeps, "rngSeed=1020304050", "simindex=0", "turnoffFermionMeasurements=0"],
+                         cwd=str(tmp_path), capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    o = SdwOracle(SdwParams(L=4, m=20, s=10, r=-1.0))
+    for _ in range(therm):
+        o.sweep_thermalization()
+    ref = {"greenLocal": [], "occDiffSq": [], "pairPlusMax": [], "greenK0": []}
+    for _ in range(sweeps):
+        ob = o.measured_sweep_fermionic()
+        for name in ref:
+            ref[name].append(ob[name])
+    for name in ref:
+        got = [float(x) for x in open(os.path.join(str(tmp_path), name + ".series")) if x.strip() and x[0] != "#"]
+        assert len(got) == sweeps and np.allclose(got, ref[name], rtol=2e-5, atol=2e-6), name
+    # the vector observables go through the reference's VectorObservableHandler (results-<name>.values)
+    assert any("kOccX" in f for f in os.listdir(str(tmp_path))), sorted(os.listdir(str(tmp_path)))
 
 
 # ---------------------------------------------------------------- DetHubbard (BASELINE configs C1, C5)

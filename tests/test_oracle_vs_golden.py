@@ -196,3 +196,26 @@ def test_bosonic_observables_vs_reference_values():
             ob = bosonic_observables(g[tag + "_phi"][it], 0.1)
             got = [ob["normMeanPhi"], ob["associatedEnergy"], ob.get("phiRhoS_Gs", 0.0), ob.get("phiRhoS_Gc", 0.0)]
             assert np.allclose(got, g[tag + "_obs"][it], rtol=1e-12, atol=1e-13)
+
+
+@pytest.mark.parametrize("tag", ["o2", "o2_apbc", "o3", "o2_L6"])
+def test_fermionic_observables_vs_reference_values(tag):
+    """measure / finishMeasurements restated (shiftGreenSymmetric, greenK0, greenLocal, occDiffSq, k-space occupation,
+    equal-time pairing correlations) against the values of the reference's own measured sweeps."""
+    import json
+    import os
+    from dqmc_oracle import SdwParams
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fermion_observables.npz"))
+    d = json.loads(str(g[tag + "_pars"]))
+    for key in ("N", "beta"):
+        d.pop(key, None)
+    o = SdwOracle(SdwParams(**d))
+    n = 3 if tag != "o2_L6" else 1                   # L = 6 costs a few seconds per sweep in pure Python
+    for it in range(n):
+        ob = o.measured_sweep_fermionic()
+        sc = [ob["greenK0"], ob["greenLocal"], ob["occDiffSq"], ob["pairPlusMax"], ob["pairMinusMax"]]
+        vec = np.concatenate([ob["kOccX"], ob["kOccY"], ob["pairPlus"], ob["pairMinus"]])
+        assert np.allclose(sc, g[tag + "_scalars"][it], rtol=1e-9, atol=1e-11)
+        assert np.allclose(vec, g[tag + "_vectors"][it], rtol=1e-9, atol=1e-11)
+    if n == 3:
+        assert maxabs(o.shift_green_symmetric(), g[tag + "_green_shifted"]) < 1e-10

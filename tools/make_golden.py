@@ -164,6 +164,30 @@ def observables_fixture():
     print("bosonic_observables done")
 
 
+def fermion_fixture():
+    """Fermionic observables of measured sweeps (sweep(true) with turnoffFermionMeasurements = false,
+    detsdwopdim.cpp:508-1000): greenK0, greenLocal, occDiffSq, pairPlusMax, pairMinusMax, kOccX, kOccY, pairPlus,
+    pairMinus after each of three sweeps, plus shiftGreenSymmetric of the final G."""
+    d = {}
+    for tag, kw in (("o2", dict(rngIndex=16)), ("o2_apbc", dict(weakZflux=False, bc=3, rngIndex=17)),
+                    ("o3", dict(opdim=3, weakZflux=False, rngIndex=18)), ("o2_L6", dict(L=6, m=10, s=5, rngIndex=19))):
+        p = SdwParams(fermionMeasurements=True, **kw)
+        rep = rb.RefSdw(p)
+        sc, vec = [], []
+        for _ in range(3):
+            o = rep.measured_sweep_fermionic()
+            sc.append([o["greenK0"], o["greenLocal"], o["occDiffSq"], o["pairPlusMax"], o["pairMinusMax"]])
+            vec.append(np.concatenate([o["kOccX"], o["kOccY"], o["pairPlus"], o["pairMinus"]]))
+        d[tag + "_pars"] = pars_json(p)
+        d[tag + "_scalars"] = np.array(sc)
+        d[tag + "_vectors"] = np.array(vec)
+        d[tag + "_phi"] = rep.phi()
+        d[tag + "_green"] = rep.green()
+        d[tag + "_green_shifted"] = rep.shift_green_symmetric()
+    np.savez_compressed(os.path.join(OUT, "fermion_observables.npz"), **d)
+    print("fermion_observables done")
+
+
 def config_stream_fixture():
     """Configuration streams: fields after two thermalisation sweeps and the bytes / lines the
     reference's own writers append for them (DetSDW::saveConfigurationStreamBinary / Text,
@@ -200,6 +224,7 @@ if __name__ == "__main__":
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "observables":
         observables_fixture()
+        fermion_fixture()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "woodbury":
         # (no fixture for updateMethod=iterative: the reference's updateInSlice_iterative corrupts the heap in this
@@ -223,6 +248,7 @@ if __name__ == "__main__":
     hubbard_fixture("hubbard_L4_cb", 4, dict(checkerboard=True, U=6.0, mu=0.3, m=24, s=5))
     config_stream_fixture()
     observables_fixture()
+    fermion_fixture()
     wolff_all()
     sdw_fixture("sdw_o2_repeat2_L4", 4, dict(repeatUpdateInSlice=2, rngIndex=10))
     sdw_fixture("sdw_o3_woodbury_L4", 4, dict(updateMethod=1, opdim=3, weakZflux=False, rngIndex=9))

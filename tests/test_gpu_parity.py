@@ -591,6 +591,17 @@ def test_full_size_properties(kw):
     assert relerr(b.green(0), o.green[0]) < TOL_G
     assert np.all(b.green_consistency() < 1e-8)                     # wrapped vs advanced G at the last advance
     assert relerr(b.green(1), b.green_for_timeslice(0, rep=1)) < 1e-9
+    # a measured sweep at full size through properties that need no oracle: the k grid is complete, so the
+    # momentum-space occupations sum to the real-space ones, sum_k (kOccX + kOccY) = 4 N (1 - greenLocal); 0 <= n_k <= 2
+    b.sweep(True)
+    for rep in range(b.R):
+        ob = b.fermionic_observables(rep)
+        N = p.N
+        assert abs((ob["kOccX"].sum() + ob["kOccY"].sum()) - 4.0 * N * (1.0 - ob["greenLocal"])) < 1e-8 * N
+        assert ob["kOccX"].min() > -1e-6 and ob["kOccX"].max() < 2.0 + 1e-6
+        assert ob["kOccY"].min() > -1e-6 and ob["kOccY"].max() < 2.0 + 1e-6
+        assert np.isfinite(ob["pairPlus"]).all() and np.isfinite(ob["occDiffSq"])
+    assert np.all(b.green_consistency() < 1e-8)
 
 
 # ---------------------------------------------------------------- the reference's own driver on top of the C ABI

@@ -123,6 +123,9 @@ class DetHubbardBatch:
 
     sweepThermalization = sweep
 
+    def synchronize(self):
+        self._ck(self.lib.dqmc_synchronize(self.h))
+
     def rng_draw(self, n, rep=0):
         out = np.zeros(n)
         self._ck(self.lib.dqmc_rng_draw(self.h, rep, n, _ptr(out)))

@@ -11,9 +11,9 @@ p<index>_<name><value> per control parameter (detqmcpt.h:655-660) with <observab
 configuration streams, plus exchange-parameters.values / exchange-acceptance.values / exchange-diffusion.values
 (detqmcpt.h:596-651) in the working directory.
 
-Only the bosonic observables are measured (normMeanPhi, associatedEnergy, phiRhoS_Gs, phiRhoS_Gc: the reference's list
-with turnoffFermionMeasurements, also what include/detsdw_gpu.h measures);
-fermionic measurements are row 1 of section 8(f).
+The bosonic observables (normMeanPhi, associatedEnergy, phiRhoS_Gs, phiRhoS_Gc: the reference's list with
+turnoffFermionMeasurements) are always measured; with turnoffFermionMeasurements=False the measurement sweeps are
+sweep(true) and the fermionic scalars / vectors of DetSDW::measure are recorded as well.
 """
 import os
 
@@ -22,6 +22,8 @@ import numpy as np
 from .sdw import DetSDWBatch, ReplicaExchangeLadder
 
 OBSERVABLES = ("normMeanPhi", "associatedEnergy", "phiRhoS_Gs", "phiRhoS_Gc")
+FERMIONIC_SCALARS = ("pairPlusMax", "pairMinusMax", "greenK0", "greenLocal", "occDiffSq")      # detsdwopdim.cpp:278-333
+FERMIONIC_VECTORS = ("kOccX", "kOccY", "pairPlus", "pairMinus")
 
 
 def num_to_string(v):
@@ -53,7 +55,7 @@ class DetQMCPT:
     def __init__(self, model_pars, control_values, thermalization, sweeps, measureInterval=1, exchangeInterval=1,
                  saveConfigurationStreamInterval=0, saveConfigurationStreamBinary=False,
                  saveConfigurationStreamText=False, rngSeed=1020304050, simindex=0, outdir=".",
-                 controlParameterName="r", device=None, make_batch=None):
+                 controlParameterName="r", device=None, make_batch=None, turnoffFermionMeasurements=True):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
@@ -72,6 +74,7 @@ class DetQMCPT:
         self.cfgInterval = int(saveConfigurationStreamInterval)
         self.cfgBinary, self.cfgText = bool(saveConfigurationStreamBinary), bool(saveConfigurationStreamText)
         self.outdir = outdir
+        self.fermionic = not turnoffFermionMeasurements
         self.name = controlParameterName
         pars = dict(model_pars if isinstance(model_pars, dict) else vars(model_pars))
         pars["seed"] = rngSeed
@@ -127,7 +130,10 @@ class DetQMCPT:
         b = self.batch
         cpis = self.local_parameter_indices()
         for i in range(self.n_local):
-            self.records.append((self.sweepsDone, int(cpis[i]), bosonic_observables(b.phi(i), b.pars["dtau"])))
+            obs = bosonic_observables(b.phi(i), b.pars["dtau"])
+            if self.fermionic:                         # finishMeasurements of the sweep(True) that just ran
+                obs.update(b.fermionic_observables(i))
+            self.records.append((self.sweepsDone, int(cpis[i]), obs))
 
     def _buffer_configurations(self):
         # buffer_local_system_configuration, detqmcpt.h:690-700: the configuration goes to the stream of the control
@@ -150,7 +156,7 @@ class DetQMCPT:
             else:
                 self.swCounter += 1
                 take = self.swCounter % self.measureInterval == 0
-                b.sweep(False)                         # bosonic observables only in this loop
+                b.sweep(take and self.fermionic)       # sweep(true) accumulates the fermionic observables on the device
                 if take:
                     self._measure()
                     if (self.cfgBinary or self.cfgText) and self.cfgInterval and self.swCounter % self.cfgInterval == 0:
@@ -181,10 +187,12 @@ class DetQMCPT:
         cfgs = self._gather(self.configs)
         if self.rank != 0:
             return
-        series = {cpi: {o: [] for o in OBSERVABLES} for cpi in range(self.P)}
+        scalars = OBSERVABLES + (FERMIONIC_SCALARS if self.fermionic else ())
+        vectors = FERMIONIC_VECTORS if self.fermionic else ()
+        series = {cpi: {o: [] for o in scalars + vectors} for cpi in range(self.P)}
         flat = sorted((r for part in recs for r in part), key=lambda r: (r[0], r[1]))
         for _, cpi, obs in flat:
-            for o in OBSERVABLES:
+            for o in scalars + vectors:
                 series[cpi][o].append(obs[o])
         header = "## %s = %s\n## thermalization = %d\n## sweeps = %d\n## exchangeInterval = %d\n"
         for cpi in range(self.P):
@@ -194,7 +202,15 @@ class DetQMCPT:
                              self.exchangeInterval)
             with open(os.path.join(d, "results.values"), "w") as res:
                 res.write(meta + "## observable \t value \t error\n")
-                for o in OBSERVABLES:
+                for o in vectors:                      # vector observables: mean and error per component
+                    v = np.asarray(series[cpi][o])
+                    with open(os.path.join(d, "results-%s.values" % o), "w") as f:
+                        f.write(meta + "## %s: index \t value \t error\n" % o)
+                        for idx in range(v.shape[1] if v.ndim == 2 else 0):
+                            col = v[:, idx]
+                            err = float(col.std(ddof=1) / np.sqrt(len(col))) if len(col) > 1 else 0.0
+                            f.write("%d\t%.15g\t%.15g\n" % (idx, float(col.mean()), err))
+                for o in scalars:
                     v = np.asarray(series[cpi][o])
                     with open(os.path.join(d, o + ".series"), "w") as f:
                         f.write(meta + "## time series of %s\n" % o)
@@ -249,7 +265,7 @@ def main(argv=None):
                       ("saveConfigurationStreamInterval", int), ("rngSeed", int), ("simindex", int)):
         if key in args:
             mc[key] = conv(args.pop(key))
-    for key in ("saveConfigurationStreamBinary", "saveConfigurationStreamText"):
+    for key in ("saveConfigurationStreamBinary", "saveConfigurationStreamText", "turnoffFermionMeasurements"):
         if key in args:
             mc[key] = args.pop(key).lower() in ("1", "true", "yes")
     outdir = args.pop("outdir", ".")

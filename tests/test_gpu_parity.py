@@ -512,6 +512,33 @@ def test_parallel_tempering_driver_vs_oracle_loop(tmp_path):
                        rtol=1e-12, atol=0)
 
 
+def test_parallel_tempering_driver_fermionic_series(tmp_path):
+    """DetQMCPT with turnoffFermionMeasurements = False: the measurement sweeps are sweep(true); without exchanges
+    (exchangeInterval = 0) every control parameter's greenLocal / occDiffSq series is the oracle's for that replica."""
+    import os
+    from detqmc_b200 import DetQMCPT
+    from dqmc_oracle import SdwOracle, SdwParams
+    values = np.array([-1.4, -0.6])
+    kw = dict(L=4, m=20, s=10)
+    pt = DetQMCPT(SdwParams(**kw), values, thermalization=2, sweeps=2, exchangeInterval=0, outdir=str(tmp_path),
+                  turnoffFermionMeasurements=False)
+    pt.run()
+    for c in range(2):
+        o = SdwOracle(SdwParams(r=float(values[c]), rngIndex=c + 1, **kw))
+        for _ in range(2):
+            o.sweep_thermalization()
+        want = {"greenLocal": [], "occDiffSq": []}
+        for _ in range(2):
+            ob = o.measured_sweep_fermionic()
+            for name in want:
+                want[name].append(ob[name])
+        for name in want:
+            got = [float(x) for x in open(os.path.join(pt.subdir(c), name + ".series")) if x[0] != "#"]
+            assert np.allclose(got, want[name], rtol=1e-9, atol=1e-11)
+        rows = [x.split() for x in open(os.path.join(pt.subdir(c), "results-kOccX.values")) if x[0] != "#"]
+        assert len(rows) == 16
+
+
 def _pt_rank(rank, world, port, outdir):
     import os
     import torch.distributed as dist

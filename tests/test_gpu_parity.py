@@ -52,6 +52,32 @@ def test_library_refuses_without_fallback():
         DetSDWBatch(SdwParams(), n_replicas=1, device=4096)
 
 
+def test_error_behaviour():
+    """Parameter combinations the reference's check() rejects (detsdwparams.cpp:38-200) and calls in the wrong state
+    come back as errors with a message, never as a silent fallback."""
+    from detqmc_b200 import DetSDWBatch, DqmcError
+    from dqmc_oracle import SdwParams
+    bad = [dict(L=5),                                                  # checkerboard break-up needs an even L
+           dict(opdim=3, weakZflux=True),                              # flux only for O(1), O(2) (detsdwparams.cpp:57-60)
+           dict(wolffClusterShiftUpdate=True, globalShift=True),       # combined move excludes the others (:94-96)
+           dict(delaySteps=0), dict(m=1), dict(globalUpdateInterval=0)]
+    for kw in bad:
+        with pytest.raises(DqmcError):
+            DetSDWBatch(SdwParams(**kw), n_replicas=1)
+    with pytest.raises(DqmcError):
+        DetSDWBatch(SdwParams(cdwU=1.0), n_replicas=1)
+    b = make_batch(SdwParams())
+    with pytest.raises(DqmcError):
+        b.wrap_down(3)                                                 # currentTimeslice is m after the set-up
+    with pytest.raises(DqmcError):
+        b.fermionic_observables()                                      # no measured sweep yet
+    with pytest.raises(DqmcError):
+        b.global_shift_move() if b.wrap_down(b.m) else b.global_shift_move()   # needs currentTimeslice == m
+    with pytest.raises(DqmcError):
+        b.set_lanes(2)                                                 # more lanes than replicas
+    assert b.lib.dqmc_last_error(b.h)                                  # a message is kept for the caller
+
+
 @pytest.mark.parametrize("shape", [(288, 288, 288), (128, 128, 128), (100, 37, 53), (32, 32, 32), (196, 784, 64)])
 @pytest.mark.parametrize("trans", [(False, False), (True, False), (False, True), (True, True)])
 def test_gemm_dmma(shape, trans):

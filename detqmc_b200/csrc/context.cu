@@ -1208,6 +1208,7 @@ int dqmc_create(const dqmc_params* params, int n_replicas, int device, dqmc_ctx*
     CK(dmalloc(&ctx->ctrl, R));
     CK(dmalloc(&ctx->accepted, R));
     CK(dmalloc(&ctx->siteState, R));
+    CK(dmalloc(&ctx->cursorAdd, R));
     CK(dmalloc(&ctx->kvec, R));
     CK(dmalloc(&ctx->errflag, 1));
     CK(dmalloc(&ctx->actions, R));
@@ -1282,7 +1283,7 @@ void dqmc_destroy(dqmc_ctx* ctx) {
                    ctx->bkPhi, ctx->bkCosh, ctx->bkSinh, ctx->rvals, ctx->tau, ctx->perm, ctx->colnorm, ctx->vecA,
                    ctx->vecB, ctx->vecC, ctx->vecD, ctx->dtmp, ctx->logdet, ctx->bkLogdet, ctx->consistency, ctx->eyeM,
                    ctx->onesV, ctx->X, ctx->Y, ctx->cfgStream, ctx->shiftL, ctx->shiftR, ctx->fmAcc, ctx->rngbuf, ctx->cursor, ctx->ctrl, ctx->accepted, ctx->errflag,
-                   ctx->actions, ctx->shiftbuf, ctx->cbtab, ctx->acceptedTotal, ctx->siteState, ctx->kvec, ctx->aux,
+                   ctx->actions, ctx->shiftbuf, ctx->cbtab, ctx->acceptedTotal, ctx->siteState, ctx->cursorAdd, ctx->kvec, ctx->aux,
                    ctx->propT, ctx->propTinv, ctx->hubScale, ctx->hubTmp, ctx->hubReal};
     for (void* p : dev) if (p) cudaFree(p);
     qr_workspace_destroy(&ctx->qr);
@@ -1886,13 +1887,47 @@ int dqmc_sweep(dqmc_ctx* ctx, int thermalization) {
                             (ctx->performedSweeps % ctx->p.globalUpdateInterval == 0);
     if (global_now) {
         // globalMove() before a down-sweep, detmodel.h:1422-1424 + detsdwopdim.cpp:3460-3485
-        if (preloaded) RET(sync_resident_cursor(ctx));        // the host draws must come after the device's
-        else RET(host_sync_rng(ctx));
+        // a global shift reads OPDIM + 1 values per replica; a Wolff cluster an unbounded number (it re-heads the window)
+        const bool inplace = preloaded && !ctx->p.wolffClusterUpdate && !ctx->p.wolffClusterShiftUpdate;
+        if (preloaded && !inplace) {
+            RET(sync_resident_cursor(ctx));
+        } else if (inplace) {
+            // The host draws come from the same streams, right after what the device has consumed.  The window
+            // stays where it is: the host reads its values at the device cursors without consuming them, and the
+            // cursors are advanced by what it read (no re-upload of the resident window).
+            CK(cudaMemcpyAsync(ctx->h_cursor, ctx->cursor, sizeof(int) * ctx->R, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaMemcpyAsync(ctx->h_ctrl, ctx->ctrl, sizeof(dqmc_control_data) * ctx->R, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaMemcpyAsync(ctx->h_err, ctx->errflag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            if (*ctx->h_err) { ctx->err = "device error flag set (random-number window exhausted)"; return DQMC_ERR_STATE; }
+            for (int r = 0; r < ctx->R; ++r) {
+                ctx->ctrl_host[r] = ctx->h_ctrl[r];
+                ctx->rng[r].begin_window((size_t)ctx->h_cursor[r]);
+            }
+        } else {
+            RET(host_sync_rng(ctx));
+        }
         // DetSDW::globalMove, detsdwopdim.cpp:3460-3485: shift, Wolff cluster, Wolff cluster + shift, in this order
-        if (ctx->p.globalShift) RET(global_move_kind(ctx, 0, nullptr));
-        if (ctx->p.wolffClusterUpdate) RET(global_move_kind(ctx, 1, nullptr));
-        if (ctx->p.wolffClusterShiftUpdate) RET(global_move_kind(ctx, 2, nullptr));
-        if (preloaded) RET(reupload_resident(ctx));
+        int grc = DQMC_OK;
+        if (ctx->p.globalShift) grc = global_move_kind(ctx, 0, nullptr);
+        if (grc == DQMC_OK && ctx->p.wolffClusterUpdate) grc = global_move_kind(ctx, 1, nullptr);
+        if (grc == DQMC_OK && ctx->p.wolffClusterShiftUpdate) grc = global_move_kind(ctx, 2, nullptr);
+        if (preloaded && !inplace && grc == DQMC_OK) grc = reupload_resident(ctx);
+        if (inplace) {
+            size_t most = 0;
+            for (int r = 0; r < ctx->R; ++r) {
+                const size_t used = ctx->rng[r].end_window();
+                ctx->h_cursor[r] = (int)used;
+                most = std::max(most, used);
+            }
+            if (grc == DQMC_OK) {
+                CK(cudaMemcpyAsync(ctx->cursorAdd, ctx->h_cursor, sizeof(int) * ctx->R, cudaMemcpyHostToDevice, ctx->stream));
+                CKL(launch_cursor_add(ctx->cursor, ctx->cursorAdd, ctx->R, ctx->stream));
+                CK(cudaStreamSynchronize(ctx->stream));          // h_cursor is reused
+                ctx->rngResidentUsedBound += most;
+            }
+        }
+        RET(grc);
     }
     if (!preloaded) RET(stream_begin_sweep(ctx));
     RET(run_sweep(ctx, ctx->lastSweepDir == +1 ? -1 : +1, thermalization));

@@ -79,6 +79,7 @@ cudaError_t launch_exchange_pack(const double* rng, const int* cursor, int windo
                                  const dqmc_control_data* ctrl, double* ctrl_out, int R, int copy_uniforms,
                                  cudaStream_t st);
 cudaError_t launch_cursor_advance(int* cursor, int rep, int n, cudaStream_t st);
+cudaError_t launch_cursor_add(int* cursor, const int* add, int n, cudaStream_t st);
 
 // ------------------------------------------------------------------------------------------------
 // Batched complex GEMM on FP64 tensor cores (gemm_kernels.cu)
@@ -288,6 +289,7 @@ struct dqmc_ctx {
     dqmc_control_data* ctrl;      // [R] device
     uint32_t* accepted;    // [R]
     int* siteState;        // [R] delayed-update rounds: next site
+    int* cursorAdd;        // [R] values read by the host from the resident window (global moves)
     int* kvec;             // [R] delayed-update rounds: pending rank
     int* errflag;
     double* actions;       // [R]

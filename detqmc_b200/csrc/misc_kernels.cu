@@ -191,6 +191,10 @@ __global__ void exchange_pack_kernel(const double* rng, const int* cursor, int w
     for (int i = tid; i < R * words; i += nth) ctrl_out[i] = src[i];
 }
 __global__ void cursor_advance_kernel(int* cursor, int rep, int n) { cursor[rep] += n; }
+__global__ void cursor_add_kernel(int* cursor, const int* add, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) cursor[i] += add[i];
+}
 
 }  // namespace
 
@@ -198,6 +202,10 @@ cudaError_t launch_exchange_pack(const double* rng, const int* cursor, int windo
                                  const dqmc_control_data* ctrl, double* ctrl_out, int R, int copy_uniforms,
                                  cudaStream_t st) {
     exchange_pack_kernel<<<8, 256, 0, st>>>(rng, cursor, window, uni_out, n_uni, ctrl, ctrl_out, R, copy_uniforms);
+    return cudaGetLastError();
+}
+cudaError_t launch_cursor_add(int* cursor, const int* add, int n, cudaStream_t st) {
+    cursor_add_kernel<<<(n + 127) / 128, 128, 0, st>>>(cursor, add, n);
     return cudaGetLastError();
 }
 cudaError_t launch_cursor_advance(int* cursor, int rep, int n, cudaStream_t st) {

@@ -116,6 +116,10 @@ void RngStream::skip(size_t n) {
 }
 
 double RngStream::draw() {
+    if (win_) {
+        ensure(winOff_ + winUsed_ + 1);
+        return buf_[head_ + winOff_ + winUsed_++];
+    }
     ensure(1);
     consumed_ += 1;
     return buf_[head_++];

@@ -60,6 +60,11 @@ public:
     uint64_t consumed() const { return consumed_; }
     // make sure at least n values are buffered (generation can then overlap with device work)
     void prefetch(size_t n) { ensure(n); }
+    // Read-only window: between begin_window(off) and end_window() draws return the values at head + off + i WITHOUT
+    // consuming them -- that stretch of the stream is resident on the device, whose cursor owns the consumption.
+    // end_window() returns how many values were read.
+    void begin_window(size_t off) { win_ = true; winOff_ = off; winUsed_ = 0; }
+    size_t end_window() { win_ = false; return winUsed_; }
 private:
     void ensure(size_t n);
     Dsfmt19937 gen_;
@@ -68,6 +73,8 @@ private:
     std::vector<double> buf_;     // buffered values [head_, buf_.size())
     size_t head_ = 0;
     uint64_t consumed_;
+    bool win_ = false;
+    size_t winOff_ = 0, winUsed_ = 0;
 };
 
 }  // namespace dqmc

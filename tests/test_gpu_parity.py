@@ -329,6 +329,30 @@ def test_lanes_do_not_change_results():
             assert b1.control_data(rep).lastAccRatioLocal_phi == b.control_data(rep).lastAccRatioLocal_phi
 
 
+def test_resident_random_numbers_equal_streamed():
+    """dqmc_rng_preload (the random-number stream of several sweeps resident in HBM, what bench.py times as `value`)
+    gives the same trajectory as the default streamed mode, across global moves (sweeps 0 and 10, where the host
+    draws from the same streams) and with replica-exchange steps consuming look-ahead uniforms in between."""
+    from dqmc_oracle import SdwParams
+    for wolff in (False, True):                # global shift only: in-place window; with clusters: re-headed window
+      p = SdwParams(L=4, m=20, s=10, wolffClusterUpdate=wolff)
+      idx = [1, 2, 3]
+      a = make_batch(p, n_replicas=3, rng_indices=idx)
+      c = make_batch(p, n_replicas=3, rng_indices=idx)
+      c.rng_preload(14)
+      for sw in range(12):
+          a.sweepThermalization()
+          c.sweepThermalization()
+      c.rng_release()
+      for rep in range(3):
+          assert maxabs(a.phi(rep), c.phi(rep)) == 0.0
+          assert maxabs(a.green(rep), c.green(rep)) == 0.0
+          assert a.control_data(rep).phiDelta == c.control_data(rep).phiDelta
+          assert a.control_data(rep).acceptedGlobalShifts == c.control_data(rep).acceptedGlobalShifts
+          assert list(a.wolff_statistics(rep)) == list(c.wolff_statistics(rep))
+          assert maxabs(a.rng_draw(3, rep=rep), c.rng_draw(3, rep=rep)) == 0.0
+
+
 def test_global_shift_move_vs_oracle():
     from dqmc_oracle import SdwOracle
     g = load_golden("sdw_o2_flux_L4")

@@ -9,11 +9,11 @@
 // was uploaded before the launch; the kernel consumes them with a cursor in exactly the
 // reference's order: OPDIM values per proposal, plus one more only if the acceptance probability is
 // <= 1 (:3113).  The decision needs only the MSF x MSF site block of the effective Green's function
-// (G + pending X*Y), which warp 0 gathers with shuffle reductions; the full rows / columns are
-// gathered by the whole CTA only on acceptance.  Every `delaySteps` accepted updates (or at the end
-// of the slice) the rank-(MSF*j) correction G += X*Y is flushed as a tensor-core GEMM (DMMA
-// m8n8k4.f64) by the same CTA, straight out of L1/L2.  Reductions are fixed-order: the kernel is
-// deterministic, which the 100-sweep trajectory parity requires.
+// (G + pending X*Y); the full rows / columns are gathered by the whole CTA only on acceptance.  After
+// `delaySteps` accepted updates (or at the end of the slice) a ROUND ends and the host launches the rank-K
+// correction G += X*Y as a batched tensor-core GEMM (DMMA m8n8k4.f64) on all SMs (context.cu: launch_update);
+// only small delay blocks (< 8, e.g. Woodbury = 1) are flushed by the CTA itself.  Reductions are fixed-order:
+// the kernel is deterministic, which the 100-sweep trajectory parity requires.
 #include "dqmc_internal.h"
 
 namespace dqmc {

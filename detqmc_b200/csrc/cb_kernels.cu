@@ -203,7 +203,7 @@ void cb_build_tables(const dqmc_params& p, std::vector<cplx>& out) {
 // ------------------------------------------------------------------------------------------------
 namespace {
 
-constexpr int kCbTileVecs = 8;      // vectors per CTA tile
+constexpr int kCbTileVecs = 16;     // vectors per CTA tile (16: 5-9 % faster than 8 on the single-slice multiplies)
 constexpr int kCbMaxThreads = 256;
 
 __device__ __forceinline__ cplx cfma(cplx a, cplx b, cplx c) {    // a*b + c

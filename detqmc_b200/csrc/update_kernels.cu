@@ -398,9 +398,15 @@ __global__ void __launch_bounds__(MAXT) update_round_kernel(UpdateModel md, Upda
     double newp[3] = {0, 0, 0}, cNew = 0, xNew = 0, probSPhi = 0;
     cplx Dl[MSF * MSF];
     bool have_rng = true;
+    // per-phase clock counts of replica 0: development builds only (-DDQMC_UPD_TIMING); the counters cost 14 registers
+    // in a kernel that sits at the 168-register cap of an 11-warp CTA
+#ifdef DQMC_UPD_TIMING
     long long tq[6] = {0, 0, 0, 0, 0, 0};
     long long tmark = clock64();
 #define TICK(i) if (a.debug) { long long now__; asm volatile("mov.u64 %0, %%clock64;" : "=l"(now__) :: "memory"); tq[i] += now__ - tmark; tmark = now__; }
+#else
+#define TICK(i)
+#endif
 
     for (; site < N; ++site) {
         // K_done: pending terms already in X, Y;  the update of site-1 (if accepted) adds MSF more in phase 1
@@ -630,9 +636,11 @@ __global__ void __launch_bounds__(MAXT) update_round_kernel(UpdateModel md, Upda
         }
     }
     __syncthreads();
+#ifdef DQMC_UPD_TIMING
     if (a.debug && b == 0 && (tid == 0 || tid == 32 || tid == kDecThreads))
         printf("upd dbg round %d tid %3d sites %d: ph1 %lld waitA %lld ph2(dec) %lld waitB %lld Sred %lld top %lld\n", a.round, tid,
                site - site0, tq[0], tq[1], tq[2], tq[3], tq[4], tq[5]);
+#endif
     if (a.inline_flush && j > 0 && !sAbort) {
         flush_delayed(G, X, Y, D, MSF * j, KMAX);
         j = 0;

@@ -70,8 +70,9 @@ template <int n>
 __device__ __forceinline__ cplx small_det_inv(const cplx* Min, cplx* inv) {
     if (n == 2) {
         const cplx det = csub(cmul(Min[0], Min[3]), cmul(Min[1], Min[2]));
-        const cplx one = make_double2(1, 0);
-        const cplx id = cdiv(one, det);
+        // 1 / det with one division (conj(det) / |det|^2)
+        const double rden = 1.0 / (det.x * det.x + det.y * det.y);
+        const cplx id = make_double2(det.x * rden, -det.y * rden);
         inv[0] = cmul(Min[3], id);
         inv[1] = cmul(make_double2(-Min[1].x, -Min[1].y), id);
         inv[2] = cmul(make_double2(-Min[2].x, -Min[2].y), id);
@@ -391,6 +392,7 @@ __global__ void __launch_bounds__(MAXT) update_round_kernel(UpdateModel md, Upda
     int j = 0;                                             // accepted updates whose X, Y columns exist or are in flight
     int delayNow = min(md.delaySteps, N - site0);
     int site = site0;
+    int sx = site0 % L, sy = site0 / L;                    // coordinates of `site`
     bool prev_acc = false;                                 // previous site accepted, its X_j / Y_j still to be appended
     cplx Gr[TPT][MSF], Gc[TPT][MSF];                       // gather threads: row / column entries of G for the last decided site
 
@@ -408,7 +410,7 @@ __global__ void __launch_bounds__(MAXT) update_round_kernel(UpdateModel md, Upda
 #define TICK(i)
 #endif
 
-    for (; site < N; ++site) {
+    for (; site < N; ++site, sx = (sx + 1 == L ? 0 : sx + 1), sy += (sx == 0 ? 1 : 0)) {
         // K_done: pending terms already in X, Y;  the update of site-1 (if accepted) adds MSF more in phase 1
         const int K_done = MSF * (j - (prev_acc ? 1 : 0));
         const int buf = site & 1;
@@ -423,7 +425,7 @@ __global__ void __launch_bounds__(MAXT) update_round_kernel(UpdateModel md, Upda
                 if (have_rng) {
                     double oldp[3] = {0, 0, 0};
                     double oldSq = 0, newSq = 0, tdot = 0, sdot = 0;
-                    const int x = site % L, y = site / L;
+                    const int x = sx, y = sy;              // site % L, site / L, tracked incrementally
                     const int nb0 = y * L + (x + 1 == L ? 0 : x + 1);
                     const int nb1 = y * L + (x == 0 ? L - 1 : x - 1);
                     const int nb2 = (y + 1 == L ? 0 : y + 1) * L + x;

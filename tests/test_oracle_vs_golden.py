@@ -219,3 +219,21 @@ def test_fermionic_observables_vs_reference_values(tag):
         assert np.allclose(vec, g[tag + "_vectors"][it], rtol=1e-9, atol=1e-11)
     if n == 3:
         assert maxabs(o.shift_green_symmetric(), g[tag + "_green_shifted"]) < 1e-10
+
+
+def test_host_mirror_observables_equal_oracle():
+    """The host mirror's copy of the bosonic observables (detqmc_b200/pt.py, used by the parallel-tempering loop and
+    DetSDWBatch.bosonic_observables) against the reference's values and the oracle restatement; numToString formatting
+    of the sub-directory names (tools.h:46-50)."""
+    import os
+    from detqmc_b200.pt import bosonic_observables as mirror_observables, num_to_string
+    from dqmc_oracle import bosonic_observables
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "bosonic_observables.npz"))
+    for tag in ("o2", "o3", "o2_L6"):
+        for it in range(g[tag + "_phi"].shape[0]):
+            phi = g[tag + "_phi"][it]
+            a, b = mirror_observables(phi, 0.1), bosonic_observables(phi, 0.1)
+            got = [a["normMeanPhi"], a["associatedEnergy"], a["phiRhoS_Gs"], a["phiRhoS_Gc"]]
+            assert np.allclose(got, g[tag + "_obs"][it], rtol=1e-12, atol=1e-13)
+            assert a["normMeanPhi"] == b["normMeanPhi"] and a["associatedEnergy"] == b["associatedEnergy"]
+    assert [num_to_string(v) for v in (-1.9, 0.4, -1.0, 1e-7, 123456789.0)] == ["-1.9", "0.4", "-1", "1e-07", "1.23457e+08"]

@@ -38,10 +38,10 @@ def snapshot(name):
     print("kept", variant_path(name))
 
 
-def run(names, tests, steps, warmup):
+def run(names, tests, steps, warmup, untested=()):
     keep = LIB + ".ab_keep"
     shutil.copy2(LIB, keep)
-    tested = set()
+    tested = set(untested)
     try:
         for name in names:
             shutil.copy2(variant_path(name), LIB)
@@ -73,9 +73,10 @@ if __name__ == "__main__":
     ap.add_argument("--tests", default=QUICK)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--no-tests-for", default="head", help="comma-separated variants whose parity is already known")
     ap.add_argument("names", nargs="*")
     a = ap.parse_args()
     if a.snapshot:
         snapshot(a.snapshot)
     else:
-        run(a.names, a.tests, a.steps, a.warmup)
+        run(a.names, a.tests, a.steps, a.warmup, [n for n in a.no_tests_for.split(",") if n])

@@ -237,3 +237,17 @@ def test_host_mirror_observables_equal_oracle():
             assert np.allclose(got, g[tag + "_obs"][it], rtol=1e-12, atol=1e-13)
             assert a["normMeanPhi"] == b["normMeanPhi"] and a["associatedEnergy"] == b["associatedEnergy"]
     assert [num_to_string(v) for v in (-1.9, 0.4, -1.0, 1e-7, 123456789.0)] == ["-1.9", "0.4", "-1", "1e-07", "1.23457e+08"]
+
+
+def test_oracle_full_size_setup_vs_reference():
+    """BASELINE config C2 at full size (L = 8, beta = 8, D = 128): G and log|det| of the NumPy oracle after set-up
+    against the summary the unmodified reference produced (tools/make_golden.py, BIG fixtures).  (The first sweep of
+    C2 and C3 was checked the same way when the fixtures were made -- identical acceptance and fields -- but takes
+    minutes in pure Python, too long for this suite.)"""
+    g = load_golden("sdw_c2_L8_b8_traj100")
+    o = SdwOracle(sdw_params_of(g))
+    st = int(g["stride"])
+    assert np.abs(o.green[0][::st, ::st] - g["green0_sub"]).max() < 1e-11 * float(g["green0_maxabs"])
+    assert abs(np.trace(o.green[0]) - g["green0_trace"]) < 1e-10
+    assert abs(np.log(o.green_inv_sv[0]).sum() - float(g["logdet0"])) < 1e-10 * abs(float(g["logdet0"]))
+    assert maxabs(o.phi, g["phi0"]) == 0.0

@@ -210,6 +210,101 @@ def config_stream_fixture():
     print("config_streams done")
 
 
+# ------------------------------------------------------------------------------------------------
+# Full-size fixtures (BASELINE configs C2-C5).  The matrices are too large to commit whole: a strided
+# sub-sample of G plus three full-matrix functionals (trace, Frobenius norm, a fixed random bilinear
+# probe u^H G v) are stored; the fields (phi / aux) are stored whole so that "identical accept /
+# reject decisions" is checked site by site.
+def probe_vectors(D):
+    gen = np.random.default_rng(20261018)
+    u = gen.standard_normal(D) + 1j * gen.standard_normal(D)
+    v = gen.standard_normal(D) + 1j * gen.standard_normal(D)
+    return u / np.linalg.norm(u), v / np.linalg.norm(v)
+
+
+def summarise_matrix(G, stride):
+    u, v = probe_vectors(G.shape[0])
+    return dict(sub=np.ascontiguousarray(G[::stride, ::stride]), trace=np.trace(G), fro=np.linalg.norm(G),
+                probe=np.vdot(u, G @ v), maxabs=np.abs(G).max())
+
+
+def put(d, key, G, stride):
+    for k, v in summarise_matrix(G, stride).items():
+        d[key + "_" + k] = v
+
+
+def big_sdw_fixture(name, sweeps, kw, stride, keep=(1,)):
+    import time
+    p = SdwParams(**kw)
+    t0 = time.time()
+    r = rb.RefSdw(p)
+    d = {"params": pars_json(p), "stride": stride}
+    d["phi0"] = r.phi()
+    put(d, "green0", r.green(), stride)
+    d["logdet0"] = np.log(r.sv()).sum()
+    put(d, "green_slice_m", r.green_for_timeslice(p.m), stride)
+    print(name, "setup %.0f s" % (time.time() - t0), flush=True)
+    acc, gsa, pdel = [], [], []
+    for sw in range(sweeps):
+        r.sweep(therm=True)
+        sc = r.scalars()
+        acc.append(sc["lastAccRatio"]); gsa.append(sc["acceptedGlobalShifts"]); pdel.append(sc["phiDelta"])
+        if sw + 1 in keep or sw + 1 == sweeps:
+            d["phi_after_%d" % (sw + 1)] = r.phi()
+            G = r.green()
+            put(d, "green_after_%d" % (sw + 1), G, stride)
+            # the reference's own wrapped-vs-recomputed deviation at this point (bounds what parity can mean)
+            k = int(sc["currentTimeslice"]) or p.m          # G(0) = G(beta); computeGreenFromScratch(0) is not defined
+            Gs = r.green_for_timeslice(k)
+            d["ref_selfdev_after_%d" % (sw + 1)] = np.abs(G - Gs).max() / np.abs(Gs).max()
+        print(name, "sweep", sw + 1, "%.0f s" % (time.time() - t0), "acc", acc[-1], flush=True)
+    d["lastAccRatio"], d["acceptedGlobalShifts"], d["phiDelta"] = np.array(acc), np.array(gsa), np.array(pdel)
+    d["n_sweeps"] = sweeps
+    sc = r.scalars()
+    d["phiAction_final"], d["exchangeAction_final"] = sc["phiAction"], sc["exchangeAction"]
+    d["rng_next"] = r.rng_draw(8)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
+    print(name, "done", flush=True)
+
+
+def big_hubbard_fixture(name, sweeps, kw, stride):
+    import time
+    p = HubbardParams(**kw)
+    t0 = time.time()
+    r = rb.RefHubbard(p)
+    d = {"params": pars_json(p), "stride": stride}
+    d["aux0"] = r.aux()[1:].astype(np.int8)
+    for gc in (0, 1):
+        put(d, "green0_%d" % gc, r.green(gc), stride)
+        d["logdet0_%d" % gc] = np.log(r.sv(gc)).sum()
+    print(name, "setup %.0f s" % (time.time() - t0), flush=True)
+    for sw in range(sweeps):
+        r.sweep(False)
+        d["aux_after_%d" % (sw + 1)] = r.aux()[1:].astype(np.int8)
+        for gc in (0, 1):
+            put(d, "green_after_%d_%d" % (sw + 1, gc), r.green(gc), stride)
+        print(name, "sweep", sw + 1, "%.0f s" % (time.time() - t0), flush=True)
+    d["n_sweeps"] = sweeps
+    d["rng_next"] = r.rng_draw(8)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
+    print(name, "done", flush=True)
+
+
+BIG = {
+    # C2: 100-sweep trajectory at L = 8, beta = 8
+    "sdw_c2_L8_b8_traj100": lambda: big_sdw_fixture("sdw_c2_L8_b8_traj100", 100, dict(L=8, m=80, s=10), 2,
+                                                    keep=(1, 2, 10, 50)),
+    # C3: one replica of the L = 12, beta = 10 ladder, 6 sweeps (3 down, 3 up)
+    "sdw_c3_L12_b10": lambda: big_sdw_fixture("sdw_c3_L12_b10", 6, dict(L=12, m=100, s=10), 3, keep=(1, 2)),
+    # C4: O(3), L = 14, beta = 14 (D = 784)
+    "sdw_c4_o3_L14_b14": lambda: big_sdw_fixture("sdw_c4_o3_L14_b14", 2, dict(opdim=3, L=14, m=140, s=10,
+                                                                                weakZflux=False), 4, keep=(1,)),
+    # C5: DetHubbard L = 20, U = 8, beta = 20
+    "hubbard_c5_L20_U8_b20": lambda: big_hubbard_fixture("hubbard_c5_L20_U8_b20", 2,
+                                                         dict(L=20, m=200, s=10, U=8.0, mu=0.0, t=1.0), 4),
+}
+
+
 if __name__ == "__main__":
     assert rb.available(), "build oracle/_ref first: make -C oracle"
 
@@ -219,6 +314,9 @@ if __name__ == "__main__":
         sdw_fixture("sdw_o2_wolffshift_L4", 6, dict(wolffClusterShiftUpdate=True, globalShift=False, globalUpdateInterval=2,
                                                     rngIndex=7))
 
+    if len(sys.argv) > 1 and sys.argv[1] in BIG:                     # python tools/make_golden.py <big fixture name>
+        BIG[sys.argv[1]]()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "config_streams":
         config_stream_fixture()
         sys.exit(0)

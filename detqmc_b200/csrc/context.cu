@@ -50,7 +50,7 @@ namespace {
 
 // profiling categories (dqmc_profile_get): one per kernel family
 const char* const kProfNames[DQMC_PROF_NCAT] = {"cb_mult", "gemm_dmma", "qrcp_factor", "qr_form_q", "trsm_upper",
-                                                "update_slice", "other", "cb_chain", "update_flush"};
+                                                "update_slice", "other", "cb_chain", "update_flush", "update_build_xy"};
 int prof_category(const char* call) {
     if (!std::strncmp(call, "cb_launch", 9)) return 0;
     if (!std::strncmp(call, "gemm_launch", 11)) return 1;
@@ -650,12 +650,26 @@ int launch_update(dqmc_ctx* ctx, int k, int therm) {
     // small delay blocks (Woodbury = 1) are flushed inside the kernel; otherwise every round is
     // followed by the rank-K update G += X Y on all SMs
     a.inline_flush = ctx->p.delaySteps < 8 ? 1 : 0;
+    a.y_in_smem = 0;
+    const bool window = ctx->winSites > 0 && !a.inline_flush;
+    a.wmax = ctx->winSites;
+    a.strideScratch = (long long)ctx->winScratchStride; a.strideHdr = ctx->winHdrStride;
+    a.wscratch = window ? ctx->winScratch + size_t(ro) * ctx->winScratchStride : nullptr;
+    a.whdr = window ? ctx->winHdr + size_t(ro) * ctx->winHdrStride : nullptr;
     const int rounds = update_rounds_per_slice(ctx->umodel, a.inline_flush);
     const int passes = std::max(1, ctx->p.repeatUpdateInSlice);       // updateInSlice repeats the pass, detsdwopdim.cpp:2438
     for (int rd = 0; rd < rounds * passes; ++rd) {
         a.round = rd % rounds;
         a.final_pass = rd / rounds == passes - 1 ? 1 : 0;
-        CKL(update_round_launch(ctx->umodel, a, ctx->stream));
+        if (window) {
+            // decisions of up to delaySteps acceptances on the window block, then X, Y for all rows / columns
+            CKL(update_window_launch(ctx->umodel, a, ctx->stream));
+            ctx->profForce = 9;
+            CKL(update_build_xy_launch(ctx->umodel, a, ctx->stream));
+            ctx->profForce = -1;
+        } else {
+            CKL(update_round_launch(ctx->umodel, a, ctx->stream));
+        }
         if (!a.inline_flush) {
             GemmArgs g;
             g.M = g.N = ctx->D; g.K = ctx->kmax;
@@ -851,14 +865,21 @@ int global_move_kind(dqmc_ctx* ctx, int kind, int32_t* accepted_out) {
         if (ctx->opdim < 3) probFermion = probFermion * probFermion;
         const double prob = probScalar * probFermion;
         ctx->lastGlobalProb[r] = prob;
-        double* ws = ctx->wolffStats.data() + 5 * r;      // attempted, accepted, attemptedShift, acceptedShift, added size
-        if (kind == 0) ctx->ctrl_host[r].attemptedGlobalShifts += 1;
-        else ws[kind == 1 ? 0 : 2] += 1;
+        // UpdateStatistics counters (detsdwopdim.cpp:3487-3562, 3647-3748) live in the control data: they follow the
+        // control parameter through dqmc_exchange_apply / dqmc_set_control_data and the checkpoint
+        dqmc_control_data& cd = ctx->ctrl_host[r];
+        if (kind == 0) cd.attemptedGlobalShifts += 1;
+        else if (kind == 1) cd.attemptedWolffClusterUpdates += 1;
+        else cd.attemptedWolffClusterShiftUpdates += 1;
         bool acc = prob >= 1.0 || ctx->rng[r].draw() < prob;
         if (accepted_out) accepted_out[r] = acc ? 1 : 0;
         if (acc) {
-            if (kind == 0) ctx->ctrl_host[r].acceptedGlobalShifts += 1;
-            else { ws[kind == 1 ? 1 : 3] += 1; ws[4] += clusterSize[r]; }
+            if (kind == 0) cd.acceptedGlobalShifts += 1;
+            else {
+                if (kind == 1) cd.acceptedWolffClusterUpdates += 1;
+                else cd.acceptedWolffClusterShiftUpdates += 1;
+                cd.addedWolffClusterSize += clusterSize[r];
+            }
         } else {
             // globalMoveRestoreBackups (:3902-3917) for this replica
             CK(cudaMemcpyAsync(ctx->phi + size_t(r) * phi_stride(ctx), ctx->bkPhi + size_t(r) * phi_stride(ctx),
@@ -1168,6 +1189,17 @@ int dqmc_create(const dqmc_params* params, int n_replicas, int device, dqmc_ctx*
     CK(dmalloc(&ctx->Y, D * ctx->kmax * R));
     CK(cudaMemsetAsync(ctx->X, 0, sizeof(cplx) * D * ctx->kmax * R, ctx->stream));   // finite everywhere (see extend_xy)
     CK(cudaMemsetAsync(ctx->Y, 0, sizeof(cplx) * D * ctx->kmax * R, ctx->stream));
+    // window rounds (update_kernels.cu): per-round record of the accepted updates; DQMC_UPDATE_LEGACY=1 keeps the
+    // round kernel of round 1 (development A/B switch)
+    ctx->winSites = (hub || std::getenv("DQMC_UPDATE_LEGACY")) ? 0 : update_window_sites(ctx->umodel);
+    ctx->winScratchStride = ctx->winSites ? update_window_scratch_elems(ctx->umodel) : 0;
+    ctx->winHdrStride = ctx->winSites ? update_window_hdr_ints(ctx->umodel) : 0;
+    if (ctx->winSites) {
+        CK(dmalloc(&ctx->winScratch, ctx->winScratchStride * R));
+        CK(dmalloc(&ctx->winHdr, size_t(ctx->winHdrStride) * R));
+        CK(cudaMemsetAsync(ctx->winScratch, 0, sizeof(cplx) * ctx->winScratchStride * R, ctx->stream));
+        CK(cudaMemsetAsync(ctx->winHdr, 0, sizeof(int) * size_t(ctx->winHdrStride) * R, ctx->stream));
+    }
     ctx->rngCap = size_t(ctx->m) * ctx->N * (ctx->p.opdim + 1) * size_t(std::max(1, hub ? 1 : ctx->p.repeatUpdateInSlice));   // Hubbard: <= 2 values per attempt
     ctx->rngAlloc = ctx->rngCap * kStreamSweeps;               // streamed mode keeps several sweeps' worth on the device
     ctx->rngStride = ctx->rngCap;
@@ -1214,6 +1246,7 @@ int dqmc_create(const dqmc_params* params, int n_replicas, int device, dqmc_ctx*
     CK(dmalloc(&ctx->actions, R));
     CK(dmalloc(&ctx->shiftbuf, 3 * R));
     CK(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_rng), 2 * ctx->rngCap * R * sizeof(double)));   // two staging chunks
+    ctx->hRngAlloc = 2 * ctx->rngCap * R;
     CK(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_cursor), R * sizeof(int)));
     CK(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_scalars), (8 * R + 16) * sizeof(double)));
     CK(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_ctrl), R * sizeof(dqmc_control_data)));
@@ -1258,7 +1291,6 @@ int dqmc_create(const dqmc_params* params, int n_replicas, int device, dqmc_ctx*
     ctx->rng.resize(R);
     ctx->h_r.assign(R, p.r);
     ctx->lastGlobalProb.assign(R, 0.0);
-    ctx->wolffStats.assign(size_t(5) * R, 0.0);
     ctx->ctrl_host.resize(R);
     for (size_t r = 0; r < R; ++r) {
         ctx->rng[r].seed(0, (uint32_t)r);
@@ -1282,7 +1314,7 @@ void dqmc_destroy(dqmc_ctx* ctx) {
                    ctx->stQ, ctx->stT, ctx->stD, ctx->bkQ, ctx->bkT, ctx->bkD, ctx->phi, ctx->coshT, ctx->sinhT,
                    ctx->bkPhi, ctx->bkCosh, ctx->bkSinh, ctx->rvals, ctx->tau, ctx->perm, ctx->colnorm, ctx->vecA,
                    ctx->vecB, ctx->vecC, ctx->vecD, ctx->dtmp, ctx->logdet, ctx->bkLogdet, ctx->consistency, ctx->eyeM,
-                   ctx->onesV, ctx->X, ctx->Y, ctx->cfgStream, ctx->shiftL, ctx->shiftR, ctx->fmAcc, ctx->rngbuf, ctx->cursor, ctx->ctrl, ctx->accepted, ctx->errflag,
+                   ctx->onesV, ctx->X, ctx->Y, ctx->winScratch, ctx->winHdr, ctx->cfgStream, ctx->shiftL, ctx->shiftR, ctx->fmAcc, ctx->rngbuf, ctx->cursor, ctx->ctrl, ctx->accepted, ctx->errflag,
                    ctx->actions, ctx->shiftbuf, ctx->cbtab, ctx->acceptedTotal, ctx->siteState, ctx->cursorAdd, ctx->kvec, ctx->aux,
                    ctx->propT, ctx->propTinv, ctx->hubScale, ctx->hubTmp, ctx->hubReal};
     for (void* p : dev) if (p) cudaFree(p);
@@ -1855,7 +1887,11 @@ int dqmc_get_fermionic_observables(dqmc_ctx* ctx, int rep, double* scalars, doub
 
 int dqmc_get_wolff_statistics(dqmc_ctx* ctx, int rep, double* out) {
     if (!valid_rep(ctx, rep) || !out) return DQMC_ERR_PARAM;
-    for (int i = 0; i < 5; ++i) out[i] = ctx->wolffStats[size_t(5) * rep + i];
+    RET(host_sync_rng(ctx));
+    const dqmc_control_data& cd = ctx->ctrl_host[rep];    // attempted, accepted, attemptedShift, acceptedShift, added size
+    out[0] = cd.attemptedWolffClusterUpdates; out[1] = cd.acceptedWolffClusterUpdates;
+    out[2] = cd.attemptedWolffClusterShiftUpdates; out[3] = cd.acceptedWolffClusterShiftUpdates;
+    out[4] = cd.addedWolffClusterSize;
     return DQMC_OK;
 }
 
@@ -1946,14 +1982,23 @@ int dqmc_rng_preload(dqmc_ctx* ctx, int n_sweeps) {
     if (ctx->rngResident) RET(dqmc_rng_release(ctx));
     RET(host_sync_rng(ctx));
     const size_t per = ctx->rngCap * size_t(std::max(n_sweeps, 2)) + 16;
-    if (per > ctx->rngAlloc || true) {
+    if (per > ctx->rngAlloc) {
         CK(cudaStreamSynchronize(ctx->stream));
+        // the captured sweeps hold the address of the old buffer in their kernel arguments: drop them
+        for (auto& g : ctx->graphs) cudaGraphExecDestroy(g.exec);
+        ctx->graphs.clear();
         cudaFree(ctx->rngbuf);
-        cudaFreeHost(ctx->h_rng);
-        ctx->rngbuf = nullptr; ctx->h_rng = nullptr;
+        ctx->rngbuf = nullptr;
         CK(dmalloc(&ctx->rngbuf, per * ctx->R));
-        CK(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_rng), per * ctx->R * sizeof(double)));
         ctx->rngAlloc = per;
+    }
+    if (per * ctx->R > ctx->hRngAlloc) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (ctx->copyStream) CK(cudaStreamSynchronize(ctx->copyStream));
+        cudaFreeHost(ctx->h_rng);
+        ctx->h_rng = nullptr;
+        CK(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_rng), per * ctx->R * sizeof(double)));
+        ctx->hRngAlloc = per * ctx->R;
     }
     ctx->rngStride = per;
     for (int r = 0; r < ctx->R; ++r)

@@ -184,7 +184,19 @@ struct UpdateArgs {
     int debug;                    // print per-phase clock counts of replica 0 (development)
     int final_pass;               // last of the repeatUpdateInSlice passes: record the acceptance statistics / adapt the step
     int y_in_smem;                // set by the launcher: the CTA keeps the pending Y rows in shared memory
+    // ---- window rounds (update_window_kernel + update_build_xy_kernel) ----
+    dqmc::cplx* wscratch;         // [batch][strideScratch] per-round record of the accepted updates (see update_kernels.cu)
+    long long strideScratch;
+    int* whdr;                    // [batch][strideHdr] ints: nacc, site0, w, pad, sites[delaySteps]
+    int strideHdr;
+    int wmax;                     // sites per window
 };
+// window rounds: sizes of the per-replica scratch (cplx elements) and header (ints) for a model
+int update_window_sites(const UpdateModel& m);            // sites per window, 0 = window path not applicable
+size_t update_window_scratch_elems(const UpdateModel& m);
+int update_window_hdr_ints(const UpdateModel& m);
+cudaError_t update_window_launch(const UpdateModel& m, const UpdateArgs& a, cudaStream_t st);
+cudaError_t update_build_xy_launch(const UpdateModel& m, const UpdateArgs& a, cudaStream_t st);
 // one round of the delayed local updates; with inline_flush == 0 the caller applies
 // G += X[:, :kvec] Y[:kvec, :] (rank-K update GEMM) after every round
 int update_rounds_per_slice(const UpdateModel& m, int inline_flush);
@@ -256,6 +268,8 @@ struct dqmc_ctx {
     double* bkLogdet;
     double* consistency;   // [nmat]
     dqmc::cplx* X; dqmc::cplx* Y;   // [R][D*KMAX]
+    dqmc::cplx* winScratch; int* winHdr;   // window rounds: per-round record [R][winScratchStride], header [R][winHdrStride]
+    size_t winScratchStride; int winHdrStride; int winSites;
     double* cfgStream;               // [R][N*m*opdim] configuration-stream staging (allocated on first use)
     // fermionic measurements (allocated on first use): block-diagonal shift matrices, per-replica accumulators
     dqmc::cplx* shiftL; dqmc::cplx* shiftR; double* fmAcc; size_t fmAccLen; int fmSlices;
@@ -265,6 +279,7 @@ struct dqmc_ctx {
     int* cursor;           // [R]
     int rngWindow;         // number of values per replica in the uploaded window
     size_t rngAlloc, rngStride;
+    size_t hRngAlloc;      // doubles in the pinned staging buffer h_rng
     bool rngResident;      // window pre-loaded for several sweeps (dqmc_rng_preload) or streamed (rngAuto)
     bool rngAuto;          // streamed mode of dqmc_sweep: chunks are uploaded one sweep ahead on copyStream
     size_t rngUploaded;    // values per replica present in the device buffer (streamed mode)
@@ -303,7 +318,6 @@ struct dqmc_ctx {
     int* h_err;
     uint32_t* h_acc;
     std::vector<double> lastGlobalProb;
-    std::vector<double> wolffStats;   // [R][5] attempted, accepted, attemptedShift, acceptedShift, addedWolffClusterSize
 
     // Hubbard
     int32_t* aux;          // [R][(m+1)*N]

@@ -678,6 +678,431 @@ __global__ void __launch_bounds__(MAXT) update_round_kernel(UpdateModel md, Upda
     }
 }
 
+
+// =================================================================================================
+// Window rounds: the same Metropolis chain, organised so that NO D-wide work sits between two decisions.
+//
+// A round covers a window of w consecutive sites.  The CTA keeps the (MSF w) x (MSF w) block of the effective
+// Green's function that couples the window's sites to each other in shared memory ("Gw") and applies every accepted
+// update to that block immediately (rank MSF, O((MSF w)^2)): by the algebra of updateInSlice_delayed
+// (detsdwopdim.cpp:3064-3138) the window block of G + X Y evolves by its own rows and columns only, so the
+// decision of a site needs nothing but its MSF x MSF diagonal block of Gw.  The D-wide columns X_j = C_j Delta_j and
+// rows Y_j = M_j^-1 (R_j - 1_j) of the delayed update are NOT formed here: the kernel records, per accepted site,
+// the site, Delta_j, M_j^-1 and the window parts of X_j / Y_j (which are the couplings X_l[s_j, :], Y_l[:, s_j]
+// that a later C_j / R_j needs), and `update_build_xy_kernel` rebuilds X and Y for all rows / columns in parallel on
+// all SMs afterwards; the rank-K GEMM G += X Y follows as before.  The arithmetic is that of the reference's delayed
+// update, reordered.
+//
+//   warp 0        proposal, decision (all lanes redundantly: no divergence, no shuffles); on acceptance lane <-> future
+//                 site: window parts of X_j, Y_j and the diagonal blocks of all future sites
+//   warps 1..     apply Gw += x_w y_w to the future part of the window while warp 0 goes on with the next sites
+//                 (named barriers kBarStart / kBarDone; warp 0 waits only when the NEXT acceptance arrives
+//                 before the previous block update has finished)
+//
+// Scratch record of a round, per replica (cplx elements, WPM = MSF * wmax):
+//   [j][0][MSF*MSF] Delta_j   [j][1][MSF*MSF] M_j^-1                      j < delaySteps
+//   then [j][0][q][WPM] x_w of term (j, q)    [j][1][q][WPM] y_w          window position a = i + r * w
+// Header (ints): nacc, site0, w, 0, sites[delaySteps].
+// =================================================================================================
+constexpr int kWinThreads = 256;
+constexpr int kBarStart = 1, kBarDone = 2;
+
+__device__ __forceinline__ void named_bar_sync(int id, int n) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int n) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
+
+template <int MSF>
+__host__ __device__ inline size_t win_small_off(int j, int which) { return size_t(j * 2 + which) * MSF * MSF; }
+template <int MSF>
+__host__ __device__ inline size_t win_xy_off(int jmax, int WPM, int j, int which, int q) {
+    return size_t(jmax) * 2 * MSF * MSF + (size_t(j * 2 + which) * MSF + q) * WPM;
+}
+
+template <int MSF, int OPDIM>
+__global__ void __launch_bounds__(kWinThreads) update_window_kernel(UpdateModel md, UpdateArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int D = md.D, N = md.N, L = md.L;
+    const int wmax = a.wmax, WPM = MSF * wmax, ldw = WPM + 1;
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    int* hdr = a.whdr + size_t(b) * a.strideHdr;
+    const int site0 = a.round == 0 ? 0 : a.site_state[b];
+    if (site0 >= N) {                                      // slice already finished in an earlier round
+        if (tid == 0) {
+            if (a.kvec) a.kvec[b] = 0;
+            hdr[0] = 0;
+        }
+        return;
+    }
+    const int w = min(wmax, N - site0);                    // sites of this window
+    const int WP = MSF * w;                                // window positions: a = i + r * w  <->  matrix index site0 + i + r * N
+    double* phik = reinterpret_cast<double*>(smem_raw);    // [OPDIM][N]   fields of this slice, kept current
+    double* tsum = phik + OPDIM * N;                       // [OPDIM][wmax] phi(k+1) + phi(k-1) at the window's sites
+    double* ck = tsum + OPDIM * wmax;                      // [wmax] cosh table
+    double* xk = ck + wmax;                                // [wmax] sinh table
+    double* rngs = xk + wmax;                              // [wmax * (OPDIM+1)] random numbers from the cursor on
+    cplx* Gw = reinterpret_cast<cplx*>(rngs + ((wmax * (OPDIM + 1) + 1) & ~1));   // [WPM][ldw] column major
+    cplx* Sdiag = Gw + size_t(ldw) * WPM;                  // [wmax][MSF*MSF] diagonal blocks, owned by warp 0
+    cplx* xw_s = Sdiag + wmax * MSF * MSF;                 // [MSF][WPM] window part of the newest X_j
+    cplx* yw_s = xw_s + MSF * WPM;                         // [MSF][WPM] window part of the newest Y_j
+    __shared__ int sPos, sQuit, sNload;
+
+    const int k = a.k;
+    cplx* G = a.G + size_t(b) * a.strideG;
+    double* phi = a.phi + size_t(b) * a.stridePhi;
+    double* coshT = a.coshT + size_t(b) * a.strideTab;
+    double* sinhT = a.sinhT + size_t(b) * a.strideTab;
+    const double* rng = a.rng + size_t(b) * a.strideRng;
+    cplx* scratch = a.wscratch + size_t(b) * a.strideScratch;
+    const double rpar = a.rvals[b];
+    const double phiDelta = a.ctrl[b].phiDelta;
+    const double dtau = md.dtau;
+    const int cursor0 = a.cursor[b];
+    double* phik_g = phi + size_t(k) * OPDIM * N;
+    {
+        const int kEarlier = k > 1 ? k - 1 : md.m;
+        const int kLater = k < md.m ? k + 1 : 1;
+        const double* pl = phi + size_t(kLater) * OPDIM * N;
+        const double* pe = phi + size_t(kEarlier) * OPDIM * N;
+        for (int i = tid; i < OPDIM * N; i += blockDim.x) phik[i] = phik_g[i];
+        for (int i = tid; i < OPDIM * w; i += blockDim.x) {
+            const int d = i / w, pos = i - d * w;
+            tsum[d * wmax + pos] = pl[d * N + site0 + pos] + pe[d * N + site0 + pos];
+        }
+        for (int i = tid; i < w; i += blockDim.x) {
+            ck[i] = coshT[size_t(k) * N + site0 + i];
+            xk[i] = sinhT[size_t(k) * N + site0 + i];
+        }
+        const int want = w * (OPDIM + 1);
+        const int have = max(0, min(want, a.rngWindow - cursor0));
+        for (int i = tid; i < have; i += blockDim.x) rngs[i] = rng[cursor0 + i];
+        // window block of G: column c of the block is MSF contiguous runs of w elements of a column of G
+        for (int idx = tid; idx < WP * WP; idx += blockDim.x) {
+            const int c = idx / WP, ar = idx - c * WP;
+            const int rc = c / w, ic = c - rc * w;
+            const int ra = ar / w, ia = ar - ra * w;
+            Gw[ar + size_t(c) * ldw] = G[size_t(site0 + ic + rc * N) * D + site0 + ia + ra * N];
+        }
+        if (tid == 0) { sQuit = 0; sNload = have; sPos = 0; }
+    }
+    __syncthreads();
+    for (int i = tid; i < w * MSF * MSF; i += blockDim.x) {
+        const int pos = i / (MSF * MSF), e = i - pos * MSF * MSF, r = e / MSF, c = e - r * MSF;
+        Sdiag[i] = Gw[pos + r * w + size_t(pos + c * w) * ldw];
+    }
+    __syncthreads();
+
+    if (warp == 0) {
+        // ============================================================ the Metropolis chain
+        int cur = 0, j = 0, pos = 0;
+        unsigned accepted = 0;
+        bool outstanding = false, aborted = false;
+        const int delayNow = min(md.delaySteps, N - site0);
+        const int nload = sNload;
+        int sx = site0 % L, sy = site0 / L;
+        for (; pos < w; ++pos, sx = (sx + 1 == L ? 0 : sx + 1), sy += (sx == 0 ? 1 : 0)) {
+            const int site = site0 + pos;
+            if (cur + OPDIM + 1 > nload) { aborted = true; break; }
+            // ---------------------------------------------- proposal (proposeNewPhiBox, deltaSPhi, get_delta_forsite)
+            double oldp[3] = {0, 0, 0}, newp[3] = {0, 0, 0};
+            double oldSq = 0, newSq = 0, tdot = 0, sdot = 0;
+            {
+                const int x = sx, y = sy;
+                const int nb0 = y * L + (x + 1 == L ? 0 : x + 1);
+                const int nb1 = y * L + (x == 0 ? L - 1 : x - 1);
+                const int nb2 = (y + 1 == L ? 0 : y + 1) * L + x;
+                const int nb3 = (y == 0 ? L - 1 : y - 1) * L + x;
+#pragma unroll
+                for (int d = 0; d < OPDIM; ++d) {
+                    oldp[d] = phik[d * N + site];
+                    const double u = rngs[cur + d];
+                    newp[d] = oldp[d] + (-phiDelta + (phiDelta - (-phiDelta)) * u);   // randRange(-delta, +delta)
+                    const double diff = newp[d] - oldp[d];
+                    oldSq += oldp[d] * oldp[d];
+                    newSq += newp[d] * newp[d];
+                    const double* pk = phik + d * N;
+                    const double sn = ((pk[nb0] + pk[nb1]) + pk[nb2]) + pk[nb3];
+                    tdot += tsum[d * wmax + pos] * diff;
+                    sdot += sn * diff;
+                }
+            }
+            const double sqDiff = newSq - oldSq;
+            const double pow4Diff = newSq * newSq - oldSq * oldSq;
+            const double d1 = (1.0 / (md.c * md.c * dtau)) * (sqDiff - tdot);
+            const double d2 = 0.5 * dtau * (4.0 * sqDiff - 2.0 * sdot);
+            const double d3 = dtau * (0.5 * rpar * sqDiff + 0.25 * md.u * pow4Diff);
+            const double probSPhi = exp(-(d1 + d2 + d3));
+            double cNew, sc;
+            cosh_sinhc(md.lambda * dtau * sqrt(newSq), cNew, sc);
+            const double xNew = md.lambda * dtau * sc;              // sinh(lambda dtau |phi|) / |phi|
+            cplx Dl[MSF * MSF];
+            {
+                cplx evOld[MSF * MSF], emvNew[MSF * MSF];
+                ev_block<MSF, OPDIM>(evOld, +1.0, oldp, ck[pos], xk[pos]);
+                ev_block<MSF, OPDIM>(emvNew, -1.0, newp, cNew, xNew);
+#pragma unroll
+                for (int r = 0; r < MSF; ++r)
+#pragma unroll
+                    for (int c = 0; c < MSF; ++c) {
+                        cplx sacc = make_double2(r == c ? -1.0 : 0.0, 0.0);
+#pragma unroll
+                        for (int t = 0; t < MSF; ++t) sacc = cfma(emvNew[r * MSF + t], evOld[t * MSF + c], sacc);
+                        Dl[r * MSF + c] = sacc;
+                    }
+            }
+            // ---------------------------------------------- decision: M = 1 - S Delta + Delta
+            cplx M[MSF * MSF], Minv[MSF * MSF];
+#pragma unroll
+            for (int r = 0; r < MSF; ++r)
+#pragma unroll
+                for (int c = 0; c < MSF; ++c) {
+                    cplx sacc = make_double2(r == c ? 1.0 : 0.0, 0.0);
+#pragma unroll
+                    for (int t = 0; t < MSF; ++t) sacc = csub(sacc, cmul(Sdiag[pos * MSF * MSF + r * MSF + t], Dl[t * MSF + c]));
+                    M[r * MSF + c] = cadd(sacc, Dl[r * MSF + c]);
+                }
+            const cplx det = small_det_inv<MSF>(M, Minv);
+            const double probFermion = (OPDIM == 3) ? det.x : (det.x * det.x + det.y * det.y);
+            const double prob = probSPhi * probFermion;
+            cur += OPDIM;
+            bool acc;
+            if (prob > 1.0) {
+                acc = true;
+            } else {
+                acc = rngs[cur] < prob;
+                cur += 1;
+            }
+            if (!acc) continue;
+            // ---------------------------------------------- accepted
+            accepted += 1;
+            if (lane == 0) {
+#pragma unroll
+                for (int d = 0; d < OPDIM; ++d) {
+                    phik[d * N + site] = newp[d];
+                    phik_g[d * N + site] = newp[d];
+                }
+                coshT[size_t(k) * N + site] = cNew;
+                sinhT[size_t(k) * N + site] = xNew;
+                hdr[4 + j] = site;
+#pragma unroll
+                for (int i = 0; i < MSF * MSF; ++i) {
+                    scratch[win_small_off<MSF>(j, 0) + i] = Dl[i];
+                    scratch[win_small_off<MSF>(j, 1) + i] = Minv[i];
+                }
+            }
+            const bool last = (j + 1 == delayNow) || (pos + 1 == w);
+            if (!last) {
+                if (outstanding) {                          // column / row `pos` of Gw must be current
+                    named_bar_sync(kBarDone, blockDim.x);
+                    outstanding = false;
+                }
+                const int rf = w - 1 - pos;                 // future sites of the window
+                cplx* xg = scratch + win_xy_off<MSF>(md.delaySteps, WPM, j, 0, 0);
+                cplx* yg = scratch + win_xy_off<MSF>(md.delaySteps, WPM, j, 1, 0);
+                for (int off = lane; off < rf; off += 32) {
+                    const int f = pos + 1 + off;
+                    cplx xv[MSF][MSF], yv[MSF][MSF];        // xv[r][q] = X_(j,q)[f + r w],  yv[q][r] = Y_(j,q)[f + r w]
+#pragma unroll
+                    for (int r = 0; r < MSF; ++r) {
+                        const int ar = f + r * w;
+                        cplx cg[MSF], rg[MSF];
+#pragma unroll
+                        for (int p = 0; p < MSF; ++p) {
+                            cg[p] = Gw[ar + size_t(pos + p * w) * ldw];
+                            rg[p] = Gw[pos + p * w + size_t(ar) * ldw];
+                        }
+#pragma unroll
+                        for (int q = 0; q < MSF; ++q) {
+                            cplx xa = make_double2(0, 0), ya = make_double2(0, 0);
+#pragma unroll
+                            for (int p = 0; p < MSF; ++p) {
+                                xa = cfma(cg[p], Dl[p * MSF + q], xa);
+                                ya = cfma(Minv[q * MSF + p], rg[p], ya);
+                            }
+                            xv[r][q] = xa;
+                            yv[q][r] = ya;
+                            xw_s[q * WPM + ar] = xa;
+                            yw_s[q * WPM + ar] = ya;
+                            xg[size_t(q) * WPM + ar] = xa;
+                            yg[size_t(q) * WPM + ar] = ya;
+                        }
+                    }
+#pragma unroll
+                    for (int r = 0; r < MSF; ++r)
+#pragma unroll
+                        for (int c = 0; c < MSF; ++c) {
+                            cplx sacc = Sdiag[f * MSF * MSF + r * MSF + c];
+#pragma unroll
+                            for (int q = 0; q < MSF; ++q) sacc = cfma(xv[r][q], yv[q][c], sacc);
+                            Sdiag[f * MSF * MSF + r * MSF + c] = sacc;
+                        }
+                }
+                if (lane == 0) sPos = pos;
+                __threadfence_block();
+                __syncwarp();
+                named_bar_arrive(kBarStart, blockDim.x);
+                outstanding = true;
+            } else {
+                __syncwarp();
+            }
+            j += 1;
+            if (j == delayNow) { ++pos; break; }
+        }
+        if (outstanding) named_bar_sync(kBarDone, blockDim.x);
+        if (lane == 0) sQuit = 1;
+        __threadfence_block();
+        __syncwarp();
+        named_bar_arrive(kBarStart, blockDim.x);
+        if (lane == 0) {
+            const int site = aborted ? N : site0 + pos;
+            if (aborted) atomicExch(a.errflag, 1);
+            a.cursor[b] = cursor0 + cur;
+            hdr[0] = aborted ? 0 : j;
+            hdr[1] = site0;
+            hdr[2] = w;
+            if (a.kvec) a.kvec[b] = aborted ? 0 : MSF * j;
+            a.site_state[b] = site;
+            const unsigned total = (a.round == 0 ? 0u : a.accepted[b]) + accepted;
+            a.accepted[b] = total;
+            if (a.acceptedTotal) a.acceptedTotal[b] += accepted;
+            if (site >= N && !aborted && a.final_pass) {
+                // end of the slice (last pass): acceptance statistics and step-size adaptation
+                // (RunningAverage::addValue, RunningAverage.h:57-68; updateInSliceThermalization, detsdwopdim.cpp:3329-3341)
+                dqmc_control_data* cd = a.ctrl + b;
+                const double ratio = double(total) / double(N);
+                cd->lastAccRatioLocal_phi = ratio;
+                if (a.thermalization) {
+                    const int ps = cd->ra_samples_added % 100;
+                    if (cd->ra_samples_added >= 100) cd->ra_average -= cd->ra_values[ps] / 100.0;
+                    cd->ra_values[ps] = ratio;
+                    cd->ra_average += ratio / 100.0;
+                    cd->ra_samples_added += 1;
+                    if (cd->ra_count < 100) cd->ra_count += 1;
+                    if (cd->ra_samples_added % 100 == 0) {
+                        if (cd->ra_average < md.accRatio) cd->phiDelta *= 0.95;
+                        else if (cd->ra_average > md.accRatio) cd->phiDelta *= 1.05;
+                    }
+                }
+            }
+        }
+    } else {
+        // ============================================================ block updates of the window
+        const int bw = warp - 1, nbw = nwarps - 1;
+        for (;;) {
+            named_bar_sync(kBarStart, blockDim.x);
+            if (*(volatile int*)&sQuit) break;
+            const int pos = *(volatile int*)&sPos;
+            const int rf = w - 1 - pos, nf = MSF * rf;
+            for (int ci = bw; ci < nf; ci += nbw) {
+                const int rc = ci / rf;
+                const int c = pos + 1 + (ci - rc * rf) + rc * w;
+                cplx yv[MSF];
+#pragma unroll
+                for (int q = 0; q < MSF; ++q) yv[q] = yw_s[q * WPM + c];
+                cplx* col = Gw + size_t(c) * ldw;
+#pragma unroll
+                for (int r = 0; r < MSF; ++r)
+                    for (int i = lane; i < rf; i += 32) {
+                        const int ar = pos + 1 + i + r * w;
+                        cplx gv = col[ar];
+#pragma unroll
+                        for (int q = 0; q < MSF; ++q) gv = cfma(xw_s[q * WPM + ar], yv[q], gv);
+                        col[ar] = gv;
+                    }
+            }
+            __threadfence_block();
+            named_bar_arrive(kBarDone, blockDim.x);
+        }
+    }
+}
+
+// Rebuild the D-wide X (D x K) and Y (K x D) of a window round from its record, one thread per row of X
+// (blockIdx.y == 0) or column of Y (blockIdx.y == 1):
+//   C_j[t, q] = G[t, s_j + qN] + sum_{l < j, p} X_(l,p)[t] * Y_(l,p)[s_j + qN]        X_(j,r)[t] = sum_q C_j[t, q] Delta_j[q, r]
+//   R_j[q, t] = G[s_j + qN, t] - delta + sum_{l < j, p} X_(l,p)[s_j + qN] * Y_(l,p)[t]  Y_(j,q')[t] = sum_q Minv_j[q', q] R_j[q, t]
+// (detsdwopdim.cpp:3064-3070, 3123-3138).  The couplings Y_(l,p)[s_j + qN], X_(l,p)[s_j + qN] are window entries
+// recorded by update_window_kernel.
+constexpr int kBxyThreads = 64;
+
+template <int MSF>
+__global__ void __launch_bounds__(kBxyThreads) update_build_xy_kernel(UpdateModel md, UpdateArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int b = blockIdx.z;
+    const int* hdr = a.whdr + size_t(b) * a.strideHdr;
+    const int J = hdr[0];
+    if (J <= 0) return;
+    const int D = md.D, N = md.N;
+    const int site0 = hdr[1], w = hdr[2];
+    const int WPM = MSF * a.wmax;
+    const int K = MSF * J;
+    const int side = blockIdx.y;                           // 0: rows of X, 1: columns of Y
+    const int tid = threadIdx.x;
+    const int t = blockIdx.x * kBxyThreads + tid;
+    cplx* coef = reinterpret_cast<cplx*>(smem_raw);        // [K][J][MSF]: coupling of term l to (j, q), l < j * MSF
+    cplx* small = coef + size_t(K) * J * MSF;              // [J][MSF*MSF]: Delta_j (side 0) or Minv_j (side 1)
+    int* sites = reinterpret_cast<int*>(small + J * MSF * MSF);   // [J]
+    cplx* rowbuf = reinterpret_cast<cplx*>(sites + ((J + 3) & ~3));   // [K][kBxyThreads]
+    const cplx* scratch = a.wscratch + size_t(b) * a.strideScratch;
+    for (int i = tid; i < J; i += kBxyThreads) sites[i] = hdr[4 + i];
+    for (int i = tid; i < J * MSF * MSF; i += kBxyThreads) {
+        const int j = i / (MSF * MSF), e = i - j * MSF * MSF;
+        small[i] = scratch[win_small_off<MSF>(j, side) + e];
+    }
+    __syncthreads();
+    // side 0 needs Y_(l,p)[s_j + qN] (which = 1), side 1 needs X_(l,p)[s_j + qN] (which = 0)
+    for (int i = tid; i < K * J * MSF; i += kBxyThreads) {
+        const int l = i / (J * MSF), rem = i - l * (J * MSF), j = rem / MSF, q = rem - j * MSF;
+        cplx v = make_double2(0, 0);
+        if (l < j * MSF) {
+            const int pj = sites[j] - site0 + q * w;
+            v = scratch[win_xy_off<MSF>(md.delaySteps, WPM, l / MSF, side == 0 ? 1 : 0, l % MSF) + pj];
+        }
+        coef[i] = v;
+    }
+    __syncthreads();
+    if (t >= D) return;
+    const cplx* G = a.G + size_t(b) * a.strideG;
+    cplx* out = (side == 0 ? a.X : a.Y) + size_t(b) * a.strideXY;
+    for (int j = 0; j < J; ++j) {
+        const int sj = sites[j];
+        cplx acc0[MSF], acc1[MSF];
+#pragma unroll
+        for (int q = 0; q < MSF; ++q) {
+            const int u = sj + q * N;
+            cplx v = side == 0 ? G[size_t(u) * D + t] : G[size_t(t) * D + u];
+            if (side == 1 && t == u) v.x -= 1.0;
+            acc0[q] = v;
+            acc1[q] = make_double2(0, 0);
+        }
+        const int nl = j * MSF;                            // even for MSF = 2, 4: two independent accumulation chains
+        for (int l = 0; l < nl; l += 2) {
+            const cplx v0 = rowbuf[l * kBxyThreads + tid], v1 = rowbuf[(l + 1) * kBxyThreads + tid];
+            const cplx* c0 = coef + (size_t(l) * J + j) * MSF;
+            const cplx* c1 = coef + (size_t(l + 1) * J + j) * MSF;
+#pragma unroll
+            for (int q = 0; q < MSF; ++q) {
+                acc0[q] = cfma(v0, c0[q], acc0[q]);
+                acc1[q] = cfma(v1, c1[q], acc1[q]);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < MSF; ++q) acc0[q] = cadd(acc0[q], acc1[q]);
+#pragma unroll
+        for (int r = 0; r < MSF; ++r) {
+            cplx v = make_double2(0, 0);
+#pragma unroll
+            for (int q = 0; q < MSF; ++q)
+                v = side == 0 ? cfma(acc0[q], small[j * MSF * MSF + q * MSF + r], v)
+                              : cfma(small[j * MSF * MSF + r * MSF + q], acc0[q], v);
+            rowbuf[(j * MSF + r) * kBxyThreads + tid] = v;
+            out[size_t(j * MSF + r) * D + t] = v;
+        }
+    }
+}
+
 }  // namespace
 
 int update_rounds_per_slice(const UpdateModel& m, int inline_flush) {
@@ -714,6 +1139,62 @@ cudaError_t update_round_launch(const UpdateModel& m, const UpdateArgs& a, cudaS
     else LAUNCH3(4, 3)
 #undef LAUNCH3
 #undef LAUNCH
+    return cudaGetLastError();
+}
+
+
+// ---- window rounds ------------------------------------------------------------------------------
+// Sites per window: two delay blocks' worth (a round ends after delaySteps acceptances, at ~50 % acceptance that
+// takes 2 * delaySteps sites), bounded by the shared memory of the (MSF w)^2 window block.
+int update_window_sites(const UpdateModel& m) {
+    if (m.delaySteps < 8) return 0;                        // tiny delay blocks are flushed inside the legacy kernel
+    if (m.msf * m.delaySteps > 64) return 0;               // update_build_xy keeps K x J x MSF couplings in shared memory
+    int w = 2 * m.delaySteps;
+    const int cap = 64 / m.msf;                            // (MSF w)^2 * 16 B <= 64 KiB
+    if (w > cap) w = cap;
+    if (w > m.N) w = m.N;
+    w &= ~1;
+    return w < 2 ? 0 : w;
+}
+size_t update_window_scratch_elems(const UpdateModel& m) {
+    const size_t wpm = size_t(m.msf) * update_window_sites(m);
+    return size_t(m.delaySteps) * 2 * m.msf * m.msf + size_t(m.delaySteps) * 2 * m.msf * wpm;
+}
+int update_window_hdr_ints(const UpdateModel& m) { return (4 + m.delaySteps + 3) & ~3; }
+
+cudaError_t update_window_launch(const UpdateModel& m, const UpdateArgs& a, cudaStream_t st) {
+    const int wmax = a.wmax, wpm = m.msf * wmax;
+    const size_t smem = size_t(m.opdim * m.N + m.opdim * wmax + 2 * wmax + ((wmax * (m.opdim + 1) + 1) & ~1)) * sizeof(double) +
+                        (size_t(wpm + 1) * wpm + size_t(wmax) * m.msf * m.msf + size_t(2) * m.msf * wpm) * sizeof(cplx);
+#define LAUNCHW(MSF, OPD)                                                                                   \
+    {                                                                                                       \
+        cudaError_t e = cudaFuncSetAttribute(update_window_kernel<MSF, OPD>,                                \
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
+        if (e != cudaSuccess) return e;                                                                     \
+        update_window_kernel<MSF, OPD><<<a.batch, kWinThreads, smem, st>>>(m, a);                           \
+    }
+    if (m.opdim == 1) LAUNCHW(2, 1)
+    else if (m.opdim == 2) LAUNCHW(2, 2)
+    else LAUNCHW(4, 3)
+#undef LAUNCHW
+    return cudaGetLastError();
+}
+
+cudaError_t update_build_xy_launch(const UpdateModel& m, const UpdateArgs& a, cudaStream_t st) {
+    const int J = m.delaySteps, K = m.msf * J;
+    const size_t smem = (size_t(K) * J * m.msf + size_t(J) * m.msf * m.msf + size_t(K) * kBxyThreads) * sizeof(cplx) +
+                        size_t((J + 3) & ~3) * sizeof(int);
+    dim3 grid((m.D + kBxyThreads - 1) / kBxyThreads, 2, a.batch);
+#define LAUNCHB(MSF)                                                                                        \
+    {                                                                                                       \
+        cudaError_t e = cudaFuncSetAttribute(update_build_xy_kernel<MSF>,                                   \
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
+        if (e != cudaSuccess) return e;                                                                     \
+        update_build_xy_kernel<MSF><<<grid, kBxyThreads, smem, st>>>(m, a);                                 \
+    }
+    if (m.msf == 2) LAUNCHB(2)
+    else LAUNCHB(4)
+#undef LAUNCHB
     return cudaGetLastError();
 }
 

@@ -27,7 +27,10 @@ class DqmcParams(ctypes.Structure):
 class ControlData(ctypes.Structure):
     _fields_ = [("phiDelta", c_f64), ("lastAccRatioLocal_phi", c_f64), ("ra_average", c_f64),
                 ("ra_samples_added", c_i32), ("ra_count", c_i32), ("ra_values", c_f64 * 100),
-                ("acceptedGlobalShifts", c_u32), ("attemptedGlobalShifts", c_u32)]
+                ("acceptedGlobalShifts", c_u32), ("attemptedGlobalShifts", c_u32),
+                ("acceptedWolffClusterUpdates", c_u32), ("attemptedWolffClusterUpdates", c_u32),
+                ("acceptedWolffClusterShiftUpdates", c_u32), ("attemptedWolffClusterShiftUpdates", c_u32),
+                ("addedWolffClusterSize", c_f64)]
 
 
 # every symbol include/dqmc_gpu.h declares: (name, restype, argtypes)

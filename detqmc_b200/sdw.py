@@ -357,7 +357,7 @@ class DetSDWBatch:
         self._ck(self.lib.dqmc_profile_enable(self.h, int(on)))
 
     def profile_get(self):
-        ncat = 9                                      # DQMC_PROF_NCAT
+        ncat = 10                                     # DQMC_PROF_NCAT
         ms = np.zeros(ncat)
         cnt = np.zeros(ncat, dtype=np.uint64)
         self._ck(self.lib.dqmc_profile_get(self.h, _ptr(ms), _ptr(cnt)))
@@ -391,7 +391,7 @@ def exchange_walk(control_values, par_process, process_par, actions, uniforms):
     return used.value, swapped[:n - 1]
 
 
-CTRL_WORDS = ctypes.sizeof(ControlData) // 8      # 105 doubles per control-data blob
+CTRL_WORDS = ctypes.sizeof(ControlData) // 8      # 108 doubles per control-data blob
 
 
 class ReplicaExchangeLadder:
@@ -432,7 +432,7 @@ class ReplicaExchangeLadder:
         return self.values[self.process_par[lo:lo + self.n_local]]
 
     def walk(self, gathered):
-        """gathered: array [world, payload_len].  Returns (r_new[n_local], ctrl_new[n_local, 105],
+        """gathered: array [world, payload_len].  Returns (r_new[n_local], ctrl_new[n_local, CTRL_WORDS],
         n_uniforms_used_by_this_rank)."""
         g = np.asarray(gathered, dtype=np.float64).reshape(self.world, self.payload_len)
         nl, nu = self.n_local, self.n_uniforms

@@ -88,6 +88,13 @@ typedef struct dqmc_control_data {
     double ra_values[100];
     uint32_t acceptedGlobalShifts;
     uint32_t attemptedGlobalShifts;
+    /* Wolff-cluster statistics of UpdateStatistics (detsdwopdim.h:283-300): like the counters above they belong to
+     * the control PARAMETER, not to the replica, so they travel with the blob through an exchange and a checkpoint */
+    uint32_t acceptedWolffClusterUpdates;
+    uint32_t attemptedWolffClusterUpdates;
+    uint32_t acceptedWolffClusterShiftUpdates;
+    uint32_t attemptedWolffClusterShiftUpdates;
+    double addedWolffClusterSize;
 } dqmc_control_data;
 
 /* ---- lifecycle ------------------------------------------------------------------------------ */
@@ -265,7 +272,7 @@ int dqmc_rng_preload(dqmc_ctx* ctx, int n_sweeps);
 int dqmc_rng_release(dqmc_ctx* ctx);
 
 /* ---- measurement hooks (no reference twin; the reference's -DTIMING timers, timing.h:32-78) ---- */
-#define DQMC_PROF_NCAT 9
+#define DQMC_PROF_NCAT 10
 /* Bracket every kernel launch with CUDA events on the context's stream and accumulate device
  * time per kernel family. */
 int dqmc_profile_enable(dqmc_ctx* ctx, int on);

@@ -353,6 +353,32 @@ def test_resident_random_numbers_equal_streamed():
           assert maxabs(a.rng_draw(3, rep=rep), c.rng_draw(3, rep=rep)) == 0.0
 
 
+def test_random_number_modes_interleaved():
+    """Streamed sweeps, then a pre-loaded window (re-allocates the device buffer), release, streamed again, a second
+    pre-load of a different size: the captured sweep graphs must never replay with the address of a freed buffer
+    (dqmc_rng_preload vs the graph cache).  Trajectory equals a plain streamed run."""
+    from dqmc_oracle import SdwParams
+    p = SdwParams(L=4, m=20, s=10)
+    idx = [1, 2]
+    a = make_batch(p, n_replicas=2, rng_indices=idx)
+    c = make_batch(p, n_replicas=2, rng_indices=idx)
+    plan = [("stream", 3), ("preload", 12, 4), ("stream", 3), ("preload", 3, 2), ("preload", 20, 3), ("stream", 2)]
+    for step in plan:
+        n = step[-1]
+        if step[0] == "preload":
+            c.rng_preload(step[1])
+        for _ in range(n):
+            a.sweepThermalization()
+            c.sweepThermalization()
+        if step[0] == "preload":
+            c.rng_release()
+        for rep in range(2):
+            assert maxabs(a.phi(rep), c.phi(rep)) == 0.0, step
+    for rep in range(2):
+        assert maxabs(a.green(rep), c.green(rep)) == 0.0
+        assert maxabs(a.rng_draw(3, rep=rep), c.rng_draw(3, rep=rep)) == 0.0
+
+
 def test_global_shift_move_vs_oracle():
     from dqmc_oracle import SdwOracle
     g = load_golden("sdw_o2_flux_L4")
@@ -393,6 +419,13 @@ def test_wolff_cluster_moves_vs_reference_record():
             assert maxabs(b.phi(0)[1:], g[tag + "_phi"][it][1:]) < 1e-13
             assert relerr(b.green(0), g[tag + "_green"][it]) < TOL_G
         assert maxabs(b.rng_draw(4, rep=0), g[tag + "_rng_next"]) == 0.0
+        # the Wolff statistics are part of the control data (UpdateStatistics, detsdwopdim.cpp:5227): they follow the
+        # control parameter when the blob is installed on another replica (exchange, checkpoint)
+        cd = b.control_data(0)
+        assert [cd.attemptedWolffClusterUpdates, cd.acceptedWolffClusterUpdates, cd.attemptedWolffClusterShiftUpdates,
+                cd.acceptedWolffClusterShiftUpdates, cd.addedWolffClusterSize] == list(b.wolff_statistics(0))
+        b.set_control_data(cd, rep=1)
+        assert list(b.wolff_statistics(1)) == list(b.wolff_statistics(0))
 
 
 def test_sweep_simple_vs_oracle():
@@ -728,36 +761,41 @@ def test_full_size_vs_reference_golden(name):
         if key in g.files:
             assert maxabs(b.phi()[1:], g[key][1:]) < 1e-11, (name, sw)
             # the reference's own wrapped-vs-recomputed deviation at this point bounds what parity can mean
-            tol = max(TOL_G, 100.0 * float(g["ref_selfdev_after_%d" % (sw + 1)]))
+            sd = "ref_selfdev_after_%d" % (sw + 1)
+            tol = max(TOL_G, 100.0 * float(g[sd])) if sd in g.files else TOL_G
             assert_matrix_matches_summary(b.green(), g, "green_after_%d" % (sw + 1), tol, (name, sw))
     assert np.array_equal(b.rng_draw(8), g["rng_next"])                # the stream was consumed exactly as in the reference
 
 
 @pytest.mark.timeout(900)
 def test_hubbard_full_size_vs_reference_golden():
-    """BASELINE config C5 (DetHubbard L = 20, U = 8, beta = 20) at full size against the unmodified reference: G and
-    log|det| of both spin components after set-up, identical auxiliary fields after each of two sweeps (80 000
-    decisions each), G after the sweeps."""
+    """BASELINE config C5 (DetHubbard L = 20, U = 8, beta = 20) at full size against the unmodified reference:
+    identical auxiliary fields after each of two sweeps (80 000 decisions each) and an identically consumed random
+    stream; log|det| within 1e-10.  Green's function: the reference's own SVD-based value sits 2.9e-9 (spin up) /
+    9e-10 (spin down) away from the s-converged column-pivoted-QR value (tools/c5_accuracy_study.py, which wrote
+    tests/golden/hubbard_c5_truth.npz), so the CUDA path is held to that converged value within 2e-10 and to the
+    reference within 1e-8 = a few times the reference's own error."""
     from detqmc_b200 import DetHubbardBatch
     from helpers import hubbard_params_of
     g = load_golden("hubbard_c5_L20_U8_b20")
+    truth = load_golden("hubbard_c5_truth")
     p = hubbard_params_of(g)
     b = DetHubbardBatch(p)
     assert np.array_equal(b.auxfield()[1:], g["aux0"])
+    st = int(truth["stride"])
     for gc in (0, 1):
-        assert_matrix_matches_summary(b.green(0, gc), g, "green0_%d" % gc, TOL_G, "c5 setup")
+        G = b.green(0, gc)
+        assert np.abs(G[::st, ::st] - truth["green0_%d_sub" % gc]).max() < 2e-10 * float(truth["green0_%d_maxabs" % gc])
+        assert float(truth["ref_dev_%d" % gc]) < 1e-8                  # the reference's own distance from the converged value
+        assert_matrix_matches_summary(G, g, "green0_%d" % gc, 1e-8, "c5 setup")
         ld = float(g["logdet0_%d" % gc])
         assert abs(b.logdet(0, gc) - ld) < 1e-10 * abs(ld)
     for sw in range(int(g["n_sweeps"])):
         b.sweep()
         assert np.array_equal(b.auxfield()[1:], g["aux_after_%d" % (sw + 1)]), sw
         for gc in (0, 1):
-            # wrapping over s = 10 slices at U = 8 amplifies round-off (the reference's own wrapped-vs-recomputed
-            # deviation here is ~1e-6, test_hubbard_full_size_properties): the Green's functions of two correct
-            # implementations agree to that level, not to 1e-10
-            assert_matrix_matches_summary(b.green(0, gc), g, "green_after_%d_%d" % (sw + 1, gc), 1e-5, ("c5", sw))
+            assert_matrix_matches_summary(b.green(0, gc), g, "green_after_%d_%d" % (sw + 1, gc), 1e-8, ("c5", sw))
     assert np.array_equal(b.rng_draw(8), g["rng_next"])
-
 
 # ---------------------------------------------------------------- the reference's own driver on top of the C ABI
 def test_reference_driver_with_gpu_shim(tmp_path):

@@ -233,7 +233,7 @@ def put(d, key, G, stride):
         d[key + "_" + k] = v
 
 
-def big_sdw_fixture(name, sweeps, kw, stride, keep=(1,)):
+def big_sdw_fixture(name, sweeps, kw, stride, keep=(1,), selfdev=True):
     import time
     p = SdwParams(**kw)
     t0 = time.time()
@@ -253,10 +253,17 @@ def big_sdw_fixture(name, sweeps, kw, stride, keep=(1,)):
             d["phi_after_%d" % (sw + 1)] = r.phi()
             G = r.green()
             put(d, "green_after_%d" % (sw + 1), G, stride)
-            # the reference's own wrapped-vs-recomputed deviation at this point (bounds what parity can mean)
-            k = int(sc["currentTimeslice"]) or p.m          # G(0) = G(beta); computeGreenFromScratch(0) is not defined
-            Gs = r.green_for_timeslice(k)
-            d["ref_selfdev_after_%d" % (sw + 1)] = np.abs(G - Gs).max() / np.abs(Gs).max()
+            # the reference's own wrapped-vs-recomputed deviation at this point (bounds what parity can mean).
+            # computeGreenFromScratch must NOT be called on the replica that keeps sweeping: it overwrites state
+            # the next sweep reads (a first version of this fixture diverged from a plain run in sweep 2), so a
+            # second replica is set to the same fields and recomputes G there.
+            if selfdev:
+                k = int(sc["currentTimeslice"]) or p.m          # G(0) = G(beta); computeGreenFromScratch(0) is not defined
+                r2 = rb.RefSdw(p)
+                r2.set_phi(d["phi_after_%d" % (sw + 1)])
+                Gs = r2.green_for_timeslice(k)
+                d["ref_selfdev_after_%d" % (sw + 1)] = np.abs(G - Gs).max() / np.abs(Gs).max()
+                del r2
         print(name, "sweep", sw + 1, "%.0f s" % (time.time() - t0), "acc", acc[-1], flush=True)
     d["lastAccRatio"], d["acceptedGlobalShifts"], d["phiDelta"] = np.array(acc), np.array(gsa), np.array(pdel)
     d["n_sweeps"] = sweeps
@@ -298,7 +305,7 @@ BIG = {
     "sdw_c3_L12_b10": lambda: big_sdw_fixture("sdw_c3_L12_b10", 6, dict(L=12, m=100, s=10), 3, keep=(1, 2)),
     # C4: O(3), L = 14, beta = 14 (D = 784)
     "sdw_c4_o3_L14_b14": lambda: big_sdw_fixture("sdw_c4_o3_L14_b14", 2, dict(opdim=3, L=14, m=140, s=10,
-                                                                                weakZflux=False), 4, keep=(1,)),
+                                                                                weakZflux=False), 4, keep=(1,), selfdev=False),
     # C5: DetHubbard L = 20, U = 8, beta = 20
     "hubbard_c5_L20_U8_b20": lambda: big_hubbard_fixture("hubbard_c5_L20_U8_b20", 2,
                                                          dict(L=20, m=200, s=10, U=8.0, mu=0.0, t=1.0), 4),

@@ -688,23 +688,23 @@ __global__ void __launch_bounds__(MAXT) update_round_kernel(UpdateModel md, Upda
 // (detsdwopdim.cpp:3064-3138) the window block of G + X Y evolves by its own rows and columns only, so the
 // decision of a site needs nothing but its MSF x MSF diagonal block of Gw.  The D-wide columns X_j = C_j Delta_j and
 // rows Y_j = M_j^-1 (R_j - 1_j) of the delayed update are NOT formed here: the kernel records, per accepted site,
-// the site, Delta_j, M_j^-1 and the window parts of X_j / Y_j (which are the couplings X_l[s_j, :], Y_l[:, s_j]
-// that a later C_j / R_j needs), and `update_build_xy_kernel` rebuilds X and Y for all rows / columns in parallel on
-// all SMs afterwards; the rank-K GEMM G += X Y follows as before.  The arithmetic is that of the reference's delayed
-// update, reordered.
+// the site, Delta_j, M_j^-1 and the couplings X_l[s_j, :], Y_l[:, s_j] (l < j; window entries of the earlier
+// updates) that a later C_j / R_j needs, and `update_build_xy_kernel` rebuilds X and Y for all rows / columns in
+// parallel on all SMs afterwards; the rank-K GEMM G += X Y follows as before.  The arithmetic is that of the
+// reference's delayed update, reordered.
 //
 //   warp 0        proposal, decision (all lanes redundantly: no divergence, no shuffles); on acceptance lane <-> future
-//                 site: window parts of X_j, Y_j and the diagonal blocks of all future sites
-//   warps 1..     apply Gw += x_w y_w to the future part of the window while warp 0 goes on with the next sites
+//                 site: window parts of X_j, Y_j and the diagonal blocks of all future sites; lane <-> earlier term:
+//                 the couplings of the new site
+//   warps 1..16   apply Gw += x_w y_w to the future part of the window while warp 0 goes on with the next sites
 //                 (named barriers kBarStart / kBarDone; warp 0 waits only when the NEXT acceptance arrives
 //                 before the previous block update has finished)
 //
-// Scratch record of a round, per replica (cplx elements, WPM = MSF * wmax):
-//   [j][0][MSF*MSF] Delta_j   [j][1][MSF*MSF] M_j^-1                      j < delaySteps
-//   then [j][0][q][WPM] x_w of term (j, q)    [j][1][q][WPM] y_w          window position a = i + r * w
-// Header (ints): nacc, site0, w, 0, sites[delaySteps].
+// Record of a round, per replica (cplx elements; J = delaySteps, K = MSF J):
+//   [j][0][MSF*MSF] Delta_j   [j][1][MSF*MSF] M_j^-1                                                       j < J
+//   then coefX[l][j][q] = Y_l[s_j + qN], coefY[l][j][q] = X_l[s_j + qN]       term l = MSF j' + p < MSF j, [K][J][MSF] each
+// Header (ints): nacc, site0, w, 0, sites[J].
 // =================================================================================================
-constexpr int kWinThreads = 256;
 constexpr int kBarStart = 1, kBarDone = 2;
 
 __device__ __forceinline__ void named_bar_sync(int id, int n) {
@@ -717,17 +717,50 @@ __device__ __forceinline__ void named_bar_arrive(int id, int n) {
 template <int MSF>
 __host__ __device__ inline size_t win_small_off(int j, int which) { return size_t(j * 2 + which) * MSF * MSF; }
 template <int MSF>
-__host__ __device__ inline size_t win_xy_off(int jmax, int WPM, int j, int which, int q) {
-    return size_t(jmax) * 2 * MSF * MSF + (size_t(j * 2 + which) * MSF + q) * WPM;
+__host__ __device__ inline size_t win_coef_off(int J, int which) {
+    return size_t(J) * 2 * MSF * MSF + size_t(which) * (size_t(MSF) * J) * J * MSF;
 }
 
+// determinant of the MSF x MSF decision matrix; the inverse is needed only when the proposal is accepted
+template <int MSF>
+__device__ __forceinline__ cplx small_det(const cplx* M) {
+    if (MSF == 2) return csub(cmul(M[0], M[3]), cmul(M[1], M[2]));
+    cplx inv[MSF * MSF];
+    return small_det_inv<MSF>(M, inv);
+}
+
+#ifdef DQMC_UPD_TIMING
+#define WTICK(i) { long long now__; asm volatile("mov.u64 %0, %%clock64;" : "=l"(now__) :: "memory"); wq[i] += now__ - wmark; wmark = now__; }
+#else
+#define WTICK(i)
+#endif
+
+constexpr int kBarSdiag = 3, kBarPosted = 4;
+
+// Proposal table of a window: everything about the proposal of window site `pos` that does not depend on earlier
+// decisions, for every random-number cursor the site can be reached with (cursor = OPDIM pos + e, e = number of
+// acceptance draws consumed so far, 0 <= e <= pos).  Entry (pos, e) sits at index pos (pos + 1) / 2 + e.
 template <int MSF, int OPDIM>
-__global__ void __launch_bounds__(kWinThreads) update_window_kernel(UpdateModel md, UpdateArgs a) {
+struct PropTable {
+    static constexpr int DIFF = 1, NEWP = 1 + OPDIM, CNEW = 1 + 2 * OPDIM, XNEW = 2 + 2 * OPDIM;
+    static constexpr int DELTA = (3 + 2 * OPDIM + 1) & ~1;             // 16-byte aligned complex block
+    static constexpr int STRIDE = DELTA + 2 * MSF * MSF;               // doubles per entry
+};
+
+template <int MSF, int OPDIM, int BW>
+__global__ void __launch_bounds__(32 * (2 + BW)) update_window_kernel(UpdateModel md, UpdateArgs a) {
+    constexpr int NT = 32 * (2 + BW);                      // warp 0: decisions, warp 1: accept helper, BW block-update warps
+    typedef PropTable<MSF, OPDIM> PT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
+#ifdef DQMC_UPD_TIMING
+    long long wq[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long wmark = clock64();
+#endif
     const int D = md.D, N = md.N, L = md.L;
     const int wmax = a.wmax, WPM = MSF * wmax, ldw = WPM + 1;
+    const int JM = md.delaySteps;
     const int b = blockIdx.x;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int* hdr = a.whdr + size_t(b) * a.strideHdr;
     const int site0 = a.round == 0 ? 0 : a.site_state[b];
     if (site0 >= N) {                                      // slice already finished in an earlier round
@@ -744,14 +777,16 @@ __global__ void __launch_bounds__(kWinThreads) update_window_kernel(UpdateModel 
     double* ck = tsum + OPDIM * wmax;                      // [wmax] cosh table
     double* xk = ck + wmax;                                // [wmax] sinh table
     double* rngs = xk + wmax;                              // [wmax * (OPDIM+1)] random numbers from the cursor on
-    cplx* Gw = reinterpret_cast<cplx*>(rngs + ((wmax * (OPDIM + 1) + 1) & ~1));   // [WPM][ldw] column major
-    cplx* Sdiag = Gw + size_t(ldw) * WPM;                  // [wmax][MSF*MSF] diagonal blocks, owned by warp 0
-    cplx* xw_s = Sdiag + wmax * MSF * MSF;                 // [MSF][WPM] window part of the newest X_j
-    cplx* yw_s = xw_s + MSF * WPM;                         // [MSF][WPM] window part of the newest Y_j
-    __shared__ int sPos, sQuit, sNload;
+    double* ptab = rngs + ((wmax * (OPDIM + 1) + 1) & ~1); // [wmax (wmax+1) / 2][PT::STRIDE] proposal table
+    cplx* Gw = reinterpret_cast<cplx*>(ptab + size_t(wmax) * (wmax + 1) / 2 * PT::STRIDE);   // [WPM][ldw] column major
+    cplx* Sdiag = Gw + size_t(ldw) * WPM;                  // [wmax][MSF*MSF] diagonal blocks
+    cplx* xh = Sdiag + wmax * MSF * MSF;                   // [MSF*JM][WPM] window parts of X_l, term l = MSF j + q
+    cplx* yh = xh + size_t(MSF) * JM * WPM;                // [MSF*JM][WPM] window parts of Y_l
+    __shared__ int sPos, sTerm, sQuit, sNload;
+    __shared__ int mbPos, mbEntry, mbQuit;                 // mailbox warp 0 -> warp 1
 
     const int k = a.k;
-    cplx* G = a.G + size_t(b) * a.strideG;
+    const cplx* __restrict__ G = a.G + size_t(b) * a.strideG;
     double* phi = a.phi + size_t(b) * a.stridePhi;
     double* coshT = a.coshT + size_t(b) * a.strideTab;
     double* sinhT = a.sinhT + size_t(b) * a.strideTab;
@@ -763,52 +798,136 @@ __global__ void __launch_bounds__(kWinThreads) update_window_kernel(UpdateModel 
     const int cursor0 = a.cursor[b];
     double* phik_g = phi + size_t(k) * OPDIM * N;
     {
+        // window block of G: column c of the block is MSF contiguous runs of w elements of a column of G
+        // (warp <-> column, lane <-> row of a run; all loads of a thread in flight together)
+        for (int c0 = warp; c0 < WP; c0 += 4 * (NT / 32)) {
+            cplx v[4][MSF];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int c = c0 + u * (NT / 32);
+                if (c < WP) {
+                    const int rc = c / w, ic = c - rc * w;
+                    const cplx* col = G + size_t(site0 + ic + rc * N) * D + site0;
+#pragma unroll
+                    for (int r = 0; r < MSF; ++r)
+                        if (lane < w) v[u][r] = col[lane + r * N];
+                }
+            }
+            if (w > 32) {                                  // (not used by the shipped window sizes; kept correct)
+                for (int u = 0; u < 4; ++u) {
+                    const int c = c0 + u * (NT / 32);
+                    if (c < WP) {
+                        const int rc = c / w, ic = c - rc * w;
+                        const cplx* col = G + size_t(site0 + ic + rc * N) * D + site0;
+                        for (int r = 0; r < MSF; ++r)
+                            for (int i = lane + 32; i < w; i += 32) Gw[i + r * w + size_t(c) * ldw] = col[i + r * N];
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int c = c0 + u * (NT / 32);
+                if (c < WP && lane < w) {
+#pragma unroll
+                    for (int r = 0; r < MSF; ++r) Gw[lane + r * w + size_t(c) * ldw] = v[u][r];
+                }
+            }
+        }
         const int kEarlier = k > 1 ? k - 1 : md.m;
         const int kLater = k < md.m ? k + 1 : 1;
         const double* pl = phi + size_t(kLater) * OPDIM * N;
         const double* pe = phi + size_t(kEarlier) * OPDIM * N;
-        for (int i = tid; i < OPDIM * N; i += blockDim.x) phik[i] = phik_g[i];
-        for (int i = tid; i < OPDIM * w; i += blockDim.x) {
+        for (int i = tid; i < OPDIM * N; i += NT) phik[i] = phik_g[i];
+        for (int i = tid; i < OPDIM * w; i += NT) {
             const int d = i / w, pos = i - d * w;
             tsum[d * wmax + pos] = pl[d * N + site0 + pos] + pe[d * N + site0 + pos];
         }
-        for (int i = tid; i < w; i += blockDim.x) {
+        for (int i = tid; i < w; i += NT) {
             ck[i] = coshT[size_t(k) * N + site0 + i];
             xk[i] = sinhT[size_t(k) * N + site0 + i];
         }
         const int want = w * (OPDIM + 1);
         const int have = max(0, min(want, a.rngWindow - cursor0));
-        for (int i = tid; i < have; i += blockDim.x) rngs[i] = rng[cursor0 + i];
-        // window block of G: column c of the block is MSF contiguous runs of w elements of a column of G
-        for (int idx = tid; idx < WP * WP; idx += blockDim.x) {
-            const int c = idx / WP, ar = idx - c * WP;
-            const int rc = c / w, ic = c - rc * w;
-            const int ra = ar / w, ia = ar - ra * w;
-            Gw[ar + size_t(c) * ldw] = G[size_t(site0 + ic + rc * N) * D + site0 + ia + ra * N];
-        }
-        if (tid == 0) { sQuit = 0; sNload = have; sPos = 0; }
+        for (int i = tid; i < have; i += NT) rngs[i] = rng[cursor0 + i];
+        if (tid == 0) { sQuit = 0; sNload = have; sPos = 0; sTerm = 0; mbQuit = 0; }
     }
     __syncthreads();
-    for (int i = tid; i < w * MSF * MSF; i += blockDim.x) {
+    for (int i = tid; i < w * MSF * MSF; i += NT) {
         const int pos = i / (MSF * MSF), e = i - pos * MSF * MSF, r = e / MSF, c = e - r * MSF;
         Sdiag[i] = Gw[pos + r * w + size_t(pos + c * w) * ldw];
     }
+    // ---- proposal table (proposeNewPhiBox, deltaSPhi without the neighbour term, get_delta_forsite): one entry per thread
+    {
+        const int nload = sNload;
+        const double invc2dtau = 1.0 / (md.c * md.c * dtau);
+        const double lamdtau = md.lambda * dtau;
+        const int nent = w * (w + 1) / 2;
+        for (int ent = tid; ent < nent; ent += NT) {
+            int pos = int((sqrt(8.0 * ent + 1.0) - 1.0) * 0.5);
+            while (pos * (pos + 1) / 2 > ent) --pos;
+            while ((pos + 1) * (pos + 2) / 2 <= ent) ++pos;
+            const int e = ent - pos * (pos + 1) / 2;
+            const int cur = OPDIM * pos + e;
+            double* T = ptab + size_t(ent) * PT::STRIDE;
+            if (cur + OPDIM > nload) continue;             // never reached: the chain aborts before it would read this entry
+            const int site = site0 + pos;
+            double oldp[3] = {0, 0, 0}, newp[3] = {0, 0, 0};
+            double oldSq = 0, newSq = 0, tdot = 0;
+#pragma unroll
+            for (int d = 0; d < OPDIM; ++d) {
+                oldp[d] = phik[d * N + site];
+                const double u = rngs[cur + d];
+                newp[d] = oldp[d] + (-phiDelta + (phiDelta - (-phiDelta)) * u);   // randRange(-delta, +delta)
+                const double diff = newp[d] - oldp[d];
+                oldSq += oldp[d] * oldp[d];
+                newSq += newp[d] * newp[d];
+                tdot += tsum[d * wmax + pos] * diff;
+                T[PT::DIFF + d] = diff;
+                T[PT::NEWP + d] = newp[d];
+            }
+            const double sqDiff = newSq - oldSq;
+            const double pow4Diff = newSq * newSq - oldSq * oldSq;
+            const double d1 = invc2dtau * (sqDiff - tdot);
+            const double d3 = dtau * (0.5 * rpar * sqDiff + 0.25 * md.u * pow4Diff);
+            T[0] = (d1 + d3) + 0.5 * dtau * (4.0 * sqDiff);     // deltaSPhi without -dtau * (neighbour sum . diff)
+            double cNew, sc;
+            cosh_sinhc(lamdtau * sqrt(newSq), cNew, sc);
+            const double xNew = lamdtau * sc;                   // sinh(lambda dtau |phi|) / |phi|
+            T[PT::CNEW] = cNew;
+            T[PT::XNEW] = xNew;
+            cplx evOld[MSF * MSF], emvNew[MSF * MSF];
+            ev_block<MSF, OPDIM>(evOld, +1.0, oldp, ck[pos], xk[pos]);
+            ev_block<MSF, OPDIM>(emvNew, -1.0, newp, cNew, xNew);
+            cplx* Dl = reinterpret_cast<cplx*>(T + PT::DELTA);
+#pragma unroll
+            for (int r = 0; r < MSF; ++r)
+#pragma unroll
+                for (int c = 0; c < MSF; ++c) {
+                    cplx sacc = make_double2(r == c ? -1.0 : 0.0, 0.0);
+#pragma unroll
+                    for (int t = 0; t < MSF; ++t) sacc = cfma(emvNew[r * MSF + t], evOld[t * MSF + c], sacc);
+                    Dl[r * MSF + c] = sacc;
+                }
+        }
+    }
     __syncthreads();
+    WTICK(0)
 
     if (warp == 0) {
         // ============================================================ the Metropolis chain
-        int cur = 0, j = 0, pos = 0;
+        int cur = 0, j = 0, pos = 0, posted = 0;
         unsigned accepted = 0;
-        bool outstanding = false, aborted = false;
-        const int delayNow = min(md.delaySteps, N - site0);
+        bool aborted = false, pendingSdiag = false;
+        const int delayNow = min(JM, N - site0);
         const int nload = sNload;
         int sx = site0 % L, sy = site0 / L;
         for (; pos < w; ++pos, sx = (sx + 1 == L ? 0 : sx + 1), sy += (sx == 0 ? 1 : 0)) {
             const int site = site0 + pos;
             if (cur + OPDIM + 1 > nload) { aborted = true; break; }
-            // ---------------------------------------------- proposal (proposeNewPhiBox, deltaSPhi, get_delta_forsite)
-            double oldp[3] = {0, 0, 0}, newp[3] = {0, 0, 0};
-            double oldSq = 0, newSq = 0, tdot = 0, sdot = 0;
+            const int ent = pos * (pos + 1) / 2 + (cur - OPDIM * pos);
+            const double* T = ptab + size_t(ent) * PT::STRIDE;
+            // bosonic part: the neighbour term of deltaSPhi uses the CURRENT fields of the slice
+            double sdot = 0;
             {
                 const int x = sx, y = sy;
                 const int nb0 = y * L + (x + 1 == L ? 0 : x + 1);
@@ -817,44 +936,22 @@ __global__ void __launch_bounds__(kWinThreads) update_window_kernel(UpdateModel 
                 const int nb3 = (y == 0 ? L - 1 : y - 1) * L + x;
 #pragma unroll
                 for (int d = 0; d < OPDIM; ++d) {
-                    oldp[d] = phik[d * N + site];
-                    const double u = rngs[cur + d];
-                    newp[d] = oldp[d] + (-phiDelta + (phiDelta - (-phiDelta)) * u);   // randRange(-delta, +delta)
-                    const double diff = newp[d] - oldp[d];
-                    oldSq += oldp[d] * oldp[d];
-                    newSq += newp[d] * newp[d];
                     const double* pk = phik + d * N;
                     const double sn = ((pk[nb0] + pk[nb1]) + pk[nb2]) + pk[nb3];
-                    tdot += tsum[d * wmax + pos] * diff;
-                    sdot += sn * diff;
+                    sdot += sn * T[PT::DIFF + d];
                 }
             }
-            const double sqDiff = newSq - oldSq;
-            const double pow4Diff = newSq * newSq - oldSq * oldSq;
-            const double d1 = (1.0 / (md.c * md.c * dtau)) * (sqDiff - tdot);
-            const double d2 = 0.5 * dtau * (4.0 * sqDiff - 2.0 * sdot);
-            const double d3 = dtau * (0.5 * rpar * sqDiff + 0.25 * md.u * pow4Diff);
-            const double probSPhi = exp(-(d1 + d2 + d3));
-            double cNew, sc;
-            cosh_sinhc(md.lambda * dtau * sqrt(newSq), cNew, sc);
-            const double xNew = md.lambda * dtau * sc;              // sinh(lambda dtau |phi|) / |phi|
+            const double udraw = rngs[cur + OPDIM];             // consumed only if the probability is <= 1
+            const double probSPhi = exp(-(T[0] - dtau * sdot));
             cplx Dl[MSF * MSF];
-            {
-                cplx evOld[MSF * MSF], emvNew[MSF * MSF];
-                ev_block<MSF, OPDIM>(evOld, +1.0, oldp, ck[pos], xk[pos]);
-                ev_block<MSF, OPDIM>(emvNew, -1.0, newp, cNew, xNew);
 #pragma unroll
-                for (int r = 0; r < MSF; ++r)
-#pragma unroll
-                    for (int c = 0; c < MSF; ++c) {
-                        cplx sacc = make_double2(r == c ? -1.0 : 0.0, 0.0);
-#pragma unroll
-                        for (int t = 0; t < MSF; ++t) sacc = cfma(emvNew[r * MSF + t], evOld[t * MSF + c], sacc);
-                        Dl[r * MSF + c] = sacc;
-                    }
+            for (int i = 0; i < MSF * MSF; ++i) Dl[i] = reinterpret_cast<const cplx*>(T + PT::DELTA)[i];
+            if (pendingSdiag) {                             // diagonal blocks after the previous acceptance
+                named_bar_sync(kBarSdiag, 64);
+                pendingSdiag = false;
             }
             // ---------------------------------------------- decision: M = 1 - S Delta + Delta
-            cplx M[MSF * MSF], Minv[MSF * MSF];
+            cplx M[MSF * MSF];
 #pragma unroll
             for (int r = 0; r < MSF; ++r)
 #pragma unroll
@@ -864,7 +961,7 @@ __global__ void __launch_bounds__(kWinThreads) update_window_kernel(UpdateModel 
                     for (int t = 0; t < MSF; ++t) sacc = csub(sacc, cmul(Sdiag[pos * MSF * MSF + r * MSF + t], Dl[t * MSF + c]));
                     M[r * MSF + c] = cadd(sacc, Dl[r * MSF + c]);
                 }
-            const cplx det = small_det_inv<MSF>(M, Minv);
+            const cplx det = small_det<MSF>(M);
             const double probFermion = (OPDIM == 3) ? det.x : (det.x * det.x + det.y * det.y);
             const double prob = probSPhi * probFermion;
             cur += OPDIM;
@@ -872,90 +969,37 @@ __global__ void __launch_bounds__(kWinThreads) update_window_kernel(UpdateModel 
             if (prob > 1.0) {
                 acc = true;
             } else {
-                acc = rngs[cur] < prob;
+                acc = udraw < prob;
                 cur += 1;
             }
+            WTICK(1)
             if (!acc) continue;
-            // ---------------------------------------------- accepted
+            // ---------------------------------------------- accepted: hand over to warp 1
             accepted += 1;
             if (lane == 0) {
 #pragma unroll
-                for (int d = 0; d < OPDIM; ++d) {
-                    phik[d * N + site] = newp[d];
-                    phik_g[d * N + site] = newp[d];
-                }
-                coshT[size_t(k) * N + site] = cNew;
-                sinhT[size_t(k) * N + site] = xNew;
-                hdr[4 + j] = site;
-#pragma unroll
-                for (int i = 0; i < MSF * MSF; ++i) {
-                    scratch[win_small_off<MSF>(j, 0) + i] = Dl[i];
-                    scratch[win_small_off<MSF>(j, 1) + i] = Minv[i];
-                }
+                for (int d = 0; d < OPDIM; ++d) phik[d * N + site] = T[PT::NEWP + d];
+                mbPos = pos;
+                mbEntry = ent;
             }
-            const bool last = (j + 1 == delayNow) || (pos + 1 == w);
-            if (!last) {
-                if (outstanding) {                          // column / row `pos` of Gw must be current
-                    named_bar_sync(kBarDone, blockDim.x);
-                    outstanding = false;
-                }
-                const int rf = w - 1 - pos;                 // future sites of the window
-                cplx* xg = scratch + win_xy_off<MSF>(md.delaySteps, WPM, j, 0, 0);
-                cplx* yg = scratch + win_xy_off<MSF>(md.delaySteps, WPM, j, 1, 0);
-                for (int off = lane; off < rf; off += 32) {
-                    const int f = pos + 1 + off;
-                    cplx xv[MSF][MSF], yv[MSF][MSF];        // xv[r][q] = X_(j,q)[f + r w],  yv[q][r] = Y_(j,q)[f + r w]
-#pragma unroll
-                    for (int r = 0; r < MSF; ++r) {
-                        const int ar = f + r * w;
-                        cplx cg[MSF], rg[MSF];
-#pragma unroll
-                        for (int p = 0; p < MSF; ++p) {
-                            cg[p] = Gw[ar + size_t(pos + p * w) * ldw];
-                            rg[p] = Gw[pos + p * w + size_t(ar) * ldw];
-                        }
-#pragma unroll
-                        for (int q = 0; q < MSF; ++q) {
-                            cplx xa = make_double2(0, 0), ya = make_double2(0, 0);
-#pragma unroll
-                            for (int p = 0; p < MSF; ++p) {
-                                xa = cfma(cg[p], Dl[p * MSF + q], xa);
-                                ya = cfma(Minv[q * MSF + p], rg[p], ya);
-                            }
-                            xv[r][q] = xa;
-                            yv[q][r] = ya;
-                            xw_s[q * WPM + ar] = xa;
-                            yw_s[q * WPM + ar] = ya;
-                            xg[size_t(q) * WPM + ar] = xa;
-                            yg[size_t(q) * WPM + ar] = ya;
-                        }
-                    }
-#pragma unroll
-                    for (int r = 0; r < MSF; ++r)
-#pragma unroll
-                        for (int c = 0; c < MSF; ++c) {
-                            cplx sacc = Sdiag[f * MSF * MSF + r * MSF + c];
-#pragma unroll
-                            for (int q = 0; q < MSF; ++q) sacc = cfma(xv[r][q], yv[q][c], sacc);
-                            Sdiag[f * MSF * MSF + r * MSF + c] = sacc;
-                        }
-                }
-                if (lane == 0) sPos = pos;
-                __threadfence_block();
-                __syncwarp();
-                named_bar_arrive(kBarStart, blockDim.x);
-                outstanding = true;
-            } else {
-                __syncwarp();
-            }
+            __syncwarp();
+            named_bar_arrive(kBarPosted, 64);
+            pendingSdiag = true;
+            posted += 1;
             j += 1;
+            WTICK(2)
             if (j == delayNow) { ++pos; break; }
         }
-        if (outstanding) named_bar_sync(kBarDone, blockDim.x);
-        if (lane == 0) sQuit = 1;
-        __threadfence_block();
+        if (pendingSdiag) named_bar_sync(kBarSdiag, 64);
+        if (lane == 0) mbQuit = 1;
         __syncwarp();
-        named_bar_arrive(kBarStart, blockDim.x);
+        named_bar_arrive(kBarPosted, 64);
+        WTICK(3)
+#ifdef DQMC_UPD_TIMING
+        if (a.debug && b == 0 && lane == 0)
+            printf("win dbg round %d sites %d acc %d: prologue %lld site %lld post %lld tail %lld\n",
+                   a.round, pos, j, wq[0], wq[1], wq[2], wq[3]);
+#endif
         if (lane == 0) {
             const int site = aborted ? N : site0 + pos;
             if (aborted) atomicExch(a.errflag, 1);
@@ -988,42 +1032,162 @@ __global__ void __launch_bounds__(kWinThreads) update_window_kernel(UpdateModel 
                 }
             }
         }
+    } else if (warp == 1) {
+        // ============================================================ accept helper: everything an acceptance entails
+        // except the decision chain itself -- M^-1, the window parts of X_j / Y_j, the diagonal blocks of the future
+        // sites (warp 0 waits for these only), couplings and record for update_build_xy, fields / tables in global
+        // memory, and the start of the block update
+        const int delayNow = min(JM, N - site0);
+        cplx* coefX = scratch + win_coef_off<MSF>(JM, 0);
+        cplx* coefY = scratch + win_coef_off<MSF>(JM, 1);
+        bool outstanding = false;
+        for (int j = 0;; ++j) {
+            named_bar_sync(kBarPosted, 64);
+            if (*(volatile int*)&mbQuit) break;
+            const int pos = *(volatile int*)&mbPos;
+            const int ent = *(volatile int*)&mbEntry;
+            const int site = site0 + pos;
+            const double* T = ptab + size_t(ent) * PT::STRIDE;
+            cplx Dl[MSF * MSF], M[MSF * MSF], Minv[MSF * MSF];
+#pragma unroll
+            for (int i = 0; i < MSF * MSF; ++i) Dl[i] = reinterpret_cast<const cplx*>(T + PT::DELTA)[i];
+#pragma unroll
+            for (int r = 0; r < MSF; ++r)
+#pragma unroll
+                for (int c = 0; c < MSF; ++c) {
+                    cplx sacc = make_double2(r == c ? 1.0 : 0.0, 0.0);
+#pragma unroll
+                    for (int t = 0; t < MSF; ++t) sacc = csub(sacc, cmul(Sdiag[pos * MSF * MSF + r * MSF + t], Dl[t * MSF + c]));
+                    M[r * MSF + c] = cadd(sacc, Dl[r * MSF + c]);
+                }
+            small_det_inv<MSF>(M, Minv);
+            const bool last = (j + 1 == delayNow) || (pos + 1 == w);
+            if (!last) {
+                if (outstanding) {                          // column / row `pos` of Gw must be current
+                    named_bar_sync(kBarDone, 32 * (1 + BW));
+                    outstanding = false;
+                }
+                const int rf = w - 1 - pos;                 // future sites of the window
+                cplx* xt = xh + size_t(MSF) * j * WPM;
+                cplx* yt = yh + size_t(MSF) * j * WPM;
+                for (int off = lane; off < rf; off += 32) {
+                    const int f = pos + 1 + off;
+                    cplx xv[MSF][MSF], yv[MSF][MSF];        // xv[r][q] = X_(j,q)[f + r w],  yv[q][r] = Y_(j,q)[f + r w]
+#pragma unroll
+                    for (int r = 0; r < MSF; ++r) {
+                        const int ar = f + r * w;
+                        cplx cg[MSF], rg[MSF];
+#pragma unroll
+                        for (int p = 0; p < MSF; ++p) {
+                            cg[p] = Gw[ar + size_t(pos + p * w) * ldw];
+                            rg[p] = Gw[pos + p * w + size_t(ar) * ldw];
+                        }
+#pragma unroll
+                        for (int q = 0; q < MSF; ++q) {
+                            cplx xa = make_double2(0, 0), ya = make_double2(0, 0);
+#pragma unroll
+                            for (int p = 0; p < MSF; ++p) {
+                                xa = cfma(cg[p], Dl[p * MSF + q], xa);
+                                ya = cfma(Minv[q * MSF + p], rg[p], ya);
+                            }
+                            xv[r][q] = xa;
+                            yv[q][r] = ya;
+                            xt[q * WPM + ar] = xa;
+                            yt[q * WPM + ar] = ya;
+                        }
+                    }
+#pragma unroll
+                    for (int r = 0; r < MSF; ++r)
+#pragma unroll
+                        for (int c = 0; c < MSF; ++c) {
+                            cplx sacc = Sdiag[f * MSF * MSF + r * MSF + c];
+#pragma unroll
+                            for (int q = 0; q < MSF; ++q) sacc = cfma(xv[r][q], yv[q][c], sacc);
+                            Sdiag[f * MSF * MSF + r * MSF + c] = sacc;
+                        }
+                }
+                if (lane == 0) { sPos = pos; sTerm = MSF * j; }
+                __syncwarp();
+                named_bar_arrive(kBarSdiag, 64);            // warp 0 may decide the next sites
+                named_bar_arrive(kBarStart, 32 * (1 + BW)); // the block update of the window starts
+                outstanding = true;
+            } else {
+                named_bar_arrive(kBarSdiag, 64);
+            }
+            // record for update_build_xy and the fields / tables of the accepted site
+            if (lane == 0) {
+#pragma unroll
+                for (int d = 0; d < OPDIM; ++d) phik_g[d * N + site] = T[PT::NEWP + d];
+                coshT[size_t(k) * N + site] = T[PT::CNEW];
+                sinhT[size_t(k) * N + site] = T[PT::XNEW];
+                hdr[4 + j] = site;
+#pragma unroll
+                for (int i = 0; i < MSF * MSF; ++i) {
+                    scratch[win_small_off<MSF>(j, 0) + i] = Dl[i];
+                    scratch[win_small_off<MSF>(j, 1) + i] = Minv[i];
+                }
+            }
+            // couplings of this site to the earlier terms (lane <-> term l): Y_l[s_j + qN] and X_l[s_j + qN]
+            for (int l = lane; l < MSF * j; l += 32) {
+#pragma unroll
+                for (int q = 0; q < MSF; ++q) {
+                    coefX[(size_t(l) * JM + j) * MSF + q] = yh[size_t(l) * WPM + pos + q * w];
+                    coefY[(size_t(l) * JM + j) * MSF + q] = xh[size_t(l) * WPM + pos + q * w];
+                }
+            }
+        }
+        if (outstanding) named_bar_sync(kBarDone, 32 * (1 + BW));
+        if (lane == 0) sQuit = 1;
+        __syncwarp();
+        named_bar_arrive(kBarStart, 32 * (1 + BW));
     } else {
         // ============================================================ block updates of the window
-        const int bw = warp - 1, nbw = nwarps - 1;
+        // thread <-> (row slot ai, column group cg): 64 row slots, four columns in flight
+        const int tb = tid - 64;
+        const int ai = tb & 63, cg = tb >> 6;
+        constexpr int NCG = BW * 32 / 64;
         for (;;) {
-            named_bar_sync(kBarStart, blockDim.x);
+            named_bar_sync(kBarStart, 32 * (1 + BW));
             if (*(volatile int*)&sQuit) break;
             const int pos = *(volatile int*)&sPos;
+            const int tb0 = *(volatile int*)&sTerm;
             const int rf = w - 1 - pos, nf = MSF * rf;
-            for (int ci = bw; ci < nf; ci += nbw) {
-                const int rc = ci / rf;
-                const int c = pos + 1 + (ci - rc * rf) + rc * w;
-                cplx yv[MSF];
+            for (int a0 = ai; a0 < nf; a0 += 64) {
+                const int ra = a0 / rf;
+                const int ar = pos + 1 + (a0 - ra * rf) + ra * w;
+                cplx xv[MSF];
 #pragma unroll
-                for (int q = 0; q < MSF; ++q) yv[q] = yw_s[q * WPM + c];
-                cplx* col = Gw + size_t(c) * ldw;
+                for (int q = 0; q < MSF; ++q) xv[q] = xh[size_t(tb0 + q) * WPM + ar];
+                for (int c0 = cg; c0 < nf; c0 += 4 * NCG) {
+                    cplx gv[4];
+                    int cc[4];
 #pragma unroll
-                for (int r = 0; r < MSF; ++r)
-                    for (int i = lane; i < rf; i += 32) {
-                        const int ar = pos + 1 + i + r * w;
-                        cplx gv = col[ar];
-#pragma unroll
-                        for (int q = 0; q < MSF; ++q) gv = cfma(xw_s[q * WPM + ar], yv[q], gv);
-                        col[ar] = gv;
+                    for (int u = 0; u < 4; ++u) {
+                        const int ci = c0 + u * NCG;
+                        const int cl = ci < nf ? ci : c0;             // clamp: duplicates are not stored
+                        const int rc = cl / rf;
+                        cc[u] = pos + 1 + (cl - rc * rf) + rc * w;
+                        gv[u] = Gw[ar + size_t(cc[u]) * ldw];
                     }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+#pragma unroll
+                        for (int q = 0; q < MSF; ++q) gv[u] = cfma(xv[q], yh[size_t(tb0 + q) * WPM + cc[u]], gv[u]);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (c0 + u * NCG < nf) Gw[ar + size_t(cc[u]) * ldw] = gv[u];
+                }
             }
-            __threadfence_block();
-            named_bar_arrive(kBarDone, blockDim.x);
+            named_bar_arrive(kBarDone, 32 * (1 + BW));
         }
     }
 }
 
 // Rebuild the D-wide X (D x K) and Y (K x D) of a window round from its record, one thread per row of X
 // (blockIdx.y == 0) or column of Y (blockIdx.y == 1):
-//   C_j[t, q] = G[t, s_j + qN] + sum_{l < j, p} X_(l,p)[t] * Y_(l,p)[s_j + qN]        X_(j,r)[t] = sum_q C_j[t, q] Delta_j[q, r]
-//   R_j[q, t] = G[s_j + qN, t] - delta + sum_{l < j, p} X_(l,p)[s_j + qN] * Y_(l,p)[t]  Y_(j,q')[t] = sum_q Minv_j[q', q] R_j[q, t]
-// (detsdwopdim.cpp:3064-3070, 3123-3138).  The couplings Y_(l,p)[s_j + qN], X_(l,p)[s_j + qN] are window entries
+//   C_j[t, q] = G[t, s_j + qN] + sum_{l < MSF j} X_l[t] * Y_l[s_j + qN]            X_(j,r)[t] = sum_q C_j[t, q] Delta_j[q, r]
+//   R_j[q, t] = G[s_j + qN, t] - delta + sum_{l < MSF j} X_l[s_j + qN] * Y_l[t]     Y_(j,q')[t] = sum_q Minv_j[q', q] R_j[q, t]
+// (detsdwopdim.cpp:3064-3070, 3123-3138).  The couplings Y_l[s_j + qN], X_l[s_j + qN] are window entries
 // recorded by update_window_kernel.
 constexpr int kBxyThreads = 64;
 
@@ -1034,54 +1198,76 @@ __global__ void __launch_bounds__(kBxyThreads) update_build_xy_kernel(UpdateMode
     const int* hdr = a.whdr + size_t(b) * a.strideHdr;
     const int J = hdr[0];
     if (J <= 0) return;
-    const int D = md.D, N = md.N;
-    const int site0 = hdr[1], w = hdr[2];
-    const int WPM = MSF * a.wmax;
+    const int D = md.D, N = md.N, JM = md.delaySteps;
     const int K = MSF * J;
     const int side = blockIdx.y;                           // 0: rows of X, 1: columns of Y
     const int tid = threadIdx.x;
-    const int t = blockIdx.x * kBxyThreads + tid;
-    cplx* coef = reinterpret_cast<cplx*>(smem_raw);        // [K][J][MSF]: coupling of term l to (j, q), l < j * MSF
-    cplx* small = coef + size_t(K) * J * MSF;              // [J][MSF*MSF]: Delta_j (side 0) or Minv_j (side 1)
-    int* sites = reinterpret_cast<int*>(small + J * MSF * MSF);   // [J]
-    cplx* rowbuf = reinterpret_cast<cplx*>(sites + ((J + 3) & ~3));   // [K][kBxyThreads]
+    const int t = min(blockIdx.x * kBxyThreads + tid, D - 1);          // threads past the end redo row D-1 and do not store
+    const bool active = blockIdx.x * kBxyThreads + tid < D;
+    cplx* coef = reinterpret_cast<cplx*>(smem_raw);        // [K][JM][MSF]: coupling of term l to (j, q), l < MSF j
+    cplx* small = coef + size_t(K) * JM * MSF;             // [J][MSF*MSF]: Delta_j (side 0) or Minv_j (side 1)
+    cplx* rowbuf = small + J * MSF * MSF;                  // [K][kBxyThreads]: G entries first, X_l[t] / Y_l[t] once term l is done
+    __shared__ int sites[64];
+#ifdef DQMC_UPD_TIMING
+    long long wq[4] = {0, 0, 0, 0};
+    long long wmark = clock64();
+#endif
     const cplx* scratch = a.wscratch + size_t(b) * a.strideScratch;
+    const cplx* __restrict__ G = a.G + size_t(b) * a.strideG;
     for (int i = tid; i < J; i += kBxyThreads) sites[i] = hdr[4 + i];
-    for (int i = tid; i < J * MSF * MSF; i += kBxyThreads) {
-        const int j = i / (MSF * MSF), e = i - j * MSF * MSF;
-        small[i] = scratch[win_small_off<MSF>(j, side) + e];
-    }
-    __syncthreads();
-    // side 0 needs Y_(l,p)[s_j + qN] (which = 1), side 1 needs X_(l,p)[s_j + qN] (which = 0)
-    for (int i = tid; i < K * J * MSF; i += kBxyThreads) {
-        const int l = i / (J * MSF), rem = i - l * (J * MSF), j = rem / MSF, q = rem - j * MSF;
-        cplx v = make_double2(0, 0);
-        if (l < j * MSF) {
-            const int pj = sites[j] - site0 + q * w;
-            v = scratch[win_xy_off<MSF>(md.delaySteps, WPM, l / MSF, side == 0 ? 1 : 0, l % MSF) + pj];
+    {
+        const cplx* __restrict__ src = scratch + win_coef_off<MSF>(JM, side);
+        const int n = K * JM * MSF;
+        for (int base = 0; base < n; base += 8 * kBxyThreads) {
+            cplx v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = base + u * kBxyThreads + tid;
+                if (i < n) v[u] = src[i];
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = base + u * kBxyThreads + tid;
+                if (i < n) coef[i] = v[u];
+            }
         }
-        coef[i] = v;
+        for (int i = tid; i < J * MSF * MSF; i += kBxyThreads) {
+            const int j = i / (MSF * MSF), e = i - j * MSF * MSF;
+            small[i] = scratch[win_small_off<MSF>(j, side) + e];
+        }
     }
     __syncthreads();
-    if (t >= D) return;
-    const cplx* G = a.G + size_t(b) * a.strideG;
+    WTICK(0)
+    // the entries of G this row / column needs, eight loads in flight
+    for (int base = 0; base < K; base += 8) {
+        cplx v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int l = base + u;
+            if (l < K) {
+                const int sj = sites[l / MSF] + (l % MSF) * N;
+                v[u] = side == 0 ? G[size_t(sj) * D + t] : G[size_t(t) * D + sj];
+                if (side == 1 && t == sj) v[u].x -= 1.0;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (base + u < K) rowbuf[(base + u) * kBxyThreads + tid] = v[u];
+    }
     cplx* out = (side == 0 ? a.X : a.Y) + size_t(b) * a.strideXY;
+    WTICK(1)
     for (int j = 0; j < J; ++j) {
-        const int sj = sites[j];
         cplx acc0[MSF], acc1[MSF];
 #pragma unroll
         for (int q = 0; q < MSF; ++q) {
-            const int u = sj + q * N;
-            cplx v = side == 0 ? G[size_t(u) * D + t] : G[size_t(t) * D + u];
-            if (side == 1 && t == u) v.x -= 1.0;
-            acc0[q] = v;
+            acc0[q] = rowbuf[(j * MSF + q) * kBxyThreads + tid];
             acc1[q] = make_double2(0, 0);
         }
         const int nl = j * MSF;                            // even for MSF = 2, 4: two independent accumulation chains
         for (int l = 0; l < nl; l += 2) {
             const cplx v0 = rowbuf[l * kBxyThreads + tid], v1 = rowbuf[(l + 1) * kBxyThreads + tid];
-            const cplx* c0 = coef + (size_t(l) * J + j) * MSF;
-            const cplx* c1 = coef + (size_t(l + 1) * J + j) * MSF;
+            const cplx* c0 = coef + (size_t(l) * JM + j) * MSF;
+            const cplx* c1 = coef + (size_t(l + 1) * JM + j) * MSF;
 #pragma unroll
             for (int q = 0; q < MSF; ++q) {
                 acc0[q] = cfma(v0, c0[q], acc0[q]);
@@ -1090,6 +1276,7 @@ __global__ void __launch_bounds__(kBxyThreads) update_build_xy_kernel(UpdateMode
         }
 #pragma unroll
         for (int q = 0; q < MSF; ++q) acc0[q] = cadd(acc0[q], acc1[q]);
+        cplx res[MSF];
 #pragma unroll
         for (int r = 0; r < MSF; ++r) {
             cplx v = make_double2(0, 0);
@@ -1097,16 +1284,29 @@ __global__ void __launch_bounds__(kBxyThreads) update_build_xy_kernel(UpdateMode
             for (int q = 0; q < MSF; ++q)
                 v = side == 0 ? cfma(acc0[q], small[j * MSF * MSF + q * MSF + r], v)
                               : cfma(small[j * MSF * MSF + r * MSF + q], acc0[q], v);
-            rowbuf[(j * MSF + r) * kBxyThreads + tid] = v;
-            out[size_t(j * MSF + r) * D + t] = v;
+            res[r] = v;
+        }
+#pragma unroll
+        for (int r = 0; r < MSF; ++r) {
+            rowbuf[(j * MSF + r) * kBxyThreads + tid] = res[r];
+            if (active) out[size_t(j * MSF + r) * D + t] = res[r];
         }
     }
+    WTICK(2)
+#ifdef DQMC_UPD_TIMING
+    if (a.debug && b == 0 && blockIdx.x == 0 && tid == 0)
+        printf("bxy dbg round %d side %d J %d: coef %lld gload %lld recur %lld\n", a.round, side, J, wq[0], wq[1], wq[2]);
+#endif
 }
 
 }  // namespace
 
 int update_rounds_per_slice(const UpdateModel& m, int inline_flush) {
-    return inline_flush ? 1 : (m.N + m.delaySteps - 1) / m.delaySteps;
+    if (inline_flush) return 1;
+    // a round ends after delaySteps acceptances or (window rounds) at the end of its window
+    const int w = update_window_sites(m);
+    const int per = (w > 0 && w < m.delaySteps) ? w : m.delaySteps;
+    return (m.N + per - 1) / per;
 }
 
 cudaError_t update_round_launch(const UpdateModel& m, const UpdateArgs& a, cudaStream_t st) {
@@ -1146,44 +1346,51 @@ cudaError_t update_round_launch(const UpdateModel& m, const UpdateArgs& a, cudaS
 // ---- window rounds ------------------------------------------------------------------------------
 // Sites per window: two delay blocks' worth (a round ends after delaySteps acceptances, at ~50 % acceptance that
 // takes 2 * delaySteps sites), bounded by the shared memory of the (MSF w)^2 window block.
+static size_t window_smem_bytes(const UpdateModel& m, int wmax) {
+    const int wpm = m.msf * wmax;
+    const int dl = (3 + 2 * m.opdim + 1) & ~1, pstride = dl + 2 * m.msf * m.msf;
+    return size_t(m.opdim * m.N + m.opdim * wmax + 2 * wmax + ((wmax * (m.opdim + 1) + 1) & ~1) +
+                  size_t(wmax) * (wmax + 1) / 2 * pstride) * sizeof(double) +
+           (size_t(wpm + 1) * wpm + size_t(wmax) * m.msf * m.msf + size_t(2) * m.msf * m.delaySteps * wpm) * sizeof(cplx);
+}
 int update_window_sites(const UpdateModel& m) {
     if (m.delaySteps < 8) return 0;                        // tiny delay blocks are flushed inside the legacy kernel
     if (m.msf * m.delaySteps > 64) return 0;               // update_build_xy keeps K x J x MSF couplings in shared memory
     int w = 2 * m.delaySteps;
-    const int cap = 64 / m.msf;                            // (MSF w)^2 * 16 B <= 64 KiB
-    if (w > cap) w = cap;
+    if (w > 32) w = 32;                                    // one lane per future site in the accept helper
     if (w > m.N) w = m.N;
     w &= ~1;
+    while (w >= 2 && window_smem_bytes(m, w) > size_t(208) * 1024) w -= 2;
     return w < 2 ? 0 : w;
 }
 size_t update_window_scratch_elems(const UpdateModel& m) {
-    const size_t wpm = size_t(m.msf) * update_window_sites(m);
-    return size_t(m.delaySteps) * 2 * m.msf * m.msf + size_t(m.delaySteps) * 2 * m.msf * wpm;
+    const size_t J = m.delaySteps, K = size_t(m.msf) * J;
+    return J * 2 * m.msf * m.msf + 2 * K * J * m.msf;
 }
 int update_window_hdr_ints(const UpdateModel& m) { return (4 + m.delaySteps + 3) & ~3; }
 
 cudaError_t update_window_launch(const UpdateModel& m, const UpdateArgs& a, cudaStream_t st) {
-    const int wmax = a.wmax, wpm = m.msf * wmax;
-    const size_t smem = size_t(m.opdim * m.N + m.opdim * wmax + 2 * wmax + ((wmax * (m.opdim + 1) + 1) & ~1)) * sizeof(double) +
-                        (size_t(wpm + 1) * wpm + size_t(wmax) * m.msf * m.msf + size_t(2) * m.msf * wpm) * sizeof(cplx);
-#define LAUNCHW(MSF, OPD)                                                                                   \
+    const size_t smem = window_smem_bytes(m, a.wmax);
+#define LAUNCHW(MSF, OPD, BW)                                                                               \
     {                                                                                                       \
-        cudaError_t e = cudaFuncSetAttribute(update_window_kernel<MSF, OPD>,                                \
+        cudaError_t e = cudaFuncSetAttribute(update_window_kernel<MSF, OPD, BW>,                            \
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
         if (e != cudaSuccess) return e;                                                                     \
-        update_window_kernel<MSF, OPD><<<a.batch, kWinThreads, smem, st>>>(m, a);                           \
+        update_window_kernel<MSF, OPD, BW><<<a.batch, 32 * (2 + BW), smem, st>>>(m, a);                     \
     }
-    if (m.opdim == 1) LAUNCHW(2, 1)
-    else if (m.opdim == 2) LAUNCHW(2, 2)
-    else LAUNCHW(4, 3)
+    // 16 block-update warps for the 2 x 2 site blocks (96 registers per thread suffice); the 4 x 4 blocks of O(3)
+    // need the registers more than the warps
+    if (m.opdim == 1) LAUNCHW(2, 1, 16)
+    else if (m.opdim == 2) LAUNCHW(2, 2, 16)
+    else LAUNCHW(4, 3, 4)
 #undef LAUNCHW
     return cudaGetLastError();
 }
 
 cudaError_t update_build_xy_launch(const UpdateModel& m, const UpdateArgs& a, cudaStream_t st) {
     const int J = m.delaySteps, K = m.msf * J;
-    const size_t smem = (size_t(K) * J * m.msf + size_t(J) * m.msf * m.msf + size_t(K) * kBxyThreads) * sizeof(cplx) +
-                        size_t((J + 3) & ~3) * sizeof(int);
+    if (J > 64) return cudaErrorInvalidValue;
+    const size_t smem = (size_t(K) * J * m.msf + size_t(J) * m.msf * m.msf + size_t(K) * kBxyThreads) * sizeof(cplx);
     dim3 grid((m.D + kBxyThreads - 1) / kBxyThreads, 2, a.batch);
 #define LAUNCHB(MSF)                                                                                        \
     {                                                                                                       \

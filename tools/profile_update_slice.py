@@ -16,13 +16,14 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 from bench import WORKLOAD, ladder_values  # noqa: E402
 from detqmc_b200 import DetSDWBatch  # noqa: E402
 
-R = 64
+R = int(os.environ.get("DQMC_PROF_R", "64"))
 b = DetSDWBatch(dict(WORKLOAD), n_replicas=R, rng_indices=[i + 1 for i in range(R)], r_values=ladder_values(R))
 b.sweepThermalization()
 b.synchronize()
 rt = ctypes.CDLL("libcudart.so")
 rt.cudaProfilerStart()
-acc = b.update_in_slice(1, True)
+for k_ in range(1, 1 + int(os.environ.get("DQMC_PROF_SLICES", "1"))):
+    acc = b.update_in_slice(k_, True)
 b.synchronize()
 rt.cudaProfilerStop()
 print("accepted", acc[:8])

@@ -32,24 +32,38 @@ def build():
 
 
 def summarise(path):
-    pat = re.compile(r"upd dbg round (\d+) tid +(\d+) sites (\d+): ph1 (\d+) waitA (\d+) ph2\(dec\) (\d+) waitB (\d+) Sred (\d+) top (\d+)")
-    tot = {}
+    win = re.compile(r"win dbg round (\d+) sites (\d+) acc (\d+): prologue (\d+) site (\d+) post (\d+) tail (\d+)")
+    bxy = re.compile(r"bxy dbg round (\d+) side (\d+) J (\d+): coef (\d+) gload (\d+) recur (\d+)")
+    w = [0] * 7
+    bx = {0: [0] * 5, 1: [0] * 5}
     for line in open(path):
-        m = pat.search(line)
-        if not m:
-            continue
-        tid, sites = int(m.group(2)), int(m.group(3))
-        v = [int(x) for x in m.groups()[3:]]
-        t = tot.setdefault(tid, [0] * 7)
-        t[0] += sites
-        for i, x in enumerate(v):
-            t[1 + i] += x
-    print("clocks per site (replica 0):  tid  sites   ph1  waitA   ph2  waitB  (Sred)   top   sum")
-    for tid, t in sorted(tot.items()):
-        n = max(t[0], 1)
-        per = [x / n for x in t[1:]]
-        print("  tid %3d  %6d  %6.0f %6.0f %6.0f %6.0f %6.0f %6.0f  %6.0f" %
-              (tid, t[0], per[0], per[1], per[2], per[3], per[4], per[5], per[0] + per[1] + per[2] + per[3] + per[5]))
+        m = win.search(line)
+        if m:
+            v = [int(x) for x in m.groups()]
+            if v[1] == 0:
+                continue
+            w[0] += 1
+            for i in range(1, 7):
+                w[i] += v[i]
+        m = bxy.search(line)
+        if m:
+            v = [int(x) for x in m.groups()]
+            t = bx[v[1]]
+            t[0] += 1
+            t[1] += v[2]
+            for i in range(3):
+                t[2 + i] += v[3 + i]
+    if w[0]:
+        sites, acc = w[1], w[2]
+        print("window kernel (warp 0 of replica 0): %d rounds, %d sites, %d accepted" % (w[0], sites, acc))
+        print("  per round: prologue %.0f tail %.0f clocks" % (w[3] / w[0], w[6] / w[0]))
+        print("  per site: proposal look-up + decision (incl. waiting for the diagonal blocks) %.0f clocks" % (w[4] / sites))
+        print("  per accepted site: hand-over %.0f clocks" % (w[5] / max(acc, 1)))
+        print("  total per site %.0f clocks" % (sum(w[3:7]) / sites))
+    for side, t in bx.items():
+        if t[0]:
+            print("build_xy side %d: %d launches, mean J %.1f: coef %.0f gload %.0f recurrence %.0f clocks per launch"
+                  % (side, t[0], t[1] / t[0], t[2] / t[0], t[3] / t[0], t[4] / t[0]))
 
 
 def run():

@@ -686,24 +686,29 @@ __global__ void __launch_bounds__(MAXT) update_round_kernel(UpdateModel md, Upda
 // Green's function that couples the window's sites to each other in shared memory ("Gw") and applies every accepted
 // update to that block immediately (rank MSF, O((MSF w)^2)): by the algebra of updateInSlice_delayed
 // (detsdwopdim.cpp:3064-3138) the window block of G + X Y evolves by its own rows and columns only, so the
-// decision of a site needs nothing but its MSF x MSF diagonal block of Gw.  The D-wide columns X_j = C_j Delta_j and
-// rows Y_j = M_j^-1 (R_j - 1_j) of the delayed update are NOT formed here: the kernel records, per accepted site,
-// the site, Delta_j, M_j^-1 and the couplings X_l[s_j, :], Y_l[:, s_j] (l < j; window entries of the earlier
-// updates) that a later C_j / R_j needs, and `update_build_xy_kernel` rebuilds X and Y for all rows / columns in
-// parallel on all SMs afterwards; the rank-K GEMM G += X Y follows as before.  The arithmetic is that of the
-// reference's delayed update, reordered.
+// decision of a site needs nothing but its MSF x MSF diagonal block of Gw.
 //
-//   warp 0        proposal, decision (all lanes redundantly: no divergence, no shuffles); on acceptance lane <-> future
-//                 site: window parts of X_j, Y_j and the diagonal blocks of all future sites; lane <-> earlier term:
-//                 the couplings of the new site
-//   warps 1..16   apply Gw += x_w y_w to the future part of the window while warp 0 goes on with the next sites
+// The D-wide columns X_j = C_j Delta_j and rows Y_j = M_j^-1 (R_j - 1_j) of the delayed update are NOT formed here.
+// Every C_j is a combination of columns of the round's INITIAL Green's function G0 at the accepted sites, and every
+// R_j - 1_j a combination of its rows:
+//     X_l = sum_i G0[:, S_i] Tx[i, l],      Y_l = sum_i Ty[l, i] (G0 - 1)[S_i, :]      (S_i = s_j + q N for term i = MSF j + q)
+// with block-triangular K x K coefficient matrices that follow the reference's recurrences
+//     Tx[:, (j, r)]  = sum_q ( e_(j,q) + sum_{l < MSF j} Tx[:, l] Y_l[S_(j,q)] ) Delta_j[q, r]
+//     Ty[(j, q'), :] = sum_q Minv_j[q', q] ( e_(j,q)^T + sum_{l < MSF j} X_l[S_(j,q)] Ty[l, :] )
+// whose couplings Y_l[S_(j,q)], X_l[S_(j,q)] are window entries.  Two helper warps run these recurrences while the
+// chain goes on; the round hands A = Tx Ty to `update_gather_kernel`, which copies the K columns of G0 into X and
+// forms Y = A (G0 - 1)[S, :] on all SMs; the rank-K GEMM G += X Y follows as before.  The arithmetic is that of the
+// reference's delayed update, re-associated.
+//
+//   warp 0        proposal look-up, decision (all lanes redundantly: no divergence, no shuffles); on acceptance
+//                 lane <-> future site: window parts of X_j, Y_j and the diagonal blocks of all future sites
+//   warp 1 / 2    Tx / Ty recurrences of the accepted update, fields and tables of the accepted site (polling a counter;
+//                 never waited for by warp 0)
+//   warps 3..     apply Gw += x_w y_w to the future part of the window while warp 0 goes on with the next sites
 //                 (named barriers kBarStart / kBarDone; warp 0 waits only when the NEXT acceptance arrives
 //                 before the previous block update has finished)
 //
-// Record of a round, per replica (cplx elements; J = delaySteps, K = MSF J):
-//   [j][0][MSF*MSF] Delta_j   [j][1][MSF*MSF] M_j^-1                                                       j < J
-//   then coefX[l][j][q] = Y_l[s_j + qN], coefY[l][j][q] = X_l[s_j + qN]       term l = MSF j' + p < MSF j, [K][J][MSF] each
-// Header (ints): nacc, site0, w, 0, sites[J].
+// Output of a round, per replica: header (ints) nacc, site0, w, 0, sites[J]; scratch (cplx) A[i * KM + i'], KM = MSF delaySteps.
 // =================================================================================================
 constexpr int kBarStart = 1, kBarDone = 2;
 
@@ -712,13 +717,6 @@ __device__ __forceinline__ void named_bar_sync(int id, int n) {
 }
 __device__ __forceinline__ void named_bar_arrive(int id, int n) {
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory");
-}
-
-template <int MSF>
-__host__ __device__ inline size_t win_small_off(int j, int which) { return size_t(j * 2 + which) * MSF * MSF; }
-template <int MSF>
-__host__ __device__ inline size_t win_coef_off(int J, int which) {
-    return size_t(J) * 2 * MSF * MSF + size_t(which) * (size_t(MSF) * J) * J * MSF;
 }
 
 // determinant of the MSF x MSF decision matrix; the inverse is needed only when the proposal is accepted
@@ -735,8 +733,6 @@ __device__ __forceinline__ cplx small_det(const cplx* M) {
 #define WTICK(i)
 #endif
 
-constexpr int kBarSdiag = 3, kBarPosted = 4;
-
 // Proposal table of a window: everything about the proposal of window site `pos` that does not depend on earlier
 // decisions, for every random-number cursor the site can be reached with (cursor = OPDIM pos + e, e = number of
 // acceptance draws consumed so far, 0 <= e <= pos).  Entry (pos, e) sits at index pos (pos + 1) / 2 + e.
@@ -747,9 +743,45 @@ struct PropTable {
     static constexpr int STRIDE = DELTA + 2 * MSF * MSF;               // doubles per entry
 };
 
+// Shared-memory carve-up of the window kernel (offsets in doubles; every region starts 16-byte aligned)
+struct WinLayout {
+    int phik, tsum, ck, xk, rngs, ptab, Gw, Sdiag, xh, yh, Tx, Ty, smallD, smallM, total;
+};
+__host__ __device__ inline int win_even(int x) { return (x + 1) & ~1; }
+// packed block-triangular K x K coefficient matrix: term l = MSF j + r holds its first MSF (j + 1) entries
+__host__ __device__ inline int win_tri_off(int msf, int l) {
+    const int j = l / msf, r = l - j * msf;
+    return msf * msf * (j * (j + 1) / 2) + r * msf * (j + 1);
+}
+__host__ __device__ inline WinLayout win_layout(int msf, int opdim, int N, int wmax, int JM) {
+    WinLayout o;
+    const int wpm = msf * wmax, ldw = wpm + 1, KM = msf * JM;
+    const int pstride = ((3 + 2 * opdim + 1) & ~1) + 2 * msf * msf;
+    int p = 0;
+    o.phik = p;   p += win_even(opdim * N);
+    o.tsum = p;   p += win_even(opdim * wmax);
+    o.ck = p;     p += win_even(wmax);
+    o.xk = p;     p += win_even(wmax);
+    o.rngs = p;   p += win_even(wmax * (opdim + 1));
+    o.ptab = p;   p += wmax * (wmax + 1) / 2 * pstride;
+    o.Gw = p;     p += 2 * ldw * wpm;
+    o.Sdiag = p;  p += 2 * wmax * msf * msf;
+    o.xh = p;     p += 2 * KM * wpm;
+    o.yh = p;     p += 2 * KM * wpm;
+    o.Tx = p;     p += 2 * msf * msf * (JM * (JM + 1) / 2);
+    o.Ty = p;     p += 2 * msf * msf * (JM * (JM + 1) / 2);
+    o.smallD = p; p += 2 * JM * msf * msf;
+    o.smallM = p; p += 2 * JM * msf * msf;
+    o.total = p;
+    return o;
+}
+
+constexpr int kWinMaxJ = 64;
+
 template <int MSF, int OPDIM, int BW>
-__global__ void __launch_bounds__(32 * (2 + BW)) update_window_kernel(UpdateModel md, UpdateArgs a) {
-    constexpr int NT = 32 * (2 + BW);                      // warp 0: decisions, warp 1: accept helper, BW block-update warps
+__global__ void __launch_bounds__(32 * (3 + BW)) update_window_kernel(UpdateModel md, UpdateArgs a) {
+    constexpr int NT = 32 * (3 + BW);                      // warp 0: chain, warps 1 / 2: Tx / Ty, BW block-update warps
+    constexpr int NBLK = 32 * (1 + BW);                    // participants of kBarStart / kBarDone
     typedef PropTable<MSF, OPDIM> PT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
 #ifdef DQMC_UPD_TIMING
@@ -758,7 +790,7 @@ __global__ void __launch_bounds__(32 * (2 + BW)) update_window_kernel(UpdateMode
 #endif
     const int D = md.D, N = md.N, L = md.L;
     const int wmax = a.wmax, WPM = MSF * wmax, ldw = WPM + 1;
-    const int JM = md.delaySteps;
+    const int JM = md.delaySteps, KM = MSF * JM;
     const int b = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int* hdr = a.whdr + size_t(b) * a.strideHdr;
@@ -772,18 +804,25 @@ __global__ void __launch_bounds__(32 * (2 + BW)) update_window_kernel(UpdateMode
     }
     const int w = min(wmax, N - site0);                    // sites of this window
     const int WP = MSF * w;                                // window positions: a = i + r * w  <->  matrix index site0 + i + r * N
-    double* phik = reinterpret_cast<double*>(smem_raw);    // [OPDIM][N]   fields of this slice, kept current
-    double* tsum = phik + OPDIM * N;                       // [OPDIM][wmax] phi(k+1) + phi(k-1) at the window's sites
-    double* ck = tsum + OPDIM * wmax;                      // [wmax] cosh table
-    double* xk = ck + wmax;                                // [wmax] sinh table
-    double* rngs = xk + wmax;                              // [wmax * (OPDIM+1)] random numbers from the cursor on
-    double* ptab = rngs + ((wmax * (OPDIM + 1) + 1) & ~1); // [wmax (wmax+1) / 2][PT::STRIDE] proposal table
-    cplx* Gw = reinterpret_cast<cplx*>(ptab + size_t(wmax) * (wmax + 1) / 2 * PT::STRIDE);   // [WPM][ldw] column major
-    cplx* Sdiag = Gw + size_t(ldw) * WPM;                  // [wmax][MSF*MSF] diagonal blocks
-    cplx* xh = Sdiag + wmax * MSF * MSF;                   // [MSF*JM][WPM] window parts of X_l, term l = MSF j + q
-    cplx* yh = xh + size_t(MSF) * JM * WPM;                // [MSF*JM][WPM] window parts of Y_l
-    __shared__ int sPos, sTerm, sQuit, sNload;
-    __shared__ int mbPos, mbEntry, mbQuit;                 // mailbox warp 0 -> warp 1
+    const WinLayout lay = win_layout(MSF, OPDIM, N, wmax, JM);
+    double* sm = reinterpret_cast<double*>(smem_raw);
+    double* phik = sm + lay.phik;                          // [OPDIM][N]   fields of this slice, kept current
+    double* tsum = sm + lay.tsum;                          // [OPDIM][wmax] phi(k+1) + phi(k-1) at the window's sites
+    double* ck = sm + lay.ck;                              // [wmax] cosh table
+    double* xk = sm + lay.xk;                              // [wmax] sinh table
+    double* rngs = sm + lay.rngs;                          // [wmax * (OPDIM+1)] random numbers from the cursor on
+    double* ptab = sm + lay.ptab;                          // [wmax (wmax+1) / 2][PT::STRIDE] proposal table
+    cplx* Gw = reinterpret_cast<cplx*>(sm + lay.Gw);       // [WPM][ldw] column major
+    cplx* Sdiag = reinterpret_cast<cplx*>(sm + lay.Sdiag); // [wmax][MSF*MSF] diagonal blocks
+    cplx* xh = reinterpret_cast<cplx*>(sm + lay.xh);       // [KM][WPM] window parts of X_l, term l = MSF j + q
+    cplx* yh = reinterpret_cast<cplx*>(sm + lay.yh);       // [KM][WPM] window parts of Y_l
+    cplx* Txp = reinterpret_cast<cplx*>(sm + lay.Tx);      // packed: Tx[i, l] at win_tri_off(l) + i
+    cplx* Typ = reinterpret_cast<cplx*>(sm + lay.Ty);      // packed: Ty[l, i] at win_tri_off(l) + i
+    cplx* smallD = reinterpret_cast<cplx*>(sm + lay.smallD);   // [JM][MSF*MSF] Delta_j
+    cplx* smallM = reinterpret_cast<cplx*>(sm + lay.smallM);   // [JM][MSF*MSF] M_j^-1
+    __shared__ int sPos, sTerm, sQuit, sNload, sNacc;
+    __shared__ int mbPos[kWinMaxJ], mbEnt[kWinMaxJ];       // accepted updates, in order (chain -> helper warps)
+    __shared__ int nPosted, chainDone;
 
     const int k = a.k;
     const cplx* __restrict__ G = a.G + size_t(b) * a.strideG;
@@ -813,17 +852,6 @@ __global__ void __launch_bounds__(32 * (2 + BW)) update_window_kernel(UpdateMode
                         if (lane < w) v[u][r] = col[lane + r * N];
                 }
             }
-            if (w > 32) {                                  // (not used by the shipped window sizes; kept correct)
-                for (int u = 0; u < 4; ++u) {
-                    const int c = c0 + u * (NT / 32);
-                    if (c < WP) {
-                        const int rc = c / w, ic = c - rc * w;
-                        const cplx* col = G + size_t(site0 + ic + rc * N) * D + site0;
-                        for (int r = 0; r < MSF; ++r)
-                            for (int i = lane + 32; i < w; i += 32) Gw[i + r * w + size_t(c) * ldw] = col[i + r * N];
-                    }
-                }
-            }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int c = c0 + u * (NT / 32);
@@ -849,7 +877,7 @@ __global__ void __launch_bounds__(32 * (2 + BW)) update_window_kernel(UpdateMode
         const int want = w * (OPDIM + 1);
         const int have = max(0, min(want, a.rngWindow - cursor0));
         for (int i = tid; i < have; i += NT) rngs[i] = rng[cursor0 + i];
-        if (tid == 0) { sQuit = 0; sNload = have; sPos = 0; sTerm = 0; mbQuit = 0; }
+        if (tid == 0) { sQuit = 0; sNload = have; sPos = 0; sTerm = 0; sNacc = 0; nPosted = 0; chainDone = 0; }
     }
     __syncthreads();
     for (int i = tid; i < w * MSF * MSF; i += NT) {
@@ -915,9 +943,9 @@ __global__ void __launch_bounds__(32 * (2 + BW)) update_window_kernel(UpdateMode
 
     if (warp == 0) {
         // ============================================================ the Metropolis chain
-        int cur = 0, j = 0, pos = 0, posted = 0;
+        int cur = 0, j = 0, pos = 0;
         unsigned accepted = 0;
-        bool aborted = false, pendingSdiag = false;
+        bool aborted = false, outstanding = false;
         const int delayNow = min(JM, N - site0);
         const int nload = sNload;
         int sx = site0 % L, sy = site0 / L;
@@ -946,10 +974,6 @@ __global__ void __launch_bounds__(32 * (2 + BW)) update_window_kernel(UpdateMode
             cplx Dl[MSF * MSF];
 #pragma unroll
             for (int i = 0; i < MSF * MSF; ++i) Dl[i] = reinterpret_cast<const cplx*>(T + PT::DELTA)[i];
-            if (pendingSdiag) {                             // diagonal blocks after the previous acceptance
-                named_bar_sync(kBarSdiag, 64);
-                pendingSdiag = false;
-            }
             // ---------------------------------------------- decision: M = 1 - S Delta + Delta
             cplx M[MSF * MSF];
 #pragma unroll
@@ -961,7 +985,9 @@ __global__ void __launch_bounds__(32 * (2 + BW)) update_window_kernel(UpdateMode
                     for (int t = 0; t < MSF; ++t) sacc = csub(sacc, cmul(Sdiag[pos * MSF * MSF + r * MSF + t], Dl[t * MSF + c]));
                     M[r * MSF + c] = cadd(sacc, Dl[r * MSF + c]);
                 }
-            const cplx det = small_det<MSF>(M);
+            // determinant and inverse together: the reciprocal overlaps with the exponential of the bosonic part
+            cplx Minv[MSF * MSF];
+            const cplx det = small_det_inv<MSF>(M, Minv);
             const double probFermion = (OPDIM == 3) ? det.x : (det.x * det.x + det.y * det.y);
             const double prob = probSPhi * probFermion;
             cur += OPDIM;
@@ -974,26 +1000,87 @@ __global__ void __launch_bounds__(32 * (2 + BW)) update_window_kernel(UpdateMode
             }
             WTICK(1)
             if (!acc) continue;
-            // ---------------------------------------------- accepted: hand over to warp 1
+            // ---------------------------------------------- accepted
             accepted += 1;
-            if (lane == 0) {
+            if (lane == 0) {                                // record for the helper warps (they poll nPosted)
 #pragma unroll
                 for (int d = 0; d < OPDIM; ++d) phik[d * N + site] = T[PT::NEWP + d];
-                mbPos = pos;
-                mbEntry = ent;
+                mbPos[j] = pos;
+                mbEnt[j] = ent;
+#pragma unroll
+                for (int i = 0; i < MSF * MSF; ++i) {
+                    smallD[j * MSF * MSF + i] = Dl[i];
+                    smallM[j * MSF * MSF + i] = Minv[i];
+                }
+                __threadfence_block();
+                *(volatile int*)&nPosted = j + 1;
             }
-            __syncwarp();
-            named_bar_arrive(kBarPosted, 64);
-            pendingSdiag = true;
-            posted += 1;
+            const bool last = (j + 1 == delayNow) || (pos + 1 == w);
+            if (!last) {
+                if (outstanding) {                          // column / row `pos` of Gw must be current
+                    named_bar_sync(kBarDone, NBLK);
+                    outstanding = false;
+                }
+                // window parts of X_j, Y_j and the diagonal blocks of the future sites (lane <-> future site)
+                const int f = pos + 1 + lane;
+                if (f < w) {
+                    cplx* xt = xh + size_t(MSF) * j * WPM;
+                    cplx* yt = yh + size_t(MSF) * j * WPM;
+                    cplx xv[MSF][MSF], yv[MSF][MSF];        // xv[r][q] = X_(j,q)[f + r w],  yv[q][r] = Y_(j,q)[f + r w]
+#pragma unroll
+                    for (int r = 0; r < MSF; ++r) {
+                        const int ar = f + r * w;
+                        cplx cg[MSF], rg[MSF];
+#pragma unroll
+                        for (int p = 0; p < MSF; ++p) {
+                            cg[p] = Gw[ar + size_t(pos + p * w) * ldw];
+                            rg[p] = Gw[pos + p * w + size_t(ar) * ldw];
+                        }
+#pragma unroll
+                        for (int q = 0; q < MSF; ++q) {
+                            cplx xa = make_double2(0, 0), ya = make_double2(0, 0);
+#pragma unroll
+                            for (int p = 0; p < MSF; ++p) {
+                                xa = cfma(cg[p], Dl[p * MSF + q], xa);
+                                ya = cfma(Minv[q * MSF + p], rg[p], ya);
+                            }
+                            xv[r][q] = xa;
+                            yv[q][r] = ya;
+                            xt[q * WPM + ar] = xa;
+                            yt[q * WPM + ar] = ya;
+                        }
+                    }
+#pragma unroll
+                    for (int r = 0; r < MSF; ++r)
+#pragma unroll
+                        for (int c = 0; c < MSF; ++c) {
+                            cplx sacc = Sdiag[f * MSF * MSF + r * MSF + c];
+#pragma unroll
+                            for (int q = 0; q < MSF; ++q) sacc = cfma(xv[r][q], yv[q][c], sacc);
+                            Sdiag[f * MSF * MSF + r * MSF + c] = sacc;
+                        }
+                }
+                if (lane == 0) { sPos = pos; sTerm = MSF * j; }
+                __threadfence_block();
+                __syncwarp();
+                named_bar_arrive(kBarStart, NBLK);          // the block update of the window starts
+                outstanding = true;
+            } else {
+                __syncwarp();
+            }
             j += 1;
             WTICK(2)
             if (j == delayNow) { ++pos; break; }
         }
-        if (pendingSdiag) named_bar_sync(kBarSdiag, 64);
-        if (lane == 0) mbQuit = 1;
+        if (outstanding) named_bar_sync(kBarDone, NBLK);
+        if (lane == 0) {
+            sQuit = 1;
+            sNacc = aborted ? 0 : j;
+            __threadfence_block();
+            *(volatile int*)&chainDone = 1;
+        }
         __syncwarp();
-        named_bar_arrive(kBarPosted, 64);
+        named_bar_arrive(kBarStart, NBLK);
         WTICK(3)
 #ifdef DQMC_UPD_TIMING
         if (a.debug && b == 0 && lane == 0)
@@ -1032,122 +1119,69 @@ __global__ void __launch_bounds__(32 * (2 + BW)) update_window_kernel(UpdateMode
                 }
             }
         }
-    } else if (warp == 1) {
-        // ============================================================ accept helper: everything an acceptance entails
-        // except the decision chain itself -- M^-1, the window parts of X_j / Y_j, the diagonal blocks of the future
-        // sites (warp 0 waits for these only), couplings and record for update_build_xy, fields / tables in global
-        // memory, and the start of the block update
-        const int delayNow = min(JM, N - site0);
-        cplx* coefX = scratch + win_coef_off<MSF>(JM, 0);
-        cplx* coefY = scratch + win_coef_off<MSF>(JM, 1);
-        bool outstanding = false;
+    } else if (warp == 1 || warp == 2) {
+        // ============================================================ coefficient recurrences of the accepted updates
+        // warp 1: column block j of Tx (lane <-> row i) + fields / tables of the accepted site in global memory
+        // warp 2: row block j of Ty (lane <-> column i)
+        const bool xside = warp == 1;
+        cplx* Tp = xside ? Txp : Typ;
+        const cplx* coup = xside ? yh : xh;                // Y_l[S_(j,q)] for Tx, X_l[S_(j,q)] for Ty
+        const cplx* smallS = xside ? smallD : smallM;
         for (int j = 0;; ++j) {
-            named_bar_sync(kBarPosted, 64);
-            if (*(volatile int*)&mbQuit) break;
-            const int pos = *(volatile int*)&mbPos;
-            const int ent = *(volatile int*)&mbEntry;
-            const int site = site0 + pos;
-            const double* T = ptab + size_t(ent) * PT::STRIDE;
-            cplx Dl[MSF * MSF], M[MSF * MSF], Minv[MSF * MSF];
-#pragma unroll
-            for (int i = 0; i < MSF * MSF; ++i) Dl[i] = reinterpret_cast<const cplx*>(T + PT::DELTA)[i];
-#pragma unroll
-            for (int r = 0; r < MSF; ++r)
-#pragma unroll
-                for (int c = 0; c < MSF; ++c) {
-                    cplx sacc = make_double2(r == c ? 1.0 : 0.0, 0.0);
-#pragma unroll
-                    for (int t = 0; t < MSF; ++t) sacc = csub(sacc, cmul(Sdiag[pos * MSF * MSF + r * MSF + t], Dl[t * MSF + c]));
-                    M[r * MSF + c] = cadd(sacc, Dl[r * MSF + c]);
+            for (;;) {
+                if (*(volatile int*)&nPosted > j) break;
+                if (*(volatile int*)&chainDone) {
+                    if (*(volatile int*)&nPosted > j) break;
+                    goto helpers_done;
                 }
-            small_det_inv<MSF>(M, Minv);
-            const bool last = (j + 1 == delayNow) || (pos + 1 == w);
-            if (!last) {
-                if (outstanding) {                          // column / row `pos` of Gw must be current
-                    named_bar_sync(kBarDone, 32 * (1 + BW));
-                    outstanding = false;
-                }
-                const int rf = w - 1 - pos;                 // future sites of the window
-                cplx* xt = xh + size_t(MSF) * j * WPM;
-                cplx* yt = yh + size_t(MSF) * j * WPM;
-                for (int off = lane; off < rf; off += 32) {
-                    const int f = pos + 1 + off;
-                    cplx xv[MSF][MSF], yv[MSF][MSF];        // xv[r][q] = X_(j,q)[f + r w],  yv[q][r] = Y_(j,q)[f + r w]
-#pragma unroll
-                    for (int r = 0; r < MSF; ++r) {
-                        const int ar = f + r * w;
-                        cplx cg[MSF], rg[MSF];
-#pragma unroll
-                        for (int p = 0; p < MSF; ++p) {
-                            cg[p] = Gw[ar + size_t(pos + p * w) * ldw];
-                            rg[p] = Gw[pos + p * w + size_t(ar) * ldw];
-                        }
-#pragma unroll
-                        for (int q = 0; q < MSF; ++q) {
-                            cplx xa = make_double2(0, 0), ya = make_double2(0, 0);
-#pragma unroll
-                            for (int p = 0; p < MSF; ++p) {
-                                xa = cfma(cg[p], Dl[p * MSF + q], xa);
-                                ya = cfma(Minv[q * MSF + p], rg[p], ya);
-                            }
-                            xv[r][q] = xa;
-                            yv[q][r] = ya;
-                            xt[q * WPM + ar] = xa;
-                            yt[q * WPM + ar] = ya;
-                        }
-                    }
-#pragma unroll
-                    for (int r = 0; r < MSF; ++r)
-#pragma unroll
-                        for (int c = 0; c < MSF; ++c) {
-                            cplx sacc = Sdiag[f * MSF * MSF + r * MSF + c];
-#pragma unroll
-                            for (int q = 0; q < MSF; ++q) sacc = cfma(xv[r][q], yv[q][c], sacc);
-                            Sdiag[f * MSF * MSF + r * MSF + c] = sacc;
-                        }
-                }
-                if (lane == 0) { sPos = pos; sTerm = MSF * j; }
-                __syncwarp();
-                named_bar_arrive(kBarSdiag, 64);            // warp 0 may decide the next sites
-                named_bar_arrive(kBarStart, 32 * (1 + BW)); // the block update of the window starts
-                outstanding = true;
-            } else {
-                named_bar_arrive(kBarSdiag, 64);
+                __nanosleep(40);
             }
-            // record for update_build_xy and the fields / tables of the accepted site
-            if (lane == 0) {
+            __threadfence_block();
+            const int pos = mbPos[j];
+            cplx S[MSF * MSF];
+#pragma unroll
+            for (int i = 0; i < MSF * MSF; ++i) S[i] = smallS[j * MSF * MSF + i];
+            const int nrows = MSF * (j + 1), nprev = MSF * j;
+            for (int i = lane; i < nrows; i += 32) {
+                cplx c[MSF];
+#pragma unroll
+                for (int q = 0; q < MSF; ++q) c[q] = make_double2(i == nprev + q ? 1.0 : 0.0, 0.0);
+                for (int l = (i / MSF) * MSF; l < nprev; ++l) {
+                    const cplx t = Tp[win_tri_off(MSF, l) + i];
+                    const cplx* cp = coup + size_t(l) * WPM + pos;
+#pragma unroll
+                    for (int q = 0; q < MSF; ++q) c[q] = cfma(t, cp[q * w], c[q]);
+                }
+#pragma unroll
+                for (int r = 0; r < MSF; ++r) {
+                    cplx v = make_double2(0, 0);
+#pragma unroll
+                    for (int q = 0; q < MSF; ++q)
+                        v = xside ? cfma(c[q], S[q * MSF + r], v)          // Tx[:, (j, r)] = sum_q c_q Delta_j[q, r]
+                                  : cfma(S[r * MSF + q], c[q], v);         // Ty[(j, r), :] = sum_q Minv_j[r, q] r_q
+                    Tp[win_tri_off(MSF, nprev + r) + i] = v;
+                }
+            }
+            if (xside && lane == 0) {
+                const int site = site0 + pos;
+                const double* T = ptab + size_t(mbEnt[j]) * PT::STRIDE;
 #pragma unroll
                 for (int d = 0; d < OPDIM; ++d) phik_g[d * N + site] = T[PT::NEWP + d];
                 coshT[size_t(k) * N + site] = T[PT::CNEW];
                 sinhT[size_t(k) * N + site] = T[PT::XNEW];
                 hdr[4 + j] = site;
-#pragma unroll
-                for (int i = 0; i < MSF * MSF; ++i) {
-                    scratch[win_small_off<MSF>(j, 0) + i] = Dl[i];
-                    scratch[win_small_off<MSF>(j, 1) + i] = Minv[i];
-                }
             }
-            // couplings of this site to the earlier terms (lane <-> term l): Y_l[s_j + qN] and X_l[s_j + qN]
-            for (int l = lane; l < MSF * j; l += 32) {
-#pragma unroll
-                for (int q = 0; q < MSF; ++q) {
-                    coefX[(size_t(l) * JM + j) * MSF + q] = yh[size_t(l) * WPM + pos + q * w];
-                    coefY[(size_t(l) * JM + j) * MSF + q] = xh[size_t(l) * WPM + pos + q * w];
-                }
-            }
+            __syncwarp();
         }
-        if (outstanding) named_bar_sync(kBarDone, 32 * (1 + BW));
-        if (lane == 0) sQuit = 1;
-        __syncwarp();
-        named_bar_arrive(kBarStart, 32 * (1 + BW));
+    helpers_done:;
     } else {
         // ============================================================ block updates of the window
         // thread <-> (row slot ai, column group cg): 64 row slots, four columns in flight
-        const int tb = tid - 64;
+        const int tb = tid - 96;
         const int ai = tb & 63, cg = tb >> 6;
         constexpr int NCG = BW * 32 / 64;
         for (;;) {
-            named_bar_sync(kBarStart, 32 * (1 + BW));
+            named_bar_sync(kBarStart, NBLK);
             if (*(volatile int*)&sQuit) break;
             const int pos = *(volatile int*)&sPos;
             const int tb0 = *(volatile int*)&sTerm;
@@ -1178,124 +1212,108 @@ __global__ void __launch_bounds__(32 * (2 + BW)) update_window_kernel(UpdateMode
                         if (c0 + u * NCG < nf) Gw[ar + size_t(cc[u]) * ldw] = gv[u];
                 }
             }
-            named_bar_arrive(kBarDone, 32 * (1 + BW));
+            __threadfence_block();
+            named_bar_arrive(kBarDone, NBLK);
+        }
+    }
+    __syncthreads();
+    // ---- A = Tx Ty, the K x K core of the round's update  G += G0[:, S] A (G0 - 1)[S, :]
+    {
+        const int Kc = MSF * sNacc;
+        for (int e = tid; e < Kc * Kc; e += NT) {
+            const int i = e / Kc, ip = e - i * Kc;
+            cplx acc = make_double2(0, 0);
+            for (int l = (max(i, ip) / MSF) * MSF; l < Kc; ++l) {
+                const int off = win_tri_off(MSF, l);
+                acc = cfma(Txp[off + i], Typ[off + ip], acc);
+            }
+            scratch[size_t(i) * KM + ip] = acc;
         }
     }
 }
 
-// Rebuild the D-wide X (D x K) and Y (K x D) of a window round from its record, one thread per row of X
-// (blockIdx.y == 0) or column of Y (blockIdx.y == 1):
-//   C_j[t, q] = G[t, s_j + qN] + sum_{l < MSF j} X_l[t] * Y_l[s_j + qN]            X_(j,r)[t] = sum_q C_j[t, q] Delta_j[q, r]
-//   R_j[q, t] = G[s_j + qN, t] - delta + sum_{l < MSF j} X_l[s_j + qN] * Y_l[t]     Y_(j,q')[t] = sum_q Minv_j[q', q] R_j[q, t]
-// (detsdwopdim.cpp:3064-3070, 3123-3138).  The couplings Y_l[s_j + qN], X_l[s_j + qN] are window entries
-// recorded by update_window_kernel.
-constexpr int kBxyThreads = 64;
+// X and Y of a window round for all rows / columns, on all SMs (one CTA per tile of kGthTile matrix indices t):
+//   X_i[t] = G0[t, S_i]                                   (copy of K columns)
+//   Y_i[t] = sum_i' A[i, i'] ( G0[S_i', t] - delta(t, S_i') )
+// so that G0 + X Y is the Green's function after the round's accepted updates (detsdwopdim.cpp:3064-3070, 3123-3138, 3156).
+constexpr int kGthThreads = 256, kGthTile = 32;
 
 template <int MSF>
-__global__ void __launch_bounds__(kBxyThreads) update_build_xy_kernel(UpdateModel md, UpdateArgs a) {
+__global__ void __launch_bounds__(kGthThreads) update_gather_kernel(UpdateModel md, UpdateArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int b = blockIdx.z;
+    const int b = blockIdx.y;
     const int* hdr = a.whdr + size_t(b) * a.strideHdr;
     const int J = hdr[0];
     if (J <= 0) return;
-    const int D = md.D, N = md.N, JM = md.delaySteps;
+    const int D = md.D, N = md.N, KM = MSF * md.delaySteps;
     const int K = MSF * J;
-    const int side = blockIdx.y;                           // 0: rows of X, 1: columns of Y
-    const int tid = threadIdx.x;
-    const int t = min(blockIdx.x * kBxyThreads + tid, D - 1);          // threads past the end redo row D-1 and do not store
-    const bool active = blockIdx.x * kBxyThreads + tid < D;
-    cplx* coef = reinterpret_cast<cplx*>(smem_raw);        // [K][JM][MSF]: coupling of term l to (j, q), l < MSF j
-    cplx* small = coef + size_t(K) * JM * MSF;             // [J][MSF*MSF]: Delta_j (side 0) or Minv_j (side 1)
-    cplx* rowbuf = small + J * MSF * MSF;                  // [K][kBxyThreads]: G entries first, X_l[t] / Y_l[t] once term l is done
-    __shared__ int sites[64];
+    const int tid = threadIdx.x, lane = tid & 31, wv = tid >> 5;
+    constexpr int NW = kGthThreads / 32;
+    const int t0 = blockIdx.x * kGthTile;
+    cplx* As = reinterpret_cast<cplx*>(smem_raw);          // [K][K]
+    cplx* Rs = As + size_t(KM) * KM;                       // [K][kGthTile + 1]
+    __shared__ int sidx[kWinMaxJ * 4];
 #ifdef DQMC_UPD_TIMING
     long long wq[4] = {0, 0, 0, 0};
     long long wmark = clock64();
 #endif
-    const cplx* scratch = a.wscratch + size_t(b) * a.strideScratch;
+    const cplx* __restrict__ scratch = a.wscratch + size_t(b) * a.strideScratch;
     const cplx* __restrict__ G = a.G + size_t(b) * a.strideG;
-    for (int i = tid; i < J; i += kBxyThreads) sites[i] = hdr[4 + i];
-    {
-        const cplx* __restrict__ src = scratch + win_coef_off<MSF>(JM, side);
-        const int n = K * JM * MSF;
-        for (int base = 0; base < n; base += 8 * kBxyThreads) {
-            cplx v[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int i = base + u * kBxyThreads + tid;
-                if (i < n) v[u] = src[i];
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int i = base + u * kBxyThreads + tid;
-                if (i < n) coef[i] = v[u];
-            }
-        }
-        for (int i = tid; i < J * MSF * MSF; i += kBxyThreads) {
-            const int j = i / (MSF * MSF), e = i - j * MSF * MSF;
-            small[i] = scratch[win_small_off<MSF>(j, side) + e];
-        }
+    cplx* X = a.X + size_t(b) * a.strideXY;
+    cplx* Y = a.Y + size_t(b) * a.strideXY;
+    for (int l = tid; l < K; l += kGthThreads) sidx[l] = hdr[4 + l / MSF] + (l % MSF) * N;
+    for (int e = tid; e < K * K; e += kGthThreads) {
+        const int i = e / K, ip = e - i * K;
+        As[e] = scratch[size_t(i) * KM + ip];
     }
     __syncthreads();
     WTICK(0)
-    // the entries of G this row / column needs, eight loads in flight
-    for (int base = 0; base < K; base += 8) {
-        cplx v[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int l = base + u;
-            if (l < K) {
-                const int sj = sites[l / MSF] + (l % MSF) * N;
-                v[u] = side == 0 ? G[size_t(sj) * D + t] : G[size_t(t) * D + sj];
-                if (side == 1 && t == sj) v[u].x -= 1.0;
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u)
-            if (base + u < K) rowbuf[(base + u) * kBxyThreads + tid] = v[u];
-    }
-    cplx* out = (side == 0 ? a.X : a.Y) + size_t(b) * a.strideXY;
-    WTICK(1)
-    for (int j = 0; j < J; ++j) {
-        cplx acc0[MSF], acc1[MSF];
-#pragma unroll
-        for (int q = 0; q < MSF; ++q) {
-            acc0[q] = rowbuf[(j * MSF + q) * kBxyThreads + tid];
-            acc1[q] = make_double2(0, 0);
-        }
-        const int nl = j * MSF;                            // even for MSF = 2, 4: two independent accumulation chains
-        for (int l = 0; l < nl; l += 2) {
-            const cplx v0 = rowbuf[l * kBxyThreads + tid], v1 = rowbuf[(l + 1) * kBxyThreads + tid];
-            const cplx* c0 = coef + (size_t(l) * JM + j) * MSF;
-            const cplx* c1 = coef + (size_t(l + 1) * JM + j) * MSF;
-#pragma unroll
-            for (int q = 0; q < MSF; ++q) {
-                acc0[q] = cfma(v0, c0[q], acc0[q]);
-                acc1[q] = cfma(v1, c1[q], acc1[q]);
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < MSF; ++q) acc0[q] = cadd(acc0[q], acc1[q]);
-        cplx res[MSF];
-#pragma unroll
-        for (int r = 0; r < MSF; ++r) {
+    // rows of G0 - 1 at the accepted sites for this tile (lane <-> term: the sites of a window are close together)
+    for (int tt = wv; tt < kGthTile; tt += NW) {
+        const int t = t0 + tt;
+        for (int l = lane; l < K; l += 32) {
             cplx v = make_double2(0, 0);
-#pragma unroll
-            for (int q = 0; q < MSF; ++q)
-                v = side == 0 ? cfma(acc0[q], small[j * MSF * MSF + q * MSF + r], v)
-                              : cfma(small[j * MSF * MSF + r * MSF + q], acc0[q], v);
-            res[r] = v;
+            if (t < D) {
+                const int s = sidx[l];
+                v = G[size_t(t) * D + s];
+                if (t == s) v.x -= 1.0;
+            }
+            Rs[l * (kGthTile + 1) + tt] = v;
         }
+    }
+    // columns of G0 at the accepted sites
+    {
+        const int t = t0 + lane;
+        if (t < D)
+            for (int l = wv; l < K; l += NW) X[size_t(l) * D + t] = G[size_t(sidx[l]) * D + t];
+    }
+    __syncthreads();
+    WTICK(1)
+    {
+        const int t = t0 + lane;
+        for (int i0 = wv; i0 < K; i0 += 4 * NW) {
+            cplx acc[4];
 #pragma unroll
-        for (int r = 0; r < MSF; ++r) {
-            rowbuf[(j * MSF + r) * kBxyThreads + tid] = res[r];
-            if (active) out[size_t(j * MSF + r) * D + t] = res[r];
+            for (int u = 0; u < 4; ++u) acc[u] = make_double2(0, 0);
+            for (int l = 0; l < K; ++l) {
+                const cplx rv = Rs[l * (kGthTile + 1) + lane];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = min(i0 + u * NW, K - 1);
+                    acc[u] = cfma(As[i * K + l], rv, acc[u]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * NW;
+                if (i < K && t < D) Y[size_t(i) * D + t] = acc[u];
+            }
         }
     }
     WTICK(2)
 #ifdef DQMC_UPD_TIMING
     if (a.debug && b == 0 && blockIdx.x == 0 && tid == 0)
-        printf("bxy dbg round %d side %d J %d: coef %lld gload %lld recur %lld\n", a.round, side, J, wq[0], wq[1], wq[2]);
+        printf("gth dbg round %d J %d: coef %lld gload %lld product %lld\n", a.round, J, wq[0], wq[1], wq[2]);
 #endif
 }
 
@@ -1347,25 +1365,21 @@ cudaError_t update_round_launch(const UpdateModel& m, const UpdateArgs& a, cudaS
 // Sites per window: two delay blocks' worth (a round ends after delaySteps acceptances, at ~50 % acceptance that
 // takes 2 * delaySteps sites), bounded by the shared memory of the (MSF w)^2 window block.
 static size_t window_smem_bytes(const UpdateModel& m, int wmax) {
-    const int wpm = m.msf * wmax;
-    const int dl = (3 + 2 * m.opdim + 1) & ~1, pstride = dl + 2 * m.msf * m.msf;
-    return size_t(m.opdim * m.N + m.opdim * wmax + 2 * wmax + ((wmax * (m.opdim + 1) + 1) & ~1) +
-                  size_t(wmax) * (wmax + 1) / 2 * pstride) * sizeof(double) +
-           (size_t(wpm + 1) * wpm + size_t(wmax) * m.msf * m.msf + size_t(2) * m.msf * m.delaySteps * wpm) * sizeof(cplx);
+    return size_t(win_layout(m.msf, m.opdim, m.N, wmax, m.delaySteps).total) * sizeof(double);
 }
 int update_window_sites(const UpdateModel& m) {
     if (m.delaySteps < 8) return 0;                        // tiny delay blocks are flushed inside the legacy kernel
-    if (m.msf * m.delaySteps > 64) return 0;               // update_build_xy keeps K x J x MSF couplings in shared memory
+    if (m.msf * m.delaySteps > 64 || m.delaySteps > kWinMaxJ) return 0;   // K x K coefficient matrices in shared memory
     int w = 2 * m.delaySteps;
-    if (w > 32) w = 32;                                    // one lane per future site in the accept helper
+    if (w > 32) w = 32;                                    // one lane per future site on acceptance
     if (w > m.N) w = m.N;
     w &= ~1;
-    while (w >= 2 && window_smem_bytes(m, w) > size_t(208) * 1024) w -= 2;
-    return w < 2 ? 0 : w;
+    while (w >= 2 && window_smem_bytes(m, w) > size_t(225) * 1024) w -= 2;   // 227 KB per CTA minus the static part
+    return w < 4 ? 0 : w;
 }
 size_t update_window_scratch_elems(const UpdateModel& m) {
-    const size_t J = m.delaySteps, K = size_t(m.msf) * J;
-    return J * 2 * m.msf * m.msf + 2 * K * J * m.msf;
+    const size_t K = size_t(m.msf) * m.delaySteps;
+    return K * K;
 }
 int update_window_hdr_ints(const UpdateModel& m) { return (4 + m.delaySteps + 3) & ~3; }
 
@@ -1376,7 +1390,7 @@ cudaError_t update_window_launch(const UpdateModel& m, const UpdateArgs& a, cuda
         cudaError_t e = cudaFuncSetAttribute(update_window_kernel<MSF, OPD, BW>,                            \
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
         if (e != cudaSuccess) return e;                                                                     \
-        update_window_kernel<MSF, OPD, BW><<<a.batch, 32 * (2 + BW), smem, st>>>(m, a);                     \
+        update_window_kernel<MSF, OPD, BW><<<a.batch, 32 * (3 + BW), smem, st>>>(m, a);                     \
     }
     // 16 block-update warps for the 2 x 2 site blocks (96 registers per thread suffice); the 4 x 4 blocks of O(3)
     // need the registers more than the warps
@@ -1388,16 +1402,16 @@ cudaError_t update_window_launch(const UpdateModel& m, const UpdateArgs& a, cuda
 }
 
 cudaError_t update_build_xy_launch(const UpdateModel& m, const UpdateArgs& a, cudaStream_t st) {
-    const int J = m.delaySteps, K = m.msf * J;
-    if (J > 64) return cudaErrorInvalidValue;
-    const size_t smem = (size_t(K) * J * m.msf + size_t(J) * m.msf * m.msf + size_t(K) * kBxyThreads) * sizeof(cplx);
-    dim3 grid((m.D + kBxyThreads - 1) / kBxyThreads, 2, a.batch);
+    const int KM = m.msf * m.delaySteps;
+    if (m.delaySteps > kWinMaxJ) return cudaErrorInvalidValue;
+    const size_t smem = (size_t(KM) * KM + size_t(KM) * (kGthTile + 1)) * sizeof(cplx);
+    dim3 grid((m.D + kGthTile - 1) / kGthTile, a.batch);
 #define LAUNCHB(MSF)                                                                                        \
     {                                                                                                       \
-        cudaError_t e = cudaFuncSetAttribute(update_build_xy_kernel<MSF>,                                   \
+        cudaError_t e = cudaFuncSetAttribute(update_gather_kernel<MSF>,                                     \
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
         if (e != cudaSuccess) return e;                                                                     \
-        update_build_xy_kernel<MSF><<<grid, kBxyThreads, smem, st>>>(m, a);                                 \
+        update_gather_kernel<MSF><<<grid, kGthThreads, smem, st>>>(m, a);                                   \
     }
     if (m.msf == 2) LAUNCHB(2)
     else LAUNCHB(4)

@@ -33,7 +33,7 @@ def build():
 
 def summarise(path):
     win = re.compile(r"win dbg round (\d+) sites (\d+) acc (\d+): prologue (\d+) site (\d+) post (\d+) tail (\d+)")
-    bxy = re.compile(r"bxy dbg round (\d+) side (\d+) J (\d+): coef (\d+) gload (\d+) recur (\d+)")
+    bxy = re.compile(r"gth dbg round (\d+) (J) (\d+): coef (\d+) gload (\d+) product (\d+)")
     w = [0] * 7
     bx = {0: [0] * 5, 1: [0] * 5}
     for line in open(path):
@@ -47,7 +47,7 @@ def summarise(path):
                 w[i] += v[i]
         m = bxy.search(line)
         if m:
-            v = [int(x) for x in m.groups()]
+            v = [0 if x == "J" else int(x) for x in m.groups()]
             t = bx[v[1]]
             t[0] += 1
             t[1] += v[2]
@@ -62,7 +62,7 @@ def summarise(path):
         print("  total per site %.0f clocks" % (sum(w[3:7]) / sites))
     for side, t in bx.items():
         if t[0]:
-            print("build_xy side %d: %d launches, mean J %.1f: coef %.0f gload %.0f recurrence %.0f clocks per launch"
+            print("gather (side %d): %d launches, mean J %.1f: coef %.0f gload %.0f product %.0f clocks per launch"
                   % (side, t[0], t[1] / t[0], t[2] / t[0], t[3] / t[0], t[4] / t[0]))
 
 

@@ -955,6 +955,11 @@ size_t fm_acc_len(const dqmc_ctx* ctx) {
 
 int fm_prepare(dqmc_ctx* ctx) {
     if (ctx->fmAcc) return DQMC_OK;
+    if (ctx->p.model == DQMC_MODEL_HUBBARD) {            // DetHubbard::measure needs no shift: five sums + zcorr[N]
+        ctx->fmAccLen = 5 + size_t(ctx->N);
+        CK(dmalloc(&ctx->fmAcc, ctx->fmAccLen * ctx->R));
+        return DQMC_OK;
+    }
     std::vector<cplx> SL, SR;
     cb_build_shift_matrices(ctx->p, ctx->msf, SL, SR);
     CK(dmalloc(&ctx->shiftL, SL.size()));
@@ -971,6 +976,11 @@ int fm_prepare(dqmc_ctx* ctx) {
 int measure_slice(dqmc_ctx* ctx) {
     const int ro = ctx->laneOff, rc = ctx->laneCnt, D = ctx->D;
     const size_t dd = DD(ctx);
+    if (ctx->p.model == DQMC_MODEL_HUBBARD) {            // dethubbard.cpp:511-539
+        CKL(hub_measure_launch(ctx->G + size_t(2 * ro) * dd, (long long)dd, ctx->N, ctx->p.L,
+                               ctx->fmAcc + size_t(ro) * ctx->fmAccLen, (long long)ctx->fmAccLen, rc, ctx->stream));
+        return DQMC_OK;
+    }
     cplx* G = ctx->G + size_t(ro) * dd;
     cplx* T = ctx->W[0] + size_t(ro) * dd;
     cplx* gs = ctx->W[1] + size_t(ro) * dd;
@@ -1397,6 +1407,33 @@ int dqmc_rng_draw(dqmc_ctx* ctx, int rep, size_t n, double* out) {
     if (!valid_rep(ctx, rep) || (n && !out)) return DQMC_ERR_PARAM;
     RET(host_sync_rng(ctx));
     for (size_t i = 0; i < n; ++i) out[i] = ctx->rng[rep].draw();
+    return DQMC_OK;
+}
+// Look-ahead of a replica's stream: the values already drawn from the source (the driver's RngWrapper) but not yet
+// consumed.  They belong to the replica's state: the reference checkpoints model and generator together
+// (detsdwopdim.h:1127-1148 + the driver's rng state), here the generator has run ahead by exactly these values.
+// out == NULL: *n receives the count; otherwise up to *n values are copied and *n receives the number copied.
+int dqmc_rng_look_ahead(dqmc_ctx* ctx, int rep, double* out, size_t* n) {
+    if (!valid_rep(ctx, rep) || !n) return DQMC_ERR_PARAM;
+    RET(host_sync_rng(ctx));
+    const size_t have = ctx->rng[rep].buffered();
+    if (!out) { *n = have; return DQMC_OK; }
+    const size_t cnt = std::min(*n, have);
+    std::memcpy(out, ctx->rng[rep].buffered_values(), cnt * sizeof(double));
+    *n = cnt;
+    return DQMC_OK;
+}
+int dqmc_rng_set_look_ahead(dqmc_ctx* ctx, int rep, const double* values, size_t n) {
+    if (!valid_rep(ctx, rep) || (n && !values)) return DQMC_ERR_PARAM;
+    RET(host_sync_rng(ctx));
+    ctx->rng[rep].set_buffered(values, n);
+    return DQMC_OK;
+}
+// performedSweeps of the reference's model state (detsdwopdim.h:1127-1148): fixes the phase of the global-move schedule
+// (performedSweeps % globalUpdateInterval, detmodel.h:1422-1424) after a resume
+int dqmc_set_performed_sweeps(dqmc_ctx* ctx, uint32_t n) {
+    if (!ctx) return DQMC_ERR_PARAM;
+    ctx->performedSweeps = n;
     return DQMC_OK;
 }
 int dqmc_rng_peek(dqmc_ctx* ctx, int rep, size_t n, double* out) {
@@ -1838,6 +1875,7 @@ int dqmc_wolff_cluster_move(dqmc_ctx* ctx, int with_shift, int32_t* accepted) {
 // finishMeasurements (detsdwopdim.cpp:903-1000, fermionic part) for one replica after dqmc_sweep(ctx, 2)
 int dqmc_get_fermionic_observables(dqmc_ctx* ctx, int rep, double* scalars, double* vectors) {
     if (!valid_rep(ctx, rep) || !scalars || !vectors) return DQMC_ERR_PARAM;
+    if (ctx->p.model != DQMC_MODEL_SDW) { ctx->err = "DetSDW observables; use dqmc_get_hubbard_observables"; return DQMC_ERR_STATE; }
     if (!ctx->fmAcc || ctx->fmSlices != ctx->m) { ctx->err = "no measured sweep (dqmc_sweep(ctx, 2)) yet"; return DQMC_ERR_STATE; }
     const int N = ctx->N, L = ctx->p.L, m = ctx->m, w = 2 * L - 1;
     const size_t nb = size_t(w) * w;
@@ -1885,6 +1923,30 @@ int dqmc_get_fermionic_observables(dqmc_ctx* ctx, int rep, double* scalars, doub
     return DQMC_OK;
 }
 
+// DetHubbard::finishMeasurements (dethubbard.cpp:601-612) for one replica after dqmc_sweep(ctx, 2).
+// scalars: occupationUp, occupationDown, totalOccupation, doubleOccupation, localMoment, kineticEnergy, potentialEnergy,
+// totalEnergy; zcorr: spinzCorrelationFunction [N]
+int dqmc_get_hubbard_observables(dqmc_ctx* ctx, int rep, double* scalars, double* zcorr) {
+    if (!valid_rep(ctx, rep) || !scalars || !zcorr) return DQMC_ERR_PARAM;
+    if (ctx->p.model != DQMC_MODEL_HUBBARD) { ctx->err = "only defined for DetHubbard"; return DQMC_ERR_STATE; }
+    if (!ctx->fmAcc || ctx->fmSlices != ctx->m) { ctx->err = "no measured sweep (dqmc_sweep(ctx, 2)) yet"; return DQMC_ERR_STATE; }
+    std::vector<double> acc(ctx->fmAccLen);
+    CK(cudaMemcpyAsync(acc.data(), ctx->fmAcc + size_t(rep) * ctx->fmAccLen, sizeof(double) * ctx->fmAccLen,
+                       cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const double nm = double(ctx->N) * ctx->m;
+    const double occUp = 1.0 - acc[0] / nm, occDn = 1.0 - acc[1] / nm;
+    const double occTotal = occUp + occDn;
+    const double occDouble = 1.0 + (acc[2] - acc[0] - acc[1]) / nm;
+    const double ePot = ctx->p.U * occDouble;
+    const double eKin = (ctx->p.t / nm) * (acc[3] + acc[4]) - ctx->p.mu * occTotal;
+    scalars[0] = occUp; scalars[1] = occDn; scalars[2] = occTotal; scalars[3] = occDouble;
+    scalars[4] = occTotal - 2 * occDouble;
+    scalars[5] = eKin; scalars[6] = ePot; scalars[7] = eKin + ePot;
+    for (int i = 0; i < ctx->N; ++i) zcorr[i] = acc[5 + i] / ctx->m;
+    return DQMC_OK;
+}
+
 int dqmc_get_wolff_statistics(dqmc_ctx* ctx, int rep, double* out) {
     if (!valid_rep(ctx, rep) || !out) return DQMC_ERR_PARAM;
     RET(host_sync_rng(ctx));
@@ -1908,7 +1970,6 @@ int dqmc_phi_action(dqmc_ctx* ctx, double* out) {
 int dqmc_sweep(dqmc_ctx* ctx, int thermalization) {
     if (!ctx) return DQMC_ERR_PARAM;
     if (thermalization == 2) {                     // sweep(true): fermionic measurements after every slice
-        if (ctx->p.model != DQMC_MODEL_SDW) { ctx->err = "fermionic measurements are defined for DetSDW"; return DQMC_ERR_STATE; }
         RET(fm_prepare(ctx));
         CK(cudaMemsetAsync(ctx->fmAcc, 0, sizeof(double) * ctx->fmAccLen * ctx->R, ctx->stream));
         ctx->fmSlices = ctx->m;

@@ -210,6 +210,8 @@ cudaError_t hub_scales_launch(const int32_t* aux, long long strideAux, int N, in
                               double* out, int off, int batch, cudaStream_t st);
 cudaError_t hub_real_part_launch(const cplx* in, double* out, size_t n, cudaStream_t st);
 cudaError_t hub_to_complex_launch(const double* in, cplx* out, size_t n, cudaStream_t st);
+cudaError_t hub_measure_launch(const cplx* G, long long strideG, int N, int L, double* acc, long long strideAcc, int batch,
+                               cudaStream_t st);
 cudaError_t hub_update_slice_launch(cplx* G, long long strideG, int N, int32_t* aux, long long strideAux, int k,
                                     double alpha, const double* rng, long long strideRng, int rngWindow, int* cursor,
                                     uint32_t* accepted, unsigned long long* acceptedTotal, int* errflag, int batch,

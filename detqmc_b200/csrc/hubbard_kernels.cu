@@ -246,6 +246,52 @@ __global__ void __launch_bounds__(1024) hub_update_slice_kernel(cplx* Gall, long
     }
 }
 
+// DetHubbard::measure (dethubbard.cpp:511-539) for one time slice: sums of the diagonal and nearest-neighbour
+// elements of both Green's-function components and the spin-z correlations with site 0, accumulated over the
+// slices of a sweep.  acc (per replica): sum_GiiUp, sum_GiiDn, sum_GiiUpDn, sum_GneighUp, sum_GneighDn, zcorr[N].
+// One CTA per replica; the block sums are reduced in a fixed order (deterministic).
+__global__ void __launch_bounds__(256) hub_measure_kernel(const cplx* Gall, long long strideG, int N, int L, double* accAll,
+                                                          long long strideAcc) {
+    __shared__ double part[5][256];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const cplx* Gu = Gall + size_t(2 * b) * strideG;
+    const cplx* Gd = Gall + size_t(2 * b + 1) * strideG;
+    double* acc = accAll + size_t(b) * strideAcc;
+    double s[5] = {0, 0, 0, 0, 0};
+    const double gu00 = Gu[0].x, gd00 = Gd[0].x;
+    for (int site = tid; site < N; site += blockDim.x) {
+        const double gu = Gu[size_t(site) * N + site].x, gd = Gd[size_t(site) * N + site].x;
+        s[0] += gu;
+        s[1] += gd;
+        s[2] += gu * gd;
+        // PeriodicCubicLatticeNearestNeighbors (neighbortable.h), d = 2: +x, -x, +y, -y; element (site, neighbour)
+        const int x = site % L, y = site / L;
+        const int nb[4] = {y * L + (x + 1) % L, y * L + (x + L - 1) % L, ((y + 1) % L) * L + x, ((y + L - 1) % L) * L + x};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            s[3] += Gu[size_t(nb[q]) * N + site].x;
+            s[4] += Gd[size_t(nb[q]) * N + site].x;
+        }
+        if (site == 0) {
+            acc[5] += -2.0 * gu00 * gd00 + gu00 + gd00;
+        } else {
+            const double gu0j = Gu[size_t(site) * N].x, gd0j = Gd[size_t(site) * N].x;
+            acc[5 + site] += gu00 * gu - gu00 * gd + gd00 * gd - gd00 * gu - gu0j * gu0j - gd0j * gd0j;
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 5; ++q) part[q][tid] = s[q];
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if (tid < off) {
+#pragma unroll
+            for (int q = 0; q < 5; ++q) part[q][tid] += part[q][tid + off];
+        }
+        __syncthreads();
+    }
+    if (tid < 5) acc[tid] += part[tid][0];
+}
+
 }  // namespace
 
 cudaError_t hub_scales_launch(const int32_t* aux, long long strideAux, int N, int k, double alpha, double sign,
@@ -272,6 +318,12 @@ cudaError_t hub_update_slice_launch(cplx* G, long long strideG, int N, int32_t* 
     const int threads = N >= 256 ? 1024 : 256;
     hub_update_slice_kernel<<<batch, threads, smem, st>>>(G, strideG, N, aux, strideAux, k, alpha, rng, strideRng,
                                                           rngWindow, cursor, accepted, acceptedTotal, errflag);
+    return cudaGetLastError();
+}
+
+cudaError_t hub_measure_launch(const cplx* G, long long strideG, int N, int L, double* acc, long long strideAcc, int batch,
+                               cudaStream_t st) {
+    hub_measure_kernel<<<batch, 256, 0, st>>>(G, strideG, N, L, acc, strideAcc);
     return cudaGetLastError();
 }
 

@@ -65,6 +65,11 @@ public:
     // end_window() returns how many values were read.
     void begin_window(size_t off) { win_ = true; winOff_ = off; winUsed_ = 0; }
     size_t end_window() { win_ = false; return winUsed_; }
+    // values drawn from the source ahead of consumption (part of the replica's state in a checkpoint)
+    size_t buffered() const { return buf_.size() - head_; }
+    const double* buffered_values() const { return buf_.data() + head_; }
+    // resume: replace the buffered values (drawn from a superseded generator state) by the checkpointed look-ahead
+    void set_buffered(const double* v, size_t n) { buf_.assign(v, v + n); head_ = 0; }
 private:
     void ensure(size_t n);
     Dsfmt19937 gen_;

@@ -811,9 +811,10 @@ __global__ void __launch_bounds__(32 * (3 + BW)) update_window_kernel(UpdateMode
     double* ck = sm + lay.ck;                              // [wmax] cosh table
     double* xk = sm + lay.xk;                              // [wmax] sinh table
     double* rngs = sm + lay.rngs;                          // [wmax * (OPDIM+1)] random numbers from the cursor on
-    double* ptab = sm + lay.ptab;                          // [wmax (wmax+1) / 2][PT::STRIDE] proposal table
+    double* ptab = sm + lay.ptab;                          // [PT::STRIDE][NE] proposal table, field-major (lanes read different entries)
+    const int NE = wmax * (wmax + 1) / 2;
     cplx* Gw = reinterpret_cast<cplx*>(sm + lay.Gw);       // [WPM][ldw] column major
-    cplx* Sdiag = reinterpret_cast<cplx*>(sm + lay.Sdiag); // [wmax][MSF*MSF] diagonal blocks
+    cplx* Sdiag = reinterpret_cast<cplx*>(sm + lay.Sdiag); // [MSF*MSF][wmax] diagonal blocks, element-major
     cplx* xh = reinterpret_cast<cplx*>(sm + lay.xh);       // [KM][WPM] window parts of X_l, term l = MSF j + q
     cplx* yh = reinterpret_cast<cplx*>(sm + lay.yh);       // [KM][WPM] window parts of Y_l
     cplx* Txp = reinterpret_cast<cplx*>(sm + lay.Tx);      // packed: Tx[i, l] at win_tri_off(l) + i
@@ -838,9 +839,10 @@ __global__ void __launch_bounds__(32 * (3 + BW)) update_window_kernel(UpdateMode
     double* phik_g = phi + size_t(k) * OPDIM * N;
     {
         // window block of G: column c of the block is MSF contiguous runs of w elements of a column of G
-        // (warp <-> column, lane <-> row of a run; all loads of a thread in flight together)
-        for (int c0 = warp; c0 < WP; c0 += 4 * (NT / 32)) {
-            cplx v[4][MSF];
+        // (warp <-> column, lane <-> row of a run).  The loads of the first pass stay in flight while the fields,
+        // tables and random numbers of the window are fetched: one global round trip instead of two.
+        cplx gv[4][MSF];
+        auto gw_load = [&](int c0) {
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int c = c0 + u * (NT / 32);
@@ -849,18 +851,21 @@ __global__ void __launch_bounds__(32 * (3 + BW)) update_window_kernel(UpdateMode
                     const cplx* col = G + size_t(site0 + ic + rc * N) * D + site0;
 #pragma unroll
                     for (int r = 0; r < MSF; ++r)
-                        if (lane < w) v[u][r] = col[lane + r * N];
+                        if (lane < w) gv[u][r] = col[lane + r * N];
                 }
             }
+        };
+        auto gw_store = [&](int c0) {
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int c = c0 + u * (NT / 32);
                 if (c < WP && lane < w) {
 #pragma unroll
-                    for (int r = 0; r < MSF; ++r) Gw[lane + r * w + size_t(c) * ldw] = v[u][r];
+                    for (int r = 0; r < MSF; ++r) Gw[lane + r * w + size_t(c) * ldw] = gv[u][r];
                 }
             }
-        }
+        };
+        gw_load(warp);
         const int kEarlier = k > 1 ? k - 1 : md.m;
         const int kLater = k < md.m ? k + 1 : 1;
         const double* pl = phi + size_t(kLater) * OPDIM * N;
@@ -877,12 +882,17 @@ __global__ void __launch_bounds__(32 * (3 + BW)) update_window_kernel(UpdateMode
         const int want = w * (OPDIM + 1);
         const int have = max(0, min(want, a.rngWindow - cursor0));
         for (int i = tid; i < have; i += NT) rngs[i] = rng[cursor0 + i];
+        gw_store(warp);
+        for (int c0 = warp + 4 * (NT / 32); c0 < WP; c0 += 4 * (NT / 32)) {
+            gw_load(c0);
+            gw_store(c0);
+        }
         if (tid == 0) { sQuit = 0; sNload = have; sPos = 0; sTerm = 0; sNacc = 0; nPosted = 0; chainDone = 0; }
     }
     __syncthreads();
     for (int i = tid; i < w * MSF * MSF; i += NT) {
         const int pos = i / (MSF * MSF), e = i - pos * MSF * MSF, r = e / MSF, c = e - r * MSF;
-        Sdiag[i] = Gw[pos + r * w + size_t(pos + c * w) * ldw];
+        Sdiag[e * wmax + pos] = Gw[pos + r * w + size_t(pos + c * w) * ldw];
     }
     // ---- proposal table (proposeNewPhiBox, deltaSPhi without the neighbour term, get_delta_forsite): one entry per thread
     {
@@ -896,7 +906,7 @@ __global__ void __launch_bounds__(32 * (3 + BW)) update_window_kernel(UpdateMode
             while ((pos + 1) * (pos + 2) / 2 <= ent) ++pos;
             const int e = ent - pos * (pos + 1) / 2;
             const int cur = OPDIM * pos + e;
-            double* T = ptab + size_t(ent) * PT::STRIDE;
+            double* T = ptab + ent;                        // field f at T[f * NE]
             if (cur + OPDIM > nload) continue;             // never reached: the chain aborts before it would read this entry
             const int site = site0 + pos;
             double oldp[3] = {0, 0, 0}, newp[3] = {0, 0, 0};
@@ -910,8 +920,8 @@ __global__ void __launch_bounds__(32 * (3 + BW)) update_window_kernel(UpdateMode
                 oldSq += oldp[d] * oldp[d];
                 newSq += newp[d] * newp[d];
                 tdot += tsum[d * wmax + pos] * diff;
-                T[PT::DIFF + d] = diff;
-                T[PT::NEWP + d] = newp[d];
+                T[(PT::DIFF + d) * NE] = diff;
+                T[(PT::NEWP + d) * NE] = newp[d];
             }
             const double sqDiff = newSq - oldSq;
             const double pow4Diff = newSq * newSq - oldSq * oldSq;
@@ -921,12 +931,11 @@ __global__ void __launch_bounds__(32 * (3 + BW)) update_window_kernel(UpdateMode
             double cNew, sc;
             cosh_sinhc(lamdtau * sqrt(newSq), cNew, sc);
             const double xNew = lamdtau * sc;                   // sinh(lambda dtau |phi|) / |phi|
-            T[PT::CNEW] = cNew;
-            T[PT::XNEW] = xNew;
+            T[PT::CNEW * NE] = cNew;
+            T[PT::XNEW * NE] = xNew;
             cplx evOld[MSF * MSF], emvNew[MSF * MSF];
             ev_block<MSF, OPDIM>(evOld, +1.0, oldp, ck[pos], xk[pos]);
             ev_block<MSF, OPDIM>(emvNew, -1.0, newp, cNew, xNew);
-            cplx* Dl = reinterpret_cast<cplx*>(T + PT::DELTA);
 #pragma unroll
             for (int r = 0; r < MSF; ++r)
 #pragma unroll
@@ -934,7 +943,8 @@ __global__ void __launch_bounds__(32 * (3 + BW)) update_window_kernel(UpdateMode
                     cplx sacc = make_double2(r == c ? -1.0 : 0.0, 0.0);
 #pragma unroll
                     for (int t = 0; t < MSF; ++t) sacc = cfma(emvNew[r * MSF + t], evOld[t * MSF + c], sacc);
-                    Dl[r * MSF + c] = sacc;
+                    T[(PT::DELTA + 2 * (r * MSF + c)) * NE] = sacc.x;
+                    T[(PT::DELTA + 2 * (r * MSF + c) + 1) * NE] = sacc.y;
                 }
         }
     }
@@ -943,69 +953,86 @@ __global__ void __launch_bounds__(32 * (3 + BW)) update_window_kernel(UpdateMode
 
     if (warp == 0) {
         // ============================================================ the Metropolis chain
+        // A rejected proposal changes nothing but the random-number cursor (by OPDIM + 1), so lane i evaluates site
+        // pos + i under the assumption that the sites pos .. pos + i - 1 are rejected; the first lane that accepts ends
+        // the batch, the lanes before it were evaluated on the true state and stand, the ones after it are discarded.
         int cur = 0, j = 0, pos = 0;
         unsigned accepted = 0;
         bool aborted = false, outstanding = false;
         const int delayNow = min(JM, N - site0);
         const int nload = sNload;
-        int sx = site0 % L, sy = site0 / L;
-        for (; pos < w; ++pos, sx = (sx + 1 == L ? 0 : sx + 1), sy += (sx == 0 ? 1 : 0)) {
-            const int site = site0 + pos;
-            if (cur + OPDIM + 1 > nload) { aborted = true; break; }
-            const int ent = pos * (pos + 1) / 2 + (cur - OPDIM * pos);
-            const double* T = ptab + size_t(ent) * PT::STRIDE;
-            // bosonic part: the neighbour term of deltaSPhi uses the CURRENT fields of the slice
-            double sdot = 0;
-            {
-                const int x = sx, y = sy;
-                const int nb0 = y * L + (x + 1 == L ? 0 : x + 1);
-                const int nb1 = y * L + (x == 0 ? L - 1 : x - 1);
-                const int nb2 = (y + 1 == L ? 0 : y + 1) * L + x;
-                const int nb3 = (y == 0 ? L - 1 : y - 1) * L + x;
+        while (pos < w) {
+            const int mypos = pos + lane;
+            const bool in = mypos < w;
+            const int mycur = cur + lane * (OPDIM + 1);
+            const bool have = in && (mycur + OPDIM + 1 <= nload);
+            bool acc = false, draw = false;
+            int ent = 0;
+            cplx Dl[MSF * MSF], Minv[MSF * MSF];
+            if (have) {
+                ent = mypos * (mypos + 1) / 2 + (mycur - OPDIM * mypos);
+                const double* T = ptab + ent;
+                // bosonic part: the neighbour term of deltaSPhi uses the CURRENT fields of the slice
+                double sdot = 0;
+                {
+                    const int site = site0 + mypos;
+                    const int y = site / L, x = site - y * L;
+                    const int nb0 = y * L + (x + 1 == L ? 0 : x + 1);
+                    const int nb1 = y * L + (x == 0 ? L - 1 : x - 1);
+                    const int nb2 = (y + 1 == L ? 0 : y + 1) * L + x;
+                    const int nb3 = (y == 0 ? L - 1 : y - 1) * L + x;
 #pragma unroll
-                for (int d = 0; d < OPDIM; ++d) {
-                    const double* pk = phik + d * N;
-                    const double sn = ((pk[nb0] + pk[nb1]) + pk[nb2]) + pk[nb3];
-                    sdot += sn * T[PT::DIFF + d];
+                    for (int d = 0; d < OPDIM; ++d) {
+                        const double* pk = phik + d * N;
+                        const double sn = ((pk[nb0] + pk[nb1]) + pk[nb2]) + pk[nb3];
+                        sdot += sn * T[(PT::DIFF + d) * NE];
+                    }
                 }
+                const double udraw = rngs[mycur + OPDIM];       // consumed only if the probability is <= 1
+                const double probSPhi = exp(-(T[0] - dtau * sdot));       // field 0: deltaSPhi without the neighbour term
+#pragma unroll
+                for (int i = 0; i < MSF * MSF; ++i)
+                    Dl[i] = make_double2(T[(PT::DELTA + 2 * i) * NE], T[(PT::DELTA + 2 * i + 1) * NE]);
+                // ------------------------------------------ decision: M = 1 - S Delta + Delta
+                cplx M[MSF * MSF];
+#pragma unroll
+                for (int r = 0; r < MSF; ++r)
+#pragma unroll
+                    for (int c = 0; c < MSF; ++c) {
+                        cplx sacc = make_double2(r == c ? 1.0 : 0.0, 0.0);
+#pragma unroll
+                        for (int t = 0; t < MSF; ++t)
+                            sacc = csub(sacc, cmul(Sdiag[(r * MSF + t) * wmax + mypos], Dl[t * MSF + c]));
+                        M[r * MSF + c] = cadd(sacc, Dl[r * MSF + c]);
+                    }
+                // determinant and inverse together: the reciprocal overlaps with the exponential of the bosonic part
+                const cplx det = small_det_inv<MSF>(M, Minv);
+                const double probFermion = (OPDIM == 3) ? det.x : (det.x * det.x + det.y * det.y);
+                const double prob = probSPhi * probFermion;
+                draw = !(prob > 1.0);
+                acc = draw ? (udraw < prob) : true;
             }
-            const double udraw = rngs[cur + OPDIM];             // consumed only if the probability is <= 1
-            const double probSPhi = exp(-(T[0] - dtau * sdot));
-            cplx Dl[MSF * MSF];
-#pragma unroll
-            for (int i = 0; i < MSF * MSF; ++i) Dl[i] = reinterpret_cast<const cplx*>(T + PT::DELTA)[i];
-            // ---------------------------------------------- decision: M = 1 - S Delta + Delta
-            cplx M[MSF * MSF];
-#pragma unroll
-            for (int r = 0; r < MSF; ++r)
-#pragma unroll
-                for (int c = 0; c < MSF; ++c) {
-                    cplx sacc = make_double2(r == c ? 1.0 : 0.0, 0.0);
-#pragma unroll
-                    for (int t = 0; t < MSF; ++t) sacc = csub(sacc, cmul(Sdiag[pos * MSF * MSF + r * MSF + t], Dl[t * MSF + c]));
-                    M[r * MSF + c] = cadd(sacc, Dl[r * MSF + c]);
-                }
-            // determinant and inverse together: the reciprocal overlaps with the exponential of the bosonic part
-            cplx Minv[MSF * MSF];
-            const cplx det = small_det_inv<MSF>(M, Minv);
-            const double probFermion = (OPDIM == 3) ? det.x : (det.x * det.x + det.y * det.y);
-            const double prob = probSPhi * probFermion;
-            cur += OPDIM;
-            bool acc;
-            if (prob > 1.0) {
-                acc = true;
-            } else {
-                acc = udraw < prob;
-                cur += 1;
-            }
+            const unsigned inMask = __ballot_sync(0xffffffffu, in);
+            const unsigned haveMask = __ballot_sync(0xffffffffu, have);
+            const unsigned accMask = __ballot_sync(0xffffffffu, acc);
+            const unsigned stopMask = inMask & ~haveMask;       // sites the window holds no random numbers for
+            const int ia = accMask ? __ffs(accMask) - 1 : 32;
+            const int is = stopMask ? __ffs(stopMask) - 1 : 32;
             WTICK(1)
-            if (!acc) continue;
-            // ---------------------------------------------- accepted
-            accepted += 1;
-            if (lane == 0) {                                // record for the helper warps (they poll nPosted)
+            if (is < ia) { pos += is; aborted = true; break; }
+            if (ia == 32) {                                     // every site of the batch rejected
+                const int nb = __popc(inMask);
+                pos += nb;
+                cur += nb * (OPDIM + 1);
+                continue;
+            }
+            // ---------------------------------------------- accepted: lane ia's proposal
+            const int apos = pos + ia;
+            if (lane == ia) {                                   // record for the other lanes and the helper warps (they poll nPosted)
+                const double* T = ptab + ent;
 #pragma unroll
-                for (int d = 0; d < OPDIM; ++d) phik[d * N + site] = T[PT::NEWP + d];
-                mbPos[j] = pos;
+                for (int d = 0; d < OPDIM; ++d) phik[d * N + site0 + apos] = T[(PT::NEWP + d) * NE];
+                mbPos[j] = apos;
                 mbEnt[j] = ent;
 #pragma unroll
                 for (int i = 0; i < MSF * MSF; ++i) {
@@ -1015,14 +1042,23 @@ __global__ void __launch_bounds__(32 * (3 + BW)) update_window_kernel(UpdateMode
                 __threadfence_block();
                 *(volatile int*)&nPosted = j + 1;
             }
-            const bool last = (j + 1 == delayNow) || (pos + 1 == w);
+            cur = __shfl_sync(0xffffffffu, mycur + OPDIM + (draw ? 1 : 0), ia);
+            __syncwarp();
+            const bool last = (j + 1 == delayNow) || (apos + 1 == w);
             if (!last) {
-                if (outstanding) {                          // column / row `pos` of Gw must be current
+#pragma unroll
+                for (int i = 0; i < MSF * MSF; ++i) {
+                    Dl[i] = smallD[j * MSF * MSF + i];
+                    Minv[i] = smallM[j * MSF * MSF + i];
+                }
+                WTICK(2)
+                if (outstanding) {                          // column / row `apos` of Gw must be current
                     named_bar_sync(kBarDone, NBLK);
                     outstanding = false;
                 }
+                WTICK(4)
                 // window parts of X_j, Y_j and the diagonal blocks of the future sites (lane <-> future site)
-                const int f = pos + 1 + lane;
+                const int f = apos + 1 + lane;
                 if (f < w) {
                     cplx* xt = xh + size_t(MSF) * j * WPM;
                     cplx* yt = yh + size_t(MSF) * j * WPM;
@@ -1033,8 +1069,8 @@ __global__ void __launch_bounds__(32 * (3 + BW)) update_window_kernel(UpdateMode
                         cplx cg[MSF], rg[MSF];
 #pragma unroll
                         for (int p = 0; p < MSF; ++p) {
-                            cg[p] = Gw[ar + size_t(pos + p * w) * ldw];
-                            rg[p] = Gw[pos + p * w + size_t(ar) * ldw];
+                            cg[p] = Gw[ar + size_t(apos + p * w) * ldw];
+                            rg[p] = Gw[apos + p * w + size_t(ar) * ldw];
                         }
 #pragma unroll
                         for (int q = 0; q < MSF; ++q) {
@@ -1054,23 +1090,23 @@ __global__ void __launch_bounds__(32 * (3 + BW)) update_window_kernel(UpdateMode
                     for (int r = 0; r < MSF; ++r)
 #pragma unroll
                         for (int c = 0; c < MSF; ++c) {
-                            cplx sacc = Sdiag[f * MSF * MSF + r * MSF + c];
+                            cplx sacc = Sdiag[(r * MSF + c) * wmax + f];
 #pragma unroll
                             for (int q = 0; q < MSF; ++q) sacc = cfma(xv[r][q], yv[q][c], sacc);
-                            Sdiag[f * MSF * MSF + r * MSF + c] = sacc;
+                            Sdiag[(r * MSF + c) * wmax + f] = sacc;
                         }
                 }
-                if (lane == 0) { sPos = pos; sTerm = MSF * j; }
+                if (lane == 0) { sPos = apos; sTerm = MSF * j; }
                 __threadfence_block();
                 __syncwarp();
                 named_bar_arrive(kBarStart, NBLK);          // the block update of the window starts
                 outstanding = true;
-            } else {
-                __syncwarp();
             }
+            accepted += 1;
             j += 1;
+            pos = apos + 1;
             WTICK(2)
-            if (j == delayNow) { ++pos; break; }
+            if (j == delayNow) break;
         }
         if (outstanding) named_bar_sync(kBarDone, NBLK);
         if (lane == 0) {
@@ -1084,8 +1120,8 @@ __global__ void __launch_bounds__(32 * (3 + BW)) update_window_kernel(UpdateMode
         WTICK(3)
 #ifdef DQMC_UPD_TIMING
         if (a.debug && b == 0 && lane == 0)
-            printf("win dbg round %d sites %d acc %d: prologue %lld site %lld post %lld tail %lld\n",
-                   a.round, pos, j, wq[0], wq[1], wq[2], wq[3]);
+            printf("win dbg round %d sites %d acc %d: prologue %lld site %lld post %lld tail %lld wait %lld\n",
+                   a.round, pos, j, wq[0], wq[1], wq[2], wq[3], wq[4]);
 #endif
         if (lane == 0) {
             const int site = aborted ? N : site0 + pos;
@@ -1164,11 +1200,11 @@ __global__ void __launch_bounds__(32 * (3 + BW)) update_window_kernel(UpdateMode
             }
             if (xside && lane == 0) {
                 const int site = site0 + pos;
-                const double* T = ptab + size_t(mbEnt[j]) * PT::STRIDE;
+                const double* T = ptab + mbEnt[j];
 #pragma unroll
-                for (int d = 0; d < OPDIM; ++d) phik_g[d * N + site] = T[PT::NEWP + d];
-                coshT[size_t(k) * N + site] = T[PT::CNEW];
-                sinhT[size_t(k) * N + site] = T[PT::XNEW];
+                for (int d = 0; d < OPDIM; ++d) phik_g[d * N + site] = T[(PT::NEWP + d) * NE];
+                coshT[size_t(k) * N + site] = T[PT::CNEW * NE];
+                sinhT[size_t(k) * N + site] = T[PT::XNEW * NE];
                 hdr[4 + j] = site;
             }
             __syncwarp();
@@ -1176,40 +1212,36 @@ __global__ void __launch_bounds__(32 * (3 + BW)) update_window_kernel(UpdateMode
     helpers_done:;
     } else {
         // ============================================================ block updates of the window
-        // thread <-> (row slot ai, column group cg): 64 row slots, four columns in flight
+        // thread <-> (window position a of the row, column group cg): rows and columns at or before the accepted site are
+        // masked out instead of compacted (no index arithmetic in the loop), eight columns per thread
         const int tb = tid - 96;
-        const int ai = tb & 63, cg = tb >> 6;
+        const int ar = tb & 63, cg = tb >> 6;
         constexpr int NCG = BW * 32 / 64;
+        int ari = ar;
+        while (ari >= w) ari -= w;                          // site index of the row within the window
         for (;;) {
             named_bar_sync(kBarStart, NBLK);
             if (*(volatile int*)&sQuit) break;
             const int pos = *(volatile int*)&sPos;
             const int tb0 = *(volatile int*)&sTerm;
-            const int rf = w - 1 - pos, nf = MSF * rf;
-            for (int a0 = ai; a0 < nf; a0 += 64) {
-                const int ra = a0 / rf;
-                const int ar = pos + 1 + (a0 - ra * rf) + ra * w;
+            for (int a0 = ar; a0 < WP; a0 += 64) {
+                int ai = a0 == ar ? ari : a0;
+                while (ai >= w) ai -= w;
+                if (ai <= pos) continue;
                 cplx xv[MSF];
 #pragma unroll
-                for (int q = 0; q < MSF; ++q) xv[q] = xh[size_t(tb0 + q) * WPM + ar];
-                for (int c0 = cg; c0 < nf; c0 += 4 * NCG) {
-                    cplx gv[4];
-                    int cc[4];
+                for (int q = 0; q < MSF; ++q) xv[q] = xh[size_t(tb0 + q) * WPM + a0];
+                int c = cg, ci = cg;
+                while (ci >= w) ci -= w;
+                for (; c < WP; c += NCG) {
+                    if (ci > pos) {
+                        cplx gv = Gw[a0 + size_t(c) * ldw];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int ci = c0 + u * NCG;
-                        const int cl = ci < nf ? ci : c0;             // clamp: duplicates are not stored
-                        const int rc = cl / rf;
-                        cc[u] = pos + 1 + (cl - rc * rf) + rc * w;
-                        gv[u] = Gw[ar + size_t(cc[u]) * ldw];
+                        for (int q = 0; q < MSF; ++q) gv = cfma(xv[q], yh[size_t(tb0 + q) * WPM + c], gv);
+                        Gw[a0 + size_t(c) * ldw] = gv;
                     }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-#pragma unroll
-                        for (int q = 0; q < MSF; ++q) gv[u] = cfma(xv[q], yh[size_t(tb0 + q) * WPM + cc[u]], gv[u]);
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        if (c0 + u * NCG < nf) Gw[ar + size_t(cc[u]) * ldw] = gv[u];
+                    ci += NCG;
+                    while (ci >= w) ci -= w;
                 }
             }
             __threadfence_block();

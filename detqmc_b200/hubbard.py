@@ -117,11 +117,25 @@ class DetHubbardBatch:
         return acc
 
     def sweep(self, takeMeasurements=False):
-        if takeMeasurements:
-            raise DqmcError("measurements are outside the accelerated path (SURVEY 8f)")
+        """sweep(takeMeasurements) (dethubbard.cpp:173-183): with measurements, DetHubbard::measure runs on the device
+        after the update of every slice; read the result with observables()."""
+        self._ck(self.lib.dqmc_sweep(self.h, 2 if takeMeasurements else 0))
+
+    def sweepThermalization(self):
         self._ck(self.lib.dqmc_sweep(self.h, 0))
 
-    sweepThermalization = sweep
+    OBSERVABLES = ("occupationUp", "occupationDown", "totalOccupation", "doubleOccupation", "localMoment",
+                   "kineticEnergy", "potentialEnergy", "totalEnergy")
+
+    def observables(self, rep=0):
+        """finishMeasurements (dethubbard.cpp:601-612) after sweep(True): the reference's scalar observables by name
+        plus spinzCorrelationFunction [N]."""
+        sc = np.zeros(8)
+        zc = np.zeros(self.N)
+        self._ck(self.lib.dqmc_get_hubbard_observables(self.h, rep, _ptr(sc), _ptr(zc)))
+        out = dict(zip(self.OBSERVABLES, sc.tolist()))
+        out["spinzCorrelationFunction"] = zc
+        return out
 
     def synchronize(self):
         self._ck(self.lib.dqmc_synchronize(self.h))

@@ -47,6 +47,10 @@ SYMBOLS = [
     ("dqmc_wolff_cluster_move", c_i32, [c_vp, c_i32, c_vp]),
     ("dqmc_sweep_simple", c_i32, [c_vp, c_i32]),
     ("dqmc_get_fermionic_observables", c_i32, [c_vp, c_i32, c_vp, c_vp]),
+    ("dqmc_get_hubbard_observables", c_i32, [c_vp, c_i32, c_vp, c_vp]),
+    ("dqmc_rng_look_ahead", c_i32, [c_vp, c_i32, c_vp, c_vp]),
+    ("dqmc_rng_set_look_ahead", c_i32, [c_vp, c_i32, c_vp, ctypes.c_size_t]),
+    ("dqmc_set_performed_sweeps", c_i32, [c_vp, c_u32]),
     ("dqmc_get_wolff_statistics", c_i32, [c_vp, c_i32, c_vp]),
     ("dqmc_launch_count", c_u64, [c_vp]),
     ("dqmc_rng_seed", c_i32, [c_vp, c_i32, c_u32, c_u32]),

@@ -10,12 +10,15 @@
 // delayed updates, global shift moves -- runs on the GPU through include/dqmc_gpu.h.
 //
 // Differences a maintainer has to know:
-//   * fermionic measurements (measure(k)) are not part of the accelerated path: run with
-//     turnoffFermionMeasurements = true; the bosonic observables below are evaluated on the host from
-//     the downloaded field after every measurement sweep.
+//   * fermionic measurements (measure(k), detsdwopdim.cpp:540-900) run on the device during sweep(true) unless
+//     turnoffFermionMeasurements is set; the bosonic observables are evaluated on the host from the downloaded
+//     field after every measurement sweep.
 //   * random numbers: the replica consumes the driver's RngWrapper through a pre-drawn FIFO
-//     (dqmc_rng_set_source).  Values drawn ahead but not yet consumed are part of the model's state
-//     and are saved / restored by saveContents / loadContents.
+//     (dqmc_rng_set_source).  Values drawn ahead but not yet consumed are part of the model's state:
+//     saveContents stores them, loadContents puts them back in front of the stream, so a resumed run continues
+//     with exactly the numbers an uninterrupted run would have used.
+//   * checkpoints are NOT interchangeable with the reference's (different archive layout: fields, control blob,
+//     look-ahead, sweep counter).
 #ifndef DETSDW_GPU_H_
 #define DETSDW_GPU_H_
 
@@ -255,24 +258,57 @@ public:
         check(dqmc_set_control_data(ctx, 0, &cd), "dqmc_set_control_data");
     }
 
-    // checkpointing: fields + control data (G and the UDT storage are rebuilt, as in the reference:
-    // detsdwopdim.h:1117-1148, detmodel.h:493-502)
+    // checkpointing: fields + control data + random numbers drawn ahead of consumption + sweep counter (G and the
+    // UDT storage are rebuilt, as in the reference: detsdwopdim.h:1117-1148, detmodel.h:493-502)
     template <class Archive>
     void saveContents(Archive& ar) {
         std::vector<double> phi = downloadPhi();
         dqmc_control_data cd;
         dqmc_get_control_data(ctx, 0, &cd);
         std::string blob(reinterpret_cast<const char*>(&cd), sizeof cd);
-        ar & phi & blob & performedSweeps;
+        size_t n = 0;
+        check(dqmc_rng_look_ahead(ctx, 0, nullptr, &n), "dqmc_rng_look_ahead");
+        std::vector<double> ahead(n);
+        if (n) check(dqmc_rng_look_ahead(ctx, 0, ahead.data(), &n), "dqmc_rng_look_ahead");
+        ar & phi & blob & ahead & performedSweeps;
     }
     template <class Archive>
     void loadContents(Archive& ar) {
-        std::vector<double> phi;
+        std::vector<double> phi, ahead;
         std::string blob;
-        ar & phi & blob & performedSweeps;
+        ar & phi & blob & ahead & performedSweeps;
         check(dqmc_upload_fields(ctx, 0, phi.data()), "dqmc_upload_fields");
         set_control_data(blob);
+        check(dqmc_rng_set_look_ahead(ctx, 0, ahead.data(), ahead.size()), "dqmc_rng_set_look_ahead");
         check(dqmc_setup_storage(ctx), "dqmc_setup_storage");
+        check(dqmc_set_performed_sweeps(ctx, performedSweeps), "dqmc_set_performed_sweeps");
+    }
+
+    // system configurations for DetQMCPT's buffered configuration streams (detqmcpt.h:679, 697;
+    // detsdwopdim.cpp:5116-5160): the reference's own DetSDW_SystemConfig / file-handle types, filled from the device
+    SystemConfig getCurrentSystemConfiguration() {
+        std::vector<double> phi = downloadPhi();           // [k][dim][site] == Cube(site, dim, k), column major
+        const CubeNum cube(phi.data(), pars.L * pars.L, OPDIM, pars.m + 1);
+        return SystemConfig(pars, cube);
+    }
+    SystemConfig_FileHandle prepareSystemConfigurationStreamFileHandle(bool binaryStream, bool textStream,
+                                                                       const std::string& directory = ".") {
+        if (!binaryStream && !textStream) throw_GeneralError("binaryStream or textStream must be specified to create a file handle");
+        typedef SystemConfig_FileHandle::OfstreamPointer Ptr;
+        SystemConfig_FileHandle fh;
+        if (binaryStream) {
+            const std::string path = directory + "/configs-phi.binarystream";
+            fh.phi_output_binary = Ptr(new std::ofstream(path.c_str(), std::ios::binary | std::ios::app));
+            if (fh.phi_output_binary->fail()) std::cerr << "Could not open file " << path << " for writing.\n";
+        }
+        if (textStream) {
+            const std::string path = directory + "/configs-phi.textstream";
+            fh.phi_output_text = Ptr(new std::ofstream(path.c_str(), std::ios::app));
+            if (fh.phi_output_text->fail()) std::cerr << "Could not open file " << path << " for writing.\n";
+            fh.phi_output_text->precision(14);
+            fh.phi_output_text->setf(std::ios::scientific, std::ios::floatfield);
+        }
+        return fh;
     }
 
     dqmc_ctx* context() { return ctx; }
@@ -350,9 +386,22 @@ void createReplica(std::unique_ptr<DetSDWGpu<OPDIM>>& replica_out, RngWrapper& r
     replica_out = std::unique_ptr<DetSDWGpu<OPDIM>>(new DetSDWGpu<OPDIM>(rng, pars));
 }
 
-// replica-exchange probability (detsdwopdim.cpp:5251-5264) for the PT driver
+// replica-exchange probability for the PT driver: DetQMCPT calls get_replica_exchange_probability<Model>
+// (detqmcpt.h:1041), a function template the model specialises (detmodel.h:93-108, detsdwopdim.cpp:5251-5325)
 template <int OPDIM>
 inline num get_replica_exchange_probability_gpu(num r1, num action1, num r2, num action2) {
+    return dqmc_exchange_probability(r1, action1, r2, action2);
+}
+template <>
+inline num get_replica_exchange_probability<DetSDWGpu<1>>(num r1, num action1, num r2, num action2) {
+    return dqmc_exchange_probability(r1, action1, r2, action2);
+}
+template <>
+inline num get_replica_exchange_probability<DetSDWGpu<2>>(num r1, num action1, num r2, num action2) {
+    return dqmc_exchange_probability(r1, action1, r2, action2);
+}
+template <>
+inline num get_replica_exchange_probability<DetSDWGpu<3>>(num r1, num action1, num r2, num action2) {
     return dqmc_exchange_probability(r1, action1, r2, action2);
 }
 

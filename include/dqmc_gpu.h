@@ -141,6 +141,16 @@ int dqmc_rng_draw(dqmc_ctx* ctx, int rep, size_t n, double* out);
 /* Look at the next n values without consuming them / consume n values. */
 int dqmc_rng_peek(dqmc_ctx* ctx, int rep, size_t n, double* out);
 int dqmc_rng_skip(dqmc_ctx* ctx, int rep, size_t n);
+/* Checkpointing of a stream fed by dqmc_rng_set_source: the values already drawn from the driver's generator but not
+ * yet consumed are part of the replica's state (the reference saves model and generator together, detqmc.h:316-356).
+ * dqmc_rng_look_ahead: out == NULL -> *n = number of such values; else copy up to *n of them (oldest first).
+ * dqmc_rng_set_look_ahead: after a resume (the driver has restored its generator), discard whatever the replica
+ * drew from the superseded generator state and install the saved values as the head of the stream. */
+int dqmc_rng_look_ahead(dqmc_ctx* ctx, int rep, double* out, size_t* n);
+int dqmc_rng_set_look_ahead(dqmc_ctx* ctx, int rep, const double* values, size_t n);
+/* performedSweeps of the model state (detsdwopdim.h:1127-1148): restores the phase of the global-move schedule
+ * (performedSweeps % globalUpdateInterval, detmodel.h:1422-1424) after loadContents. */
+int dqmc_set_performed_sweeps(dqmc_ctx* ctx, uint32_t n);
 /* Total number of values consumed from replica rep's stream so far. */
 uint64_t dqmc_rng_consumed(const dqmc_ctx* ctx, int rep);
 /* Context-free: the first n rand01() values of RngWrapper(seed, process_index) (rngwrapper.cpp:30-50,
@@ -263,6 +273,11 @@ int dqmc_sweep(dqmc_ctx* ctx, int thermalization);
  * vectors[4 N] = kOccX | kOccY | pairPlus | pairMinus (momentum-space occupation per band, equal-time pairing
  * correlations between site 0 and site i). */
 int dqmc_get_fermionic_observables(dqmc_ctx* ctx, int rep, double* scalars, double* vectors);
+/* DetHubbard: dqmc_sweep(ctx, 2) accumulates DetHubbard::measure (dethubbard.cpp:511-539) after the update of every
+ * slice; finishMeasurements (dethubbard.cpp:601-612) for replica `rep`:
+ * scalars[8] = occupationUp, occupationDown, totalOccupation, doubleOccupation, localMoment, kineticEnergy,
+ * potentialEnergy, totalEnergy; zcorr[N] = spinzCorrelationFunction. */
+int dqmc_get_hubbard_observables(dqmc_ctx* ctx, int rep, double* scalars, double* zcorr);
 
 /* Resident random numbers: upload the next n_sweeps sweeps' worth of every replica's stream once;
  * dqmc_sweep then runs without per-sweep host<->device copies or synchronisation (the consumption

@@ -274,6 +274,13 @@ class RefHubbard:
         if rc:
             raise RuntimeError("reference sweep failed")
 
+    def measured_sweep(self):
+        """sweep(true): the reference's scalar observables (dethubbard.cpp:88-95 order of finishMeasurements) and zcorr"""
+        sc, zc = np.zeros(8), np.zeros(self.N)
+        if lib().ref_hub_measured_sweep(self.h, _p(sc), _p(zc)):
+            raise RuntimeError("reference sweep failed")
+        return sc, zc
+
     def rng_draw(self, n):
         out = np.zeros(n)
         lib().ref_hub_rng_draw(self.h, c_i32(n), _p(out))

@@ -485,6 +485,23 @@ int ref_hub_sweep(void* h, int therm) {
     }
     return 0;
 }
+// sweep(true) (dethubbard.cpp:173-183): measure() after every slice, finishMeasurements at the end.
+// scalars[8] = occUp, occDn, occTotal, occDouble, localMoment, eKinetic, ePotential, eTotal; zcorr[N]
+int ref_hub_measured_sweep(void* h, double* scalars, double* zcorr) {
+    CoutSilencer q;
+    HubHandle* hh = static_cast<HubHandle*>(h);
+    try {
+        hh->rep->sweep(true);
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "ref_hub_measured_sweep: %s\n", e.what());
+        return 1;
+    }
+    DetHubbard& r = *hh->rep;
+    scalars[0] = r.occUp; scalars[1] = r.occDn; scalars[2] = r.occTotal; scalars[3] = r.occDouble;
+    scalars[4] = r.localMoment; scalars[5] = r.eKinetic; scalars[6] = r.ePotential; scalars[7] = r.eTotal;
+    for (arma::uword i = 0; i < r.zcorr.n_elem; ++i) zcorr[i] = r.zcorr[i];
+    return 0;
+}
 void ref_hub_rng_draw(void* h, int n, double* out) {
     HubHandle* hh = static_cast<HubHandle*>(h);
     for (int i = 0; i < n; ++i) out[i] = hh->rng.rand01();

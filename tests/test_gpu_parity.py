@@ -908,6 +908,87 @@ def test_hubbard_vs_golden(name):
         assert abs(b.total_occupation() - 1.0) < 1e-10                 # half filling
 
 
+@pytest.mark.parametrize("tag", ["c1", "cb"])
+def test_hubbard_observables_vs_golden(tag):
+    """DetHubbard::measure on the device (dqmc_sweep(ctx, 2) + dqmc_get_hubbard_observables) against the observables
+    the reference measured itself over six sweeps (tools/make_golden.py hubbard_observables)."""
+    import json
+    from detqmc_b200 import DetHubbardBatch
+    from dqmc_oracle import HubbardParams
+    g = load_golden("hubbard_observables")
+    d = json.loads(str(g["params_" + tag]))
+    d.pop("N", None)
+    b = DetHubbardBatch(HubbardParams(**d))
+    for _ in range(4):
+        b.sweepThermalization()
+    for i in range(6):
+        b.sweep(True)
+        ob = b.observables()
+        got = np.array([ob[k] for k in b.OBSERVABLES])
+        assert np.allclose(got, g["scalars_" + tag][i], rtol=1e-9, atol=1e-10), (i, got, g["scalars_" + tag][i])
+        assert maxabs(ob["spinzCorrelationFunction"], g["zcorr_" + tag][i]) < 1e-9
+    assert np.array_equal(b.auxfield()[1:], g["aux_final_" + tag])
+
+
+def _series(path):
+    return [float(x) for x in open(path) if x.strip() and x[0] != "#"]
+
+
+def test_reference_driver_with_hubbard_shim(tmp_path):
+    """host/_build/detqmchubbard_gpu = the reference's DetQMC<Model, ModelParams> driver (compiled unmodified from the
+    reference tree) on include/dethubbard_gpu.h: its time series must equal the observables the reference's own
+    DetHubbard measured for the same seed (BASELINE config C1)."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "host", "_build", "detqmchubbard_gpu")
+    if not os.path.exists(exe):
+        pytest.skip("host/_build/detqmchubbard_gpu not built (needs the reference tree: make -C host)")
+    g = load_golden("hubbard_observables")
+    out = subprocess.run([exe, "L=4", "U=4", "beta=4", "dtau=0.1", "s=10", "mu=0", "t=1", "thermalization=4", "sweeps=6",
+                          "rngSeed=1020304050", "simindex=0"], cwd=str(tmp_path), capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    names = ("occupationUp", "occupationDown", "totalOccupation", "doubleOccupation", "localMoment", "kineticEnergy",
+             "potentialEnergy", "totalEnergy")
+    for i, name in enumerate(names):
+        got = _series(os.path.join(str(tmp_path), name + ".series"))
+        assert len(got) == 6 and np.allclose(got, g["scalars_c1"][:, i], rtol=2e-5, atol=2e-6), name
+    assert "libdqmc_b200" in open(os.path.join(str(tmp_path), "info.dat")).read()
+    assert any("spinzCorrelationFunction" in f for f in os.listdir(str(tmp_path)))
+
+
+@pytest.mark.parametrize("model", ["sdw", "hubbard"])
+def test_resume_continues_the_uninterrupted_run(tmp_path, model):
+    """saveState / resume through the reference's driver (detqmc.h:264-356): a run stopped after 4 of 8 sweeps and
+    resumed from its state file produces the same time series as an uninterrupted run -- the random numbers the
+    replica had drawn ahead of consumption are part of the checkpoint (dqmc_rng_look_ahead / dqmc_rng_set_look_ahead),
+    and so is the sweep counter that fixes the global-move schedule (dqmc_set_performed_sweeps)."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "host", "_build", "detqmcsdw_gpu" if model == "sdw" else "detqmchubbard_gpu")
+    if not os.path.exists(exe):
+        pytest.skip("host/_build not built (needs the reference tree: make -C host)")
+    common = (["L=4", "beta=2", "dtau=0.1", "s=10", "r=-1", "globalUpdateInterval=3"] if model == "sdw"
+              else ["L=4", "U=4", "beta=2", "dtau=0.1", "s=10", "mu=0.2"])
+    common += ["thermalization=4", "rngSeed=1020304050", "simindex=0"]
+    obs = "normMeanPhi" if model == "sdw" else "doubleOccupation"
+
+    def run(d, sweeps):
+        os.makedirs(d, exist_ok=True)
+        out = subprocess.run([exe] + common + ["sweeps=%d" % sweeps], cwd=d, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+        return out.stdout
+
+    a = os.path.join(str(tmp_path), "straight")
+    b = os.path.join(str(tmp_path), "resumed")
+    run(a, 8)
+    run(b, 4)
+    assert "will resume simulation" in run(b, 8)
+    sa, sb = _series(os.path.join(a, obs + ".series")), _series(os.path.join(b, obs + ".series"))
+    assert len(sa) == 8 and len(sb) == 8
+    assert np.allclose(sa, sb, rtol=0, atol=1e-9), (sa, sb)
+
+
 def test_hubbard_full_size_properties():
     """BASELINE config C5 (L=20, U=8, beta=20, m=200, s=10) at full size: properties that need no oracle --
     half-filling identity <n> = 1 for every auxiliary-field configuration, wrapped vs recomputed G at the

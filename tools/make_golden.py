@@ -106,6 +106,27 @@ def hubbard_fixture(name, sweeps, kw):
     print(name, "done")
 
 
+def hubbard_observables_fixture():
+    """DetHubbard::measure / finishMeasurements (dethubbard.cpp:511-612) of the reference over a few measured sweeps
+    after a short thermalisation, for BASELINE config C1 and an off-half-filling checkerboard case."""
+    d = {}
+    for tag, kw in (("c1", dict()), ("cb", dict(checkerboard=True, U=6.0, mu=0.3, m=24, s=5))):
+        p = HubbardParams(**kw)
+        r = rb.RefHubbard(p)
+        d["params_" + tag] = pars_json(p)
+        for _ in range(4):
+            r.sweep(True)
+        sc, zc = [], []
+        for _ in range(6):
+            a, b = r.measured_sweep()
+            sc.append(a)
+            zc.append(b)
+        d["scalars_" + tag], d["zcorr_" + tag] = np.array(sc), np.array(zc)
+        d["aux_final_" + tag] = r.aux()[1:]
+    np.savez_compressed(os.path.join(OUT, "hubbard_observables.npz"), **d)
+    print("hubbard_observables done")
+
+
 def exchange_fixture():
     gen = np.random.default_rng(7)
     rows = []
@@ -331,6 +352,9 @@ if __name__ == "__main__":
         observables_fixture()
         fermion_fixture()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "hubbard_observables":
+        hubbard_observables_fixture()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "woodbury":
         # (no fixture for updateMethod=iterative: the reference's updateInSlice_iterative corrupts the heap in this
         # build -- "double free or corruption" at teardown -- although its fields equal woodbury's sweep by sweep)
@@ -351,6 +375,7 @@ if __name__ == "__main__":
     sdw_fixture("sdw_o2_flux_L6", 2, dict(L=6, m=30, rngIndex=5), chain=(20, 10))
     hubbard_fixture("hubbard_L4_U4_b4", 6, dict())                      # BASELINE config C1
     hubbard_fixture("hubbard_L4_cb", 4, dict(checkerboard=True, U=6.0, mu=0.3, m=24, s=5))
+    hubbard_observables_fixture()
     config_stream_fixture()
     observables_fixture()
     fermion_fixture()

@@ -32,9 +32,9 @@ def build():
 
 
 def summarise(path):
-    win = re.compile(r"win dbg round (\d+) sites (\d+) acc (\d+): prologue (\d+) site (\d+) post (\d+) tail (\d+)")
+    win = re.compile(r"win dbg round (\d+) sites (\d+) acc (\d+): prologue (\d+) site (\d+) post (\d+) tail (\d+) wait (\d+)")
     bxy = re.compile(r"gth dbg round (\d+) (J) (\d+): coef (\d+) gload (\d+) product (\d+)")
-    w = [0] * 7
+    w = [0] * 8
     bx = {0: [0] * 5, 1: [0] * 5}
     for line in open(path):
         m = win.search(line)
@@ -43,7 +43,7 @@ def summarise(path):
             if v[1] == 0:
                 continue
             w[0] += 1
-            for i in range(1, 7):
+            for i in range(1, 8):
                 w[i] += v[i]
         m = bxy.search(line)
         if m:
@@ -58,8 +58,8 @@ def summarise(path):
         print("window kernel (warp 0 of replica 0): %d rounds, %d sites, %d accepted" % (w[0], sites, acc))
         print("  per round: prologue %.0f tail %.0f clocks" % (w[3] / w[0], w[6] / w[0]))
         print("  per site: proposal look-up + decision (incl. waiting for the diagonal blocks) %.0f clocks" % (w[4] / sites))
-        print("  per accepted site: hand-over %.0f clocks" % (w[5] / max(acc, 1)))
-        print("  total per site %.0f clocks" % (sum(w[3:7]) / sites))
+        print("  per accepted site: acceptance work %.0f clocks, waiting for the previous block update %.0f clocks" % (w[5] / max(acc, 1), w[7] / max(acc, 1)))
+        print("  total per site %.0f clocks" % (sum(w[3:8]) / sites))
     for side, t in bx.items():
         if t[0]:
             print("gather (side %d): %d launches, mean J %.1f: coef %.0f gload %.0f product %.0f clocks per launch"

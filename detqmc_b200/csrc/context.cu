@@ -10,6 +10,8 @@
 
 #include "dqmc_internal.h"
 
+#include <dlfcn.h>
+
 using namespace dqmc;
 
 namespace {
@@ -2139,6 +2141,18 @@ int dqmc_exchange_pack(dqmc_ctx* ctx, double* payload_dev, int n_uniforms) {
                                (long long)phi_stride(ctx), R, ctx->stream));
     double* uni = payload_dev + R;
     double* blobs = uni + n_uniforms;
+    if (!ctx->rngResident && n_uniforms > 8 * R + 16) {
+        ctx->err = "n_uniforms exceeds the staging buffer (8 R + 16 doubles)";
+        return DQMC_ERR_PARAM;
+    }
+    if (ctx->rngResident && !ctx->rngAuto && n_uniforms > 0) {
+        // explicitly preloaded window: the look-ahead must lie inside it (the cursor of replica 0 is on the device;
+        // the bound the host tracks is conservative)
+        if (ctx->rngResidentUsedBound + size_t(n_uniforms) > size_t(ctx->rngWindow)) {
+            ctx->err = "resident random-number window too small for the exchange look-ahead";
+            return DQMC_ERR_STATE;
+        }
+    }
     if (!ctx->rngResident && n_uniforms > 0) {
         const double* src = ctx->rng[0].peek((size_t)n_uniforms);
         std::memcpy(ctx->h_scalars, src, sizeof(double) * n_uniforms);      // h_scalars holds >= 8R+16 doubles
@@ -2167,6 +2181,58 @@ int dqmc_exchange_apply(dqmc_ctx* ctx, const double* r_new, const dqmc_control_d
     return DQMC_OK;
 }
 
+// ---- NCCL communicator injected by the host: the one collective of the path ---------------------
+// The library does not link NCCL: it takes ncclAllGather from the NCCL the host process already uses (so that the
+// communicator and the entry point come from the same library), or loads libnccl.so.2 if none is loaded.
+typedef int (*nccl_allgather_fn)(const void*, void*, size_t, int, void*, cudaStream_t);
+static nccl_allgather_fn resolve_nccl_allgather() {
+    static nccl_allgather_fn fn = nullptr;
+    if (fn) return fn;
+    void* sym = dlsym(RTLD_DEFAULT, "ncclAllGather");
+    if (!sym) {
+        void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (h) sym = dlsym(h, "ncclAllGather");
+    }
+    fn = reinterpret_cast<nccl_allgather_fn>(sym);
+    return fn;
+}
+
+int dqmc_set_comm(dqmc_ctx* ctx, void* nccl_comm, int nranks, int rank) {
+    if (!ctx || nranks < 1 || rank < 0 || rank >= nranks || (nranks > 1 && !nccl_comm)) return DQMC_ERR_PARAM;
+    if (nccl_comm && !resolve_nccl_allgather()) { ctx->err = "ncclAllGather not found (no NCCL in this process)"; return DQMC_ERR_STATE; }
+    ctx->comm = nccl_comm;
+    ctx->commRanks = nranks;
+    ctx->commRank = rank;
+    return DQMC_OK;
+}
+
+int dqmc_exchange_payload_len(dqmc_ctx* ctx, int n_uniforms) {
+    if (!ctx || n_uniforms < 0) return -1;
+    return ctx->R + n_uniforms + ctx->R * int(sizeof(dqmc_control_data) / sizeof(double));
+}
+
+// gather side of replicaExchangeStep (detqmcpt.h:968-1012) in one call: pack the local payload into its slot of
+// gathered_dev and all-gather in place on the context's stream; with gathered_host the result is copied back and the
+// call returns after the stream has drained
+int dqmc_exchange_allgather(dqmc_ctx* ctx, int n_uniforms, double* gathered_dev, double* gathered_host) {
+    if (!ctx || !gathered_dev || n_uniforms < 0) return DQMC_ERR_PARAM;
+    const int ranks = ctx->commRanks > 0 ? ctx->commRanks : 1, rank = ctx->commRanks > 0 ? ctx->commRank : 0;
+    const size_t len = size_t(dqmc_exchange_payload_len(ctx, n_uniforms));
+    RET(dqmc_exchange_pack(ctx, gathered_dev + size_t(rank) * len, n_uniforms));
+    if (ranks > 1 || ctx->comm) {
+        nccl_allgather_fn ag = resolve_nccl_allgather();
+        if (!ag) { ctx->err = "ncclAllGather not found"; return DQMC_ERR_STATE; }
+        const int rc = ag(gathered_dev + size_t(rank) * len, gathered_dev, len, /* ncclDouble */ 8, ctx->comm, ctx->stream);
+        if (rc != 0) { ctx->err = "ncclAllGather failed"; return DQMC_ERR_CUDA; }
+        ctx->launches += 1;
+    }
+    if (gathered_host) {
+        CK(cudaMemcpyAsync(gathered_host, gathered_dev, sizeof(double) * len * ranks, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return DQMC_OK;
+}
+
 double dqmc_exchange_probability(double par1, double action1, double par2, double action2) {
     const double delta = (par1 - par2) * (action2 - action1);
     return delta <= 0.0 ? 1.0 : std::exp(-delta);
@@ -2183,7 +2249,9 @@ int dqmc_exchange_walk(int n, const double* control_values, int32_t* par_process
         bool acc = prob >= 1.0;
         if (!acc) {
             if (!uniforms) return DQMC_ERR_PARAM;
-            acc = uniforms[used++] <= prob;
+            const double u = uniforms[used++];
+            if (!(u > 0.0 && u < 1.0)) return DQMC_ERR_STATE;      // beyond the look-ahead the owner packed (sentinel -1)
+            acc = u <= prob;
         }
         if (acc) {
             process_par[p1] = cpi2;

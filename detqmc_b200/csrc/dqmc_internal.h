@@ -233,6 +233,8 @@ struct dqmc_ctx {
     std::string err;
     uint64_t launches;
 
+    // NCCL communicator of the exchange step (dqmc_set_comm); nullptr = single process
+    void* comm = nullptr; int commRanks = 0, commRank = 0;
     // sweep state (detmodel.h:463, 481; detsdwopdim.h performedSweeps)
     int currentTimeslice;
     int lastSweepDir;      // +1 up, -1 down

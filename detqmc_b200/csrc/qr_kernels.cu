@@ -728,6 +728,382 @@ __global__ void __launch_bounds__(kPanelRegThreads) qr_panel_reg_kernel(cplx* Aa
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Panel factorisation, second generation: the 32-column panel is factored as four 8-column sub-panels.
+//
+//   * A sub-panel is a chain of eight column steps on eight warps (warp <-> column in registers, lane <-> row):
+//     reflector of the own column, one named barrier, one dot product + rank-1 update per warp.  Only the eight
+//     columns of the sub-panel take part, so a step costs a quarter of the instructions of the 32-column version
+//     and its latency is that of two warp reductions.
+//   * The remaining columns of the panel receive the sub-panel's block reflector  A -= V_s (T_s^H (V_s^H A))  on the
+//     FP64 tensor cores (DMMA m8n8k4), all sixteen warps, operands in shared memory.
+//   * The 32 x 32 compact-WY factor T is assembled from the sub-panel factors and the cross Gram blocks
+//     V_s^H V_t (DMMA), and V T is formed on the tensor cores as well.
+// Same interface and results (up to summation order) as qr_panel_reg_kernel: R and the reflectors in A, explicit unit
+// lower-trapezoidal V and V T in the workspace.
+// ------------------------------------------------------------------------------------------------
+constexpr int kP2Threads = 512;
+constexpr int kP2Sub = 8;                      // columns per sub-panel
+constexpr int kP2KSplit = 4;                   // row splits of the V_s^H A products
+
+__device__ __forceinline__ void dmma_qr(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+struct P2Layout {
+    int ldp;            // leading dimension of the panel (== 4 mod 8: conflict-free (column, 4 rows) fragment loads)
+    size_t P, vbuf, G, T, Zp, Zs, W, total;   // offsets in cplx elements
+};
+__host__ __device__ inline P2Layout p2_layout(int m) {
+    P2Layout l;
+    l.ldp = ((m + 7) & ~7) + 4;
+    size_t p = 0;
+    l.P = p;    p += size_t(32) * l.ldp;
+    l.vbuf = p; p += size_t(2) * ((m + 1) & ~1);
+    l.G = p;    p += 32 * 33;
+    l.T = p;    p += 32 * 33;
+    l.Zp = p;   p += size_t(kP2KSplit) * 3 * 64;     // partial 8 x 24 products (three 8 x 8 blocks per split)
+    l.Zs = p;   p += 8 * 24;
+    l.W = p;    p += 8 * 24;
+    l.total = p;
+    return l;
+}
+
+// element (row r, column c) of the unit lower-trapezoidal V held in the panel buffer (R sits on / above the diagonal)
+__device__ __forceinline__ cplx p2_vget(const cplx* P, int ldp, int r, int c, int m) {
+    cplx v = make_double2(0, 0);
+    if (r < m) {
+        v = P[size_t(c) * ldp + r];
+        if (r <= c) v = make_double2(r == c ? 1.0 : 0.0, 0.0);
+    }
+    return v;
+}
+
+template <int MAXT>
+__global__ void __launch_bounds__(kP2Threads) qr_panel2_kernel(cplx* Aall, long long strideA, int D, int j0, int nbc,
+                                                               cplx* Vall, cplx* VTall, long long strideV) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int m = D - j0;
+    const P2Layout lay = p2_layout(m);
+    const int ldp = lay.ldp;
+    cplx* sm = reinterpret_cast<cplx*>(smem_raw);
+    cplx* P = sm + lay.P;
+    cplx* vbuf = sm + lay.vbuf;
+    cplx* Gm = sm + lay.G;                       // [32][33] Gram matrix of the reflectors, strict upper part
+    cplx* Tm = sm + lay.T;                       // [32][33] compact-WY factor
+    cplx* Zp = sm + lay.Zp;
+    cplx* Zs = sm + lay.Zs;
+    cplx* Ws = sm + lay.W;
+    __shared__ cplx s_tau[32];
+
+    const int b = blockIdx.x;
+    cplx* A = Aall + size_t(b) * strideA;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int grp = lane >> 2, t4 = lane & 3;
+    const int mv = (m + 1) & ~1;
+
+    // ---- panel to shared memory (rows beyond m are never read: every fragment load is predicated on r < m)
+    for (int idx = tid; idx < nbc * m; idx += kP2Threads) {
+        const int c = idx / m, r = idx - c * m;
+        P[size_t(c) * ldp + r] = A[size_t(j0 + c) * D + j0 + r];
+    }
+    for (int i = tid; i < 32 * 33; i += kP2Threads) { Gm[i] = make_double2(0, 0); Tm[i] = make_double2(0, 0); }
+    __syncthreads();
+
+    for (int c0 = 0; c0 < nbc; c0 += kP2Sub) {
+        const int ns = min(kP2Sub, nbc - c0);                       // columns of this sub-panel
+        if (w < kP2Sub) {
+            // =========================================================== column steps of the sub-panel (8 warps)
+            // lane holds rows c0 + lane + 32 t of column c0 + w
+            cplx a[MAXT];
+            const bool live = w < ns;
+#pragma unroll
+            for (int t = 0; t < MAXT; ++t) {
+                const int r = c0 + lane + 32 * t;
+                a[t] = (live && r < m) ? P[size_t(c0 + w) * ldp + r] : make_double2(0, 0);
+            }
+            for (int cl = 0; cl < ns; ++cl) {
+                const int c = c0 + cl;
+                cplx* vb = vbuf + (cl & 1) * mv;
+                if (w == cl) {
+                    // reflector of the own column (zlarfg conventions); row c is lane cl, t = 0
+                    double xn = 0;
+#pragma unroll
+                    for (int t = 0; t < MAXT; ++t) {
+                        const int r = c0 + lane + 32 * t;
+                        const double n2 = fma(a[t].x, a[t].x, a[t].y * a[t].y);
+                        xn += (r > c && r < m) ? n2 : 0.0;
+                    }
+                    xn = warp_sum(xn);
+                    const double alr = __shfl_sync(0xffffffffu, a[0].x, cl);
+                    const double ali = __shfl_sync(0xffffffffu, a[0].y, cl);
+                    const bool trivial = xn == 0.0 && ali == 0.0;
+                    const double x2 = alr * alr + ali * ali + xn;
+                    const double inrm = trivial ? 0.0 : rsqrt(x2);
+                    const double nrm = x2 * inrm;
+                    const double beta = trivial ? alr : (alr >= 0 ? -nrm : nrm);
+                    const double ib = alr >= 0 ? -inrm : inrm;                        // 1 / beta
+                    const cplx tau = trivial ? make_double2(0, 0) : make_double2((beta - alr) * ib, -ali * ib);
+                    const double dr = alr - beta, di = ali;
+                    const double iden = trivial ? 0.0 : __drcp_rn(dr * dr + di * di);
+                    const cplx sc = make_double2(dr * iden, -di * iden);
+#pragma unroll
+                    for (int t = 0; t < MAXT; ++t) {
+                        const int r = c0 + lane + 32 * t;
+                        const cplx scaled = cmul(a[t], sc);
+                        const cplx vnew = r > c ? scaled : make_double2(r == c ? 1.0 : 0.0, 0.0);
+                        if (r < m) vb[r - c0] = vnew;
+                        a[t].x = r > c ? scaled.x : (r == c ? beta : a[t].x);         // row c keeps the R diagonal
+                        a[t].y = r > c ? scaled.y : (r == c ? 0.0 : a[t].y);
+                    }
+                    if (lane == 0) s_tau[c] = tau;
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                const cplx tau = s_tau[c];
+                if (w != cl && live && (tau.x != 0.0 || tau.y != 0.0)) {
+                    // dot = v_c^H x over rows >= c (v is zero above c); x = own column (w > cl) or own reflector (w < cl)
+                    double dr = 0, di = 0;
+                    cplx vv[MAXT];
+#pragma unroll
+                    for (int t = 0; t < MAXT; ++t) {
+                        const int r = c0 + lane + 32 * t;
+                        vv[t] = r < m ? vb[r - c0] : make_double2(0, 0);
+                        cplx x = a[t];
+                        if (w < cl) {                                                  // own reflector: unit diagonal, zero above
+                            const int cw = c0 + w;
+                            x = r > cw ? a[t] : make_double2(r == cw ? 1.0 : 0.0, 0.0);
+                        }
+                        dr = fma(vv[t].x, x.x, fma(vv[t].y, x.y, dr));
+                        di = fma(vv[t].x, x.y, fma(-vv[t].y, x.x, di));
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        dr += __shfl_xor_sync(0xffffffffu, dr, o);
+                        di += __shfl_xor_sync(0xffffffffu, di, o);
+                    }
+                    if (w > cl) {
+                        const cplx fw = cmul(make_double2(tau.x, -tau.y), make_double2(dr, di));   // conj(tau) (v^H a)
+#pragma unroll
+                        for (int t = 0; t < MAXT; ++t) {
+                            a[t].x -= fw.x * vv[t].x - fw.y * vv[t].y;
+                            a[t].y -= fw.x * vv[t].y + fw.y * vv[t].x;
+                        }
+                    } else if (lane == 0) {
+                        Gm[(c0 + w) * 33 + c] = make_double2(dr, -di);                 // v_w^H v_c = conj(v_c^H v_w)
+                    }
+                }
+                // compact-WY factor of the sub-panel, column cl - 1 (its Gram column was completed in the previous step)
+                if (cl > 0 && w == cl - 1) {
+                    const int cc = c - 1;
+                    const cplx tcc = s_tau[cc];
+                    if (lane == 0) Tm[cc * 33 + cc] = tcc;
+                    const int i = c0 + lane;
+                    if (i < cc) {
+                        cplx sacc = make_double2(0, 0);
+                        for (int l = i; l < cc; ++l) sacc = cfma_(Tm[i * 33 + l], Gm[l * 33 + cc], sacc);
+                        Tm[i * 33 + cc] = make_double2(-(tcc.x * sacc.x - tcc.y * sacc.y), -(tcc.x * sacc.y + tcc.y * sacc.x));
+                    }
+                }
+            }
+            if (live) {
+#pragma unroll
+                for (int t = 0; t < MAXT; ++t) {
+                    const int r = c0 + lane + 32 * t;
+                    if (r < m) P[size_t(c0 + w) * ldp + r] = a[t];
+                }
+            }
+        }
+        __syncthreads();
+        if (w == 0) {
+            const int cc = c0 + ns - 1;
+            const cplx tcc = s_tau[cc];
+            if (lane == 0) Tm[cc * 33 + cc] = tcc;
+            const int i = c0 + lane;
+            if (i < cc) {
+                cplx sacc = make_double2(0, 0);
+                for (int l = i; l < cc; ++l) sacc = cfma_(Tm[i * 33 + l], Gm[l * 33 + cc], sacc);
+                Tm[i * 33 + cc] = make_double2(-(tcc.x * sacc.x - tcc.y * sacc.y), -(tcc.x * sacc.y + tcc.y * sacc.x));
+            }
+        }
+        const int nrest = nbc - (c0 + ns);                          // panel columns to the right of the sub-panel
+        if (nrest <= 0) { __syncthreads(); break; }
+        const int nblk = (nrest + 7) / 8;
+        const int mloc = m - c0;                                    // rows c0 .. m-1 take part
+        const int nk4 = (mloc + 3) / 4;
+        const int k4per = (nk4 + kP2KSplit - 1) / kP2KSplit;
+        // ---- Z = V_s^H A_rest (8 x nrest): warp <-> (8-column block, row split), partial sums in shared memory
+        if (w < 3 * kP2KSplit) {
+            const int blk = w % 3, ks = w / 3;
+            if (blk < nblk) {
+                double zr0 = 0, zr1 = 0, zi0 = 0, zi1 = 0;
+                const int cv = c0 + grp;                            // A fragment: conj(V_s[k, i = grp])
+                const int cb = c0 + ns + blk * 8 + grp;             // B fragment: A_rest[k, n = grp]
+                const bool cbok = blk * 8 + grp < nrest, cvok = grp < ns;
+                for (int s4 = ks * k4per; s4 < min(nk4, (ks + 1) * k4per); ++s4) {
+                    const int r = c0 + 4 * s4 + t4;
+                    const cplx av = cvok ? p2_vget(P, ldp, r, cv, m) : make_double2(0, 0);
+                    const cplx bv = (cbok && r < m) ? P[size_t(cb) * ldp + r] : make_double2(0, 0);
+                    // conj(a) b = (ax bx + ay by) + i (ax by - ay bx)
+                    dmma_qr(zr0, zr1, av.x, bv.x);
+                    dmma_qr(zr0, zr1, av.y, bv.y);
+                    dmma_qr(zi0, zi1, av.x, bv.y);
+                    dmma_qr(zi0, zi1, -av.y, bv.x);
+                }
+                cplx* zp = Zp + (size_t(ks) * 3 + blk) * 64;        // [i = grp][n = 2 t4 + e]
+                zp[grp * 8 + 2 * t4] = make_double2(zr0, zi0);
+                zp[grp * 8 + 2 * t4 + 1] = make_double2(zr1, zi1);
+            }
+        }
+        __syncthreads();
+        // ---- fixed-order sum of the partial products, then W = T_s^H Z
+        if (tid < 8 * 24) {
+            const int i = tid / 24, n = tid - i * 24;
+            cplx z = make_double2(0, 0);
+            if (n < nrest && i < ns) {
+                const int blk = n >> 3, nn = n & 7;
+#pragma unroll
+                for (int ks = 0; ks < kP2KSplit; ++ks) {
+                    const cplx p = Zp[(size_t(ks) * 3 + blk) * 64 + i * 8 + nn];
+                    z.x += p.x;
+                    z.y += p.y;
+                }
+            }
+            Zs[i * 24 + n] = z;
+        }
+        __syncthreads();
+        if (tid < 8 * 24) {
+            const int i = tid / 24, n = tid - i * 24;
+            cplx wv = make_double2(0, 0);
+            if (i < ns)
+                for (int l = 0; l <= i; ++l) {                      // (T_s^H)[i, l] = conj(T_s[l, i])
+                    const cplx t = Tm[(c0 + l) * 33 + c0 + i];
+                    wv = cfmac_(t, Zs[l * 24 + n], wv);
+                }
+            Ws[i * 24 + n] = wv;
+        }
+        __syncthreads();
+        // ---- A_rest -= V_s W on the tensor cores: task = (8-row block, 8-column block)
+        {
+            const int nrb = (mloc + 7) / 8;
+            for (int task = w; task < nrb * nblk; task += kP2Threads / 32) {
+                const int rb = task / nblk, blk = task - rb * nblk;
+                const int r = c0 + rb * 8 + grp;                    // accumulator row
+                const int cn = c0 + ns + blk * 8 + 2 * t4;          // accumulator columns cn, cn + 1
+                const bool ok0 = r < m && blk * 8 + 2 * t4 < nrest, ok1 = r < m && blk * 8 + 2 * t4 + 1 < nrest;
+                cplx x0 = ok0 ? P[size_t(cn) * ldp + r] : make_double2(0, 0);
+                cplx x1 = ok1 ? P[size_t(cn + 1) * ldp + r] : make_double2(0, 0);
+#pragma unroll
+                for (int k4 = 0; k4 < kP2Sub; k4 += 4) {
+                    const int i = k4 + t4;                          // A fragment: -V_s[r, i]; B fragment: W[i, n = grp]
+                    cplx av = i < ns ? p2_vget(P, ldp, r, c0 + i, m) : make_double2(0, 0);
+                    av.x = -av.x; av.y = -av.y;
+                    const cplx bv = Ws[i * 24 + blk * 8 + grp];
+                    dmma_qr(x0.x, x1.x, av.x, bv.x);
+                    dmma_qr(x0.x, x1.x, -av.y, bv.y);
+                    dmma_qr(x0.y, x1.y, av.x, bv.y);
+                    dmma_qr(x0.y, x1.y, av.y, bv.x);
+                }
+                if (ok0) P[size_t(cn) * ldp + r] = x0;
+                if (ok1) P[size_t(cn + 1) * ldp + r] = x1;
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- cross Gram blocks G[s-block, t-block] = V_s^H V_t (s < t) on the tensor cores, two row splits each
+    {
+        const int nsub = (nbc + kP2Sub - 1) / kP2Sub;
+        const int npairs = nsub * (nsub - 1) / 2;                   // <= 6
+        const int nk4 = (m + 3) / 4, k4per = (nk4 + 1) / 2;
+        if (w < 2 * npairs) {
+            const int pr = w >> 1, ks = w & 1;
+            int sb = 0, tb = 1, cnt = pr;                           // pair index -> (s, t), s < t
+            while (cnt >= nsub - 1 - sb) { cnt -= nsub - 1 - sb; ++sb; tb = sb + 1; }
+            tb = sb + 1 + cnt;
+            double zr0 = 0, zr1 = 0, zi0 = 0, zi1 = 0;
+            const int ca = sb * 8 + grp, cb = tb * 8 + grp;
+            for (int s4 = ks * k4per; s4 < min(nk4, (ks + 1) * k4per); ++s4) {
+                const int r = 4 * s4 + t4;
+                const cplx av = ca < nbc ? p2_vget(P, ldp, r, ca, m) : make_double2(0, 0);
+                const cplx bv = cb < nbc ? p2_vget(P, ldp, r, cb, m) : make_double2(0, 0);
+                dmma_qr(zr0, zr1, av.x, bv.x);
+                dmma_qr(zr0, zr1, av.y, bv.y);
+                dmma_qr(zi0, zi1, av.x, bv.y);
+                dmma_qr(zi0, zi1, -av.y, bv.x);
+            }
+            cplx* zp = Zp + size_t(w) * 64;                         // 12 x 64 <= kP2KSplit * 3 * 64
+            zp[grp * 8 + 2 * t4] = make_double2(zr0, zi0);
+            zp[grp * 8 + 2 * t4 + 1] = make_double2(zr1, zi1);
+        }
+        __syncthreads();
+        for (int e = tid; e < npairs * 64; e += kP2Threads) {
+            const int pr = e >> 6, ii = (e >> 3) & 7, nn = e & 7;
+            int sb = 0, cnt = pr;
+            while (cnt >= nsub - 1 - sb) { cnt -= nsub - 1 - sb; ++sb; }
+            const int tb = sb + 1 + cnt;
+            const cplx p0 = Zp[size_t(2 * pr) * 64 + ii * 8 + nn], p1 = Zp[size_t(2 * pr + 1) * 64 + ii * 8 + nn];
+            if (sb * 8 + ii < nbc && tb * 8 + nn < nbc)
+                Gm[(sb * 8 + ii) * 33 + tb * 8 + nn] = make_double2(p0.x + p1.x, p0.y + p1.y);
+        }
+        __syncthreads();
+        // ---- off-diagonal blocks of T, block column by block column:  T[0:c0, c0:c0+8] = -T[0:c0, 0:c0] G[0:c0, c0:c0+8] T_tt
+        for (int tb = 1; tb < nsub; ++tb) {
+            const int c0 = tb * 8, nt = min(8, nbc - c0);
+            // X = G[0:c0, c0:c0+nt] T_tt   (into Zs-like scratch: reuse Zp, c0 x 8)
+            for (int e = tid; e < c0 * 8; e += kP2Threads) {
+                const int i = e >> 3, cc = e & 7;
+                cplx x = make_double2(0, 0);
+                if (cc < nt)
+                    for (int l = 0; l <= cc; ++l) x = cfma_(Gm[i * 33 + c0 + l], Tm[(c0 + l) * 33 + c0 + cc], x);
+                Zp[e] = x;
+            }
+            __syncthreads();
+            for (int e = tid; e < c0 * 8; e += kP2Threads) {
+                const int i = e >> 3, cc = e & 7;
+                if (cc < nt) {
+                    cplx x = make_double2(0, 0);
+                    for (int l = i; l < c0; ++l) x = cfma_(Tm[i * 33 + l], Zp[l * 8 + cc], x);
+                    Tm[i * 33 + c0 + cc] = make_double2(-x.x, -x.y);
+                }
+            }
+            __syncthreads();
+        }
+    }
+
+    // ---- write back: R (and v below it) to A, explicit V to the workspace
+    cplx* V = Vall + size_t(b) * strideV;
+    cplx* VT = VTall + size_t(b) * strideV;
+    for (int idx = tid; idx < nbc * m; idx += kP2Threads) {
+        const int c = idx / m, r = idx - c * m;
+        const cplx pv = P[size_t(c) * ldp + r];
+        A[size_t(j0 + c) * D + j0 + r] = pv;
+        V[size_t(j0 + c) * D + j0 + r] = r > c ? pv : make_double2(r == c ? 1.0 : 0.0, 0.0);
+    }
+    // ---- V T on the tensor cores: task = (8-row block, 8-column block), T upper triangular
+    {
+        const int nrb = (m + 7) / 8, ncb = (nbc + 7) / 8;
+        for (int task = w; task < nrb * ncb; task += kP2Threads / 32) {
+            const int rb = task / ncb, cb = task - rb * ncb;
+            const int r = rb * 8 + grp;
+            double xr0 = 0, xr1 = 0, xi0 = 0, xi1 = 0;
+            for (int k4 = 0; k4 < (cb + 1) * 8; k4 += 4) {
+                const int l = k4 + t4;                              // A fragment: V[r, l]; B fragment: T[l, c = cb 8 + grp]
+                const cplx av = l < nbc ? p2_vget(P, ldp, r, l, m) : make_double2(0, 0);
+                const cplx bv = (l < nbc && cb * 8 + grp < nbc) ? Tm[l * 33 + cb * 8 + grp] : make_double2(0, 0);
+                dmma_qr(xr0, xr1, av.x, bv.x);
+                dmma_qr(xr0, xr1, -av.y, bv.y);
+                dmma_qr(xi0, xi1, av.x, bv.y);
+                dmma_qr(xi0, xi1, av.y, bv.x);
+            }
+            const int cn = cb * 8 + 2 * t4;
+            if (r < m && cn < nbc) VT[size_t(j0 + cn) * D + j0 + r] = make_double2(xr0, xi0);
+            if (r < m && cn + 1 < nbc) VT[size_t(j0 + cn + 1) * D + j0 + r] = make_double2(xr1, xi1);
+        }
+    }
+}
+
 // inverse of every nb x nb diagonal block of the upper-triangular R (stored in A): out [batch][P][nb*nb]
 __global__ void trtri_blocks_kernel(const cplx* Aall, long long strideA, int D, int nb, cplx* outAll, long long strideOut) {
     __shared__ cplx Rs[32 * 33], Xs[32 * 33];
@@ -838,11 +1214,17 @@ cudaError_t qr_blocked_factor(QrWorkspace& ws, cplx* A, int D, long long strideA
     QR_TRY(cudaFuncSetAttribute(qr_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     QR_TRY(cudaFuncSetAttribute(qr_panel_reg_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)(smem + size_t(2) * D * sizeof(cplx))));
+    QR_TRY(cudaFuncSetAttribute(qr_panel2_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)(p2_layout(std::min(D, 320)).total * sizeof(cplx))));
     for (int j0 = 0; j0 < D; j0 += nb) {
         const int nbc = std::min(nb, D - j0), m = D - j0, n2 = D - j0 - nbc;
         const size_t sm = size_t(nbc) * (m | 1) * sizeof(cplx) + 2 * 32 * 33 * sizeof(cplx);
         static const bool force_smem_panel = std::getenv("DQMC_QR_SMEM_PANEL") != nullptr;
-        if (m <= 320 && nb == 32 && !force_smem_panel) {
+        static const bool old_reg_panel = std::getenv("DQMC_QR_REG_PANEL") != nullptr;
+        if (m <= 320 && nb == 32 && !force_smem_panel && !old_reg_panel) {
+            const size_t sm2 = p2_layout(m).total * sizeof(cplx);
+            qr_panel2_kernel<10><<<batch, kP2Threads, sm2, st>>>(A, strideA, D, j0, nbc, V, VT, (long long)dd);
+        } else if (m <= 320 && nb == 32 && !force_smem_panel) {
             qr_panel_reg_kernel<10><<<batch, kPanelRegThreads, sm + size_t(2) * m * sizeof(cplx), st>>>(A, strideA, D, j0, nbc, V,
                                                                                                   VT, (long long)dd);
         } else {

@@ -48,6 +48,9 @@ SYMBOLS = [
     ("dqmc_sweep_simple", c_i32, [c_vp, c_i32]),
     ("dqmc_get_fermionic_observables", c_i32, [c_vp, c_i32, c_vp, c_vp]),
     ("dqmc_get_hubbard_observables", c_i32, [c_vp, c_i32, c_vp, c_vp]),
+    ("dqmc_set_comm", c_i32, [c_vp, c_vp, c_i32, c_i32]),
+    ("dqmc_exchange_payload_len", c_i32, [c_vp, c_i32]),
+    ("dqmc_exchange_allgather", c_i32, [c_vp, c_i32, c_vp, c_vp]),
     ("dqmc_rng_look_ahead", c_i32, [c_vp, c_i32, c_vp, c_vp]),
     ("dqmc_rng_set_look_ahead", c_i32, [c_vp, c_i32, c_vp, ctypes.c_size_t]),
     ("dqmc_set_performed_sweeps", c_i32, [c_vp, c_u32]),

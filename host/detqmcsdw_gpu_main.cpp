@@ -7,6 +7,7 @@
 //
 //   detqmcsdw_gpu opdim=2 L=4 beta=2 dtau=0.1 s=10 r=-1 thermalization=20 sweeps=20 ...
 #include <cstdlib>
+#include <fstream>
 #include <iostream>
 #include <map>
 #include <string>
@@ -33,10 +34,18 @@ void take(std::map<std::string, std::string>& kv, S& specified, const char* key,
     specified.insert(key);
 }
 
+// a state file in the working directory resumes the simulation, as in maindetqmcsdwopdim.cpp:197-200, 320-340
 template <int OPDIM>
 int run(ModelParamsDetSDW& pm, DetQMCParams& pq) {
-    DetQMC<DetSDWGpu<OPDIM>, ModelParamsDetSDW> sim(pm, pq);
-    sim.run();
+    typedef DetQMC<DetSDWGpu<OPDIM>, ModelParamsDetSDW> Sim;
+    if (std::ifstream(pq.stateFileName.c_str())) {
+        std::cout << "Found simulation state file " << pq.stateFileName << ", will resume simulation" << std::endl;
+        Sim sim(pq.stateFileName, pq);
+        sim.run();
+    } else {
+        Sim sim(pm, pq);
+        sim.run();
+    }
     return 0;
 }
 }  // namespace

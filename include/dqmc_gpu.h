@@ -311,6 +311,15 @@ int dqmc_exchange_actions(dqmc_ctx* ctx, double* actions_dev, double* actions_ho
  *   payload[R+n_uniforms .. +R*105)      the control-data blobs (dqmc_control_data, 840 bytes each)
  * No host synchronisation. */
 int dqmc_exchange_pack(dqmc_ctx* ctx, double* payload_dev, int n_uniforms);
+/* The collective of the path (replaces the two mpi::gather of detqmcpt.h:971-1012).  dqmc_set_comm injects
+ * the host's NCCL communicator (an ncclComm_t, passed as void*; nranks / rank its geometry); the library resolves
+ * ncclAllGather from the NCCL the process has loaded, it does not link NCCL itself.  dqmc_exchange_allgather packs the
+ * local payload (layout of dqmc_exchange_pack, dqmc_exchange_payload_len doubles) into slot `rank` of gathered_dev
+ * [nranks * len] and all-gathers in place on the context's stream; gathered_host (may be NULL) receives a copy after
+ * the stream has drained.  Without a communicator (single process) it is dqmc_exchange_pack + the optional copy. */
+int dqmc_set_comm(dqmc_ctx* ctx, void* nccl_comm, int nranks, int rank);
+int dqmc_exchange_payload_len(dqmc_ctx* ctx, int n_uniforms);
+int dqmc_exchange_allgather(dqmc_ctx* ctx, int n_uniforms, double* gathered_dev, double* gathered_host);
 /* Scatter side of replicaExchangeStep (detqmcpt.h:1082-1115): install the new exchange parameter
  * and control data of every local replica and consume n_uniforms_used values from local replica
  * 0's stream (pass 0 on ranks that do not own ladder replica 0). */

@@ -41,7 +41,7 @@ namespace dqmc {
 // index: (((band*2 + sign_idx)*2 + pass) * 8 + component) * nplaq + q
 // pass 0: subgroup 1, half step; pass 1: subgroup 0, full step times e^{-+dtau mu_band}.
 // Plaquette q of subgroup g sits at x = 2*(q % (L/2)) + g, y = 2*(q / (L/2)) + g.
-int cb_table_count(const CbGeom& g) { return 2 * 2 * 2 * g.nplaq * 8; }
+int cb_table_count(const CbGeom& g) { return 2 * 2 * 3 * g.nplaq * 8; }
 
 namespace {
 
@@ -166,14 +166,16 @@ void cb_build_shift_matrices(const dqmc_params& p, int msf, std::vector<cplx>& S
 
 void cb_build_tables(const dqmc_params& p, std::vector<cplx>& out) {
     const int L = p.L, N = L * L, nplaq = N / 4, half = L / 2;
-    out.assign(size_t(2) * 2 * 2 * nplaq * 8, make_double2(0, 0));
+    // passes: 0 = subgroup 1, half step; 1 = subgroup 0, full step with the chemical potential; 2 = subgroup 0, half
+    // step without it (second factor of shiftGreenSymmetric, detsdwopdim.cpp:4505-4612)
+    out.assign(size_t(2) * 2 * 3 * nplaq * 8, make_double2(0, 0));
     for (int band = 0; band < 2; ++band) {
         const double mu = band == 0 ? p.mux : p.muy;
         for (int si = 0; si < 2; ++si) {
             const double sign = si == 0 ? -1.0 : +1.0;
-            for (int pass = 0; pass < 2; ++pass) {
+            for (int pass = 0; pass < 3; ++pass) {
                 const int subgroup = pass == 0 ? 1 : 0;
-                const double pf = sign * p.dtau * (pass == 0 ? 0.5 : 1.0);
+                const double pf = sign * p.dtau * (pass == 1 ? 1.0 : 0.5);
                 const double ovfac = pass == 1 ? std::exp(-sign * p.dtau * mu) : 1.0;
                 for (int q = 0; q < nplaq; ++q) {
                     const int i1 = 2 * (q % half) + subgroup;     // x
@@ -181,7 +183,7 @@ void cb_build_tables(const dqmc_params& p, std::vector<cplx>& out) {
                     zc M[16];
                     plaquette_matrix(p, band, i1, i2, pf, M);
                     // exp of a Hermitian block is Hermitian; symmetrise the round-off and compress
-                    cplx* dst = out.data() + ((size_t(band) * 2 + si) * 2 + pass) * 8 * nplaq + q;
+                    cplx* dst = out.data() + ((size_t(band) * 2 + si) * 3 + pass) * 8 * nplaq + q;
                     double dg[4];
                     for (int r = 0; r < 4; ++r) dg[r] = M[r * 4 + r].real() * ovfac;
                     dst[0 * nplaq] = make_double2(dg[0], dg[1]);
@@ -274,10 +276,10 @@ __device__ __forceinline__ void hopping_pass(cplx* tile, int ldt, int nv, const 
         const int q = p - bs * g.nplaq;
         const int band = bs & 1;       // XUP, YDOWN, XDOWN, YUP -> x, y, x, y
         PlaqMat<REALM> M;
-        M.load(tab + ((size_t(band) * 2 + sign_idx) * 2 + pass) * 8 * g.nplaq + q, g.nplaq, transposed != 0);
+        M.load(tab + ((size_t(band) * 2 + sign_idx) * 3 + pass) * 8 * g.nplaq + q, g.nplaq, transposed != 0);
         int oi, oj, ok, ol;
         const int base = bs * g.N;
-        if (pass == 1) {               // subgroup 0: (even, even) corner
+        if (pass >= 1) {               // subgroup 0: (even, even) corner
             oi = base + q; oj = oi + sh.quarter; ok = oj + sh.quarter; ol = ok + sh.quarter;
         } else {                       // subgroup 1: (odd, odd) corner, neighbours wrap around
             const int py = q / sh.half, px = q - py * sh.half;
@@ -305,6 +307,16 @@ __device__ __forceinline__ void hopping_stage(cplx* tile, int ldt, int nv, const
     hopping_pass<MSF, REALM>(tile, ldt, nv, tab, g, sh, sign_idx, transposed, 1);
     __syncthreads();
     hopping_pass<MSF, REALM>(tile, ldt, nv, tab, g, sh, sign_idx, transposed, 0);
+    __syncthreads();
+}
+
+// half-step stage of shiftGreenSymmetric (detsdwopdim.cpp:4505-4612): E1(h) then E0(h), no chemical potential
+template <int MSF, bool REALM>
+__device__ __forceinline__ void shift_stage(cplx* tile, int ldt, int nv, const cplx* __restrict__ tab, const CbGeom& g,
+                                            const CbShape& sh, int sign_idx, int transposed) {
+    hopping_pass<MSF, REALM>(tile, ldt, nv, tab, g, sh, sign_idx, transposed, 0);
+    __syncthreads();
+    hopping_pass<MSF, REALM>(tile, ldt, nv, tab, g, sh, sign_idx, transposed, 2);
     __syncthreads();
 }
 
@@ -345,6 +357,7 @@ __device__ __forceinline__ void potential_apply(cplx* t, int N, int pos, const P
 
 template <int MSF, bool REALM>
 __global__ void __launch_bounds__(kCbMaxThreads) cb_mult_kernel(CbGeom g, CbLaunch a, CbShape sh) {
+    pdl_enter();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int D = g.D, N = g.N;
     const int ldt = D + 1;
@@ -412,7 +425,8 @@ __global__ void __launch_bounds__(kCbMaxThreads) cb_mult_kernel(CbGeom g, CbLaun
 
     // potential stage: item = (site position, vector group)
     const int pot_items = N * sh.Gp;
-    for (int step = 0; step < a.kcount; ++step) {
+    if (a.shift) shift_stage<MSF, REALM>(tile, ldt, nv, a.cbtab, g, sh, a.sign_idx, a.transposed);
+    for (int step = 0; step < (a.shift ? 0 : a.kcount); ++step) {
         const int k = a.kfirst + step * a.kstep;
         const double* phi_k = phi + size_t(k) * g.opdim * N;
         const double* cosh_k = coshT + size_t(k) * N;
@@ -435,7 +449,8 @@ __global__ void __launch_bounds__(kCbMaxThreads) cb_mult_kernel(CbGeom g, CbLaun
         if (!a.k_then_v) hopping_stage<MSF, REALM>(tile, ldt, nv, a.cbtab, g, sh, a.sign_idx, a.transposed);
     }
 
-    // ---- store
+    // ---- store (in place unless an output matrix is given)
+    if (a.out) A = a.out + size_t(b) * a.strideOut;
     if (!a.rows) {
         const double* cs = a.colscale ? a.colscale + size_t(b) * a.strideScale : nullptr;
         if (nv == kCbTileVecs) {
@@ -497,7 +512,7 @@ cudaError_t cb_launch(const CbGeom& g, const CbLaunch& a, cudaStream_t st) {
         cudaError_t e = cudaFuncSetAttribute(cb_mult_kernel<MSF, RM>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                              (int)smem);                                                      \
         if (e != cudaSuccess) return e;                                                                       \
-        cb_mult_kernel<MSF, RM><<<grid, nthreads, smem, st>>>(g, a, sh);                                      \
+        launch_pdl(cb_mult_kernel<MSF, RM>, dim3(grid), dim3(nthreads), smem, st, g, a, sh);                                      \
     }
     if (g.msf == 2) {
         if (realm) CB_LAUNCH(2, true) else CB_LAUNCH(2, false)

@@ -962,21 +962,15 @@ int fm_prepare(dqmc_ctx* ctx) {
         CK(dmalloc(&ctx->fmAcc, ctx->fmAccLen * ctx->R));
         return DQMC_OK;
     }
-    std::vector<cplx> SL, SR;
-    cb_build_shift_matrices(ctx->p, ctx->msf, SL, SR);
-    CK(dmalloc(&ctx->shiftL, SL.size()));
-    CK(dmalloc(&ctx->shiftR, SR.size()));
-    CK(cudaMemcpy(ctx->shiftL, SL.data(), SL.size() * sizeof(cplx), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(ctx->shiftR, SR.data(), SR.size() * sizeof(cplx), cudaMemcpyHostToDevice));
     ctx->fmAccLen = fm_acc_len(ctx);
     CK(dmalloc(&ctx->fmAcc, ctx->fmAccLen * ctx->R));
     return DQMC_OK;
 }
 
-// measure(k) for the replicas of the current lane: gs = shiftGreenSymmetric(G) as two products with the block-diagonal
-// half-step hopping matrices (:4505-4612), then the accumulation kernel
+// measure(k) for the replicas of the current lane: gs = shiftGreenSymmetric(G) (:4505-4612) as two sparse checkerboard
+// passes of cb_mult_kernel (half-step factors from the left and from the right), then the accumulation kernel
 int measure_slice(dqmc_ctx* ctx) {
-    const int ro = ctx->laneOff, rc = ctx->laneCnt, D = ctx->D;
+    const int ro = ctx->laneOff, rc = ctx->laneCnt;
     const size_t dd = DD(ctx);
     if (ctx->p.model == DQMC_MODEL_HUBBARD) {            // dethubbard.cpp:511-539
         CKL(hub_measure_launch(ctx->G + size_t(2 * ro) * dd, (long long)dd, ctx->N, ctx->p.L,
@@ -984,23 +978,26 @@ int measure_slice(dqmc_ctx* ctx) {
         return DQMC_OK;
     }
     cplx* G = ctx->G + size_t(ro) * dd;
-    cplx* T = ctx->W[0] + size_t(ro) * dd;
     cplx* gs = ctx->W[1] + size_t(ro) * dd;
-    GemmArgs g;
-    g.M = g.N = g.K = D;
-    g.transa = g.transb = 0;
-    g.rowscale = g.colscale = g.kscale = nullptr;
-    g.strideRow = g.strideCol = g.strideK = 0;
-    g.alpha = 1.0; g.beta = 0.0; g.kvec = nullptr; g.b_kmajor = 0;
-    g.batch = rc;
-    g.A = G; g.lda = D; g.strideA = (long long)dd;
-    g.B = ctx->shiftR; g.ldb = D; g.strideB = 0;
-    g.C = T; g.ldc = D; g.strideC = (long long)dd;
-    CKL(gemm_launch(g, ctx->stream));
-    g.A = ctx->shiftL; g.strideA = 0;
-    g.B = T; g.strideB = (long long)dd;
-    g.C = gs;
-    CKL(gemm_launch(g, ctx->stream));
+    // gs = E0(-h) E1(-h) G E1(+h) E0(+h), h = dtau / 2: two checkerboard passes (the first one out of place)
+    CbLaunch a;
+    a.A = G; a.strideA = (long long)dd;
+    a.phi = ctx->phi + size_t(ro) * phi_stride(ctx);
+    a.coshT = ctx->coshT + size_t(ro) * tab_stride(ctx);
+    a.sinhT = ctx->sinhT + size_t(ro) * tab_stride(ctx);
+    a.stridePhi = (long long)phi_stride(ctx); a.strideTab = (long long)tab_stride(ctx);
+    a.cbtab = ctx->cbtab;
+    a.real_tables = ctx->p.weakZflux ? 0 : 1;
+    a.kfirst = 1; a.kstep = 1; a.kcount = 1;
+    a.rows = 0; a.k_then_v = 1; a.sign_idx = 0; a.transposed = 0;
+    a.colscale = nullptr; a.strideScale = 0;
+    a.batch = rc;
+    a.shift = 1;
+    a.out = gs; a.strideOut = (long long)dd;
+    CKL(cb_launch(ctx->geom, a, ctx->stream));
+    a.A = gs; a.out = nullptr;
+    a.rows = 1; a.sign_idx = 1; a.transposed = 1;
+    CKL(cb_launch(ctx->geom, a, ctx->stream));
     CKL(launch_fermion_measure(gs, (long long)dd, ctx->N, ctx->p.L, ctx->msf, ctx->fmAcc + size_t(ro) * ctx->fmAccLen,
                                (long long)ctx->fmAccLen, rc, ctx->stream));
     return DQMC_OK;
@@ -1238,6 +1235,7 @@ int dqmc_create(const dqmc_params* params, int n_replicas, int device, dqmc_ctx*
         // bound kernels of one replica overlap with the throughput-bound kernels of the others
         int want = std::min(ctx->R, DQMC_MAX_LANES);
         gemm_set_matrices_in_flight(ctx->R * ctx->ngc);
+        pdl_set_enabled(ctx->R * ctx->ngc <= 16);
         if (const char* e = std::getenv("DQMC_LANES")) want = std::atoi(e);
         want = std::max(1, std::min(want, std::min(DQMC_MAX_LANES, ctx->R)));
         ctx->nlanes = want;

@@ -14,6 +14,35 @@
 #define DQMC_MAX_LANES 64
 
 namespace dqmc {
+// ------------------------------------------------------------------------------------------------
+// Programmatic dependent launch.  A sweep is a chain of ~5000 small dependent kernels per replica; with few replicas
+// per GPU the hand-over from one kernel to the next (2-3 us inside a CUDA graph) is a sizeable part of the step.
+// Every kernel of the library starts with pdl_enter(): wait for the predecessor's results, then allow the successor
+// to be scheduled, so that the successor's launch and prologue overlap this kernel's execution.  The attribute is set
+// only when pdl_enabled() (few matrices in flight: the pre-launched CTAs hold SM resources that a large batch would
+// rather use for other lanes); without it griddepcontrol.* are no-ops.
+// ------------------------------------------------------------------------------------------------
+bool pdl_enabled();
+void pdl_set_enabled(bool on);
+__device__ __forceinline__ void pdl_enter() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 
 typedef double2 cplx;
 
@@ -45,6 +74,9 @@ struct CbLaunch {
     const double* colscale;  // optional [batch][D]: scale vector v (column v) by colscale[v] on store
     long long strideScale;
     int batch;
+    int shift = 0;           // 1: half-step stage of shiftGreenSymmetric (E1 then E0 at +-dtau/2, no potential) instead of B
+    cplx* out = nullptr;     // optional output matrices (default: in place)
+    long long strideOut = 0;
 };
 
 int cb_table_count(const CbGeom& g);                    // number of cplx in the table

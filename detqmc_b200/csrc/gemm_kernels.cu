@@ -43,6 +43,7 @@ struct GemmCfg {
 
 template <int WM, int WN, int MB, int NB>
 __global__ void __launch_bounds__(32 * WM * WN) zgemm_dmma_kernel(GemmArgs g) {
+    pdl_enter();
     typedef GemmCfg<WM, WN, MB, NB> C;
     extern __shared__ __align__(16) double smem[];
     const int tid = threadIdx.x;
@@ -210,6 +211,7 @@ constexpr int KT = 32;
 template <int WM, int WN, int MB, int NB>
 __global__ void __launch_bounds__(32 * WM * WN, (WM * WN <= 4 ? 3 : (WM * WN <= 8 ? 2 : 1)))
 zgemm_rank_update_kernel(GemmArgs g) {
+    pdl_enter();
     constexpr int TM = 8 * MB * WM, TN = 8 * NB * WN, LDM = TM + 4, LDN = TN + 4, NT = 32 * WM * WN;
     extern __shared__ __align__(16) double smem[];
     double* As_re = smem;
@@ -328,7 +330,7 @@ cudaError_t launch_rank_update(const GemmArgs& g, cudaStream_t st) {
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid((g.M + TM - 1) / TM, (g.N + TN - 1) / TN, g.batch);
-    zgemm_rank_update_kernel<WM, WN, MB, NB><<<grid, 32 * WM * WN, smem, st>>>(g);
+    launch_pdl(zgemm_rank_update_kernel<WM, WN, MB, NB>, dim3(grid), dim3(32 * WM * WN), smem, st, g);
     return cudaGetLastError();
 }
 
@@ -340,7 +342,7 @@ cudaError_t launch_cfg(const GemmArgs& g, cudaStream_t st) {
                                          (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid((g.M + C::TM - 1) / C::TM, (g.N + C::TN - 1) / C::TN, g.batch);
-    zgemm_dmma_kernel<WM, WN, MB, NB><<<grid, C::NT, smem, st>>>(g);
+    launch_pdl(zgemm_dmma_kernel<WM, WN, MB, NB>, dim3(grid), dim3(C::NT), smem, st, g);
     return cudaGetLastError();
 }
 
@@ -351,6 +353,14 @@ cudaError_t launch_cfg(const GemmArgs& g, cudaStream_t st) {
 // launch, same arithmetic in the same order (results do not depend on the tile shape).
 static int g_matrices_in_flight = 1 << 30;
 void gemm_set_matrices_in_flight(int n) { g_matrices_in_flight = n > 0 ? n : 1 << 30; }
+
+// programmatic dependent launch (dqmc_internal.h): on for small batches unless DQMC_PDL=0 / 1 says otherwise
+static bool g_pdl = false;
+bool pdl_enabled() { return g_pdl; }
+void pdl_set_enabled(bool on) {
+    static const char* env = std::getenv("DQMC_PDL");
+    g_pdl = env ? std::atoi(env) != 0 : on;
+}
 
 cudaError_t gemm_launch(const GemmArgs& g, cudaStream_t st) {
     if (g.batch <= 0 || g.M <= 0 || g.N <= 0) return cudaSuccess;

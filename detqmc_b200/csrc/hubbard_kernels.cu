@@ -145,6 +145,7 @@ namespace {
 // out[mat][i] = exp(sign * sigma(gc) * alpha * aux[rep][k][i]),  mat = off + blockIdx.y, rep = mat / 2
 __global__ void hub_scales_kernel(const int32_t* aux, long long strideAux, int N, int k, double alpha, double sign,
                                   double* out, int off) {
+    pdl_enter();
     const int mat = off + blockIdx.y;
     const int rep = mat >> 1, gc = mat & 1;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -155,10 +156,12 @@ __global__ void hub_scales_kernel(const int32_t* aux, long long strideAux, int N
 }
 
 __global__ void hub_real_part_kernel(const cplx* in, double* out, size_t n) {
+    pdl_enter();
     const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i < n) out[i] = in[i].x;
 }
 __global__ void hub_to_complex_kernel(const double* in, cplx* out, size_t n) {
+    pdl_enter();
     const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i < n) out[i] = make_double2(in[i], 0.0);
 }
@@ -171,6 +174,7 @@ __global__ void __launch_bounds__(1024) hub_update_slice_kernel(cplx* Gall, long
                                                                 const double* rngAll, long long strideRng, int rngWindow,
                                                                 int* cursorAll, uint32_t* acceptedAll,
                                                                 unsigned long long* acceptedTotal, int* errflag) {
+    pdl_enter();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* colU = reinterpret_cast<double*>(smem_raw);     // [N] G_up[:, site]
     double* rowU = colU + N;                                // [N] factor * (1 - G_up)[site, :]
@@ -252,6 +256,7 @@ __global__ void __launch_bounds__(1024) hub_update_slice_kernel(cplx* Gall, long
 // One CTA per replica; the block sums are reduced in a fixed order (deterministic).
 __global__ void __launch_bounds__(256) hub_measure_kernel(const cplx* Gall, long long strideG, int N, int L, double* accAll,
                                                           long long strideAcc) {
+    pdl_enter();
     __shared__ double part[5][256];
     const int b = blockIdx.x, tid = threadIdx.x;
     const cplx* Gu = Gall + size_t(2 * b) * strideG;
@@ -297,16 +302,16 @@ __global__ void __launch_bounds__(256) hub_measure_kernel(const cplx* Gall, long
 cudaError_t hub_scales_launch(const int32_t* aux, long long strideAux, int N, int k, double alpha, double sign,
                               double* out, int off, int batch, cudaStream_t st) {
     dim3 grid((N + 127) / 128, batch);
-    hub_scales_kernel<<<grid, 128, 0, st>>>(aux, strideAux, N, k, alpha, sign, out, off);
+    launch_pdl(hub_scales_kernel, dim3(grid), dim3(128), 0, st, aux, strideAux, N, k, alpha, sign, out, off);
     return cudaGetLastError();
 }
 
 cudaError_t hub_real_part_launch(const cplx* in, double* out, size_t n, cudaStream_t st) {
-    hub_real_part_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, out, n);
+    launch_pdl(hub_real_part_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, in, out, n);
     return cudaGetLastError();
 }
 cudaError_t hub_to_complex_launch(const double* in, cplx* out, size_t n, cudaStream_t st) {
-    hub_to_complex_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, out, n);
+    launch_pdl(hub_to_complex_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, in, out, n);
     return cudaGetLastError();
 }
 
@@ -316,14 +321,14 @@ cudaError_t hub_update_slice_launch(cplx* G, long long strideG, int N, int32_t* 
                                     cudaStream_t st) {
     const size_t smem = size_t(4) * N * sizeof(double);
     const int threads = N >= 256 ? 1024 : 256;
-    hub_update_slice_kernel<<<batch, threads, smem, st>>>(G, strideG, N, aux, strideAux, k, alpha, rng, strideRng,
+    launch_pdl(hub_update_slice_kernel, dim3(batch), dim3(threads), smem, st, G, strideG, N, aux, strideAux, k, alpha, rng, strideRng,
                                                           rngWindow, cursor, accepted, acceptedTotal, errflag);
     return cudaGetLastError();
 }
 
 cudaError_t hub_measure_launch(const cplx* G, long long strideG, int N, int L, double* acc, long long strideAcc, int batch,
                                cudaStream_t st) {
-    hub_measure_kernel<<<batch, 256, 0, st>>>(G, strideG, N, L, acc, strideAcc);
+    launch_pdl(hub_measure_kernel, dim3(batch), dim3(256), 0, st, G, strideG, N, L, acc, strideAcc);
     return cudaGetLastError();
 }
 

@@ -29,6 +29,7 @@ __device__ __forceinline__ double block_reduce(double v, double* red) {
 }
 
 __global__ void set_identity_kernel(cplx* A, int D, long long stride) {
+    pdl_enter();
     cplx* a = A + size_t(blockIdx.y) * stride;
     const size_t idx = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (idx >= size_t(D) * D) return;
@@ -37,6 +38,7 @@ __global__ void set_identity_kernel(cplx* A, int D, long long stride) {
 }
 
 __global__ void conj_transpose_kernel(const cplx* A, cplx* B, int D, long long stride) {
+    pdl_enter();
     __shared__ cplx tile[32][33];
     const cplx* a = A + size_t(blockIdx.z) * stride;
     cplx* bm = B + size_t(blockIdx.z) * stride;
@@ -59,6 +61,7 @@ __global__ void conj_transpose_kernel(const cplx* A, cplx* B, int D, long long s
 // B[j, i] = rowscale[j] * conj(A[i, j])   (separate batch strides; strideA = 0 shares one input)
 __global__ void scaled_conj_transpose_kernel(const cplx* A, long long strideA, cplx* B, long long strideB,
                                              const double* rowscale, long long strideS, int D) {
+    pdl_enter();
     __shared__ cplx tile[32][33];
     const cplx* a = A + size_t(blockIdx.z) * strideA;
     cplx* bm = B + size_t(blockIdx.z) * strideB;
@@ -80,6 +83,7 @@ __global__ void scaled_conj_transpose_kernel(const cplx* A, long long strideA, c
 }
 
 __global__ void max_abs_diff_kernel(const cplx* A, const cplx* B, int D, long long stride, double* out) {
+    pdl_enter();
     __shared__ double red[32];
     const cplx* a = A + size_t(blockIdx.x) * stride;
     const cplx* b = B + size_t(blockIdx.x) * stride;
@@ -95,6 +99,7 @@ __global__ void max_abs_diff_kernel(const cplx* A, const cplx* B, int D, long lo
 // coshTermPhi / sinhTermPhi for every (slice >= 1, site)   (detsdwopdim.cpp:1131-1136, 1174-1181)
 __global__ void update_tables_kernel(const double* phi, double* coshT, double* sinhT, int N, int opdim, int m,
                                      double lambda_dtau, long long stridePhi, long long strideTab) {
+    pdl_enter();
     const int b = blockIdx.y;
     const size_t idx = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (idx >= size_t(m) * N) return;
@@ -109,6 +114,7 @@ __global__ void update_tables_kernel(const double* phi, double* coshT, double* s
 
 // addGlobalRandomDisplacement (detsdwopdim.cpp:3755-3763): every slice INCLUDING the unused k = 0
 __global__ void shift_fields_kernel(double* phi, const double* shift, int N, int opdim, int m, long long stridePhi) {
+    pdl_enter();
     const int b = blockIdx.y;
     const size_t idx = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (idx >= size_t(m + 1) * opdim * N) return;
@@ -119,6 +125,7 @@ __global__ void shift_fields_kernel(double* phi, const double* shift, int N, int
 // phiAction (detsdwopdim.cpp:4242-4299), one CTA per replica, fixed reduction order
 __global__ void phi_action_kernel(const double* phi, const double* rvals, double* out, int L, int opdim, int m,
                                   double dtau, double c, double u, long long stridePhi) {
+    pdl_enter();
     __shared__ double red[32];
     const int b = blockIdx.x;
     const int N = L * L;
@@ -150,6 +157,7 @@ __global__ void phi_action_kernel(const double* phi, const double* rvals, double
 // out[((ix*L + iy)*m + (k-1))*opdim + dim] = phi(site = iy*L + ix, dim, k), k = 1..m; one CTA row per replica.
 __global__ void config_stream_kernel(const double* __restrict__ phi, double* __restrict__ out, int L, int opdim, int m,
                                      long long stridePhi, long long strideOut) {
+    pdl_enter();
     const int N = L * L;
     const double* p = phi + size_t(blockIdx.y) * stridePhi;
     double* o = out + size_t(blockIdx.y) * strideOut;
@@ -167,6 +175,7 @@ __global__ void config_stream_kernel(const double* __restrict__ phi, double* __r
 // get_exchange_action_contribution (detsdwopdim.cpp:5204-5216)
 __global__ void exchange_action_kernel(const double* phi, double* out, int N, int opdim, int m, double dtau,
                                        long long stridePhi) {
+    pdl_enter();
     __shared__ double red[32];
     const int b = blockIdx.x;
     const double* ph = phi + size_t(b) * stridePhi + size_t(opdim) * N;     // skip slice 0
@@ -180,6 +189,7 @@ __global__ void exchange_action_kernel(const double* phi, double* out, int N, in
 // (resident mode), and the control-data blobs of all local replicas
 __global__ void exchange_pack_kernel(const double* rng, const int* cursor, int window, double* uni_out, int n_uni,
                                      const dqmc_control_data* ctrl, double* ctrl_out, int R, int copy_uniforms) {
+    pdl_enter();
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int nth = gridDim.x * blockDim.x;
     if (copy_uniforms) {
@@ -190,8 +200,10 @@ __global__ void exchange_pack_kernel(const double* rng, const int* cursor, int w
     const double* src = reinterpret_cast<const double*>(ctrl);
     for (int i = tid; i < R * words; i += nth) ctrl_out[i] = src[i];
 }
-__global__ void cursor_advance_kernel(int* cursor, int rep, int n) { cursor[rep] += n; }
+__global__ void cursor_advance_kernel(int* cursor, int rep, int n) {
+    pdl_enter(); cursor[rep] += n; }
 __global__ void cursor_add_kernel(int* cursor, const int* add, int n) {
+    pdl_enter();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) cursor[i] += add[i];
 }
@@ -201,67 +213,67 @@ __global__ void cursor_add_kernel(int* cursor, const int* add, int n) {
 cudaError_t launch_exchange_pack(const double* rng, const int* cursor, int window, double* uni_out, int n_uni,
                                  const dqmc_control_data* ctrl, double* ctrl_out, int R, int copy_uniforms,
                                  cudaStream_t st) {
-    exchange_pack_kernel<<<8, 256, 0, st>>>(rng, cursor, window, uni_out, n_uni, ctrl, ctrl_out, R, copy_uniforms);
+    launch_pdl(exchange_pack_kernel, dim3(8), dim3(256), 0, st, rng, cursor, window, uni_out, n_uni, ctrl, ctrl_out, R, copy_uniforms);
     return cudaGetLastError();
 }
 cudaError_t launch_cursor_add(int* cursor, const int* add, int n, cudaStream_t st) {
-    cursor_add_kernel<<<(n + 127) / 128, 128, 0, st>>>(cursor, add, n);
+    launch_pdl(cursor_add_kernel, dim3((n + 127) / 128), dim3(128), 0, st, cursor, add, n);
     return cudaGetLastError();
 }
 cudaError_t launch_cursor_advance(int* cursor, int rep, int n, cudaStream_t st) {
-    cursor_advance_kernel<<<1, 1, 0, st>>>(cursor, rep, n);
+    launch_pdl(cursor_advance_kernel, dim3(1), dim3(1), 0, st, cursor, rep, n);
     return cudaGetLastError();
 }
 
 cudaError_t launch_set_identity(cplx* A, int D, long long stride, int batch, cudaStream_t st) {
     dim3 grid((unsigned)((size_t(D) * D + 255) / 256), batch);
-    set_identity_kernel<<<grid, 256, 0, st>>>(A, D, stride);
+    launch_pdl(set_identity_kernel, dim3(grid), dim3(256), 0, st, A, D, stride);
     return cudaGetLastError();
 }
 cudaError_t launch_scaled_conj_transpose(const cplx* A, long long strideA, cplx* B, long long strideB,
                                          const double* rowscale, long long strideS, int D, int batch, cudaStream_t st) {
     dim3 grid((D + 31) / 32, (D + 31) / 32, batch), block(32, 8);
-    scaled_conj_transpose_kernel<<<grid, block, 0, st>>>(A, strideA, B, strideB, rowscale, strideS, D);
+    launch_pdl(scaled_conj_transpose_kernel, dim3(grid), dim3(block), 0, st, A, strideA, B, strideB, rowscale, strideS, D);
     return cudaGetLastError();
 }
 
 cudaError_t launch_conj_transpose(const cplx* A, cplx* B, int D, long long stride, int batch, cudaStream_t st) {
     dim3 grid((D + 31) / 32, (D + 31) / 32, batch);
-    conj_transpose_kernel<<<grid, dim3(32, 8), 0, st>>>(A, B, D, stride);
+    launch_pdl(conj_transpose_kernel, dim3(grid), dim3(dim3(32, 8)), 0, st, A, B, D, stride);
     return cudaGetLastError();
 }
 cudaError_t launch_max_abs_diff(const cplx* A, const cplx* B, int D, long long stride, int batch, double* out,
                                 cudaStream_t st) {
-    max_abs_diff_kernel<<<batch, 512, 0, st>>>(A, B, D, stride, out);
+    launch_pdl(max_abs_diff_kernel, dim3(batch), dim3(512), 0, st, A, B, D, stride, out);
     return cudaGetLastError();
 }
 cudaError_t launch_update_tables(const double* phi, double* coshT, double* sinhT, int N, int opdim, int m,
                                  double lambda_dtau, long long stridePhi, long long strideTab, int batch,
                                  cudaStream_t st) {
     dim3 grid((unsigned)((size_t(m) * N + 255) / 256), batch);
-    update_tables_kernel<<<grid, 256, 0, st>>>(phi, coshT, sinhT, N, opdim, m, lambda_dtau, stridePhi, strideTab);
+    launch_pdl(update_tables_kernel, dim3(grid), dim3(256), 0, st, phi, coshT, sinhT, N, opdim, m, lambda_dtau, stridePhi, strideTab);
     return cudaGetLastError();
 }
 cudaError_t launch_shift_fields(double* phi, const double* shift, int N, int opdim, int m, long long stridePhi,
                                 int batch, cudaStream_t st) {
     dim3 grid((unsigned)((size_t(m + 1) * opdim * N + 255) / 256), batch);
-    shift_fields_kernel<<<grid, 256, 0, st>>>(phi, shift, N, opdim, m, stridePhi);
+    launch_pdl(shift_fields_kernel, dim3(grid), dim3(256), 0, st, phi, shift, N, opdim, m, stridePhi);
     return cudaGetLastError();
 }
 cudaError_t launch_phi_action(const double* phi, const double* rvals, double* out, int L, int opdim, int m,
                               double dtau, double c, double u, long long stridePhi, int batch, cudaStream_t st) {
-    phi_action_kernel<<<batch, 512, 0, st>>>(phi, rvals, out, L, opdim, m, dtau, c, u, stridePhi);
+    launch_pdl(phi_action_kernel, dim3(batch), dim3(512), 0, st, phi, rvals, out, L, opdim, m, dtau, c, u, stridePhi);
     return cudaGetLastError();
 }
 cudaError_t launch_config_stream(const double* phi, double* out, int L, int opdim, int m, long long stridePhi,
                                  long long strideOut, int batch, cudaStream_t st) {
     dim3 grid(std::max(1, std::min(64, (L * L * m * opdim + 255) / 256)), batch);
-    config_stream_kernel<<<grid, 256, 0, st>>>(phi, out, L, opdim, m, stridePhi, strideOut);
+    launch_pdl(config_stream_kernel, dim3(grid), dim3(256), 0, st, phi, out, L, opdim, m, stridePhi, strideOut);
     return cudaGetLastError();
 }
 cudaError_t launch_exchange_action(const double* phi, double* out, int N, int opdim, int m, double dtau,
                                    long long stridePhi, int batch, cudaStream_t st) {
-    exchange_action_kernel<<<batch, 512, 0, st>>>(phi, out, N, opdim, m, dtau, stridePhi);
+    launch_pdl(exchange_action_kernel, dim3(batch), dim3(512), 0, st, phi, out, N, opdim, m, dtau, stridePhi);
     return cudaGetLastError();
 }
 
@@ -303,6 +315,7 @@ __device__ __forceinline__ double fm_block_sum(double v, double* red) {
 template <int MSF>
 __global__ void __launch_bounds__(256) fermion_measure_kernel(const cplx* __restrict__ gsAll, long long strideG, int N,
                                                               int L, double* __restrict__ accAll, long long strideAcc) {
+    pdl_enter();
     extern __shared__ double fm_smem[];
     __shared__ double red[8];
     const int D = MSF * N, nb = (2 * L - 1) * (2 * L - 1);
@@ -393,8 +406,8 @@ __global__ void __launch_bounds__(256) fermion_measure_kernel(const cplx* __rest
 cudaError_t launch_fermion_measure(const cplx* gs, long long strideG, int N, int L, int msf, double* acc, long long strideAcc,
                                    int batch, cudaStream_t st) {
     const size_t smem = size_t(4) * (2 * L - 1) * (2 * L - 1) * sizeof(double);
-    if (msf == 4) fermion_measure_kernel<4><<<batch, 256, smem, st>>>(gs, strideG, N, L, acc, strideAcc);
-    else fermion_measure_kernel<2><<<batch, 256, smem, st>>>(gs, strideG, N, L, acc, strideAcc);
+    if (msf == 4) launch_pdl(fermion_measure_kernel<4>, dim3(batch), dim3(256), smem, st, gs, strideG, N, L, acc, strideAcc);
+    else launch_pdl(fermion_measure_kernel<2>, dim3(batch), dim3(256), smem, st, gs, strideG, N, L, acc, strideAcc);
     return cudaGetLastError();
 }
 

@@ -68,6 +68,7 @@ __device__ __forceinline__ void apply_reflector(cplx* A, int D, const cplx* v, c
 
 __global__ void __launch_bounds__(kQrThreads) qrcp_factor_kernel(cplx* Aall, int D, long long strideA,
                                                                  cplx* tauAll, int* permAll, double* normAll) {
+    pdl_enter();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cplx* v = reinterpret_cast<cplx*>(smem_raw);                 // [D]
     __shared__ double red_val[32];
@@ -203,6 +204,7 @@ __global__ void __launch_bounds__(kQrThreads) qrcp_factor_kernel(cplx* Aall, int
 // Q = H_0 H_1 ... H_{D-1} by backward accumulation (LAPACK zung2r).
 __global__ void __launch_bounds__(kQrThreads) qr_form_q_kernel(const cplx* Aall, const cplx* tauAll, cplx* Qall,
                                                                int D, long long strideA) {
+    pdl_enter();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cplx* v = reinterpret_cast<cplx*>(smem_raw);
     const int b = blockIdx.x;
@@ -227,6 +229,7 @@ __global__ void __launch_bounds__(kQrThreads) qr_form_q_kernel(const cplx* Aall,
 
 __global__ void qr_extract_dt_kernel(const cplx* Aall, const int* permAll, double* dAll, cplx* Tall, int D,
                                      long long strideA) {
+    pdl_enter();
     const int b = blockIdx.y;
     const cplx* A = Aall + size_t(b) * strideA;
     const int* perm = permAll + size_t(b) * D;
@@ -250,6 +253,7 @@ constexpr int kTrsmCols = 16;
 constexpr int kTrsmThreads = 256;
 __global__ void __launch_bounds__(kTrsmThreads) trsm_upper_kernel(const cplx* Aall, cplx* Yall, cplx* Zall,
                                                                   const int* permAll, int D, long long strideA) {
+    pdl_enter();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cplx* ys = reinterpret_cast<cplx*>(smem_raw);                // [D][kTrsmCols]
     __shared__ cplx zl[kTrsmCols];
@@ -298,6 +302,7 @@ __global__ void __launch_bounds__(kTrsmThreads) trsm_upper_kernel(const cplx* Aa
 }
 
 __global__ void scale_split_kernel(const double* dAll, double* invBig, double* small_, double* logacc, int D) {
+    pdl_enter();
     const int b = blockIdx.x;
     const double* d = dAll + size_t(b) * D;
     __shared__ double red[32];
@@ -320,6 +325,7 @@ __global__ void scale_split_kernel(const double* dAll, double* invBig, double* s
 }
 
 __global__ void logdiag_kernel(const cplx* Aall, double* logacc, int D, long long strideA) {
+    pdl_enter();
     const int b = blockIdx.x;
     const cplx* A = Aall + size_t(b) * strideA;
     __shared__ double red[32];
@@ -365,6 +371,7 @@ __device__ __forceinline__ cplx cfmac_(cplx a, cplx b, cplx c) {     // conj(a)*
 // squared column norms, then rank by counting: perm[rank] = column (descending, ties by index)
 __global__ void __launch_bounds__(1024) colnorm_rank_kernel(const cplx* Aall, int D, long long strideA, int* permAll,
                                                             double* normAll) {
+    pdl_enter();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* nrm = reinterpret_cast<double*>(smem_raw);            // [D]
     const int b = blockIdx.x;
@@ -393,6 +400,7 @@ __global__ void __launch_bounds__(1024) colnorm_rank_kernel(const cplx* Aall, in
 // out[:, j] = in[:, perm[j]]
 __global__ void permute_columns_kernel(const cplx* inAll, cplx* outAll, const int* permAll, int D, long long strideIn,
                                        long long strideOut) {
+    pdl_enter();
     const int b = blockIdx.y, j = blockIdx.x;
     const cplx* src = inAll + size_t(b) * strideIn + size_t(permAll[size_t(b) * D + j]) * D;
     cplx* dst = outAll + size_t(b) * strideOut + size_t(j) * D;
@@ -402,6 +410,7 @@ __global__ void permute_columns_kernel(const cplx* inAll, cplx* outAll, const in
 // out[perm[j], :] = in[j, :]
 __global__ void permute_rows_kernel(const cplx* inAll, cplx* outAll, const int* permAll, int D, long long strideIn,
                                     long long strideOut) {
+    pdl_enter();
     const int b = blockIdx.y, c = blockIdx.x;
     const cplx* src = inAll + size_t(b) * strideIn + size_t(c) * D;
     cplx* dst = outAll + size_t(b) * strideOut + size_t(c) * D;
@@ -412,6 +421,7 @@ __global__ void permute_rows_kernel(const cplx* inAll, cplx* outAll, const int* 
 // Householder QR of the panel A[j0:D, j0:j0+nbc] of every matrix of the batch.
 __global__ void __launch_bounds__(kPanelThreads) qr_panel_kernel(cplx* Aall, long long strideA, int D, int j0, int nbc,
                                                                  cplx* Vall, cplx* VTall, long long strideV) {
+    pdl_enter();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int m = D - j0;
     const int ldp = m | 1;                                          // odd leading dimension
@@ -565,6 +575,7 @@ constexpr int kPanelRegThreads = 512;      // 16 warps, two panel columns per wa
 template <int MAXT>
 __global__ void __launch_bounds__(kPanelRegThreads) qr_panel_reg_kernel(cplx* Aall, long long strideA, int D, int j0,
                                                                         int nbc, cplx* Vall, cplx* VTall, long long strideV) {
+    pdl_enter();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int m = D - j0;
     const int ldp = m | 1;
@@ -761,7 +772,7 @@ __host__ __device__ inline P2Layout p2_layout(int m) {
     l.ldp = ((m + 7) & ~7) + 4;
     size_t p = 0;
     l.P = p;    p += size_t(32) * l.ldp;
-    l.vbuf = p; p += size_t(2) * ((m + 1) & ~1);
+    l.vbuf = p; p += size_t(2) * 32 * 10;                // two reflector buffers of 32 * MAXT rows (zero beyond row m)
     l.G = p;    p += 32 * 33;
     l.T = p;    p += 32 * 33;
     l.Zp = p;   p += size_t(kP2KSplit) * 3 * 64;     // partial 8 x 24 products (three 8 x 8 blocks per split)
@@ -769,6 +780,24 @@ __host__ __device__ inline P2Layout p2_layout(int m) {
     l.W = p;    p += 8 * 24;
     l.total = p;
     return l;
+}
+
+// 1 / sqrt(x) and 1 / x for normal positive x: hardware approximation + two Newton steps (the library versions
+// handle special cases that cannot occur here and cost ~3x the instructions on the serial path of a column step)
+__device__ __forceinline__ double fast_rsqrt(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double hx = 0.5 * x;
+    y = y * fma(-hx * y, y, 1.5);
+    y = y * fma(-hx * y, y, 1.5);
+    return y;
+}
+__device__ __forceinline__ double fast_rcp(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    y = y * fma(-x, y, 2.0);
+    y = y * fma(-x, y, 2.0);
+    return y;
 }
 
 // element (row r, column c) of the unit lower-trapezoidal V held in the panel buffer (R sits on / above the diagonal)
@@ -784,6 +813,7 @@ __device__ __forceinline__ cplx p2_vget(const cplx* P, int ldp, int r, int c, in
 template <int MAXT>
 __global__ void __launch_bounds__(kP2Threads) qr_panel2_kernel(cplx* Aall, long long strideA, int D, int j0, int nbc,
                                                                cplx* Vall, cplx* VTall, long long strideV) {
+    pdl_enter();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int m = D - j0;
     const P2Layout lay = p2_layout(m);
@@ -802,7 +832,6 @@ __global__ void __launch_bounds__(kP2Threads) qr_panel2_kernel(cplx* Aall, long 
     cplx* A = Aall + size_t(b) * strideA;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int grp = lane >> 2, t4 = lane & 3;
-    const int mv = (m + 1) & ~1;
 
     // ---- panel to shared memory (rows beyond m are never read: every fragment load is predicated on r < m)
     for (int idx = tid; idx < nbc * m; idx += kP2Threads) {
@@ -810,100 +839,146 @@ __global__ void __launch_bounds__(kP2Threads) qr_panel2_kernel(cplx* Aall, long 
         P[size_t(c) * ldp + r] = A[size_t(j0 + c) * D + j0 + r];
     }
     for (int i = tid; i < 32 * 33; i += kP2Threads) { Gm[i] = make_double2(0, 0); Tm[i] = make_double2(0, 0); }
+    for (int i = tid; i < 2 * 32 * MAXT; i += kP2Threads) vbuf[i] = make_double2(0, 0);
     __syncthreads();
 
     for (int c0 = 0; c0 < nbc; c0 += kP2Sub) {
         const int ns = min(kP2Sub, nbc - c0);                       // columns of this sub-panel
-        if (w < kP2Sub) {
-            // =========================================================== column steps of the sub-panel (8 warps)
-            // lane holds rows c0 + lane + 32 t of column c0 + w
+        {
+            // =========================================================== column steps of the sub-panel
+            // warps 0..7: warp <-> column c0 + w in registers, lane holds rows c0 + lane + 32 t (zero beyond row m, so
+            // no per-row predicates: only the first 32-row block contains rows at or above the diagonal).
+            // warps 8..15: cross Gram entries v_j^H v_c with the reflectors of the earlier sub-panels (for T).
             cplx a[MAXT];
-            const bool live = w < ns;
+            const bool colwarp = w < kP2Sub;
+            const bool live = colwarp && w < ns;
+            if (colwarp) {
 #pragma unroll
-            for (int t = 0; t < MAXT; ++t) {
-                const int r = c0 + lane + 32 * t;
-                a[t] = (live && r < m) ? P[size_t(c0 + w) * ldp + r] : make_double2(0, 0);
+                for (int t = 0; t < MAXT; ++t) {
+                    const int r = c0 + lane + 32 * t;
+                    a[t] = (live && r < m) ? P[size_t(c0 + w) * ldp + r] : make_double2(0, 0);
+                }
             }
             for (int cl = 0; cl < ns; ++cl) {
                 const int c = c0 + cl;
-                cplx* vb = vbuf + (cl & 1) * mv;
+                cplx* vb = vbuf + (cl & 1) * (32 * MAXT);
                 if (w == cl) {
-                    // reflector of the own column (zlarfg conventions); row c is lane cl, t = 0
-                    double xn = 0;
+                    // reflector of the own column (zlarfg conventions); row c is lane cl of the first row block
+                    double xn0 = (lane > cl) ? fma(a[0].x, a[0].x, a[0].y * a[0].y) : 0.0, xn1 = 0.0;
 #pragma unroll
-                    for (int t = 0; t < MAXT; ++t) {
-                        const int r = c0 + lane + 32 * t;
-                        const double n2 = fma(a[t].x, a[t].x, a[t].y * a[t].y);
-                        xn += (r > c && r < m) ? n2 : 0.0;
+                    for (int t = 1; t < MAXT; ++t) {
+                        if (t & 1) xn1 = fma(a[t].x, a[t].x, fma(a[t].y, a[t].y, xn1));
+                        else xn0 = fma(a[t].x, a[t].x, fma(a[t].y, a[t].y, xn0));
                     }
-                    xn = warp_sum(xn);
+                    const double xn = warp_sum(xn0 + xn1);
                     const double alr = __shfl_sync(0xffffffffu, a[0].x, cl);
                     const double ali = __shfl_sync(0xffffffffu, a[0].y, cl);
                     const bool trivial = xn == 0.0 && ali == 0.0;
                     const double x2 = alr * alr + ali * ali + xn;
-                    const double inrm = trivial ? 0.0 : rsqrt(x2);
+                    const double inrm = trivial ? 0.0 : fast_rsqrt(x2);
                     const double nrm = x2 * inrm;
                     const double beta = trivial ? alr : (alr >= 0 ? -nrm : nrm);
                     const double ib = alr >= 0 ? -inrm : inrm;                        // 1 / beta
                     const cplx tau = trivial ? make_double2(0, 0) : make_double2((beta - alr) * ib, -ali * ib);
                     const double dr = alr - beta, di = ali;
-                    const double iden = trivial ? 0.0 : __drcp_rn(dr * dr + di * di);
+                    const double iden = trivial ? 0.0 : fast_rcp(dr * dr + di * di);
                     const cplx sc = make_double2(dr * iden, -di * iden);
+                    {
+                        const cplx scaled = cmul(a[0], sc);
+                        const cplx vnew = lane > cl ? scaled : make_double2(lane == cl ? 1.0 : 0.0, 0.0);
+                        vb[lane] = vnew;
+                        a[0].x = lane > cl ? scaled.x : (lane == cl ? beta : a[0].x);  // row c keeps the R diagonal
+                        a[0].y = lane > cl ? scaled.y : (lane == cl ? 0.0 : a[0].y);
+                    }
 #pragma unroll
-                    for (int t = 0; t < MAXT; ++t) {
-                        const int r = c0 + lane + 32 * t;
-                        const cplx scaled = cmul(a[t], sc);
-                        const cplx vnew = r > c ? scaled : make_double2(r == c ? 1.0 : 0.0, 0.0);
-                        if (r < m) vb[r - c0] = vnew;
-                        a[t].x = r > c ? scaled.x : (r == c ? beta : a[t].x);         // row c keeps the R diagonal
-                        a[t].y = r > c ? scaled.y : (r == c ? 0.0 : a[t].y);
+                    for (int t = 1; t < MAXT; ++t) {
+                        a[t] = cmul(a[t], sc);
+                        vb[lane + 32 * t] = a[t];
                     }
                     if (lane == 0) s_tau[c] = tau;
                 }
-                asm volatile("bar.sync 1, 256;" ::: "memory");
+                __syncthreads();
                 const cplx tau = s_tau[c];
-                if (w != cl && live && (tau.x != 0.0 || tau.y != 0.0)) {
-                    // dot = v_c^H x over rows >= c (v is zero above c); x = own column (w > cl) or own reflector (w < cl)
-                    double dr = 0, di = 0;
-                    cplx vv[MAXT];
+                const bool nontrivial = tau.x != 0.0 || tau.y != 0.0;
+                if (colwarp) {
+                    if (w != cl && live && nontrivial) {
+                        // dot = v_c^H x (v is zero above row c); x = own column (w > cl) or own reflector (w < cl)
+                        double dr0 = 0, di0 = 0, dr1 = 0, di1 = 0;
+                        cplx vv[MAXT];
 #pragma unroll
-                    for (int t = 0; t < MAXT; ++t) {
-                        const int r = c0 + lane + 32 * t;
-                        vv[t] = r < m ? vb[r - c0] : make_double2(0, 0);
-                        cplx x = a[t];
-                        if (w < cl) {                                                  // own reflector: unit diagonal, zero above
-                            const int cw = c0 + w;
-                            x = r > cw ? a[t] : make_double2(r == cw ? 1.0 : 0.0, 0.0);
+                        for (int t = 0; t < MAXT; ++t) vv[t] = vb[lane + 32 * t];
+                        {
+                            cplx x = a[0];
+                            if (w < cl) x = lane > w ? a[0] : make_double2(lane == w ? 1.0 : 0.0, 0.0);   // unit diagonal, zero above
+                            dr0 = fma(vv[0].x, x.x, vv[0].y * x.y);
+                            di0 = fma(vv[0].x, x.y, -vv[0].y * x.x);
                         }
-                        dr = fma(vv[t].x, x.x, fma(vv[t].y, x.y, dr));
-                        di = fma(vv[t].x, x.y, fma(-vv[t].y, x.x, di));
-                    }
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        dr += __shfl_xor_sync(0xffffffffu, dr, o);
-                        di += __shfl_xor_sync(0xffffffffu, di, o);
+                        for (int t = 1; t < MAXT; ++t) {
+                            if (t & 1) {
+                                dr1 = fma(vv[t].x, a[t].x, fma(vv[t].y, a[t].y, dr1));
+                                di1 = fma(vv[t].x, a[t].y, fma(-vv[t].y, a[t].x, di1));
+                            } else {
+                                dr0 = fma(vv[t].x, a[t].x, fma(vv[t].y, a[t].y, dr0));
+                                di0 = fma(vv[t].x, a[t].y, fma(-vv[t].y, a[t].x, di0));
+                            }
+                        }
+                        double dr = dr0 + dr1, di = di0 + di1;
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+                            dr += __shfl_xor_sync(0xffffffffu, dr, o);
+                            di += __shfl_xor_sync(0xffffffffu, di, o);
+                        }
+                        if (w > cl) {
+                            const cplx fw = cmul(make_double2(tau.x, -tau.y), make_double2(dr, di));   // conj(tau) (v^H a)
+#pragma unroll
+                            for (int t = 0; t < MAXT; ++t) {
+                                a[t].x -= fw.x * vv[t].x - fw.y * vv[t].y;
+                                a[t].y -= fw.x * vv[t].y + fw.y * vv[t].x;
+                            }
+                        } else if (lane == 0) {
+                            Gm[(c0 + w) * 33 + c] = make_double2(dr, -di);             // v_w^H v_c = conj(v_c^H v_w)
+                        }
                     }
-                    if (w > cl) {
-                        const cplx fw = cmul(make_double2(tau.x, -tau.y), make_double2(dr, di));   // conj(tau) (v^H a)
+                    // compact-WY factor of the sub-panel, column cl - 1 (its Gram column was completed in the previous step)
+                    if (cl > 0 && w == cl - 1) {
+                        const int cc = c - 1;
+                        const cplx tcc = s_tau[cc];
+                        if (lane == 0) Tm[cc * 33 + cc] = tcc;
+                        const int i = c0 + lane;
+                        if (i < cc) {
+                            cplx sacc = make_double2(0, 0);
+                            for (int l = i; l < cc; ++l) sacc = cfma_(Tm[i * 33 + l], Gm[l * 33 + cc], sacc);
+                            Tm[i * 33 + cc] = make_double2(-(tcc.x * sacc.x - tcc.y * sacc.y), -(tcc.x * sacc.y + tcc.y * sacc.x));
+                        }
+                    }
+                } else if (nontrivial) {
+                    // cross Gram: G[j, c] = v_j^H v_c for the reflectors j < c0 of the earlier sub-panels (rows >= c only:
+                    // v_c vanishes above; V[r, j] = P[j][r] there because r >= c > j)
+                    for (int j = w - kP2Sub; j < c0; j += kP2Sub) {
+                        const cplx* vj = P + size_t(j) * ldp + c0;
+                        double gr0 = 0, gi0 = 0, gr1 = 0, gi1 = 0;
 #pragma unroll
                         for (int t = 0; t < MAXT; ++t) {
-                            a[t].x -= fw.x * vv[t].x - fw.y * vv[t].y;
-                            a[t].y -= fw.x * vv[t].y + fw.y * vv[t].x;
+                            const int rr = lane + 32 * t;
+                            if (c0 + rr < m) {
+                                const cplx x = vj[rr], v = vb[rr];
+                                if (t & 1) {
+                                    gr1 = fma(x.x, v.x, fma(x.y, v.y, gr1));           // conj(x) v
+                                    gi1 = fma(x.x, v.y, fma(-x.y, v.x, gi1));
+                                } else {
+                                    gr0 = fma(x.x, v.x, fma(x.y, v.y, gr0));
+                                    gi0 = fma(x.x, v.y, fma(-x.y, v.x, gi0));
+                                }
+                            }
                         }
-                    } else if (lane == 0) {
-                        Gm[(c0 + w) * 33 + c] = make_double2(dr, -di);                 // v_w^H v_c = conj(v_c^H v_w)
-                    }
-                }
-                // compact-WY factor of the sub-panel, column cl - 1 (its Gram column was completed in the previous step)
-                if (cl > 0 && w == cl - 1) {
-                    const int cc = c - 1;
-                    const cplx tcc = s_tau[cc];
-                    if (lane == 0) Tm[cc * 33 + cc] = tcc;
-                    const int i = c0 + lane;
-                    if (i < cc) {
-                        cplx sacc = make_double2(0, 0);
-                        for (int l = i; l < cc; ++l) sacc = cfma_(Tm[i * 33 + l], Gm[l * 33 + cc], sacc);
-                        Tm[i * 33 + cc] = make_double2(-(tcc.x * sacc.x - tcc.y * sacc.y), -(tcc.x * sacc.y + tcc.y * sacc.x));
+                        double gr = gr0 + gr1, gi = gi0 + gi1;
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+                            gr += __shfl_xor_sync(0xffffffffu, gr, o);
+                            gi += __shfl_xor_sync(0xffffffffu, gi, o);
+                        }
+                        if (lane == 0) Gm[j * 33 + c] = make_double2(gr, gi);
                     }
                 }
             }
@@ -1012,42 +1087,9 @@ __global__ void __launch_bounds__(kP2Threads) qr_panel2_kernel(cplx* Aall, long 
         __syncthreads();
     }
 
-    // ---- cross Gram blocks G[s-block, t-block] = V_s^H V_t (s < t) on the tensor cores, two row splits each
+    // ---- off-diagonal blocks of T (the cross Gram blocks V_s^H V_t were accumulated during the column steps)
     {
         const int nsub = (nbc + kP2Sub - 1) / kP2Sub;
-        const int npairs = nsub * (nsub - 1) / 2;                   // <= 6
-        const int nk4 = (m + 3) / 4, k4per = (nk4 + 1) / 2;
-        if (w < 2 * npairs) {
-            const int pr = w >> 1, ks = w & 1;
-            int sb = 0, tb = 1, cnt = pr;                           // pair index -> (s, t), s < t
-            while (cnt >= nsub - 1 - sb) { cnt -= nsub - 1 - sb; ++sb; tb = sb + 1; }
-            tb = sb + 1 + cnt;
-            double zr0 = 0, zr1 = 0, zi0 = 0, zi1 = 0;
-            const int ca = sb * 8 + grp, cb = tb * 8 + grp;
-            for (int s4 = ks * k4per; s4 < min(nk4, (ks + 1) * k4per); ++s4) {
-                const int r = 4 * s4 + t4;
-                const cplx av = ca < nbc ? p2_vget(P, ldp, r, ca, m) : make_double2(0, 0);
-                const cplx bv = cb < nbc ? p2_vget(P, ldp, r, cb, m) : make_double2(0, 0);
-                dmma_qr(zr0, zr1, av.x, bv.x);
-                dmma_qr(zr0, zr1, av.y, bv.y);
-                dmma_qr(zi0, zi1, av.x, bv.y);
-                dmma_qr(zi0, zi1, -av.y, bv.x);
-            }
-            cplx* zp = Zp + size_t(w) * 64;                         // 12 x 64 <= kP2KSplit * 3 * 64
-            zp[grp * 8 + 2 * t4] = make_double2(zr0, zi0);
-            zp[grp * 8 + 2 * t4 + 1] = make_double2(zr1, zi1);
-        }
-        __syncthreads();
-        for (int e = tid; e < npairs * 64; e += kP2Threads) {
-            const int pr = e >> 6, ii = (e >> 3) & 7, nn = e & 7;
-            int sb = 0, cnt = pr;
-            while (cnt >= nsub - 1 - sb) { cnt -= nsub - 1 - sb; ++sb; }
-            const int tb = sb + 1 + cnt;
-            const cplx p0 = Zp[size_t(2 * pr) * 64 + ii * 8 + nn], p1 = Zp[size_t(2 * pr + 1) * 64 + ii * 8 + nn];
-            if (sb * 8 + ii < nbc && tb * 8 + nn < nbc)
-                Gm[(sb * 8 + ii) * 33 + tb * 8 + nn] = make_double2(p0.x + p1.x, p0.y + p1.y);
-        }
-        __syncthreads();
         // ---- off-diagonal blocks of T, block column by block column:  T[0:c0, c0:c0+8] = -T[0:c0, 0:c0] G[0:c0, c0:c0+8] T_tt
         for (int tb = 1; tb < nsub; ++tb) {
             const int c0 = tb * 8, nt = min(8, nbc - c0);
@@ -1106,6 +1148,7 @@ __global__ void __launch_bounds__(kP2Threads) qr_panel2_kernel(cplx* Aall, long 
 
 // inverse of every nb x nb diagonal block of the upper-triangular R (stored in A): out [batch][P][nb*nb]
 __global__ void trtri_blocks_kernel(const cplx* Aall, long long strideA, int D, int nb, cplx* outAll, long long strideOut) {
+    pdl_enter();
     __shared__ cplx Rs[32 * 33], Xs[32 * 33];
     const int b = blockIdx.y, p = blockIdx.x;
     const int j0 = p * nb, nbc = min(nb, D - j0);
@@ -1189,17 +1232,17 @@ void qr_workspace_destroy(QrWorkspace* ws) {
 
 cudaError_t qr_prepivot_launch(const cplx* A, long long strideA, cplx* Aout, long long strideOut, int* perm,
                                double* norms, int D, int batch, cudaStream_t st) {
-    colnorm_rank_kernel<<<batch, 1024, size_t(D) * sizeof(double), st>>>(A, D, strideA, perm, norms);
+    launch_pdl(colnorm_rank_kernel, dim3(batch), dim3(1024), size_t(D) * sizeof(double), st, A, D, strideA, perm, norms);
     QR_TRY(cudaGetLastError());
     dim3 grid(D, batch);
-    permute_columns_kernel<<<grid, 128, 0, st>>>(A, Aout, perm, D, strideA, strideOut);
+    launch_pdl(permute_columns_kernel, dim3(grid), dim3(128), 0, st, A, Aout, perm, D, strideA, strideOut);
     return cudaGetLastError();
 }
 
 cudaError_t permute_rows_launch(const cplx* in, long long strideIn, cplx* out, long long strideOut, const int* perm,
                                 int D, int batch, cudaStream_t st) {
     dim3 grid(D, batch);
-    permute_rows_kernel<<<grid, 128, 0, st>>>(in, out, perm, D, strideIn, strideOut);
+    launch_pdl(permute_rows_kernel, dim3(grid), dim3(128), 0, st, in, out, perm, D, strideIn, strideOut);
     return cudaGetLastError();
 }
 
@@ -1223,12 +1266,12 @@ cudaError_t qr_blocked_factor(QrWorkspace& ws, cplx* A, int D, long long strideA
         static const bool old_reg_panel = std::getenv("DQMC_QR_REG_PANEL") != nullptr;
         if (m <= 320 && nb == 32 && !force_smem_panel && !old_reg_panel) {
             const size_t sm2 = p2_layout(m).total * sizeof(cplx);
-            qr_panel2_kernel<10><<<batch, kP2Threads, sm2, st>>>(A, strideA, D, j0, nbc, V, VT, (long long)dd);
+            launch_pdl(qr_panel2_kernel<10>, dim3(batch), dim3(kP2Threads), sm2, st, A, strideA, D, j0, nbc, V, VT, (long long)dd);
         } else if (m <= 320 && nb == 32 && !force_smem_panel) {
-            qr_panel_reg_kernel<10><<<batch, kPanelRegThreads, sm + size_t(2) * m * sizeof(cplx), st>>>(A, strideA, D, j0, nbc, V,
+            launch_pdl(qr_panel_reg_kernel<10>, dim3(batch), dim3(kPanelRegThreads), sm + size_t(2) * m * sizeof(cplx), st, A, strideA, D, j0, nbc, V,
                                                                                                   VT, (long long)dd);
         } else {
-            qr_panel_kernel<<<batch, kPanelThreads, sm, st>>>(A, strideA, D, j0, nbc, V, VT, (long long)dd);
+            launch_pdl(qr_panel_kernel, dim3(batch), dim3(kPanelThreads), sm, st, A, strideA, D, j0, nbc, V, VT, (long long)dd);
         }
         QR_TRY(cudaGetLastError());
         ws.launches += 1;
@@ -1298,7 +1341,7 @@ cudaError_t trsm_upper_blocked(QrWorkspace& ws, const cplx* A, cplx* Y, cplx* Zo
     const long long sR = (long long)nb * (D + nb);
     cplx* Rinv = ws.Rinv + size_t(off) * sR;
     dim3 grid(np, batch);
-    trtri_blocks_kernel<<<grid, 128, 0, st>>>(A, strideA, D, nb, Rinv, sR);
+    launch_pdl(trtri_blocks_kernel, dim3(grid), dim3(128), 0, st, A, strideA, D, nb, Rinv, sR);
     QR_TRY(cudaGetLastError());
     ws.launches += 1;
     for (int p = np - 1; p >= 0; --p) {
@@ -1321,21 +1364,21 @@ cudaError_t trsm_upper_blocked(QrWorkspace& ws, const cplx* A, cplx* Y, cplx* Zo
 cudaError_t qrcp_factor_launch(cplx* A, int D, long long strideA, cplx* tau, int* perm, double* colnorm,
                                int batch, cudaStream_t st) {
     const size_t smem = size_t(D) * sizeof(cplx);
-    qrcp_factor_kernel<<<batch, kQrThreads, smem, st>>>(A, D, strideA, tau, perm, colnorm);
+    launch_pdl(qrcp_factor_kernel, dim3(batch), dim3(kQrThreads), smem, st, A, D, strideA, tau, perm, colnorm);
     return cudaGetLastError();
 }
 
 cudaError_t qr_form_q_launch(const cplx* A, const cplx* tau, cplx* Q, int D, long long strideA, int batch,
                              cudaStream_t st) {
     const size_t smem = size_t(D) * sizeof(cplx);
-    qr_form_q_kernel<<<batch, kQrThreads, smem, st>>>(A, tau, Q, D, strideA);
+    launch_pdl(qr_form_q_kernel, dim3(batch), dim3(kQrThreads), smem, st, A, tau, Q, D, strideA);
     return cudaGetLastError();
 }
 
 cudaError_t qr_extract_dt_launch(const cplx* A, const int* perm, double* d, cplx* T, int D, long long strideA,
                                  int batch, cudaStream_t st) {
     dim3 grid((unsigned)((size_t(D) * D + 255) / 256), batch);
-    qr_extract_dt_kernel<<<grid, 256, 0, st>>>(A, perm, d, T, D, strideA);
+    launch_pdl(qr_extract_dt_kernel, dim3(grid), dim3(256), 0, st, A, perm, d, T, D, strideA);
     return cudaGetLastError();
 }
 
@@ -1345,19 +1388,19 @@ cudaError_t trsm_upper_launch(const cplx* A, cplx* Y, cplx* Zout, const int* per
     cudaError_t e = cudaFuncSetAttribute(trsm_upper_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid((D + kTrsmCols - 1) / kTrsmCols, batch);
-    trsm_upper_kernel<<<grid, kTrsmThreads, smem, st>>>(A, Y, Zout, perm, D, strideA);
+    launch_pdl(trsm_upper_kernel, dim3(grid), dim3(kTrsmThreads), smem, st, A, Y, Zout, perm, D, strideA);
     return cudaGetLastError();
 }
 
 cudaError_t scale_split_launch(const double* d, double* inv_big, double* small_, double* logacc, int D,
                                int batch, cudaStream_t st) {
-    scale_split_kernel<<<batch, 256, 0, st>>>(d, inv_big, small_, logacc, D);
+    launch_pdl(scale_split_kernel, dim3(batch), dim3(256), 0, st, d, inv_big, small_, logacc, D);
     return cudaGetLastError();
 }
 
 cudaError_t logdiag_accumulate_launch(const cplx* A, double* logacc, int D, long long strideA, int batch,
                                       cudaStream_t st) {
-    logdiag_kernel<<<batch, 256, 0, st>>>(A, logacc, D, strideA);
+    launch_pdl(logdiag_kernel, dim3(batch), dim3(256), 0, st, A, logacc, D, strideA);
     return cudaGetLastError();
 }
 

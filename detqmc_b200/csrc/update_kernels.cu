@@ -316,6 +316,7 @@ __device__ __forceinline__ void extend_xy(cplx* __restrict__ X, cplx* __restrict
 // O(K) site block sits between the two barriers.
 template <int MSF, int OPDIM, int TPT, int MAXT>
 __global__ void __launch_bounds__(MAXT) update_round_kernel(UpdateModel md, UpdateArgs a) {
+    pdl_enter();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int D = md.D, N = md.N, L = md.L;
     const int KMAX = (MSF * md.delaySteps + 3) & ~3;
@@ -780,6 +781,7 @@ constexpr int kWinMaxJ = 64;
 
 template <int MSF, int OPDIM, int BW>
 __global__ void __launch_bounds__(32 * (3 + BW)) update_window_kernel(UpdateModel md, UpdateArgs a) {
+    pdl_enter();
     constexpr int NT = 32 * (3 + BW);                      // warp 0: chain, warps 1 / 2: Tx / Ty, BW block-update warps
     constexpr int NBLK = 32 * (1 + BW);                    // participants of kBarStart / kBarDone
     typedef PropTable<MSF, OPDIM> PT;
@@ -1272,6 +1274,7 @@ constexpr int kGthThreads = 256, kGthTile = 32;
 
 template <int MSF>
 __global__ void __launch_bounds__(kGthThreads) update_gather_kernel(UpdateModel md, UpdateArgs a) {
+    pdl_enter();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int b = blockIdx.y;
     const int* hdr = a.whdr + size_t(b) * a.strideHdr;
@@ -1376,7 +1379,7 @@ cudaError_t update_round_launch(const UpdateModel& m, const UpdateArgs& a, cudaS
         cudaError_t e = cudaFuncSetAttribute(update_round_kernel<MSF, OPD, TPT, MAXT>,                      \
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
         if (e != cudaSuccess) return e;                                                                     \
-        update_round_kernel<MSF, OPD, TPT, MAXT><<<a.batch, threads, smem, st>>>(m, aa);                     \
+        launch_pdl(update_round_kernel<MSF, OPD, TPT, MAXT>, dim3(a.batch), dim3(threads), smem, st, m, aa);                     \
     }
 #define LAUNCH3(MSF, OPD)                                                                                   \
     {                                                                                                       \
@@ -1422,7 +1425,7 @@ cudaError_t update_window_launch(const UpdateModel& m, const UpdateArgs& a, cuda
         cudaError_t e = cudaFuncSetAttribute(update_window_kernel<MSF, OPD, BW>,                            \
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
         if (e != cudaSuccess) return e;                                                                     \
-        update_window_kernel<MSF, OPD, BW><<<a.batch, 32 * (3 + BW), smem, st>>>(m, a);                     \
+        launch_pdl(update_window_kernel<MSF, OPD, BW>, dim3(a.batch), dim3(32 * (3 + BW)), smem, st, m, a);                     \
     }
     // 16 block-update warps for the 2 x 2 site blocks (96 registers per thread suffice); the 4 x 4 blocks of O(3)
     // need the registers more than the warps
@@ -1443,7 +1446,7 @@ cudaError_t update_build_xy_launch(const UpdateModel& m, const UpdateArgs& a, cu
         cudaError_t e = cudaFuncSetAttribute(update_gather_kernel<MSF>,                                     \
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
         if (e != cudaSuccess) return e;                                                                     \
-        update_gather_kernel<MSF><<<grid, kGthThreads, smem, st>>>(m, a);                                   \
+        launch_pdl(update_gather_kernel<MSF>, dim3(grid), dim3(kGthThreads), smem, st, m, a);                                   \
     }
     if (m.msf == 2) LAUNCHB(2)
     else LAUNCHB(4)

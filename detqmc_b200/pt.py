@@ -162,7 +162,10 @@ class DetQMCPT:
                     if (self.cfgBinary or self.cfgText) and self.cfgInterval and self.swCounter % self.cfgInterval == 0:
                         self._buffer_configurations()
                 self.sweepsDone += 1
-            if self.exchangeInterval and (self.sweepsDone + self.sweepsDoneThermalization) % self.exchangeInterval == 0:
+            # the reference exchanges only while the stage is T or M (detqmcpt.h:948-953): none after the last sweep
+            finished = self.sweepsDoneThermalization == self.thermalization and self.sweepsDone == self.sweeps
+            if (self.exchangeInterval and not finished
+                    and (self.sweepsDone + self.sweepsDoneThermalization) % self.exchangeInterval == 0):
                 self.replica_exchange_step()
             # replicaExchangeConsistencyCheck, detqmcpt.h:1120-1135
             want = self.values[self.local_parameter_indices()]

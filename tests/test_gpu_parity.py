@@ -565,6 +565,8 @@ def test_parallel_tempering_driver_vs_oracle_loop(tmp_path):
                     series[process_par[pi]][name].append(ob[name])
                 if (step - therm + 1) % cfg_interval == 0:
                     cfgs[process_par[pi]].append(config_stream(o.phi))
+        if step == therm + sweeps - 1:
+            break                                        # no exchange after the last sweep (detqmcpt.h:948-953)
         actions = [o.exchange_action() for o in reps]
         ctrl = [get_ctrl(o) for o in reps]
         for c1 in range(P - 1):
@@ -591,8 +593,37 @@ def test_parallel_tempering_driver_vs_oracle_loop(tmp_path):
         got = np.fromfile(path) if os.path.exists(path) else np.zeros(0)
         assert got.shape == want.shape and (got.size == 0 or maxabs(got, want) < 1e-12)
     acc_file = [x.split() for x in open(os.path.join(str(tmp_path), "exchange-acceptance.values")) if x[0] != "#"]
-    assert np.allclose([float(a[1]) for a in acc_file][:P - 1], [accepted[c] / (therm + sweeps) for c in range(P - 1)],
+    assert np.allclose([float(a[1]) for a in acc_file][:P - 1], [accepted[c] / (therm + sweeps - 1) for c in range(P - 1)],
                        rtol=1e-12, atol=0)
+
+
+def test_parallel_tempering_vs_reference_driver(tmp_path):
+    """detqmc_b200.DetQMCPT against the reference's OWN replica-exchange driver: tests/golden/pt_reference.npz holds the
+    output of the unmodified DetQMCPT<DetSDW<CB_ASSAAD_BERG, 2>> (detqmcpt.h) run with one thread per ladder process
+    on a thread-backed stand-in for boost::mpi (oracle/ref_pt_harness.cpp, tools/make_golden.py pt_reference).  Same
+    seed, same ladder: the time series of every control parameter (which replica's measurement lands where depends on
+    every accepted swap), the exchange acceptance ratios and the diffusion fractions must be the reference's."""
+    import os
+    from detqmc_b200 import DetQMCPT
+    from detqmc_b200.pt import OBSERVABLES
+    from dqmc_oracle import SdwParams
+    g = load_golden("pt_reference")
+    values = g["values"]
+    P = len(values)
+    m = int(round(float(g["beta"]) / 0.1))
+    pt = DetQMCPT(SdwParams(L=int(g["L"]), m=m, s=int(g["s"])), values, thermalization=int(g["thermalization"]),
+                  sweeps=int(g["sweeps"]), exchangeInterval=int(g["exchangeInterval"]), outdir=str(tmp_path))
+    pt.run()
+    for c in range(P):
+        d = pt.subdir(c)
+        assert os.path.basename(d) == str(g["subdirs"][c])            # the reference's directory names
+        for name in OBSERVABLES:
+            got = [float(x) for x in open(os.path.join(d, name + ".series")) if x[0] != "#"]
+            want = g["series_" + name][c]                             # the reference writes 6 significant digits
+            assert len(got) == len(want) and np.allclose(got, want, rtol=2e-5, atol=2e-6), (c, name, got, want)
+    for fname, key in (("exchange-acceptance.values", "acceptance"), ("exchange-diffusion.values", "diffusion")):
+        rows = [x.split() for x in open(os.path.join(str(tmp_path), fname)) if x[0] != "#"]
+        assert np.allclose([float(r[1]) for r in rows], g[key], rtol=1e-12, atol=1e-15), fname
 
 
 def test_parallel_tempering_driver_fermionic_series(tmp_path):

@@ -127,6 +127,39 @@ def hubbard_observables_fixture():
     print("hubbard_observables done")
 
 
+def pt_reference_fixture():
+    """Replica-exchange trajectory of the reference's own DetQMCPT driver (detqmcpt.h, unmodified) run with one thread
+    per ladder process on the thread-backed boost::mpi stand-in (oracle/_ref/ref_pt, oracle/ref_pt_harness.cpp):
+    per-parameter time series, exchange acceptance and diffusion statistics."""
+    import subprocess
+    import tempfile
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_pt")
+    values = [-1.9, -1.5, -1.1, -0.7, -0.3, 0.1]
+    L, beta, s, therm, sweeps, xint = 4, 2.0, 10, 4, 8, 1
+    d = {"values": np.array(values), "L": L, "beta": beta, "s": s, "thermalization": therm, "sweeps": sweeps,
+         "exchangeInterval": xint}
+    with tempfile.TemporaryDirectory() as tmp:
+        env = dict(os.environ, OPENBLAS_NUM_THREADS="1")
+        subprocess.run([exe, str(L), str(beta), str(s), str(therm), str(sweeps), str(xint)] + [repr(v) for v in values],
+                       cwd=tmp, check=True, stdout=subprocess.DEVNULL, env=env)
+
+        def table(name):
+            return np.array([[float(x) for x in l.split()] for l in open(os.path.join(tmp, name)) if l[0] != "#" and l.strip()])
+        d["acceptance"] = table("exchange-acceptance.values")[:, 1]
+        d["diffusion"] = table("exchange-diffusion.values")[:, 1]
+        subdirs = sorted(x for x in os.listdir(tmp) if x.startswith("p") and os.path.isdir(os.path.join(tmp, x)))
+        assert len(subdirs) == len(values), subdirs
+        for obs in ("normMeanPhi", "associatedEnergy", "phiRhoS_Gs", "phiRhoS_Gc"):
+            rows = []
+            for cpi in range(len(values)):
+                sub = [x for x in subdirs if x.startswith("p%d_" % cpi)][0]
+                rows.append([float(l) for l in open(os.path.join(tmp, sub, obs + ".series")) if l[0] != "#" and l.strip()])
+            d["series_" + obs] = np.array(rows)
+        d["subdirs"] = np.array(subdirs)
+    np.savez_compressed(os.path.join(OUT, "pt_reference.npz"), **d)
+    print("pt_reference done; acceptance", d["acceptance"])
+
+
 def exchange_fixture():
     gen = np.random.default_rng(7)
     rows = []
@@ -352,6 +385,9 @@ if __name__ == "__main__":
         observables_fixture()
         fermion_fixture()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "pt_reference":
+        pt_reference_fixture()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "hubbard_observables":
         hubbard_observables_fixture()
         sys.exit(0)
@@ -376,6 +412,7 @@ if __name__ == "__main__":
     hubbard_fixture("hubbard_L4_U4_b4", 6, dict())                      # BASELINE config C1
     hubbard_fixture("hubbard_L4_cb", 4, dict(checkerboard=True, U=6.0, mu=0.3, m=24, s=5))
     hubbard_observables_fixture()
+    pt_reference_fixture()
     config_stream_fixture()
     observables_fixture()
     fermion_fixture()

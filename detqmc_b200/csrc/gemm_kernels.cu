@@ -322,9 +322,155 @@ zgemm_rank_update_kernel(GemmArgs g) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Rank-K update, second generation:  C += alpha * A(M x K) * B(K x N),  K <= 32 per pass.
+// The operand panels go from global to shared memory with cp.async (16-byte LDGSTS, no register staging) in their
+// natural interleaved complex layout and stay in flight while the accumulators are loaded from C; fragments are read
+// with one LDS.128 per complex element (leading dimensions == 2 (mod 8) complex elements: the 4 k-rows x 2 elements
+// a quarter warp reads fall into 8 distinct 16-byte bank groups).  alpha is applied to the A fragments in registers.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+template <int WM, int WN, int MB, int NB>
+__global__ void __launch_bounds__(32 * WM * WN, (WM * WN <= 4 ? 3 : (WM * WN <= 8 ? 2 : 1)))
+zgemm_rank_update2_kernel(GemmArgs g) {
+    pdl_enter();
+    constexpr int TM = 8 * MB * WM, TN = 8 * NB * WN, LDA = TM + 2, LDB = TN + 2, NT = 32 * WM * WN;
+    static_assert(LDA % 8 == 2 && LDB % 8 == 2, "fragment loads need leading dimensions == 2 (mod 8)");
+    extern __shared__ __align__(16) double smem[];
+    cplx* As = reinterpret_cast<cplx*>(smem);              // [KT][LDA]
+    cplx* Bs = As + KT * LDA;                              // [KT][LDB]
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int wm = warp % WM, wn = warp / WM;
+    const int grp = lane >> 2, t4 = lane & 3;
+    const int b = blockIdx.z;
+    const int m0 = blockIdx.x * TM, n0 = blockIdx.y * TN;
+    const int K = g.kvec ? min(g.kvec[b], g.K) : g.K;
+    if (K <= 0) return;
+
+    const cplx* __restrict__ A = g.A + size_t(b) * g.strideA;
+    const cplx* __restrict__ B = g.B + size_t(b) * g.strideB;
+    cplx* __restrict__ Cm = g.C + size_t(b) * g.strideC;
+    const cplx zero = make_double2(0, 0);
+
+    auto stage = [&](int kc, int Kc, int K4) {
+        for (int idx = tid; idx < TM * K4; idx += NT) {
+            const int mm = idx % TM, kk = idx / TM;
+            const int gm = m0 + mm;
+            cplx* dst = As + kk * LDA + mm;
+            if (gm < g.M && kk < Kc) cp_async16(dst, A + size_t(kc + kk) * g.lda + gm);
+            else *dst = zero;
+        }
+        if (g.b_kmajor) {
+            for (int idx = tid; idx < TN * K4; idx += NT) {
+                const int nn = idx % TN, kk = idx / TN;
+                const int gn = n0 + nn;
+                cplx* dst = Bs + kk * LDB + nn;
+                if (gn < g.N && kk < Kc) cp_async16(dst, B + size_t(kc + kk) * g.ldb + gn);
+                else *dst = zero;
+            }
+        } else {
+            for (int idx = tid; idx < TN * K4; idx += NT) {
+                const int kk = idx % K4, nn = idx / K4;
+                const int gn = n0 + nn;
+                cplx* dst = Bs + kk * LDB + nn;
+                if (gn < g.N && kk < Kc) cp_async16(dst, B + size_t(gn) * g.ldb + kc + kk);
+                else *dst = zero;
+            }
+        }
+        cp_async_commit();
+    };
+
+    // the first (usually only) pass of the panels is in flight while the accumulators are loaded from C
+    const int Kc0 = min(KT, K), K40 = (Kc0 + 3) & ~3;
+    stage(0, Kc0, K40);
+
+    double acc_re[MB][NB][2], acc_im[MB][NB][2];
+#pragma unroll
+    for (int mb = 0; mb < MB; ++mb) {
+        const int gm = m0 + wm * (8 * MB) + mb * 8 + grp;
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int gn = n0 + wn * (8 * NB) + nb * 8 + 2 * t4 + e;
+                cplx c = zero;
+                if (gm < g.M && gn < g.N) c = Cm[size_t(gn) * g.ldc + gm];
+                acc_re[mb][nb][e] = c.x;
+                acc_im[mb][nb][e] = c.y;
+            }
+    }
+    const double alpha = g.alpha;
+    for (int kc = 0; kc < K; kc += KT) {
+        const int Kc = min(KT, K - kc);
+        const int K4 = (Kc + 3) & ~3;
+        if (kc > 0) {
+            __syncthreads();
+            stage(kc, Kc, K4);
+        }
+        cp_async_wait_all();
+        __syncthreads();
+        for (int k4 = 0; k4 < K4; k4 += 4) {
+            double ar[MB], ai[MB], nai[MB], br[NB], bi[NB];
+#pragma unroll
+            for (int mb = 0; mb < MB; ++mb) {
+                const cplx a = As[(k4 + t4) * LDA + wm * (8 * MB) + mb * 8 + grp];
+                ar[mb] = alpha * a.x;
+                ai[mb] = alpha * a.y;
+                nai[mb] = -ai[mb];
+            }
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb) {
+                const cplx bb = Bs[(k4 + t4) * LDB + wn * (8 * NB) + nb * 8 + grp];
+                br[nb] = bb.x;
+                bi[nb] = bb.y;
+            }
+#pragma unroll
+            for (int mb = 0; mb < MB; ++mb)
+#pragma unroll
+                for (int nb = 0; nb < NB; ++nb) {
+                    dmma(acc_re[mb][nb][0], acc_re[mb][nb][1], ar[mb], br[nb]);
+                    dmma(acc_re[mb][nb][0], acc_re[mb][nb][1], nai[mb], bi[nb]);
+                    dmma(acc_im[mb][nb][0], acc_im[mb][nb][1], ar[mb], bi[nb]);
+                    dmma(acc_im[mb][nb][0], acc_im[mb][nb][1], ai[mb], br[nb]);
+                }
+        }
+    }
+#pragma unroll
+    for (int mb = 0; mb < MB; ++mb) {
+        const int gm = m0 + wm * (8 * MB) + mb * 8 + grp;
+        if (gm >= g.M) continue;
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int gn = n0 + wn * (8 * NB) + nb * 8 + 2 * t4 + e;
+                if (gn >= g.N) continue;
+                Cm[size_t(gn) * g.ldc + gm] = make_double2(acc_re[mb][nb][e], acc_im[mb][nb][e]);
+            }
+    }
+}
+
 template <int WM, int WN, int MB, int NB>
 cudaError_t launch_rank_update(const GemmArgs& g, cudaStream_t st) {
     constexpr int TM = 8 * MB * WM, TN = 8 * NB * WN;
+    static const bool legacy = std::getenv("DQMC_RANKUPD_LEGACY") != nullptr;
+    // complex leading dimensions of the cp.async variant must be == 2 (mod 8); alignment: 16-byte elements throughout
+    if (!legacy && (TM + 2) % 8 == 2 && (TN + 2) % 8 == 2) {
+        const size_t smem2 = size_t(KT) * (TM + 2 + TN + 2) * sizeof(cplx);
+        cudaError_t e2 = cudaFuncSetAttribute(zgemm_rank_update2_kernel<WM, WN, MB, NB>,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+        if (e2 != cudaSuccess) return e2;
+        dim3 grid2((g.M + TM - 1) / TM, (g.N + TN - 1) / TN, g.batch);
+        launch_pdl(zgemm_rank_update2_kernel<WM, WN, MB, NB>, dim3(grid2), dim3(32 * WM * WN), smem2, st, g);
+        return cudaGetLastError();
+    }
     const size_t smem = size_t(2) * KT * (TM + 4 + TN + 4) * sizeof(double);
     cudaError_t e = cudaFuncSetAttribute(zgemm_rank_update_kernel<WM, WN, MB, NB>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -106,7 +106,7 @@ class ClockSampler:
 def _ref_worker(args):
     """One replica on one host core through the UNMODIFIED reference (oracle/_ref), or the NumPy port
     when the reference library has not been built.  Returns (kind, sweeps, seconds)."""
-    idx, r, sweeps = args
+    idx, r, sweeps, warm = args
     os.environ["OPENBLAS_NUM_THREADS"] = "1"
     os.environ["OMP_NUM_THREADS"] = "1"
     import ref_bindings as rb
@@ -116,25 +116,33 @@ def _ref_worker(args):
     # untimed, so that the timed window starts one sweep after a global move like the GPU arm's windows
     if rb.available():
         rep = rb.RefSdw(p)
-        rep.sweep(therm=True)
+        for _ in range(warm):
+            rep.sweep(therm=True)
         t0 = time.perf_counter()
         for _ in range(sweeps):
             rep.sweep(therm=True)
         return "reference", sweeps, time.perf_counter() - t0
     rep = SdwOracle(p)
-    rep.sweep_thermalization()
+    for _ in range(warm):
+        rep.sweep_thermalization()
     t0 = time.perf_counter()
     for _ in range(sweeps):
         rep.sweep_thermalization()
     return "port", sweeps, time.perf_counter() - t0
 
 
-def cpu_baseline(n_procs, sweeps_each, P):
+def cpu_baseline(n_procs, sweeps_each, P, warm=1):
     """Bounded sample of the same workload on the host cores: n_procs replicas of the ladder, one
     single-threaded process each (the reference's own parallel model: one MPI rank per replica)."""
     import multiprocessing as mp
+    try:                                                   # map the reference library in this process as well, so that
+        import ref_bindings as rb                          # a loader hook on the parent sees which native code runs
+        if rb.available():
+            rb.lib()
+    except Exception:
+        pass
     vals = ladder_values(P)
-    jobs = [(i + 1, vals[i * P // n_procs], sweeps_each) for i in range(n_procs)]
+    jobs = [(i + 1, vals[i * P // n_procs], sweeps_each, warm) for i in range(n_procs)]
     t0 = time.perf_counter()
     with mp.get_context("fork").Pool(n_procs) as pool:
         res = pool.map(_ref_worker, jobs)
@@ -143,9 +151,10 @@ def cpu_baseline(n_procs, sweeps_each, P):
     sweep_time = max(r[2] for r in res)                     # excludes construction
     total = sum(r[1] for r in res)
     return {"value": total / sweep_time, "unit": "replica-sweeps/s", "cores": n_procs, "kind": kind,
+            "per_core": total / sweep_time / n_procs, "timed_s": sweep_time,
             "sample": "%d replicas of the ladder x %d sweeps each, one single-threaded process per replica "
-                      "(OPENBLAS_NUM_THREADS=1), construction and one warm-up sweep (the one with the global-shift move) "
-                      "excluded; wall %.1f s" % (n_procs, sweeps_each, wall)}
+                      "(OPENBLAS_NUM_THREADS=1), construction and %d warm-up sweep(s) (the first one holds the global-shift "
+                      "move) excluded; wall %.1f s" % (n_procs, sweeps_each, warm, wall)}
 
 
 def run_reference(args):
@@ -154,13 +163,20 @@ def run_reference(args):
         return
     cores = os.cpu_count() or 1
     n_procs = max(1, min(cores, args.replicas))
-    steps = max(1, min(args.steps, 2))                      # each step = one sweep per sampled replica
-    base = cpu_baseline(n_procs, steps, args.replicas)
+    # a step of this arm = one sweep of the SAMPLED replicas (one per host core, all cores busy); --steps / --warmup are
+    # honoured up to 8 / 2 (7-16 s per sweep and core: the whole run stays within a few minutes) and reported as run
+    steps = max(1, min(args.steps, 8))
+    warm = max(1, min(args.warmup, 2))
+    base = cpu_baseline(n_procs, steps, args.replicas, warm)
     line = {"impl": "reference", "metric": "DetSDW O(2) L=12 beta=10 sweeps/sec", "value": base["value"],
-            "unit": "replica-sweeps/s", "n_gpus": args.gpus, "steps": steps, "warmup": 1,
-            "ms_per_step": 1e3 * args.replicas / base["value"], "higher_is_better": True, "scaling": "strong",
+            "unit": "replica-sweeps/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+            "ms_per_step": 1e3 * base["timed_s"] / steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64 (complex128)", "data": "synthetic",
-            "config": {"workload": workload_name(args.replicas), "replicas": args.replicas},
+            "config": {"workload": workload_name(args.replicas), "replicas": args.replicas,
+                       "replicas_per_step": n_procs,
+                       "note": "value = replica-sweeps per second of this host (%d cores, one replica per core); a step "
+                               "sweeps %d of the %d replicas, ms_per_step is the time of such a step; per core: see "
+                               "cpu_baseline.per_core" % (n_procs, n_procs, args.replicas)},
             "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": "replica-sweeps/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0}}
@@ -377,12 +393,19 @@ def run_b200(args):
             fl = 4.0 * D ** 3 * R
             entry.update(bound="tensor", achieved=fl / (per * 1e-3) / 1e12, peak=fp64_peak, unit="TFLOP/s")
         elif name == "update_slice":
-            # propose/decide rounds: row/column gathers ~ 2 * 8 * MSF * D * K per accepted update, K ~ MSF*delay/2;
-            # a strictly sequential Metropolis chain: latency bound by construction
-            fl_step = acc_per_step * 16.0 * msf * D * (msf * WORKLOAD["delaySteps"] / 2.0)
+            # window rounds: per accepted update a rank-MSF update of the future part of the (MSF w)^2 window block
+            # (on average a third of it) + the K x K coefficient recurrences; a strictly sequential Metropolis chain:
+            # latency bound by construction, one CTA per replica
+            wp = msf * 2 * WORKLOAD["delaySteps"]
+            fl_step = acc_per_step * 8.0 * msf * (wp * wp / 3.0 + 2.0 * msf * WORKLOAD["delaySteps"] * wp)
             fl = fl_step / (cnt / prof_steps)
             entry.update(bound="tensor", achieved=fl / (per * 1e-3) / 1e12, peak=fp64_peak, unit="TFLOP/s",
-                         note="sequential Metropolis chain: latency bound")
+                         note="sequential Metropolis chain on one SM per replica: latency bound")
+        elif name == "update_build_xy":
+            # gather: per accepted update MSF columns of G copied (read + write), MSF rows read, MSF rows of Y written
+            by = acc_per_step * msf * 4.0 * D * 16 / (cnt / prof_steps)
+            entry.update(bound="hbm", achieved=by / (per * 1e-3) / 1e9, peak=hbm_peak, unit="GB/s",
+                         note="strided row gathers + K x K x D products on the FP64 pipe; launches of finished rounds are empty")
         elif name == "update_flush":
             # rank-K flush G += X Y: 8 D^2 MSF flop per accepted update (launches of finished rounds are empty)
             fl = acc_per_step * 8.0 * D * D * msf / (cnt / prof_steps)
@@ -393,12 +416,18 @@ def run_b200(args):
     dominant = max((n for n in fam if "frac" in fam[n]), key=lambda n: fam[n]["ms_per_step"])
     dom = fam[dominant]
     traffic = None
-    tr_path = os.path.join(ROOT, "profiles", "traffic_r01.json")
-    if os.path.exists(tr_path):
-        try:
-            traffic = json.load(open(tr_path)).get(dominant)
-        except Exception:
-            traffic = None
+    for tr_name in ("traffic_r02.json", "traffic_r01.json"):       # dram bytes per launch from the ncu captures
+        tr_path = os.path.join(ROOT, "profiles", tr_name)
+        if os.path.exists(tr_path):
+            try:
+                tr = json.load(open(tr_path))
+                for fname, entry in fam.items():
+                    if fname in tr:
+                        entry["traffic"] = tr[fname]
+                traffic = tr.get(dominant)
+            except Exception:
+                traffic = None
+            break
     roofline = {"kernel": dominant, "bound": dom["bound"], "achieved": dom["achieved"], "peak": dom["peak"],
                 "unit": dom["unit"], "frac": dom["frac"], "traffic": traffic,
                 "peak_source": hbm_src if dom["bound"] == "hbm" else

@@ -133,6 +133,7 @@ struct GemmArgs {
     int batch;
 };
 cudaError_t gemm_launch(const GemmArgs& g, cudaStream_t st);
+int gemm_matrices_in_flight();
 void gemm_set_matrices_in_flight(int n);   // tile-shape hint: matrices of all lanes that are in flight on the device
 
 // ------------------------------------------------------------------------------------------------

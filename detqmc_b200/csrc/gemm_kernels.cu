@@ -198,6 +198,142 @@ __global__ void __launch_bounds__(32 * WM * WN) zgemm_dmma_kernel(GemmArgs g) {
     }
 }
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------------
+// Batched complex GEMM, second generation: the same tiling and arithmetic as zgemm_dmma_kernel, but the operand tiles
+// travel global -> shared with cp.async (16-byte LDGSTS) through a kStages-deep ring, in their interleaved complex
+// layout; conjugation and the k-scaling are applied to the fragments in registers, one LDS.128 per complex element.
+// The ring keeps kStages - 1 k-tiles in flight, which hides the L2 / HBM latency that the register-staged version
+// exposed between its 8-deep k-tiles (long-scoreboard stalls on the staging stores, profiles/prof_gemm_r02_*).
+// ------------------------------------------------------------------------------------------------
+constexpr int kStages = 4;
+
+template <int WM, int WN, int MB, int NB>
+__global__ void __launch_bounds__(32 * WM * WN) zgemm_dmma2_kernel(GemmArgs g) {
+    pdl_enter();
+    constexpr int TM = 8 * MB * WM, TN = 8 * NB * WN, LDA = TM + 2, LDB = TN + 2, NT = 32 * WM * WN;
+    constexpr int STAGE = BK * (LDA + LDB);                 // cplx elements per stage
+    extern __shared__ __align__(16) double smem[];
+    cplx* ring = reinterpret_cast<cplx*>(smem);
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int wm = warp % WM, wn = warp / WM;
+    const int grp = lane >> 2, t4 = lane & 3;
+    const int b = blockIdx.z;
+    const int m0 = blockIdx.x * TM, n0 = blockIdx.y * TN;
+
+    const cplx* __restrict__ A = g.A + size_t(b) * g.strideA;
+    const cplx* __restrict__ B = g.B + size_t(b) * g.strideB;
+    const double* __restrict__ ks = g.kscale ? g.kscale + size_t(b) * g.strideK : nullptr;
+    const cplx zero = make_double2(0, 0);
+
+    double acc_re[MB][NB][2], acc_im[MB][NB][2];
+#pragma unroll
+    for (int i = 0; i < MB; ++i)
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+            acc_re[i][j][0] = acc_re[i][j][1] = 0.0;
+            acc_im[i][j][0] = acc_im[i][j][1] = 0.0;
+        }
+
+    auto load_tile = [&](int kt) {
+        cplx* As = ring + (kt % kStages) * STAGE;
+        cplx* Bs = As + BK * LDA;
+        const int k0 = kt * BK;
+        for (int idx = tid; idx < TM * BK; idx += NT) {
+            int mm, kk;
+            if (!g.transa) { mm = idx % TM; kk = idx / TM; }
+            else { kk = idx % BK; mm = idx / BK; }
+            const int gm = m0 + mm, gk = k0 + kk;
+            cplx* dst = As + kk * LDA + mm;
+            if (gm < g.M && gk < g.K) cp_async16(dst, g.transa ? A + size_t(gm) * g.lda + gk : A + size_t(gk) * g.lda + gm);
+            else *dst = zero;
+        }
+        for (int idx = tid; idx < TN * BK; idx += NT) {
+            int nn, kk;
+            if (!g.transb) { kk = idx % BK; nn = idx / BK; }
+            else { nn = idx % TN; kk = idx / TN; }
+            const int gn = n0 + nn, gk = k0 + kk;
+            cplx* dst = Bs + kk * LDB + nn;
+            if (gn < g.N && gk < g.K) cp_async16(dst, g.transb ? B + size_t(gk) * g.ldb + gn : B + size_t(gn) * g.ldb + gk);
+            else *dst = zero;
+        }
+    };
+
+    const int nk = (g.K + BK - 1) / BK;
+#pragma unroll
+    for (int s = 0; s < kStages - 1; ++s) {
+        if (s < nk) load_tile(s);
+        cp_async_commit();
+    }
+    const double asign = g.transa ? -1.0 : 1.0, bsign = g.transb ? -1.0 : 1.0;
+    for (int kt = 0; kt < nk; ++kt) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(kStages - 2) : "memory");
+        __syncthreads();                                    // tile kt has landed; everyone is done with tile kt - 1
+        if (kt + kStages - 1 < nk) load_tile(kt + kStages - 1);
+        cp_async_commit();
+        const cplx* As = ring + (kt % kStages) * STAGE;
+        const cplx* Bs = As + BK * LDA;
+#pragma unroll
+        for (int k4 = 0; k4 < BK; k4 += 4) {
+            double ar[MB], ai[MB], nai[MB], br[NB], bi[NB];
+            const int gk = kt * BK + k4 + t4;
+            const double sc = (ks && gk < g.K) ? __ldg(ks + gk) : 1.0;
+#pragma unroll
+            for (int mb = 0; mb < MB; ++mb) {
+                const cplx a = As[(k4 + t4) * LDA + wm * (8 * MB) + mb * 8 + grp];
+                ar[mb] = sc * a.x;
+                ai[mb] = sc * asign * a.y;
+                nai[mb] = -ai[mb];
+            }
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb) {
+                const cplx bb = Bs[(k4 + t4) * LDB + wn * (8 * NB) + nb * 8 + grp];
+                br[nb] = bb.x;
+                bi[nb] = bsign * bb.y;
+            }
+#pragma unroll
+            for (int mb = 0; mb < MB; ++mb)
+#pragma unroll
+                for (int nb = 0; nb < NB; ++nb) {
+                    dmma(acc_re[mb][nb][0], acc_re[mb][nb][1], ar[mb], br[nb]);
+                    dmma(acc_re[mb][nb][0], acc_re[mb][nb][1], nai[mb], bi[nb]);
+                    dmma(acc_im[mb][nb][0], acc_im[mb][nb][1], ar[mb], bi[nb]);
+                    dmma(acc_im[mb][nb][0], acc_im[mb][nb][1], ai[mb], br[nb]);
+                }
+        }
+    }
+
+    // ---- epilogue
+    cplx* __restrict__ Cm = g.C + size_t(b) * g.strideC;
+    const double* __restrict__ rs = g.rowscale ? g.rowscale + size_t(b) * g.strideRow : nullptr;
+    const double* __restrict__ cs = g.colscale ? g.colscale + size_t(b) * g.strideCol : nullptr;
+#pragma unroll
+    for (int mb = 0; mb < MB; ++mb) {
+        const int gm = m0 + wm * (8 * MB) + mb * 8 + grp;
+        if (gm >= g.M) continue;
+        const double rsc = rs ? rs[gm] : 1.0;
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int gn = n0 + wn * (8 * NB) + nb * 8 + 2 * t4 + e;
+                if (gn >= g.N) continue;
+                const double sc = g.alpha * rsc * (cs ? cs[gn] : 1.0);
+                cplx v = make_double2(acc_re[mb][nb][e] * sc, acc_im[mb][nb][e] * sc);
+                cplx* dst = Cm + size_t(gn) * g.ldc + gm;
+                if (g.beta != 0.0) { const cplx o = *dst; v.x += o.x; v.y += o.y; }
+                *dst = v;
+            }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Rank-K update  C += alpha * A(M x K) * B(K x N)  for small K (one shared-memory pass per 32): the delayed-update flush G += X*Y
 // (detsdwopdim.cpp:3156), the block-reflector updates of the QR (A2 -= V W) and the triangular
@@ -329,12 +465,6 @@ zgemm_rank_update_kernel(GemmArgs g) {
 // with one LDS.128 per complex element (leading dimensions == 2 (mod 8) complex elements: the 4 k-rows x 2 elements
 // a quarter warp reads fall into 8 distinct 16-byte bank groups).  alpha is applied to the A fragments in registers.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 template <int WM, int WN, int MB, int NB>
 __global__ void __launch_bounds__(32 * WM * WN, (WM * WN <= 4 ? 3 : (WM * WN <= 8 ? 2 : 1)))
@@ -483,6 +613,19 @@ cudaError_t launch_rank_update(const GemmArgs& g, cudaStream_t st) {
 template <int WM, int WN, int MB, int NB>
 cudaError_t launch_cfg(const GemmArgs& g, cudaStream_t st) {
     typedef GemmCfg<WM, WN, MB, NB> C;
+    static const bool legacy = std::getenv("DQMC_GEMM_LEGACY") != nullptr;
+    static const bool always = std::getenv("DQMC_GEMM_RING_ALWAYS") != nullptr;
+    // the cp.async ring pays for tiles with enough arithmetic per k-step; the skinny panel products of the blocked
+    // QR (32-wide tiles) measured slower with it
+    if (!legacy && (always || (C::TM >= 48 && C::TN >= 48))) {
+        const size_t smem2 = size_t(kStages) * BK * (C::TM + 2 + C::TN + 2) * sizeof(cplx);
+        cudaError_t e2 = cudaFuncSetAttribute(zgemm_dmma2_kernel<WM, WN, MB, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)smem2);
+        if (e2 != cudaSuccess) return e2;
+        dim3 grid2((g.M + C::TM - 1) / C::TM, (g.N + C::TN - 1) / C::TN, g.batch);
+        launch_pdl(zgemm_dmma2_kernel<WM, WN, MB, NB>, dim3(grid2), dim3(C::NT), smem2, st, g);
+        return cudaGetLastError();
+    }
     const size_t smem = C::SMEM_DOUBLES * sizeof(double);
     cudaError_t e = cudaFuncSetAttribute(zgemm_dmma_kernel<WM, WN, MB, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem);
@@ -499,6 +642,7 @@ cudaError_t launch_cfg(const GemmArgs& g, cudaStream_t st) {
 // launch, same arithmetic in the same order (results do not depend on the tile shape).
 static int g_matrices_in_flight = 1 << 30;
 void gemm_set_matrices_in_flight(int n) { g_matrices_in_flight = n > 0 ? n : 1 << 30; }
+int gemm_matrices_in_flight() { return g_matrices_in_flight; }
 
 // programmatic dependent launch (dqmc_internal.h): on for small batches unless DQMC_PDL=0 / 1 says otherwise
 static bool g_pdl = false;

@@ -164,6 +164,87 @@ void cb_build_shift_matrices(const dqmc_params& p, int msf, std::vector<cplx>& S
     }
 }
 
+// Dense hopping propagators of DetSDW<CB_NONE> (setupPropK, detsdwopdim.cpp:1210-1286; computePropagator,
+// detmodel.cpp:31-39): block b (band b % 2) of P is exp(-dtau k_band), of Pinv exp(+dtau k_band), with the Hermitian
+// single-particle matrix k = -mu - hoppings (antiperiodic signs across the boundary, Peierls phases of the weak flux).
+// The reference diagonalises k; here exp() is a scaled Taylor series with repeated squaring (|dtau k| < 1).
+static void expm_dense(const std::vector<zc>& A, int n, std::vector<zc>& out) {
+    double nrm = 0;
+    for (int r = 0; r < n; ++r) {
+        double row = 0;
+        for (int c = 0; c < n; ++c) row += std::abs(A[size_t(r) * n + c]);
+        nrm = std::max(nrm, row);
+    }
+    int sq = 0;
+    double scale = 1.0;
+    while (nrm * scale > 0.25) { scale *= 0.5; ++sq; }
+    std::vector<zc> S(A.size()), term(A.size()), acc(A.size()), tmp(A.size());
+    for (size_t i = 0; i < A.size(); ++i) S[i] = A[i] * scale;
+    for (int r = 0; r < n; ++r)
+        for (int c = 0; c < n; ++c) acc[size_t(r) * n + c] = term[size_t(r) * n + c] = (r == c) ? 1.0 : 0.0;
+    auto mul = [&](const std::vector<zc>& X, const std::vector<zc>& Y, std::vector<zc>& Z) {
+        std::fill(Z.begin(), Z.end(), zc(0));
+        for (int r = 0; r < n; ++r)
+            for (int k = 0; k < n; ++k) {
+                const zc x = X[size_t(r) * n + k];
+                if (x == zc(0)) continue;
+                for (int c = 0; c < n; ++c) Z[size_t(r) * n + c] += x * Y[size_t(k) * n + c];
+            }
+    };
+    for (int k = 1; k <= 20; ++k) {
+        mul(term, S, tmp);
+        for (size_t i = 0; i < tmp.size(); ++i) { term[i] = tmp[i] / double(k); acc[i] += term[i]; }
+    }
+    for (int q = 0; q < sq; ++q) {
+        mul(acc, acc, tmp);
+        acc.swap(tmp);
+    }
+    out = acc;
+}
+
+void cb_build_dense_propagators(const dqmc_params& p, int msf, std::vector<cplx>& P, std::vector<cplx>& Pinv) {
+    const int L = p.L, N = L * L, D = msf * N;
+    const double pi = M_PI;
+    P.assign(size_t(D) * D, make_double2(0, 0));
+    Pinv.assign(size_t(D) * D, make_double2(0, 0));
+    for (int band = 0; band < 2; ++band) {
+        const double hh = band == 0 ? p.txhor : p.tyhor, hv = band == 0 ? p.txver : p.tyver;
+        const double mu = band == 0 ? p.mux : p.muy;
+        const double zmag = p.weakZflux ? 1.0 / N : 0.0;             // zmag[XUP] = zmag[YDOWN] = +1/N (:219-220)
+        std::vector<zc> k(size_t(N) * N, zc(0));                      // row-major k(site, neigh)
+        for (int site = 0; site < N; ++site) k[size_t(site) * N + site] = -mu;
+        for (int site = 0; site < N; ++site) {
+            const int x = site % L, y = site / L;
+            for (int dir = 0; dir < 4; ++dir) {                       // XPLUS, XMINUS, YPLUS, YMINUS
+                int nx = x, ny = y;
+                double hop = dir < 2 ? hh : hv;
+                zc phase = 1.0;
+                if (dir == 0) { nx = (x + 1) % L; if ((p.bc == 1 || p.bc == 3) && x == L - 1) hop = -hop;
+                                phase = std::exp(zc(0, -2.0 * pi * zmag * y)); }
+                if (dir == 1) { nx = (x + L - 1) % L; if ((p.bc == 1 || p.bc == 3) && x == 0) hop = -hop;
+                                phase = std::exp(zc(0, +2.0 * pi * zmag * y)); }
+                if (dir == 2) { ny = (y + 1) % L; if ((p.bc == 2 || p.bc == 3) && y == L - 1) hop = -hop;
+                                if (y == L - 1) phase = std::exp(zc(0, +2.0 * pi * zmag * L * x)); }
+                if (dir == 3) { ny = (y + L - 1) % L; if ((p.bc == 2 || p.bc == 3) && y == 0) hop = -hop;
+                                if (y == 0) phase = std::exp(zc(0, -2.0 * pi * zmag * L * x)); }
+                k[size_t(site) * N + ny * L + nx] -= hop * phase;
+            }
+        }
+        std::vector<zc> a(k.size()), em, ep;
+        for (size_t i = 0; i < k.size(); ++i) a[i] = -p.dtau * k[i];
+        expm_dense(a, N, em);
+        for (size_t i = 0; i < k.size(); ++i) a[i] = +p.dtau * k[i];
+        expm_dense(a, N, ep);
+        for (int b = band; b < msf; b += 2)
+            for (int r = 0; r < N; ++r)
+                for (int c = 0; c < N; ++c) {
+                    const zc m1 = em[size_t(r) * N + c], p1 = ep[size_t(r) * N + c];
+                    P[size_t(b * N + c) * D + b * N + r] = make_double2(m1.real(), m1.imag());        // column-major
+                    Pinv[size_t(b * N + c) * D + b * N + r] = make_double2(p1.real(), p1.imag());
+                }
+    }
+}
+
 void cb_build_tables(const dqmc_params& p, std::vector<cplx>& out) {
     const int L = p.L, N = L * L, nplaq = N / 4, half = L / 2;
     // passes: 0 = subgroup 1, half step; 1 = subgroup 0, full step with the chemical potential; 2 = subgroup 0, half
@@ -437,7 +518,7 @@ __global__ void __launch_bounds__(kCbMaxThreads) cb_mult_kernel(CbGeom g, CbLaun
         const int it0 = threadIdx.x;
         const int pos0 = it0 % N, grp0 = it0 / N;
         if (it0 < pot_items) pc0 = potential_coef<MSF>(phi_k, cosh_k, sinh_k, g, sinv[pos0], a.sign_idx, a.transposed);
-        if (a.k_then_v) hopping_stage<MSF, REALM>(tile, ldt, nv, a.cbtab, g, sh, a.sign_idx, a.transposed);
+        if (a.k_then_v && !a.skip_hopping) hopping_stage<MSF, REALM>(tile, ldt, nv, a.cbtab, g, sh, a.sign_idx, a.transposed);
         if (it0 < pot_items)
             for (int v = grp0; v < nv; v += sh.Gp) potential_apply<MSF>(tile + v * ldt, N, pos0, pc0);
         for (int it = it0 + blockDim.x; it < pot_items; it += blockDim.x) {
@@ -446,7 +527,7 @@ __global__ void __launch_bounds__(kCbMaxThreads) cb_mult_kernel(CbGeom g, CbLaun
             for (int v = grp; v < nv; v += sh.Gp) potential_apply<MSF>(tile + v * ldt, N, pos, pc);
         }
         __syncthreads();
-        if (!a.k_then_v) hopping_stage<MSF, REALM>(tile, ldt, nv, a.cbtab, g, sh, a.sign_idx, a.transposed);
+        if (!a.k_then_v && !a.skip_hopping) hopping_stage<MSF, REALM>(tile, ldt, nv, a.cbtab, g, sh, a.sign_idx, a.transposed);
     }
 
     // ---- store (in place unless an output matrix is given)

@@ -126,6 +126,72 @@ int gemm(dqmc_ctx* ctx, int ta, int tb, const cplx* A, long long sA, const cplx*
          const double* ks, long long sK, double beta, int batch);
 int hub_bmult(dqmc_ctx* ctx, int op, cplx* A, long long strideA, int k2, int k1, const double* colscale,
               long long strideScale, int off, int batch);
+int sdw_bmult_dense(dqmc_ctx* ctx, const OpSpec& o, cplx* A, long long strideA, int k2, int k1, const double* colscale,
+                    long long strideScale, int off, int batch);
+
+// Dense hopping path (DetSDW<CB_NONE>: computeBmatSDW, detsdwopdim.cpp:1307-1497; the reference's sweepSimple uses it
+// for every model, :4366-4420): B_k = e^{-dtau V_k} e^{-dtau K}.  The hopping factor is a D x D GEMM with the
+// block-diagonal propagator, the potential factor the potential stage of cb_mult_kernel (no plaquette passes).
+int ensure_dense(dqmc_ctx* ctx) {
+    if (ctx->denseP) return DQMC_OK;
+    std::vector<cplx> P, Pinv;
+    cb_build_dense_propagators(ctx->p, ctx->msf, P, Pinv);
+    CK(dmalloc(&ctx->denseP, P.size()));
+    CK(dmalloc(&ctx->densePinv, Pinv.size()));
+    CK(dmalloc(&ctx->denseTmp, DD(ctx) * size_t(ctx->nmat)));
+    CK(cudaMemcpy(ctx->denseP, P.data(), P.size() * sizeof(cplx), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->densePinv, Pinv.data(), Pinv.size() * sizeof(cplx), cudaMemcpyHostToDevice));
+    return DQMC_OK;
+}
+
+int sdw_bmult_dense(dqmc_ctx* ctx, const OpSpec& o, cplx* A, long long strideA, int k2, int k1, const double* colscale,
+                    long long strideScale, int off, int batch) {
+    RET(ensure_dense(ctx));
+    const size_t dd = DD(ctx);
+    cplx* tmp = ctx->denseTmp + size_t(off) * dd;
+    const cplx* Pm = o.sign_idx == 0 ? ctx->denseP : ctx->densePinv;
+    CbLaunch a;
+    a.strideA = strideA;
+    a.phi = ctx->phi + size_t(off) * phi_stride(ctx);
+    a.coshT = ctx->coshT + size_t(off) * tab_stride(ctx);
+    a.sinhT = ctx->sinhT + size_t(off) * tab_stride(ctx);
+    a.stridePhi = (long long)phi_stride(ctx);
+    a.strideTab = (long long)tab_stride(ctx);
+    a.cbtab = ctx->cbtab;
+    a.real_tables = ctx->p.weakZflux ? 0 : 1;
+    a.kstep = 1; a.kcount = 1;
+    a.rows = o.rows; a.k_then_v = o.k_then_v; a.sign_idx = o.sign_idx; a.transposed = o.transposed;
+    a.strideScale = strideScale;
+    a.batch = batch;
+    a.skip_hopping = 1;
+    const int n = k2 - k1;
+    for (int i = 0; i < n; ++i) {
+        const int k = o.ascending ? k1 + 1 + i : k2 - i;
+        const bool last = i == n - 1;
+        a.kfirst = k;
+        // hopping factor: tmp = Pm * X (columns) or X * Pm (rows)
+        auto hop = [&](const cplx* X, long long sX, const double* cols, long long sCol) {
+            if (!o.rows) return gemm(ctx, 0, 0, Pm, 0, X, sX, tmp, (long long)dd, nullptr, 0, cols, sCol, nullptr, 0, 0.0, batch);
+            return gemm(ctx, 0, 0, X, sX, Pm, 0, tmp, (long long)dd, nullptr, 0, cols, sCol, nullptr, 0, 0.0, batch);
+        };
+        if (o.k_then_v) {
+            RET(hop(A, strideA, nullptr, 0));
+            a.A = tmp; a.strideA = (long long)dd;
+            a.out = A; a.strideOut = strideA;
+            a.colscale = last ? colscale : nullptr;
+            CKL(cb_launch(ctx->geom, a, ctx->stream));
+        } else {
+            a.A = A; a.strideA = strideA;
+            a.out = nullptr; a.strideOut = 0;
+            a.colscale = nullptr;
+            CKL(cb_launch(ctx->geom, a, ctx->stream));
+            RET(hop(A, strideA, last ? colscale : nullptr, strideScale));
+            CK(cudaMemcpy2DAsync(A, size_t(strideA) * sizeof(cplx), tmp, dd * sizeof(cplx), dd * sizeof(cplx), batch,
+                                 cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+    }
+    return DQMC_OK;
+}
 
 // B-matrix multiply of the model: `off` / `batch` count MATRICES (== replicas for DetSDW)
 int sdw_bmult(dqmc_ctx* ctx, int op, cplx* A, long long strideA, int k2, int k1, const double* colscale,
@@ -133,6 +199,7 @@ int sdw_bmult(dqmc_ctx* ctx, int op, cplx* A, long long strideA, int k2, int k1,
     if (k2 <= k1) return DQMC_OK;
     if (ctx->p.model == DQMC_MODEL_HUBBARD) return hub_bmult(ctx, op, A, strideA, k2, k1, colscale, strideScale, off, batch);
     const OpSpec& o = kOps[op];
+    if (ctx->denseNow) return sdw_bmult_dense(ctx, o, A, strideA, k2, k1, colscale, strideScale, off, batch);
     CbLaunch a;
     a.A = A;
     a.strideA = strideA;
@@ -977,6 +1044,7 @@ int measure_slice(dqmc_ctx* ctx) {
                                ctx->fmAcc + size_t(ro) * ctx->fmAccLen, (long long)ctx->fmAccLen, rc, ctx->stream));
         return DQMC_OK;
     }
+    if (ctx->denseNow) { ctx->err = "fermionic measurements are served with the checkerboard break-up only"; return DQMC_ERR_STATE; }
     cplx* G = ctx->G + size_t(ro) * dd;
     cplx* gs = ctx->W[1] + size_t(ro) * dd;
     // gs = E0(-h) E1(-h) G E1(+h) E0(+h), h = dtau / 2: two checkerboard passes (the first one out of place)
@@ -1140,6 +1208,7 @@ int dqmc_create(const dqmc_params* params, int n_replicas, int device, dqmc_ctx*
     ctx->lastSweepDir = +1;
     ctx->performedSweeps = 0;
     ctx->rngWindow = 0;
+    ctx->denseNow = !hub && p.denseHopping != 0;
 
     int ndev = 0;
     (void)cudaGetLastError();        // do not inherit a stale error from an earlier failed call
@@ -1324,7 +1393,7 @@ void dqmc_destroy(dqmc_ctx* ctx) {
                    ctx->stQ, ctx->stT, ctx->stD, ctx->bkQ, ctx->bkT, ctx->bkD, ctx->phi, ctx->coshT, ctx->sinhT,
                    ctx->bkPhi, ctx->bkCosh, ctx->bkSinh, ctx->rvals, ctx->tau, ctx->perm, ctx->colnorm, ctx->vecA,
                    ctx->vecB, ctx->vecC, ctx->vecD, ctx->dtmp, ctx->logdet, ctx->bkLogdet, ctx->consistency, ctx->eyeM,
-                   ctx->onesV, ctx->X, ctx->Y, ctx->winScratch, ctx->winHdr, ctx->cfgStream, ctx->shiftL, ctx->shiftR, ctx->fmAcc, ctx->rngbuf, ctx->cursor, ctx->ctrl, ctx->accepted, ctx->errflag,
+                   ctx->onesV, ctx->X, ctx->Y, ctx->winScratch, ctx->winHdr, ctx->cfgStream, ctx->shiftL, ctx->shiftR, ctx->denseP, ctx->densePinv, ctx->denseTmp, ctx->fmAcc, ctx->rngbuf, ctx->cursor, ctx->ctrl, ctx->accepted, ctx->errflag,
                    ctx->actions, ctx->shiftbuf, ctx->cbtab, ctx->acceptedTotal, ctx->siteState, ctx->cursorAdd, ctx->kvec, ctx->aux,
                    ctx->propT, ctx->propTinv, ctx->hubScale, ctx->hubTmp, ctx->hubReal};
     for (void* p : dev) if (p) cudaFree(p);
@@ -1746,7 +1815,11 @@ int dqmc_sweep_simple(dqmc_ctx* ctx, int thermalization) {
     RET(sc.alloc(ctx));
     int rc = DQMC_OK;
     const size_t window = size_t(ctx->N) * (ctx->p.opdim + 1) * size_t(std::max(1, ctx->p.repeatUpdateInSlice));
+    // the reference builds the B matrices of this sweep with the dense hopping exponential whatever the checkerboard
+    // setting (sweepSimple_skeleton with sdwComputeBmat -> computeBmatSDW, detsdwopdim.cpp:4366-4420, 1307-1497)
+    const bool denseBefore = ctx->denseNow;
     for (int k = 1; k <= ctx->m && rc == DQMC_OK; ++k) {
+        ctx->denseNow = true;
         for (int mat = 0; mat < ctx->nmat && rc == DQMC_OK; ++mat) {
             rc = green_for_timeslice_dev(ctx, mat, k, sc);
             if (rc == DQMC_OK &&
@@ -1756,10 +1829,12 @@ int dqmc_sweep_simple(dqmc_ctx* ctx, int thermalization) {
                 rc = DQMC_ERR_CUDA;
             }
         }
+        ctx->denseNow = denseBefore;
         if (rc == DQMC_OK) rc = upload_rng_window(ctx, window);
         if (rc == DQMC_OK) rc = launch_update(ctx, k, thermalization);
         if (rc == DQMC_OK) rc = finish_rng_window(ctx);
     }
+    ctx->denseNow = denseBefore;
     cudaStreamSynchronize(ctx->stream);
     sc.release();
     if (rc != DQMC_OK) return rc;

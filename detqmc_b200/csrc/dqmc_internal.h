@@ -74,6 +74,7 @@ struct CbLaunch {
     const double* colscale;  // optional [batch][D]: scale vector v (column v) by colscale[v] on store
     long long strideScale;
     int batch;
+    int skip_hopping = 0;    // 1: potential stage only (the hopping factor is applied as a dense GEMM: CB_NONE path)
     int shift = 0;           // 1: half-step stage of shiftGreenSymmetric (E1 then E0 at +-dtau/2, no potential) instead of B
     cplx* out = nullptr;     // optional output matrices (default: in place)
     long long strideOut = 0;
@@ -82,6 +83,7 @@ struct CbLaunch {
 int cb_table_count(const CbGeom& g);                    // number of cplx in the table
 // host-side construction of the plaquette tables from the model parameters
 void cb_build_tables(const dqmc_params& p, std::vector<cplx>& out);
+void cb_build_dense_propagators(const dqmc_params& p, int msf, std::vector<cplx>& P, std::vector<cplx>& Pinv);
 void cb_build_shift_matrices(const dqmc_params& p, int msf, std::vector<cplx>& SL, std::vector<cplx>& SR);
 cudaError_t cb_launch(const CbGeom& g, const CbLaunch& a, cudaStream_t st);
 
@@ -266,6 +268,9 @@ struct dqmc_ctx {
     std::string err;
     uint64_t launches;
 
+    // dense hopping path (CB_NONE): block-diagonal e^{-+dtau K}, a work matrix per batch member; denseNow switches the
+    // B-matrix multiplies to it (always for denseHopping models, temporarily inside dqmc_sweep_simple)
+    dqmc::cplx* denseP = nullptr; dqmc::cplx* densePinv = nullptr; dqmc::cplx* denseTmp = nullptr; bool denseNow = false;
     // NCCL communicator of the exchange step (dqmc_set_comm); nullptr = single process
     void* comm = nullptr; int commRanks = 0, commRank = 0;
     // sweep state (detmodel.h:463, 481; detsdwopdim.h performedSweeps)

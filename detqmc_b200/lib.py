@@ -16,7 +16,7 @@ class DqmcError(RuntimeError):
 class DqmcParams(ctypes.Structure):
     _fields_ = [("model", c_i32), ("opdim", c_i32), ("L", c_i32), ("m", c_i32), ("s", c_i32), ("bc", c_i32),
                 ("weakZflux", c_i32), ("delaySteps", c_i32), ("globalShift", c_i32),
-                ("globalUpdateInterval", c_i32), ("checkerboard", c_i32), ("reserved0", c_i32),
+                ("globalUpdateInterval", c_i32), ("checkerboard", c_i32), ("denseHopping", c_i32),
                 ("dtau", c_f64), ("r", c_f64), ("c", c_f64), ("u", c_f64), ("lambda_", c_f64),
                 ("txhor", c_f64), ("txver", c_f64), ("tyhor", c_f64), ("tyver", c_f64),
                 ("mux", c_f64), ("muy", c_f64), ("accRatio", c_f64), ("t", c_f64), ("U", c_f64), ("mu", c_f64),

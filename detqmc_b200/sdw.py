@@ -22,7 +22,7 @@ _DEFAULTS = dict(opdim=2, L=4, m=20, s=10, dtau=0.1, r=-1.0, c=3.0, u=1.0, lam=1
                  tyhor=0.5, tyver=1.0, cdwU=0.0, mu=-0.5, accRatio=0.5, weakZflux=True, bc=0, updateMethod=2,
                  delaySteps=16, globalShift=True, globalUpdateInterval=10, repeatUpdateInSlice=1,
                  wolffClusterUpdate=False, wolffClusterShiftUpdate=False, repeatWolffPerSweep=1,
-                 seed=1020304050, rngIndex=1)
+                 checkerboard=True, seed=1020304050, rngIndex=1)
 
 
 def _ptr(a):
@@ -45,6 +45,7 @@ def make_params(pars=None, **kw):
     p.model = 0
     p.opdim, p.L, p.m, p.s, p.bc = d["opdim"], d["L"], d["m"], d["s"], d["bc"]
     p.weakZflux = int(bool(d["weakZflux"]))
+    p.denseHopping = 0 if d.get("checkerboard", True) else 1      # checkerboard = false: DetSDW<CB_NONE>, dense e^{-dtau K}
     # woodbury == delayed with 1 step; iterative (detsdwopdim.cpp:2491-2880) evaluates the same ratio and the same
     # rank-MSF update entry by entry (the reference's fields equal woodbury's sweep by sweep): same kernel
     p.delaySteps = d["delaySteps"] if d["updateMethod"] == 2 else 1
@@ -323,7 +324,7 @@ class DetSDWBatch:
     def sweepSimple(self, takeMeasurements=False):
         """greenUpdate = simple (detsdwopdim.cpp:4366-4393): G from scratch at every slice, then the slice update."""
         if takeMeasurements:
-            raise DqmcError("fermionic measurements are outside the accelerated path (SURVEY 8f)")
+            raise DqmcError("fermionic measurements are served by the stabilized sweep (sweep(True)) only")
         self._ck(self.lib.dqmc_sweep_simple(self.h, 0))
 
     def sweepSimpleThermalization(self):

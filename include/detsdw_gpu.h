@@ -57,7 +57,8 @@ public:
         if (pars.opdim != (uint32_t)OPDIM) throw_GeneralError("DetSDWGpu: opdim mismatch");
         kOccX.zeros(pars.L * pars.L); kOccY.zeros(pars.L * pars.L);
         pairPlus.zeros(pars.L * pars.L); pairMinus.zeros(pars.L * pars.L);
-        if (!pars.checkerboard) throw_GeneralError("DetSDWGpu: the GPU path implements the checkerboard break-up only");
+        if (!pars.checkerboard && !pars.turnoffFermionMeasurements)
+            throw_GeneralError("DetSDWGpu: fermionic measurements are served with the checkerboard break-up only");
         if (pars.turnoffFermions) throw_GeneralError("DetSDWGpu: turnoffFermions is a pure-boson run, use the reference");
         if (pars.cdwU != 0.0) throw_GeneralError("DetSDWGpu: cdwU != 0 is outside the accelerated path");
         // iterative (detsdwopdim.cpp:2491-2880) and woodbury (:2883-3019) evaluate the same ratio and apply the same
@@ -76,6 +77,7 @@ public:
         p.s = (int32_t)pars.s;
         p.bc = pars.bc_string == "pbc" ? 0 : pars.bc_string == "apbc-x" ? 1 : pars.bc_string == "apbc-y" ? 2 : 3;
         p.weakZflux = pars.weakZflux ? 1 : 0;
+        p.denseHopping = pars.checkerboard ? 0 : 1;          // checkerboard = false: DetSDW<CB_NONE, OPDIM>, dense e^{-dtau K}
         p.delaySteps = pars.updateMethod_string == "delayed" ? (int32_t)pars.delaySteps : 1;
         p.globalShift = pars.globalShift ? 1 : 0;
         p.wolffClusterUpdate = pars.wolffClusterUpdate ? 1 : 0;

@@ -62,7 +62,8 @@ typedef struct dqmc_params {
     int32_t globalShift;          /* SDW: attempt global shift moves */
     int32_t globalUpdateInterval; /* SDW: every # sweeps */
     int32_t checkerboard;         /* Hubbard: checkerboard form of e^{-dtau T} (dethubbard.cpp:768-821) */
-    int32_t reserved0;
+    int32_t denseHopping;         /* SDW: 1 = dense hopping exponential e^{-dtau K} (CheckerboardMethod CB_NONE, computeBmatSDW
+                                   * detsdwopdim.cpp:1307-1497) instead of the checkerboard break-up */
     double dtau;
     double r;                     /* SDW: initial value of the exchange parameter for all replicas */
     double c, u, lambda;          /* SDW bosonic action + coupling */

@@ -157,17 +157,17 @@ class SweepSkeleton:
     def sweep_simple_skeleton(self, update):
         """sweepSimple_skeleton / sweepSimpleThermalization_skeleton: for every slice the Green's function is the plain
         inverse of 1 + B(k, 0) B(m, k) (no stabilisation), then the slice is updated.
-        NOTE: the reference builds these B matrices with computeBmatSDW (detsdwopdim.cpp:1307-1497), i.e. with the
-        DENSE hopping exponential even when checkerboard = true, so its simple sweep samples a G that differs from the
-        one of its own stabilised sweep by the O(dtau^2) break-up error (8e-4 at L = 4, beta = 2).  This restatement
-        keeps the checkerboard B of the stabilised path (what the GPU path serves); against the live reference the
-        fields agree sweep by sweep at the test size, G agrees to the break-up error: parity unpinned."""
+        The reference builds these B matrices with computeBmatSDW (detsdwopdim.cpp:1307-1497), i.e. with the DENSE
+        hopping exponential even when checkerboard = true; so does this restatement (force_dense) -- pinned by
+        tests/golden/sdw_dense_hopping.npz (the reference's own simple sweeps)."""
         eye = np.eye(self.sz, dtype=self.dtype)
         for k in range(1, self.m + 1):
+            self.force_dense = True
             for gc in range(len(self.green)):
                 b_k0 = self.left_multiply_bmat(gc, eye, k, 0)
                 b_mk = self.left_multiply_bmat(gc, eye, self.m, k) if k < self.m else eye
                 self.green[gc] = np.linalg.inv(eye + b_k0 @ b_mk)
+            self.force_dense = False
             update(k)
 
     # detmodel.h:953-1017
@@ -359,6 +359,7 @@ class SdwParams:
         self.repeatWolffPerSweep = 1
         self.fermionMeasurements = False    # not turnoffFermionMeasurements
         self.repeatUpdateInSlice = 1
+        self.checkerboard = True            # False: DetSDW<CB_NONE>, dense hopping exponential (reference goldens only)
         self.seed = 1020304050
         self.rngIndex = 1
         for k, v in kw.items():
@@ -536,10 +537,63 @@ class SdwOracle(SweepSkeleton):
                 out[:, c * N:(c + 1) * N] += A[:, r * N:(r + 1) * N] * ev[r, c][None, :]
         return out
 
+    # setupPropK / computePropagator (detsdwopdim.cpp:1210-1286, detmodel.cpp:31-39): dense e^{-+dtau k_band} of
+    # DetSDW<CB_NONE> and of computeBmatSDW (which the reference's sweepSimple uses for every model)
+    def dense_propagators(self):
+        if getattr(self, "_prop", None) is not None:
+            return self._prop
+        p, L, N = self.p, self.p.L, self.N
+        hops = {0: (p.txhor, p.txver), 1: (p.tyhor, p.tyver)}
+        zmag = 1.0 / N if p.weakZflux else 0.0                       # zmag[XUP] = zmag[YDOWN] = +1/N (:219-220)
+        prop = {}
+        for band in (0, 1):
+            hh, hv = hops[band]
+            k = -p.mu * np.eye(N, dtype=np.complex128)
+            for site in range(N):
+                x, y = site % L, site // L
+                for d in range(4):                                   # XPLUS, XMINUS, YPLUS, YMINUS
+                    nx, ny, hop, phase = x, y, (hh if d < 2 else hv), 1.0 + 0j
+                    if d == 0:
+                        nx = (x + 1) % L
+                        if p.bc in (1, 3) and x == L - 1:
+                            hop = -hop
+                        phase = np.exp(-2j * np.pi * zmag * y)
+                    elif d == 1:
+                        nx = (x - 1) % L
+                        if p.bc in (1, 3) and x == 0:
+                            hop = -hop
+                        phase = np.exp(+2j * np.pi * zmag * y)
+                    elif d == 2:
+                        ny = (y + 1) % L
+                        if p.bc in (2, 3) and y == L - 1:
+                            hop = -hop
+                        if y == L - 1:
+                            phase = np.exp(+2j * np.pi * zmag * L * x)
+                    else:
+                        ny = (y - 1) % L
+                        if p.bc in (2, 3) and y == 0:
+                            hop = -hop
+                        if y == 0:
+                            phase = np.exp(-2j * np.pi * zmag * L * x)
+                    k[site, ny * L + nx] -= hop * phase
+            ev, vec = np.linalg.eigh(k)
+            for sign in (-1, +1):                                    # sign = -1: e^{-dtau k} (B), +1: e^{+dtau k} (B^-1)
+                prop[(band, sign)] = (vec * np.exp(sign * p.dtau * ev)) @ vec.conj().T
+        self._prop = prop
+        return prop
+
+    def _dense_now(self):
+        return (not getattr(self.p, "checkerboard", True)) or getattr(self, "force_dense", False)
+
     def _apply_k_left(self, sign, A):
         N = self.N
         mu = self.p.mu
         out = np.empty_like(A)
+        if self._dense_now():
+            prop = self.dense_propagators()
+            for bs in range(self.msf):
+                out[bs * N:(bs + 1) * N, :] = prop[(BAND_OF_BANDSPIN[bs], sign)] @ A[bs * N:(bs + 1) * N, :]
+            return out
         for bs in range(self.msf):
             f = np.exp(-sign * self.p.dtau * mu)       # sign=-1 (B): e^{+dtau mu}; sign=+1: e^{-dtau mu}
             out[bs * N:(bs + 1) * N, :] = f * (self.cb[(BAND_OF_BANDSPIN[bs], sign)] @ A[bs * N:(bs + 1) * N, :])
@@ -549,6 +603,11 @@ class SdwOracle(SweepSkeleton):
         N = self.N
         mu = self.p.mu
         out = np.empty_like(A)
+        if self._dense_now():
+            prop = self.dense_propagators()
+            for bs in range(self.msf):
+                out[:, bs * N:(bs + 1) * N] = A[:, bs * N:(bs + 1) * N] @ prop[(BAND_OF_BANDSPIN[bs], sign)]
+            return out
         for bs in range(self.msf):
             f = np.exp(-sign * self.p.dtau * mu)
             out[:, bs * N:(bs + 1) * N] = f * (A[:, bs * N:(bs + 1) * N] @ self.cb[(BAND_OF_BANDSPIN[bs], sign)])

@@ -21,7 +21,7 @@ class RefSdwParams(ctypes.Structure):
                 ("globalShift", c_i32), ("globalUpdateInterval", c_i32), ("repeatUpdateInSlice", c_i32),
                 ("seed", c_u32), ("rngIndex", c_u32),
                 ("wolffClusterUpdate", c_i32), ("wolffClusterShiftUpdate", c_i32), ("repeatWolffPerSweep", c_i32),
-                ("fermionMeasurements", c_i32)]
+                ("fermionMeasurements", c_i32), ("denseHopping", c_i32)]
 
 
 class RefHubParams(ctypes.Structure):
@@ -81,7 +81,8 @@ def sdw_params_from(p):
                         p.updateMethod, p.delaySteps, int(p.globalShift), p.globalUpdateInterval,
                         p.repeatUpdateInSlice, p.seed, p.rngIndex,
                         int(getattr(p, "wolffClusterUpdate", False)), int(getattr(p, "wolffClusterShiftUpdate", False)),
-                        int(getattr(p, "repeatWolffPerSweep", 1)), int(getattr(p, "fermionMeasurements", False)))
+                        int(getattr(p, "repeatWolffPerSweep", 1)), int(getattr(p, "fermionMeasurements", False)),
+                        0 if getattr(p, "checkerboard", True) else 1)
 
 
 class RefSdw:
@@ -133,6 +134,12 @@ class RefSdw:
         a = np.array(A, dtype=np.complex128, order="F", copy=True)
         lib().ref_sdw_bmult(self.h, c_i32(op), _p(a), c_u32(k2), c_u32(k1))
         return a
+
+    def dense_bmat(self, k2, k1):
+        """computeBmatSDW(k2, k1) (detsdwopdim.cpp:1307-1497): dense B with the full hopping exponential."""
+        out = np.zeros((self.D, self.D), dtype=np.complex128, order="F")
+        lib().ref_sdw_dense_bmat(self.h, c_u32(k2), c_u32(k1), _p(out))
+        return out
 
     def update_in_slice(self, k, therm=False):
         return lib().ref_sdw_update_in_slice(self.h, c_u32(k), c_i32(int(therm)))

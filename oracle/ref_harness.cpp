@@ -65,6 +65,7 @@ struct ref_sdw_params {
     int32_t wolffClusterShiftUpdate;
     int32_t repeatWolffPerSweep;
     int32_t fermionMeasurements;   // 0: turnoffFermionMeasurements (default), 1: measure
+    int32_t denseHopping;          // 1: checkerboard = false, DetSDW<CB_NONE, OPDIM>
 };
 
 struct ref_hub_params {
@@ -114,11 +115,12 @@ struct SdwBase {
     virtual void sweep_simple(int therm) = 0;
     virtual void measured_sweep_fermionic(double* scalars, double* vectors) = 0;
     virtual void shift_green_symmetric(double* out) = 0;
+    virtual void dense_bmat(uint32_t k2, uint32_t k1, double* out) = 0;
 };
 
-template <int OPDIM>
+template <int OPDIM, CheckerboardMethod CB = CB_ASSAAD_BERG>
 struct SdwImpl : public SdwBase {
-    typedef DetSDW<CB_ASSAAD_BERG, OPDIM> Model;
+    typedef DetSDW<CB, OPDIM> Model;
     RngWrapper rng;
     std::unique_ptr<Model> rep;
 
@@ -142,7 +144,7 @@ struct SdwImpl : public SdwBase {
         SETP(mu, p.mu);
         SETP(accRatio, p.accRatio);
         SETP(weakZflux, p.weakZflux != 0);
-        SETP(checkerboard, true);
+        SETP(checkerboard, CB != CB_NONE);
         SETP(delaySteps, (uint32_t)p.delaySteps);
         SETP(globalShift, p.globalShift != 0);
         SETP(wolffClusterUpdate, p.wolffClusterUpdate != 0);
@@ -260,6 +262,10 @@ struct SdwImpl : public SdwBase {
         typename Model::MatData gs = rep->shiftGreenSymmetric();
         std::memcpy(out, gs.memptr(), sizeof(cpx_t) * gs.n_elem);
     }
+    void dense_bmat(uint32_t k2, uint32_t k1, double* out) {
+        typename Model::MatData B = rep->computeBmatSDW(k2, k1);
+        std::memcpy(out, B.memptr(), sizeof(cpx_t) * B.n_elem);
+    }
     void sweep_simple(int therm) {
         // greenUpdate = simple (detsdwopdim.cpp:4366-4420)
         if (therm) rep->sweepSimpleThermalization();
@@ -341,7 +347,8 @@ void* ref_sdw_create(const ref_sdw_params* p) {
     try {
         switch (p->opdim) {
         case 1: return static_cast<SdwBase*>(new SdwImpl<1>(*p));
-        case 2: return static_cast<SdwBase*>(new SdwImpl<2>(*p));
+        case 2: return p->denseHopping ? static_cast<SdwBase*>(new SdwImpl<2, CB_NONE>(*p))
+                                       : static_cast<SdwBase*>(new SdwImpl<2>(*p));
         case 3: return static_cast<SdwBase*>(new SdwImpl<3>(*p));
         }
     } catch (const std::exception& e) {
@@ -356,6 +363,10 @@ void ref_sdw_set_phi(void* h, const double* in) { CoutSilencer q; static_cast<Sd
 void ref_sdw_get_green(void* h, double* out) { static_cast<SdwBase*>(h)->get_green(out); }
 void ref_sdw_get_sv(void* h, double* out) { static_cast<SdwBase*>(h)->get_sv(out); }
 void ref_sdw_get_tables(void* h, double* c, double* s) { static_cast<SdwBase*>(h)->get_tables(c, s); }
+// computeBmatSDW (detsdwopdim.cpp:1307-1497): the dense B(k2, k1) = prod e^{-dtau V_k} e^{-dtau K}
+void ref_sdw_dense_bmat(void* h, uint32_t k2, uint32_t k1, double* out) {
+    static_cast<SdwBase*>(h)->dense_bmat(k2, k1, out);
+}
 void ref_sdw_bmult(void* h, int op, double* A, uint32_t k2, uint32_t k1) {
     static_cast<SdwBase*>(h)->bmult(op, A, k2, k1);
 }

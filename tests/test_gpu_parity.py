@@ -428,6 +428,55 @@ def test_wolff_cluster_moves_vs_reference_record():
         assert list(b.wolff_statistics(1)) == list(b.wolff_statistics(0))
 
 
+def _dense_params(g, tag, **over):
+    import json
+    from dqmc_oracle import SdwParams
+    d = json.loads(str(g["params_" + tag]))
+    for k in ("N", "beta"):
+        d.pop(k, None)
+    d.update(over)
+    return SdwParams(**d)
+
+
+@pytest.mark.parametrize("tag", ["flux", "noflux_apbcx"])
+def test_dense_hopping_bmat_and_sweep_simple_vs_reference(tag):
+    """SURVEY 8a rows a8 / a26 against the reference itself (tests/golden/sdw_dense_hopping.npz): the dense B matrices of
+    computeBmatSDW (detsdwopdim.cpp:1307-1497) and the reference's sweepSimple, which builds its B matrices with the
+    dense hopping exponential whatever the checkerboard setting (detsdwopdim.cpp:4366-4420)."""
+    g = load_golden("sdw_dense_hopping")
+    p = _dense_params(g, tag)
+    bd = make_batch(_dense_params(g, tag, checkerboard=False))          # same stream -> same random fields
+    D = 2 * p.N
+    eye = np.eye(D, dtype=np.complex128)
+    for k2, k1 in ((7, 3), (20, 19)):
+        want = g["bmat_%s_%d_%d" % (tag, k2, k1)]
+        assert relerr(bd.bmat_mult(0, eye, k2, k1), want) < 1e-12      # B I
+        assert relerr(bd.bmat_mult(1, eye, k2, k1), want) < 1e-12      # I B
+        A = rand_cplx((D, D), 3)
+        assert relerr(bd.bmat_mult(2, bd.bmat_mult(0, A, k2, k1), k2, k1), A) < 1e-11      # B^-1 B A
+        assert relerr(bd.bmat_mult(3, bd.bmat_mult(1, A, k2, k1), k2, k1), A) < 1e-11      # A B B^-1
+    b = make_batch(p)                                                   # checkerboard model, simple sweeps
+    for _ in range(2):
+        b.sweepSimpleThermalization()
+    assert maxabs(b.phi()[1:], g["simple_phi_" + tag]) < 1e-12
+    assert relerr(b.green(), g["simple_green_" + tag]) < 1e-9
+    assert np.array_equal(b.rng_draw(4), g["simple_rng_next_" + tag])
+
+
+def test_dense_hopping_model_vs_reference():
+    """checkerboard = false: the stabilised sweep of DetSDW<CB_NONE, 2> (dense e^{-dtau K} in every B-matrix product)
+    against the reference's own run of that model."""
+    g = load_golden("sdw_dense_hopping")
+    b = make_batch(_dense_params(g, "cbnone"))
+    assert relerr(b.green(), g["cbnone_green0"]) < TOL_G
+    assert abs(b.logdet() - float(g["cbnone_logdet0"])) < 1e-10 * abs(float(g["cbnone_logdet0"]))
+    for _ in range(4):
+        b.sweepThermalization()
+    assert maxabs(b.phi()[1:], g["cbnone_phi"]) < 1e-12
+    assert relerr(b.green(), g["cbnone_green"]) < 1e-9
+    assert np.array_equal(b.rng_draw(4), g["cbnone_rng_next"])
+
+
 def test_sweep_simple_vs_oracle():
     """greenUpdate = simple (dqmc_sweep_simple): G from scratch at every slice, then the slice update -- against the
     oracle restatement (plain inverse of 1 + B(k,0) B(m,k) with the checkerboard B): identical decisions, fields and

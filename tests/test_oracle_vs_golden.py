@@ -5,7 +5,7 @@ import pytest
 
 from dqmc_oracle import (SdwOracle, HubbardOracle, exchange_probability, replica_exchange_walk)
 from dsfmt_oracle import RngOracle
-from helpers import load_golden, sdw_params_of, hubbard_params_of, maxabs
+from helpers import load_golden, sdw_params_of, hubbard_params_of, maxabs, relerr
 
 SDW_CASES = ["sdw_o2_wolff_L4", "sdw_o2_wolffshift_L4", "sdw_o3_woodbury_L4", "sdw_o2_repeat2_L4",
              "sdw_o2_flux_L4", "sdw_o2_noflux_apbcxy_L4", "sdw_o3_L4", "sdw_o1_apbcx_L4",
@@ -251,3 +251,35 @@ def test_oracle_full_size_setup_vs_reference():
     assert abs(np.trace(o.green[0]) - g["green0_trace"]) < 1e-10
     assert abs(np.log(o.green_inv_sv[0]).sum() - float(g["logdet0"])) < 1e-10 * abs(float(g["logdet0"]))
     assert maxabs(o.phi, g["phi0"]) == 0.0
+
+
+def test_oracle_dense_hopping_vs_reference():
+    """The oracle's dense hopping path (setupPropK / computeBmatSDW / sweepSimple / DetSDW<CB_NONE>) against the
+    reference's own dense B matrices, simple sweeps and CB_NONE sweeps (tools/make_golden.py dense)."""
+    import json
+    from dqmc_oracle import SdwOracle, SdwParams
+    g = load_golden("sdw_dense_hopping")
+
+    def params(tag, **over):
+        d = json.loads(str(g["params_" + tag]))
+        for k in ("N", "beta"):
+            d.pop(k, None)
+        d.update(over)
+        return SdwParams(**d)
+
+    for tag in ("flux", "noflux_apbcx"):
+        od = SdwOracle(params(tag, checkerboard=False))
+        eye = np.eye(od.sz, dtype=np.complex128)
+        for k2, k1 in ((7, 3), (20, 19)):
+            assert relerr(od.left_multiply_bmat(0, eye, k2, k1), g["bmat_%s_%d_%d" % (tag, k2, k1)]) < 1e-12
+        o = SdwOracle(params(tag))
+        for _ in range(2):
+            o.sweep_simple_thermalization()
+        assert maxabs(o.phi[1:], g["simple_phi_" + tag]) < 1e-12
+        assert relerr(o.green[0], g["simple_green_" + tag]) < 1e-9
+    o = SdwOracle(params("cbnone"))
+    assert relerr(o.green[0], g["cbnone_green0"]) < 1e-10
+    for _ in range(4):
+        o.sweep_thermalization()
+    assert maxabs(o.phi[1:], g["cbnone_phi"]) < 1e-12
+    assert relerr(o.green[0], g["cbnone_green"]) < 1e-9

@@ -127,6 +127,36 @@ def hubbard_observables_fixture():
     print("hubbard_observables done")
 
 
+def dense_fixture():
+    """Dense hopping path of the reference: computeBmatSDW, sweepSimple (which builds its B
+    matrices with the dense hopping exponential whatever the checkerboard setting, detsdwopdim.cpp:4366-4420), and
+    stabilised sweeps of DetSDW<CB_NONE, 2> (checkerboard = false)."""
+    d = {}
+    for tag, kw in (("flux", dict()), ("noflux_apbcx", dict(weakZflux=False, bc=1, rngIndex=4))):
+        p = SdwParams(**kw)
+        r = rb.RefSdw(p)
+        d["params_" + tag] = pars_json(p)
+        d["bmat_%s_7_3" % tag] = r.dense_bmat(7, 3)
+        d["bmat_%s_20_19" % tag] = r.dense_bmat(20, 19)
+        for sw in range(2):
+            r.sweep_simple(True)
+        d["simple_phi_" + tag] = r.phi()[1:]
+        d["simple_green_" + tag] = r.green()
+        d["simple_rng_next_" + tag] = r.rng_draw(4)
+    p = SdwParams(checkerboard=False, rngIndex=6)
+    r = rb.RefSdw(p)
+    d["params_cbnone"] = pars_json(p)
+    d["cbnone_green0"] = r.green()
+    d["cbnone_logdet0"] = float(np.log(r.sv()).sum())
+    for sw in range(4):
+        r.sweep(True)
+    d["cbnone_phi"] = r.phi()[1:]
+    d["cbnone_green"] = r.green()
+    d["cbnone_rng_next"] = r.rng_draw(4)
+    np.savez_compressed(os.path.join(OUT, "sdw_dense_hopping.npz"), **d)
+    print("sdw_dense_hopping done")
+
+
 def pt_reference_fixture():
     """Replica-exchange trajectory of the reference's own DetQMCPT driver (detqmcpt.h, unmodified) run with one thread
     per ladder process on the thread-backed boost::mpi stand-in (oracle/_ref/ref_pt, oracle/ref_pt_harness.cpp):
@@ -385,6 +415,9 @@ if __name__ == "__main__":
         observables_fixture()
         fermion_fixture()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "dense":
+        dense_fixture()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "pt_reference":
         pt_reference_fixture()
         sys.exit(0)
@@ -412,6 +445,7 @@ if __name__ == "__main__":
     hubbard_fixture("hubbard_L4_U4_b4", 6, dict())                      # BASELINE config C1
     hubbard_fixture("hubbard_L4_cb", 4, dict(checkerboard=True, U=6.0, mu=0.3, m=24, s=5))
     hubbard_observables_fixture()
+    dense_fixture()
     pt_reference_fixture()
     config_stream_fixture()
     observables_fixture()

@@ -55,7 +55,8 @@ class DetQMCPT:
     def __init__(self, model_pars, control_values, thermalization, sweeps, measureInterval=1, exchangeInterval=1,
                  saveConfigurationStreamInterval=0, saveConfigurationStreamBinary=False,
                  saveConfigurationStreamText=False, rngSeed=1020304050, simindex=0, outdir=".",
-                 controlParameterName="r", device=None, make_batch=None, turnoffFermionMeasurements=True):
+                 controlParameterName="r", device=None, make_batch=None, turnoffFermionMeasurements=True,
+                 resume=False):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
@@ -102,6 +103,43 @@ class DetQMCPT:
         # local records: (sweep index, control-parameter index, {observable: value}) and buffered configurations
         self.records = []
         self.configs = []
+        self._rng_indices = idx
+        if resume and os.path.exists(self.state_path()):
+            self.load_state()
+
+    # ------------------------------------------------------------------ saveState / resume, detqmcpt.h:201-253, 447-520
+    def state_path(self):
+        return os.path.join(self.outdir, "simulation.state.rank%d" % self.rank)
+
+    def save_state(self):
+        """Every rank dumps its share of what DetQMCPT::saveContents serialises: the replicas (fields, control data,
+        generator position), the sweep counters, the ladder (current_process_par / current_par_process) with its
+        exchange statistics, and the measurements recorded so far."""
+        import pickle
+        L = self.ladder
+        st = dict(batch=self.batch.save_state(), sweepsDone=self.sweepsDone,
+                  sweepsDoneThermalization=self.sweepsDoneThermalization, swCounter=self.swCounter,
+                  ladder={k: getattr(L, k).copy() for k in ("par_process", "process_par", "proposed", "accepted", "going",
+                                                            "count_up", "count_down")},
+                  records=self.records, configs_written=True, values=self.values.copy())
+        os.makedirs(self.outdir, exist_ok=True)
+        with open(self.state_path(), "wb") as f:
+            pickle.dump(st, f)
+
+    def load_state(self):
+        import pickle
+        with open(self.state_path(), "rb") as f:
+            st = pickle.load(f)
+        if not np.array_equal(st["values"], self.values):
+            raise ValueError("state file belongs to a different ladder")
+        self.batch.load_state(st["batch"], self._rng_indices)
+        self.sweepsDone, self.sweepsDoneThermalization = st["sweepsDone"], st["sweepsDoneThermalization"]
+        self.swCounter = st["swCounter"]
+        for k, v in st["ladder"].items():
+            getattr(self.ladder, k)[...] = v
+        self.records = st["records"]
+        print("State of previous simulation has been loaded.\n  sweepsDoneThermalization: %d\n  sweepsDone: %d"
+              % (self.sweepsDoneThermalization, self.sweepsDone))
 
     # ------------------------------------------------------------------ replicaExchangeStep, detqmcpt.h:962-1118
     def replica_exchange_step(self):
@@ -173,6 +211,7 @@ class DetQMCPT:
             if np.abs(want - have).max() > 1e-10:
                 raise RuntimeError("replica exchange consistency check failed")
         self.save()
+        self.save_state()
 
     # ------------------------------------------------------------------ gather to rank 0 and write
     def _gather(self, obj):
@@ -188,6 +227,7 @@ class DetQMCPT:
     def save(self):
         recs = self._gather(self.records)
         cfgs = self._gather(self.configs)
+        self.configs = []          # configuration streams are appended; the records stay (series are rewritten in full)
         if self.rank != 0:
             return
         scalars = OBSERVABLES + (FERMIONIC_SCALARS if self.fermionic else ())
@@ -245,7 +285,6 @@ class DetQMCPT:
             for c in range(self.P):
                 tot = L.count_up[c] + L.count_down[c]
                 f.write("%d\t%.15g\n" % (c, (L.count_up[c] / tot) if tot else 0.0))
-        self.records, self.configs = [], []
 
 
 def main(argv=None):
@@ -268,7 +307,7 @@ def main(argv=None):
                       ("saveConfigurationStreamInterval", int), ("rngSeed", int), ("simindex", int)):
         if key in args:
             mc[key] = conv(args.pop(key))
-    for key in ("saveConfigurationStreamBinary", "saveConfigurationStreamText", "turnoffFermionMeasurements"):
+    for key in ("saveConfigurationStreamBinary", "saveConfigurationStreamText", "turnoffFermionMeasurements", "resume"):
         if key in args:
             mc[key] = args.pop(key).lower() in ("1", "true", "yes")
     outdir = args.pop("outdir", ".")

@@ -207,6 +207,37 @@ class DetSDWBatch:
     def rng_skip(self, n, rep=0):
         self._ck(self.lib.dqmc_rng_skip(self.h, rep, n))
 
+    def rng_consumed(self, rep=0):
+        return int(self.lib.dqmc_rng_consumed(self.h, rep))
+
+    # ------------------------------------------------------------------ checkpoint (saveContents / loadContents)
+    def save_state(self):
+        """State of every replica as the reference serialises it (detsdwopdim.h:1117-1148 + the generator,
+        detqmcpt.h:248-250): fields, control data, exchange parameter, position in the random-number stream
+        (the generator is re-seeded and advanced on load), sweep counter.  G and the UdV storage are rebuilt."""
+        self.synchronize()
+        reps = []
+        for rep in range(self.R):
+            cd = self.control_data(rep)
+            reps.append(dict(phi=self.phi(rep), ctrl=bytes(cd), r=self.get_exchange_parameter_value(rep),
+                             consumed=self.rng_consumed(rep)))
+        return dict(replicas=reps, performedSweeps=self.sweep_state()["performedSweeps"])
+
+    def load_state(self, state, rng_indices):
+        assert len(state["replicas"]) == self.R
+        for rep, st in enumerate(state["replicas"]):
+            self.set_phi(st["phi"], rep)
+            self.set_control_data(ControlData.from_buffer_copy(st["ctrl"]), rep)
+            self.set_exchange_parameter_value(st["r"], rep)
+            self._ck(self.lib.dqmc_rng_seed(self.h, rep, self.pars["seed"], int(rng_indices[rep])))
+            left = int(st["consumed"])
+            while left > 0:                               # advance the fresh stream to where the saved run stood
+                n = min(left, 1 << 20)
+                self.rng_skip(n, rep)
+                left -= n
+        self.setup_storage()                              # loadContents: setupUdVStorage_and_calculateGreen, lastSweepDir = Up
+        self._ck(self.lib.dqmc_set_performed_sweeps(self.h, int(state["performedSweeps"])))
+
     # ------------------------------------------------------------------ operators
     def bmat_mult(self, op, A, k2, k1, rep=0):
         a = np.array(A, dtype=np.complex128, order="F", copy=True)

@@ -675,6 +675,37 @@ def test_parallel_tempering_vs_reference_driver(tmp_path):
         assert np.allclose([float(r[1]) for r in rows], g[key], rtol=1e-12, atol=1e-15), fname
 
 
+def test_parallel_tempering_resume(tmp_path):
+    """DetQMCPT state save / resume (detqmcpt.h:201-253, 447-520): a ladder run stopped after 4 of 8 measurement
+    sweeps and resumed from the per-rank state files reproduces the uninterrupted run -- per-parameter series,
+    exchange acceptance and diffusion (fields, control data, generator position, ladder assignment and exchange
+    statistics are all part of the state)."""
+    import os
+    from detqmc_b200 import DetQMCPT
+    from detqmc_b200.pt import OBSERVABLES
+    from dqmc_oracle import SdwParams
+    values = np.array([-1.6, -1.2, -0.8, -0.4])
+    # exchanges after sweeps 3, 6, 9 of 12: none is due at the stopping point (sweep 8).  Like the reference, a run
+    # that stops does not exchange after its last sweep (detqmcpt.h:948-953), so a stop AT an exchange point would
+    # differ from the uninterrupted run by that one exchange step -- in the reference as well
+    kw = dict(thermalization=4, exchangeInterval=3)
+    a, b = os.path.join(str(tmp_path), "straight"), os.path.join(str(tmp_path), "resumed")
+    DetQMCPT(SdwParams(L=4, m=20, s=10, globalUpdateInterval=3), values, sweeps=8, outdir=a, **kw).run()
+    DetQMCPT(SdwParams(L=4, m=20, s=10, globalUpdateInterval=3), values, sweeps=4, outdir=b, **kw).run()
+    pt = DetQMCPT(SdwParams(L=4, m=20, s=10, globalUpdateInterval=3), values, sweeps=8, outdir=b, resume=True, **kw)
+    assert pt.sweepsDone == 4 and pt.sweepsDoneThermalization == 4
+    pt.run()
+    for c in range(len(values)):
+        for name in OBSERVABLES:
+            sa = [float(x) for x in open(os.path.join(a, os.path.basename(pt.subdir(c)), name + ".series")) if x[0] != "#"]
+            sb = [float(x) for x in open(os.path.join(pt.subdir(c), name + ".series")) if x[0] != "#"]
+            assert len(sa) == 8 and len(sb) == 8 and np.allclose(sa, sb, rtol=0, atol=1e-9), (c, name)
+    for fname in ("exchange-acceptance.values", "exchange-diffusion.values"):
+        ra = [x.split()[1] for x in open(os.path.join(a, fname)) if x[0] != "#"]
+        rb_ = [x.split()[1] for x in open(os.path.join(b, fname)) if x[0] != "#"]
+        assert ra == rb_, fname
+
+
 def test_parallel_tempering_driver_fermionic_series(tmp_path):
     """DetQMCPT with turnoffFermionMeasurements = False: the measurement sweeps are sweep(true); without exchanges
     (exchangeInterval = 0) every control parameter's greenLocal / occDiffSq series is the oracle's for that replica."""

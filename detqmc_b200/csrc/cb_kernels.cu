@@ -29,6 +29,7 @@
 #include "dqmc_internal.h"
 
 #include <cmath>
+#include <cstdlib>
 #include <complex>
 
 namespace dqmc {
@@ -572,11 +573,219 @@ __global__ void __launch_bounds__(kCbMaxThreads) cb_mult_kernel(CbGeom g, CbLaun
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Column tiles (left multiplies) through the bulk-copy engine.
+//
+// A column of the matrix is D contiguous elements; it is brought in as D / L pieces of one lattice row each
+// (L sites = L * 16 bytes, `cp.async.bulk.shared.global` completing on an mbarrier: no registers, no LSU instructions)
+// and stored the same way (`cp.async.bulk.global.shared`), so the tile keeps the NATURAL site order -- with the lattice
+// rows padded to a stride of `rs` elements, rs == L / 2 (mod 4).  With that stride the four corners of consecutive
+// plaquettes q = py * L/2 + px sit at 16-byte units 2 q + const (mod 8) for both subgroups, the vectors of the tile
+// are 1 (mod 8) units apart, and a quarter warp = 4 consecutive plaquettes x 2 vectors reads eight distinct bank
+// groups (only the x-wrapped corner of the odd subgroup deviates).  A thread keeps its plaquette matrix in registers
+// and walks over every other vector of the tile.
+// ------------------------------------------------------------------------------------------------
+struct CbNat {
+    int rs;        // stride of a lattice row in the tile
+    int blk;       // stride of a band-spin block: L * rs
+    int ldv;       // stride of a vector: 1 (mod 8)
+    int half;      // L / 2
+    int ngrp;      // groups of four plaquettes per band-spin block
+    int Gp;        // vector groups of the potential stage
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+template <int MSF, bool REALM, int NV>
+__device__ __forceinline__ void hopping_pass_nat(cplx* tile, const cplx* __restrict__ tab, const CbGeom& g,
+                                                 const CbNat& nt, int sign_idx, int transposed, int pass) {
+    const int items = MSF * nt.ngrp * 8;
+    for (int item = threadIdx.x; item < items; item += blockDim.x) {
+        const int qlo = item & 3, vpar = (item >> 2) & 1, rest = item >> 3;
+        const int bs = rest / nt.ngrp;
+        const int q = (rest - bs * nt.ngrp) * 4 + qlo;
+        if (q >= g.nplaq) continue;
+        const int band = bs & 1;
+        PlaqMat<REALM> M;
+        M.load(tab + ((size_t(band) * 2 + sign_idx) * 3 + pass) * 8 * g.nplaq + q, g.nplaq, transposed != 0);
+        const int sg = pass >= 1 ? 0 : 1;
+        const int py = q / nt.half, px = q - py * nt.half;
+        const int x0 = 2 * px + sg, y0 = 2 * py + sg;
+        const int x1 = x0 + 1 == g.L ? 0 : x0 + 1, y1 = y0 + 1 == g.L ? 0 : y0 + 1;
+        const int base = bs * nt.blk;
+        const int oi = base + y0 * nt.rs + x0, oj = base + y0 * nt.rs + x1;
+        const int ok = base + y1 * nt.rs + x0, ol = base + y1 * nt.rs + x1;
+#pragma unroll
+        for (int v = 0; v < NV; v += 2) {
+            cplx* t = tile + (v + vpar) * nt.ldv;
+            cplx a = t[oi], b = t[oj], c = t[ok], e = t[ol];
+            M.apply(a, b, c, e);
+            t[oi] = a; t[oj] = b; t[ok] = c; t[ol] = e;
+        }
+    }
+}
+
+template <int MSF, bool REALM, int NV>
+__global__ void __launch_bounds__(kCbMaxThreads) cb_mult_bulk_kernel(CbGeom g, CbLaunch a, CbNat nt) {
+    pdl_enter();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long bar;
+    const int D = g.D, N = g.N, L = g.L;
+    cplx* tile = reinterpret_cast<cplx*>(smem_raw);
+    const int b = blockIdx.y;
+    const int v0 = blockIdx.x * NV;
+    const int rows = D / L;                                 // lattice rows per vector
+    const cplx* A = a.A + size_t(b) * a.strideA;
+    const double* phi = a.phi + size_t(b) * a.stridePhi;
+    const double* coshT = a.coshT + size_t(b) * a.strideTab;
+    const double* sinhT = a.sinhT + size_t(b) * a.strideTab;
+    const unsigned bar_s = smem_u32(&bar);
+    const unsigned rowBytes = unsigned(L) * sizeof(cplx);
+
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(unsigned(NV) * D * 16u)
+                     : "memory");
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < NV * rows; c += blockDim.x) {
+        const int v = c / rows, r = c - v * rows;
+        const int bs = r / L, y = r - bs * L;
+        const unsigned dst = smem_u32(tile + v * nt.ldv + bs * nt.blk + y * nt.rs);
+        const cplx* src = A + size_t(v0 + v) * D + size_t(r) * L;
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dst), "l"(src), "r"(rowBytes), "r"(bar_s) : "memory");
+    }
+    {
+        unsigned done = 0;
+        while (!done) {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+                         "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar_s) : "memory");
+        }
+    }
+
+    if (a.shift) {
+        hopping_pass_nat<MSF, REALM, NV>(tile, a.cbtab, g, nt, a.sign_idx, a.transposed, 0);
+        __syncthreads();
+        hopping_pass_nat<MSF, REALM, NV>(tile, a.cbtab, g, nt, a.sign_idx, a.transposed, 2);
+        __syncthreads();
+    }
+    const int pot_items = N * nt.Gp;
+    for (int step = 0; step < (a.shift ? 0 : a.kcount); ++step) {
+        const int k = a.kfirst + step * a.kstep;
+        const double* phi_k = phi + size_t(k) * g.opdim * N;
+        const double* cosh_k = coshT + size_t(k) * N;
+        const double* sinh_k = sinhT + size_t(k) * N;
+        PotCoef pc0;
+        const int it0 = threadIdx.x;
+        const int s0 = it0 % N, grp0 = it0 / N;
+        if (it0 < pot_items) pc0 = potential_coef<MSF>(phi_k, cosh_k, sinh_k, g, s0, a.sign_idx, a.transposed);
+        if (a.k_then_v && !a.skip_hopping) {
+            hopping_pass_nat<MSF, REALM, NV>(tile, a.cbtab, g, nt, a.sign_idx, a.transposed, 0);
+            __syncthreads();
+            hopping_pass_nat<MSF, REALM, NV>(tile, a.cbtab, g, nt, a.sign_idx, a.transposed, 1);
+            __syncthreads();
+            hopping_pass_nat<MSF, REALM, NV>(tile, a.cbtab, g, nt, a.sign_idx, a.transposed, 0);
+            __syncthreads();
+        }
+        if (it0 < pot_items) {
+            const int pos0 = (s0 / L) * nt.rs + s0 % L;
+            for (int v = grp0; v < NV; v += nt.Gp) potential_apply<MSF>(tile + v * nt.ldv, nt.blk, pos0, pc0);
+        }
+        for (int it = it0 + blockDim.x; it < pot_items; it += blockDim.x) {
+            const int s = it % N, grp = it / N;
+            const PotCoef pc = potential_coef<MSF>(phi_k, cosh_k, sinh_k, g, s, a.sign_idx, a.transposed);
+            const int pos = (s / L) * nt.rs + s % L;
+            for (int v = grp; v < NV; v += nt.Gp) potential_apply<MSF>(tile + v * nt.ldv, nt.blk, pos, pc);
+        }
+        __syncthreads();
+        if (!a.k_then_v && !a.skip_hopping) {
+            hopping_pass_nat<MSF, REALM, NV>(tile, a.cbtab, g, nt, a.sign_idx, a.transposed, 0);
+            __syncthreads();
+            hopping_pass_nat<MSF, REALM, NV>(tile, a.cbtab, g, nt, a.sign_idx, a.transposed, 1);
+            __syncthreads();
+            hopping_pass_nat<MSF, REALM, NV>(tile, a.cbtab, g, nt, a.sign_idx, a.transposed, 0);
+            __syncthreads();
+        }
+    }
+    if (a.colscale) {
+        const double* cs = a.colscale + size_t(b) * a.strideScale;
+        for (int idx = threadIdx.x; idx < NV * D; idx += blockDim.x) {
+            const int v = idx / D, e = idx - v * D;
+            const int r = e / L, x = e - r * L, bs = r / L, y = r - bs * L;
+            cplx* p = tile + v * nt.ldv + bs * nt.blk + y * nt.rs + x;
+            const double sc = cs[v0 + v];
+            *p = make_double2(p->x * sc, p->y * sc);
+        }
+    }
+    // ---- store: the generic-proxy writes of the tile become visible to the bulk-copy engine, then one piece per thread
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    cplx* O = a.out ? a.out + size_t(b) * a.strideOut : a.A + size_t(b) * a.strideA;
+    for (int c = threadIdx.x; c < NV * rows; c += blockDim.x) {
+        const int v = c / rows, r = c - v * rows;
+        const int bs = r / L, y = r - bs * L;
+        const unsigned src = smem_u32(tile + v * nt.ldv + bs * nt.blk + y * nt.rs);
+        cplx* dst = O + size_t(v0 + v) * D + size_t(r) * L;
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(rowBytes)
+                     : "memory");
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
 int pow2_floor(int x) { int p = 1; while (2 * p <= x) p *= 2; return p; }
 
 }  // namespace
 
+// Column tiles through the bulk-copy engine (cb_mult_bulk_kernel); returns cudaErrorNotSupported when the shape does
+// not qualify (the caller then uses the general kernel).
+template <int NV>
+static cudaError_t cb_launch_bulk(const CbGeom& g, const CbLaunch& a, cudaStream_t st) {
+    if (a.rows || (g.L & 1) || g.D % NV != 0 || g.D % g.L != 0) return cudaErrorNotSupported;
+    CbNat nt;
+    nt.half = g.L / 2;
+    nt.rs = g.L;
+    while (nt.rs % 4 != nt.half % 4) ++nt.rs;
+    nt.blk = g.L * nt.rs;
+    nt.ldv = g.msf * nt.blk;
+    while (nt.ldv % 8 != 1) ++nt.ldv;
+    nt.ngrp = (g.nplaq + 3) / 4;
+    const int items = g.msf * nt.ngrp * 8;
+    int nthreads = std::min(kCbMaxThreads, ((items + 31) / 32) * 32);
+    nthreads = std::max(nthreads, 64);
+    nt.Gp = std::max(1, std::min(NV, pow2_floor(std::max(1, nthreads / g.N))));
+    const size_t smem = size_t(NV) * nt.ldv * sizeof(cplx);
+    if (smem > size_t(200) * 1024) return cudaErrorNotSupported;
+    dim3 grid(g.D / NV, a.batch);
+    const bool realm = a.real_tables != 0;
+#define CB_LAUNCHB(MSF, RM)                                                                                   \
+    {                                                                                                         \
+        cudaError_t e = cudaFuncSetAttribute(cb_mult_bulk_kernel<MSF, RM, NV>,                                \
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
+        if (e != cudaSuccess) return e;                                                                       \
+        launch_pdl(cb_mult_bulk_kernel<MSF, RM, NV>, dim3(grid), dim3(nthreads), smem, st, g, a, nt);         \
+    }
+    if (g.msf == 2) {
+        if (realm) CB_LAUNCHB(2, true) else CB_LAUNCHB(2, false)
+    } else {
+        if (realm) CB_LAUNCHB(4, true) else CB_LAUNCHB(4, false)
+    }
+#undef CB_LAUNCHB
+    return cudaGetLastError();
+}
+
 cudaError_t cb_launch(const CbGeom& g, const CbLaunch& a, cudaStream_t st) {
+    {
+        // DQMC_CB_BULK: 0 = general kernel only, 8 / 16 = vectors per bulk tile
+        static const int bulk = std::getenv("DQMC_CB_BULK") ? std::atoi(std::getenv("DQMC_CB_BULK")) : 8;
+        cudaError_t e = cudaErrorNotSupported;
+        if (bulk == 8) e = cb_launch_bulk<8>(g, a, st);
+        else if (bulk == 16) e = cb_launch_bulk<16>(g, a, st);
+        if (e != cudaErrorNotSupported) return e;
+    }
     CbShape sh;
     sh.half = g.L / 2;
     sh.quarter = g.N / 4;

@@ -437,19 +437,19 @@ __device__ __forceinline__ void potential_apply(cplx* t, int N, int pos, const P
     }
 }
 
-template <int MSF, bool REALM>
+template <int MSF, bool REALM, int TV>
 __global__ void __launch_bounds__(kCbMaxThreads) cb_mult_kernel(CbGeom g, CbLaunch a, CbShape sh) {
     pdl_enter();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int D = g.D, N = g.N;
     const int ldt = D + 1;
     cplx* tile = reinterpret_cast<cplx*>(smem_raw);
-    int* sperm = reinterpret_cast<int*>(tile + kCbTileVecs * ldt);      // [D] matrix index -> tile position
+    int* sperm = reinterpret_cast<int*>(tile + TV * ldt);      // [D] matrix index -> tile position
     int* sinv = sperm + D;                                               // [N] tile position -> site
 
     const int b = blockIdx.y;
-    const int v0 = blockIdx.x * kCbTileVecs;
-    const int nv = min(kCbTileVecs, D - v0);
+    const int v0 = blockIdx.x * TV;
+    const int nv = min(TV, D - v0);
     cplx* A = a.A + size_t(b) * a.strideA;
     const double* phi = a.phi + size_t(b) * a.stridePhi;
     const double* coshT = a.coshT + size_t(b) * a.strideTab;
@@ -466,14 +466,14 @@ __global__ void __launch_bounds__(kCbMaxThreads) cb_mult_kernel(CbGeom g, CbLaun
     // ---- load the tile (coalesced along the contiguous direction of the column-major matrix); the
     // global loads of a thread are issued back to back (8 in flight) before the shared-memory stores
     if (!a.rows) {
-        if (nv == kCbTileVecs) {
+        if (nv == TV) {
             for (int e = threadIdx.x; e < D; e += blockDim.x) {
-                cplx buf[kCbTileVecs];
+                cplx buf[TV];
 #pragma unroll
-                for (int v = 0; v < kCbTileVecs; ++v) buf[v] = A[size_t(v0 + v) * D + e];
+                for (int v = 0; v < TV; ++v) buf[v] = A[size_t(v0 + v) * D + e];
                 const int pos = sperm[e];
 #pragma unroll
-                for (int v = 0; v < kCbTileVecs; ++v) tile[v * ldt + pos] = buf[v];
+                for (int v = 0; v < TV; ++v) tile[v * ldt + pos] = buf[v];
             }
         } else {
             for (int v = 0; v < nv; ++v) {
@@ -482,19 +482,19 @@ __global__ void __launch_bounds__(kCbMaxThreads) cb_mult_kernel(CbGeom g, CbLaun
                 for (int e = threadIdx.x; e < D; e += blockDim.x) t[sperm[e]] = src[e];
             }
         }
-    } else if (nv == kCbTileVecs) {
+    } else if (nv == TV) {
         constexpr int U = 8;
-        for (int base = 0; base < kCbTileVecs * D; base += U * blockDim.x) {
+        for (int base = 0; base < TV * D; base += U * blockDim.x) {
             cplx buf[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int idx = base + u * blockDim.x + threadIdx.x;
-                if (idx < kCbTileVecs * D) buf[u] = A[size_t(idx / kCbTileVecs) * D + v0 + idx % kCbTileVecs];
+                if (idx < TV * D) buf[u] = A[size_t(idx / TV) * D + v0 + idx % TV];
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int idx = base + u * blockDim.x + threadIdx.x;
-                if (idx < kCbTileVecs * D) tile[(idx % kCbTileVecs) * ldt + sperm[idx / kCbTileVecs]] = buf[u];
+                if (idx < TV * D) tile[(idx % TV) * ldt + sperm[idx / TV]] = buf[u];
             }
         }
     } else {
@@ -535,17 +535,17 @@ __global__ void __launch_bounds__(kCbMaxThreads) cb_mult_kernel(CbGeom g, CbLaun
     if (a.out) A = a.out + size_t(b) * a.strideOut;
     if (!a.rows) {
         const double* cs = a.colscale ? a.colscale + size_t(b) * a.strideScale : nullptr;
-        if (nv == kCbTileVecs) {
-            double sc[kCbTileVecs];
+        if (nv == TV) {
+            double sc[TV];
 #pragma unroll
-            for (int v = 0; v < kCbTileVecs; ++v) sc[v] = cs ? cs[v0 + v] : 1.0;
+            for (int v = 0; v < TV; ++v) sc[v] = cs ? cs[v0 + v] : 1.0;
             for (int e = threadIdx.x; e < D; e += blockDim.x) {
                 const int pos = sperm[e];
-                cplx buf[kCbTileVecs];
+                cplx buf[TV];
 #pragma unroll
-                for (int v = 0; v < kCbTileVecs; ++v) buf[v] = tile[v * ldt + pos];
+                for (int v = 0; v < TV; ++v) buf[v] = tile[v * ldt + pos];
 #pragma unroll
-                for (int v = 0; v < kCbTileVecs; ++v)
+                for (int v = 0; v < TV; ++v)
                     A[size_t(v0 + v) * D + e] = cs ? make_double2(buf[v].x * sc[v], buf[v].y * sc[v]) : buf[v];
             }
         } else {
@@ -560,9 +560,9 @@ __global__ void __launch_bounds__(kCbMaxThreads) cb_mult_kernel(CbGeom g, CbLaun
                 }
             }
         }
-    } else if (nv == kCbTileVecs) {
-        for (int idx = threadIdx.x; idx < kCbTileVecs * D; idx += blockDim.x) {
-            const int e = idx / kCbTileVecs, v = idx % kCbTileVecs;
+    } else if (nv == TV) {
+        for (int idx = threadIdx.x; idx < TV * D; idx += blockDim.x) {
+            const int e = idx / TV, v = idx % TV;
             A[size_t(e) * D + v0 + v] = tile[v * ldt + sperm[e]];
         }
     } else {
@@ -790,26 +790,31 @@ cudaError_t cb_launch(const CbGeom& g, const CbLaunch& a, cudaStream_t st) {
     sh.half = g.L / 2;
     sh.quarter = g.N / 4;
     sh.pairs = g.msf * g.nplaq;
-    sh.G = std::max(1, std::min(kCbTileVecs, pow2_floor(std::max(1, kCbMaxThreads / sh.pairs))));
+    // 8-vector tiles for small batches (twice the CTAs: the launch is latency bound), 16 otherwise
+    static const int tvEnv = std::getenv("DQMC_CB_TILE") ? std::atoi(std::getenv("DQMC_CB_TILE")) : 0;
+    const int tv = tvEnv ? tvEnv : (((g.D + 15) / 16) * a.batch < 2 * 148 ? 8 : 16);
+    sh.G = std::max(1, std::min(tv, pow2_floor(std::max(1, kCbMaxThreads / sh.pairs))));
     int nthreads = std::min(kCbMaxThreads, ((sh.pairs * sh.G + 31) / 32) * 32);
     nthreads = std::max(nthreads, 64);
-    sh.Gp = std::max(1, std::min(kCbTileVecs, pow2_floor(std::max(1, nthreads / g.N))));
-    const size_t smem = size_t(kCbTileVecs) * (g.D + 1) * sizeof(cplx) + size_t(g.D + g.N) * sizeof(int);
-    dim3 grid((g.D + kCbTileVecs - 1) / kCbTileVecs, a.batch);
+    sh.Gp = std::max(1, std::min(tv, pow2_floor(std::max(1, nthreads / g.N))));
+    const size_t smem = size_t(tv) * (g.D + 1) * sizeof(cplx) + size_t(g.D + g.N) * sizeof(int);
+    dim3 grid((g.D + tv - 1) / tv, a.batch);
     const bool realm = a.real_tables != 0;
-#define CB_LAUNCH(MSF, RM)                                                                                    \
+#define CB_LAUNCH2(MSF, RM, TV)                                                                               \
     {                                                                                                         \
-        cudaError_t e = cudaFuncSetAttribute(cb_mult_kernel<MSF, RM>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                             (int)smem);                                                      \
+        cudaError_t e = cudaFuncSetAttribute(cb_mult_kernel<MSF, RM, TV>,                                     \
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
         if (e != cudaSuccess) return e;                                                                       \
-        launch_pdl(cb_mult_kernel<MSF, RM>, dim3(grid), dim3(nthreads), smem, st, g, a, sh);                                      \
+        launch_pdl(cb_mult_kernel<MSF, RM, TV>, dim3(grid), dim3(nthreads), smem, st, g, a, sh);              \
     }
+#define CB_LAUNCH(MSF, RM) { if (tv == 8) CB_LAUNCH2(MSF, RM, 8) else CB_LAUNCH2(MSF, RM, 16) }
     if (g.msf == 2) {
         if (realm) CB_LAUNCH(2, true) else CB_LAUNCH(2, false)
     } else {
         if (realm) CB_LAUNCH(4, true) else CB_LAUNCH(4, false)
     }
 #undef CB_LAUNCH
+#undef CB_LAUNCH2
     return cudaGetLastError();
 }
 

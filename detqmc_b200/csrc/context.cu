@@ -1107,6 +1107,40 @@ int sweep_up(dqmc_ctx* ctx, int therm) {
     return DQMC_OK;
 }
 
+// L2 residency of the Green's functions: G of all replicas is read and written by every update round (window block,
+// gather, rank-K flush) and every wrap; with DQMC_L2_PERSIST=1 its address range is marked persisting in the launch
+// attributes of the context's streams (stream attributes are recorded into captured kernel nodes), everything else
+// streams through.  hitRatio = share of the range that fits the persisting carve-out.
+int apply_l2_policy(dqmc_ctx* ctx, cudaStream_t st) {
+    static const int on = std::getenv("DQMC_L2_PERSIST") ? std::atoi(std::getenv("DQMC_L2_PERSIST")) : 0;
+    if (!on || !ctx->G) return DQMC_OK;
+    int dev = 0, maxPersist = 0, maxWindow = 0;
+    CK(cudaGetDevice(&dev));
+    CK(cudaDeviceGetAttribute(&maxPersist, cudaDevAttrMaxPersistingL2CacheSize, dev));
+    CK(cudaDeviceGetAttribute(&maxWindow, cudaDevAttrMaxAccessPolicyWindowSize, dev));
+    if (maxPersist <= 0 || maxWindow <= 0) return DQMC_OK;
+    const size_t gbytes = sizeof(cplx) * DD(ctx) * size_t(ctx->R) * ctx->ngc;
+    const size_t window = std::min(gbytes, size_t(maxWindow));
+    static bool limitSet = false;
+    if (!limitSet) {
+        CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min(window, size_t(maxPersist))));
+        limitSet = true;
+        if (std::getenv("DQMC_L2_VERBOSE"))
+            std::fprintf(stderr, "libdqmc_b200: L2 persisting carve-out %d MB max, window %zu MB of %zu MB\n", maxPersist >> 20,
+                         window >> 20, gbytes >> 20);
+    }
+    cudaStreamAttrValue v;
+    std::memset(&v, 0, sizeof v);
+    v.accessPolicyWindow.base_ptr = ctx->G;
+    v.accessPolicyWindow.num_bytes = window;
+    const double ratioEnv = std::getenv("DQMC_L2_RATIO") ? std::atof(std::getenv("DQMC_L2_RATIO")) : 0.0;
+    v.accessPolicyWindow.hitRatio = ratioEnv > 0 ? float(ratioEnv) : float(std::min(1.0, double(maxPersist) / double(window)));
+    v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    CK(cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v));
+    return DQMC_OK;
+}
+
 // One sweep direction as a CUDA graph: the launch sequence of a sweep is static (slice / round / panel loops
 // with fixed trip counts, fixed device addresses), so it is captured once per (direction, thermalisation,
 // random-number window, lanes, stabiliser) and replayed -- ~5000 kernel launches per sweep become one graph
@@ -1310,6 +1344,8 @@ int dqmc_create(const dqmc_params* params, int n_replicas, int device, dqmc_ctx*
         ctx->nlanes = want;
         for (int i = 0; i <= DQMC_MAX_LANES; ++i) ctx->laneStart[i] = i >= want ? ctx->R : (ctx->R * i) / want;
     }
+    RET(apply_l2_policy(ctx, ctx->stream));
+    for (int i = 1; i < DQMC_MAX_LANES; ++i) RET(apply_l2_policy(ctx, ctx->laneStream[i]));
     CK(dmalloc(&ctx->rngbuf, ctx->rngAlloc * R));
     CK(cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
     for (int i = 0; i < 2; ++i) CK(cudaEventCreateWithFlags(&ctx->copyEvent[i], cudaEventDisableTiming));
@@ -1425,6 +1461,7 @@ int dqmc_set_stream(dqmc_ctx* ctx, void* cuda_stream) {
         CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
         ctx->own_stream = true;
     }
+    RET(apply_l2_policy(ctx, ctx->stream));
     return DQMC_OK;
 }
 

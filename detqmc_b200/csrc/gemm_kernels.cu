@@ -656,11 +656,13 @@ cudaError_t gemm_launch(const GemmArgs& g, cudaStream_t st) {
     if (g.batch <= 0 || g.M <= 0 || g.N <= 0) return cudaSuccess;
     if ((g.K <= KT || g.kvec) && !g.transa && !g.transb && g.beta == 1.0 && !g.rowscale && !g.colscale && !g.kscale) {
         static const int cfgEnv = std::getenv("DQMC_RANKUPD_CFG") ? std::atoi(std::getenv("DQMC_RANKUPD_CFG")) : 0;
-        const int cfg = cfgEnv ? cfgEnv : (g_matrices_in_flight <= 16 ? 1 : 2);
+        // 32 x 32 tiles for small batches (81 CTAs per matrix: the launch is latency bound), 96 x 48 otherwise
+        const int cfg = cfgEnv ? cfgEnv : (g_matrices_in_flight <= 16 ? 5 : 2);
         if (g.M % 48 == 0 && g.N % 48 == 0 && cfg == 1) return launch_rank_update<2, 2, 3, 3>(g, st);   // 48 x 48
         if (g.M % 96 == 0 && g.N % 48 == 0 && cfg == 2) return launch_rank_update<4, 2, 3, 3>(g, st);   // 96 x 48
         if (g.M % 48 == 0 && g.N % 96 == 0 && cfg == 3) return launch_rank_update<2, 4, 3, 3>(g, st);   // 48 x 96
         if (g.M % 96 == 0 && g.N % 96 == 0 && cfg == 4) return launch_rank_update<4, 4, 3, 3>(g, st);   // 96 x 96, 16 warps
+        if (g.M % 32 == 0 && g.N % 32 == 0 && cfg == 5) return launch_rank_update<2, 2, 2, 2>(g, st);   // 32 x 32, 4 warps
         if (g.M % 96 == 0 && g.N % 96 == 0) return launch_rank_update<4, 3, 3, 4>(g, st);
         static const int cfg2 = std::getenv("DQMC_RANKUPD_CFG2") ? std::atoi(std::getenv("DQMC_RANKUPD_CFG2")) : 3;
         if (cfg2 == 1 && g.M > 32 && g.N > 32) return launch_rank_update<4, 4, 2, 2>(g, st);            // 64 x 64, 16 warps

@@ -12,6 +12,9 @@
 // whole stabilisation code (GEMM, blocked QR, Green's function) is shared with DetSDW.
 #include "dqmc_internal.h"
 
+#include <algorithm>
+#include <cstdlib>
+
 #include <cmath>
 
 namespace dqmc {
@@ -167,57 +170,118 @@ __global__ void hub_to_complex_kernel(const double* in, cplx* out, size_t n) {
 }
 
 // updateInSlice (dethubbard.cpp:141-171): N attempts at random sites, in the reference's draw order
-// (site = randInt(0, N-1); a further rand01() only if ratio <= 1).  One CTA per replica; the rank-1
-// update of both components (dethubbard.cpp:910-933) is applied immediately by the whole CTA.
-__global__ void __launch_bounds__(1024) hub_update_slice_kernel(cplx* Gall, long long strideG, int N, int32_t* auxAll,
+// (site = randInt(0, N-1); a further rand01() only if ratio <= 1).  One CTA per replica.
+//
+// The rank-1 updates of both components (dethubbard.cpp:910-933) are DELAYED: with the pending updates
+// G_eff = G - sum_l u_l v_l^T held in shared memory (KD columns u_l, rows v_l per component), an attempt needs the
+// diagonal element G_eff[site, site] only (KD products), an acceptance the column and the row of G_eff at the site
+// (2 N KD products instead of N^2), and G itself is touched once per KD acceptances by the rank-KD flush
+// G -= U V^T (4 x 4 register tiles per thread).  The arithmetic is the reference's, re-associated: every accepted
+// flip contributes the same outer product  G_eff[:, site] * f (e_site - G_eff[site, :]).
+__global__ void __launch_bounds__(512) hub_update_slice_kernel(cplx* Gall, long long strideG, int N, int32_t* auxAll,
                                                                 long long strideAux, int k, double alpha,
                                                                 const double* rngAll, long long strideRng, int rngWindow,
                                                                 int* cursorAll, uint32_t* acceptedAll,
-                                                                unsigned long long* acceptedTotal, int* errflag) {
+                                                                unsigned long long* acceptedTotal, int* errflag, int KD) {
     pdl_enter();
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* colU = reinterpret_cast<double*>(smem_raw);     // [N] G_up[:, site]
-    double* rowU = colU + N;                                // [N] factor * (1 - G_up)[site, :]
-    double* colD = rowU + N;
-    double* rowD = colD + N;
+    double* Uu = reinterpret_cast<double*>(smem_raw);       // [KD][N] pending columns, spin up
+    double* Vu = Uu + size_t(KD) * N;                       // [KD][N] pending rows (factor included)
+    double* Ud = Vu + size_t(KD) * N;
+    double* Vd = Ud + size_t(KD) * N;
     __shared__ int sSite, sAcc, sAbort;
     __shared__ double sFacU, sFacD;
-    const int b = blockIdx.x, tid = threadIdx.x;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
     cplx* Gu = Gall + size_t(2 * b) * strideG;
     cplx* Gd = Gall + size_t(2 * b + 1) * strideG;
     int32_t* aux = auxAll + size_t(b) * strideAux + size_t(k) * N;
     const double* rng = rngAll + size_t(b) * strideRng;
     int cursor = cursorAll[b];
     unsigned accepted = 0;
+    int np = 0;                                             // pending updates (uniform across the CTA)
     if (tid == 0) sAbort = 0;
     __syncthreads();
+
+    auto flush = [&]() {
+        // G -= U V^T for both components: thread <-> 4 x 4 tile (rows i0.., columns j0..)
+        const int nti = (N + 3) / 4;
+        for (int tile = tid; tile < nti * nti; tile += blockDim.x) {
+            const int ti = tile % nti, tj = tile / nti;
+            const int i0 = 4 * ti, j0 = 4 * tj;
+            double au[4][4], ad[4][4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+                for (int r = 0; r < 4; ++r) { au[c][r] = 0.0; ad[c][r] = 0.0; }
+            for (int l = 0; l < np; ++l) {
+                double uu[4], vu[4], ud[4], vd[4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const int i = min(i0 + r, N - 1), j = min(j0 + r, N - 1);
+                    uu[r] = Uu[l * N + i]; ud[r] = Ud[l * N + i];
+                    vu[r] = Vu[l * N + j]; vd[r] = Vd[l * N + j];
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        au[c][r] = fma(uu[r], vu[c], au[c][r]);
+                        ad[c][r] = fma(ud[r], vd[c], ad[c][r]);
+                    }
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+                    if (i0 + r < N && j0 + c < N) {
+                        const size_t idx = size_t(j0 + c) * N + i0 + r;
+                        Gu[idx].x -= au[c][r];
+                        Gd[idx].x -= ad[c][r];
+                    }
+        }
+    };
+
     for (int attempt = 0; attempt < N; ++attempt) {
-        if (tid == 0) {
+        if (tid < 32) {
+            bool abort = false, acc = false;
+            int site = 0;
             if (cursor + 2 > rngWindow) {
-                sAbort = 1;
-                sAcc = 0;
+                abort = true;
             } else {
-                const int site = int(double(N) * rng[cursor]);          // randInt(0, N-1), rngwrapper.h:60-68
+                site = int(double(N) * rng[cursor]);                    // randInt(0, N-1), rngwrapper.h:60-68
                 cursor += 1;
+                // diagonal elements of G_eff: the pending terms are summed in a fixed order (lane l, then a tree)
+                double pu = 0.0, pd = 0.0;
+                for (int l = lane; l < np; l += 32) {
+                    pu = fma(Uu[l * N + site], Vu[l * N + site], pu);
+                    pd = fma(Ud[l * N + site], Vd[l * N + site], pd);
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    pu += __shfl_xor_sync(0xffffffffu, pu, o);
+                    pd += __shfl_xor_sync(0xffffffffu, pd, o);
+                }
                 const double a = double(aux[site]);
                 const double dU = exp(-2.0 * alpha * a) - 1.0, dD = exp(+2.0 * alpha * a) - 1.0;
-                const double gu = Gu[size_t(site) * N + site].x, gd = Gd[size_t(site) * N + site].x;
+                const double gu = Gu[size_t(site) * N + site].x - pu, gd = Gd[size_t(site) * N + site].x - pd;
                 const double ratio = (1.0 + dU * (1.0 - gu)) * (1.0 + dD * (1.0 - gd));
-                bool acc;
                 if (ratio > 1.0) {
                     acc = true;
                 } else {
                     acc = rng[cursor] < ratio;
                     cursor += 1;
                 }
-                if (acc) {
-                    accepted += 1;
+                if (acc && lane == 0) {
                     aux[site] = -aux[site];
                     sFacU = dU / (1.0 + dU * (1.0 - gu));
                     sFacD = dD / (1.0 + dD * (1.0 - gd));
                 }
+                if (acc) accepted += 1;
+            }
+            if (lane == 0) {
                 sSite = site;
                 sAcc = acc ? 1 : 0;
+                if (abort) { sAbort = 1; sAcc = 0; }
             }
         }
         __syncthreads();
@@ -225,23 +289,33 @@ __global__ void __launch_bounds__(1024) hub_update_slice_kernel(cplx* Gall, long
         if (sAcc) {
             const int site = sSite;
             const double fU = sFacU, fD = sFacD;
+            // column and row of G_eff at the site become the next pending update
             for (int i = tid; i < N; i += blockDim.x) {
-                colU[i] = Gu[size_t(site) * N + i].x;
-                colD[i] = Gd[size_t(site) * N + i].x;
-                const double du = (i == site ? 1.0 : 0.0) - Gu[size_t(i) * N + site].x;
-                const double dd = (i == site ? 1.0 : 0.0) - Gd[size_t(i) * N + site].x;
-                rowU[i] = fU * du;
-                rowD[i] = fD * dd;
+                double cu = Gu[size_t(site) * N + i].x, cd = Gd[size_t(site) * N + i].x;       // G[i, site]
+                double ru = Gu[size_t(i) * N + site].x, rd = Gd[size_t(i) * N + site].x;       // G[site, i]
+                for (int l = 0; l < np; ++l) {
+                    cu = fma(-Uu[l * N + i], Vu[l * N + site], cu);
+                    cd = fma(-Ud[l * N + i], Vd[l * N + site], cd);
+                    ru = fma(-Uu[l * N + site], Vu[l * N + i], ru);
+                    rd = fma(-Ud[l * N + site], Vd[l * N + i], rd);
+                }
+                const double e = i == site ? 1.0 : 0.0;
+                Uu[np * N + i] = cu;
+                Ud[np * N + i] = cd;
+                Vu[np * N + i] = fU * (e - ru);
+                Vd[np * N + i] = fD * (e - rd);
             }
+            np += 1;
             __syncthreads();
-            for (size_t idx = tid; idx < size_t(N) * N; idx += blockDim.x) {
-                const int i = int(idx % N), j = int(idx / N);
-                Gu[idx].x -= colU[i] * rowU[j];
-                Gd[idx].x -= colD[i] * rowD[j];
+            if (np == KD) {
+                flush();
+                np = 0;
+                __threadfence_block();
             }
         }
         __syncthreads();
     }
+    if (np > 0) flush();
     if (tid == 0) {
         if (sAbort) atomicExch(errflag, 1);
         cursorAll[b] = cursor;
@@ -319,10 +393,17 @@ cudaError_t hub_update_slice_launch(cplx* G, long long strideG, int N, int32_t* 
                                     double alpha, const double* rng, long long strideRng, int rngWindow, int* cursor,
                                     uint32_t* accepted, unsigned long long* acceptedTotal, int* errflag, int batch,
                                     cudaStream_t st) {
-    const size_t smem = size_t(4) * N * sizeof(double);
-    const int threads = N >= 256 ? 1024 : 256;
+    // delay depth: as many pending updates as 200 KB of shared memory hold (two components, columns and rows), at most 32
+    int KD = int((size_t(200) * 1024) / (size_t(4) * N * sizeof(double)));
+    KD = std::max(1, std::min(KD, 32));
+    static const int kdEnv = std::getenv("DQMC_HUB_DELAY") ? std::atoi(std::getenv("DQMC_HUB_DELAY")) : 0;
+    if (kdEnv > 0) KD = std::min(KD, kdEnv);
+    const size_t smem = size_t(4) * KD * N * sizeof(double);
+    const int threads = N >= 256 ? 512 : 256;
+    cudaError_t e = cudaFuncSetAttribute(hub_update_slice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
     launch_pdl(hub_update_slice_kernel, dim3(batch), dim3(threads), smem, st, G, strideG, N, aux, strideAux, k, alpha, rng, strideRng,
-                                                          rngWindow, cursor, accepted, acceptedTotal, errflag);
+                                                          rngWindow, cursor, accepted, acceptedTotal, errflag, KD);
     return cudaGetLastError();
 }
 

@@ -12,6 +12,8 @@
 // whole stabilisation code (GEMM, blocked QR, Green's function) is shared with DetSDW.
 #include "dqmc_internal.h"
 
+#include <cooperative_groups.h>
+
 #include <algorithm>
 #include <cstdlib>
 
@@ -178,20 +180,28 @@ __global__ void hub_to_complex_kernel(const double* in, cplx* out, size_t n) {
 // (2 N KD products instead of N^2), and G itself is touched once per KD acceptances by the rank-KD flush
 // G -= U V^T (4 x 4 register tiles per thread).  The arithmetic is the reference's, re-associated: every accepted
 // flip contributes the same outer product  G_eff[:, site] * f (e_site - G_eff[site, :]).
+//
+// A thread-block cluster of CS CTAs serves one replica: streaming the two N x N matrices through ONE SM was the
+// bottleneck of the flush, so every CTA of the cluster runs the identical decision chain (same random numbers, same
+// arithmetic, private copy of the slice's auxiliary spins: no communication) and flushes its own 1 / CS of the
+// columns of G; a cluster barrier on both sides of a flush orders it against the other CTAs' reads of G.
 __global__ void __launch_bounds__(512) hub_update_slice_kernel(cplx* Gall, long long strideG, int N, int32_t* auxAll,
                                                                 long long strideAux, int k, double alpha,
                                                                 const double* rngAll, long long strideRng, int rngWindow,
                                                                 int* cursorAll, uint32_t* acceptedAll,
-                                                                unsigned long long* acceptedTotal, int* errflag, int KD) {
+                                                                unsigned long long* acceptedTotal, int* errflag, int KD,
+                                                                int CS) {
     pdl_enter();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* Uu = reinterpret_cast<double*>(smem_raw);       // [KD][N] pending columns, spin up
     double* Vu = Uu + size_t(KD) * N;                       // [KD][N] pending rows (factor included)
     double* Ud = Vu + size_t(KD) * N;
     double* Vd = Ud + size_t(KD) * N;
+    int32_t* sAux = reinterpret_cast<int32_t*>(Vd + size_t(KD) * N);   // [N] this slice's auxiliary spins, private copy
     __shared__ int sSite, sAcc, sAbort;
     __shared__ double sFacU, sFacD;
-    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+    const int b = blockIdx.x / CS, crank = blockIdx.x % CS, tid = threadIdx.x, lane = tid & 31;
+    cooperative_groups::cluster_group cluster = cooperative_groups::this_cluster();
     cplx* Gu = Gall + size_t(2 * b) * strideG;
     cplx* Gd = Gall + size_t(2 * b + 1) * strideG;
     int32_t* aux = auxAll + size_t(b) * strideAux + size_t(k) * N;
@@ -200,13 +210,16 @@ __global__ void __launch_bounds__(512) hub_update_slice_kernel(cplx* Gall, long 
     unsigned accepted = 0;
     int np = 0;                                             // pending updates (uniform across the CTA)
     if (tid == 0) sAbort = 0;
+    for (int i = tid; i < N; i += blockDim.x) sAux[i] = aux[i];
     __syncthreads();
 
     auto flush = [&]() {
-        // G -= U V^T for both components: thread <-> 4 x 4 tile (rows i0.., columns j0..)
+        // G -= U V^T for both components: thread <-> 4 x 4 tile (rows i0.., columns j0..); this CTA's share of the columns
         const int nti = (N + 3) / 4;
-        for (int tile = tid; tile < nti * nti; tile += blockDim.x) {
-            const int ti = tile % nti, tj = tile / nti;
+        const int tj0 = (nti * crank) / CS, tj1 = (nti * (crank + 1)) / CS;
+        if (CS > 1) cluster.sync();                          // every CTA has finished reading G for its pending updates
+        for (int tile = tid; tile < nti * (tj1 - tj0); tile += blockDim.x) {
+            const int ti = tile % nti, tj = tj0 + tile / nti;
             const int i0 = 4 * ti, j0 = 4 * tj;
             double au[4][4], ad[4][4];
 #pragma unroll
@@ -239,6 +252,7 @@ __global__ void __launch_bounds__(512) hub_update_slice_kernel(cplx* Gall, long 
                         Gd[idx].x -= ad[c][r];
                     }
         }
+        if (CS > 1) { __threadfence(); cluster.sync(); }     // the other CTAs' shares are visible before G is read again
     };
 
     for (int attempt = 0; attempt < N; ++attempt) {
@@ -261,7 +275,7 @@ __global__ void __launch_bounds__(512) hub_update_slice_kernel(cplx* Gall, long 
                     pu += __shfl_xor_sync(0xffffffffu, pu, o);
                     pd += __shfl_xor_sync(0xffffffffu, pd, o);
                 }
-                const double a = double(aux[site]);
+                const double a = double(sAux[site]);
                 const double dU = exp(-2.0 * alpha * a) - 1.0, dD = exp(+2.0 * alpha * a) - 1.0;
                 const double gu = Gu[size_t(site) * N + site].x - pu, gd = Gd[size_t(site) * N + site].x - pd;
                 const double ratio = (1.0 + dU * (1.0 - gu)) * (1.0 + dD * (1.0 - gd));
@@ -271,8 +285,9 @@ __global__ void __launch_bounds__(512) hub_update_slice_kernel(cplx* Gall, long 
                     acc = rng[cursor] < ratio;
                     cursor += 1;
                 }
+                __syncwarp();
                 if (acc && lane == 0) {
-                    aux[site] = -aux[site];
+                    sAux[site] = -sAux[site];
                     sFacU = dU / (1.0 + dU * (1.0 - gu));
                     sFacD = dD / (1.0 + dD * (1.0 - gd));
                 }
@@ -316,6 +331,9 @@ __global__ void __launch_bounds__(512) hub_update_slice_kernel(cplx* Gall, long 
         __syncthreads();
     }
     if (np > 0) flush();
+    if (crank != 0) return;
+    __syncthreads();
+    for (int i = tid; i < N; i += blockDim.x) aux[i] = sAux[i];
     if (tid == 0) {
         if (sAbort) atomicExch(errflag, 1);
         cursorAll[b] = cursor;
@@ -398,12 +416,17 @@ cudaError_t hub_update_slice_launch(cplx* G, long long strideG, int N, int32_t* 
     KD = std::max(1, std::min(KD, 32));
     static const int kdEnv = std::getenv("DQMC_HUB_DELAY") ? std::atoi(std::getenv("DQMC_HUB_DELAY")) : 0;
     if (kdEnv > 0) KD = std::min(KD, kdEnv);
-    const size_t smem = size_t(4) * KD * N * sizeof(double);
+    const size_t smem = size_t(4) * KD * N * sizeof(double) + size_t(N) * sizeof(int32_t);
     const int threads = N >= 256 ? 512 : 256;
+    // cluster size: 8 CTAs per replica for the large lattices (the flush is bandwidth bound), one for the small ones
+    static const int csEnv = std::getenv("DQMC_HUB_CLUSTER") ? std::atoi(std::getenv("DQMC_HUB_CLUSTER")) : 0;
+    int CS = csEnv > 0 ? csEnv : (N >= 256 ? 8 : 1);
+    CS = std::max(1, std::min(CS, 8));
     cudaError_t e = cudaFuncSetAttribute(hub_update_slice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    launch_pdl(hub_update_slice_kernel, dim3(batch), dim3(threads), smem, st, G, strideG, N, aux, strideAux, k, alpha, rng, strideRng,
-                                                          rngWindow, cursor, accepted, acceptedTotal, errflag, KD);
+    e = launch_pdl_cluster(hub_update_slice_kernel, dim3(batch * CS), dim3(threads), smem, st, (unsigned)CS, G, strideG, N, aux,
+                           strideAux, k, alpha, rng, strideRng, rngWindow, cursor, accepted, acceptedTotal, errflag, KD, CS);
+    if (e != cudaSuccess) return e;
     return cudaGetLastError();
 }
 

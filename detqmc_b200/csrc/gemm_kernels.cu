@@ -28,8 +28,11 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
                  : "d"(a), "d"(b));
 }
 
-template <int WM, int WN, int MB, int NB>
+// BKT = depth of a k-tile: 8 for batches that fill the SMs (other CTAs hide the load latency of the one-tile
+// register prefetch), 32 for small batches, where a CTA is alone on its SM and every k-tile costs a global round trip
+template <int WM, int WN, int MB, int NB, int BKT = 8>
 struct GemmCfg {
+    static constexpr int BK = BKT;
     static constexpr int TM = 8 * MB * WM, TN = 8 * NB * WN;
     // Leading dimensions == 4 or 12 (mod 16): the 16 lanes of a half warp (grp 0..3 x t4 0..3) read the doubles
     // t4 * LD + grp, which then fall into 16 different 8-byte bank pairs (with LD == 8 (mod 16) rows t4 and t4 + 2
@@ -41,10 +44,11 @@ struct GemmCfg {
     static constexpr int SMEM_DOUBLES = 2 * (2 * BK * LDM + 2 * BK * LDN);   // two stages, re+im
 };
 
-template <int WM, int WN, int MB, int NB>
+template <int WM, int WN, int MB, int NB, int BKT>
 __global__ void __launch_bounds__(32 * WM * WN) zgemm_dmma_kernel(GemmArgs g) {
     pdl_enter();
-    typedef GemmCfg<WM, WN, MB, NB> C;
+    typedef GemmCfg<WM, WN, MB, NB, BKT> C;
+    constexpr int BK = BKT;
     extern __shared__ __align__(16) double smem[];
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -610,14 +614,14 @@ cudaError_t launch_rank_update(const GemmArgs& g, cudaStream_t st) {
     return cudaGetLastError();
 }
 
-template <int WM, int WN, int MB, int NB>
+template <int WM, int WN, int MB, int NB, int BKT = 8>
 cudaError_t launch_cfg(const GemmArgs& g, cudaStream_t st) {
-    typedef GemmCfg<WM, WN, MB, NB> C;
+    typedef GemmCfg<WM, WN, MB, NB, BKT> C;
     static const bool legacy = std::getenv("DQMC_GEMM_LEGACY") != nullptr;
     static const bool always = std::getenv("DQMC_GEMM_RING_ALWAYS") != nullptr;
     // the cp.async ring pays for tiles with enough arithmetic per k-step; the skinny panel products of the blocked
     // QR (32-wide tiles) measured slower with it
-    if (!legacy && (always || (C::TM >= 48 && C::TN >= 48))) {
+    if (!legacy && BKT == 8 && (always || (C::TM >= 48 && C::TN >= 48))) {
         const size_t smem2 = size_t(kStages) * BK * (C::TM + 2 + C::TN + 2) * sizeof(cplx);
         cudaError_t e2 = cudaFuncSetAttribute(zgemm_dmma2_kernel<WM, WN, MB, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               (int)smem2);
@@ -627,11 +631,11 @@ cudaError_t launch_cfg(const GemmArgs& g, cudaStream_t st) {
         return cudaGetLastError();
     }
     const size_t smem = C::SMEM_DOUBLES * sizeof(double);
-    cudaError_t e = cudaFuncSetAttribute(zgemm_dmma_kernel<WM, WN, MB, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(zgemm_dmma_kernel<WM, WN, MB, NB, BKT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid((g.M + C::TM - 1) / C::TM, (g.N + C::TN - 1) / C::TN, g.batch);
-    launch_pdl(zgemm_dmma_kernel<WM, WN, MB, NB>, dim3(grid), dim3(C::NT), smem, st, g);
+    launch_pdl(zgemm_dmma_kernel<WM, WN, MB, NB, BKT>, dim3(grid), dim3(C::NT), smem, st, g);
     return cudaGetLastError();
 }
 
@@ -674,7 +678,14 @@ cudaError_t gemm_launch(const GemmArgs& g, cudaStream_t st) {
     // 96 x 96 tiles when they fit the problem exactly (D = 288), otherwise 64 x 64; skinny shapes
     // (the panel products of the blocked QR / triangular solve) get 32 x 64 and 64 x 32 tiles
     static const int smallEnv = std::getenv("DQMC_GEMM_SMALL") ? std::atoi(std::getenv("DQMC_GEMM_SMALL")) : -1;
-    const int small = smallEnv >= 0 ? smallEnv : (g_matrices_in_flight <= 8 ? 2 : 0);
+    const int small = smallEnv >= 0 ? smallEnv : (g_matrices_in_flight <= 8 ? 1 : 0);
+    // small batches: 32-deep k-tiles for the shapes that run as a handful of CTAs (DQMC_GEMM_DEEPK=0 / 1 overrides)
+    static const int deepEnv = std::getenv("DQMC_GEMM_DEEPK") ? std::atoi(std::getenv("DQMC_GEMM_DEEPK")) : -1;
+    const bool deep = deepEnv >= 0 ? deepEnv != 0 : g_matrices_in_flight <= 16;
+    if (small == 3 && g.M % 32 == 0 && g.N % 32 == 0 && g.K >= 64) return launch_cfg<2, 2, 2, 2, 32>(g, st);   // 32 x 32, 4 warps
+    if (deep && g.M <= 32 && g.N <= 32) return launch_cfg<2, 2, 2, 2, 32>(g, st);
+    if (deep && g.M <= 32) return launch_cfg<2, 4, 2, 1, 32>(g, st);
+    if (deep && g.N <= 32) return launch_cfg<4, 1, 2, 4, 32>(g, st);
     if (small == 1 && g.M % 48 == 0 && g.N % 48 == 0 && g.K >= 64) return launch_cfg<2, 2, 3, 3>(g, st);   // 48 x 48, 4 warps
     if (small == 2 && g.M % 96 == 0 && g.N % 48 == 0 && g.K >= 64) return launch_cfg<4, 2, 3, 3>(g, st);   // 96 x 48, 8 warps
     if (g.M % 96 == 0 && g.N % 96 == 0 && g.K >= 64) return launch_cfg<4, 3, 3, 4>(g, st);   // 12 warps, 24 x 32 each

@@ -16,6 +16,8 @@
 // the kernel is deterministic, which the 100-sweep trajectory parity requires.
 #include "dqmc_internal.h"
 
+#include <cstdlib>
+
 namespace dqmc {
 namespace {
 
@@ -1352,6 +1354,82 @@ __global__ void __launch_bounds__(kGthThreads) update_gather_kernel(UpdateModel 
 #endif
 }
 
+
+// The same for small batches: tiles of 8 matrix indices (four times the CTAs of the kernel above: with one replica per
+// launch that one runs as D / 32 CTAs and every phase is a dependent global round trip), one output row of Y per thread.
+constexpr int kGthSmallTile = 8;
+
+template <int MSF>
+__global__ void __launch_bounds__(kGthThreads) update_gather_small_kernel(UpdateModel md, UpdateArgs a) {
+    pdl_enter();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int TILE = kGthSmallTile, NG = kGthThreads / TILE;
+    const int b = blockIdx.y;
+    const int* hdr = a.whdr + size_t(b) * a.strideHdr;
+    const int D = md.D, N = md.N, KM = MSF * md.delaySteps;
+    const int tid = threadIdx.x;
+    const int t0 = blockIdx.x * TILE;
+    cplx* As = reinterpret_cast<cplx*>(smem_raw);          // [KM][KM]
+    cplx* Rs = As + size_t(KM) * KM;                       // [K][TILE + 1]
+    __shared__ int sidx[kWinMaxJ * 4];
+    const cplx* __restrict__ scratch = a.wscratch + size_t(b) * a.strideScratch;
+    const cplx* __restrict__ G = a.G + size_t(b) * a.strideG;
+    cplx* X = a.X + size_t(b) * a.strideXY;
+    cplx* Y = a.Y + size_t(b) * a.strideXY;
+    // the whole coefficient buffer is fetched whatever the number of accepted updates: its loads are in flight during
+    // the header round trip (entries beyond K x K are stale and never used)
+    cplx av[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int e = tid + u * kGthThreads;
+        if (e < KM * KM) av[u] = scratch[e];
+    }
+    const int J = hdr[0];
+    if (J <= 0) return;
+    const int K = MSF * J;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int e = tid + u * kGthThreads;
+        if (e < KM * KM) As[e] = av[u];
+    }
+    for (int e = tid + 4 * kGthThreads; e < KM * KM; e += kGthThreads) As[e] = scratch[e];
+    for (int l = tid; l < K; l += kGthThreads) sidx[l] = hdr[4 + l / MSF] + (l % MSF) * N;
+    __syncthreads();
+    // rows of G0 - 1 at the accepted sites (thread <-> term fastest: the sites of a window are close together)
+    for (int idx = tid; idx < K * TILE; idx += kGthThreads) {
+        const int tt = idx / K, l = idx - tt * K;
+        const int t = t0 + tt;
+        cplx v = make_double2(0, 0);
+        if (t < D) {
+            const int s = sidx[l];
+            v = G[size_t(t) * D + s];
+            if (t == s) v.x -= 1.0;
+        }
+        Rs[l * (TILE + 1) + tt] = v;
+    }
+    // columns of G0 at the accepted sites
+    for (int idx = tid; idx < K * TILE; idx += kGthThreads) {
+        const int l = idx / TILE, tt = idx - l * TILE;
+        const int t = t0 + tt;
+        if (t < D) X[size_t(l) * D + t] = G[size_t(sidx[l]) * D + t];
+    }
+    __syncthreads();
+    {
+        const int tt = tid % TILE, ig = tid / TILE;
+        const int t = t0 + tt;
+        for (int i = ig; i < K; i += NG) {
+            cplx acc0 = make_double2(0, 0), acc1 = make_double2(0, 0);
+            int l = 0;
+            for (; l + 1 < K; l += 2) {
+                acc0 = cfma(As[i * KM + l], Rs[l * (TILE + 1) + tt], acc0);
+                acc1 = cfma(As[i * KM + l + 1], Rs[(l + 1) * (TILE + 1) + tt], acc1);
+            }
+            if (l < K) acc0 = cfma(As[i * KM + l], Rs[l * (TILE + 1) + tt], acc0);
+            if (t < D) Y[size_t(i) * D + t] = make_double2(acc0.x + acc1.x, acc0.y + acc1.y);
+        }
+    }
+}
+
 }  // namespace
 
 int update_rounds_per_slice(const UpdateModel& m, int inline_flush) {
@@ -1440,6 +1518,24 @@ cudaError_t update_build_xy_launch(const UpdateModel& m, const UpdateArgs& a, cu
     const int KM = m.msf * m.delaySteps;
     if (m.delaySteps > kWinMaxJ) return cudaErrorInvalidValue;
     const size_t smem = (size_t(KM) * KM + size_t(KM) * (kGthTile + 1)) * sizeof(cplx);
+    // small batches: 8-wide tiles (DQMC_GATHER_SMALL=0 / 1 overrides)
+    static const int smallEnv = std::getenv("DQMC_GATHER_SMALL") ? std::atoi(std::getenv("DQMC_GATHER_SMALL")) : -1;
+    const bool small = smallEnv >= 0 ? smallEnv != 0 : gemm_matrices_in_flight() <= 16;
+    if (small) {
+        const size_t smem_s = (size_t(KM) * KM + size_t(KM) * (kGthSmallTile + 1)) * sizeof(cplx);
+        dim3 grid_s((m.D + kGthSmallTile - 1) / kGthSmallTile, a.batch);
+#define LAUNCHS(MSF)                                                                                        \
+    {                                                                                                       \
+        cudaError_t e = cudaFuncSetAttribute(update_gather_small_kernel<MSF>,                               \
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s);    \
+        if (e != cudaSuccess) return e;                                                                     \
+        launch_pdl(update_gather_small_kernel<MSF>, dim3(grid_s), dim3(kGthThreads), smem_s, st, m, a);     \
+    }
+        if (m.msf == 2) LAUNCHS(2)
+        else LAUNCHS(4)
+#undef LAUNCHS
+        return cudaGetLastError();
+    }
     dim3 grid((m.D + kGthTile - 1) / kGthTile, a.batch);
 #define LAUNCHB(MSF)                                                                                        \
     {                                                                                                       \

@@ -329,6 +329,34 @@ def test_lanes_do_not_change_results():
             assert b1.control_data(rep).lastAccRatioLocal_phi == b.control_data(rep).lastAccRatioLocal_phi
 
 
+def test_large_batch_kernel_variants_match_single_replica_runs():
+    """The library picks its kernel shapes by the number of matrices in flight: more than 16 replicas (the headline
+    batch of 64) run the 96 x 48 rank-K flush, the 32-wide gather tiles, 16-vector checkerboard row tiles, the wide GEMM
+    tiles and no programmatic dependent launch; small batches the 32 x 32 flush, 8-wide gather tiles, 8-vector tiles,
+    deep k-tiles.  At the headline matrix size (L = 12, D = 288, flux, delaySteps = 16, short imaginary time) replicas of
+    an 18-replica batch must follow exactly the trajectories of the same replicas run one at a time."""
+    from dqmc_oracle import SdwParams
+    base = dict(L=12, m=20, s=10, opdim=2, weakZflux=True, delaySteps=16, updateMethod=2, globalShift=True,
+                globalUpdateInterval=2)
+    R = 18
+    idx = list(range(1, R + 1))
+    rs = np.linspace(-1.9, 0.4, R)
+    big = make_batch(SdwParams(**base), n_replicas=R, rng_indices=idx, r_values=rs)
+    for _ in range(3):
+        big.sweepThermalization()
+    pick = (0, 7, 17)
+    ref = [(big.phi(i).copy(), big.green(i).copy(), big.control_data(i).lastAccRatioLocal_phi) for i in pick]
+    big.close()
+    for (phi, g, acc), i in zip(ref, pick):
+        one = make_batch(SdwParams(**base), n_replicas=1, rng_indices=[idx[i]], r_values=[rs[i]])
+        for _ in range(3):
+            one.sweepThermalization()
+        assert maxabs(one.phi(0)[1:], phi[1:]) == 0.0, i
+        assert relerr(one.green(0), g) < TOL_G, i
+        assert one.control_data(0).lastAccRatioLocal_phi == acc, i
+        one.close()
+
+
 def test_resident_random_numbers_equal_streamed():
     """dqmc_rng_preload (the random-number stream of several sweeps resident in HBM, what bench.py times as `value`)
     gives the same trajectory as the default streamed mode, across global moves (sweeps 0 and 10, where the host

@@ -678,7 +678,9 @@ cudaError_t gemm_launch(const GemmArgs& g, cudaStream_t st) {
     // 96 x 96 tiles when they fit the problem exactly (D = 288), otherwise 64 x 64; skinny shapes
     // (the panel products of the blocked QR / triangular solve) get 32 x 64 and 64 x 32 tiles
     static const int smallEnv = std::getenv("DQMC_GEMM_SMALL") ? std::atoi(std::getenv("DQMC_GEMM_SMALL")) : -1;
-    const int small = smallEnv >= 0 ? smallEnv : (g_matrices_in_flight <= 8 ? 1 : 0);
+    // tile shape of the D x D products by the matrices of THIS launch (with one lane per replica a launch carries one
+    // matrix whatever the batch: 96 x 96 tiles would be 9 CTAs of 12 warps, 48 x 48 tiles are 36 CTAs of 4)
+    const int small = smallEnv >= 0 ? smallEnv : (g.batch <= 8 ? 1 : 0);
     // small batches: 32-deep k-tiles for the shapes that run as a handful of CTAs (DQMC_GEMM_DEEPK=0 / 1 overrides)
     static const int deepEnv = std::getenv("DQMC_GEMM_DEEPK") ? std::atoi(std::getenv("DQMC_GEMM_DEEPK")) : -1;
     const bool deep = deepEnv >= 0 ? deepEnv != 0 : g_matrices_in_flight <= 16;

@@ -334,7 +334,7 @@ def run_b200(args):
     d2h = n_local * (4 + 840) + 4 + world * lad.payload_len * 8
 
     # ---------------------------------------------------------------- per-kernel-family device time
-    lanes_default = int(os.environ.get("DQMC_LANES", str(min(n_local, 64))))
+    lanes_default = int(os.environ.get("DQMC_LANES", str(min(n_local, 32))))   # the library's default
     batch.set_lanes(1)                                      # per-kernel times are only meaningful without overlap
     batch.profile_enable(True)
     acc0 = batch.accepted_total().astype(np.float64).sum()

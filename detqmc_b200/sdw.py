@@ -123,7 +123,7 @@ class DetSDWBatch:
         self._ck(self.lib.dqmc_set_option(self.h, 0, 1 if full_pivot else 0))
 
     def set_lanes(self, n):
-        """1..64 independent lanes (CUDA streams) per context, default one per replica; results do not depend on it."""
+        """1..64 independent lanes (CUDA streams) per context, default one per replica up to 32; results do not depend on it."""
         self._ck(self.lib.dqmc_set_option(self.h, 1, int(n)))
 
     def synchronize(self):

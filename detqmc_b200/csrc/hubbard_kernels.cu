@@ -424,6 +424,27 @@ cudaError_t hub_update_slice_launch(cplx* G, long long strideG, int N, int32_t* 
     CS = std::max(1, std::min(CS, 8));
     cudaError_t e = cudaFuncSetAttribute(hub_update_slice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+    // halve the cluster until one of them fits the device (co-scheduling CS CTAs of this size on one GPC); the answer
+    // for a (size, cluster) pair is remembered
+    static size_t cachedSmem = 0;
+    static int cachedWant = 0, cachedCS = 0;
+    if (cachedSmem == smem && cachedWant == CS) CS = cachedCS;
+    const int want = CS;
+    while (CS > 1 && !(cachedSmem == smem && cachedWant == want)) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(CS);
+        cfg.blockDim = dim3(threads);
+        cfg.dynamicSmemBytes = smem;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int nclusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&nclusters, hub_update_slice_kernel, &cfg) == cudaSuccess && nclusters >= 1) break;
+        (void)cudaGetLastError();
+        CS /= 2;
+    }
+    cachedSmem = smem; cachedWant = want; cachedCS = CS;
     e = launch_pdl_cluster(hub_update_slice_kernel, dim3(batch * CS), dim3(threads), smem, st, (unsigned)CS, G, strideG, N, aux,
                            strideAux, k, alpha, rng, strideRng, rngWindow, cursor, accepted, acceptedTotal, errflag, KD, CS);
     if (e != cudaSuccess) return e;

@@ -660,9 +660,9 @@ cudaError_t gemm_launch(const GemmArgs& g, cudaStream_t st) {
     if (g.batch <= 0 || g.M <= 0 || g.N <= 0) return cudaSuccess;
     if ((g.K <= KT || g.kvec) && !g.transa && !g.transb && g.beta == 1.0 && !g.rowscale && !g.colscale && !g.kscale) {
         static const int cfgEnv = std::getenv("DQMC_RANKUPD_CFG") ? std::atoi(std::getenv("DQMC_RANKUPD_CFG")) : 0;
-        // 32 x 32 tiles for small batches (81 CTAs per matrix: the launch is latency bound); otherwise 64 x 48 tiles at
+        // 32 x 32 tiles for up to 32 matrices in flight (81 CTAs per matrix: the launch is latency bound); otherwise 64 x 48 tiles at
         // 80 registers (three CTAs per SM hide the C-tile round trip better than two 96 x 48 ones: 120.6 -> 119.4 ms per step)
-        const int cfg = cfgEnv ? cfgEnv : (g_matrices_in_flight <= 16 ? 5 : 7);
+        const int cfg = cfgEnv ? cfgEnv : (g_matrices_in_flight <= 32 ? 5 : 7);   // measured: 32 replicas 78.1 -> 75.4 ms with the small tiles, 64: 121.8 -> 130.5
         if (g.M % 48 == 0 && g.N % 48 == 0 && cfg == 1) return launch_rank_update<2, 2, 3, 3>(g, st);   // 48 x 48
         if (g.M % 96 == 0 && g.N % 48 == 0 && cfg == 2) return launch_rank_update<4, 2, 3, 3>(g, st);   // 96 x 48
         if (g.M % 48 == 0 && g.N % 96 == 0 && cfg == 3) return launch_rank_update<2, 4, 3, 3>(g, st);   // 48 x 96
@@ -686,7 +686,7 @@ cudaError_t gemm_launch(const GemmArgs& g, cudaStream_t st) {
     const int small = smallEnv >= 0 ? smallEnv : (g.batch <= 8 ? 1 : 0);
     // small batches: 32-deep k-tiles for the shapes that run as a handful of CTAs (DQMC_GEMM_DEEPK=0 / 1 overrides)
     static const int deepEnv = std::getenv("DQMC_GEMM_DEEPK") ? std::atoi(std::getenv("DQMC_GEMM_DEEPK")) : -1;
-    const bool deep = deepEnv >= 0 ? deepEnv != 0 : g_matrices_in_flight <= 16;
+    const bool deep = deepEnv >= 0 ? deepEnv != 0 : g_matrices_in_flight <= 32;
     if (small == 3 && g.M % 32 == 0 && g.N % 32 == 0 && g.K >= 64) return launch_cfg<2, 2, 2, 2, 32>(g, st);   // 32 x 32, 4 warps
     if (deep && g.M <= 32 && g.N <= 32) return launch_cfg<2, 2, 2, 2, 32>(g, st);
     // DQMC_SKINNY_CFG: shape of the M <= 32 panel products -- 0: 32 x 32 tiles (8 warps), 1: 32 x 16 (8 warps), 2: 32 x 8 (4 warps)

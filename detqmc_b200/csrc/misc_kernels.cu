@@ -2,6 +2,10 @@
 // global field shift, bosonic action and exchange action reductions.
 #include "dqmc_internal.h"
 
+#include <cooperative_groups.h>
+#include <algorithm>
+#include <cstdlib>
+
 namespace dqmc {
 namespace {
 
@@ -312,21 +316,30 @@ __device__ __forceinline__ double fm_block_sum(double v, double* red) {
     return t;
 }
 
+// A thread-block cluster of CS CTAs serves one replica (one SM streams the D x D matrix at ~50 GB/s only): every CTA takes
+// a 1 / CS share of the matrix elements into its own shared-memory bins, CTA 0 then adds the bins and the partial sums
+// of its peers through distributed shared memory in rank order.
 template <int MSF>
 __global__ void __launch_bounds__(256) fermion_measure_kernel(const cplx* __restrict__ gsAll, long long strideG, int N,
-                                                              int L, double* __restrict__ accAll, long long strideAcc) {
+                                                              int L, double* __restrict__ accAll, long long strideAcc,
+                                                              int CS) {
     pdl_enter();
     extern __shared__ double fm_smem[];
     __shared__ double red[8];
+    __shared__ double part[3];
+    cooperative_groups::cluster_group cluster = cooperative_groups::this_cluster();
+    const int rep = blockIdx.x / CS, crank = blockIdx.x % CS;
     const int D = MSF * N, nb = (2 * L - 1) * (2 * L - 1);
-    const cplx* gs = gsAll + size_t(blockIdx.x) * strideG;
-    double* acc = accAll + size_t(blockIdx.x) * strideAcc;
+    const cplx* gs = gsAll + size_t(rep) * strideG;
+    double* acc = accAll + size_t(rep) * strideAcc;
     double* bins = fm_smem;                                  // [2][nb] complex
     const int tid = threadIdx.x;
+    const int gtid = crank * blockDim.x + tid, gstep = CS * blockDim.x;
     for (int i = tid; i < 4 * nb; i += blockDim.x) bins[i] = 0.0;
+    __syncthreads();
     // scalar functions of the Green's function (:569-593)
     double sre = 0, tr = 0;
-    for (size_t e = tid; e < size_t(D) * D; e += blockDim.x) {
+    for (size_t e = gtid; e < size_t(D) * D; e += gstep) {
         const cplx v = gs[e];
         sre += v.x;
         if (int(e / D) == int(e % D)) tr += v.x;
@@ -334,7 +347,7 @@ __global__ void __launch_bounds__(256) fermion_measure_kernel(const cplx* __rest
     const double f = MSF == 4 ? 1.0 : 2.0;
     const double ssum = fm_block_sum(sre, red), strace = fm_block_sum(tr, red);
     // displacement bins of the band-diagonal, spin-summed Green's function
-    for (int e = tid; e < N * N; e += blockDim.x) {
+    for (int e = gtid; e < N * N; e += gstep) {
         const int i = e % N, j = e / N;
         const int dx = i % L - j % L + L - 1, dy = i / L - j / L + L - 1;
         const cplx gx = fm_add(fm_gl1<MSF>(gs, D, N, i, 0, j, 0), fm_gl1<MSF>(gs, D, N, i, 2, j, 2));
@@ -345,12 +358,10 @@ __global__ void __launch_bounds__(256) fermion_measure_kernel(const cplx* __rest
         atomicAdd(&bins[2 * nb + 2 * bi], gy.x);
         atomicAdd(&bins[2 * nb + 2 * bi + 1], gy.y);
     }
-    __syncthreads();
-    for (int i = tid; i < 4 * nb; i += blockDim.x) acc[3 + i] += bins[i];
     // equal-time pairing correlations (:673-718): band b, spin sp -> block (b == 0 ? (sp == 0 ? 0 : 2) : (sp == 0 ? 3 : 1))
     double* pairPlus = acc + 3 + 4 * nb;
     double* pairMinus = pairPlus + N;
-    for (int i = tid; i < N; i += blockDim.x) {
+    for (int i = gtid; i < N; i += gstep) {
         cplx pp = make_double2(0, 0), pm = make_double2(0, 0);
 #pragma unroll
         for (int pr = 0; pr < 2; ++pr) {
@@ -372,7 +383,7 @@ __global__ void __launch_bounds__(256) fermion_measure_kernel(const cplx* __rest
     }
     // occDiffSq (:744-776)
     double occ = 0;
-    for (int i = tid; i < N; i += blockDim.x) {
+    for (int i = gtid; i < N; i += gstep) {
         // g(b1, s1, b2, s2) at site i; blocks: XU = 0, YD = 1, XD = 2, YU = 3
         auto g = [&](int bs1, int bs2) { return fm_gl1<MSF>(gs, D, N, i, bs1, i, bs2); };
         const int XU = 0, YD = 1, XD = 2, YU = 3;
@@ -396,18 +407,39 @@ __global__ void __launch_bounds__(256) fermion_measure_kernel(const cplx* __rest
         occ += t.x;
     }
     const double socc = fm_block_sum(occ, red);
-    if (tid == 0) {
-        acc[0] += f * ssum;
-        acc[1] += f * strace / (4.0 * N);
-        acc[2] += socc / N;
+    if (tid == 0) { part[0] = ssum; part[1] = strace; part[2] = socc; }
+    __syncthreads();
+    if (CS > 1) cluster.sync();                              // every CTA's bins and partial sums are complete
+    if (crank == 0) {
+        for (int i = tid; i < 4 * nb; i += blockDim.x) {
+            double t = bins[i];
+            for (int r = 1; r < CS; ++r) t += cluster.map_shared_rank(bins, r)[i];
+            acc[3 + i] += t;
+        }
+        if (tid == 0) {
+            double t0 = part[0], t1 = part[1], t2 = part[2];
+            for (int r = 1; r < CS; ++r) {
+                const double* pr = cluster.map_shared_rank(part, r);
+                t0 += pr[0]; t1 += pr[1]; t2 += pr[2];
+            }
+            acc[0] += f * t0;
+            acc[1] += f * t1 / (4.0 * N);
+            acc[2] += t2 / N;
+        }
     }
+    if (CS > 1) cluster.sync();                              // peers stay resident until CTA 0 has read their shared memory
 }
 
 cudaError_t launch_fermion_measure(const cplx* gs, long long strideG, int N, int L, int msf, double* acc, long long strideAcc,
                                    int batch, cudaStream_t st) {
     const size_t smem = size_t(4) * (2 * L - 1) * (2 * L - 1) * sizeof(double);
-    if (msf == 4) launch_pdl(fermion_measure_kernel<4>, dim3(batch), dim3(256), smem, st, gs, strideG, N, L, acc, strideAcc);
-    else launch_pdl(fermion_measure_kernel<2>, dim3(batch), dim3(256), smem, st, gs, strideG, N, L, acc, strideAcc);
+    static const int csEnv = std::getenv("DQMC_MEASURE_CLUSTER") ? std::atoi(std::getenv("DQMC_MEASURE_CLUSTER")) : 0;
+    int CS = csEnv > 0 ? csEnv : (msf * N >= 128 ? 8 : 1);
+    CS = std::max(1, std::min(CS, 8));
+    cudaError_t e;
+    if (msf == 4) e = launch_pdl_cluster(fermion_measure_kernel<4>, dim3(batch * CS), dim3(256), smem, st, (unsigned)CS, gs, strideG, N, L, acc, strideAcc, CS);
+    else e = launch_pdl_cluster(fermion_measure_kernel<2>, dim3(batch * CS), dim3(256), smem, st, (unsigned)CS, gs, strideG, N, L, acc, strideAcc, CS);
+    if (e != cudaSuccess) return e;
     return cudaGetLastError();
 }
 

@@ -86,18 +86,31 @@ __global__ void scaled_conj_transpose_kernel(const cplx* A, long long strideA, c
     }
 }
 
-__global__ void max_abs_diff_kernel(const cplx* A, const cplx* B, int D, long long stride, double* out) {
+// max |A - B| per matrix; a cluster of CS CTAs per matrix, CTA 0 takes the maximum over its peers' partial results
+// (distributed shared memory)
+__global__ void max_abs_diff_kernel(const cplx* A, const cplx* B, int D, long long stride, double* out, int CS) {
     pdl_enter();
     __shared__ double red[32];
-    const cplx* a = A + size_t(blockIdx.x) * stride;
-    const cplx* b = B + size_t(blockIdx.x) * stride;
+    __shared__ double part;
+    cooperative_groups::cluster_group cluster = cooperative_groups::this_cluster();
+    const int m = blockIdx.x / CS, crank = blockIdx.x % CS;
+    const cplx* a = A + size_t(m) * stride;
+    const cplx* b = B + size_t(m) * stride;
     double mx = 0;
-    for (size_t idx = threadIdx.x; idx < size_t(D) * D; idx += blockDim.x) {
+    for (size_t idx = size_t(crank) * blockDim.x + threadIdx.x; idx < size_t(D) * D; idx += size_t(CS) * blockDim.x) {
         const double dx = a[idx].x - b[idx].x, dy = a[idx].y - b[idx].y;
         mx = fmax(mx, sqrt(dx * dx + dy * dy));
     }
     mx = block_reduce<true>(mx, red);
-    if (threadIdx.x == 0) out[blockIdx.x] = mx;
+    if (threadIdx.x == 0) part = mx;
+    __syncthreads();
+    if (CS > 1) cluster.sync();
+    if (crank == 0 && threadIdx.x == 0) {
+        double t = part;
+        for (int r = 1; r < CS; ++r) t = fmax(t, *cluster.map_shared_rank(&part, r));
+        out[m] = t;
+    }
+    if (CS > 1) cluster.sync();
 }
 
 // coshTermPhi / sinhTermPhi for every (slice >= 1, site)   (detsdwopdim.cpp:1131-1136, 1174-1181)
@@ -248,7 +261,9 @@ cudaError_t launch_conj_transpose(const cplx* A, cplx* B, int D, long long strid
 }
 cudaError_t launch_max_abs_diff(const cplx* A, const cplx* B, int D, long long stride, int batch, double* out,
                                 cudaStream_t st) {
-    launch_pdl(max_abs_diff_kernel, dim3(batch), dim3(512), 0, st, A, B, D, stride, out);
+    const int CS = D >= 128 ? 8 : 1;
+    cudaError_t e = launch_pdl_cluster(max_abs_diff_kernel, dim3(batch * CS), dim3(512), 0, st, (unsigned)CS, A, B, D, stride, out, CS);
+    if (e != cudaSuccess) return e;
     return cudaGetLastError();
 }
 cudaError_t launch_update_tables(const double* phi, double* coshT, double* sinhT, int N, int opdim, int m,

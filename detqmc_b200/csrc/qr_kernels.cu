@@ -12,6 +12,8 @@
 // norm exactly (no down-dating, so no cancellation).  Matrices are L2 resident (D x D x 16 B).
 #include "dqmc_internal.h"
 
+#include <cooperative_groups.h>
+
 #include <algorithm>
 #include <cstdlib>
 
@@ -368,16 +370,19 @@ __device__ __forceinline__ cplx cfmac_(cplx a, cplx b, cplx c) {     // conj(a)*
     return make_double2(fma(a.x, b.x, fma(a.y, b.y, c.x)), fma(a.x, b.y, fma(-a.y, b.x, c.y)));
 }
 
-// squared column norms, then rank by counting: perm[rank] = column (descending, ties by index)
+// squared column norms, then rank by counting: perm[rank] = column (descending, ties by index).  A cluster of CS CTAs
+// per matrix (one SM streams the matrix at ~50 GB/s only): every CTA takes the norms of its share of the columns (same
+// summation order per column whichever CTA computes it), CTA 0 collects them through distributed shared memory and ranks.
 __global__ void __launch_bounds__(1024) colnorm_rank_kernel(const cplx* Aall, int D, long long strideA, int* permAll,
-                                                            double* normAll) {
+                                                            double* normAll, int CS) {
     pdl_enter();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* nrm = reinterpret_cast<double*>(smem_raw);            // [D]
-    const int b = blockIdx.x;
+    cooperative_groups::cluster_group cluster = cooperative_groups::this_cluster();
+    const int b = blockIdx.x / CS, crank = blockIdx.x % CS;
     const cplx* A = Aall + size_t(b) * strideA;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    for (int c = warp; c < D; c += nwarps) {
+    for (int c = crank * nwarps + warp; c < D; c += CS * nwarps) {
         const cplx* col = A + size_t(c) * D;
         double s = 0;
         for (int i = lane; i < D; i += 32) { const cplx v = col[i]; s = fma(v.x, v.x, fma(v.y, v.y, s)); }
@@ -385,6 +390,18 @@ __global__ void __launch_bounds__(1024) colnorm_rank_kernel(const cplx* Aall, in
         if (lane == 0) nrm[c] = s;
     }
     __syncthreads();
+    if (CS > 1) {
+        cluster.sync();
+        if (crank == 0) {
+            for (int c = tid; c < D; c += blockDim.x) {
+                const int owner = (c / nwarps) % CS;
+                if (owner != 0) nrm[c] = cluster.map_shared_rank(nrm, owner)[c];
+            }
+        }
+        __syncthreads();
+        cluster.sync();                                           // peers stay resident until their norms have been read
+        if (crank != 0) return;
+    }
     for (int j = tid; j < D; j += blockDim.x) {
         const double nj = nrm[j];
         int rank = 0;
@@ -1232,7 +1249,9 @@ void qr_workspace_destroy(QrWorkspace* ws) {
 
 cudaError_t qr_prepivot_launch(const cplx* A, long long strideA, cplx* Aout, long long strideOut, int* perm,
                                double* norms, int D, int batch, cudaStream_t st) {
-    launch_pdl(colnorm_rank_kernel, dim3(batch), dim3(1024), size_t(D) * sizeof(double), st, A, D, strideA, perm, norms);
+    const int CS = D >= 128 ? 8 : 1;
+    QR_TRY(launch_pdl_cluster(colnorm_rank_kernel, dim3(batch * CS), dim3(1024), size_t(D) * sizeof(double), st, (unsigned)CS, A, D,
+                              strideA, perm, norms, CS));
     QR_TRY(cudaGetLastError());
     dim3 grid(D, batch);
     launch_pdl(permute_columns_kernel, dim3(grid), dim3(128), 0, st, A, Aout, perm, D, strideA, strideOut);

@@ -9,13 +9,16 @@
 //
 // B_k = e^{-dtau V_k} * blockdiag_bandspin( e^{dtau mu_b} E1(1/2) E0(1) E1(1/2) ),  E_g = product of
 // the 4-site plaquette exponentials of subgroup g.  A left multiply acts on every COLUMN of A
-// independently, a right multiply on every ROW, so a CTA stages a tile of kCbTileVecs vectors (each
+// independently, a right multiply on every ROW, so a CTA stages a tile of 8 or 16 vectors (each
 // of length D = msf*N) in shared memory, applies all slices of the chain there, and writes the tile
 // back: HBM traffic is one read + one write of the matrix per chain, whatever its length.  The
 // reference recomputes every checkerboard block 2x (O(2)) / 3x (O(3)) and copies the matrix per
 // pass; here all band blocks of a vector are transformed once.
 //
-// Shared-memory layout: inside every band-spin block the N sites are stored in 4-sublattice order
+// Two kernels: `cb_mult_bulk_kernel` for column tiles (bulk-copy engine in and out, natural site order with padded
+// lattice rows; see its own comment) and the general `cb_mult_kernel` for row tiles and for shapes the bulk path does
+// not take.  The general kernel's
+// shared-memory layout: inside every band-spin block the N sites are stored in 4-sublattice order
 // (x parity, y parity, then plaquette index), so the four corners of consecutive plaquettes are four
 // unit-stride streams -- conflict-free 16-byte accesses for both plaquette subgroups -- and the
 // per-site potential stage is unit stride as well.  A thread owns one (plaquette, band-spin) pair
@@ -287,7 +290,6 @@ void cb_build_tables(const dqmc_params& p, std::vector<cplx>& out) {
 // ------------------------------------------------------------------------------------------------
 namespace {
 
-constexpr int kCbTileVecs = 16;     // vectors per CTA tile (16: 5-9 % faster than 8 on the single-slice multiplies)
 constexpr int kCbMaxThreads = 256;
 
 __device__ __forceinline__ cplx cfma(cplx a, cplx b, cplx c) {    // a*b + c
@@ -336,7 +338,7 @@ struct PlaqMat {
 struct CbShape {
     int half, quarter;      // L/2, N/4
     int pairs;              // msf * nplaq
-    int G;                  // vector groups of the hopping passes (divides kCbTileVecs)
+    int G;                  // vector groups of the hopping passes (divides the tile's vector count)
     int Gp;                 // vector groups of the potential stage
 };
 

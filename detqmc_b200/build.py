@@ -10,7 +10,7 @@ OUT = os.path.join(HERE, "libdqmc_b200.so")
 SOURCES = ["context.cu", "cb_kernels.cu", "gemm_kernels.cu", "qr_kernels.cu", "update_kernels.cu",
            "misc_kernels.cu", "hubbard_kernels.cu", "rng_stream.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-diag-suppress", "128,550"]
+              "-Xcompiler", "-fPIC", "-diag-suppress", "128,550"] + os.environ.get("DQMC_NVCC_EXTRA", "").split()
 
 
 def needs_build():

@@ -1338,7 +1338,7 @@ int dqmc_create(const dqmc_params* params, int n_replicas, int device, dqmc_ctx*
         // bound kernels of one replica overlap with the throughput-bound kernels of the others
         int want = std::min(ctx->R, 32);                  // measured at 64 replicas: 32 lanes 120.6 ms, 64 lanes 121.8 ms per step
         gemm_set_matrices_in_flight(ctx->R * ctx->ngc);
-        pdl_set_enabled(ctx->R * ctx->ngc <= 6);          // measured: gains at 1 / 2 / 4 replicas (50.1 -> 48.2, 50.7 -> 49.6, 53.9 -> 51.8 ms), losses at 8 (56.0 -> 56.6) and 16 (60.4 -> 64.6)
+        pdl_set_enabled(true);                            // DQMC_PDL=0 switches the launch attribute off
         if (const char* e = std::getenv("DQMC_LANES")) want = std::atoi(e);
         want = std::max(1, std::min(want, std::min(DQMC_MAX_LANES, ctx->R)));
         ctx->nlanes = want;

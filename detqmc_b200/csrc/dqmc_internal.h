@@ -15,18 +15,23 @@
 
 namespace dqmc {
 // ------------------------------------------------------------------------------------------------
-// Programmatic dependent launch.  A sweep is a chain of ~5000 small dependent kernels per replica; with few replicas
-// per GPU the hand-over from one kernel to the next (2-3 us inside a CUDA graph) is a sizeable part of the step.
-// Every kernel of the library starts with pdl_enter(): wait for the predecessor's results, then allow the successor
-// to be scheduled, so that the successor's launch and prologue overlap this kernel's execution.  The attribute is set
-// only when pdl_enabled() (few matrices in flight: the pre-launched CTAs hold SM resources that a large batch would
-// rather use for other lanes); without it griddepcontrol.* are no-ops.
+// Programmatic dependent launch.  A sweep is a chain of ~3500 small dependent kernels per replica; the hand-over from
+// one kernel to the next (2-3 us inside a CUDA graph) is a sizeable part of the step.  Every launch carries the
+// programmatic-stream-serialization attribute and every kernel starts with pdl_enter() = `griddepcontrol.wait`: the
+// successor's launch is processed while the predecessor still runs and its CTAs start the moment the predecessor's
+// last CTA has exited, waiting in hardware only for the predecessor's memory to be visible.  The predecessor does NOT
+// trigger its dependents early (`griddepcontrol.launch_dependents` at kernel start, the first version, -DDQMC_PDL_EARLY):
+// early CTAs sit on shared memory and registers for the whole run time of a long predecessor (a QR panel, a window
+// round), which cost more than the overlap gained from 8 replicas per GPU on (measured, same box: 8 replicas 55.4 ->
+// 52.7 ms per step, 16: 63.5 -> 57.4, 64: 119.9 -> 117.8 against no attribute; 1 replica 47.5 vs 47.8).
 // ------------------------------------------------------------------------------------------------
 bool pdl_enabled();
 void pdl_set_enabled(bool on);
 __device__ __forceinline__ void pdl_enter() {
     asm volatile("griddepcontrol.wait;" ::: "memory");
+#ifdef DQMC_PDL_EARLY
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
 }
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {

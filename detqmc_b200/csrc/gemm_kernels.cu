@@ -648,7 +648,7 @@ static int g_matrices_in_flight = 1 << 30;
 void gemm_set_matrices_in_flight(int n) { g_matrices_in_flight = n > 0 ? n : 1 << 30; }
 int gemm_matrices_in_flight() { return g_matrices_in_flight; }
 
-// programmatic dependent launch (dqmc_internal.h): on for small batches unless DQMC_PDL=0 / 1 says otherwise
+// programmatic dependent launch (dqmc_internal.h): on unless DQMC_PDL=0 says otherwise
 static bool g_pdl = false;
 bool pdl_enabled() { return g_pdl; }
 void pdl_set_enabled(bool on) {

@@ -691,7 +691,7 @@ cudaError_t gemm_launch(const GemmArgs& g, cudaStream_t st) {
     if (deep && g.M <= 32 && g.N <= 32) return launch_cfg<2, 2, 2, 2, 32>(g, st);
     // DQMC_SKINNY_CFG: shape of the M <= 32 panel products -- 0: 32 x 32 tiles (8 warps), 1: 32 x 16 (8 warps), 2: 32 x 8 (4 warps)
     static const int skinnyEnv = std::getenv("DQMC_SKINNY_CFG") ? std::atoi(std::getenv("DQMC_SKINNY_CFG")) : -1;
-    const int skinny = skinnyEnv >= 0 ? skinnyEnv : (g_matrices_in_flight <= 16 ? 1 : 0);   // measured: 1 replica 49.7 -> 48.3 ms, 64: 122.0 -> 125.8
+    const int skinny = skinnyEnv >= 0 ? skinnyEnv : (g_matrices_in_flight <= 32 ? 1 : 0);   // measured: 1 replica 49.7 -> 48.3 ms, 32: 70.2 -> 69.4, 64: 117.9 -> 121.0
     if (g.M <= 32 && g.N > 32 && skinny == 1) { if (deep) return launch_cfg<4, 2, 1, 1, 32>(g, st); return launch_cfg<4, 2, 1, 1>(g, st); }
     if (g.M <= 32 && g.N > 32 && skinny == 2) { if (deep) return launch_cfg<4, 1, 1, 1, 32>(g, st); return launch_cfg<4, 1, 1, 1>(g, st); }
     if (deep && g.M <= 32) return launch_cfg<2, 4, 2, 1, 32>(g, st);

@@ -42,7 +42,7 @@ def build(force=False, verbose=False):
             sys.stderr.write(out.decode())
         if p.returncode != 0:
             raise RuntimeError("nvcc failed on " + src)
-    cmd = ["nvcc", "-shared", "-Wno-deprecated-gpu-targets", "-o", OUT] + objs + ["-ldl"]
+    cmd = ["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT] + objs + ["-ldl"]
     subprocess.check_call(cmd)
     return OUT
 

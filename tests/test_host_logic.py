@@ -38,6 +38,23 @@ def test_library_exports_every_declared_symbol():
     assert lib.dqmc_profile_name(0).decode() == "cb_mult"
 
 
+def test_library_is_built_for_sm_100a_with_the_hardware_paths_the_design_claims():
+    """The shipped library is sm_100a machine code and contains what DESIGN.md says the hot kernels use: FP64
+    tensor-core MMAs (DMMA), cp.async (LDGSTS), bulk copies through the copy engine with mbarrier completion (UBLKCP,
+    SYNCS) and thread-block-cluster barriers (UCGABAR).  Skipped where the CUDA binary tools are not installed."""
+    import shutil
+    import subprocess
+    from detqmc_b200.lib import LIB_PATH
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not available")
+    elf = subprocess.run(["cuobjdump", "-lelf", LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"\.(sm_[0-9a-z]+)\.cubin", elf))
+    assert archs == {"sm_100a"}, archs
+    sass = subprocess.run(["cuobjdump", "-sass", LIB_PATH], capture_output=True, text=True).stdout
+    for mnemonic in ("DMMA.8x8x4", "LDGSTS", "UBLKCP", "SYNCS", "UCGABAR"):
+        assert mnemonic in sass, mnemonic
+
+
 def test_create_without_gpu_fails_loudly():
     """No CPU fallback: without a CUDA device dqmc_create must return an error, not a context that works."""
     import torch

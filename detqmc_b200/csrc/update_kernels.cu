@@ -82,35 +82,45 @@ __device__ __forceinline__ cplx small_det_inv(const cplx* Min, cplx* inv) {
         return det;
     }
     cplx a[n * n], b[n * n];
+#pragma unroll
     for (int i = 0; i < n * n; ++i) { a[i] = Min[i]; b[i] = make_double2((i % (n + 1)) == 0 ? 1.0 : 0.0, 0.0); }
     cplx det = make_double2(1, 0);
+#pragma unroll
     for (int col = 0; col < n; ++col) {
-        int piv = col;
-        double best = a[col * n + col].x * a[col * n + col].x + a[col * n + col].y * a[col * n + col].y;
+        // partial pivoting with compile-time indices only (a run-time pivot row would push a and b into local memory):
+        // every later row that beats the current candidate is swapped into place.  The row that ends up at `col` is the
+        // first one of maximal modulus, as with a single swap; the rows below end up in a different order, which the
+        // elimination does not see, and the sign of det follows the parity of the complete permutation either way.
+#pragma unroll
         for (int r = col + 1; r < n; ++r) {
+            const double best = a[col * n + col].x * a[col * n + col].x + a[col * n + col].y * a[col * n + col].y;
             const double v = a[r * n + col].x * a[r * n + col].x + a[r * n + col].y * a[r * n + col].y;
-            if (v > best) { best = v; piv = r; }
-        }
-        if (piv != col) {
-            for (int c = 0; c < n; ++c) {
-                cplx t = a[col * n + c]; a[col * n + c] = a[piv * n + c]; a[piv * n + c] = t;
-                t = b[col * n + c]; b[col * n + c] = b[piv * n + c]; b[piv * n + c] = t;
+            if (v > best) {
+#pragma unroll
+                for (int c = 0; c < n; ++c) {
+                    cplx t = a[col * n + c]; a[col * n + c] = a[r * n + c]; a[r * n + c] = t;
+                    t = b[col * n + c]; b[col * n + c] = b[r * n + c]; b[r * n + c] = t;
+                }
+                det = make_double2(-det.x, -det.y);
             }
-            det = make_double2(-det.x, -det.y);
         }
         const cplx p = a[col * n + col];
         det = cmul(det, p);
         const cplx ip = cdiv(make_double2(1, 0), p);
+#pragma unroll
         for (int c = 0; c < n; ++c) { a[col * n + c] = cmul(a[col * n + c], ip); b[col * n + c] = cmul(b[col * n + c], ip); }
+#pragma unroll
         for (int r = 0; r < n; ++r) {
             if (r == col) continue;
             const cplx f = a[r * n + col];
+#pragma unroll
             for (int c = 0; c < n; ++c) {
                 a[r * n + c] = csub(a[r * n + c], cmul(f, a[col * n + c]));
                 b[r * n + c] = csub(b[r * n + c], cmul(f, b[col * n + c]));
             }
         }
     }
+#pragma unroll
     for (int i = 0; i < n * n; ++i) inv[i] = b[i];
     return det;
 }
@@ -972,8 +982,9 @@ __global__ void __launch_bounds__(32 * (3 + BW)) update_window_kernel(UpdateMode
             const bool have = in && (mycur + OPDIM + 1 <= nload);
             bool acc = false, draw = false;
             int ent = 0;
-            cplx Dl[MSF * MSF], Minv[MSF * MSF];
+            cplx Minv[MSF * MSF];
             if (have) {
+                cplx Dl[MSF * MSF];                             // Delta of this proposal: re-read from the table on acceptance
                 ent = mypos * (mypos + 1) / 2 + (mycur - OPDIM * mypos);
                 const double* T = ptab + ent;
                 // bosonic part: the neighbour term of deltaSPhi uses the CURRENT fields of the slice
@@ -1040,7 +1051,7 @@ __global__ void __launch_bounds__(32 * (3 + BW)) update_window_kernel(UpdateMode
                 mbEnt[j] = ent;
 #pragma unroll
                 for (int i = 0; i < MSF * MSF; ++i) {
-                    smallD[j * MSF * MSF + i] = Dl[i];
+                    smallD[j * MSF * MSF + i] = make_double2(T[(PT::DELTA + 2 * i) * NE], T[(PT::DELTA + 2 * i + 1) * NE]);
                     smallM[j * MSF * MSF + i] = Minv[i];
                 }
                 __threadfence_block();
@@ -1050,6 +1061,7 @@ __global__ void __launch_bounds__(32 * (3 + BW)) update_window_kernel(UpdateMode
             __syncwarp();
             const bool last = (j + 1 == delayNow) || (apos + 1 == w);
             if (!last) {
+                cplx Dl[MSF * MSF];
 #pragma unroll
                 for (int i = 0; i < MSF * MSF; ++i) {
                     Dl[i] = smallD[j * MSF * MSF + i];
